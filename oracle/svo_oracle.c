@@ -1,0 +1,534 @@
+/*
+ * TEST INFRASTRUCTURE ONLY -- the parity oracle, never the product. See
+ * svo_oracle.h for what is restated and how it is pinned to the reference's
+ * own object code (oracle/_ref) and to tests/golden/.
+ *
+ * Written from SURVEY.md Appendix A-C against the reference source; every
+ * floating-point expression keeps the reference's operand order and rounding
+ * points (two roundings for a*b - c, IEEE divide, the (a<b)?b:a forms of
+ * std::max/std::min). Compile with -ffp-contract=off.
+ */
+#include "svo_oracle.h"
+
+#include <math.h>
+#include <pthread.h>
+#include <stdatomic.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define SVO_MAX_SCALE 23 /* VoxelOctree.hpp:38 */
+
+static inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+/* std::max / std::min as libstdc++ defines them (operand order matters for -0.0f / NaN) */
+static inline float maxStd(float a, float b) { return (a < b) ? b : a; }
+static inline float minStd(float a, float b) { return (b < a) ? b : a; }
+static inline uint32_t popc8(uint32_t v) { return (uint32_t)__builtin_popcount(v & 0xFFu); } /* == BitCount[], VoxelOctree.cpp:36-53 */
+
+/* Util.hpp:47-58 */
+float svo_oracle_inv_sqrt(float x) {
+    float halfX = x*0.5f;
+    float y = u2f(0x5f3759dfu - (f2u(x) >> 1));
+    return y*(1.5f - halfX*y*y);
+}
+
+/* VoxelOctree.cpp:207-346 */
+int svo_oracle_raymarch(const uint32_t *octree, const float *o, const float *d, float rayScale,
+        uint32_t *normal, float *t, uint64_t *voxel, svo_oracle_counters *c) {
+    uint64_t stackParent[SVO_MAX_SCALE + 1];
+    float stackMaxT[SVO_MAX_SCALE + 1];
+    float dT[3], bT[3], pos[3];
+    uint32_t octantMask = 7;
+
+    for (int a = 0; a < 3; ++a) {
+        float da = d[a];
+        if (fabsf(da) < 1e-4f) da = 1e-4f;          /* :217-219 (sign is dropped) */
+        dT[a] = 1.0f/-fabsf(da);                    /* :221-223 */
+        bT[a] = dT[a]*o[a];                         /* :225-227 */
+        if (da > 0.0f) {                            /* :229-232 */
+            octantMask ^= 1u << a;
+            bT[a] = 3.0f*dT[a] - bT[a];
+        }
+    }
+
+    float minT = maxStd(2.0f*dT[0] - bT[0], maxStd(2.0f*dT[1] - bT[1], 2.0f*dT[2] - bT[2]));
+    float maxT = minStd(dT[0] - bT[0], minStd(dT[1] - bT[1], dT[2] - bT[2]));
+    minT = maxStd(minT, 0.0f);
+
+    uint32_t current = 0;
+    uint64_t parent = 0;
+    uint32_t idx = 0;
+    int scale = SVO_MAX_SCALE - 1;
+    float scaleExp2 = 0.5f;
+    for (int a = 0; a < 3; ++a) {                   /* :248-250 */
+        pos[a] = 1.0f;
+        if (1.5f*dT[a] - bT[a] > minT) { idx ^= 1u << a; pos[a] = 1.5f; }
+    }
+
+    uint64_t iterations = 0, descF = 0, farF = 0, leafF = 0, pushes = 0, pops = 0;
+    int result = SVO_ORACLE_MISS;
+    float tOut = 0.0f;
+
+    while (scale < SVO_MAX_SCALE) {
+        ++iterations;
+        if (current == 0) { current = octree[parent]; ++descF; }
+
+        float cornerT[3];
+        for (int a = 0; a < 3; ++a) cornerT[a] = pos[a]*dT[a] - bT[a];
+        float maxTC = minStd(cornerT[0], minStd(cornerT[1], cornerT[2]));
+
+        uint32_t childShift = idx ^ octantMask;
+        uint32_t childMasks = current << childShift;
+
+        if ((childMasks & 0x8000u) && minT <= maxT) {
+            if (maxTC*rayScale >= scaleExp2) {      /* LOD exit :265-268 */
+                result = SVO_ORACLE_LOD;
+                tOut = maxTC;
+                if (voxel) *voxel = parent | ((uint64_t)childShift << 60);
+                break;
+            }
+            float maxTV = minStd(maxT, maxTC);
+            float half = scaleExp2*0.5f;
+            float centerT[3];
+            for (int a = 0; a < 3; ++a) centerT[a] = half*dT[a] + cornerT[a];
+
+            if (minT <= maxTV) {
+                uint64_t childOffset = current >> 18;
+                if (current & 0x20000u) {           /* far word :278-279 */
+                    childOffset = (childOffset << 32) | (uint64_t)octree[parent + 1];
+                    ++farF;
+                }
+                if (!(childMasks & 0x80u)) {        /* leaf :281-285 */
+                    uint64_t leaf = childOffset + parent + popc8(((childMasks >> (8 + childShift)) << childShift) & 127u);
+                    *normal = octree[leaf];
+                    ++leafF;
+                    if (voxel) *voxel = leaf;
+                    result = SVO_ORACLE_LEAF;
+                    tOut = minT;
+                    break;
+                }
+                stackParent[scale] = parent;        /* push :287-306 */
+                stackMaxT[scale] = maxT;
+                ++pushes;
+                uint32_t siblings = popc8(childMasks & 127u);
+                parent += childOffset + siblings;
+                if (current & 0x10000u) parent += siblings;
+                idx = 0;
+                --scale;
+                scaleExp2 = half;
+                for (int a = 0; a < 3; ++a)
+                    if (centerT[a] > minT) { idx ^= 1u << a; pos[a] += scaleExp2; }
+                maxT = maxTV;
+                current = 0;
+                continue;
+            }
+        }
+
+        uint32_t stepMask = 0;                      /* advance :310-316 */
+        for (int a = 0; a < 3; ++a)
+            if (cornerT[a] <= maxTC) { stepMask ^= 1u << a; pos[a] -= scaleExp2; }
+        minT = maxTC;
+        idx ^= stepMask;
+
+        if ((idx & stepMask) != 0) {                /* pop :318-338 */
+            ++pops;
+            int32_t differingBits = 0;
+            for (int a = 0; a < 3; ++a)
+                if (stepMask & (1u << a))
+                    differingBits |= (int32_t)(f2u(pos[a]) ^ f2u(pos[a] + scaleExp2));
+            scale = (int)(f2u((float)differingBits) >> 23) - 127;
+            scaleExp2 = u2f((uint32_t)(scale - SVO_MAX_SCALE + 127) << 23);
+            /* scale == 23 (ray left the root) reads slot 23, which the
+             * reference never wrote either; give it a defined value */
+            parent = (scale < SVO_MAX_SCALE) ? stackParent[scale] : 0;
+            maxT = (scale < SVO_MAX_SCALE) ? stackMaxT[scale] : 0.0f;
+            idx = 0;
+            for (int a = 0; a < 3; ++a) {
+                uint32_t sh = f2u(pos[a]) >> scale;
+                pos[a] = u2f(sh << scale);
+                idx |= (sh & 1u) << a;
+            }
+            current = 0;
+        }
+    }
+
+    if (c) {
+        c->rays += 1;
+        c->iterations += iterations;
+        c->desc_fetches += descF;
+        c->far_fetches += farF;
+        c->leaf_fetches += leafF;
+        c->pushes += pushes;
+        c->pops += pops;
+        if (iterations > c->max_iterations) c->max_iterations = iterations;
+        if (result != SVO_ORACLE_MISS) c->hits += 1;
+        if (result == SVO_ORACLE_LOD) c->lod_exits += 1;
+    }
+    if (result != SVO_ORACLE_MISS) *t = tOut;       /* :266 / :344 */
+    return result;
+}
+
+static void mergeCounters(svo_oracle_counters *dst, const svo_oracle_counters *src) {
+    dst->rays += src->rays;
+    dst->iterations += src->iterations;
+    dst->desc_fetches += src->desc_fetches;
+    dst->far_fetches += src->far_fetches;
+    dst->leaf_fetches += src->leaf_fetches;
+    dst->pushes += src->pushes;
+    dst->pops += src->pops;
+    if (src->max_iterations > dst->max_iterations) dst->max_iterations = src->max_iterations;
+    dst->hits += src->hits;
+    dst->lod_exits += src->lod_exits;
+}
+
+/* ---- batch --------------------------------------------------------------- */
+
+typedef struct {
+    const uint32_t *octree;
+    uint64_t begin, end;
+    const float *o, *d;
+    float rayScale;
+    uint8_t *hit; float *t; uint32_t *normal; uint64_t *voxel;
+    svo_oracle_counters counters;
+} BatchJob;
+
+static void *batchWorker(void *arg) {
+    BatchJob *j = (BatchJob *)arg;
+    for (uint64_t i = j->begin; i < j->end; ++i) {
+        uint32_t n = j->normal ? j->normal[i] : 0;
+        float t = j->t ? j->t[i] : 0.0f;
+        uint64_t v = j->voxel ? j->voxel[i] : 0;
+        int r = svo_oracle_raymarch(j->octree, j->o + 3*i, j->d + 3*i, j->rayScale, &n, &t, &v, &j->counters);
+        if (j->hit) j->hit[i] = (uint8_t)r;
+        if (j->t) j->t[i] = t;
+        if (j->normal) j->normal[i] = n;
+        if (j->voxel) j->voxel[i] = v;
+    }
+    return NULL;
+}
+
+void svo_oracle_raymarch_batch(const uint32_t *octree, uint64_t n, const float *o, const float *d,
+        float rayScale, uint8_t *hit, float *t, uint32_t *normal, uint64_t *voxel,
+        svo_oracle_counters *c, int threads) {
+    if (threads < 1) threads = 1;
+    if ((uint64_t)threads > n) threads = n ? (int)n : 1;
+    BatchJob *jobs = (BatchJob *)calloc((size_t)threads, sizeof(BatchJob));
+    pthread_t *tids = (pthread_t *)calloc((size_t)threads, sizeof(pthread_t));
+    for (int k = 0; k < threads; ++k) {
+        BatchJob *j = &jobs[k];
+        j->octree = octree;
+        j->begin = n*(uint64_t)k/(uint64_t)threads;
+        j->end = n*(uint64_t)(k + 1)/(uint64_t)threads;
+        j->o = o; j->d = d; j->rayScale = rayScale;
+        j->hit = hit; j->t = t; j->normal = normal; j->voxel = voxel;
+        if (k > 0) pthread_create(&tids[k], NULL, batchWorker, j);
+    }
+    batchWorker(&jobs[0]);
+    for (int k = 1; k < threads; ++k) pthread_join(tids[k], NULL);
+    if (c) for (int k = 0; k < threads; ++k) mergeCounters(c, &jobs[k].counters);
+    free(jobs);
+    free(tids);
+}
+
+/* ---- camera / per-frame constants ---------------------------------------- */
+
+/* Mat4.cpp:67-78, row-major a[i*4 + t] */
+static void mat4Mul(const float *a, const float *b, float *out) {
+    float r[16];
+    for (int i = 0; i < 4; ++i)
+        for (int t = 0; t < 4; ++t)
+            r[i*4 + t] = a[i*4 + 0]*b[0*4 + t] + a[i*4 + 1]*b[1*4 + t] + a[i*4 + 2]*b[2*4 + t] + a[i*4 + 3]*b[3*4 + t];
+    memcpy(out, r, sizeof r);
+}
+
+static void mat4Translate(float x, float y, float z, float *m) {
+    static const float id[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    memcpy(m, id, sizeof id);
+    m[3] = x; m[7] = y; m[11] = z;
+}
+
+/* Mat4.cpp:59-65 */
+static void mat4PseudoInvert(const float *m, float *out) {
+    float trans[16], rot[16];
+    mat4Translate(-m[3], -m[7], -m[11], trans);
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j)
+            rot[i*4 + j] = m[j*4 + i];
+    rot[12] = rot[13] = rot[14] = 0.0f;
+    mat4Mul(rot, trans, out);
+}
+
+/* Mat4.cpp:114-125 */
+static void mat4RotXYZ(float rx, float ry, float rz, float *m) {
+    const float pi = (float)3.14159265358979323846;
+    float r[3] = {rx*pi/180.0f, ry*pi/180.0f, rz*pi/180.0f};
+    float c[3] = {cosf(r[0]), cosf(r[1]), cosf(r[2])};
+    float s[3] = {sinf(r[0]), sinf(r[1]), sinf(r[2])};
+    float v[16] = {
+        c[1]*c[2], -c[0]*s[2] + s[0]*s[1]*c[2],  s[0]*s[2] + c[0]*s[1]*c[2], 0.0f,
+        c[1]*s[2],  c[0]*c[2] + s[0]*s[1]*s[2], -s[0]*c[2] + c[0]*s[1]*s[2], 0.0f,
+            -s[1],                   s[0]*c[1],                   c[0]*c[1], 0.0f,
+             0.0f,                        0.0f,                        0.0f, 1.0f};
+    memcpy(m, v, sizeof v);
+}
+
+void svo_oracle_orbit_camera(float pitchDeg, float yawDeg, float radius, float *model16, float *view16) {
+    float a[16], b[16];
+    mat4Translate(0.0f, 0.0f, -radius, view16);
+    mat4RotXYZ(pitchDeg, 0.0f, 0.0f, a);
+    mat4RotXYZ(0.0f, yawDeg, 0.0f, b);
+    mat4Mul(a, b, model16);
+}
+
+/* Main.cpp:149-163 */
+void svo_oracle_frame_constants(const float *model16, const float *view16, const float *center,
+        int width, int height, int strips, svo_oracle_frame *out) {
+    float inv[16], m[16];
+    mat4PseudoInvert(model16, inv);                 /* MatrixStack.cpp:71-73 */
+    mat4Mul(inv, view16, m);
+
+    out->width = width;
+    out->height = height;
+    out->strips = strips;
+    out->tile_size = 8;                             /* Main.cpp:63 */
+    for (int i = 0; i < 3; ++i) {
+        /* tform*Vec3() + center + Vec3(1.0), Mat4.cpp:80-86 */
+        float tp = m[i*4 + 0]*0.0f + m[i*4 + 1]*0.0f + m[i*4 + 2]*0.0f + m[i*4 + 3];
+        out->pos[i] = tp + center[i] + 1.0f;
+    }
+    m[3] = m[7] = m[11] = 0.0f;
+
+    out->a11 = m[0]; out->a12 = m[1];
+    out->a21 = m[4]; out->a22 = m[5];
+    out->a31 = m[8]; out->a32 = m[9];
+    out->scale = 2.0f/width;
+    out->tile_scale = out->tile_size*out->scale;
+    float planeDist = 1.0f/tanf((float)3.14159265358979323846/6.0f);
+    out->zx = planeDist*m[2];
+    out->zy = planeDist*m[6];
+    out->zz = planeDist*m[10];
+    out->coarse_scale = 2.0f*out->tile_size/(planeDist*height);
+    out->aspect = height/(float)width;              /* Main.cpp:62 */
+
+    float l[3];
+    for (int i = 0; i < 3; ++i)
+        l[i] = m[i*4 + 0]*-1.0f + m[i*4 + 1]*1.0f + m[i*4 + 2]*-1.0f + m[i*4 + 3];
+    float inv_len = 1.0f/sqrtf(l[0]*l[0] + l[1]*l[1] + l[2]*l[2]); /* Vec3.hpp:57-61 */
+    for (int i = 0; i < 3; ++i) out->light[i] = l[i]*inv_len;
+    out->beam_bias = 0.03f;                         /* Main.cpp:197 */
+}
+
+/* ---- shading -------------------------------------------------------------- */
+
+/* Util.hpp:86-100 */
+void svo_oracle_decompress_material(uint32_t word, float *n, float *shade) {
+    static const int mod3[] = {0, 1, 2, 0, 1};
+    uint32_t sign = (word & 0x80000000u) >> 31;
+    uint32_t face = (word & 0x60000000u) >> 29;
+    uint32_t u = (word & 0x1FFC0000u) >> 18;
+    uint32_t v = (word & 0x0003FF80u) >> 7;
+    uint32_t c = word & 0x7Fu;
+    float tmp[4] = {0.0f, 0.0f, 0.0f, 0.0f}; /* face == 3 never occurs in valid data; stay in bounds */
+    tmp[face & 3] = sign ? -1.0f : 1.0f;
+    if (face < 3) {
+        tmp[mod3[face + 1]] = u*4.8852e-4f*2.0f - 1.0f;
+        tmp[mod3[face + 2]] = v*4.8852e-4f*2.0f - 1.0f;
+    }
+    float s = svo_oracle_inv_sqrt(tmp[0]*tmp[0] + tmp[1]*tmp[1] + tmp[2]*tmp[2]);
+    n[0] = tmp[0]*s; n[1] = tmp[1]*s; n[2] = tmp[2]*s;
+    *shade = c*1.0f/127.0f;
+}
+
+/* Main.cpp:81-90 with Vec3::dot / Vec3::reflect (Vec3.hpp:49-51,63-71) */
+float svo_oracle_shade(uint32_t material, const float *ray, const float *light) {
+    float n[3], c;
+    svo_oracle_decompress_material(material, n, &c);
+    float proj = (n[0]*ray[0] + n[1]*ray[1] + n[2]*ray[2])*2.0f;
+    float r[3] = {ray[0] - n[0]*proj, ray[1] - n[1]*proj, ray[2] - n[2]*proj};
+    float d = maxStd(light[0]*r[0] + light[1]*r[1] + light[2]*r[2], 0.0f);
+    float specular = d*d;
+    return c*0.9f*fabsf(light[0]*n[0] + light[1]*n[1] + light[2]*n[2]) + specular*0.2f;
+}
+
+/* Main.cpp:128-132: float -> double, double multiply, truncate */
+uint32_t svo_oracle_pack(float v) {
+    uint32_t g = (uint32_t)(minStd(v, 1.0f)*255.0);
+    return g | (g << 8) | (g << 16) | 0xFF000000u;
+}
+
+/* ---- frame ----------------------------------------------------------------- */
+
+typedef struct {
+    const uint32_t *octree;
+    const svo_oracle_frame *f;
+    uint32_t *rgba;
+    float *depth;            /* may be NULL */
+    const uint64_t *depthOffset;
+    atomic_int *next;
+    svo_oracle_counters coarse, fine;
+} FrameJob;
+
+static void rayDir(const svo_oracle_frame *f, float dx, float dy, float *dir) {
+    dir[0] = dx*f->a11 + dy*f->a12 + f->zx;
+    dir[1] = dx*f->a21 + dy*f->a22 + f->zy;
+    dir[2] = dx*f->a31 + dy*f->a32 + f->zz;
+    float s = svo_oracle_inv_sqrt(dir[0]*dir[0] + dir[1]*dir[1] + dir[2]*dir[2]);
+    dir[0] *= s; dir[1] *= s; dir[2] *= s;
+}
+
+/* Main.cpp:92-137, stride == 1 */
+static void renderTile(FrameJob *j, int x0, int y0, int x1, int y1, float minT) {
+    const svo_oracle_frame *f = j->f;
+    float dy = f->aspect - y0*f->scale;
+    for (int y = y0; y < y1; ++y, dy -= f->scale) {
+        float dx = -1.0f + x0*f->scale;
+        for (int x = x0; x < x1; ++x, dx += f->scale) {
+            float dir[3], org[3];
+            rayDir(f, dx, dy, dir);
+            for (int a = 0; a < 3; ++a) org[a] = f->pos[a] + dir[a]*minT;
+            uint32_t material = 0;
+            float t = 0.0f;
+            float v = 0.0f;
+            if (svo_oracle_raymarch(j->octree, org, dir, 0.0f, &material, &t, NULL, &j->fine))
+                v = svo_oracle_shade(material, dir, f->light);
+            j->rgba[x + (size_t)y*(size_t)f->width] = svo_oracle_pack(v);
+        }
+    }
+}
+
+/* Main.cpp:139-202 for the strip [y0, y1) */
+static void renderStrip(FrameJob *j, int strip) {
+    const svo_oracle_frame *f = j->f;
+    const float TreeMiss = 1e10f;
+    int stride = (f->height - 1)/f->strips + 1;     /* Main.cpp:351 */
+    int x0 = 0, x1 = f->width;
+    int y0 = strip*stride;
+    int y1 = (strip + 1)*stride < f->height ? (strip + 1)*stride : f->height;
+    if (y0 >= y1) return;
+    int tile = f->tile_size;
+    int tilesX = (x1 - x0 - 1)/tile + 2;
+    int tilesY = (y1 - y0 - 1)/tile + 2;
+    float *depth = (float *)malloc(sizeof(float)*(size_t)tilesX*(size_t)tilesY);
+
+    memset(j->rgba + (size_t)y0*(size_t)f->width, 0, sizeof(uint32_t)*(size_t)(y1 - y0)*(size_t)f->width);
+
+    float dy = f->aspect - y0*f->scale;
+    for (int y = 0, idx = 0; y < tilesY; ++y, dy -= f->tile_scale) {
+        float dx = -1.0f + x0*f->scale;
+        for (int x = 0; x < tilesX; ++x, dx += f->tile_scale, ++idx) {
+            float dir[3];
+            rayDir(f, dx, dy, dir);
+            uint32_t material = 0;
+            float t = 0.0f;
+            if (svo_oracle_raymarch(j->octree, f->pos, dir, f->coarse_scale, &material, &t, NULL, &j->coarse))
+                depth[idx] = t;
+            else
+                depth[idx] = TreeMiss;
+
+            if (x > 0 && y > 0) {
+                float minT = minStd(minStd(depth[idx], depth[idx - 1]), minStd(depth[idx - tilesX], depth[idx - tilesX - 1]));
+                if (minT != TreeMiss) {
+                    int tx0 = (x - 1)*tile + x0;
+                    int ty0 = (y - 1)*tile + y0;
+                    int tx1 = tx0 + tile < x1 ? tx0 + tile : x1;
+                    int ty1 = ty0 + tile < y1 ? ty0 + tile : y1;
+                    renderTile(j, tx0, ty0, tx1, ty1, maxStd(minT - f->beam_bias, 0.0f));
+                }
+            }
+        }
+    }
+    if (j->depth) memcpy(j->depth + j->depthOffset[strip], depth, sizeof(float)*(size_t)tilesX*(size_t)tilesY);
+    free(depth);
+}
+
+static void *frameWorker(void *arg) {
+    FrameJob *j = (FrameJob *)arg;
+    for (;;) {
+        int s = atomic_fetch_add(j->next, 1);
+        if (s >= j->f->strips) break;
+        renderStrip(j, s);
+    }
+    return NULL;
+}
+
+int svo_oracle_render_frame(const uint32_t *octree, const svo_oracle_frame *f, uint32_t *rgba,
+        float *depth, svo_oracle_counters *coarse, svo_oracle_counters *fine, int threads) {
+    if (!octree || !f || !rgba || f->width < 1 || f->height < 1 || f->strips < 1) return -1;
+    if (threads < 1) threads = 1;
+    if (threads > f->strips) threads = f->strips;
+
+    uint64_t *offsets = (uint64_t *)calloc((size_t)f->strips + 1, sizeof(uint64_t));
+    int stride = (f->height - 1)/f->strips + 1;
+    for (int s = 0; s < f->strips; ++s) {
+        int y0 = s*stride;
+        int y1 = (s + 1)*stride < f->height ? (s + 1)*stride : f->height;
+        int tilesX = (f->width - 1)/f->tile_size + 2;
+        int tilesY = (y1 - y0 - 1)/f->tile_size + 2;
+        uint64_t cells = (uint64_t)(tilesX > 0 ? tilesX : 0)*(uint64_t)(tilesY > 0 ? tilesY : 0);
+        offsets[s + 1] = offsets[s] + cells;
+    }
+
+    atomic_int next;
+    atomic_init(&next, 0);
+    FrameJob *jobs = (FrameJob *)calloc((size_t)threads, sizeof(FrameJob));
+    pthread_t *tids = (pthread_t *)calloc((size_t)threads, sizeof(pthread_t));
+    for (int k = 0; k < threads; ++k) {
+        jobs[k].octree = octree;
+        jobs[k].f = f;
+        jobs[k].rgba = rgba;
+        jobs[k].depth = depth;
+        jobs[k].depthOffset = offsets;
+        jobs[k].next = &next;
+        if (k > 0) pthread_create(&tids[k], NULL, frameWorker, &jobs[k]);
+    }
+    frameWorker(&jobs[0]);
+    for (int k = 1; k < threads; ++k) pthread_join(tids[k], NULL);
+    for (int k = 0; k < threads; ++k) {
+        if (coarse) mergeCounters(coarse, &jobs[k].coarse);
+        if (fine) mergeCounters(fine, &jobs[k].fine);
+    }
+    free(jobs);
+    free(tids);
+    free(offsets);
+    return 0;
+}
+
+/* ---- tree walk (App. A.1) --------------------------------------------------- */
+
+static int walkNode(const uint32_t *oct, uint64_t words, uint64_t p, uint32_t level, svo_oracle_tree_stats *st) {
+    if (p >= words || level >= 24) return -1;
+    uint32_t D = oct[p];
+    uint32_t valid = (D >> 8) & 0xFFu;
+    uint32_t nonLeaf = D & 0xFFu;
+    uint64_t off = D >> 18;
+    st->descriptors += 1;
+    st->per_level[level] += 1;
+    if (level + 1 > st->depth) st->depth = level + 1;
+    if (p > st->max_index) st->max_index = p;
+    if (D & 0x20000u) {
+        if (p + 1 >= words) return -1;
+        off = (off << 32) | oct[p + 1];
+        st->far_words += 1;
+        if (p + 1 > st->max_index) st->max_index = p + 1;
+    }
+    uint32_t count = popc8(valid);
+    if (nonLeaf == 0) {
+        if (count == 0) return 0;
+        uint64_t last = p + off + count - 1;
+        if (last >= words) return -1;
+        st->leaves += count;
+        if (last > st->max_index) st->max_index = last;
+        return 0;
+    }
+    uint64_t strideWords = (D & 0x10000u) ? 2 : 1;
+    if (D & 0x10000u) st->far_blocks += 1;
+    for (uint32_t s = 0; s < count; ++s)
+        if (walkNode(oct, words, p + off + s*strideWords, level + 1, st) != 0) return -1;
+    return 0;
+}
+
+int svo_oracle_tree_walk(const uint32_t *octree, uint64_t words, svo_oracle_tree_stats *out) {
+    memset(out, 0, sizeof *out);
+    if (words == 0) return -1;
+    return walkNode(octree, words, 0, 0, out);
+}
