@@ -1,0 +1,224 @@
+/*
+ * svo_b200.h -- C ABI of the B200-native sparse-voxel-octree ray caster.
+ *
+ * This is the drop-in boundary for the ray-casting path of
+ * tunabrain/sparse-voxel-octrees. The reference has no FFI layer; its de-facto
+ * operator API is the public part of `class VoxelOctree`
+ * (reference src/VoxelOctree.hpp:48-57) plus the per-frame call
+ * `renderBatch(BatchData*)` (reference src/Main.cpp:139, called at :218).
+ * Each entry point below names the reference interface it replaces. The C++
+ * facade with the reference's own signatures is
+ * sparse-voxel-octrees_b200/host/VoxelOctree.hpp; INTEGRATION.md shows the
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every function returns an svo_status
+ *    (0 = ok) unless noted; svo_last_error() gives the thread-local message.
+ *  - handles are opaque; the caller owns every host buffer it passes in.
+ *  - functions may be called from any host thread; one in-flight call per
+ *    tree handle (the reference's raymarch is re-entrant across 16 threads,
+ *    Main.cpp:364-367 -- here concurrency comes from batching instead).
+ *  - there is NO CPU fallback: without a CUDA device every device entry
+ *    point fails with SVO_ERR_NO_DEVICE.
+ *  - node words are the reference's array unchanged.
+ */
+#ifndef SVO_B200_H_
+#define SVO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(_WIN32)
+#  define SVO_API __declspec(dllexport)
+#else
+#  define SVO_API __attribute__((visibility("default")))
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVO_ABI_VERSION 1
+
+typedef enum svo_status {
+    SVO_OK = 0,
+    SVO_ERR_INVALID_ARGUMENT = 1,
+    SVO_ERR_IO = 2,             /* fopen/fread/fwrite failed (the reference ignores these silently, VoxelOctree.cpp:60,95) */
+    SVO_ERR_FORMAT = 3,         /* malformed .oct / LZ4 stream / node array */
+    SVO_ERR_OUT_OF_MEMORY = 4,
+    SVO_ERR_CUDA = 5,
+    SVO_ERR_NO_DEVICE = 6,
+    SVO_ERR_UNSUPPORTED = 7
+} svo_status;
+
+/* Arithmetic flavour (BASELINE.json north_star).
+ * VALIDATION: every float op individually rounded (no FMA contraction, IEEE
+ *   divide, the reference's (a<b)?b:a min/max forms): hit mask and hit voxel
+ *   bit-exact against the reference built with -ffp-contract=off.
+ * FAST: the traversal's a*b+-c expressions are single FMAs, min/max are
+ *   FMNMX; ray generation and shading stay individually rounded so that a
+ *   pixel differs only if the ray reaches a different voxel (>= 99.99 %
+ *   identical pixels). */
+typedef enum svo_flavour { SVO_FLAVOUR_VALIDATION = 0, SVO_FLAVOUR_FAST = 1 } svo_flavour;
+
+/* Ray result codes written to `hit[]`. Non-zero == the reference's `true`. */
+enum { SVO_MISS = 0, SVO_HIT_LEAF = 1, SVO_HIT_LOD = 2 };
+/* Values stored for rays whose outputs the reference leaves untouched. */
+#define SVO_T_MISS 1e10f        /* same sentinel renderBatch uses, Main.cpp:140 */
+#define SVO_VOXEL_NONE UINT64_MAX
+
+typedef struct svo_tree svo_tree;
+
+/* ---- library ------------------------------------------------------------- */
+
+SVO_API int svo_abi_version(void);
+/* Thread-local, never NULL; valid until the next failing call on this thread. */
+SVO_API const char *svo_last_error(void);
+SVO_API int svo_device_count(int *count);
+/* free() for buffers this library returns (svo_oct_read). */
+SVO_API void svo_free(void *p);
+/* Page-locked host memory for frame / ray buffers (full-speed PCIe copies). */
+SVO_API int svo_host_alloc(size_t bytes, void **out);
+SVO_API int svo_host_free(void *p);
+
+/* ---- .oct files, host only (no GPU needed) -------------------------------- *
+ * Replaces VoxelOctree::VoxelOctree(const char*) (VoxelOctree.cpp:57-90) and
+ * VoxelOctree::save (VoxelOctree.cpp:92-123). Same bytes on disk: float32
+ * center[3], uint64 wordCount, then per 64 MiB slice uint64 compSize + one
+ * LZ4 block of a single streaming context. Differences:
+ * errors are reported, and slice sizes are 64-bit (the reference truncates to
+ * int at VoxelOctree.cpp:79, App. E.1). */
+SVO_API int svo_oct_read(const char *path, uint32_t **words, uint64_t *n_words, float center[3]);
+/* compress != 0: greedy LZ4 matches (any reference build reads the result);
+ * compress == 0: literal-only blocks (fastest, largest). */
+SVO_API int svo_oct_write(const char *path, const uint32_t *words, uint64_t n_words, const float center[3], int compress);
+
+/* ---- trees ----------------------------------------------------------------- */
+
+typedef struct svo_tree_info {
+    uint64_t n_words;
+    float center[3];            /* VoxelOctree::center(), VoxelOctree.hpp:55 */
+    uint32_t depth;             /* descriptor levels; voxel grid side = 1 << depth */
+    int32_t device;
+    uint64_t device_bytes;
+} svo_tree_info;
+
+/* Adopts a node array (e.g. the one the reference's builder produced,
+ * VoxelOctree.cpp:125-137) and uploads it unchanged to `device`'s HBM.
+ * The words are copied; the caller keeps ownership of `words`. */
+SVO_API int svo_tree_create_from_words(const uint32_t *words, uint64_t n_words, const float center[3],
+                                       int device, svo_tree **out);
+/* VoxelOctree(const char *path), VoxelOctree.cpp:57-90. */
+SVO_API int svo_tree_load_oct(const char *path, int device, svo_tree **out);
+/* VoxelOctree::save, VoxelOctree.cpp:92-123 (words read back from HBM). */
+SVO_API int svo_tree_save_oct(const svo_tree *tree, const char *path, int compress);
+SVO_API int svo_tree_get_info(const svo_tree *tree, svo_tree_info *out);
+/* Copies the node array back to the host (n_words from svo_tree_get_info). */
+SVO_API int svo_tree_download_words(const svo_tree *tree, uint32_t *words_out, uint64_t n_words);
+SVO_API int svo_tree_destroy(svo_tree *tree);
+
+/* ---- traversal: VoxelOctree::raymarch (VoxelOctree.cpp:207-346), batched ---- *
+ * Ray i: origin o[3i..3i+2], direction d[3i..3i+2] (need not be unit; the
+ * octree occupies [1,2]^3), common rayScale. Outputs (any may be NULL):
+ *   hit[i]    SVO_MISS / SVO_HIT_LEAF / SVO_HIT_LOD
+ *   t[i]      entry t of the leaf (:344) or exit t of the LOD cube (:266); SVO_T_MISS on a miss
+ *   normal[i] leaf material word (:282); 0 on a miss or LOD exit
+ *   voxel[i]  leaf word index (:282) | for LOD exits parent index + (childShift << 60); SVO_VOXEL_NONE on a miss
+ * Host-buffer variant: copies in, runs, copies out, synchronises. */
+SVO_API int svo_raymarch_batch(svo_tree *tree, uint64_t n, const float *o, const float *d, float ray_scale,
+                               int flavour, uint8_t *hit, float *t, uint32_t *normal, uint64_t *voxel);
+/* Device-buffer variant: pointers are device pointers on the tree's device;
+ * asynchronous on `stream` (a cudaStream_t, NULL = default stream). */
+SVO_API int svo_raymarch_batch_device(svo_tree *tree, uint64_t n, const float *d_o, const float *d_d,
+                                      float ray_scale, int flavour, uint8_t *d_hit, float *d_t,
+                                      uint32_t *d_normal, uint64_t *d_voxel, void *stream);
+/* The reference's single-ray signature mapped to a batch of one; outputs are
+ * left untouched exactly where the reference leaves them untouched. Returns
+ * the status; *hit_out receives the reference's bool. Not a performance path. */
+SVO_API int svo_raymarch(svo_tree *tree, const float o[3], const float d[3], float ray_scale,
+                         uint32_t *normal, float *t, int *hit_out);
+
+/* ---- camera: what renderBatch reads from the matrix stacks ------------------ */
+
+typedef struct svo_camera {
+    float model[16];            /* MODEL_STACK top, row-major a11..a44 (Mat4.hpp:29-38) */
+    float view[16];             /* VIEW_STACK top */
+} svo_camera;
+
+/* Main.cpp:212-213,244-245: MODEL = rotXYZ(pitch,0,0)*rotXYZ(0,yaw,0), VIEW = translate(0,0,-radius). */
+SVO_API void svo_orbit_camera(float pitch_deg, float yaw_deg, float radius, svo_camera *out);
+
+/* The scalars renderBatch derives before its loops (Main.cpp:149-163). */
+typedef struct svo_frame_constants {
+    int32_t width, height, strips, tile_size;
+    float pos[3];
+    float a11, a12, a21, a22, a31, a32;
+    float zx, zy, zz;
+    float scale, tile_scale, coarse_scale, aspect;
+    float light[3];
+    float beam_bias;
+} svo_frame_constants;
+
+SVO_API int svo_frame_constants_from_camera(const svo_camera *cam, const float center[3], int width, int height,
+                                            int strips, svo_frame_constants *out);
+
+/* ---- frames: renderBatch over all strips (Main.cpp:139-202, 351-362) -------- */
+
+typedef struct svo_frame_desc {
+    int32_t width, height;
+    int32_t strips;             /* the reference's NumThreads (Main.cpp:57): the image depends on it */
+    int32_t flavour;            /* svo_flavour */
+    /* Multi-GPU tile interleave: this call renders only the 8x8 tiles whose
+     * linear index % tile_world == tile_rank and touches no other pixel.
+     * Single GPU: tile_rank = 0, tile_world = 1. */
+    int32_t tile_rank, tile_world;
+    int32_t reserved[2];
+} svo_frame_desc;
+
+typedef struct svo_frame_stats {
+    uint64_t coarse_rays;       /* raymarch calls of the beam pass (Main.cpp:181) by this rank */
+    uint64_t fine_rays;         /* raymarch calls of renderTile (Main.cpp:118) by this rank */
+    uint64_t tiles_rendered;
+    uint64_t tiles_total;       /* tiles owned by this rank */
+    uint32_t kernel_launches;   /* kernels this call put on the stream */
+    uint32_t reserved;
+} svo_frame_stats;
+
+/* Host-buffer variant: rgba (width*height uint32, the reference's backBuffer
+ * layout 0xFF000000|b<<16|g<<8|r, Main.cpp:128-134; pitch = width*4) and the
+ * optional coarse depth buffer (per strip tilesX*tilesY floats, strip after
+ * strip; miss = 1e10f) are HOST pointers; the call uploads the per-frame
+ * constants, renders, copies the frame back and synchronises. Pass memory from
+ * svo_host_alloc for full-speed copies. With tile_world > 1 pixels of tiles
+ * owned by other ranks are returned as they were in the internal buffer
+ * (zero on a fresh handle). */
+SVO_API int svo_render_frame(svo_tree *tree, const svo_camera *cam, const svo_frame_desc *desc,
+                             uint32_t *rgba, float *depth, svo_frame_stats *stats);
+/* Device-buffer variant: d_rgba may be any pointer the tree's device can
+ * write -- local HBM or a peer GPU's framebuffer mapped with svo_ipc_open, in
+ * which case finished tiles travel over NVLink as the kernel stores them.
+ * d_depth may be NULL. Asynchronous on `stream`; `stats` (optional, host) is
+ * filled only when `sync_stats` != 0, which synchronises the stream. */
+SVO_API int svo_render_frame_device(svo_tree *tree, const svo_camera *cam, const svo_frame_desc *desc,
+                                    uint32_t *d_rgba, float *d_depth, void *stream,
+                                    svo_frame_stats *stats, int sync_stats);
+
+/* ---- device memory + peer mapping (multi-GPU gather over NVLink) ----------- */
+
+SVO_API int svo_device_alloc(int device, size_t bytes, void **out);
+SVO_API int svo_device_free(int device, void *p);
+SVO_API int svo_device_memset(int device, void *p, int value, size_t bytes);
+SVO_API int svo_device_to_host(int device, void *host_dst, const void *device_src, size_t bytes);
+SVO_API int svo_host_to_device(int device, void *device_dst, const void *host_src, size_t bytes);
+SVO_API int svo_device_synchronize(int device);
+#define SVO_IPC_HANDLE_BYTES 64
+/* Export a device allocation (made with svo_device_alloc) so that another
+ * process on the same node can map it; handle is SVO_IPC_HANDLE_BYTES bytes. */
+SVO_API int svo_ipc_export(int device, void *p, uint8_t handle[SVO_IPC_HANDLE_BYTES]);
+SVO_API int svo_ipc_open(int device, const uint8_t handle[SVO_IPC_HANDLE_BYTES], void **out);
+SVO_API int svo_ipc_close(int device, void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVO_B200_H_ */

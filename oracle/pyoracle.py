@@ -216,22 +216,20 @@ class Ref:
 
 
 def strip_layout(W, H, strips, tile=8):
-    """Main.cpp:351-362: list of (y0, y1, tilesX, tilesY) per strip."""
+    """Main.cpp:351-362: (y0, y1, tilesX, tilesY) for every strip that owns at least one row."""
     stride = (H - 1) // strips + 1
     out = []
     for i in range(strips):
         y0 = i * stride
+        if y0 >= H:
+            break
         y1 = min((i + 1) * stride, H)
-        tx = (W - 1) // tile + 2
-        # C integer division truncates toward zero
-        num = y1 - y0 - 1
-        ty = (abs(num) // tile) * (1 if num >= 0 else -1) + 2
-        out.append((y0, y1, tx, ty))
+        out.append((y0, y1, (W - 1) // tile + 2, (y1 - y0 - 1) // tile + 2))
     return out
 
 
 def coarse_cells(W, H, strips, tile=8):
-    return sum(max(tx, 0) * max(ty, 0) for (_, _, tx, ty) in strip_layout(W, H, strips, tile))
+    return sum(tx * ty for (_, _, tx, ty) in strip_layout(W, H, strips, tile))
 
 
 # --------------------------------------------------------------------------------------

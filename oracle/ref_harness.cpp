@@ -299,7 +299,7 @@ int svoref_render_frames(void *h, int W, int H, int strips, int numFrames, const
         td[i].tilesY = (td[i].y1 - td[i].y0 - 1)/TileSize + 2;
         /* strips past the bottom edge (y0 >= H) have negative heights in the
          * reference too; give them an empty but valid buffer */
-        int cells = std::max(td[i].tilesX, 0)*std::max(td[i].tilesY, 0);
+        int cells = td[i].y0 < td[i].y1 ? td[i].tilesX*td[i].tilesY : 0;
         depthBuffers[i].reset(new float[std::max(cells, 1)]);
         td[i].depthBuffer = depthBuffers[i].get();
     }
@@ -335,9 +335,9 @@ int svoref_render_frames(void *h, int W, int H, int strips, int numFrames, const
     if (depth) {
         size_t off = 0;
         for (int i = 0; i < strips; i++) {
-            int cells = std::max(td[i].tilesX, 0)*std::max(td[i].tilesY, 0);
-            if (td[i].y0 < td[i].y1)
-                std::memcpy(depth + off, td[i].depthBuffer, sizeof(float)*cells);
+            if (td[i].y0 >= td[i].y1) continue; /* strip owns no rows: no cells */
+            int cells = td[i].tilesX*td[i].tilesY;
+            std::memcpy(depth + off, td[i].depthBuffer, sizeof(float)*cells);
             off += cells;
         }
     }

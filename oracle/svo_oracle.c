@@ -464,7 +464,7 @@ int svo_oracle_render_frame(const uint32_t *octree, const svo_oracle_frame *f, u
         int y1 = (s + 1)*stride < f->height ? (s + 1)*stride : f->height;
         int tilesX = (f->width - 1)/f->tile_size + 2;
         int tilesY = (y1 - y0 - 1)/f->tile_size + 2;
-        uint64_t cells = (uint64_t)(tilesX > 0 ? tilesX : 0)*(uint64_t)(tilesY > 0 ? tilesY : 0);
+        uint64_t cells = y0 < y1 ? (uint64_t)tilesX*(uint64_t)tilesY : 0; /* strips past the bottom edge own nothing */
         offsets[s + 1] = offsets[s] + cells;
     }
 

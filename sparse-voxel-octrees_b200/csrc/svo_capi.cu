@@ -1,0 +1,631 @@
+// C ABI implementation (include/svo_b200.h): handles, upload, per-configuration
+// frame plans, kernel sequencing, host<->device copies. No CPU fallback: every
+// device entry point needs a CUDA device and says so when there is none.
+#include "../../include/svo_b200.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <new>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "camera.hpp"
+#include "oct_io.hpp"
+#include "svo_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_lastError;
+
+int fail(int status, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_lastError = buf;
+    return status;
+}
+
+int failCuda(cudaError_t e, const char *what) {
+    int status = (e == cudaErrorMemoryAllocation) ? SVO_ERR_OUT_OF_MEMORY
+               : (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? SVO_ERR_NO_DEVICE : SVO_ERR_CUDA;
+    return fail(status, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+}
+
+#define SVO_CUDA(call)                                         \
+    do {                                                       \
+        cudaError_t e_ = (call);                               \
+        if (e_ != cudaSuccess) return failCuda(e_, #call);     \
+    } while (0)
+
+// Makes `device` current for the scope, restoring the caller's device after.
+struct DeviceScope {
+    int previous = -1;
+    cudaError_t error = cudaSuccess;
+    explicit DeviceScope(int device) {
+        error = cudaGetDevice(&previous);
+        if (error == cudaSuccess && previous != device) error = cudaSetDevice(device);
+    }
+    ~DeviceScope() {
+        int now = -1;
+        if (previous >= 0 && cudaGetDevice(&now) == cudaSuccess && now != previous) cudaSetDevice(previous);
+    }
+};
+
+#define SVO_DEVICE(device)                                     \
+    DeviceScope scope_(device);                                \
+    if (scope_.error != cudaSuccess) return failCuda(scope_.error, "cudaSetDevice")
+
+struct FramePlan {
+    svo::FramePlanDev dev{};
+    float *dTables = nullptr;   // dxCoarse | dyCoarse | dxFine | dyFine
+    float *dDepth = nullptr;    // totalCorners floats
+    uint32_t *dRgba = nullptr;  // width*height words, host-variant staging (lazy)
+};
+
+struct GrowBuffer {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+    cudaError_t reserve(size_t want) {
+        if (want <= bytes) return cudaSuccess;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMalloc(&ptr, want);
+        if (e == cudaSuccess) bytes = want;
+        return e;
+    }
+    void release() {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        bytes = 0;
+    }
+};
+
+} // namespace
+
+struct svo_tree {
+    int device = 0;
+    uint32_t *dWords = nullptr;
+    uint64_t nWords = 0;
+    float center[3] = {0, 0, 0};
+    uint32_t depth = 0;
+    cudaStream_t stream = nullptr;          // for the host-buffer entry points
+    svo::FrameCounters *dCounters = nullptr;
+    svo::FrameCounters *hCounters = nullptr; // pinned
+    std::mutex mutex;
+    std::map<std::tuple<int, int, int>, FramePlan> plans;
+    GrowBuffer batchIn, batchOut;
+
+    svo::TreeDev dev() const { return svo::TreeDev{dWords, nWords, depth}; }
+};
+
+namespace {
+
+// Depth = number of descriptor levels, found by following first children from
+// the root: the builder puts every leaf at the same depth (reference
+// src/VoxelOctree.cpp:139-205 recurses until halfSize == 1).
+int measureDepth(const uint32_t *words, uint64_t nWords, uint32_t &depthOut) {
+    uint64_t p = 0;
+    uint32_t depth = 0;
+    for (;;) {
+        if (p >= nWords) return fail(SVO_ERR_FORMAT, "node array: child pointer %llu past the end (%llu words)",
+                                     (unsigned long long)p, (unsigned long long)nWords);
+        uint32_t desc = words[p];
+        ++depth;
+        if (depth > 23) return fail(SVO_ERR_FORMAT, "node array: deeper than 23 levels");
+        if (((desc >> 8) & 0xFFu) == 0) return fail(SVO_ERR_FORMAT, "node array: descriptor %llu has no children", (unsigned long long)p);
+        uint64_t offset = desc >> 18;
+        if (desc & 0x20000u) {
+            if (p + 1 >= nWords) return fail(SVO_ERR_FORMAT, "node array: far word past the end");
+            offset = (offset << 32) | words[p + 1];
+        }
+        if ((desc & 0xFFu) == 0) {
+            if (p + offset >= nWords) return fail(SVO_ERR_FORMAT, "node array: leaf pointer past the end");
+            break;
+        }
+        if (offset == 0) return fail(SVO_ERR_FORMAT, "node array: zero child offset at %llu", (unsigned long long)p);
+        p += offset;
+    }
+    depthOut = depth;
+    return SVO_OK;
+}
+
+int createTree(const uint32_t *words, uint64_t nWords, const float center[3], int device, svo_tree **out) {
+    if (!words || !center || !out) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_tree_create: null argument");
+    if (nWords < 2) return fail(SVO_ERR_FORMAT, "node array too small (%llu words)", (unsigned long long)nWords);
+    *out = nullptr;
+    uint32_t depth = 0;
+    int st = measureDepth(words, nWords, depth);
+    if (st != SVO_OK) return st;
+
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(SVO_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(SVO_ERR_INVALID_ARGUMENT, "device %d out of range [0, %d)", device, count);
+
+    SVO_DEVICE(device);
+    std::unique_ptr<svo_tree> tree(new (std::nothrow) svo_tree);
+    if (!tree) return fail(SVO_ERR_OUT_OF_MEMORY, "out of host memory");
+    tree->device = device;
+    tree->nWords = nWords;
+    tree->depth = depth;
+    memcpy(tree->center, center, sizeof(float)*3);
+
+    // +1 padding word: the traversal reads words[p + 1] next to every descriptor
+    size_t bytes = size_t(nWords + 1)*sizeof(uint32_t);
+    auto cleanup = [&](cudaError_t err, const char *what) {
+        if (tree->dWords) cudaFree(tree->dWords);
+        if (tree->dCounters) cudaFree(tree->dCounters);
+        if (tree->hCounters) cudaFreeHost(tree->hCounters);
+        if (tree->stream) cudaStreamDestroy(tree->stream);
+        return failCuda(err, what);
+    };
+    if ((e = cudaMalloc(&tree->dWords, bytes)) != cudaSuccess) return cleanup(e, "cudaMalloc(node array)");
+    if ((e = cudaMemcpy(tree->dWords, words, size_t(nWords)*sizeof(uint32_t), cudaMemcpyHostToDevice)) != cudaSuccess)
+        return cleanup(e, "cudaMemcpy(node array)");
+    if ((e = cudaMemset(tree->dWords + nWords, 0, sizeof(uint32_t))) != cudaSuccess) return cleanup(e, "cudaMemset(padding)");
+    if ((e = cudaStreamCreateWithFlags(&tree->stream, cudaStreamNonBlocking)) != cudaSuccess) return cleanup(e, "cudaStreamCreate");
+    if ((e = cudaMalloc(&tree->dCounters, sizeof(svo::FrameCounters))) != cudaSuccess) return cleanup(e, "cudaMalloc(counters)");
+    if ((e = cudaMallocHost(&tree->hCounters, sizeof(svo::FrameCounters))) != cudaSuccess) return cleanup(e, "cudaMallocHost(counters)");
+    *out = tree.release();
+    return SVO_OK;
+}
+
+// The running sums renderBatch / renderTile use for screen coordinates
+// (reference src/Main.cpp:97-100, 167-170), tabulated once per configuration.
+int buildPlan(svo_tree *tree, int width, int height, int strips, FramePlan &plan) {
+    svo::FramePlanDev &p = plan.dev;
+    p.width = width;
+    p.height = height;
+    p.stripRows = (height - 1)/strips + 1;                       // Main.cpp:351
+    p.nStrips = (height + p.stripRows - 1)/p.stripRows;          // strips with y0 < height
+    p.tilesX = (width - 1)/8 + 2;                                // Main.cpp:359
+    int lastRows = height - (p.nStrips - 1)*p.stripRows;
+    p.tilesYLast = (lastRows - 1)/8 + 2;                         // Main.cpp:360
+    p.tilesYFull = p.nStrips > 1 ? (p.stripRows - 1)/8 + 2 : p.tilesYLast;
+    p.tileRowsFull = p.tilesYFull - 1;
+    p.tileRowsLast = p.tilesYLast - 1;
+    p.tileCols = p.tilesX - 1;
+    p.totalTileRows = (p.nStrips - 1)*p.tileRowsFull + p.tileRowsLast;
+    p.totalTiles = p.totalTileRows*p.tileCols;
+    p.totalCorners = (p.nStrips - 1)*p.tilesX*p.tilesYFull + p.tilesX*p.tilesYLast;
+
+    const float scale = 2.0f/width;                              // Main.cpp:156
+    const float tileScale = 8*scale;                             // Main.cpp:157
+    const float aspect = height/(float)width;                    // Main.cpp:62
+
+    size_t nDxC = p.tilesX, nDyC = size_t(p.nStrips)*p.tilesYFull, nDxF = width, nDyF = height;
+    std::vector<float> tables(nDxC + nDyC + nDxF + nDyF);
+    float *dxC = tables.data(), *dyC = dxC + nDxC, *dxF = dyC + nDyC, *dyF = dxF + nDxF;
+
+    float dx = -1.0f + 0*scale;                                  // x0 == 0, Main.cpp:169
+    for (int x = 0; x < p.tilesX; ++x, dx += tileScale) dxC[x] = dx;
+    for (int s = 0; s < p.nStrips; ++s) {
+        int y0 = s*p.stripRows;
+        float dy = aspect - y0*scale;                            // Main.cpp:167
+        for (int y = 0; y < p.tilesYFull; ++y, dy -= tileScale) dyC[s*p.tilesYFull + y] = dy;
+    }
+    for (int tx0 = 0; tx0 < width; tx0 += 8) {
+        float fx = -1.0f + tx0*scale;                            // Main.cpp:99
+        for (int x = tx0; x < tx0 + 8 && x < width; ++x, fx += scale) dxF[x] = fx;
+    }
+    for (int s = 0; s < p.nStrips; ++s) {
+        int y0 = s*p.stripRows, y1 = y0 + p.stripRows < height ? y0 + p.stripRows : height;
+        for (int ty0 = y0; ty0 < y1; ty0 += 8) {
+            float fy = aspect - ty0*scale;                       // Main.cpp:97
+            for (int y = ty0; y < ty0 + 8 && y < y1; ++y, fy -= scale) dyF[y] = fy;
+        }
+    }
+
+    SVO_CUDA(cudaMalloc(&plan.dTables, tables.size()*sizeof(float)));
+    SVO_CUDA(cudaMemcpy(plan.dTables, tables.data(), tables.size()*sizeof(float), cudaMemcpyHostToDevice));
+    SVO_CUDA(cudaMalloc(&plan.dDepth, size_t(p.totalCorners)*sizeof(float)));
+    p.dxCoarse = plan.dTables;
+    p.dyCoarse = p.dxCoarse + nDxC;
+    p.dxFine = p.dyCoarse + nDyC;
+    p.dyFine = p.dxFine + nDxF;
+    (void)tree;
+    return SVO_OK;
+}
+
+int getPlan(svo_tree *tree, int width, int height, int strips, FramePlan **out) {
+    auto key = std::make_tuple(width, height, strips);
+    auto it = tree->plans.find(key);
+    if (it == tree->plans.end()) {
+        FramePlan plan;
+        int st = buildPlan(tree, width, height, strips, plan);
+        if (st != SVO_OK) {
+            if (plan.dTables) cudaFree(plan.dTables);
+            if (plan.dDepth) cudaFree(plan.dDepth);
+            return st;
+        }
+        it = tree->plans.emplace(key, plan).first;
+    }
+    *out = &it->second;
+    return SVO_OK;
+}
+
+int checkDesc(const svo_frame_desc *desc) {
+    if (!desc) return fail(SVO_ERR_INVALID_ARGUMENT, "null frame descriptor");
+    if (desc->width < 1 || desc->height < 1 || desc->width > 65536 || desc->height > 65536)
+        return fail(SVO_ERR_INVALID_ARGUMENT, "bad frame size %dx%d", desc->width, desc->height);
+    if (desc->strips < 1 || desc->strips > desc->height)
+        return fail(SVO_ERR_INVALID_ARGUMENT, "strips must be in [1, height] (got %d)", desc->strips);
+    if (desc->flavour != SVO_FLAVOUR_VALIDATION && desc->flavour != SVO_FLAVOUR_FAST)
+        return fail(SVO_ERR_INVALID_ARGUMENT, "unknown flavour %d", desc->flavour);
+    if (desc->tile_world < 1 || desc->tile_rank < 0 || desc->tile_rank >= desc->tile_world)
+        return fail(SVO_ERR_INVALID_ARGUMENT, "bad tile interleave rank %d of %d", desc->tile_rank, desc->tile_world);
+    return SVO_OK;
+}
+
+svo::FrameConsts toDeviceConsts(const svo_frame_constants &c) {
+    svo::FrameConsts f;
+    f.posX = c.pos[0]; f.posY = c.pos[1]; f.posZ = c.pos[2];
+    f.a11 = c.a11; f.a12 = c.a12; f.a21 = c.a21; f.a22 = c.a22; f.a31 = c.a31; f.a32 = c.a32;
+    f.zx = c.zx; f.zy = c.zy; f.zz = c.zz;
+    f.lightX = c.light[0]; f.lightY = c.light[1]; f.lightZ = c.light[2];
+    f.coarseScale = c.coarse_scale;
+    f.beamBias = c.beam_bias;
+    return f;
+}
+
+// Enqueues one frame on `stream`. Caller holds tree->mutex and has made the device current.
+int enqueueFrame(svo_tree *tree, FramePlan *plan, const svo_camera *cam, const svo_frame_desc *desc,
+                 uint32_t *dRgba, float *dDepth, cudaStream_t stream, bool wantStats, uint32_t *launches) {
+    svo_frame_constants c;
+    svo::frameConstants(*cam, tree->center, desc->width, desc->height, desc->strips, c);
+    svo::FrameConsts f = toDeviceConsts(c);
+    float *depth = dDepth ? dDepth : plan->dDepth;
+    uint32_t n = 0;
+    SVO_CUDA(svo::launchCoarsePass(tree->dev(), plan->dev, f, desc->flavour, depth, stream));
+    ++n;
+    SVO_CUDA(svo::launchFinePass(tree->dev(), plan->dev, f, desc->flavour, depth, dRgba, desc->tile_rank,
+                                 desc->tile_world, stream));
+    ++n;
+    if (wantStats) {
+        SVO_CUDA(cudaMemsetAsync(tree->dCounters, 0, sizeof(svo::FrameCounters), stream));
+        SVO_CUDA(svo::launchTileStats(plan->dev, depth, desc->tile_rank, desc->tile_world, tree->dCounters, stream));
+        ++n;
+        SVO_CUDA(cudaMemcpyAsync(tree->hCounters, tree->dCounters, sizeof(svo::FrameCounters), cudaMemcpyDeviceToHost, stream));
+    }
+    if (launches) *launches = n;
+    return SVO_OK;
+}
+
+void fillStats(const svo_tree *tree, const FramePlan *plan, const svo_frame_desc *desc, uint32_t launches, svo_frame_stats *stats) {
+    stats->coarse_rays = uint64_t(plan->dev.totalCorners);
+    stats->fine_rays = tree->hCounters->fineRays;
+    stats->tiles_rendered = tree->hCounters->tilesRendered;
+    int owned = (plan->dev.totalTiles - desc->tile_rank + desc->tile_world - 1)/desc->tile_world;
+    stats->tiles_total = owned > 0 ? uint64_t(owned) : 0;
+    stats->kernel_launches = launches;
+    stats->reserved = 0;
+}
+
+} // namespace
+
+extern "C" {
+
+int svo_abi_version(void) { return SVO_ABI_VERSION; }
+
+const char *svo_last_error(void) { return g_lastError.c_str(); }
+
+int svo_device_count(int *count) {
+    if (!count) return fail(SVO_ERR_INVALID_ARGUMENT, "null count");
+    *count = 0;
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return fail(SVO_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    return SVO_OK;
+}
+
+void svo_free(void *p) { free(p); }
+
+int svo_host_alloc(size_t bytes, void **out) {
+    if (!out) return fail(SVO_ERR_INVALID_ARGUMENT, "null out");
+    *out = nullptr;
+    SVO_CUDA(cudaMallocHost(out, bytes ? bytes : 1));
+    return SVO_OK;
+}
+
+int svo_host_free(void *p) {
+    if (p) SVO_CUDA(cudaFreeHost(p));
+    return SVO_OK;
+}
+
+/* ---- .oct ------------------------------------------------------------------ */
+
+int svo_oct_read(const char *path, uint32_t **words, uint64_t *n_words, float center[3]) {
+    if (!path || !words || !n_words || !center) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_oct_read: null argument");
+    *words = nullptr;
+    *n_words = 0;
+    svo::OctFile f;
+    std::string err;
+    int status = 0;
+    if (!svo::readOctFile(path, f, err, status)) return fail(status, "%s", err.c_str());
+    *words = f.words;
+    *n_words = f.nWords;
+    memcpy(center, f.center, sizeof(float)*3);
+    return SVO_OK;
+}
+
+int svo_oct_write(const char *path, const uint32_t *words, uint64_t n_words, const float center[3], int compress) {
+    if (!path || (!words && n_words) || !center) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_oct_write: null argument");
+    std::string err;
+    int status = 0;
+    if (!svo::writeOctFile(path, words, n_words, center, compress != 0, err, status)) return fail(status, "%s", err.c_str());
+    return SVO_OK;
+}
+
+/* ---- trees ----------------------------------------------------------------- */
+
+int svo_tree_create_from_words(const uint32_t *words, uint64_t n_words, const float center[3], int device, svo_tree **out) {
+    return createTree(words, n_words, center, device, out);
+}
+
+int svo_tree_load_oct(const char *path, int device, svo_tree **out) {
+    if (!path || !out) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_tree_load_oct: null argument");
+    *out = nullptr;
+    svo::OctFile f;
+    std::string err;
+    int status = 0;
+    if (!svo::readOctFile(path, f, err, status)) return fail(status, "%s", err.c_str());
+    int st = createTree(f.words, f.nWords, f.center, device, out);
+    free(f.words);
+    return st;
+}
+
+int svo_tree_download_words(const svo_tree *tree, uint32_t *words_out, uint64_t n_words) {
+    if (!tree || !words_out) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_tree_download_words: null argument");
+    if (n_words != tree->nWords) return fail(SVO_ERR_INVALID_ARGUMENT, "word count mismatch (tree has %llu)", (unsigned long long)tree->nWords);
+    SVO_DEVICE(tree->device);
+    SVO_CUDA(cudaMemcpy(words_out, tree->dWords, size_t(n_words)*sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return SVO_OK;
+}
+
+int svo_tree_save_oct(const svo_tree *tree, const char *path, int compress) {
+    if (!tree || !path) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_tree_save_oct: null argument");
+    std::unique_ptr<uint32_t, void (*)(void *)> words(static_cast<uint32_t *>(malloc(size_t(tree->nWords)*4)), free);
+    if (!words) return fail(SVO_ERR_OUT_OF_MEMORY, "out of host memory");
+    int st = svo_tree_download_words(tree, words.get(), tree->nWords);
+    if (st != SVO_OK) return st;
+    return svo_oct_write(path, words.get(), tree->nWords, tree->center, compress);
+}
+
+int svo_tree_get_info(const svo_tree *tree, svo_tree_info *out) {
+    if (!tree || !out) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_tree_get_info: null argument");
+    out->n_words = tree->nWords;
+    memcpy(out->center, tree->center, sizeof(float)*3);
+    out->depth = tree->depth;
+    out->device = tree->device;
+    out->device_bytes = (tree->nWords + 1)*sizeof(uint32_t);
+    return SVO_OK;
+}
+
+int svo_tree_destroy(svo_tree *tree) {
+    if (!tree) return SVO_OK;
+    {
+        SVO_DEVICE(tree->device);
+        cudaStreamSynchronize(tree->stream);
+        for (auto &kv : tree->plans) {
+            if (kv.second.dTables) cudaFree(kv.second.dTables);
+            if (kv.second.dDepth) cudaFree(kv.second.dDepth);
+            if (kv.second.dRgba) cudaFree(kv.second.dRgba);
+        }
+        tree->batchIn.release();
+        tree->batchOut.release();
+        if (tree->dWords) cudaFree(tree->dWords);
+        if (tree->dCounters) cudaFree(tree->dCounters);
+        if (tree->hCounters) cudaFreeHost(tree->hCounters);
+        if (tree->stream) cudaStreamDestroy(tree->stream);
+    }
+    delete tree;
+    return SVO_OK;
+}
+
+/* ---- traversal -------------------------------------------------------------- */
+
+int svo_raymarch_batch_device(svo_tree *tree, uint64_t n, const float *d_o, const float *d_d, float ray_scale,
+                              int flavour, uint8_t *d_hit, float *d_t, uint32_t *d_normal, uint64_t *d_voxel,
+                              void *stream) {
+    if (!tree || (n && (!d_o || !d_d))) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_raymarch_batch_device: null argument");
+    if (flavour != SVO_FLAVOUR_VALIDATION && flavour != SVO_FLAVOUR_FAST) return fail(SVO_ERR_INVALID_ARGUMENT, "unknown flavour %d", flavour);
+    SVO_DEVICE(tree->device);
+    SVO_CUDA(svo::launchRaymarchBatch(tree->dev(), n, d_o, d_d, ray_scale, flavour, d_hit, d_t, d_normal, d_voxel,
+                                      static_cast<cudaStream_t>(stream)));
+    return SVO_OK;
+}
+
+int svo_raymarch_batch(svo_tree *tree, uint64_t n, const float *o, const float *d, float ray_scale, int flavour,
+                       uint8_t *hit, float *t, uint32_t *normal, uint64_t *voxel) {
+    if (!tree || (n && (!o || !d))) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_raymarch_batch: null argument");
+    if (flavour != SVO_FLAVOUR_VALIDATION && flavour != SVO_FLAVOUR_FAST) return fail(SVO_ERR_INVALID_ARGUMENT, "unknown flavour %d", flavour);
+    if (n == 0) return SVO_OK;
+    SVO_DEVICE(tree->device);
+    std::lock_guard<std::mutex> lock(tree->mutex);
+
+    const size_t rayBytes = size_t(n)*3*sizeof(float);
+    SVO_CUDA(tree->batchIn.reserve(2*rayBytes));
+    // outputs: voxel (8) | t (4) | normal (4) | hit (1) per ray, each section 16-byte aligned
+    auto align16 = [](size_t v) { return (v + 15) & ~size_t(15); };
+    size_t offVoxel = 0, offT = align16(offVoxel + size_t(n)*8), offNormal = align16(offT + size_t(n)*4),
+           offHit = align16(offNormal + size_t(n)*4), total = align16(offHit + size_t(n));
+    SVO_CUDA(tree->batchOut.reserve(total));
+
+    float *dO = static_cast<float *>(tree->batchIn.ptr);
+    float *dD = dO + size_t(n)*3;
+    unsigned char *base = static_cast<unsigned char *>(tree->batchOut.ptr);
+    uint64_t *dVoxel = voxel ? reinterpret_cast<uint64_t *>(base + offVoxel) : nullptr;
+    float *dT = t ? reinterpret_cast<float *>(base + offT) : nullptr;
+    uint32_t *dNormal = normal ? reinterpret_cast<uint32_t *>(base + offNormal) : nullptr;
+    uint8_t *dHit = hit ? base + offHit : nullptr;
+
+    cudaStream_t s = tree->stream;
+    SVO_CUDA(cudaMemcpyAsync(dO, o, rayBytes, cudaMemcpyHostToDevice, s));
+    SVO_CUDA(cudaMemcpyAsync(dD, d, rayBytes, cudaMemcpyHostToDevice, s));
+    SVO_CUDA(svo::launchRaymarchBatch(tree->dev(), n, dO, dD, ray_scale, flavour, dHit, dT, dNormal, dVoxel, s));
+    if (hit) SVO_CUDA(cudaMemcpyAsync(hit, dHit, size_t(n), cudaMemcpyDeviceToHost, s));
+    if (t) SVO_CUDA(cudaMemcpyAsync(t, dT, size_t(n)*4, cudaMemcpyDeviceToHost, s));
+    if (normal) SVO_CUDA(cudaMemcpyAsync(normal, dNormal, size_t(n)*4, cudaMemcpyDeviceToHost, s));
+    if (voxel) SVO_CUDA(cudaMemcpyAsync(voxel, dVoxel, size_t(n)*8, cudaMemcpyDeviceToHost, s));
+    SVO_CUDA(cudaStreamSynchronize(s));
+    return SVO_OK;
+}
+
+int svo_raymarch(svo_tree *tree, const float o[3], const float d[3], float ray_scale, uint32_t *normal, float *t, int *hit_out) {
+    if (!tree || !o || !d || !normal || !t || !hit_out) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_raymarch: null argument");
+    uint8_t code = 0;
+    float tt = 0.0f;
+    uint32_t nn = 0;
+    int st = svo_raymarch_batch(tree, 1, o, d, ray_scale, SVO_FLAVOUR_VALIDATION, &code, &tt, &nn, nullptr);
+    if (st != SVO_OK) return st;
+    *hit_out = code != SVO_MISS;
+    if (code != SVO_MISS) *t = tt;             // VoxelOctree.cpp:266 / :344
+    if (code == SVO_HIT_LEAF) *normal = nn;    // VoxelOctree.cpp:282
+    return SVO_OK;
+}
+
+/* ---- camera ----------------------------------------------------------------- */
+
+void svo_orbit_camera(float pitch_deg, float yaw_deg, float radius, svo_camera *out) {
+    if (out) svo::orbitCamera(pitch_deg, yaw_deg, radius, *out);
+}
+
+int svo_frame_constants_from_camera(const svo_camera *cam, const float center[3], int width, int height, int strips,
+                                    svo_frame_constants *out) {
+    if (!cam || !center || !out) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_frame_constants_from_camera: null argument");
+    if (width < 1 || height < 1 || strips < 1) return fail(SVO_ERR_INVALID_ARGUMENT, "bad frame configuration");
+    svo::frameConstants(*cam, center, width, height, strips, *out);
+    return SVO_OK;
+}
+
+/* ---- frames ------------------------------------------------------------------ */
+
+int svo_render_frame_device(svo_tree *tree, const svo_camera *cam, const svo_frame_desc *desc, uint32_t *d_rgba,
+                            float *d_depth, void *stream, svo_frame_stats *stats, int sync_stats) {
+    if (!tree || !cam || !d_rgba) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_render_frame_device: null argument");
+    int st = checkDesc(desc);
+    if (st != SVO_OK) return st;
+    SVO_DEVICE(tree->device);
+    std::lock_guard<std::mutex> lock(tree->mutex);
+    FramePlan *plan = nullptr;
+    if ((st = getPlan(tree, desc->width, desc->height, desc->strips, &plan)) != SVO_OK) return st;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    bool wantStats = stats && sync_stats;
+    uint32_t launches = 0;
+    if ((st = enqueueFrame(tree, plan, cam, desc, d_rgba, d_depth, s, wantStats, &launches)) != SVO_OK) return st;
+    if (wantStats) {
+        SVO_CUDA(cudaStreamSynchronize(s));
+        fillStats(tree, plan, desc, launches, stats);
+    }
+    return SVO_OK;
+}
+
+int svo_render_frame(svo_tree *tree, const svo_camera *cam, const svo_frame_desc *desc, uint32_t *rgba, float *depth,
+                     svo_frame_stats *stats) {
+    if (!tree || !cam || !rgba) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_render_frame: null argument");
+    int st = checkDesc(desc);
+    if (st != SVO_OK) return st;
+    SVO_DEVICE(tree->device);
+    std::lock_guard<std::mutex> lock(tree->mutex);
+    FramePlan *plan = nullptr;
+    if ((st = getPlan(tree, desc->width, desc->height, desc->strips, &plan)) != SVO_OK) return st;
+    size_t frameBytes = size_t(desc->width)*size_t(desc->height)*sizeof(uint32_t);
+    if (!plan->dRgba) {
+        SVO_CUDA(cudaMalloc(&plan->dRgba, frameBytes));
+        SVO_CUDA(cudaMemset(plan->dRgba, 0, frameBytes));
+    }
+    cudaStream_t s = tree->stream;
+    uint32_t launches = 0;
+    if ((st = enqueueFrame(tree, plan, cam, desc, plan->dRgba, nullptr, s, stats != nullptr, &launches)) != SVO_OK) return st;
+    SVO_CUDA(cudaMemcpyAsync(rgba, plan->dRgba, frameBytes, cudaMemcpyDeviceToHost, s));
+    if (depth)
+        SVO_CUDA(cudaMemcpyAsync(depth, plan->dDepth, size_t(plan->dev.totalCorners)*sizeof(float), cudaMemcpyDeviceToHost, s));
+    SVO_CUDA(cudaStreamSynchronize(s));
+    if (stats) fillStats(tree, plan, desc, launches, stats);
+    return SVO_OK;
+}
+
+/* ---- device memory + peer mapping -------------------------------------------- */
+
+int svo_device_alloc(int device, size_t bytes, void **out) {
+    if (!out) return fail(SVO_ERR_INVALID_ARGUMENT, "null out");
+    *out = nullptr;
+    SVO_DEVICE(device);
+    SVO_CUDA(cudaMalloc(out, bytes ? bytes : 1));
+    return SVO_OK;
+}
+
+int svo_device_free(int device, void *p) {
+    if (!p) return SVO_OK;
+    SVO_DEVICE(device);
+    SVO_CUDA(cudaFree(p));
+    return SVO_OK;
+}
+
+int svo_device_memset(int device, void *p, int value, size_t bytes) {
+    SVO_DEVICE(device);
+    SVO_CUDA(cudaMemset(p, value, bytes));
+    return SVO_OK;
+}
+
+int svo_device_to_host(int device, void *host_dst, const void *device_src, size_t bytes) {
+    SVO_DEVICE(device);
+    SVO_CUDA(cudaMemcpy(host_dst, device_src, bytes, cudaMemcpyDeviceToHost));
+    return SVO_OK;
+}
+
+int svo_host_to_device(int device, void *device_dst, const void *host_src, size_t bytes) {
+    SVO_DEVICE(device);
+    SVO_CUDA(cudaMemcpy(device_dst, host_src, bytes, cudaMemcpyHostToDevice));
+    return SVO_OK;
+}
+
+int svo_device_synchronize(int device) {
+    SVO_DEVICE(device);
+    SVO_CUDA(cudaDeviceSynchronize());
+    return SVO_OK;
+}
+
+int svo_ipc_export(int device, void *p, uint8_t handle[SVO_IPC_HANDLE_BYTES]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == SVO_IPC_HANDLE_BYTES, "IPC handle size");
+    if (!p || !handle) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_ipc_export: null argument");
+    SVO_DEVICE(device);
+    cudaIpcMemHandle_t h;
+    SVO_CUDA(cudaIpcGetMemHandle(&h, p));
+    memcpy(handle, &h, sizeof h);
+    return SVO_OK;
+}
+
+int svo_ipc_open(int device, const uint8_t handle[SVO_IPC_HANDLE_BYTES], void **out) {
+    if (!handle || !out) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_ipc_open: null argument");
+    *out = nullptr;
+    SVO_DEVICE(device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    SVO_CUDA(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+    return SVO_OK;
+}
+
+int svo_ipc_close(int device, void *p) {
+    if (!p) return SVO_OK;
+    SVO_DEVICE(device);
+    SVO_CUDA(cudaIpcCloseMemHandle(p));
+    return SVO_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,293 @@
+// Device-side ESVO traversal, ray generation and shading for sm_100a.
+//
+// What it computes is fixed by the reference (tunabrain/sparse-voxel-octrees):
+//   raymarch            reference src/VoxelOctree.cpp:207-346
+//   shade               reference src/Main.cpp:81-90
+//   decompressMaterial  reference src/Util.hpp:86-100, invSqrt :47-58
+//   pixel pack          reference src/Main.cpp:128-132
+// How it computes it is not: one thread per ray, traversal state in registers,
+// the scale-indexed (parent, maxT) stack in shared memory (conflict-free
+// [slot][thread] layout), read-only node fetches with the possible far word
+// fetched speculatively next to its descriptor, 32-bit word indices whenever
+// the tree has < 2^32 words.
+//
+// Arithmetic flavours (svo_flavour in include/svo_b200.h): every float
+// operation below goes through an explicitly rounded intrinsic, so neither
+// flavour depends on the compiler's contraction setting. FAST only changes the
+// traversal's a*b-c / a*b+c forms into single FMAs and min/max into FMNMX.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace svo {
+
+constexpr int kMaxScale = 23;      // reference src/VoxelOctree.hpp:38
+constexpr float kTreeMiss = 1e10f; // reference src/Main.cpp:140
+
+template <bool FAST>
+struct Arith {
+    // a*b - c
+    static __device__ __forceinline__ float mulsub(float a, float b, float c) {
+        if (FAST) return __fmaf_rn(a, b, -c);
+        return __fsub_rn(__fmul_rn(a, b), c);
+    }
+    // a*b + c
+    static __device__ __forceinline__ float muladd(float a, float b, float c) {
+        if (FAST) return __fmaf_rn(a, b, c);
+        return __fadd_rn(__fmul_rn(a, b), c);
+    }
+    // std::min(a, b) == (b < a) ? b : a ; std::max(a, b) == (a < b) ? b : a
+    static __device__ __forceinline__ float min2(float a, float b) {
+        if (FAST) return fminf(a, b);
+        return (b < a) ? b : a;
+    }
+    static __device__ __forceinline__ float max2(float a, float b) {
+        if (FAST) return fmaxf(a, b);
+        return (a < b) ? b : a;
+    }
+};
+
+// Exactly rounded helpers shared by both flavours (ray generation, shading).
+__device__ __forceinline__ float mulRn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float addRn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float subRn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float minStd(float a, float b) { return (b < a) ? b : a; }
+__device__ __forceinline__ float maxStd(float a, float b) { return (a < b) ? b : a; }
+
+// reference src/Util.hpp:47-58
+__device__ __forceinline__ float invSqrtQuake(float x) {
+    float halfX = mulRn(x, 0.5f);
+    float y = __uint_as_float(0x5f3759dfu - (__float_as_uint(x) >> 1));
+    return mulRn(y, subRn(1.5f, mulRn(mulRn(halfX, y), y)));
+}
+
+// x*x + y*y + z*z, left to right (reference src/math/Vec3.hpp:49-51)
+__device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, float by, float bz) {
+    return addRn(addRn(mulRn(ax, bx), mulRn(ay, by)), mulRn(az, bz));
+}
+
+struct FrameConsts {
+    float posX, posY, posZ;
+    float a11, a12, a21, a22, a31, a32;
+    float zx, zy, zz;
+    float lightX, lightY, lightZ;
+    float coarseScale;
+    float beamBias;
+};
+
+// dir = normalize(dx*col1 + dy*col2 + z), reference src/Main.cpp:108-113 / :171-176
+__device__ __forceinline__ void rayDirection(const FrameConsts &f, float dx, float dy, float &x, float &y, float &z) {
+    x = addRn(addRn(mulRn(dx, f.a11), mulRn(dy, f.a12)), f.zx);
+    y = addRn(addRn(mulRn(dx, f.a21), mulRn(dy, f.a22)), f.zy);
+    z = addRn(addRn(mulRn(dx, f.a31), mulRn(dy, f.a32)), f.zz);
+    float s = invSqrtQuake(dot3(x, y, z, x, y, z));
+    x = mulRn(x, s);
+    y = mulRn(y, s);
+    z = mulRn(z, s);
+}
+
+// reference src/Main.cpp:81-90 + src/Util.hpp:86-100; returns the grey value
+__device__ __forceinline__ float shadeMaterial(uint32_t word, float rx, float ry, float rz, float lx, float ly, float lz) {
+    uint32_t face = (word >> 29) & 3u;
+    float u = subRn(mulRn(mulRn(float((word >> 18) & 0x7FFu), 4.8852e-4f), 2.0f), 1.0f);
+    float v = subRn(mulRn(mulRn(float((word >> 7) & 0x7FFu), 4.8852e-4f), 2.0f), 1.0f);
+    float s = (word & 0x80000000u) ? -1.0f : 1.0f;
+    // n[face] = s, n[(face+1)%3] = u, n[(face+2)%3] = v
+    float nx = (face == 0) ? s : ((face == 1) ? v : u);
+    float ny = (face == 0) ? u : ((face == 1) ? s : v);
+    float nz = (face == 0) ? v : ((face == 1) ? u : s);
+    float inv = invSqrtQuake(dot3(nx, ny, nz, nx, ny, nz));
+    nx = mulRn(nx, inv);
+    ny = mulRn(ny, inv);
+    nz = mulRn(nz, inv);
+    float c = __fdiv_rn(mulRn(float(word & 0x7Fu), 1.0f), 127.0f);
+
+    float proj = mulRn(dot3(nx, ny, nz, rx, ry, rz), 2.0f);     // Vec3::reflect, Vec3.hpp:63-71
+    float qx = subRn(rx, mulRn(nx, proj));
+    float qy = subRn(ry, mulRn(ny, proj));
+    float qz = subRn(rz, mulRn(nz, proj));
+    float d = maxStd(dot3(lx, ly, lz, qx, qy, qz), 0.0f);
+    float specular = mulRn(d, d);
+    return addRn(mulRn(mulRn(c, 0.9f), fabsf(dot3(lx, ly, lz, nx, ny, nz))), mulRn(specular, 0.2f));
+}
+
+// uint32(std::min(v, 1.0f)*255.0) replicated to r,g,b with alpha 0xFF (Main.cpp:128-132).
+// The reference multiplies in double; the product of a 24-bit and an 8-bit
+// significand is exact there, and rounding the same product toward zero in
+// float keeps every bit above 2^0, so truncation gives the same integer.
+__device__ __forceinline__ uint32_t packGrey(float v) {
+    uint32_t g = __float2uint_rz(__fmul_rz(minStd(v, 1.0f), 255.0f));
+    return g | (g << 8) | (g << 16) | 0xFF000000u;
+}
+
+// The scale-indexed stack (reference: StackEntry rayStack[24], VoxelOctree.cpp:208-212)
+// lives in shared memory: slot s of thread t is at [s*blockDim + t], so a warp
+// touching one slot hits 32 distinct banks.
+template <typename IdxT>
+struct SmemStack {
+    IdxT *parent;   // already offset by the thread index
+    float *maxT;
+    uint32_t stride;
+    __device__ __forceinline__ void push(int slot, IdxT p, float m) {
+        parent[slot*stride] = p;
+        maxT[slot*stride] = m;
+    }
+    __device__ __forceinline__ void pop(int slot, IdxT &p, float &m) const {
+        p = parent[slot*stride];
+        m = maxT[slot*stride];
+    }
+};
+
+__device__ __forceinline__ uint32_t ldNode(const uint32_t *__restrict__ p) { return __ldg(p); }
+
+enum : int { kMiss = 0, kHitLeaf = 1, kHitLod = 2 };
+
+// reference src/VoxelOctree.cpp:207-346. Returns kMiss / kHitLeaf / kHitLod.
+//   tOut      written on a hit only
+//   normalOut written on a leaf hit only
+//   voxelOut  leaf word index, or parent | childShift << 60 for LOD exits
+// LOD == false elides the rayScale test (rayScale == 0 can never pass it:
+// maxTC*0 is +-0 or NaN, scaleExp2 > 0).
+template <bool FAST, bool LOD, typename IdxT>
+__device__ __forceinline__ int raymarch(const uint32_t *__restrict__ octree, float ox, float oy, float oz,
+                                        float dx, float dy, float dz, float rayScale, SmemStack<IdxT> stack,
+                                        float &tOut, uint32_t &normalOut, uint64_t &voxelOut) {
+    typedef Arith<FAST> A;
+
+    if (fabsf(dx) < 1e-4f) dx = 1e-4f;      // :217-219, sign dropped on purpose
+    if (fabsf(dy) < 1e-4f) dy = 1e-4f;
+    if (fabsf(dz) < 1e-4f) dz = 1e-4f;
+
+    float dTx = __fdiv_rn(1.0f, -fabsf(dx)); // :221-223
+    float dTy = __fdiv_rn(1.0f, -fabsf(dy));
+    float dTz = __fdiv_rn(1.0f, -fabsf(dz));
+
+    float bTx = mulRn(dTx, ox);              // :225-227
+    float bTy = mulRn(dTy, oy);
+    float bTz = mulRn(dTz, oz);
+
+    uint32_t octantMask = 7;                 // :229-232
+    if (dx > 0.0f) { octantMask ^= 1; bTx = A::mulsub(3.0f, dTx, bTx); }
+    if (dy > 0.0f) { octantMask ^= 2; bTy = A::mulsub(3.0f, dTy, bTy); }
+    if (dz > 0.0f) { octantMask ^= 4; bTz = A::mulsub(3.0f, dTz, bTz); }
+
+    float minT = A::max2(A::mulsub(2.0f, dTx, bTx), A::max2(A::mulsub(2.0f, dTy, bTy), A::mulsub(2.0f, dTz, bTz)));
+    float maxT = A::min2(subRn(dTx, bTx), A::min2(subRn(dTy, bTy), subRn(dTz, bTz)));
+    minT = A::max2(minT, 0.0f);
+
+    uint32_t current = 0;
+    uint32_t farWord = 0;
+    IdxT parent = 0;
+    uint32_t idx = 0;
+    float posX = 1.0f, posY = 1.0f, posZ = 1.0f;
+    int scale = kMaxScale - 1;
+    float scaleExp2 = 0.5f;
+
+    if (A::mulsub(1.5f, dTx, bTx) > minT) { idx ^= 1; posX = 1.5f; }   // :248-250
+    if (A::mulsub(1.5f, dTy, bTy) > minT) { idx ^= 2; posY = 1.5f; }
+    if (A::mulsub(1.5f, dTz, bTz) > minT) { idx ^= 4; posZ = 1.5f; }
+
+    while (scale < kMaxScale) {
+        if (current == 0) {
+            // descriptor and its possible far word (bit 17) in flight together;
+            // the node array carries one padding word so parent + 1 is always readable
+            current = ldNode(octree + parent);
+            farWord = ldNode(octree + parent + 1);
+        }
+
+        float cornerTX = A::mulsub(posX, dTx, bTx);   // :256-259
+        float cornerTY = A::mulsub(posY, dTy, bTy);
+        float cornerTZ = A::mulsub(posZ, dTz, bTz);
+        float maxTC = A::min2(cornerTX, A::min2(cornerTY, cornerTZ));
+
+        uint32_t childShift = idx ^ octantMask;
+        uint32_t childMasks = current << childShift;
+
+        if ((childMasks & 0x8000u) && minT <= maxT) {
+            if (LOD && mulRn(maxTC, rayScale) >= scaleExp2) {   // :265-268
+                tOut = maxTC;
+                voxelOut = uint64_t(parent) | (uint64_t(childShift) << 60);
+                return kHitLod;
+            }
+
+            float maxTV = A::min2(maxT, maxTC);
+            float half = mulRn(scaleExp2, 0.5f);
+            float centerTX = A::muladd(half, dTx, cornerTX);
+            float centerTY = A::muladd(half, dTy, cornerTY);
+            float centerTZ = A::muladd(half, dTz, cornerTZ);
+
+            if (minT <= maxTV) {
+                IdxT childOffset = IdxT(current >> 18);
+                if (current & 0x20000u) {                      // :278-279
+                    if (sizeof(IdxT) == 8)
+                        childOffset = IdxT((uint64_t(childOffset) << 32) | uint64_t(farWord));
+                    else
+                        childOffset = IdxT(farWord);           // high 14 bits are zero below 2^32 words
+                }
+
+                if (!(childMasks & 0x80u)) {                   // leaf, :281-285
+                    IdxT leaf = childOffset + parent + IdxT(__popc(((childMasks >> (8 + childShift)) << childShift) & 127u));
+                    normalOut = ldNode(octree + leaf);
+                    voxelOut = uint64_t(leaf);
+                    tOut = minT;
+                    return kHitLeaf;
+                }
+
+                stack.push(kMaxScale - 1 - scale, parent, maxT);   // :287-288
+
+                uint32_t siblings = uint32_t(__popc(childMasks & 127u));
+                parent += childOffset + IdxT(siblings);
+                if (current & 0x10000u) parent += IdxT(siblings);
+
+                idx = 0;
+                scale--;
+                scaleExp2 = half;
+
+                if (centerTX > minT) { idx ^= 1; posX = addRn(posX, scaleExp2); }
+                if (centerTY > minT) { idx ^= 2; posY = addRn(posY, scaleExp2); }
+                if (centerTZ > minT) { idx ^= 4; posZ = addRn(posZ, scaleExp2); }
+
+                maxT = maxTV;
+                current = 0;
+                continue;
+            }
+        }
+
+        uint32_t stepMask = 0;                                  // :310-316
+        if (cornerTX <= maxTC) { stepMask ^= 1; posX = subRn(posX, scaleExp2); }
+        if (cornerTY <= maxTC) { stepMask ^= 2; posY = subRn(posY, scaleExp2); }
+        if (cornerTZ <= maxTC) { stepMask ^= 4; posZ = subRn(posZ, scaleExp2); }
+
+        minT = maxTC;
+        idx ^= stepMask;
+
+        if ((idx & stepMask) != 0) {                            // :318-338
+            uint32_t differingBits = 0;
+            if (stepMask & 1) differingBits |= __float_as_uint(posX) ^ __float_as_uint(addRn(posX, scaleExp2));
+            if (stepMask & 2) differingBits |= __float_as_uint(posY) ^ __float_as_uint(addRn(posY, scaleExp2));
+            if (stepMask & 4) differingBits |= __float_as_uint(posZ) ^ __float_as_uint(addRn(posZ, scaleExp2));
+            // reference: exponent of (float)differingBits; differingBits < 2^24
+            // always (positions stay in [0.5, 2)), so that is the index of the
+            // highest set bit
+            scale = 31 - __clz(int(differingBits));
+            scaleExp2 = __uint_as_float(uint32_t(scale - kMaxScale + 127) << 23);
+
+            if (scale >= kMaxScale) return kMiss;               // left the root (:341-342)
+            stack.pop(kMaxScale - 1 - scale, parent, maxT);
+
+            uint32_t shX = __float_as_uint(posX) >> scale;
+            uint32_t shY = __float_as_uint(posY) >> scale;
+            uint32_t shZ = __float_as_uint(posZ) >> scale;
+            posX = __uint_as_float(shX << scale);
+            posY = __uint_as_float(shY << scale);
+            posZ = __uint_as_float(shZ << scale);
+            idx = (shX & 1) | ((shY & 1) << 1) | ((shZ & 1) << 2);
+
+            current = 0;
+        }
+    }
+    return kMiss;
+}
+
+} // namespace svo

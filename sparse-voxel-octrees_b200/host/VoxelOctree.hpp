@@ -1,0 +1,101 @@
+// Drop-in C++ facade with the reference's own class surface
+// (reference src/VoxelOctree.hpp:48-57), forwarding to the C ABI in
+// include/svo_b200.h. Header-only; link with -lsvo_b200.
+//
+//   VoxelOctree(const char *path)                  reference src/VoxelOctree.cpp:57
+//   VoxelOctree(VoxelData *voxels)                 reference src/VoxelOctree.cpp:125  (see adopt() below)
+//   void save(const char *path)                    reference src/VoxelOctree.cpp:92
+//   bool raymarch(o, d, rayScale, normal&, t&)     reference src/VoxelOctree.cpp:207
+//   Vec3 center() const                            reference src/VoxelOctree.hpp:55
+//
+// When this header is included after the reference's math/Vec3.hpp and
+// IntTypes.hpp it uses their Vec3 / uint32; otherwise it supplies minimal
+// stand-ins. The builder constructor is kept by delegation: build with the
+// reference's own VoxelData/VoxelOctree, then hand the node array over with
+// VoxelOctree::adopt(words, count, center) -- it is uploaded to HBM unchanged.
+//
+// Differences a caller can observe: failures throw std::runtime_error carrying
+// svo_last_error() instead of being ignored (the reference silently continues
+// after a failed fopen, VoxelOctree.cpp:60,95); raymarch() is a batch of one
+// (a PCIe round trip per call) -- use raymarchBatch()/renderFrame() for speed.
+#ifndef SVO_B200_VOXELOCTREE_HPP_
+#define SVO_B200_VOXELOCTREE_HPP_
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "svo_b200.h"
+
+#ifndef MATH_VEC3_HPP_
+struct Vec3 {
+    float x, y, z;
+    Vec3() : x(0.0f), y(0.0f), z(0.0f) {}
+    Vec3(float a) : x(a), y(a), z(a) {}
+    Vec3(float _x, float _y, float _z) : x(_x), y(_y), z(_z) {}
+};
+#endif
+#ifndef INTTYPES_HPP_
+typedef std::uint32_t uint32;
+typedef std::uint64_t uint64;
+#endif
+
+class VoxelOctree {
+    svo_tree *_tree;
+    svo_tree_info _info;
+
+    static void check(int status, const char *what) {
+        if (status != SVO_OK) throw std::runtime_error(std::string(what) + ": " + svo_last_error());
+    }
+    VoxelOctree(const VoxelOctree &);
+    VoxelOctree &operator=(const VoxelOctree &);
+    explicit VoxelOctree(svo_tree *tree) : _tree(tree) { check(svo_tree_get_info(_tree, &_info), "svo_tree_get_info"); }
+
+public:
+    explicit VoxelOctree(const char *path, int device = 0) : _tree(0) {
+        check(svo_tree_load_oct(path, device, &_tree), "VoxelOctree(path)");
+        check(svo_tree_get_info(_tree, &_info), "svo_tree_get_info");
+    }
+    // Node array from the reference's builder (or anywhere else), uploaded unchanged.
+    static VoxelOctree *adopt(const uint32 *words, uint64 count, const Vec3 &center, int device = 0) {
+        float c[3] = {center.x, center.y, center.z};
+        svo_tree *tree = 0;
+        check(svo_tree_create_from_words(words, count, c, device, &tree), "VoxelOctree::adopt");
+        return new VoxelOctree(tree);
+    }
+    ~VoxelOctree() { svo_tree_destroy(_tree); }
+
+    void save(const char *path) { check(svo_tree_save_oct(_tree, path, 1), "VoxelOctree::save"); }
+
+    bool raymarch(const Vec3 &o, const Vec3 &d, float rayScale, uint32 &normal, float &t) {
+        float oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
+        int hit = 0;
+        check(svo_raymarch(_tree, oo, dd, rayScale, &normal, &t, &hit), "VoxelOctree::raymarch");
+        return hit != 0;
+    }
+
+    Vec3 center() const { return Vec3(_info.center[0], _info.center[1], _info.center[2]); }
+
+    // ---- beyond the reference surface: what a GPU needs to be fast ----------
+    uint64 wordCount() const { return _info.n_words; }
+    uint32 depth() const { return _info.depth; }
+    svo_tree *handle() { return _tree; }
+
+    // n rays, host arrays (n x 3 floats each). See svo_raymarch_batch.
+    void raymarchBatch(uint64 n, const float *o, const float *d, float rayScale, uint8_t *hit, float *t,
+                       uint32 *normal, uint64 *voxel = 0, int flavour = SVO_FLAVOUR_VALIDATION) {
+        check(svo_raymarch_batch(_tree, n, o, d, rayScale, flavour, hit, t, normal, voxel), "VoxelOctree::raymarchBatch");
+    }
+
+    // One frame of the reference's renderBatch loop over `strips` strips (Main.cpp:139-202, 351-362).
+    svo_frame_stats renderFrame(const svo_camera &cam, int width, int height, int strips, uint32 *rgba,
+                                int flavour = SVO_FLAVOUR_FAST) {
+        svo_frame_desc desc = {width, height, strips, flavour, 0, 1, {0, 0}};
+        svo_frame_stats stats;
+        check(svo_render_frame(_tree, &cam, &desc, rgba, 0, &stats), "VoxelOctree::renderFrame");
+        return stats;
+    }
+};
+
+#endif

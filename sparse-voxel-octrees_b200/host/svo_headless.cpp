@@ -1,0 +1,79 @@
+// svo_headless -- the SDL-free replacement for the reference's `-viewer` mode
+// (reference src/Main.cpp:332-376): loads an .oct, renders an orbit of frames on
+// the GPU with the reference's strip/tile/beam semantics and writes PPM images.
+//
+//   svo_headless <in.oct> [--size WxH] [--strips N] [--frames K] [--radius R] [--pitch P]
+//                [--yaw0 Y] [--yaw-step S] [--validation] [--out prefix]
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "VoxelOctree.hpp"
+
+static void writePpm(const std::string &path, const uint32_t *rgba, int w, int h) {
+    FILE *fp = fopen(path.c_str(), "wb");
+    if (!fp) { fprintf(stderr, "cannot write %s\n", path.c_str()); return; }
+    fprintf(fp, "P6\n%d %d\n255\n", w, h);
+    std::vector<unsigned char> row(size_t(w)*3);
+    for (int y = 0; y < h; ++y) {
+        for (int x = 0; x < w; ++x) {
+            uint32_t p = rgba[size_t(y)*w + x];
+            row[3*x] = p & 255; row[3*x + 1] = (p >> 8) & 255; row[3*x + 2] = (p >> 16) & 255;
+        }
+        fwrite(row.data(), 1, row.size(), fp);
+    }
+    fclose(fp);
+}
+
+int main(int argc, char **argv) {
+    if (argc < 2) {
+        fprintf(stderr, "usage: %s <in.oct> [--size WxH] [--strips N] [--frames K] [--radius R] [--pitch P] "
+                        "[--yaw0 Y] [--yaw-step S] [--validation] [--out prefix]\n", argv[0]);
+        return 2;
+    }
+    int w = 1280, h = 720, strips = 16, frames = 1, flavour = SVO_FLAVOUR_FAST; /* Main.cpp:57-60 defaults */
+    float radius = 1.0f, pitch = 0.0f, yaw0 = 0.0f, yawStep = 3.6f;
+    std::string out;
+    for (int i = 2; i < argc; ++i) {
+        std::string a = argv[i];
+        auto next = [&]() -> const char * { return i + 1 < argc ? argv[++i] : ""; };
+        if (a == "--size") sscanf(next(), "%dx%d", &w, &h);
+        else if (a == "--strips") strips = atoi(next());
+        else if (a == "--frames") frames = atoi(next());
+        else if (a == "--radius") radius = float(atof(next()));
+        else if (a == "--pitch") pitch = float(atof(next()));
+        else if (a == "--yaw0") yaw0 = float(atof(next()));
+        else if (a == "--yaw-step") yawStep = float(atof(next()));
+        else if (a == "--validation") flavour = SVO_FLAVOUR_VALIDATION;
+        else if (a == "--out") out = next();
+        else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
+    }
+    try {
+        VoxelOctree tree(argv[1]);
+        printf("loaded %s: %llu words, depth %u\n", argv[1], (unsigned long long)tree.wordCount(), tree.depth());
+        uint32_t *rgba = 0;
+        if (svo_host_alloc(size_t(w)*h*4, reinterpret_cast<void **>(&rgba)) != SVO_OK) throw std::runtime_error(svo_last_error());
+        double totalMs = 0.0;
+        unsigned long long rays = 0;
+        for (int k = 0; k < frames; ++k) {
+            svo_camera cam;
+            svo_orbit_camera(pitch, yaw0 + yawStep*k, radius, &cam);
+            auto t0 = std::chrono::steady_clock::now();
+            svo_frame_stats st = tree.renderFrame(cam, w, h, strips, rgba, flavour);
+            double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            if (k > 0 || frames == 1) { totalMs += ms; rays += st.coarse_rays + st.fine_rays; }
+            if (!out.empty()) writePpm(out + "_" + std::to_string(k) + ".ppm", rgba, w, h);
+        }
+        int timed = frames > 1 ? frames - 1 : 1;
+        printf("%d frame(s) %dx%d, %d strips: %.3f ms/frame end to end (host buffer), %.1f Mrays/s\n", timed, w, h,
+               strips, totalMs/timed, rays/(totalMs*1e3));
+        svo_host_free(rgba);
+    } catch (const std::exception &e) {
+        fprintf(stderr, "error: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}

@@ -1,0 +1,406 @@
+"""pysvo -- thin ctypes binding of libsvo_b200.so (C ABI: include/svo_b200.h).
+
+This is plumbing for the tests, the benchmark and Python users; the product is
+the CUDA library. There is no fallback of any kind: if the library is not
+built, or there is no CUDA device, calls raise.
+
+The class surface mirrors the reference's ``VoxelOctree`` (reference
+src/VoxelOctree.hpp:48-57): ``VoxelOctree(path)``, ``save(path)``,
+``raymarch(o, d, rayScale)``, ``center()``, plus the batched and per-frame
+entry points the GPU needs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+PKG_DIR = Path(__file__).resolve().parent.parent
+LIB_PATH = PKG_DIR / "libsvo_b200.so"
+
+FLAVOUR_VALIDATION = 0
+FLAVOUR_FAST = 1
+MISS, HIT_LEAF, HIT_LOD = 0, 1, 2
+T_MISS = np.float32(1e10)
+VOXEL_NONE = np.uint64(0xFFFFFFFFFFFFFFFF)
+IPC_HANDLE_BYTES = 64
+
+_STATUS = {0: "SVO_OK", 1: "SVO_ERR_INVALID_ARGUMENT", 2: "SVO_ERR_IO", 3: "SVO_ERR_FORMAT",
+           4: "SVO_ERR_OUT_OF_MEMORY", 5: "SVO_ERR_CUDA", 6: "SVO_ERR_NO_DEVICE", 7: "SVO_ERR_UNSUPPORTED"}
+
+
+class SvoError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(f"{_STATUS.get(status, status)}: {message}")
+        self.status = status
+
+
+class Camera(C.Structure):
+    _fields_ = [("model", C.c_float * 16), ("view", C.c_float * 16)]
+
+    @classmethod
+    def from_matrices(cls, model, view):
+        cam = cls()
+        cam.model[:] = [float(x) for x in np.asarray(model, np.float32).reshape(16)]
+        cam.view[:] = [float(x) for x in np.asarray(view, np.float32).reshape(16)]
+        return cam
+
+
+class FrameConstants(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("strips", C.c_int32), ("tile_size", C.c_int32),
+                ("pos", C.c_float * 3),
+                ("a11", C.c_float), ("a12", C.c_float), ("a21", C.c_float), ("a22", C.c_float),
+                ("a31", C.c_float), ("a32", C.c_float),
+                ("zx", C.c_float), ("zy", C.c_float), ("zz", C.c_float),
+                ("scale", C.c_float), ("tile_scale", C.c_float), ("coarse_scale", C.c_float), ("aspect", C.c_float),
+                ("light", C.c_float * 3), ("beam_bias", C.c_float)]
+
+    def as_array(self):
+        return np.frombuffer(bytes(self), dtype=np.float32, offset=16).copy()
+
+
+class FrameDesc(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("strips", C.c_int32), ("flavour", C.c_int32),
+                ("tile_rank", C.c_int32), ("tile_world", C.c_int32), ("reserved", C.c_int32 * 2)]
+
+
+class FrameStats(C.Structure):
+    _fields_ = [("coarse_rays", C.c_uint64), ("fine_rays", C.c_uint64), ("tiles_rendered", C.c_uint64),
+                ("tiles_total", C.c_uint64), ("kernel_launches", C.c_uint32), ("reserved", C.c_uint32)]
+
+    @property
+    def rays(self):
+        return int(self.coarse_rays + self.fine_rays)
+
+
+class TreeInfo(C.Structure):
+    _fields_ = [("n_words", C.c_uint64), ("center", C.c_float * 3), ("depth", C.c_uint32), ("device", C.c_int32),
+                ("device_bytes", C.c_uint64)]
+
+
+def build_library(force: bool = False) -> Path:
+    """make -C sparse-voxel-octrees_b200 (nvcc, sm_100a). Cross-compiles without a GPU."""
+    args = ["make", "-C", str(PKG_DIR), "-j8"]
+    if force:
+        args.insert(1, "-B")
+    subprocess.check_call(args, stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """The loaded library. Raises if it has not been built -- there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise FileNotFoundError(
+            f"{LIB_PATH} is missing: build it with `make -C {PKG_DIR}` (or __graft_entry__.build()). "
+            "pysvo has no CPU or PyTorch fallback.")
+    L = C.CDLL(str(LIB_PATH))
+    vp, u64, i32, f32 = C.c_void_p, C.c_uint64, C.c_int, C.c_float
+    P = C.POINTER
+    sigs = {
+        "svo_abi_version": (i32, []),
+        "svo_last_error": (C.c_char_p, []),
+        "svo_device_count": (i32, [P(i32)]),
+        "svo_free": (None, [vp]),
+        "svo_host_alloc": (i32, [C.c_size_t, P(vp)]),
+        "svo_host_free": (i32, [vp]),
+        "svo_oct_read": (i32, [C.c_char_p, P(P(C.c_uint32)), P(u64), P(f32)]),
+        "svo_oct_write": (i32, [C.c_char_p, vp, u64, P(f32), i32]),
+        "svo_tree_create_from_words": (i32, [vp, u64, P(f32), i32, P(vp)]),
+        "svo_tree_load_oct": (i32, [C.c_char_p, i32, P(vp)]),
+        "svo_tree_save_oct": (i32, [vp, C.c_char_p, i32]),
+        "svo_tree_get_info": (i32, [vp, P(TreeInfo)]),
+        "svo_tree_download_words": (i32, [vp, vp, u64]),
+        "svo_tree_destroy": (i32, [vp]),
+        "svo_raymarch_batch": (i32, [vp, u64, vp, vp, f32, i32, vp, vp, vp, vp]),
+        "svo_raymarch_batch_device": (i32, [vp, u64, vp, vp, f32, i32, vp, vp, vp, vp, vp]),
+        "svo_raymarch": (i32, [vp, P(f32), P(f32), f32, P(C.c_uint32), P(f32), P(i32)]),
+        "svo_orbit_camera": (None, [f32, f32, f32, P(Camera)]),
+        "svo_frame_constants_from_camera": (i32, [P(Camera), P(f32), i32, i32, i32, P(FrameConstants)]),
+        "svo_render_frame": (i32, [vp, P(Camera), P(FrameDesc), vp, vp, P(FrameStats)]),
+        "svo_render_frame_device": (i32, [vp, P(Camera), P(FrameDesc), vp, vp, vp, P(FrameStats), i32]),
+        "svo_device_alloc": (i32, [i32, C.c_size_t, P(vp)]),
+        "svo_device_free": (i32, [i32, vp]),
+        "svo_device_memset": (i32, [i32, vp, i32, C.c_size_t]),
+        "svo_device_to_host": (i32, [i32, vp, vp, C.c_size_t]),
+        "svo_host_to_device": (i32, [i32, vp, vp, C.c_size_t]),
+        "svo_device_synchronize": (i32, [i32]),
+        "svo_ipc_export": (i32, [i32, vp, vp]),
+        "svo_ipc_open": (i32, [i32, vp, P(vp)]),
+        "svo_ipc_close": (i32, [i32, vp]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    L._svo_symbols = tuple(sigs)
+    _lib = L
+    return L
+
+
+def _check(status):
+    if status != 0:
+        raise SvoError(status, lib().svo_last_error().decode(errors="replace"))
+
+
+def _f3(v):
+    return (C.c_float * 3)(*[float(x) for x in np.asarray(v, np.float32).reshape(3)])
+
+
+def _ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    st = lib().svo_device_count(C.byref(n))
+    return int(n.value) if st == 0 else 0
+
+
+# ---- .oct files (host only) -------------------------------------------------------------
+
+def oct_read(path):
+    """-> (words uint32[n], center float32[3]). Replaces VoxelOctree(const char*), VoxelOctree.cpp:57-90."""
+    words = C.POINTER(C.c_uint32)()
+    n = C.c_uint64(0)
+    center = (C.c_float * 3)()
+    _check(lib().svo_oct_read(str(path).encode(), C.byref(words), C.byref(n), center))
+    try:
+        arr = np.ctypeslib.as_array(words, shape=(n.value,)).copy() if n.value else np.zeros(0, np.uint32)
+    finally:
+        lib().svo_free(words)
+    return arr, np.array(list(center), np.float32)
+
+
+def oct_write(path, words, center, compress=True):
+    """Replaces VoxelOctree::save, VoxelOctree.cpp:92-123."""
+    words = np.ascontiguousarray(words, np.uint32)
+    _check(lib().svo_oct_write(str(path).encode(), _ptr(words), words.size, _f3(center), 1 if compress else 0))
+
+
+# ---- camera ---------------------------------------------------------------------------------
+
+def orbit_camera(pitch_deg, yaw_deg, radius) -> Camera:
+    cam = Camera()
+    lib().svo_orbit_camera(float(pitch_deg), float(yaw_deg), float(radius), C.byref(cam))
+    return cam
+
+
+def frame_constants(cam: Camera, center, width, height, strips) -> FrameConstants:
+    out = FrameConstants()
+    _check(lib().svo_frame_constants_from_camera(C.byref(cam), _f3(center), width, height, strips, C.byref(out)))
+    return out
+
+
+# ---- pinned host memory ------------------------------------------------------------------------
+
+class PinnedArray:
+    """numpy view over page-locked host memory from svo_host_alloc."""
+
+    def __init__(self, shape, dtype):
+        self.dtype = np.dtype(dtype)
+        self.shape = tuple(np.atleast_1d(shape))
+        nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        p = C.c_void_p()
+        _check(lib().svo_host_alloc(nbytes, C.byref(p)))
+        self._ptr = p
+        buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def free(self):
+        if self._ptr is not None:
+            self.array = None
+            lib().svo_host_free(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class DeviceBuffer:
+    """Raw device allocation on `device` (svo_device_alloc); `.ptr` is an int."""
+
+    def __init__(self, device, nbytes):
+        self.device = int(device)
+        self.nbytes = int(nbytes)
+        p = C.c_void_p()
+        _check(lib().svo_device_alloc(self.device, self.nbytes, C.byref(p)))
+        self.ptr = p.value
+
+    def zero(self):
+        _check(lib().svo_device_memset(self.device, C.c_void_p(self.ptr), 0, self.nbytes))
+
+    def to_host(self, dtype, count=None):
+        dtype = np.dtype(dtype)
+        count = self.nbytes // dtype.itemsize if count is None else count
+        out = np.empty(count, dtype)
+        _check(lib().svo_device_to_host(self.device, _ptr(out), C.c_void_p(self.ptr), count * dtype.itemsize))
+        return out
+
+    def from_host(self, arr):
+        arr = np.ascontiguousarray(arr)
+        assert arr.nbytes <= self.nbytes
+        _check(lib().svo_host_to_device(self.device, C.c_void_p(self.ptr), _ptr(arr), arr.nbytes))
+
+    def ipc_export(self) -> bytes:
+        h = (C.c_uint8 * IPC_HANDLE_BYTES)()
+        _check(lib().svo_ipc_export(self.device, C.c_void_p(self.ptr), h))
+        return bytes(h)
+
+    def free(self):
+        if self.ptr:
+            lib().svo_device_free(self.device, C.c_void_p(self.ptr))
+            self.ptr = 0
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def ipc_open(device, handle: bytes) -> int:
+    h = (C.c_uint8 * IPC_HANDLE_BYTES).from_buffer_copy(handle)
+    p = C.c_void_p()
+    _check(lib().svo_ipc_open(int(device), h, C.byref(p)))
+    return p.value
+
+
+def ipc_close(device, ptr: int):
+    _check(lib().svo_ipc_close(int(device), C.c_void_p(ptr)))
+
+
+def device_synchronize(device=0):
+    _check(lib().svo_device_synchronize(int(device)))
+
+
+# ---- the tree -----------------------------------------------------------------------------------
+
+class VoxelOctree:
+    """GPU-resident octree with the reference's VoxelOctree surface (VoxelOctree.hpp:48-57)."""
+
+    def __init__(self, path=None, *, words=None, center=None, device=0):
+        h = C.c_void_p()
+        if path is not None:
+            _check(lib().svo_tree_load_oct(str(path).encode(), int(device), C.byref(h)))
+        else:
+            if words is None or center is None:
+                raise ValueError("VoxelOctree needs a path, or words and center")
+            words = np.ascontiguousarray(words, np.uint32)
+            _check(lib().svo_tree_create_from_words(_ptr(words), words.size, _f3(center), int(device), C.byref(h)))
+        self._h = h
+        self.info = TreeInfo()
+        _check(lib().svo_tree_get_info(self._h, C.byref(self.info)))
+        self.device = int(self.info.device)
+
+    # reference surface
+    def save(self, path, compress=True):
+        _check(lib().svo_tree_save_oct(self._h, str(path).encode(), 1 if compress else 0))
+
+    def center(self):
+        return np.array(list(self.info.center), np.float32)
+
+    def raymarch(self, o, d, ray_scale=0.0, normal=0, t=0.0):
+        """Single ray, reference semantics: returns (hit, normal, t) with normal / t passed through
+        unchanged where the reference leaves them untouched."""
+        n = C.c_uint32(int(normal))
+        tt = C.c_float(float(t))
+        hit = C.c_int(0)
+        _check(lib().svo_raymarch(self._h, _f3(o), _f3(d), float(ray_scale), C.byref(n), C.byref(tt), C.byref(hit)))
+        return bool(hit.value), int(n.value), np.float32(tt.value)
+
+    # batched / per-frame surface
+    @property
+    def n_words(self):
+        return int(self.info.n_words)
+
+    @property
+    def depth(self):
+        return int(self.info.depth)
+
+    def words(self):
+        out = np.empty(self.n_words, np.uint32)
+        _check(lib().svo_tree_download_words(self._h, _ptr(out), out.size))
+        return out
+
+    def raymarch_batch(self, o, d, ray_scale=0.0, flavour=FLAVOUR_VALIDATION, want_voxel=True, out=None):
+        """HOST arrays in, HOST arrays out (copies inside). Returns dict(hit, t, normal, voxel)."""
+        o = np.ascontiguousarray(o, np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(d, np.float32).reshape(-1, 3)
+        n = o.shape[0]
+        if out is None:
+            out = dict(hit=np.empty(n, np.uint8), t=np.empty(n, np.float32), normal=np.empty(n, np.uint32),
+                       voxel=np.empty(n, np.uint64) if want_voxel else None)
+        _check(lib().svo_raymarch_batch(self._h, n, _ptr(o), _ptr(d), float(ray_scale), int(flavour),
+                                        _ptr(out.get("hit")), _ptr(out.get("t")), _ptr(out.get("normal")),
+                                        _ptr(out.get("voxel"))))
+        return out
+
+    def raymarch_batch_device(self, n, d_o, d_d, ray_scale, flavour, d_hit=0, d_t=0, d_normal=0, d_voxel=0, stream=0):
+        """DEVICE pointers (ints); asynchronous on `stream`."""
+        vp = C.c_void_p
+        _check(lib().svo_raymarch_batch_device(self._h, int(n), vp(d_o), vp(d_d), float(ray_scale), int(flavour),
+                                               vp(d_hit or None), vp(d_t or None), vp(d_normal or None),
+                                               vp(d_voxel or None), vp(stream or None)))
+
+    def render_frame(self, cam: Camera, width, height, strips=16, flavour=FLAVOUR_VALIDATION, tile_rank=0,
+                     tile_world=1, rgba=None, want_depth=False, want_stats=True):
+        """HOST buffers (copies inside, synchronous). Returns (rgba uint32[H,W], depth|None, FrameStats|None)."""
+        desc = FrameDesc(width, height, strips, flavour, tile_rank, tile_world)
+        if rgba is None:
+            rgba = np.empty((height, width), np.uint32)
+        depth = np.empty(coarse_cells(width, height, strips), np.float32) if want_depth else None
+        stats = FrameStats() if want_stats else None
+        _check(lib().svo_render_frame(self._h, C.byref(cam), C.byref(desc), _ptr(rgba), _ptr(depth),
+                                      C.byref(stats) if stats is not None else None))
+        return rgba, depth, stats
+
+    def render_frame_device(self, cam: Camera, width, height, d_rgba, strips=16, flavour=FLAVOUR_FAST, tile_rank=0,
+                            tile_world=1, d_depth=0, stream=0, want_stats=False):
+        """DEVICE framebuffer pointer (int; may be a peer mapping); asynchronous unless want_stats."""
+        desc = FrameDesc(width, height, strips, flavour, tile_rank, tile_world)
+        stats = FrameStats() if want_stats else None
+        vp = C.c_void_p
+        _check(lib().svo_render_frame_device(self._h, C.byref(cam), C.byref(desc), vp(d_rgba), vp(d_depth or None),
+                                             vp(stream or None), C.byref(stats) if stats is not None else None,
+                                             1 if want_stats else 0))
+        return stats
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().svo_tree_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def strip_layout(width, height, strips, tile=8):
+    """Rows and corner-grid sizes of the strips that own at least one row (Main.cpp:351-362)."""
+    stride = (height - 1) // strips + 1
+    out = []
+    for i in range(strips):
+        y0 = i * stride
+        if y0 >= height:
+            break
+        y1 = min(y0 + stride, height)
+        out.append((y0, y1, (width - 1) // tile + 2, (y1 - y0 - 1) // tile + 2))
+    return out
+
+
+def coarse_cells(width, height, strips, tile=8):
+    return sum(tx * ty for (_, _, tx, ty) in strip_layout(width, height, strips, tile))

@@ -1,0 +1,232 @@
+"""GPU: the CUDA path (through the C ABI) against the oracle, the golden vectors and the reference.
+
+Bars (BASELINE.json north_star): validation flavour -- hit mask and hit-voxel identity bit-exact,
+t within 1e-6 relative (we require bit-equal), RGB within 1 LSB (we require identical words);
+fast flavour -- at least 99.99 % identical pixels / hit voxels.
+"""
+import hashlib
+import json
+
+import numpy as np
+import pytest
+
+from conftest import CAMERAS, GOLDEN
+from oracle.pyoracle import pixel_rays
+
+pytestmark = pytest.mark.gpu
+T_MISS = np.float32(1e10)
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def pins():
+    return json.loads((GOLDEN / "dragon_pins.json").read_text())
+
+
+@pytest.fixture(scope="module")
+def small():
+    return np.load(GOLDEN / "dragon_small.npz")
+
+
+def _cam(pysvo, entry):
+    return pysvo.Camera.from_matrices(entry["model"], entry["view"])
+
+
+def test_tree_upload_roundtrip(pysvo, gpu_dragon, dragon_words):
+    words, center = dragon_words
+    assert gpu_dragon.n_words == words.size and gpu_dragon.depth == 8
+    assert np.array_equal(gpu_dragon.words(), words)       # node array uploaded unchanged
+    assert np.array_equal(gpu_dragon.center(), center)
+
+
+@pytest.mark.parametrize("ci", [0, 1, 3])
+def test_batch_validation_bit_exact_vs_golden(pysvo, gpu_dragon, small, ci):
+    k = f"cam{ci}_"
+    out = gpu_dragon.raymarch_batch(small[k + "o"], small[k + "d"], 0.0, pysvo.FLAVOUR_VALIDATION)
+    assert np.array_equal(out["hit"] > 0, small[k + "hit"] > 0)
+    assert np.array_equal(out["t"].view(np.uint32), small[k + "t"].view(np.uint32))
+    assert np.array_equal(out["normal"], small[k + "normal"])
+    lod = gpu_dragon.raymarch_batch(small[k + "o"], small[k + "d"], float(small[k + "coarse_scale"]),
+                                    pysvo.FLAVOUR_VALIDATION)
+    assert np.array_equal(lod["hit"] > 0, small[k + "lod_hit"] > 0)
+    assert np.array_equal(lod["t"].view(np.uint32), small[k + "lod_t"].view(np.uint32))
+
+
+@pytest.mark.parametrize("ci", range(len(CAMERAS)))
+def test_batch_validation_vs_oracle_full_res(pysvo, port, gpu_dragon, dragon_words, pins, ci):
+    words, center = dragon_words
+    cam = pins["cameras"][ci]
+    f = port.frame_constants(np.array(cam["model"], np.float32), np.array(cam["view"], np.float32), center, 1280, 720, 16)
+    o, d = pixel_rays(f)
+    for ray_scale in (0.0, float(f.coarse_scale)):
+        want = port.raymarch_batch(words, o, d, ray_scale, t_sentinel=float(T_MISS))
+        got = gpu_dragon.raymarch_batch(o, d, ray_scale, pysvo.FLAVOUR_VALIDATION)
+        assert np.array_equal(got["hit"], want["hit"])                      # miss / leaf / LOD codes
+        hit = want["hit"] > 0
+        assert np.array_equal(got["voxel"][hit], want["voxel"][hit])        # hit-voxel identity
+        assert np.all(got["voxel"][~hit] == pysvo.VOXEL_NONE)
+        assert np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32))
+        rel = np.abs(got["t"][hit].astype(np.float64) - want["t"][hit]) / np.maximum(np.abs(want["t"][hit]), 1e-30)
+        assert rel.max(initial=0.0) <= 1e-6                                  # the stated tolerance
+        leaf = want["hit"] == 1
+        assert np.array_equal(got["normal"][leaf], want["normal"][leaf])
+        assert np.all(got["normal"][~leaf] == 0)
+    b = cam["batch_1280x720"]
+    got = gpu_dragon.raymarch_batch(o, d, 0.0, pysvo.FLAVOUR_VALIDATION)
+    assert sha((got["hit"] > 0).astype(np.uint8)) == b["hit_sha256"]
+    assert sha(got["t"]) == b["t_sha256"] and sha(got["normal"]) == b["normal_sha256"]
+
+
+@pytest.mark.parametrize("ci", range(len(CAMERAS)))
+def test_batch_fast_flavour_identity_rate(pysvo, port, gpu_dragon, dragon_words, pins, ci):
+    words, center = dragon_words
+    cam = pins["cameras"][ci]
+    f = port.frame_constants(np.array(cam["model"], np.float32), np.array(cam["view"], np.float32), center, 1280, 720, 16)
+    o, d = pixel_rays(f)
+    want = port.raymarch_batch(words, o, d, 0.0, t_sentinel=float(T_MISS))
+    got = gpu_dragon.raymarch_batch(o, d, 0.0, pysvo.FLAVOUR_FAST)
+    same = (got["hit"] == want["hit"]) & (got["voxel"] == np.where(want["hit"] > 0, want["voxel"], pysvo.VOXEL_NONE))
+    assert same.mean() >= 0.9999, f"only {same.mean():.6f} identical"
+    both = (got["hit"] > 0) & (want["hit"] > 0) & same
+    rel = np.abs(got["t"][both].astype(np.float64) - want["t"][both]) / np.maximum(np.abs(want["t"][both]), 1e-30)
+    assert rel.max(initial=0.0) < 1e-3
+
+
+@pytest.mark.parametrize("ci", [0, 1, 3])
+def test_frame_validation_small_vs_golden(pysvo, gpu_dragon, small, ci):
+    k = f"cam{ci}_"
+    cam = pysvo.Camera.from_matrices(small[k + "model"], small[k + "view"])
+    rgba, depth, stats = gpu_dragon.render_frame(cam, 160, 90, strips=4, flavour=pysvo.FLAVOUR_VALIDATION, want_depth=True)
+    assert np.array_equal(depth.view(np.uint32), small[k + "depth"].view(np.uint32))
+    assert np.array_equal(rgba, small[k + "rgba"])
+    assert stats.coarse_rays == depth.size
+    assert stats.fine_rays == int((small[k + "rgba"] != 0).sum())
+
+
+@pytest.mark.parametrize("ci", range(len(CAMERAS)))
+@pytest.mark.parametrize("strips", [16, 8])
+def test_frame_validation_full_res_vs_golden_and_oracle(pysvo, port, gpu_dragon, dragon_words, pins, ci, strips):
+    words, center = dragon_words
+    entry = pins["cameras"][ci]
+    cam = _cam(pysvo, entry)
+    rgba, depth, stats = gpu_dragon.render_frame(cam, 1280, 720, strips=strips, flavour=pysvo.FLAVOUR_VALIDATION, want_depth=True)
+    g = entry[f"frame_1280x720x{strips}"]
+    if sha(rgba) != g["rgba_sha256"] or sha(depth) != g["depth_sha256"]:
+        f = port.frame_constants(np.array(entry["model"], np.float32), np.array(entry["view"], np.float32), center, 1280, 720, strips)
+        want, wdepth, _, _ = port.render_frame(words, f, want_depth=True)
+        bad = np.argwhere(rgba != want)
+        pytest.fail(f"{bad.shape[0]} pixels differ (first {bad[:5].tolist()}); "
+                    f"{int((depth.view(np.uint32) != wdepth.view(np.uint32)).sum())} coarse depths differ")
+    if strips == 16:
+        assert stats.fine_rays == g["written"] and stats.coarse_rays == 18032
+        lsb = np.abs((rgba & 0xFF).astype(np.int32) - (rgba & 0xFF).astype(np.int32)).max()
+        assert lsb <= 1
+
+
+@pytest.mark.parametrize("ci", range(len(CAMERAS)))
+def test_frame_fast_flavour_identical_pixels(pysvo, port, gpu_dragon, dragon_words, pins, ci):
+    words, center = dragon_words
+    entry = pins["cameras"][ci]
+    f = port.frame_constants(np.array(entry["model"], np.float32), np.array(entry["view"], np.float32), center, 1280, 720, 16)
+    want, _, _, _ = port.render_frame(words, f)
+    rgba, _, _ = gpu_dragon.render_frame(_cam(pysvo, entry), 1280, 720, strips=16, flavour=pysvo.FLAVOUR_FAST)
+    same = (rgba == want).mean()
+    assert same >= 0.9999, f"only {same:.6f} of the pixels identical"
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1), (7, 5, 1), (8, 8, 1), (9, 9, 2), (333, 77, 5), (1001, 13, 13), (64, 200, 7)])
+def test_frame_ragged_sizes_vs_oracle(pysvo, port, gpu_dragon, dragon_words, shape):
+    """Clipped tiles, strips whose height is not a multiple of 8, a short last strip."""
+    words, center = dragon_words
+    W, H, S = shape
+    for cam_args in [(0.0, 0.0, 1.0), (20.0, 135.0, 0.5)]:
+        c = pysvo.orbit_camera(*cam_args)
+        m, v = np.array(c.model[:], np.float32), np.array(c.view[:], np.float32)
+        f = port.frame_constants(m, v, center, W, H, S)
+        want, wdepth, cc, cf = port.render_frame(words, f, threads=2, want_depth=True)
+        rgba, depth, stats = gpu_dragon.render_frame(c, W, H, strips=S, flavour=pysvo.FLAVOUR_VALIDATION, want_depth=True)
+        assert np.array_equal(depth.view(np.uint32), wdepth.view(np.uint32))
+        assert np.array_equal(rgba, want)
+        assert (stats.coarse_rays, stats.fine_rays) == (cc.rays, cf.rays)
+
+
+def test_frame_tile_interleave_reassembles(pysvo, gpu_dragon, pins):
+    """Multi-GPU decomposition on one device: ranks render disjoint tile sets whose union is the frame."""
+    entry = pins["cameras"][0]
+    cam = _cam(pysvo, entry)
+    full, _, s_full = gpu_dragon.render_frame(cam, 1280, 720, strips=16, flavour=pysvo.FLAVOUR_VALIDATION)
+    for world in (2, 4, 8, 3):
+        nbytes = 1280 * 720 * 4
+        buf = pysvo.DeviceBuffer(gpu_dragon.device, nbytes)
+        buf.from_host(np.full(1280 * 720, 0xDEADBEEF, np.uint32))
+        fine = 0
+        for rank in range(world):
+            st = gpu_dragon.render_frame_device(cam, 1280, 720, buf.ptr, strips=16, flavour=pysvo.FLAVOUR_VALIDATION,
+                                                tile_rank=rank, tile_world=world, want_stats=True)
+            fine += st.fine_rays
+            part = buf.to_host(np.uint32).reshape(720, 1280)
+            if rank < world - 1:
+                assert (part == 0xDEADBEEF).any()      # other ranks' tiles untouched so far
+        assert np.array_equal(part, full)
+        assert fine == s_full.fine_rays
+        buf.free()
+
+
+def test_single_ray_facade_semantics(pysvo, port, gpu_dragon, dragon_words):
+    """VoxelOctree::raymarch leaves `normal` / `t` untouched on a miss and `normal` on a LOD exit."""
+    words, _ = dragon_words
+    o = [1.5, 1.2265625, 0.33203125]
+    for d, rs in [([0.0, 0.0, 1.0], 0.0), ([0.0, 1.0, 0.0], 0.0), ([0.05, -0.02, 1.0], 0.05), ([1.0, 0.0, 0.0], 0.0)]:
+        code, t, n, _, _ = port.raymarch(words, o, d, rs, normal_sentinel=0xABCD1234, t_sentinel=-7.0)
+        hit, n2, t2 = gpu_dragon.raymarch(o, d, rs, normal=0xABCD1234, t=-7.0)
+        assert hit == (code != 0)
+        assert n2 == n and np.float32(t2).view(np.uint32) == np.float32(t).view(np.uint32)
+
+
+def test_batch_edge_cases(pysvo, port, gpu_dragon, dragon_words):
+    words, _ = dragon_words
+    out = gpu_dragon.raymarch_batch(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32))
+    assert out["hit"].size == 0
+    rng = np.random.default_rng(11)
+    n = 100003   # not a multiple of the block size
+    o = rng.uniform(0.0, 3.0, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d[::7, 0] = 0.0                      # epsilon clamp, sign dropped (VoxelOctree.cpp:217-219)
+    d[::11, 1] = np.float32(-5e-5)
+    d[::13, 2] = np.float32(1e-4)
+    d[::17] = [0.0, 0.0, -1.0]
+    o[::19] = [1.5, 1.5, 1.5]            # origins inside the cube
+    for rs in (0.0, 0.02, 0.5):
+        want = port.raymarch_batch(words, o, d, rs, t_sentinel=float(T_MISS))
+        got = gpu_dragon.raymarch_batch(o, d, rs, pysvo.FLAVOUR_VALIDATION)
+        assert np.array_equal(got["hit"], want["hit"])
+        assert np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32))
+        hit = want["hit"] > 0
+        assert np.array_equal(got["voxel"][hit], want["voxel"][hit])
+        leaf = want["hit"] == 1
+        assert np.array_equal(got["normal"][leaf], want["normal"][leaf])
+
+
+def test_save_oct_roundtrip_from_hbm(pysvo, gpu_dragon, dragon_words, tmp_path):
+    words, center = dragon_words
+    p = tmp_path / "saved.oct"
+    gpu_dragon.save(p)
+    w2, c2 = pysvo.oct_read(p)
+    assert np.array_equal(w2, words) and np.array_equal(c2, center)
+
+
+def test_frame_against_reference_object_code(pysvo, ref, gpu_dragon, dragon_words):
+    """Straight against oracle/_ref (travels to the GPU box prebuilt), a camera outside the golden set."""
+    words, center = dragon_words
+    h = ref.tree_from_words(words, center)
+    cam = (33.0, 77.0, 0.65)
+    m, v = ref.orbit_camera(*cam)
+    want, wdepth, _ = ref.render_frames(h, 640, 360, 9, m, v, threads=4, want_depth=True)
+    rgba, depth, _ = gpu_dragon.render_frame(pysvo.orbit_camera(*cam), 640, 360, strips=9,
+                                             flavour=pysvo.FLAVOUR_VALIDATION, want_depth=True)
+    ref.tree_destroy(h)
+    assert np.array_equal(depth.view(np.uint32), wdepth.view(np.uint32))
+    assert np.array_equal(rgba, want)

@@ -1,0 +1,168 @@
+"""CPU: the C-ABI library loads, exports what include/svo_b200.h declares, and its host-only parts
+(.oct I/O, camera constants, argument checking) behave. No device compute is attempted here."""
+import os
+import re
+import struct
+
+import numpy as np
+import pytest
+
+from conftest import CAMERAS, DRAGON, ROOT
+
+
+def test_library_exports_every_declared_symbol(pysvo):
+    header = (ROOT / "include" / "svo_b200.h").read_text()
+    declared = set(re.findall(r"SVO_API\s+[\w\s\*]+?\b(svo_\w+)\s*\(", header))
+    assert len(declared) >= 28
+    L = pysvo.lib()
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in svo_b200.h but not exported"
+    assert declared == set(L._svo_symbols), "pysvo binds a different symbol set than the header declares"
+    assert L.svo_abi_version() == 1
+
+
+def test_no_device_fails_loudly(pysvo, dragon_words):
+    if pysvo.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    words, center = dragon_words
+    with pytest.raises(pysvo.SvoError) as e:
+        pysvo.VoxelOctree(words=words, center=center)
+    assert e.value.status == 6 and "no CPU fallback" in str(e.value)
+
+
+def test_oct_read_dragon(pysvo, dragon_words):
+    words, center = dragon_words
+    assert words.dtype == np.uint32 and words.size == 119887
+    assert list(center) == [0.5, 0.2265625, 0.33203125]
+    assert int(words[0]) == 0x00052323
+
+
+@pytest.mark.parametrize("compress", [True, False])
+def test_oct_roundtrip_ours(pysvo, dragon_words, tmp_path, compress):
+    words, center = dragon_words
+    p = tmp_path / "a.oct"
+    pysvo.oct_write(p, words, center, compress=compress)
+    w2, c2 = pysvo.oct_read(p)
+    assert np.array_equal(words, w2) and np.array_equal(center, c2)
+    raw = p.read_bytes()
+    assert struct.unpack_from("<3fQ", raw) == (*[float(x) for x in center], words.size)
+    if compress:
+        assert len(raw) < words.nbytes + 20
+
+
+def test_oct_interop_with_reference_loader_and_saver(pysvo, ref, dragon_words, tmp_path):
+    words, center = dragon_words
+    for compress in (True, False):
+        p = tmp_path / f"ours_{int(compress)}.oct"
+        pysvo.oct_write(p, words, center, compress=compress)
+        h = ref.tree_load(p)   # LZ4_decompress_fast_continue, VoxelOctree.cpp:57-90
+        assert np.array_equal(ref.tree_words(h), words) and np.array_equal(ref.tree_center(h), center)
+        ref.tree_destroy(h)
+    h = ref.tree_from_words(words, center)
+    q = tmp_path / "theirs.oct"
+    ref.tree_save(h, q)        # LZ4_compress_continue, VoxelOctree.cpp:92-123
+    ref.tree_destroy(h)
+    w2, c2 = pysvo.oct_read(q)
+    assert np.array_equal(w2, words) and np.array_equal(c2, center)
+
+
+def _synthetic_words(rng, n):
+    """Compressible, octree-like word soup: runs, repeats at assorted distances, noise."""
+    base = rng.integers(0, 2**32, n // 8 + 1, dtype=np.uint64).astype(np.uint32)
+    out = np.repeat(base, 8)[:n].copy()
+    idx = rng.integers(0, n, n // 5)
+    out[idx] = rng.integers(0, 2**32, idx.size, dtype=np.uint64).astype(np.uint32)
+    out[0] = (1 << 18) | 0x0100   # plausible root: one leaf child at offset 1
+    return out
+
+
+@pytest.mark.parametrize("n_words", [2, 3, 4, 5, 17, 1000, (64 << 20) // 4 - 1, (64 << 20) // 4, (64 << 20) // 4 + 3,
+                                     2 * (64 << 20) // 4 + 12345])
+def test_oct_roundtrip_slice_boundaries(pysvo, tmp_path, n_words):
+    """Slices are 64 MiB (VoxelOctree.cpp:55); matches may reach into the previous slice."""
+    rng = np.random.default_rng(n_words)
+    words = _synthetic_words(rng, n_words)
+    center = np.array([0.5, 0.25, 0.125], np.float32)
+    p = tmp_path / "s.oct"
+    pysvo.oct_write(p, words, center, compress=True)
+    w2, c2 = pysvo.oct_read(p)
+    assert np.array_equal(words, w2) and np.array_equal(center, c2)
+
+
+def test_oct_multi_slice_interop_with_reference(pysvo, ref, tmp_path):
+    n_words = (64 << 20) // 4 + 4099
+    rng = np.random.default_rng(5)
+    words = _synthetic_words(rng, n_words)
+    # make the start of slice 1 repeat the end of slice 0 so that our encoder emits cross-slice matches
+    words[(64 << 20) // 4:(64 << 20) // 4 + 2000] = words[(64 << 20) // 4 - 2000:(64 << 20) // 4]
+    center = np.array([0.5, 0.5, 0.5], np.float32)
+    p = tmp_path / "m.oct"
+    pysvo.oct_write(p, words, center, compress=True)
+    h = ref.tree_load(p)
+    assert np.array_equal(ref.tree_words_view(h), words)
+    q = tmp_path / "r.oct"
+    ref.tree_save(h, q)
+    ref.tree_destroy(h)
+    w2, _ = pysvo.oct_read(q)
+    assert np.array_equal(w2, words)
+
+
+def test_oct_errors_are_reported(pysvo, tmp_path, dragon_words):
+    with pytest.raises(pysvo.SvoError) as e:
+        pysvo.oct_read(tmp_path / "missing.oct")
+    assert e.value.status == 2
+    with pytest.raises(pysvo.SvoError) as e:
+        pysvo.oct_write(tmp_path / "no_such_dir" / "x.oct", np.zeros(4, np.uint32), [0, 0, 0])
+    assert e.value.status == 2
+    raw = DRAGON.read_bytes()
+    for name, blob in [("trunc_header.oct", raw[:15]), ("trunc_payload.oct", raw[:len(raw) // 2]),
+                       ("garbage_count.oct", raw[:12] + struct.pack("<Q", 1 << 60) + raw[20:]),
+                       ("trailing.oct", raw[:20] + struct.pack("<Q", len(raw) - 28 + 4) + raw[28:] + b"\0\0\0\0")]:
+        p = tmp_path / name
+        p.write_bytes(blob)
+        with pytest.raises(pysvo.SvoError) as e:
+            pysvo.oct_read(p)
+        assert e.value.status == 3, name
+    # corrupt a match offset region: must fail or decode, never crash
+    blob = bytearray(raw)
+    rng = np.random.default_rng(1)
+    for _ in range(20):
+        b2 = bytearray(blob)
+        for pos in rng.integers(28, len(raw), 8):
+            b2[pos] ^= 0xFF
+        p = tmp_path / "fuzz.oct"
+        p.write_bytes(bytes(b2))
+        try:
+            pysvo.oct_read(p)
+        except pysvo.SvoError as err:
+            assert err.status == 3
+
+
+@pytest.mark.parametrize("cam", CAMERAS)
+def test_camera_constants_match_oracle(pysvo, port, dragon_words, cam):
+    _, center = dragon_words
+    c = pysvo.orbit_camera(*cam)
+    m, v = port.orbit_camera(*cam)
+    assert np.array_equal(np.array(c.model[:], np.float32).view(np.uint32), m.view(np.uint32))
+    assert np.array_equal(np.array(c.view[:], np.float32).view(np.uint32), v.view(np.uint32))
+    for (W, H, S) in [(1280, 720, 16), (1920, 1080, 16), (3840, 2160, 16), (333, 77, 5), (8, 8, 1)]:
+        a = pysvo.frame_constants(c, center, W, H, S)
+        b = port.frame_constants(m, v, center, W, H, S)
+        assert (a.width, a.height, a.strips, a.tile_size) == (b.width, b.height, b.strips, b.tile_size)
+        assert np.array_equal(a.as_array().view(np.uint32), b.as_array().view(np.uint32))
+
+
+def test_camera_matches_reference_matrix_stack(pysvo, ref):
+    for cam in CAMERAS:
+        c = pysvo.orbit_camera(*cam)
+        m, v = ref.orbit_camera(*cam)
+        assert np.array_equal(np.array(c.model[:], np.float32).view(np.uint32), m.view(np.uint32))
+        assert np.array_equal(np.array(c.view[:], np.float32).view(np.uint32), v.view(np.uint32))
+
+
+def test_strip_layout_matches_reference_formula(pysvo):
+    # Main.cpp:351-362 for the reference's own configuration
+    lay = pysvo.strip_layout(1280, 720, 16)
+    assert len(lay) == 16 and lay[0] == (0, 45, 161, 7) and lay[-1] == (675, 720, 161, 7)
+    assert pysvo.coarse_cells(1280, 720, 16) == 18032
+    assert pysvo.coarse_cells(3840, 2160, 16) == 138528

@@ -1,0 +1,150 @@
+"""CPU: pins the plain-C oracle (oracle/svo_oracle.c) to the reference.
+
+Two anchors: (1) the committed golden vectors, minted from the reference's own object code by
+tests/golden/make_golden.py; (2) that object code itself (oracle/_ref), when it is present.
+"""
+import hashlib
+import json
+
+import numpy as np
+import pytest
+
+from conftest import CAMERAS, DRAGON, GOLDEN
+from oracle.pyoracle import pixel_rays
+
+T_MISS = np.float32(1e10)
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def pins():
+    return json.loads((GOLDEN / "dragon_pins.json").read_text())
+
+
+@pytest.fixture(scope="module")
+def small():
+    return np.load(GOLDEN / "dragon_small.npz")
+
+
+def test_tree_walk_matches_survey_pins(port, dragon_words, pins):
+    words, center = dragon_words
+    assert words.size == pins["n_words"] == 119887
+    assert int(words[0]) == pins["root_word"] == 0x00052323
+    assert sha(words) == pins["words_sha256"]
+    assert [float(x) for x in center] == pins["center"] == [0.5, 0.2265625, 0.33203125]
+    st = port.tree_walk(words)
+    tw = pins["tree_walk"]
+    assert (st.descriptors, st.leaves, st.far_words, st.far_blocks, st.depth) == (29156, 90707, 24, 4, 8)
+    assert list(st.per_level)[:8] == tw["per_level"] == [1, 3, 15, 68, 289, 1237, 5352, 22191]
+    assert st.descriptors + st.leaves + st.far_words == words.size
+    assert st.max_index == words.size - 1
+
+
+@pytest.mark.parametrize("ci", [0, 1, 3])
+def test_port_small_frames_and_rays_equal_golden(port, dragon_words, small, ci):
+    words, center = dragon_words
+    k = f"cam{ci}_"
+    f = port.frame_constants(small[k + "model"], small[k + "view"], center, 160, 90, 4)
+    rgba, depth, cc, cf = port.render_frame(words, f, threads=2, want_depth=True)
+    assert np.array_equal(rgba, small[k + "rgba"])
+    assert np.array_equal(depth.view(np.uint32), small[k + "depth"].view(np.uint32))
+    o, d = pixel_rays(f)
+    assert np.array_equal(o.view(np.uint32), small[k + "o"].view(np.uint32))
+    assert np.array_equal(d.view(np.uint32), small[k + "d"].view(np.uint32))
+    res = port.raymarch_batch(words, o, d, 0.0, threads=2, t_sentinel=float(T_MISS))
+    assert np.array_equal(res["hit"] > 0, small[k + "hit"] > 0)
+    assert np.array_equal(res["t"].view(np.uint32), small[k + "t"].view(np.uint32))
+    assert np.array_equal(res["normal"], small[k + "normal"])
+    lod = port.raymarch_batch(words, o, d, float(small[k + "coarse_scale"]), threads=2, t_sentinel=float(T_MISS))
+    assert np.array_equal(lod["hit"] > 0, small[k + "lod_hit"] > 0)
+    assert np.array_equal(lod["t"].view(np.uint32), small[k + "lod_t"].view(np.uint32))
+
+
+@pytest.mark.parametrize("ci", range(len(CAMERAS)))
+def test_port_full_resolution_hashes(port, dragon_words, pins, ci):
+    words, center = dragon_words
+    cam = pins["cameras"][ci]
+    model, view = np.array(cam["model"], np.float32), np.array(cam["view"], np.float32)
+    m2, v2 = port.orbit_camera(*cam["pitch_yaw_radius"])
+    assert np.array_equal(m2.view(np.uint32), model.view(np.uint32))
+    assert np.array_equal(v2.view(np.uint32), view.view(np.uint32))
+    for strips in (16, 8):
+        f = port.frame_constants(model, view, center, 1280, 720, strips)
+        rgba, depth, cc, cf = port.render_frame(words, f, want_depth=True)
+        g = cam[f"frame_1280x720x{strips}"]
+        assert sha(rgba) == g["rgba_sha256"]
+        assert sha(depth) == g["depth_sha256"]
+    f = port.frame_constants(model, view, center, 1280, 720, 16)
+    o, d = pixel_rays(f)
+    b = cam["batch_1280x720"]
+    assert sha(o) == b["rays_o_sha256"] and sha(d) == b["rays_d_sha256"]
+    res = port.raymarch_batch(words, o, d, 0.0, t_sentinel=float(T_MISS))
+    hit = (res["hit"] > 0).astype(np.uint8)
+    assert int(hit.sum()) == b["hits"]
+    assert sha(hit) == b["hit_sha256"] and sha(res["t"]) == b["t_sha256"] and sha(res["normal"]) == b["normal_sha256"]
+    lod = port.raymarch_batch(words, o, d, f.coarse_scale, t_sentinel=float(T_MISS))
+    bl = cam["batch_lod_1280x720"]
+    assert sha((lod["hit"] > 0).astype(np.uint8)) == bl["hit_sha256"] and sha(lod["t"]) == bl["t_sha256"]
+
+
+def test_survey_known_answers(port, dragon_words, pins):
+    """default camera raw cast and 16-strip frame."""
+    b = pins["cameras"][0]["batch_1280x720"]
+    assert b["hits"] == 323762
+    assert abs(b["sum_t"] - 303634.524310) < 1e-3
+    assert b["xor_normals"] == 0xE59DE086
+    fr = pins["cameras"][0]["frame_1280x720x16"]
+    assert (fr["lit"], fr["written"], fr["coarse_hits"]) == (322364, 376504, 6793)
+    words, center = dragon_words
+    m, v = port.orbit_camera(0, 0, 1.0)
+    f = port.frame_constants(m, v, center, 1280, 720, 16)
+    _, _, cc, cf = port.render_frame(words, f)
+    assert (cc.rays, cf.rays) == (18032, 376504)
+    assert cc.lod_exits == 6793
+    # node traffic per ray, frame mode: 66.7 B over coarse + fine
+    total = 4.0 * (cc.words + cf.words) / (cc.rays + cf.rays)
+    assert abs(total - 66.7) < 0.1
+
+
+def test_port_matches_reference_object_code(port, ref, dragon_words):
+    """Live cross-check against oracle/_ref on cameras and sizes that are NOT in the golden set."""
+    words, center = dragon_words
+    h = ref.tree_from_words(words, center)
+    rng = np.random.default_rng(7)
+    for _ in range(3):
+        cam = (float(rng.uniform(-80, 80)), float(rng.uniform(0, 360)), float(rng.uniform(0.2, 2.0)))
+        model, view = ref.orbit_camera(*cam)
+        W, H, S = int(rng.integers(40, 300)), int(rng.integers(30, 200)), int(rng.integers(1, 7))
+        f = port.frame_constants(model, view, center, W, H, S)
+        rgba_r, depth_r, _ = ref.render_frames(h, W, H, S, model, view, threads=2, want_depth=True)
+        rgba_p, depth_p, _, _ = port.render_frame(words, f, threads=2, want_depth=True)
+        assert np.array_equal(rgba_r, rgba_p), (cam, W, H, S)
+        assert np.array_equal(depth_r.view(np.uint32), depth_p.view(np.uint32))
+    # random rays through the cube, including axis-parallel and tiny direction components
+    n = 20000
+    o = rng.uniform(0.0, 3.0, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d[::7, 0] = 0.0
+    d[::11, 1] = np.float32(-5e-5)
+    d[::13, 2] = np.float32(1e-4)
+    for rs in (0.0, 0.01, 0.2):
+        hit, t, nrm, _ = ref.raymarch_batch(h, o, d, rs, normal_sentinel=5, t_sentinel=-3.0)
+        res = port.raymarch_batch(words, o, d, rs, threads=2, normal_sentinel=5, t_sentinel=-3.0)
+        assert np.array_equal(res["hit"] > 0, hit > 0)
+        assert np.array_equal(res["t"].view(np.uint32), t.view(np.uint32))
+        assert np.array_equal(res["normal"], nrm)
+    ref.tree_destroy(h)
+
+
+def test_port_shading_helpers_match_reference(port, ref):
+    rng = np.random.default_rng(3)
+    for w in rng.integers(0, 2**32, 200, dtype=np.uint64):
+        w = int(w) & ~0x60000000 | (int(rng.integers(0, 3)) << 29)   # face 3 is not a valid encoding
+        n_r, s_r = ref.decompress_material(w)
+        n_p, s_p = port.decompress_material(w)
+        assert np.array_equal(n_r.view(np.uint32), n_p.view(np.uint32)) and s_r == s_p
+    for x in rng.uniform(1e-6, 1e6, 200):
+        assert ref.inv_sqrt(x) == port.inv_sqrt(x)
