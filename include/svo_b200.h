@@ -55,10 +55,12 @@ typedef enum svo_status {
  * VALIDATION: every float op individually rounded (no FMA contraction, IEEE
  *   divide, the reference's (a<b)?b:a min/max forms): hit mask and hit voxel
  *   bit-exact against the reference built with -ffp-contract=off.
- * FAST: the traversal's a*b+-c expressions are single FMAs, min/max are
- *   FMNMX; ray generation and shading stay individually rounded so that a
- *   pixel differs only if the ray reaches a different voxel (>= 99.99 %
- *   identical pixels). */
+ * FAST: the fine-pass / batch traversal uses single FMAs wherever the product
+ *   is exact (power-of-two factor) and FMNMX for min/max. The per-iteration
+ *   corner planes pos*dT - bT stay two roundings: fusing them moved 0.017 % of
+ *   the pixels to a neighbouring voxel in measurement, over the 0.01 % budget.
+ *   Ray generation, shading and the beam (coarse) pass are individually
+ *   rounded in both flavours. Bar: >= 99.99 % identical pixels. */
 typedef enum svo_flavour { SVO_FLAVOUR_VALIDATION = 0, SVO_FLAVOUR_FAST = 1 } svo_flavour;
 
 /* Ray result codes written to `hit[]`. Non-zero == the reference's `true`. */
@@ -182,6 +184,8 @@ typedef struct svo_frame_stats {
     uint64_t tiles_total;       /* tiles owned by this rank */
     uint32_t kernel_launches;   /* kernels this call put on the stream */
     uint32_t reserved;
+    float coarse_ms;            /* device time of the beam-pass kernel (CUDA events on the call's stream) */
+    float fine_ms;              /* device time of the fine-pass kernel */
 } svo_frame_stats;
 
 /* Host-buffer variant: rgba (width*height uint32, the reference's backBuffer

@@ -103,6 +103,9 @@ class Ref:
         L.svoref_render_frames.restype = C.c_int
         L.svoref_render_frames.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _f32p, C.c_int,
                                            _u32p, C.c_void_p, C.c_void_p]
+        L.svoref_render_frames_subset.restype = C.c_int
+        L.svoref_render_frames_subset.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _f32p,
+                                                  C.c_int, _u32p, C.c_void_p, C.c_void_p]
         L.svoref_hardware_threads.restype = C.c_int
 
     # -- trees
@@ -193,8 +196,9 @@ class Ref:
         return hit, t, normal, secs
 
     # -- frame loop
-    def render_frames(self, h, W, H, strips, models, views, threads=None, want_depth=False):
-        """Renders len(models) frames; returns (rgba u32[H,W] of the last frame, depth or None, seconds[f])."""
+    def render_frames(self, h, W, H, strips, models, views, threads=None, want_depth=False, strip_modulo=1):
+        """Renders len(models) frames; returns (rgba u32[H,W] of the last frame, depth or None, seconds[f]).
+        strip_modulo > 1 renders only every strip_modulo-th strip (bounded timing sample)."""
         models = np.ascontiguousarray(models, np.float32).reshape(-1, 16)
         views = np.ascontiguousarray(views, np.float32).reshape(-1, 16)
         nf = models.shape[0]
@@ -205,8 +209,8 @@ class Ref:
         depth = None
         if want_depth:
             depth = np.zeros(coarse_cells(W, H, strips), np.float32)
-        rc = self.lib.svoref_render_frames(h, W, H, strips, nf, models, views, int(threads), rgba.reshape(-1),
-                                           _null_or(depth), _null_or(secs))
+        rc = self.lib.svoref_render_frames_subset(h, W, H, strips, int(strip_modulo), nf, models, views, int(threads),
+                                                  rgba.reshape(-1), _null_or(depth), _null_or(secs))
         if rc != 0:
             raise ValueError("svoref_render_frames: bad arguments")
         return rgba, depth, secs

@@ -263,8 +263,19 @@ void svoref_inv_modelview(const float *model16, const float *view16, float *out1
  * tilesX*tilesY floats laid out strip after strip) the last coarse buffer;
  * `frameSeconds[k]` the wall time of the parallel section of frame k
  * (BASELINE.md section 3.3). Returns 0, or -1 on bad arguments. */
+int svoref_render_frames_subset(void *h, int W, int H, int strips, int stripModulo, int numFrames, const float *models,
+        const float *views, int threads, uint32_t *rgba, float *depth, double *frameSeconds);
+
 int svoref_render_frames(void *h, int W, int H, int strips, int numFrames, const float *models,
         const float *views, int threads, uint32_t *rgba, float *depth, double *frameSeconds) {
+    return svoref_render_frames_subset(h, W, H, strips, 1, numFrames, models, views, threads, rgba, depth, frameSeconds);
+}
+
+/* Same, but only strips s with s % stripModulo == 0 are rendered (a bounded
+ * sample of the frame for timing; the other rows of `rgba` are left alone). */
+int svoref_render_frames_subset(void *h, int W, int H, int strips, int stripModulo, int numFrames, const float *models,
+        const float *views, int threads, uint32_t *rgba, float *depth, double *frameSeconds) {
+    if (stripModulo < 1) return -1;
     if (!h || W < 1 || H < 1 || strips < 1 || numFrames < 1 || !rgba) return -1;
     VoxelOctree *tree = static_cast<VoxelOctree *>(h);
     if (threads < 1) threads = 1;
@@ -319,7 +330,7 @@ int svoref_render_frames(void *h, int W, int H, int strips, int numFrames, const
             for (;;) {
                 int s = nextStrip.fetch_add(1);
                 if (s >= strips) break;
-                if (td[s].y0 < td[s].y1)
+                if (td[s].y0 < td[s].y1 && s % stripModulo == 0)
                     renderBatch(&td[s]);
             }
             barrier.wait();

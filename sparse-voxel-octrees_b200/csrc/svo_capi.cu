@@ -102,6 +102,7 @@ struct svo_tree {
     cudaStream_t stream = nullptr;          // for the host-buffer entry points
     svo::FrameCounters *dCounters = nullptr;
     svo::FrameCounters *hCounters = nullptr; // pinned
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr}; // coarse start | fine start | fine end (stats only)
     std::mutex mutex;
     std::map<std::tuple<int, int, int>, FramePlan> plans;
     GrowBuffer batchIn, batchOut;
@@ -170,6 +171,7 @@ int createTree(const uint32_t *words, uint64_t nWords, const float center[3], in
         if (tree->dCounters) cudaFree(tree->dCounters);
         if (tree->hCounters) cudaFreeHost(tree->hCounters);
         if (tree->stream) cudaStreamDestroy(tree->stream);
+        for (int i = 0; i < 3; ++i) if (tree->ev[i]) cudaEventDestroy(tree->ev[i]);
         return failCuda(err, what);
     };
     if ((e = cudaMalloc(&tree->dWords, bytes)) != cudaSuccess) return cleanup(e, "cudaMalloc(node array)");
@@ -179,6 +181,8 @@ int createTree(const uint32_t *words, uint64_t nWords, const float center[3], in
     if ((e = cudaStreamCreateWithFlags(&tree->stream, cudaStreamNonBlocking)) != cudaSuccess) return cleanup(e, "cudaStreamCreate");
     if ((e = cudaMalloc(&tree->dCounters, sizeof(svo::FrameCounters))) != cudaSuccess) return cleanup(e, "cudaMalloc(counters)");
     if ((e = cudaMallocHost(&tree->hCounters, sizeof(svo::FrameCounters))) != cudaSuccess) return cleanup(e, "cudaMallocHost(counters)");
+    for (int i = 0; i < 3; ++i)
+        if ((e = cudaEventCreate(&tree->ev[i])) != cudaSuccess) return cleanup(e, "cudaEventCreate");
     *out = tree.release();
     return SVO_OK;
 }
@@ -289,12 +293,15 @@ int enqueueFrame(svo_tree *tree, FramePlan *plan, const svo_camera *cam, const s
     svo::FrameConsts f = toDeviceConsts(c);
     float *depth = dDepth ? dDepth : plan->dDepth;
     uint32_t n = 0;
+    if (wantStats) SVO_CUDA(cudaEventRecord(tree->ev[0], stream));
     SVO_CUDA(svo::launchCoarsePass(tree->dev(), plan->dev, f, desc->flavour, depth, stream));
     ++n;
+    if (wantStats) SVO_CUDA(cudaEventRecord(tree->ev[1], stream));
     SVO_CUDA(svo::launchFinePass(tree->dev(), plan->dev, f, desc->flavour, depth, dRgba, desc->tile_rank,
                                  desc->tile_world, stream));
     ++n;
     if (wantStats) {
+        SVO_CUDA(cudaEventRecord(tree->ev[2], stream));
         SVO_CUDA(cudaMemsetAsync(tree->dCounters, 0, sizeof(svo::FrameCounters), stream));
         SVO_CUDA(svo::launchTileStats(plan->dev, depth, desc->tile_rank, desc->tile_world, tree->dCounters, stream));
         ++n;
@@ -312,6 +319,9 @@ void fillStats(const svo_tree *tree, const FramePlan *plan, const svo_frame_desc
     stats->tiles_total = owned > 0 ? uint64_t(owned) : 0;
     stats->kernel_launches = launches;
     stats->reserved = 0;
+    stats->coarse_ms = stats->fine_ms = 0.0f;
+    cudaEventElapsedTime(&stats->coarse_ms, tree->ev[0], tree->ev[1]);   // events completed: caller synchronised
+    cudaEventElapsedTime(&stats->fine_ms, tree->ev[1], tree->ev[2]);
 }
 
 } // namespace
@@ -432,6 +442,7 @@ int svo_tree_destroy(svo_tree *tree) {
         if (tree->dCounters) cudaFree(tree->dCounters);
         if (tree->hCounters) cudaFreeHost(tree->hCounters);
         if (tree->stream) cudaStreamDestroy(tree->stream);
+        for (int i = 0; i < 3; ++i) if (tree->ev[i]) cudaEventDestroy(tree->ev[i]);
     }
     delete tree;
     return SVO_OK;

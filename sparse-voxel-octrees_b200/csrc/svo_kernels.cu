@@ -246,10 +246,12 @@ cudaError_t launchRaymarchBatch(const TreeDev &tree, uint64_t n, const float *o,
 
 cudaError_t launchCoarsePass(const TreeDev &tree, const FramePlanDev &plan, const FrameConsts &consts, int flavour,
                              float *depth, cudaStream_t stream) {
+    // The beam pass is individually rounded in BOTH flavours: its depths feed
+    // `minT - 0.03` (Main.cpp:197) and the tile-skip test (Main.cpp:191), so a
+    // last-bit change here moves every ray origin of a tile or drops / adds a
+    // whole tile. It is < 5 % of the rays; FAST only changes the fine pass.
+    (void)flavour;
     bool wide = tree.nWords >= (1ull << 32);
-    if (flavour != 0)
-        return wide ? launchCoarseT<true, uint64_t>(tree, plan, consts, depth, stream)
-                    : launchCoarseT<true, uint32_t>(tree, plan, consts, depth, stream);
     return wide ? launchCoarseT<false, uint64_t>(tree, plan, consts, depth, stream)
                 : launchCoarseT<false, uint32_t>(tree, plan, consts, depth, stream);
 }

@@ -69,7 +69,8 @@ class FrameDesc(C.Structure):
 
 class FrameStats(C.Structure):
     _fields_ = [("coarse_rays", C.c_uint64), ("fine_rays", C.c_uint64), ("tiles_rendered", C.c_uint64),
-                ("tiles_total", C.c_uint64), ("kernel_launches", C.c_uint32), ("reserved", C.c_uint32)]
+                ("tiles_total", C.c_uint64), ("kernel_launches", C.c_uint32), ("reserved", C.c_uint32),
+                ("coarse_ms", C.c_float), ("fine_ms", C.c_float)]
 
     @property
     def rays(self):
