@@ -55,7 +55,7 @@ def pick_workload(name):
         w = dict(WORKLOADS[name], name=name)
     else:
         for cand in ("c3_ico8192_4k", "c2_sdf2048_1080p"):
-            if make_scenes.scene_path(WORKLOADS[cand]["scene"]).exists():
+            if make_scenes.scene_available(WORKLOADS[cand]["scene"]):
                 w = dict(WORKLOADS[cand], name=cand)
                 break
         else:
@@ -69,7 +69,15 @@ def ensure_scene(w, rank, barrier):
     if not Path(w["path"]).exists():
         if rank == 0:
             from tools import make_scenes
-            make_scenes.make_scene(w["scene"], verbose=False)
+            if make_scenes.packed_path(w["scene"]).exists():
+                # transport sidecar (snapshot size cap): same words, xz chunks -> literal-only .oct on local disk
+                import pysvo
+                words, center = make_scenes.unpack_scene(w["scene"])
+                pysvo.oct_write(str(w["path"]) + ".tmp", words, center, compress=False)
+                os.replace(str(w["path"]) + ".tmp", w["path"])
+                del words
+            else:
+                make_scenes.make_scene(w["scene"], verbose=False)
     barrier()
 
 

@@ -110,6 +110,79 @@ def make_scene(name: str, scratch: str | None = None, verbose: bool = True) -> P
     return out
 
 
+# ---- transport: gpurun snapshots are capped at 512 MiB and the 8192^3 .oct is 749 MB (LZ4 only halves
+# it), so big scenes also get a sidecar with the same words in independently xz-compressed chunks
+# (~0.22 of raw). Pure transport tooling: the words are the reference builder's, bit for bit.
+XZ_CHUNK_WORDS = 16 << 20
+
+
+def packed_path(name: str) -> Path:
+    return CACHE / f"{name}.words.xz"
+
+
+def pack_scene(name: str, workers: int | None = None) -> Path:
+    """scenes/_cache/<name>.oct -> <name>.words.xz (header JSON line, then length-prefixed xz chunks)."""
+    import lzma
+    import struct
+    from concurrent.futures import ThreadPoolExecutor
+    import numpy as np
+    sys.path.insert(0, str(ROOT / "sparse-voxel-octrees_b200"))
+    import pysvo
+    words, center = pysvo.oct_read(scene_path(name))
+    chunks = [words[i:i + XZ_CHUNK_WORDS] for i in range(0, words.size, XZ_CHUNK_WORDS)]
+    with ThreadPoolExecutor(workers or os.cpu_count() or 1) as ex:
+        blobs = list(ex.map(lambda c: lzma.compress(c.tobytes(), preset=1), chunks))
+    out = packed_path(name)
+    with open(str(out) + ".tmp", "wb") as fp:
+        header = json.dumps({"n_words": int(words.size), "center": [float(x) for x in center],
+                             "chunk_words": XZ_CHUNK_WORDS, "chunks": len(blobs)}).encode()
+        fp.write(struct.pack("<I", len(header)) + header)
+        for b in blobs:
+            fp.write(struct.pack("<Q", len(b)) + b)
+    os.replace(str(out) + ".tmp", out)
+    return out
+
+
+def unpack_scene(name: str, workers: int | None = None):
+    """-> (words uint32[n], center float32[3]) from the xz sidecar."""
+    import lzma
+    import struct
+    from concurrent.futures import ThreadPoolExecutor
+    import numpy as np
+    with open(packed_path(name), "rb") as fp:
+        (hl,) = struct.unpack("<I", fp.read(4))
+        header = json.loads(fp.read(hl))
+        blobs = []
+        for _ in range(header["chunks"]):
+            (n,) = struct.unpack("<Q", fp.read(8))
+            blobs.append(fp.read(n))
+    words = np.empty(header["n_words"], np.uint32)
+    cw = header["chunk_words"]
+
+    def work(i):
+        raw = lzma.decompress(blobs[i])
+        words[i * cw:i * cw + len(raw) // 4] = np.frombuffer(raw, np.uint32)
+
+    with ThreadPoolExecutor(workers or os.cpu_count() or 1) as ex:
+        list(ex.map(work, range(len(blobs))))
+    return words, np.array(header["center"], np.float32)
+
+
+def scene_available(name: str) -> bool:
+    return scene_path(name).exists() or packed_path(name).exists()
+
+
+def load_scene(name: str, scratch: str | None = None):
+    """-> (words, center): from the .oct, else from the xz sidecar, else built now with the reference builder."""
+    sys.path.insert(0, str(ROOT / "sparse-voxel-octrees_b200"))
+    import pysvo
+    if scene_path(name).exists():
+        return pysvo.oct_read(scene_path(name))
+    if packed_path(name).exists():
+        return unpack_scene(name)
+    return pysvo.oct_read(make_scene(name, scratch, verbose=False))
+
+
 def ensure_scene(name: str, scratch: str | None = None) -> Path:
     p = scene_path(name)
     if p.exists():
@@ -118,6 +191,12 @@ def ensure_scene(name: str, scratch: str | None = None) -> Path:
 
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or ["sdf256"]
-    for n in names:
-        print(make_scene(n))
+    args = sys.argv[1:] or ["sdf256"]
+    if args[0] == "pack":
+        for n in args[1:]:
+            t0 = time.time()
+            p = pack_scene(n)
+            print(p, f"{p.stat().st_size / 1e6:.0f} MB in {time.time() - t0:.0f} s")
+    else:
+        for n in args:
+            print(make_scene(n))
