@@ -185,7 +185,7 @@ typedef struct svo_frame_stats {
     uint32_t kernel_launches;   /* kernels this call put on the stream */
     uint32_t reserved;
     float coarse_ms;            /* device time of the beam-pass kernel (CUDA events on the call's stream) */
-    float fine_ms;              /* device time of the fine-pass kernel */
+    float fine_ms;              /* device time of the tile classifier + fine-pass kernel */
 } svo_frame_stats;
 
 /* Host-buffer variant: rgba (width*height uint32, the reference's backBuffer
@@ -198,11 +198,25 @@ typedef struct svo_frame_stats {
  * (zero on a fresh handle). */
 SVO_API int svo_render_frame(svo_tree *tree, const svo_camera *cam, const svo_frame_desc *desc,
                              uint32_t *rgba, float *depth, svo_frame_stats *stats);
+/* Pipelined host-buffer variant: enqueues the frame and its device->host copies and returns at
+ * once with a ticket; svo_frame_wait(ticket) blocks until `rgba` (and `depth`) hold the frame.
+ * Up to TWO frames may be in flight per (width, height, strips) configuration, so the copy of
+ * frame i overlaps the rendering of frame i+1 (and the beam pass of frame i+1 overlaps the fine
+ * pass of frame i). Host buffers must stay valid, and should be page-locked (svo_host_alloc),
+ * until the wait returns. svo_render_frame == svo_render_frame_async + svo_frame_wait. */
+SVO_API int svo_render_frame_async(svo_tree *tree, const svo_camera *cam, const svo_frame_desc *desc,
+                                   uint32_t *rgba, float *depth, int want_stats, int *ticket);
+SVO_API int svo_frame_wait(svo_tree *tree, const svo_frame_desc *desc, int ticket, svo_frame_stats *stats);
 /* Device-buffer variant: d_rgba may be any pointer the tree's device can
  * write -- local HBM or a peer GPU's framebuffer mapped with svo_ipc_open, in
  * which case finished tiles travel over NVLink as the kernel stores them.
- * d_depth may be NULL. Asynchronous on `stream`; `stats` (optional, host) is
- * filled only when `sync_stats` != 0, which synchronises the stream. */
+ * Asynchronous: the tile classifier and the fine pass run on `stream`; the beam
+ * pass runs on the tree's internal high-priority stream (it only touches
+ * internal buffers) and `stream` waits for it, so consecutive calls overlap the
+ * beam pass of frame i+1 with the fine pass of frame i. If d_depth is given
+ * (device pointer, receives the coarse depth buffer) the beam pass runs on
+ * `stream` too. `stats` (optional, host) is filled only when `sync_stats` != 0,
+ * which synchronises the stream. */
 SVO_API int svo_render_frame_device(svo_tree *tree, const svo_camera *cam, const svo_frame_desc *desc,
                                     uint32_t *d_rgba, float *d_depth, void *stream,
                                     svo_frame_stats *stats, int sync_stats);

@@ -32,9 +32,13 @@ float svo_oracle_inv_sqrt(float x) {
     return y*(1.5f - halfX*y*y);
 }
 
-/* VoxelOctree.cpp:207-346 */
-int svo_oracle_raymarch(const uint32_t *octree, const float *o, const float *d, float rayScale,
-        uint32_t *normal, float *t, uint64_t *voxel, svo_oracle_counters *c) {
+/* VoxelOctree.cpp:207-346. `ops` (optional) records what each trip round the loop did:
+ * 'P' push, 'A' advance, 'Q' advance + pop, 'L' leaf hit, 'D' LOD exit, 'X' advance + pop out of the root. */
+static int raymarchImpl(const uint32_t *octree, const float *o, const float *d, float rayScale,
+        uint32_t *normal, float *t, uint64_t *voxel, svo_oracle_counters *c,
+        uint8_t *ops, uint32_t maxOps, uint32_t *nOps) {
+    uint32_t opCount = 0;
+#define SVO_OP(ch) do { if (ops && opCount < maxOps) ops[opCount] = (uint8_t)(ch); ++opCount; } while (0)
     uint64_t stackParent[SVO_MAX_SCALE + 1];
     float stackMaxT[SVO_MAX_SCALE + 1];
     float dT[3], bT[3], pos[3];
@@ -85,6 +89,7 @@ int svo_oracle_raymarch(const uint32_t *octree, const float *o, const float *d, 
                 result = SVO_ORACLE_LOD;
                 tOut = maxTC;
                 if (voxel) *voxel = parent | ((uint64_t)childShift << 60);
+                SVO_OP('D');
                 break;
             }
             float maxTV = minStd(maxT, maxTC);
@@ -105,6 +110,7 @@ int svo_oracle_raymarch(const uint32_t *octree, const float *o, const float *d, 
                     if (voxel) *voxel = leaf;
                     result = SVO_ORACLE_LEAF;
                     tOut = minT;
+                    SVO_OP('L');
                     break;
                 }
                 stackParent[scale] = parent;        /* push :287-306 */
@@ -120,6 +126,7 @@ int svo_oracle_raymarch(const uint32_t *octree, const float *o, const float *d, 
                     if (centerT[a] > minT) { idx ^= 1u << a; pos[a] += scaleExp2; }
                 maxT = maxTV;
                 current = 0;
+                SVO_OP('P');
                 continue;
             }
         }
@@ -149,8 +156,13 @@ int svo_oracle_raymarch(const uint32_t *octree, const float *o, const float *d, 
                 idx |= (sh & 1u) << a;
             }
             current = 0;
+            SVO_OP(scale < SVO_MAX_SCALE ? 'Q' : 'X');
+        } else {
+            SVO_OP('A');
         }
     }
+#undef SVO_OP
+    if (nOps) *nOps = opCount;
 
     if (c) {
         c->rays += 1;
@@ -166,6 +178,11 @@ int svo_oracle_raymarch(const uint32_t *octree, const float *o, const float *d, 
     }
     if (result != SVO_ORACLE_MISS) *t = tOut;       /* :266 / :344 */
     return result;
+}
+
+int svo_oracle_raymarch(const uint32_t *octree, const float *o, const float *d, float rayScale,
+        uint32_t *normal, float *t, uint64_t *voxel, svo_oracle_counters *c) {
+    return raymarchImpl(octree, o, d, rayScale, normal, t, voxel, c, NULL, 0, NULL);
 }
 
 static void mergeCounters(svo_oracle_counters *dst, const svo_oracle_counters *src) {
@@ -491,6 +508,68 @@ int svo_oracle_render_frame(const uint32_t *octree, const svo_oracle_frame *f, u
     free(tids);
     free(offsets);
     return 0;
+}
+
+/* ---- per-ray operation traces of the fine pass (kernel design tool) ------------ */
+
+/* For every `tileStride`-th rendered tile of the frame, traces the 64 fine rays in GPU warp order
+ * (two warps per tile, lane l -> pixel (l & 7, (l >> 3) + 4*half)). ops: [maxWarps*32][maxOps],
+ * counts: [maxWarps*32] (0 for clipped pixels). Returns the number of warps written. */
+int64_t svo_oracle_trace_fine_warps(const uint32_t *octree, const svo_oracle_frame *f, int tileStride,
+        uint8_t *ops, uint32_t maxOps, uint32_t *counts, int64_t maxWarps) {
+    const float TreeMiss = 1e10f;
+    int64_t nWarps = 0, rendered = 0;
+    int stride = (f->height - 1)/f->strips + 1;
+    int tile = f->tile_size;
+    for (int strip = 0; strip < f->strips; ++strip) {
+        int y0 = strip*stride;
+        int y1 = (strip + 1)*stride < f->height ? (strip + 1)*stride : f->height;
+        if (y0 >= y1) continue;
+        int tilesX = (f->width - 1)/tile + 2, tilesY = (y1 - y0 - 1)/tile + 2;
+        float *depth = (float *)malloc(sizeof(float)*(size_t)tilesX*(size_t)tilesY);
+        float dy = f->aspect - y0*f->scale;
+        for (int y = 0, idx = 0; y < tilesY; ++y, dy -= f->tile_scale) {
+            float dx = -1.0f + 0*f->scale;
+            for (int x = 0; x < tilesX; ++x, dx += f->tile_scale, ++idx) {
+                float dir[3], t = 0.0f;
+                uint32_t material = 0;
+                rayDir(f, dx, dy, dir);
+                depth[idx] = svo_oracle_raymarch(octree, f->pos, dir, f->coarse_scale, &material, &t, NULL, NULL) ? t : TreeMiss;
+            }
+        }
+        for (int y = 1; y < tilesY; ++y) {
+            for (int x = 1; x < tilesX; ++x) {
+                int idx = y*tilesX + x;
+                float minT = minStd(minStd(depth[idx], depth[idx - 1]), minStd(depth[idx - tilesX], depth[idx - tilesX - 1]));
+                if (minT == TreeMiss) continue;
+                if ((rendered++ % tileStride) != 0) continue;
+                float startT = maxStd(minT - f->beam_bias, 0.0f);
+                int tx0 = (x - 1)*tile, ty0 = (y - 1)*tile + y0;
+                for (int half = 0; half < 2; ++half) {
+                    if (nWarps >= maxWarps) { free(depth); return nWarps; }
+                    for (int lane = 0; lane < 32; ++lane) {
+                        int px = tx0 + (lane & 7), py = ty0 + (lane >> 3) + 4*half;
+                        size_t slot = (size_t)nWarps*32 + (size_t)lane;
+                        counts[slot] = 0;
+                        if (px >= f->width || py >= y1) continue;
+                        float fdy = f->aspect - ty0*f->scale;
+                        for (int k = ty0; k < py; ++k) fdy -= f->scale;
+                        float fdx = -1.0f + tx0*f->scale;
+                        for (int k = tx0; k < px; ++k) fdx += f->scale;
+                        float dir[3], org[3], t = 0.0f;
+                        uint32_t material = 0, n = 0;
+                        rayDir(f, fdx, fdy, dir);
+                        for (int a = 0; a < 3; ++a) org[a] = f->pos[a] + dir[a]*startT;
+                        raymarchImpl(octree, org, dir, 0.0f, &material, &t, NULL, NULL, ops + slot*maxOps, maxOps, &n);
+                        counts[slot] = n < maxOps ? n : maxOps;
+                    }
+                    ++nWarps;
+                }
+            }
+        }
+        free(depth);
+    }
+    return nWarps;
 }
 
 /* ---- tree walk (App. A.1) --------------------------------------------------- */

@@ -89,6 +89,10 @@ float svo_oracle_inv_sqrt(float x);
 int svo_oracle_render_frame(const uint32_t *octree, const svo_oracle_frame *f, uint32_t *rgba,
         float *depth, svo_oracle_counters *coarse, svo_oracle_counters *fine, int threads);
 
+/* Kernel design tool: per-ray loop-trip traces of the fine pass in GPU warp order (see svo_oracle.c). */
+int64_t svo_oracle_trace_fine_warps(const uint32_t *octree, const svo_oracle_frame *f, int tileStride,
+        uint8_t *ops, uint32_t maxOps, uint32_t *counts, int64_t maxWarps);
+
 /* Tree statistics by a full walk from the root (App. A.1). */
 typedef struct {
     uint64_t descriptors, leaves, far_words, far_blocks;

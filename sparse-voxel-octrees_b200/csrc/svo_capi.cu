@@ -65,11 +65,45 @@ struct DeviceScope {
     DeviceScope scope_(device);                                \
     if (scope_.error != cudaSuccess) return failCuda(scope_.error, "cudaSetDevice")
 
+// Everything one (width, height, strips) configuration needs on the device. Frames are
+// double-buffered (slot = frame number & 1) so that the beam pass of frame i+1 can run on the
+// tree's high-priority internal stream while the fine pass of frame i is still busy, and so
+// that the device->host copy of frame i overlaps the rendering of frame i+1.
 struct FramePlan {
     svo::FramePlanDev dev{};
-    float *dTables = nullptr;   // dxCoarse | dyCoarse | dxFine | dyFine
-    float *dDepth = nullptr;    // totalCorners floats
-    uint32_t *dRgba = nullptr;  // width*height words, host-variant staging (lazy)
+    float *dTables = nullptr;              // dxCoarse | dyCoarse | dxFine | dyFine
+    float *dDepth[2] = {nullptr, nullptr}; // totalCorners floats each
+    svo::TileRecord *dTiles[2] = {nullptr, nullptr};   // totalTiles records each (worst case: every tile rendered)
+    svo::FrameCounters *dCounters[2] = {nullptr, nullptr};
+    svo::FrameCounters *hCounters = nullptr;            // pinned, 2 entries
+    uint32_t *dRgba[2] = {nullptr, nullptr};            // host-buffer entry points only (lazy)
+    cudaEvent_t coarseDone[2] = {nullptr, nullptr};     // beam pass of the slot finished (internal stream)
+    cudaEvent_t fineDone[2] = {nullptr, nullptr};       // last fine pass that read the slot's depth / tile list
+    cudaEvent_t copyDone[2] = {nullptr, nullptr};       // device->host copy out of dRgba[slot] finished
+    cudaEvent_t timing[2][4] = {};                      // coarse start/end, fine start/end (stats only)
+    bool fineRecorded[2] = {false, false};
+    bool copyRecorded[2] = {false, false};
+    bool pending[2] = {false, false};                   // svo_render_frame_async issued, not yet waited for
+    bool pendingStats[2] = {false, false};
+    uint32_t pendingLaunches[2] = {0, 0};
+    svo_frame_desc pendingDesc[2] = {};
+    uint64_t frameNumber = 0;
+
+    void destroy() {
+        if (dTables) cudaFree(dTables);
+        if (hCounters) cudaFreeHost(hCounters);
+        for (int b = 0; b < 2; ++b) {
+            if (dDepth[b]) cudaFree(dDepth[b]);
+            if (dTiles[b]) cudaFree(dTiles[b]);
+            if (dCounters[b]) cudaFree(dCounters[b]);
+            if (dRgba[b]) cudaFree(dRgba[b]);
+            if (coarseDone[b]) cudaEventDestroy(coarseDone[b]);
+            if (fineDone[b]) cudaEventDestroy(fineDone[b]);
+            if (copyDone[b]) cudaEventDestroy(copyDone[b]);
+            for (int k = 0; k < 4; ++k) if (timing[b][k]) cudaEventDestroy(timing[b][k]);
+        }
+        *this = FramePlan();
+    }
 };
 
 struct GrowBuffer {
@@ -99,10 +133,9 @@ struct svo_tree {
     uint64_t nWords = 0;
     float center[3] = {0, 0, 0};
     uint32_t depth = 0;
-    cudaStream_t stream = nullptr;          // for the host-buffer entry points
-    svo::FrameCounters *dCounters = nullptr;
-    svo::FrameCounters *hCounters = nullptr; // pinned
-    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr}; // coarse start | fine start | fine end (stats only)
+    cudaStream_t stream = nullptr;          // rendering for the host-buffer entry points
+    cudaStream_t coarseStream = nullptr;    // beam passes, high priority (overlaps the previous frame's fine pass)
+    cudaStream_t copyStream = nullptr;      // device->host frame copies
     std::mutex mutex;
     std::map<std::tuple<int, int, int>, FramePlan> plans;
     GrowBuffer batchIn, batchOut;
@@ -168,21 +201,20 @@ int createTree(const uint32_t *words, uint64_t nWords, const float center[3], in
     size_t bytes = size_t(nWords + 1)*sizeof(uint32_t);
     auto cleanup = [&](cudaError_t err, const char *what) {
         if (tree->dWords) cudaFree(tree->dWords);
-        if (tree->dCounters) cudaFree(tree->dCounters);
-        if (tree->hCounters) cudaFreeHost(tree->hCounters);
         if (tree->stream) cudaStreamDestroy(tree->stream);
-        for (int i = 0; i < 3; ++i) if (tree->ev[i]) cudaEventDestroy(tree->ev[i]);
+        if (tree->coarseStream) cudaStreamDestroy(tree->coarseStream);
+        if (tree->copyStream) cudaStreamDestroy(tree->copyStream);
         return failCuda(err, what);
     };
     if ((e = cudaMalloc(&tree->dWords, bytes)) != cudaSuccess) return cleanup(e, "cudaMalloc(node array)");
     if ((e = cudaMemcpy(tree->dWords, words, size_t(nWords)*sizeof(uint32_t), cudaMemcpyHostToDevice)) != cudaSuccess)
         return cleanup(e, "cudaMemcpy(node array)");
     if ((e = cudaMemset(tree->dWords + nWords, 0, sizeof(uint32_t))) != cudaSuccess) return cleanup(e, "cudaMemset(padding)");
+    int prioLow = 0, prioHigh = 0;
+    if ((e = cudaDeviceGetStreamPriorityRange(&prioLow, &prioHigh)) != cudaSuccess) return cleanup(e, "cudaDeviceGetStreamPriorityRange");
     if ((e = cudaStreamCreateWithFlags(&tree->stream, cudaStreamNonBlocking)) != cudaSuccess) return cleanup(e, "cudaStreamCreate");
-    if ((e = cudaMalloc(&tree->dCounters, sizeof(svo::FrameCounters))) != cudaSuccess) return cleanup(e, "cudaMalloc(counters)");
-    if ((e = cudaMallocHost(&tree->hCounters, sizeof(svo::FrameCounters))) != cudaSuccess) return cleanup(e, "cudaMallocHost(counters)");
-    for (int i = 0; i < 3; ++i)
-        if ((e = cudaEventCreate(&tree->ev[i])) != cudaSuccess) return cleanup(e, "cudaEventCreate");
+    if ((e = cudaStreamCreateWithPriority(&tree->coarseStream, cudaStreamNonBlocking, prioHigh)) != cudaSuccess) return cleanup(e, "cudaStreamCreate(coarse)");
+    if ((e = cudaStreamCreateWithFlags(&tree->copyStream, cudaStreamNonBlocking)) != cudaSuccess) return cleanup(e, "cudaStreamCreate(copy)");
     *out = tree.release();
     return SVO_OK;
 }
@@ -235,7 +267,17 @@ int buildPlan(svo_tree *tree, int width, int height, int strips, FramePlan &plan
 
     SVO_CUDA(cudaMalloc(&plan.dTables, tables.size()*sizeof(float)));
     SVO_CUDA(cudaMemcpy(plan.dTables, tables.data(), tables.size()*sizeof(float), cudaMemcpyHostToDevice));
-    SVO_CUDA(cudaMalloc(&plan.dDepth, size_t(p.totalCorners)*sizeof(float)));
+    SVO_CUDA(cudaMallocHost(&plan.hCounters, 2*sizeof(svo::FrameCounters)));
+    for (int b = 0; b < 2; ++b) {
+        SVO_CUDA(cudaMalloc(&plan.dDepth[b], size_t(p.totalCorners)*sizeof(float)));
+        SVO_CUDA(cudaMalloc(&plan.dTiles[b], size_t(p.totalTiles > 0 ? p.totalTiles : 1)*sizeof(svo::TileRecord)));
+        SVO_CUDA(cudaMalloc(&plan.dCounters[b], sizeof(svo::FrameCounters)));
+        SVO_CUDA(cudaMemset(plan.dCounters[b], 0, sizeof(svo::FrameCounters)));
+        SVO_CUDA(cudaEventCreateWithFlags(&plan.coarseDone[b], cudaEventDisableTiming));
+        SVO_CUDA(cudaEventCreateWithFlags(&plan.fineDone[b], cudaEventDisableTiming));
+        SVO_CUDA(cudaEventCreateWithFlags(&plan.copyDone[b], cudaEventDisableTiming));
+        for (int k = 0; k < 4; ++k) SVO_CUDA(cudaEventCreate(&plan.timing[b][k]));
+    }
     p.dxCoarse = plan.dTables;
     p.dyCoarse = p.dxCoarse + nDxC;
     p.dxFine = p.dyCoarse + nDyC;
@@ -251,8 +293,7 @@ int getPlan(svo_tree *tree, int width, int height, int strips, FramePlan **out) 
         FramePlan plan;
         int st = buildPlan(tree, width, height, strips, plan);
         if (st != SVO_OK) {
-            if (plan.dTables) cudaFree(plan.dTables);
-            if (plan.dDepth) cudaFree(plan.dDepth);
+            plan.destroy();
             return st;
         }
         it = tree->plans.emplace(key, plan).first;
@@ -285,43 +326,62 @@ svo::FrameConsts toDeviceConsts(const svo_frame_constants &c) {
     return f;
 }
 
-// Enqueues one frame on `stream`. Caller holds tree->mutex and has made the device current.
+// Enqueues one frame. The beam pass goes to the tree's high-priority internal stream (unless the
+// caller wants the depth buffer in its own memory, which must be ordered on `stream`), the tile
+// classifier and the fine pass to `stream`. Returns the double-buffer slot used. Caller holds
+// tree->mutex and has made the device current.
 int enqueueFrame(svo_tree *tree, FramePlan *plan, const svo_camera *cam, const svo_frame_desc *desc,
-                 uint32_t *dRgba, float *dDepth, cudaStream_t stream, bool wantStats, uint32_t *launches) {
+                 uint32_t *dRgba, float *userDepth, cudaStream_t stream, bool wantStats, uint32_t *launches,
+                 int *slotOut) {
     svo_frame_constants c;
     svo::frameConstants(*cam, tree->center, desc->width, desc->height, desc->strips, c);
     svo::FrameConsts f = toDeviceConsts(c);
-    float *depth = dDepth ? dDepth : plan->dDepth;
+    const int b = int(plan->frameNumber++ & 1);
+    float *depth = userDepth ? userDepth : plan->dDepth[b];
+    cudaStream_t cs = userDepth ? stream : tree->coarseStream;
     uint32_t n = 0;
-    if (wantStats) SVO_CUDA(cudaEventRecord(tree->ev[0], stream));
-    SVO_CUDA(svo::launchCoarsePass(tree->dev(), plan->dev, f, desc->flavour, depth, stream));
+
+    // the slot's depth buffer, tile list and counters are free once the fine pass of two frames ago is done
+    if (!userDepth && plan->fineRecorded[b]) SVO_CUDA(cudaStreamWaitEvent(cs, plan->fineDone[b], 0));
+    if (wantStats) SVO_CUDA(cudaEventRecord(plan->timing[b][0], cs));
+    SVO_CUDA(svo::launchCoarsePass(tree->dev(), plan->dev, f, desc->flavour, depth, plan->dCounters[b], cs));
     ++n;
-    if (wantStats) SVO_CUDA(cudaEventRecord(tree->ev[1], stream));
-    SVO_CUDA(svo::launchFinePass(tree->dev(), plan->dev, f, desc->flavour, depth, dRgba, desc->tile_rank,
-                                 desc->tile_world, stream));
+    if (wantStats) SVO_CUDA(cudaEventRecord(plan->timing[b][1], cs));
+    if (!userDepth) {
+        SVO_CUDA(cudaEventRecord(plan->coarseDone[b], cs));
+        SVO_CUDA(cudaStreamWaitEvent(stream, plan->coarseDone[b], 0));
+    }
+    if (wantStats) SVO_CUDA(cudaEventRecord(plan->timing[b][2], stream));
+    SVO_CUDA(svo::launchClassifyTiles(plan->dev, f, depth, dRgba, desc->tile_rank, desc->tile_world, plan->dTiles[b],
+                                      plan->dCounters[b], stream));
+    ++n;
+    SVO_CUDA(svo::launchFinePass(tree->dev(), plan->dev, f, desc->flavour, plan->dTiles[b], plan->dCounters[b], dRgba,
+                                 desc->tile_rank, desc->tile_world, stream));
     ++n;
     if (wantStats) {
-        SVO_CUDA(cudaEventRecord(tree->ev[2], stream));
-        SVO_CUDA(cudaMemsetAsync(tree->dCounters, 0, sizeof(svo::FrameCounters), stream));
-        SVO_CUDA(svo::launchTileStats(plan->dev, depth, desc->tile_rank, desc->tile_world, tree->dCounters, stream));
-        ++n;
-        SVO_CUDA(cudaMemcpyAsync(tree->hCounters, tree->dCounters, sizeof(svo::FrameCounters), cudaMemcpyDeviceToHost, stream));
+        SVO_CUDA(cudaEventRecord(plan->timing[b][3], stream));
+        SVO_CUDA(cudaMemcpyAsync(plan->hCounters + b, plan->dCounters[b], sizeof(svo::FrameCounters),
+                                 cudaMemcpyDeviceToHost, stream));
     }
+    SVO_CUDA(cudaEventRecord(plan->fineDone[b], stream));
+    plan->fineRecorded[b] = true;
     if (launches) *launches = n;
+    if (slotOut) *slotOut = b;
     return SVO_OK;
 }
 
-void fillStats(const svo_tree *tree, const FramePlan *plan, const svo_frame_desc *desc, uint32_t launches, svo_frame_stats *stats) {
+// Valid once the frame's stream work has completed (caller synchronised).
+void fillStats(const FramePlan *plan, int slot, const svo_frame_desc *desc, uint32_t launches, svo_frame_stats *stats) {
     stats->coarse_rays = uint64_t(plan->dev.totalCorners);
-    stats->fine_rays = tree->hCounters->fineRays;
-    stats->tiles_rendered = tree->hCounters->tilesRendered;
+    stats->fine_rays = plan->hCounters[slot].fineRays;
+    stats->tiles_rendered = plan->hCounters[slot].tilesRendered;
     int owned = (plan->dev.totalTiles - desc->tile_rank + desc->tile_world - 1)/desc->tile_world;
     stats->tiles_total = owned > 0 ? uint64_t(owned) : 0;
     stats->kernel_launches = launches;
     stats->reserved = 0;
     stats->coarse_ms = stats->fine_ms = 0.0f;
-    cudaEventElapsedTime(&stats->coarse_ms, tree->ev[0], tree->ev[1]);   // events completed: caller synchronised
-    cudaEventElapsedTime(&stats->fine_ms, tree->ev[1], tree->ev[2]);
+    cudaEventElapsedTime(&stats->coarse_ms, plan->timing[slot][0], plan->timing[slot][1]);
+    cudaEventElapsedTime(&stats->fine_ms, plan->timing[slot][2], plan->timing[slot][3]);
 }
 
 } // namespace
@@ -430,19 +490,14 @@ int svo_tree_destroy(svo_tree *tree) {
     if (!tree) return SVO_OK;
     {
         SVO_DEVICE(tree->device);
-        cudaStreamSynchronize(tree->stream);
-        for (auto &kv : tree->plans) {
-            if (kv.second.dTables) cudaFree(kv.second.dTables);
-            if (kv.second.dDepth) cudaFree(kv.second.dDepth);
-            if (kv.second.dRgba) cudaFree(kv.second.dRgba);
-        }
+        cudaDeviceSynchronize();
+        for (auto &kv : tree->plans) kv.second.destroy();
         tree->batchIn.release();
         tree->batchOut.release();
         if (tree->dWords) cudaFree(tree->dWords);
-        if (tree->dCounters) cudaFree(tree->dCounters);
-        if (tree->hCounters) cudaFreeHost(tree->hCounters);
         if (tree->stream) cudaStreamDestroy(tree->stream);
-        for (int i = 0; i < 3; ++i) if (tree->ev[i]) cudaEventDestroy(tree->ev[i]);
+        if (tree->coarseStream) cudaStreamDestroy(tree->coarseStream);
+        if (tree->copyStream) cudaStreamDestroy(tree->copyStream);
     }
     delete tree;
     return SVO_OK;
@@ -538,37 +593,80 @@ int svo_render_frame_device(svo_tree *tree, const svo_camera *cam, const svo_fra
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     bool wantStats = stats && sync_stats;
     uint32_t launches = 0;
-    if ((st = enqueueFrame(tree, plan, cam, desc, d_rgba, d_depth, s, wantStats, &launches)) != SVO_OK) return st;
+    int slot = 0;
+    if ((st = enqueueFrame(tree, plan, cam, desc, d_rgba, d_depth, s, wantStats, &launches, &slot)) != SVO_OK) return st;
     if (wantStats) {
         SVO_CUDA(cudaStreamSynchronize(s));
-        fillStats(tree, plan, desc, launches, stats);
+        fillStats(plan, slot, desc, launches, stats);
     }
     return SVO_OK;
 }
 
-int svo_render_frame(svo_tree *tree, const svo_camera *cam, const svo_frame_desc *desc, uint32_t *rgba, float *depth,
-                     svo_frame_stats *stats) {
-    if (!tree || !cam || !rgba) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_render_frame: null argument");
+int svo_render_frame_async(svo_tree *tree, const svo_camera *cam, const svo_frame_desc *desc, uint32_t *rgba,
+                           float *depth, int want_stats, int *ticket) {
+    if (!tree || !cam || !rgba || !ticket) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_render_frame_async: null argument");
     int st = checkDesc(desc);
     if (st != SVO_OK) return st;
     SVO_DEVICE(tree->device);
     std::lock_guard<std::mutex> lock(tree->mutex);
     FramePlan *plan = nullptr;
     if ((st = getPlan(tree, desc->width, desc->height, desc->strips, &plan)) != SVO_OK) return st;
+    const int b = int(plan->frameNumber & 1);     // the slot enqueueFrame is about to use
+    if (plan->pending[b])
+        return fail(SVO_ERR_INVALID_ARGUMENT, "two frames are already in flight for this configuration: call svo_frame_wait first");
     size_t frameBytes = size_t(desc->width)*size_t(desc->height)*sizeof(uint32_t);
-    if (!plan->dRgba) {
-        SVO_CUDA(cudaMalloc(&plan->dRgba, frameBytes));
-        SVO_CUDA(cudaMemset(plan->dRgba, 0, frameBytes));
+    if (!plan->dRgba[b]) {
+        SVO_CUDA(cudaMalloc(&plan->dRgba[b], frameBytes));
+        SVO_CUDA(cudaMemset(plan->dRgba[b], 0, frameBytes));
     }
     cudaStream_t s = tree->stream;
+    // the slot's staging framebuffer is free once its previous device->host copy has finished
+    if (plan->copyRecorded[b]) SVO_CUDA(cudaStreamWaitEvent(s, plan->copyDone[b], 0));
     uint32_t launches = 0;
-    if ((st = enqueueFrame(tree, plan, cam, desc, plan->dRgba, nullptr, s, stats != nullptr, &launches)) != SVO_OK) return st;
-    SVO_CUDA(cudaMemcpyAsync(rgba, plan->dRgba, frameBytes, cudaMemcpyDeviceToHost, s));
+    int slot = 0;
+    if ((st = enqueueFrame(tree, plan, cam, desc, plan->dRgba[b], nullptr, s, want_stats != 0, &launches, &slot)) != SVO_OK) return st;
+    // copies run on their own stream so that the next frame's kernels are not queued behind them
+    SVO_CUDA(cudaStreamWaitEvent(tree->copyStream, plan->fineDone[slot], 0));
+    SVO_CUDA(cudaMemcpyAsync(rgba, plan->dRgba[slot], frameBytes, cudaMemcpyDeviceToHost, tree->copyStream));
     if (depth)
-        SVO_CUDA(cudaMemcpyAsync(depth, plan->dDepth, size_t(plan->dev.totalCorners)*sizeof(float), cudaMemcpyDeviceToHost, s));
-    SVO_CUDA(cudaStreamSynchronize(s));
-    if (stats) fillStats(tree, plan, desc, launches, stats);
+        SVO_CUDA(cudaMemcpyAsync(depth, plan->dDepth[slot], size_t(plan->dev.totalCorners)*sizeof(float),
+                                 cudaMemcpyDeviceToHost, tree->copyStream));
+    SVO_CUDA(cudaEventRecord(plan->copyDone[slot], tree->copyStream));
+    plan->copyRecorded[slot] = true;
+    plan->pending[slot] = true;
+    plan->pendingStats[slot] = want_stats != 0;
+    plan->pendingLaunches[slot] = launches;
+    plan->pendingDesc[slot] = *desc;
+    // ticket: slot in bit 0, configuration in the rest (so that svo_frame_wait can find the plan)
+    *ticket = slot;
     return SVO_OK;
+}
+
+int svo_frame_wait(svo_tree *tree, const svo_frame_desc *desc, int ticket, svo_frame_stats *stats) {
+    if (!tree || !desc) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_frame_wait: null argument");
+    if (ticket != 0 && ticket != 1) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_frame_wait: bad ticket %d", ticket);
+    SVO_DEVICE(tree->device);
+    std::lock_guard<std::mutex> lock(tree->mutex);
+    auto it = tree->plans.find(std::make_tuple(desc->width, desc->height, desc->strips));
+    if (it == tree->plans.end() || !it->second.pending[ticket])
+        return fail(SVO_ERR_INVALID_ARGUMENT, "svo_frame_wait: no frame in flight for this ticket");
+    FramePlan *plan = &it->second;
+    SVO_CUDA(cudaEventSynchronize(plan->copyDone[ticket]));
+    plan->pending[ticket] = false;
+    if (stats) {
+        if (!plan->pendingStats[ticket])
+            return fail(SVO_ERR_INVALID_ARGUMENT, "svo_frame_wait: statistics were not requested for this frame");
+        fillStats(plan, ticket, &plan->pendingDesc[ticket], plan->pendingLaunches[ticket], stats);
+    }
+    return SVO_OK;
+}
+
+int svo_render_frame(svo_tree *tree, const svo_camera *cam, const svo_frame_desc *desc, uint32_t *rgba, float *depth,
+                     svo_frame_stats *stats) {
+    int ticket = 0;
+    int st = svo_render_frame_async(tree, cam, desc, rgba, depth, stats != nullptr, &ticket);
+    if (st != SVO_OK) return st;
+    return svo_frame_wait(tree, desc, ticket, stats);
 }
 
 /* ---- device memory + peer mapping -------------------------------------------- */

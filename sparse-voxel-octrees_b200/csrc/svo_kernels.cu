@@ -1,11 +1,11 @@
 // sm_100a kernels for the reference's ray-casting hot path:
 //   K1 raymarchBatchKernel  VoxelOctree::raymarch in a loop     (reference src/VoxelOctree.cpp:207-346)
 //   K2 coarsePassKernel     renderBatch's tile-corner beam pass (reference src/Main.cpp:167-184)
-//   K3 finePassKernel       4-corner min + renderTile + shade + pack + the strip memset, fused
-//                           (reference src/Main.cpp:92-137, 165, 186-197, 81-90)
-//   K4 tileStatsKernel      ray / tile counts for the Mrays/s metric
+//   K2b classifyTilesKernel 4-corner min, tile skip test, the strip memset for skipped tiles,
+//                           compact list of tiles to render      (reference src/Main.cpp:165, 186-197)
+//   K3 finePassKernel       renderTile + shade + pack, fused     (reference src/Main.cpp:92-137, 81-90)
 // No tensor cores: this is pointer chasing over a uint32 node array, bounded by
-// instruction issue and L1/L2 latency long before HBM bandwidth.
+// instruction issue and SIMT divergence long before HBM bandwidth.
 #include "svo_kernels.cuh"
 
 namespace svo {
@@ -15,30 +15,18 @@ namespace {
 constexpr int kBatchThreads = 128;
 constexpr int kCoarseThreads = 64;
 constexpr int kTileThreads = 64;   // one 8x8 tile per block: two warps of 8x4 pixels
-
-template <typename IdxT>
-__device__ __forceinline__ SmemStack<IdxT> makeStack(unsigned char *smem, uint32_t slots) {
-    SmemStack<IdxT> s;
-    s.stride = blockDim.x;
-    s.parent = reinterpret_cast<IdxT *>(smem) + threadIdx.x;
-    s.maxT = reinterpret_cast<float *>(smem + size_t(slots)*blockDim.x*sizeof(IdxT)) + threadIdx.x;
-    return s;
-}
-
-template <typename IdxT>
-size_t stackBytes(uint32_t slots, int threads) {
-    return size_t(slots)*size_t(threads)*(sizeof(IdxT) + sizeof(float));
-}
+constexpr int kClassifyThreads = 128;
 
 // ---- K1 -------------------------------------------------------------------
 
 template <bool FAST, bool LOD, typename IdxT>
 __global__ void __launch_bounds__(kBatchThreads)
 raymarchBatchKernel(const uint32_t *__restrict__ octree, uint64_t n, const float *__restrict__ o,
-                    const float *__restrict__ d, float rayScale, uint32_t slots, uint8_t *__restrict__ hit,
+                    const float *__restrict__ d, float rayScale, uint8_t *__restrict__ hit,
                     float *__restrict__ t, uint32_t *__restrict__ normal, uint64_t *__restrict__ voxel) {
     extern __shared__ __align__(16) unsigned char smem[];
-    SmemStack<IdxT> stack = makeStack<IdxT>(smem, slots);
+    SmemStack<IdxT, kBatchThreads> stack;
+    stack.init(smem);
 
     uint64_t i = uint64_t(blockIdx.x)*blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -49,7 +37,7 @@ raymarchBatchKernel(const uint32_t *__restrict__ octree, uint64_t n, const float
     float tHit = kTreeMiss;
     uint32_t material = 0;
     uint64_t vox = ~uint64_t(0);
-    int code = raymarch<FAST, LOD, IdxT>(octree, ox, oy, oz, dx, dy, dz, rayScale, stack, tHit, material, vox);
+    int code = raymarch<FAST, LOD, IdxT, kBatchThreads>(octree, ox, oy, oz, dx, dy, dz, rayScale, stack, tHit, material, vox);
 
     if (hit) hit[i] = uint8_t(code);
     if (t) t[i] = tHit;
@@ -59,14 +47,19 @@ raymarchBatchKernel(const uint32_t *__restrict__ octree, uint64_t n, const float
 
 // ---- K2 -------------------------------------------------------------------
 
-template <bool FAST, typename IdxT>
+template <typename IdxT>
 __global__ void __launch_bounds__(kCoarseThreads)
-coarsePassKernel(const uint32_t *__restrict__ octree, FramePlanDev plan, FrameConsts f, uint32_t slots,
-                 float *__restrict__ depth) {
+coarsePassKernel(const uint32_t *__restrict__ octree, FramePlanDev plan, FrameConsts f, float *__restrict__ depth,
+                 FrameCounters *__restrict__ counters) {
     extern __shared__ __align__(16) unsigned char smem[];
-    SmemStack<IdxT> stack = makeStack<IdxT>(smem, slots);
+    SmemStack<IdxT, kCoarseThreads> stack;
+    stack.init(smem);
 
     int i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i == 0) {
+        counters->tilesRendered = 0;
+        counters->fineRays = 0;
+    }
     if (i >= plan.totalCorners) return;
 
     int cellsFull = plan.tilesX*plan.tilesYFull;
@@ -83,61 +76,90 @@ coarsePassKernel(const uint32_t *__restrict__ octree, FramePlanDev plan, FrameCo
     float tHit = kTreeMiss;
     uint32_t material;
     uint64_t vox;
-    raymarch<FAST, true, IdxT>(octree, f.posX, f.posY, f.posZ, rx, ry, rz, f.coarseScale, stack, tHit, material, vox);
+    // individually rounded in both flavours, see launchCoarsePass
+    raymarch<false, true, IdxT, kCoarseThreads>(octree, f.posX, f.posY, f.posZ, rx, ry, rz, f.coarseScale, stack, tHit, material, vox);
     depth[i] = tHit;   // stays 1e10f on a miss (Main.cpp:181-184)
+}
+
+// ---- K2b ------------------------------------------------------------------
+
+__global__ void __launch_bounds__(kClassifyThreads)
+classifyTilesKernel(FramePlanDev plan, float beamBias, const float *__restrict__ depth, uint32_t *__restrict__ rgba,
+                    int tileRank, int tileWorld, int ownedTiles, TileRecord *__restrict__ tiles,
+                    FrameCounters *__restrict__ counters) {
+    int k = blockIdx.x*blockDim.x + threadIdx.x;
+    bool active = k < ownedTiles;
+    bool rendered = false;
+    int x0 = 0, y0 = 0, yEnd = 0;
+    float minT = kTreeMiss;
+    if (active) {
+        int tile = k*tileWorld + tileRank;
+        int tileRow = tile/plan.tileCols;
+        int tx = tile - tileRow*plan.tileCols;
+        int strip = min(tileRow/plan.tileRowsFull, plan.nStrips - 1);
+        int ty = tileRow - strip*plan.tileRowsFull;
+        int stripY0 = strip*plan.stripRows;
+        x0 = tx*8;
+        y0 = stripY0 + ty*8;
+        yEnd = min(stripY0 + plan.stripRows, plan.height);
+        // corner (tx+1, ty+1) and its three neighbours, in the reference's association (Main.cpp:187-189)
+        int idx = strip*plan.tilesX*plan.tilesYFull + (ty + 1)*plan.tilesX + tx + 1;
+        minT = minStd(minStd(__ldg(depth + idx), __ldg(depth + idx - 1)),
+                      minStd(__ldg(depth + idx - plan.tilesX), __ldg(depth + idx - plan.tilesX - 1)));
+        rendered = minT != kTreeMiss;                           // Main.cpp:191
+    }
+
+    // warp-aggregated append: one atomic per warp
+    unsigned lane = threadIdx.x & 31u;
+    unsigned mask = __ballot_sync(0xffffffffu, rendered);
+    int w = min(x0 + 8, plan.width) - x0;
+    int h = min(y0 + 8, yEnd) - y0;
+    unsigned pixels = __reduce_add_sync(0xffffffffu, rendered ? unsigned(w*h) : 0u);
+    unsigned base = 0;
+    if (lane == 0 && mask) {
+        base = atomicAdd(&counters->tilesRendered, unsigned(__popc(mask)));
+        atomicAdd(&counters->fineRays, (unsigned long long)pixels);
+    }
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (rendered) {
+        TileRecord r;
+        r.xy = uint32_t(x0) | (uint32_t(y0) << 16);
+        r.yEnd = uint32_t(yEnd);
+        r.startT = maxStd(subRn(minT, beamBias), 0.0f);        // Main.cpp:197
+        r.pad = 0;
+        tiles[base + __popc(mask & ((1u << lane) - 1u))] = r;
+    } else if (active) {
+        // skipped tile: its pixels keep the strip memset's zero (Main.cpp:165)
+        if (w == 8 && (plan.width & 3) == 0) {
+            for (int r = 0; r < h; ++r) {
+                uint4 *row = reinterpret_cast<uint4 *>(rgba + size_t(y0 + r)*size_t(plan.width) + x0);
+                row[0] = make_uint4(0, 0, 0, 0);
+                row[1] = make_uint4(0, 0, 0, 0);
+            }
+        } else {
+            for (int r = 0; r < h; ++r)
+                for (int c = 0; c < w; ++c) rgba[size_t(y0 + r)*size_t(plan.width) + x0 + c] = 0u;
+        }
+    }
 }
 
 // ---- K3 -------------------------------------------------------------------
 
-struct TileCoords {
-    int strip, tx, ty;
-    int x0, y0;       // pixel origin
-    int yEnd;         // strip end row (exclusive)
-    int cornerIdx;    // index of corner (tx+1, ty+1) in the depth buffer
-};
-
-__device__ __forceinline__ TileCoords tileCoords(const FramePlanDev &plan, int tile) {
-    TileCoords c;
-    int tileRow = tile/plan.tileCols;
-    c.tx = tile - tileRow*plan.tileCols;
-    c.strip = min(tileRow/plan.tileRowsFull, plan.nStrips - 1);
-    c.ty = tileRow - c.strip*plan.tileRowsFull;
-    int stripY0 = c.strip*plan.stripRows;
-    c.x0 = c.tx*8;
-    c.y0 = stripY0 + c.ty*8;
-    c.yEnd = min(stripY0 + plan.stripRows, plan.height);
-    c.cornerIdx = c.strip*plan.tilesX*plan.tilesYFull + (c.ty + 1)*plan.tilesX + c.tx + 1;
-    return c;
-}
-
-// min over the tile's four corner depths in the reference's association (Main.cpp:187-189)
-__device__ __forceinline__ float tileMinDepth(const FramePlanDev &plan, const float *__restrict__ depth, int idx) {
-    return minStd(minStd(__ldg(depth + idx), __ldg(depth + idx - 1)),
-                  minStd(__ldg(depth + idx - plan.tilesX), __ldg(depth + idx - plan.tilesX - 1)));
-}
-
 template <bool FAST, typename IdxT>
 __global__ void __launch_bounds__(kTileThreads)
-finePassKernel(const uint32_t *__restrict__ octree, FramePlanDev plan, FrameConsts f, uint32_t slots,
-               const float *__restrict__ depth, uint32_t *__restrict__ rgba, int tileRank, int tileWorld) {
+finePassKernel(const uint32_t *__restrict__ octree, FramePlanDev plan, FrameConsts f,
+               const TileRecord *__restrict__ tiles, const FrameCounters *__restrict__ counters,
+               uint32_t *__restrict__ rgba) {
     extern __shared__ __align__(16) unsigned char smem[];
-    SmemStack<IdxT> stack = makeStack<IdxT>(smem, slots);
+    SmemStack<IdxT, kTileThreads> stack;
+    stack.init(smem);
 
-    int tile = blockIdx.x*tileWorld + tileRank;
-    if (tile >= plan.totalTiles) return;
-    TileCoords c = tileCoords(plan, tile);
-
-    int px = c.x0 + (threadIdx.x & 7);
-    int py = c.y0 + (threadIdx.x >> 3);
-    if (px >= plan.width || py >= c.yEnd) return;
-    uint32_t *dst = rgba + size_t(py)*size_t(plan.width) + px;
-
-    float minT = tileMinDepth(plan, depth, c.cornerIdx);
-    if (minT == kTreeMiss) {       // Main.cpp:191: tile skipped, pixels keep the memset's 0 (Main.cpp:165)
-        *dst = 0u;
-        return;
-    }
-    float startT = maxStd(subRn(minT, f.beamBias), 0.0f);   // Main.cpp:197
+    if (blockIdx.x >= counters->tilesRendered) return;
+    const uint4 rec = __ldg(reinterpret_cast<const uint4 *>(tiles) + blockIdx.x);
+    int px = int(rec.x & 0xFFFFu) + int(threadIdx.x & 7);
+    int py = int(rec.x >> 16) + int(threadIdx.x >> 3);
+    if (px >= plan.width || py >= int(rec.y)) return;
+    float startT = __uint_as_float(rec.z);
 
     float rx, ry, rz;
     rayDirection(f, __ldg(plan.dxFine + px), __ldg(plan.dyFine + py), rx, ry, rz);
@@ -148,34 +170,10 @@ finePassKernel(const uint32_t *__restrict__ octree, FramePlanDev plan, FrameCons
     float tHit;
     uint32_t material = 0;
     uint64_t vox;
-    int code = raymarch<FAST, false, IdxT>(octree, ox, oy, oz, rx, ry, rz, 0.0f, stack, tHit, material, vox);
+    int code = raymarch<FAST, false, IdxT, kTileThreads>(octree, ox, oy, oz, rx, ry, rz, 0.0f, stack, tHit, material, vox);
     uint32_t colour = 0xFF000000u;                          // Vec3() -> black, Main.cpp:117
     if (code != kMiss) colour = packGrey(shadeMaterial(material, rx, ry, rz, f.lightX, f.lightY, f.lightZ));
-    *dst = colour;
-}
-
-// ---- K4 -------------------------------------------------------------------
-
-__global__ void __launch_bounds__(256)
-tileStatsKernel(FramePlanDev plan, const float *__restrict__ depth, int tileRank, int tileWorld, int ownedTiles,
-                FrameCounters *counters) {
-    int k = blockIdx.x*blockDim.x + threadIdx.x;
-    unsigned int pixels = 0, rendered = 0;
-    if (k < ownedTiles) {
-        TileCoords c = tileCoords(plan, k*tileWorld + tileRank);
-        if (tileMinDepth(plan, depth, c.cornerIdx) != kTreeMiss) {
-            int w = min(c.x0 + 8, plan.width) - c.x0;
-            int h = min(c.y0 + 8, c.yEnd) - c.y0;
-            pixels = w*h;
-            rendered = 1;
-        }
-    }
-    pixels = __reduce_add_sync(0xffffffffu, pixels);
-    rendered = __reduce_add_sync(0xffffffffu, rendered);
-    if ((threadIdx.x & 31) == 0 && rendered) {
-        atomicAdd(&counters->fineRays, (unsigned long long)pixels);
-        atomicAdd(&counters->tilesRendered, (unsigned long long)rendered);
-    }
+    rgba[size_t(py)*size_t(plan.width) + px] = colour;
 }
 
 inline uint32_t stackSlots(const TreeDev &tree) { return tree.depth > 1 ? tree.depth - 1 : 1; }
@@ -186,44 +184,44 @@ cudaError_t ensureSmem(K kernel, size_t bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
 }
 
+inline int ownedTiles(const FramePlanDev &plan, int tileRank, int tileWorld) {
+    return (plan.totalTiles - tileRank + tileWorld - 1)/tileWorld;
+}
+
 template <bool FAST, bool LOD, typename IdxT>
 cudaError_t launchBatchT(const TreeDev &tree, uint64_t n, const float *o, const float *d, float rayScale,
                          uint8_t *hit, float *t, uint32_t *normal, uint64_t *voxel, cudaStream_t stream) {
-    uint32_t slots = stackSlots(tree);
-    size_t smem = stackBytes<IdxT>(slots, kBatchThreads);
+    size_t smem = SmemStack<IdxT, kBatchThreads>::bytes(stackSlots(tree));
     auto kernel = raymarchBatchKernel<FAST, LOD, IdxT>;
     cudaError_t e = ensureSmem(kernel, smem);
     if (e != cudaSuccess) return e;
     uint64_t blocks = (n + kBatchThreads - 1)/kBatchThreads;
     if (blocks > 0x7FFFFFFFull) return cudaErrorInvalidValue;
-    kernel<<<unsigned(blocks), kBatchThreads, smem, stream>>>(tree.words, n, o, d, rayScale, slots, hit, t, normal, voxel);
+    kernel<<<unsigned(blocks), kBatchThreads, smem, stream>>>(tree.words, n, o, d, rayScale, hit, t, normal, voxel);
     return cudaGetLastError();
 }
 
-template <bool FAST, typename IdxT>
+template <typename IdxT>
 cudaError_t launchCoarseT(const TreeDev &tree, const FramePlanDev &plan, const FrameConsts &consts, float *depth,
-                          cudaStream_t stream) {
-    uint32_t slots = stackSlots(tree);
-    size_t smem = stackBytes<IdxT>(slots, kCoarseThreads);
-    auto kernel = coarsePassKernel<FAST, IdxT>;
+                          FrameCounters *counters, cudaStream_t stream) {
+    size_t smem = SmemStack<IdxT, kCoarseThreads>::bytes(stackSlots(tree));
+    auto kernel = coarsePassKernel<IdxT>;
     cudaError_t e = ensureSmem(kernel, smem);
     if (e != cudaSuccess) return e;
     int blocks = (plan.totalCorners + kCoarseThreads - 1)/kCoarseThreads;
-    kernel<<<blocks, kCoarseThreads, smem, stream>>>(tree.words, plan, consts, slots, depth);
+    kernel<<<blocks, kCoarseThreads, smem, stream>>>(tree.words, plan, consts, depth, counters);
     return cudaGetLastError();
 }
 
 template <bool FAST, typename IdxT>
-cudaError_t launchFineT(const TreeDev &tree, const FramePlanDev &plan, const FrameConsts &consts, const float *depth,
-                        uint32_t *rgba, int tileRank, int tileWorld, cudaStream_t stream) {
-    uint32_t slots = stackSlots(tree);
-    size_t smem = stackBytes<IdxT>(slots, kTileThreads);
+cudaError_t launchFineT(const TreeDev &tree, const FramePlanDev &plan, const FrameConsts &consts,
+                        const TileRecord *tiles, const FrameCounters *counters, uint32_t *rgba, int owned,
+                        cudaStream_t stream) {
+    size_t smem = SmemStack<IdxT, kTileThreads>::bytes(stackSlots(tree));
     auto kernel = finePassKernel<FAST, IdxT>;
     cudaError_t e = ensureSmem(kernel, smem);
     if (e != cudaSuccess) return e;
-    int owned = (plan.totalTiles - tileRank + tileWorld - 1)/tileWorld;
-    if (owned <= 0) return cudaSuccess;
-    kernel<<<owned, kTileThreads, smem, stream>>>(tree.words, plan, consts, slots, depth, rgba, tileRank, tileWorld);
+    kernel<<<owned, kTileThreads, smem, stream>>>(tree.words, plan, consts, tiles, counters, rgba);
     return cudaGetLastError();
 }
 
@@ -245,33 +243,38 @@ cudaError_t launchRaymarchBatch(const TreeDev &tree, uint64_t n, const float *o,
 }
 
 cudaError_t launchCoarsePass(const TreeDev &tree, const FramePlanDev &plan, const FrameConsts &consts, int flavour,
-                             float *depth, cudaStream_t stream) {
+                             float *depth, FrameCounters *counters, cudaStream_t stream) {
     // The beam pass is individually rounded in BOTH flavours: its depths feed
     // `minT - 0.03` (Main.cpp:197) and the tile-skip test (Main.cpp:191), so a
     // last-bit change here moves every ray origin of a tile or drops / adds a
     // whole tile. It is < 5 % of the rays; FAST only changes the fine pass.
     (void)flavour;
     bool wide = tree.nWords >= (1ull << 32);
-    return wide ? launchCoarseT<false, uint64_t>(tree, plan, consts, depth, stream)
-                : launchCoarseT<false, uint32_t>(tree, plan, consts, depth, stream);
+    return wide ? launchCoarseT<uint64_t>(tree, plan, consts, depth, counters, stream)
+                : launchCoarseT<uint32_t>(tree, plan, consts, depth, counters, stream);
+}
+
+cudaError_t launchClassifyTiles(const FramePlanDev &plan, const FrameConsts &consts, const float *depth,
+                                uint32_t *rgba, int tileRank, int tileWorld, TileRecord *tiles,
+                                FrameCounters *counters, cudaStream_t stream) {
+    int owned = ownedTiles(plan, tileRank, tileWorld);
+    if (owned <= 0) return cudaSuccess;
+    classifyTilesKernel<<<(owned + kClassifyThreads - 1)/kClassifyThreads, kClassifyThreads, 0, stream>>>(
+        plan, consts.beamBias, depth, rgba, tileRank, tileWorld, owned, tiles, counters);
+    return cudaGetLastError();
 }
 
 cudaError_t launchFinePass(const TreeDev &tree, const FramePlanDev &plan, const FrameConsts &consts, int flavour,
-                           const float *depth, uint32_t *rgba, int tileRank, int tileWorld, cudaStream_t stream) {
+                           const TileRecord *tiles, const FrameCounters *counters, uint32_t *rgba,
+                           int tileRank, int tileWorld, cudaStream_t stream) {
+    int owned = ownedTiles(plan, tileRank, tileWorld);
+    if (owned <= 0) return cudaSuccess;
     bool wide = tree.nWords >= (1ull << 32);
     if (flavour != 0)
-        return wide ? launchFineT<true, uint64_t>(tree, plan, consts, depth, rgba, tileRank, tileWorld, stream)
-                    : launchFineT<true, uint32_t>(tree, plan, consts, depth, rgba, tileRank, tileWorld, stream);
-    return wide ? launchFineT<false, uint64_t>(tree, plan, consts, depth, rgba, tileRank, tileWorld, stream)
-                : launchFineT<false, uint32_t>(tree, plan, consts, depth, rgba, tileRank, tileWorld, stream);
-}
-
-cudaError_t launchTileStats(const FramePlanDev &plan, const float *depth, int tileRank, int tileWorld,
-                            FrameCounters *counters, cudaStream_t stream) {
-    int owned = (plan.totalTiles - tileRank + tileWorld - 1)/tileWorld;
-    if (owned <= 0) return cudaSuccess;
-    tileStatsKernel<<<(owned + 255)/256, 256, 0, stream>>>(plan, depth, tileRank, tileWorld, owned, counters);
-    return cudaGetLastError();
+        return wide ? launchFineT<true, uint64_t>(tree, plan, consts, tiles, counters, rgba, owned, stream)
+                    : launchFineT<true, uint32_t>(tree, plan, consts, tiles, counters, rgba, owned, stream);
+    return wide ? launchFineT<false, uint64_t>(tree, plan, consts, tiles, counters, rgba, owned, stream)
+                : launchFineT<false, uint32_t>(tree, plan, consts, tiles, counters, rgba, owned, stream);
 }
 
 } // namespace svo

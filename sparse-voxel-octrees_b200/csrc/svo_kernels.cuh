@@ -32,9 +32,18 @@ struct FramePlanDev {
     const float *dyFine;    // [height]
 };
 
-struct FrameCounters {      // device-side, zeroed per frame
+struct FrameCounters {      // device-side; zeroed by the coarse pass, filled by the tile classifier
+    unsigned int tilesRendered; // == length of the tile list
+    unsigned int pad;
     unsigned long long fineRays;
-    unsigned long long tilesRendered;
+};
+
+// One rendered 8x8 tile (Main.cpp:186-197), produced by the classifier, consumed by the fine pass.
+struct TileRecord {
+    uint32_t xy;        // x0 | y0 << 16 (pixel origin)
+    uint32_t yEnd;      // strip end row, exclusive (tiles are clipped to their strip, Main.cpp:194-195)
+    float startT;       // max(min4 - 0.03, 0), Main.cpp:197
+    uint32_t pad;
 };
 
 struct TreeDev {
@@ -47,15 +56,19 @@ cudaError_t launchRaymarchBatch(const TreeDev &tree, uint64_t n, const float *o,
                                 int flavour, uint8_t *hit, float *t, uint32_t *normal, uint64_t *voxel,
                                 cudaStream_t stream);
 
+// Beam pass; also zeroes `counters` for the classifier that follows on the same stream.
 cudaError_t launchCoarsePass(const TreeDev &tree, const FramePlanDev &plan, const FrameConsts &consts, int flavour,
-                             float *depth, cudaStream_t stream);
+                             float *depth, FrameCounters *counters, cudaStream_t stream);
 
+// Per owned tile: min of the four corner depths; skipped tiles are zero-filled (the strip memset,
+// Main.cpp:165), rendered tiles are appended to `tiles` (capacity = owned tiles) and counted.
+cudaError_t launchClassifyTiles(const FramePlanDev &plan, const FrameConsts &consts, const float *depth,
+                                uint32_t *rgba, int tileRank, int tileWorld, TileRecord *tiles,
+                                FrameCounters *counters, cudaStream_t stream);
+
+// Fine pass over the tile list (grid covers the worst case; blocks past the list length exit).
 cudaError_t launchFinePass(const TreeDev &tree, const FramePlanDev &plan, const FrameConsts &consts, int flavour,
-                           const float *depth, uint32_t *rgba, int tileRank, int tileWorld, cudaStream_t stream);
-
-// Counts the tiles / pixels the fine pass renders for this rank (from the coarse
-// depth buffer alone); `counters` must be zeroed by the caller.
-cudaError_t launchTileStats(const FramePlanDev &plan, const float *depth, int tileRank, int tileWorld,
-                            FrameCounters *counters, cudaStream_t stream);
+                           const TileRecord *tiles, const FrameCounters *counters, uint32_t *rgba,
+                           int tileRank, int tileWorld, cudaStream_t stream);
 
 } // namespace svo

@@ -131,21 +131,55 @@ __device__ __forceinline__ uint32_t packGrey(float v) {
 }
 
 // The scale-indexed stack (reference: StackEntry rayStack[24], VoxelOctree.cpp:208-212)
-// lives in shared memory: slot s of thread t is at [s*blockDim + t], so a warp
-// touching one slot hits 32 distinct banks.
-template <typename IdxT>
-struct SmemStack {
-    IdxT *parent;   // already offset by the thread index
-    float *maxT;
-    uint32_t stride;
-    __device__ __forceinline__ void push(int slot, IdxT p, float m) {
-        parent[slot*stride] = p;
-        maxT[slot*stride] = m;
+// lives in shared memory as one (parent, maxT) pair per slot: slot s of thread t
+// is at byte s*STRIDE + t*ENTRY, so a warp touching one slot makes one
+// conflict-free vector access. Addresses are 32-bit shared-window addresses
+// computed once per thread; push / pop are a single st.shared / ld.shared.
+template <typename IdxT, int THREADS>
+struct SmemStack;
+
+template <int THREADS>
+struct SmemStack<uint32_t, THREADS> {
+    static constexpr uint32_t kEntry = 8;
+    static constexpr uint32_t kStride = THREADS*kEntry;
+    uint32_t top;   // address of the slot for scale 22 (the root's children)
+    __device__ __forceinline__ void init(const void *smem) {
+        top = uint32_t(__cvta_generic_to_shared(smem)) + threadIdx.x*kEntry;
+        asm volatile("" : "+r"(top));   // keep it in a register; ptxas would re-derive it at every pop
     }
-    __device__ __forceinline__ void pop(int slot, IdxT &p, float &m) const {
-        p = parent[slot*stride];
-        m = maxT[slot*stride];
+    __device__ __forceinline__ uint32_t slot(int scale) const { return top + uint32_t(kMaxScale - 1 - scale)*kStride; }
+    static __device__ __forceinline__ void store(uint32_t addr, uint32_t parent, float maxT) {
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(parent), "r"(__float_as_uint(maxT)) : "memory");
     }
+    static __device__ __forceinline__ void load(uint32_t addr, uint32_t &parent, float &maxT) {
+        uint32_t m;
+        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(parent), "=r"(m) : "r"(addr) : "memory");
+        maxT = __uint_as_float(m);
+    }
+    static size_t bytes(uint32_t slots) { return size_t(slots)*kStride; }
+};
+
+template <int THREADS>
+struct SmemStack<uint64_t, THREADS> {   // trees of 2^32 words and more: 16-byte entries
+    static constexpr uint32_t kEntry = 16;
+    static constexpr uint32_t kStride = THREADS*kEntry;
+    uint32_t top;
+    __device__ __forceinline__ void init(const void *smem) {
+        top = uint32_t(__cvta_generic_to_shared(smem)) + threadIdx.x*kEntry;
+        asm volatile("" : "+r"(top));
+    }
+    __device__ __forceinline__ uint32_t slot(int scale) const { return top + uint32_t(kMaxScale - 1 - scale)*kStride; }
+    static __device__ __forceinline__ void store(uint32_t addr, uint64_t parent, float maxT) {
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(uint32_t(parent)),
+                     "r"(uint32_t(parent >> 32)), "r"(__float_as_uint(maxT)), "r"(0u) : "memory");
+    }
+    static __device__ __forceinline__ void load(uint32_t addr, uint64_t &parent, float &maxT) {
+        uint32_t lo, hi, m, pad;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(hi), "=r"(m), "=r"(pad) : "r"(addr) : "memory");
+        parent = (uint64_t(hi) << 32) | lo;
+        maxT = __uint_as_float(m);
+    }
+    static size_t bytes(uint32_t slots) { return size_t(slots)*kStride; }
 };
 
 __device__ __forceinline__ uint32_t ldNode(const uint32_t *__restrict__ p) { return __ldg(p); }
@@ -158,19 +192,25 @@ enum : int { kMiss = 0, kHitLeaf = 1, kHitLod = 2 };
 //   voxelOut  leaf word index, or parent | childShift << 60 for LOD exits
 // LOD == false elides the rayScale test (rayScale == 0 can never pass it:
 // maxTC*0 is +-0 or NaN, scaleExp2 > 0).
-template <bool FAST, bool LOD, typename IdxT>
+//
+// Inside the loop min/max are FMNMX in both flavours: every operand there is a
+// finite p*dT - bT with p*dT != 0, which can be +0 but never -0 or NaN, so
+// FMNMX and the reference's (b < a) ? b : a select the same bits.
+template <bool FAST, bool LOD, typename IdxT, int THREADS>
 __device__ __forceinline__ int raymarch(const uint32_t *__restrict__ octree, float ox, float oy, float oz,
-                                        float dx, float dy, float dz, float rayScale, SmemStack<IdxT> stack,
+                                        float dx, float dy, float dz, float rayScale,
+                                        const SmemStack<IdxT, THREADS> &stack,
                                         float &tOut, uint32_t &normalOut, uint64_t &voxelOut) {
     typedef Arith<FAST> A;
+    typedef SmemStack<IdxT, THREADS> Stack;
 
     if (fabsf(dx) < 1e-4f) dx = 1e-4f;      // :217-219, sign dropped on purpose
     if (fabsf(dy) < 1e-4f) dy = 1e-4f;
     if (fabsf(dz) < 1e-4f) dz = 1e-4f;
 
-    float dTx = __fdiv_rn(1.0f, -fabsf(dx)); // :221-223
-    float dTy = __fdiv_rn(1.0f, -fabsf(dy));
-    float dTz = __fdiv_rn(1.0f, -fabsf(dz));
+    const float dTx = __fdiv_rn(1.0f, -fabsf(dx)); // :221-223
+    const float dTy = __fdiv_rn(1.0f, -fabsf(dy));
+    const float dTz = __fdiv_rn(1.0f, -fabsf(dz));
 
     float bTx = mulRn(dTx, ox);              // :225-227
     float bTy = mulRn(dTy, oy);
@@ -180,10 +220,13 @@ __device__ __forceinline__ int raymarch(const uint32_t *__restrict__ octree, flo
     if (dx > 0.0f) { octantMask ^= 1; bTx = A::mulsub(3.0f, dTx, bTx); }
     if (dy > 0.0f) { octantMask ^= 2; bTy = A::mulsub(3.0f, dTy, bTy); }
     if (dz > 0.0f) { octantMask ^= 4; bTz = A::mulsub(3.0f, dTz, bTz); }
+    // keep the mask in a register: ptxas otherwise re-derives it from the
+    // direction signs on every trip round the loop (12 extra instructions)
+    asm volatile("" : "+r"(octantMask));
 
-    float minT = A::max2(A::pow2mulsub(2.0f, dTx, bTx), A::max2(A::pow2mulsub(2.0f, dTy, bTy), A::pow2mulsub(2.0f, dTz, bTz)));
-    float maxT = A::min2(subRn(dTx, bTx), A::min2(subRn(dTy, bTy), subRn(dTz, bTz)));
-    minT = A::max2(minT, 0.0f);
+    float minT = maxStd(A::pow2mulsub(2.0f, dTx, bTx), maxStd(A::pow2mulsub(2.0f, dTy, bTy), A::pow2mulsub(2.0f, dTz, bTz)));
+    float maxT = minStd(subRn(dTx, bTx), minStd(subRn(dTy, bTy), subRn(dTz, bTz)));
+    minT = maxStd(minT, 0.0f);
 
     uint32_t current = 0;
     uint32_t farWord = 0;
@@ -192,26 +235,28 @@ __device__ __forceinline__ int raymarch(const uint32_t *__restrict__ octree, flo
     float posX = 1.0f, posY = 1.0f, posZ = 1.0f;
     int scale = kMaxScale - 1;
     float scaleExp2 = 0.5f;
+    uint32_t sp = stack.top;                 // slot of the current scale
 
     if (A::mulsub(1.5f, dTx, bTx) > minT) { idx ^= 1; posX = 1.5f; }   // :248-250
     if (A::mulsub(1.5f, dTy, bTy) > minT) { idx ^= 2; posY = 1.5f; }
     if (A::mulsub(1.5f, dTz, bTz) > minT) { idx ^= 4; posZ = 1.5f; }
 
-    while (scale < kMaxScale) {
+    for (;;) {
         if (current == 0) {
             // descriptor and its possible far word (bit 17) in flight together;
             // the node array carries one padding word so parent + 1 is always readable
-            current = ldNode(octree + parent);
-            farWord = ldNode(octree + parent + 1);
+            const uint32_t *node = octree + parent;
+            current = ldNode(node);
+            farWord = ldNode(node + 1);
         }
 
-        float cornerTX = A::mulsub(posX, dTx, bTx);   // :256-259
-        float cornerTY = A::mulsub(posY, dTy, bTy);
-        float cornerTZ = A::mulsub(posZ, dTz, bTz);
-        float maxTC = A::min2(cornerTX, A::min2(cornerTY, cornerTZ));
+        const float cornerTX = A::mulsub(posX, dTx, bTx);   // :256-259
+        const float cornerTY = A::mulsub(posY, dTy, bTy);
+        const float cornerTZ = A::mulsub(posZ, dTz, bTz);
+        const float maxTC = fminf(cornerTX, fminf(cornerTY, cornerTZ));
 
-        uint32_t childShift = idx ^ octantMask;
-        uint32_t childMasks = current << childShift;
+        const uint32_t childShift = idx ^ octantMask;
+        const uint32_t childMasks = current << childShift;
 
         if ((childMasks & 0x8000u) && minT <= maxT) {
             if (LOD && mulRn(maxTC, rayScale) >= scaleExp2) {   // :265-268
@@ -220,12 +265,7 @@ __device__ __forceinline__ int raymarch(const uint32_t *__restrict__ octree, flo
                 return kHitLod;
             }
 
-            float maxTV = A::min2(maxT, maxTC);
-            float half = mulRn(scaleExp2, 0.5f);
-            float centerTX = A::pow2muladd(half, dTx, cornerTX);   // half is a power of two
-            float centerTY = A::pow2muladd(half, dTy, cornerTY);
-            float centerTZ = A::pow2muladd(half, dTz, cornerTZ);
-
+            const float maxTV = fminf(maxT, maxTC);
             if (minT <= maxTV) {
                 IdxT childOffset = IdxT(current >> 18);
                 if (current & 0x20000u) {                      // :278-279
@@ -243,19 +283,25 @@ __device__ __forceinline__ int raymarch(const uint32_t *__restrict__ octree, flo
                     return kHitLeaf;
                 }
 
-                stack.push(kMaxScale - 1 - scale, parent, maxT);   // :287-288
+                Stack::store(sp, parent, maxT);                // :287-288
+                sp += Stack::kStride;
 
-                uint32_t siblings = uint32_t(__popc(childMasks & 127u));
+                // siblings before this child, doubled when the block is far-interleaved (bit 16), :290-293
+                const uint32_t siblings = uint32_t(__popc(childMasks & 127u)) << ((current >> 16) & 1u);
                 parent += childOffset + IdxT(siblings);
-                if (current & 0x10000u) parent += IdxT(siblings);
 
-                idx = 0;
+                const float half = mulRn(scaleExp2, 0.5f);
+                const float centerTX = A::pow2muladd(half, dTx, cornerTX);   // half is a power of two
+                const float centerTY = A::pow2muladd(half, dTy, cornerTY);
+                const float centerTZ = A::pow2muladd(half, dTz, cornerTZ);
                 scale--;
                 scaleExp2 = half;
 
-                if (centerTX > minT) { idx ^= 1; posX = addRn(posX, scaleExp2); }
-                if (centerTY > minT) { idx ^= 2; posY = addRn(posY, scaleExp2); }
-                if (centerTZ > minT) { idx ^= 4; posZ = addRn(posZ, scaleExp2); }
+                const bool upX = centerTX > minT, upY = centerTY > minT, upZ = centerTZ > minT;
+                posX = upX ? addRn(posX, half) : posX;
+                posY = upY ? addRn(posY, half) : posY;
+                posZ = upZ ? addRn(posZ, half) : posZ;
+                idx = (upX ? 1u : 0u) | (upY ? 2u : 0u) | (upZ ? 4u : 0u);
 
                 maxT = maxTV;
                 current = 0;
@@ -264,9 +310,9 @@ __device__ __forceinline__ int raymarch(const uint32_t *__restrict__ octree, flo
         }
 
         uint32_t stepMask = 0;                                  // :310-316
-        if (cornerTX <= maxTC) { stepMask ^= 1; posX = subRn(posX, scaleExp2); }
-        if (cornerTY <= maxTC) { stepMask ^= 2; posY = subRn(posY, scaleExp2); }
-        if (cornerTZ <= maxTC) { stepMask ^= 4; posZ = subRn(posZ, scaleExp2); }
+        if (cornerTX <= maxTC) { stepMask |= 1; posX = subRn(posX, scaleExp2); }
+        if (cornerTY <= maxTC) { stepMask |= 2; posY = subRn(posY, scaleExp2); }
+        if (cornerTZ <= maxTC) { stepMask |= 4; posZ = subRn(posZ, scaleExp2); }
 
         minT = maxTC;
         idx ^= stepMask;
@@ -276,27 +322,27 @@ __device__ __forceinline__ int raymarch(const uint32_t *__restrict__ octree, flo
             if (stepMask & 1) differingBits |= __float_as_uint(posX) ^ __float_as_uint(addRn(posX, scaleExp2));
             if (stepMask & 2) differingBits |= __float_as_uint(posY) ^ __float_as_uint(addRn(posY, scaleExp2));
             if (stepMask & 4) differingBits |= __float_as_uint(posZ) ^ __float_as_uint(addRn(posZ, scaleExp2));
-            // reference: exponent of (float)differingBits; differingBits < 2^24
+            // reference: exponent of (float)differingBits. differingBits < 2^24
             // always (positions stay in [0.5, 2)), so that is the index of the
-            // highest set bit
+            // highest set bit; bit 23 set <=> the ray left the root (:341-342)
+            if (differingBits > 0x7FFFFFu) return kMiss;
             scale = 31 - __clz(int(differingBits));
             scaleExp2 = __uint_as_float(uint32_t(scale - kMaxScale + 127) << 23);
 
-            if (scale >= kMaxScale) return kMiss;               // left the root (:341-342)
-            stack.pop(kMaxScale - 1 - scale, parent, maxT);
+            sp = stack.slot(scale);
+            Stack::load(sp, parent, maxT);
 
-            uint32_t shX = __float_as_uint(posX) >> scale;
-            uint32_t shY = __float_as_uint(posY) >> scale;
-            uint32_t shZ = __float_as_uint(posZ) >> scale;
+            const uint32_t shX = __float_as_uint(posX) >> scale;   // truncate positions to the `scale` grid
+            const uint32_t shY = __float_as_uint(posY) >> scale;
+            const uint32_t shZ = __float_as_uint(posZ) >> scale;
             posX = __uint_as_float(shX << scale);
             posY = __uint_as_float(shY << scale);
             posZ = __uint_as_float(shZ << scale);
-            idx = (shX & 1) | ((shY & 1) << 1) | ((shZ & 1) << 2);
+            idx = (shX & 1u) | ((shY & 1u) << 1) | ((shZ & 1u) << 2);
 
             current = 0;
         }
     }
-    return kMiss;
 }
 
 } // namespace svo

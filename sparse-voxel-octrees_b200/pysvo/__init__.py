@@ -128,6 +128,8 @@ def lib():
         "svo_frame_constants_from_camera": (i32, [P(Camera), P(f32), i32, i32, i32, P(FrameConstants)]),
         "svo_render_frame": (i32, [vp, P(Camera), P(FrameDesc), vp, vp, P(FrameStats)]),
         "svo_render_frame_device": (i32, [vp, P(Camera), P(FrameDesc), vp, vp, vp, P(FrameStats), i32]),
+        "svo_render_frame_async": (i32, [vp, P(Camera), P(FrameDesc), vp, vp, i32, P(i32)]),
+        "svo_frame_wait": (i32, [vp, P(FrameDesc), i32, P(FrameStats)]),
         "svo_device_alloc": (i32, [i32, C.c_size_t, P(vp)]),
         "svo_device_free": (i32, [i32, vp]),
         "svo_device_memset": (i32, [i32, vp, i32, C.c_size_t]),
@@ -366,6 +368,21 @@ class VoxelOctree:
         _check(lib().svo_render_frame(self._h, C.byref(cam), C.byref(desc), _ptr(rgba), _ptr(depth),
                                       C.byref(stats) if stats is not None else None))
         return rgba, depth, stats
+
+    def render_frame_async(self, cam: Camera, width, height, rgba, strips=16, flavour=FLAVOUR_FAST, depth=None,
+                           want_stats=False):
+        """Pipelined host-buffer variant: returns a (desc, ticket) pair for frame_wait. Up to two in flight."""
+        desc = FrameDesc(width, height, strips, flavour, 0, 1)
+        ticket = C.c_int(0)
+        _check(lib().svo_render_frame_async(self._h, C.byref(cam), C.byref(desc), _ptr(rgba), _ptr(depth),
+                                            1 if want_stats else 0, C.byref(ticket)))
+        return desc, ticket.value
+
+    def frame_wait(self, pending, want_stats=False):
+        desc, ticket = pending
+        stats = FrameStats() if want_stats else None
+        _check(lib().svo_frame_wait(self._h, C.byref(desc), ticket, C.byref(stats) if stats is not None else None))
+        return stats
 
     def render_frame_device(self, cam: Camera, width, height, d_rgba, strips=16, flavour=FLAVOUR_FAST, tile_rank=0,
                             tile_world=1, d_depth=0, stream=0, want_stats=False):

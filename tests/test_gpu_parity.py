@@ -175,6 +175,40 @@ def test_frame_tile_interleave_reassembles(pysvo, gpu_dragon, pins):
         buf.free()
 
 
+def test_pipelined_frames_match_synchronous(pysvo, gpu_dragon, pins):
+    """svo_render_frame_async: two frames in flight, beam pass of frame i+1 overlapping the fine pass of
+    frame i, copies on their own stream -- every frame must equal the synchronous result."""
+    cams = [_cam(pysvo, e) for e in pins["cameras"]] * 3
+    want = [gpu_dragon.render_frame(c, 1280, 720, strips=16, flavour=pysvo.FLAVOUR_VALIDATION, want_stats=True) for c in cams[:5]]
+    bufs = [pysvo.PinnedArray((720, 1280), np.uint32) for _ in range(2)]
+    pending = [None, None]
+    got = []
+    for k, c in enumerate(cams):
+        slot = k & 1
+        if pending[slot] is not None:
+            st = gpu_dragon.frame_wait(pending[slot], want_stats=True)
+            got.append((bufs[slot].array.copy(), st))
+        pending[slot] = gpu_dragon.render_frame_async(c, 1280, 720, bufs[slot].array, strips=16,
+                                                      flavour=pysvo.FLAVOUR_VALIDATION, want_stats=True)
+    with pytest.raises(pysvo.SvoError):     # a third frame in flight is refused, not silently serialised
+        gpu_dragon.render_frame_async(cams[0], 1280, 720, bufs[len(cams) & 1].array, strips=16)
+    for slot in ((len(cams)) & 1, (len(cams) + 1) & 1):
+        st = gpu_dragon.frame_wait(pending[slot], want_stats=True)
+        got.append((bufs[slot].array.copy(), st))
+    assert len(got) == len(cams)
+    for k, (img, st) in enumerate(got):
+        ref_img, _, ref_st = want[k % 5]
+        assert np.array_equal(img, ref_img), f"frame {k}"
+        assert (st.fine_rays, st.coarse_rays, st.tiles_rendered) == (ref_st.fine_rays, ref_st.coarse_rays, ref_st.tiles_rendered)
+    # back-to-back device-variant frames on one stream (the bench's timed loop) stay correct too
+    buf = pysvo.DeviceBuffer(gpu_dragon.device, 1280 * 720 * 4)
+    for k in range(12):
+        gpu_dragon.render_frame_device(cams[k], 1280, 720, buf.ptr, strips=16, flavour=pysvo.FLAVOUR_VALIDATION)
+    pysvo.device_synchronize(gpu_dragon.device)
+    assert np.array_equal(buf.to_host(np.uint32).reshape(720, 1280), want[11 % 5][0])
+    buf.free()
+
+
 def test_single_ray_facade_semantics(pysvo, port, gpu_dragon, dragon_words):
     """VoxelOctree::raymarch leaves `normal` / `t` untouched on a miss and `normal` on a LOD exit."""
     words, _ = dragon_words

@@ -1,0 +1,175 @@
+#!/usr/bin/env python
+"""Kernel design tool: replays per-ray loop traces from the instrumented oracle through warp-level cost
+models of different loop organisations (no GPU needed). Costs are SASS instruction counts per section
+read off the ncu source page of the current kernel.
+
+    python tools/simulate_divergence.py [scene] [W H] [tile stride]
+"""
+import ctypes as C
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "sparse-voxel-octrees_b200"))
+import pysvo  # noqa: E402
+from oracle.pyoracle import Port, Frame  # noqa: E402
+
+
+def trace(scene="sdf2048", W=3840, H=2160, stride=64, cam=(20.0, 40.0, 0.9), max_ops=512):
+    port = Port()
+    path = ROOT / "scenes" / "_cache" / f"{scene}.oct" if scene != "dragon" else ROOT / "tests/golden/XYZRGB-Dragon.oct"
+    words, center = pysvo.oct_read(path)
+    m, v = port.orbit_camera(*cam)
+    f = port.frame_constants(m, v, center, W, H, 16)
+    L = port.lib
+    L.svo_oracle_trace_fine_warps.restype = C.c_int64
+    L.svo_oracle_trace_fine_warps.argtypes = [np.ctypeslib.ndpointer(np.uint32), C.POINTER(Frame), C.c_int,
+                                              np.ctypeslib.ndpointer(np.uint8), C.c_uint32,
+                                              np.ctypeslib.ndpointer(np.uint32), C.c_int64]
+    max_warps = 20000
+    ops = np.zeros((max_warps * 32, max_ops), np.uint8)
+    counts = np.zeros(max_warps * 32, np.uint32)
+    n = L.svo_oracle_trace_fine_warps(words, C.byref(f), stride, ops, max_ops, counts, max_warps)
+    return ops[:n * 32].reshape(n, 32, max_ops), counts[:n * 32].reshape(n, 32)
+
+
+P, A, Q, Lf, X = ord('P'), ord('A'), ord('Q'), ord('L'), ord('X')
+
+
+def scheme_single_loop(ops, counts, c):
+    """Current kernel: every trip all live lanes run the header, then the union of the paths they need."""
+    total = 0.0
+    lanes_useful = 0.0
+    trips = 0
+    for w in range(ops.shape[0]):
+        n = counts[w]
+        T = int(n.max())
+        if T == 0:
+            continue
+        o = ops[w][:, :T]
+        live = np.arange(T)[None, :] < n[:, None]
+        isP = (o == P) & live
+        isL = (o == Lf) & live
+        isA = ((o == A) | (o == Q) | (o == X)) & live
+        isQ = ((o == Q) | (o == X)) & live
+        anyP, anyL, anyA, anyQ = isP.any(0), isL.any(0), isA.any(0), isQ.any(0)
+        total += T * c['H'] + (anyP | anyL).sum() * c['V'] + anyP.sum() * c['P'] + anyL.sum() * c['L'] \
+            + anyA.sum() * c['A'] + anyQ.sum() * c['Q'] + c['pro']
+        trips += T
+        lanes_useful += live.sum() * c['H'] + (isP | isL).sum() * c['V'] + isP.sum() * c['P'] + isL.sum() * c['L'] \
+            + isA.sum() * c['A'] + isQ.sum() * c['Q'] + (n > 0).sum() * c['pro']
+    return total, lanes_useful / 32.0, trips
+
+
+def scheme_while_while(ops, counts, c):
+    """Outer trip = descend phase (lanes whose next op is P/L loop together) then step phase (A/Q lanes loop
+    until their next op is a P/L)."""
+    total = 0.0
+    for w in range(ops.shape[0]):
+        n = counts[w].astype(np.int64)
+        if n.max() == 0:
+            continue
+        pos = np.zeros(32, np.int64)
+        o = ops[w]
+        total += c['pro']
+        while True:
+            live = pos < n
+            if not live.any():
+                break
+            # descend phase
+            while True:
+                cur = np.where(live, o[np.arange(32), np.minimum(pos, n - 1 + (n == 0))], 0)
+                want = live & ((cur == P) | (cur == Lf))
+                if not want.any():
+                    break
+                total += c['H'] + c['V'] + (c['P'] if (cur[want] == P).any() else 0) + (c['L'] if (cur[want] == Lf).any() else 0)
+                pos = pos + want
+                live = pos < n
+            # step phase
+            while True:
+                cur = np.where(live, o[np.arange(32), np.minimum(pos, n - 1 + (n == 0))], 0)
+                want = live & ((cur == A) | (cur == Q) | (cur == X))
+                if not want.any():
+                    break
+                total += c['H'] + c['A'] + (c['Q'] if ((cur[want] == Q) | (cur[want] == X)).any() else 0)
+                pos = pos + want
+                live = pos < n
+    return total
+
+
+def main():
+    scene = sys.argv[1] if len(sys.argv) > 1 else "sdf2048"
+    W, H = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (3840, 2160)
+    stride = int(sys.argv[4]) if len(sys.argv) > 4 else 64
+    ops, counts = trace(scene, W, H, stride)
+    nw = ops.shape[0]
+    rays = int((counts > 0).sum())
+    print(f"{nw} warps, {rays} rays, trips/ray {counts[counts > 0].mean():.2f}, max {counts.max()}")
+    flat = ops[np.arange(ops.shape[2])[None, None, :] < counts[:, :, None]]
+    for ch in 'PAQLX':
+        print(f"  {ch}: {(flat == ord(ch)).sum() / rays:.2f} per ray")
+    for k in range(3):
+        w, l = nw // 2 + k, 5
+        print("  sample:", bytes(ops[w, l, :counts[w, l]]).decode())
+    cur = dict(H=18, V=9, P=44, A=13, Q=39, L=110, pro=264)
+    tight = dict(H=17, V=8, P=32, A=13, Q=26, L=105, pro=120)
+    for name, c in (("current SASS", cur), ("tightened", tight)):
+        t0, useful, trips = scheme_single_loop(ops, counts, c)
+        t1 = scheme_while_while(ops, counts, c)
+        print(f"[{name}] single loop: {t0 / rays:.1f} warp-instr/ray, simt eff {useful / t0:.3f}, warp trips/warp {trips / nw:.1f}"
+              f" | while-while: {t1 / rays:.1f} warp-instr/ray ({t0 / t1:.2f}x)")
+
+
+if __name__ == "__main__":
+    main()
+
+
+def scheme_vote(ops, counts, c, mode="majority"):
+    """Each round the warp runs ONE body (descend or step), picked by vote; other lanes wait with their
+    header result cached."""
+    total = 0.0
+    for w in range(ops.shape[0]):
+        n = counts[w].astype(np.int64)
+        if n.max() == 0:
+            continue
+        pos = np.zeros(32, np.int64)
+        o = ops[w]
+        total += c['pro']
+        ar = np.arange(32)
+        fresh = n > 0          # lanes that need a header evaluation
+        while True:
+            live = pos < n
+            if not live.any():
+                break
+            cur = np.where(live, o[ar, np.minimum(pos, np.maximum(n - 1, 0))], 0)
+            wantP = live & ((cur == P) | (cur == Lf))
+            wantA = live & ((cur == A) | (cur == Q) | (cur == X))
+            if fresh.any():
+                total += c['H']
+            nP, nA = wantP.sum(), wantA.sum()
+            if mode == "majority":
+                pickP = nP >= nA
+            else:  # prefer stepping lanes so that they catch up into descents
+                pickP = nA == 0
+            if pickP:
+                total += c['V'] + (c['P'] if (cur[wantP] == P).any() else 0) + (c['L'] if (cur[wantP] == Lf).any() else 0)
+                pos = pos + wantP
+                fresh = wantP.copy()
+            else:
+                total += c['A'] + (c['Q'] if ((cur[wantA] == Q) | (cur[wantA] == X)).any() else 0)
+                pos = pos + wantA
+                fresh = wantA.copy()
+    return total
+
+
+if __name__ == "__main__" and len(sys.argv) > 5 and sys.argv[5] == "vote":
+    ops, counts = trace(sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]))
+    rays = int((counts > 0).sum())
+    now = dict(H=18, V=9, P=28, A=13, Q=33, L=105, pro=150)
+    t0, useful, trips = scheme_single_loop(ops, counts, now)
+    print(f"single loop {t0 / rays:.1f}  eff {useful / t0:.3f}")
+    for mode in ("majority", "step-first"):
+        print(mode, f"{scheme_vote(ops, counts, now, mode) / rays:.1f}")
