@@ -288,22 +288,25 @@ def run_own(args):
 
     # ---- framebuffer: rank 0 owns it; other ranks map it and store their tiles into it over NVLink
     nbytes = W * H * 4
-    fb = None
+    fbs = []
+    fb_ptrs = [0, 0]
     if rank == 0:
-        fb = pysvo.DeviceBuffer(local_rank, nbytes)
-        fb.zero()
-        fb_ptr = fb.ptr
+        for i in range(2):          # two framebuffers: frame k is copied out while frame k+1 is rendered
+            fbs.append(pysvo.DeviceBuffer(local_rank, nbytes))
+            fbs[i].zero()
+            fb_ptrs[i] = fbs[i].ptr
     if world > 1:
-        handle = [fb.ipc_export() if rank == 0 else None]
+        handle = [[f.ipc_export() for f in fbs] if rank == 0 else None]
         dist.broadcast_object_list(handle, src=0)
         if rank != 0:
-            fb_ptr = pysvo.ipc_open(local_rank, handle[0])
+            fb_ptrs = [pysvo.ipc_open(local_rank, hdl) for hdl in handle[0]]
+    fb_ptr = fb_ptrs[0]
     flag = torch.zeros(1, device="cuda", dtype=torch.int32) if world > 1 else None
 
-    def frame(k, want_stats=False):
-        st = tree.render_frame_device(cams[k % ORBIT], W, H, fb_ptr, strips=STRIPS, flavour=flavour, tile_rank=rank,
-                                      tile_world=world, stream=stream, want_stats=want_stats)
-        if world > 1:
+    def frame(k, want_stats=False, fb=None, sync=True):
+        st = tree.render_frame_device(cams[k % ORBIT], W, H, fb or fb_ptr, strips=STRIPS, flavour=flavour,
+                                      tile_rank=rank, tile_world=world, stream=stream, want_stats=want_stats)
+        if world > 1 and sync:
             dist.all_reduce(flag)      # frame complete on every rank before rank 0 may use it
         return st
 
@@ -368,14 +371,30 @@ def run_own(args):
             if pnd is not None:
                 tree.frame_wait(pnd)
     else:
-        import ctypes as C
+        # every rank stores its tiles into rank 0's framebuffer k & 1 over NVLink; after the frame barrier
+        # rank 0 copies it to pinned host memory on a side stream while frame k+1 is rendered into the other one
+        host2 = pysvo.PinnedArray((H, W), np.uint32) if rank == 0 else None
+        hosts = [host.array, host2.array] if rank == 0 else None
+        copy_stream = torch.cuda.Stream()
+        copied = [None, None]
+        main = torch.cuda.current_stream()
         for k in range(warmup, warmup + e2e_steps):
-            frame(k)
-            torch.cuda.synchronize()
+            slot = k & 1
+            frame(k, fb=fb_ptrs[slot], sync=False)
+            if rank == 0 and copied[slot ^ 1] is not None:
+                main.wait_event(copied[slot ^ 1])   # framebuffer slot^1 is rewritten by frame k+1 after this barrier
+            dist.all_reduce(flag)
             if rank == 0:
-                pysvo._check(pysvo.lib().svo_device_to_host(local_rank, C.c_void_p(host.array.ctypes.data),
-                                                            C.c_void_p(fb_ptr), nbytes))
-            barrier()
+                if copied[slot] is not None:
+                    copied[slot].synchronize()      # frame k-2 is in host memory: its pinned buffer is free again
+                copy_stream.wait_stream(main)
+                pysvo.device_to_host_async(local_rank, hosts[slot], fb_ptrs[slot], nbytes, copy_stream.cuda_stream)
+                copied[slot] = torch.cuda.Event()
+                copied[slot].record(copy_stream)
+        if rank == 0:
+            for ev in copied:
+                if ev is not None:
+                    ev.synchronize()
     torch.cuda.synchronize()
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)

@@ -188,6 +188,23 @@ typedef struct svo_frame_stats {
     float fine_ms;              /* device time of the tile classifier + fine-pass kernel */
 } svo_frame_stats;
 
+/* Geometry of the reference's strip / tile decomposition for one configuration
+ * (Main.cpp:351-362), host only. The depth buffer has `corners` floats; tiles are numbered
+ * strip by strip, row by row; with a tile interleave tile t belongs to rank t % tile_world. */
+typedef struct svo_frame_layout {
+    int32_t n_strips;           /* strips that own at least one row */
+    int32_t strip_rows;         /* rows per strip ("stride", Main.cpp:351) */
+    int32_t tiles_x;            /* corner columns per strip (Main.cpp:359) */
+    int32_t tiles_y_full;       /* corner rows of a full strip (Main.cpp:360) */
+    int32_t tiles_y_last;       /* corner rows of the last strip */
+    int32_t tile_cols;          /* tiles per tile row */
+    int32_t tiles;              /* 8x8 tiles in the frame */
+    int32_t corners;            /* beam-pass rays per frame == depth buffer length */
+} svo_frame_layout;
+SVO_API int svo_frame_get_layout(int width, int height, int strips, svo_frame_layout *out);
+/* Pixel rectangle [x0,x1) x [y0,y1) of tile `tile` (clipped to its strip and the image). */
+SVO_API int svo_frame_tile_rect(int width, int height, int strips, int tile, int32_t rect[4]);
+
 /* Host-buffer variant: rgba (width*height uint32, the reference's backBuffer
  * layout 0xFF000000|b<<16|g<<8|r, Main.cpp:128-134; pitch = width*4) and the
  * optional coarse depth buffer (per strip tilesX*tilesY floats, strip after
@@ -228,6 +245,8 @@ SVO_API int svo_device_free(int device, void *p);
 SVO_API int svo_device_memset(int device, void *p, int value, size_t bytes);
 SVO_API int svo_device_to_host(int device, void *host_dst, const void *device_src, size_t bytes);
 SVO_API int svo_host_to_device(int device, void *device_dst, const void *host_src, size_t bytes);
+/* Asynchronous on `stream` (a cudaStream_t); host memory should be page-locked. */
+SVO_API int svo_device_to_host_async(int device, void *host_dst, const void *device_src, size_t bytes, void *stream);
 SVO_API int svo_device_synchronize(int device);
 #define SVO_IPC_HANDLE_BYTES 64
 /* Export a device allocation (made with svo_device_alloc) so that another

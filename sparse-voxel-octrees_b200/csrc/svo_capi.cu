@@ -221,8 +221,7 @@ int createTree(const uint32_t *words, uint64_t nWords, const float center[3], in
 
 // The running sums renderBatch / renderTile use for screen coordinates
 // (reference src/Main.cpp:97-100, 167-170), tabulated once per configuration.
-int buildPlan(svo_tree *tree, int width, int height, int strips, FramePlan &plan) {
-    svo::FramePlanDev &p = plan.dev;
+void planGeometry(int width, int height, int strips, svo::FramePlanDev &p) {
     p.width = width;
     p.height = height;
     p.stripRows = (height - 1)/strips + 1;                       // Main.cpp:351
@@ -237,6 +236,11 @@ int buildPlan(svo_tree *tree, int width, int height, int strips, FramePlan &plan
     p.totalTileRows = (p.nStrips - 1)*p.tileRowsFull + p.tileRowsLast;
     p.totalTiles = p.totalTileRows*p.tileCols;
     p.totalCorners = (p.nStrips - 1)*p.tilesX*p.tilesYFull + p.tilesX*p.tilesYLast;
+}
+
+int buildPlan(svo_tree *tree, int width, int height, int strips, FramePlan &plan) {
+    svo::FramePlanDev &p = plan.dev;
+    planGeometry(width, height, strips, p);
 
     const float scale = 2.0f/width;                              // Main.cpp:156
     const float tileScale = 8*scale;                             // Main.cpp:157
@@ -581,6 +585,45 @@ int svo_frame_constants_from_camera(const svo_camera *cam, const float center[3]
 
 /* ---- frames ------------------------------------------------------------------ */
 
+int svo_frame_get_layout(int width, int height, int strips, svo_frame_layout *out) {
+    if (!out) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_frame_get_layout: null argument");
+    svo_frame_desc d = {width, height, strips, SVO_FLAVOUR_VALIDATION, 0, 1, {0, 0}};
+    int st = checkDesc(&d);
+    if (st != SVO_OK) return st;
+    svo::FramePlanDev p{};
+    planGeometry(width, height, strips, p);
+    out->n_strips = p.nStrips;
+    out->strip_rows = p.stripRows;
+    out->tiles_x = p.tilesX;
+    out->tiles_y_full = p.tilesYFull;
+    out->tiles_y_last = p.tilesYLast;
+    out->tile_cols = p.tileCols;
+    out->tiles = p.totalTiles;
+    out->corners = p.totalCorners;
+    return SVO_OK;
+}
+
+int svo_frame_tile_rect(int width, int height, int strips, int tile, int32_t rect[4]) {
+    if (!rect) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_frame_tile_rect: null argument");
+    svo_frame_desc d = {width, height, strips, SVO_FLAVOUR_VALIDATION, 0, 1, {0, 0}};
+    int st = checkDesc(&d);
+    if (st != SVO_OK) return st;
+    svo::FramePlanDev p{};
+    planGeometry(width, height, strips, p);
+    if (tile < 0 || tile >= p.totalTiles) return fail(SVO_ERR_INVALID_ARGUMENT, "tile %d out of range [0, %d)", tile, p.totalTiles);
+    // same arithmetic as classifyTilesKernel
+    int tileRow = tile/p.tileCols, tx = tile - tileRow*p.tileCols;
+    int strip = tileRow/p.tileRowsFull < p.nStrips - 1 ? tileRow/p.tileRowsFull : p.nStrips - 1;
+    int ty = tileRow - strip*p.tileRowsFull;
+    int stripY0 = strip*p.stripRows;
+    int yEnd = stripY0 + p.stripRows < height ? stripY0 + p.stripRows : height;
+    rect[0] = tx*8;
+    rect[1] = stripY0 + ty*8;
+    rect[2] = rect[0] + 8 < width ? rect[0] + 8 : width;
+    rect[3] = rect[1] + 8 < yEnd ? rect[1] + 8 : yEnd;
+    return SVO_OK;
+}
+
 int svo_render_frame_device(svo_tree *tree, const svo_camera *cam, const svo_frame_desc *desc, uint32_t *d_rgba,
                             float *d_depth, void *stream, svo_frame_stats *stats, int sync_stats) {
     if (!tree || !cam || !d_rgba) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_render_frame_device: null argument");
@@ -695,6 +738,12 @@ int svo_device_memset(int device, void *p, int value, size_t bytes) {
 int svo_device_to_host(int device, void *host_dst, const void *device_src, size_t bytes) {
     SVO_DEVICE(device);
     SVO_CUDA(cudaMemcpy(host_dst, device_src, bytes, cudaMemcpyDeviceToHost));
+    return SVO_OK;
+}
+
+int svo_device_to_host_async(int device, void *host_dst, const void *device_src, size_t bytes, void *stream) {
+    SVO_DEVICE(device);
+    SVO_CUDA(cudaMemcpyAsync(host_dst, device_src, bytes, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
     return SVO_OK;
 }
 

@@ -77,6 +77,11 @@ class FrameStats(C.Structure):
         return int(self.coarse_rays + self.fine_rays)
 
 
+class FrameLayout(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("n_strips", "strip_rows", "tiles_x", "tiles_y_full", "tiles_y_last",
+                                         "tile_cols", "tiles", "corners")]
+
+
 class TreeInfo(C.Structure):
     _fields_ = [("n_words", C.c_uint64), ("center", C.c_float * 3), ("depth", C.c_uint32), ("device", C.c_int32),
                 ("device_bytes", C.c_uint64)]
@@ -126,6 +131,8 @@ def lib():
         "svo_raymarch": (i32, [vp, P(f32), P(f32), f32, P(C.c_uint32), P(f32), P(i32)]),
         "svo_orbit_camera": (None, [f32, f32, f32, P(Camera)]),
         "svo_frame_constants_from_camera": (i32, [P(Camera), P(f32), i32, i32, i32, P(FrameConstants)]),
+        "svo_frame_get_layout": (i32, [i32, i32, i32, P(FrameLayout)]),
+        "svo_frame_tile_rect": (i32, [i32, i32, i32, i32, P(C.c_int32)]),
         "svo_render_frame": (i32, [vp, P(Camera), P(FrameDesc), vp, vp, P(FrameStats)]),
         "svo_render_frame_device": (i32, [vp, P(Camera), P(FrameDesc), vp, vp, vp, P(FrameStats), i32]),
         "svo_render_frame_async": (i32, [vp, P(Camera), P(FrameDesc), vp, vp, i32, P(i32)]),
@@ -135,6 +142,7 @@ def lib():
         "svo_device_memset": (i32, [i32, vp, i32, C.c_size_t]),
         "svo_device_to_host": (i32, [i32, vp, vp, C.c_size_t]),
         "svo_host_to_device": (i32, [i32, vp, vp, C.c_size_t]),
+        "svo_device_to_host_async": (i32, [i32, vp, vp, C.c_size_t, vp]),
         "svo_device_synchronize": (i32, [i32]),
         "svo_ipc_export": (i32, [i32, vp, vp]),
         "svo_ipc_open": (i32, [i32, vp, P(vp)]),
@@ -284,6 +292,11 @@ def ipc_close(device, ptr: int):
     _check(lib().svo_ipc_close(int(device), C.c_void_p(ptr)))
 
 
+def device_to_host_async(device, host_array, device_ptr, nbytes, stream=0):
+    _check(lib().svo_device_to_host_async(int(device), _ptr(host_array), C.c_void_p(device_ptr), int(nbytes),
+                                          C.c_void_p(stream or None)))
+
+
 def device_synchronize(device=0):
     _check(lib().svo_device_synchronize(int(device)))
 
@@ -405,6 +418,18 @@ class VoxelOctree:
             self.close()
         except Exception:
             pass
+
+
+def frame_layout(width, height, strips) -> FrameLayout:
+    out = FrameLayout()
+    _check(lib().svo_frame_get_layout(width, height, strips, C.byref(out)))
+    return out
+
+
+def tile_rect(width, height, strips, tile):
+    r = (C.c_int32 * 4)()
+    _check(lib().svo_frame_tile_rect(width, height, strips, int(tile), r))
+    return tuple(r)
 
 
 def strip_layout(width, height, strips, tile=8):
