@@ -313,12 +313,11 @@ def run_own(args):
     # ---- rays per camera (untimed): coarse once per frame, fine summed over ranks
     n_distinct = min(ORBIT, steps + warmup)
     fine = torch.zeros(ORBIT, dtype=torch.int64, device="cuda")
-    coarse = 0
+    coarse = int(pysvo.frame_layout(W, H, STRIPS).corners)   # beam rays of the frame as the reference issues them
     kernel_ms = []
     for k in range(n_distinct):
         st = frame(k, want_stats=True)
         fine[k] = int(st.fine_rays)
-        coarse = int(st.coarse_rays)
         kernel_ms.append((st.coarse_ms, st.fine_ms))
     if world > 1:
         dist.all_reduce(fine)

@@ -171,14 +171,17 @@ typedef struct svo_frame_desc {
     int32_t strips;             /* the reference's NumThreads (Main.cpp:57): the image depends on it */
     int32_t flavour;            /* svo_flavour */
     /* Multi-GPU tile interleave: this call renders only the 8x8 tiles whose
-     * linear index % tile_world == tile_rank and touches no other pixel.
+     * column index tx % tile_world == tile_rank (vertical stripes one tile
+     * wide) and touches no other pixel; with tile_world >= 3 its beam pass
+     * traces only the tile corners next to those columns.
      * Single GPU: tile_rank = 0, tile_world = 1. */
     int32_t tile_rank, tile_world;
     int32_t reserved[2];
 } svo_frame_desc;
 
 typedef struct svo_frame_stats {
-    uint64_t coarse_rays;       /* raymarch calls of the beam pass (Main.cpp:181) by this rank */
+    uint64_t coarse_rays;       /* raymarch calls of the beam pass (Main.cpp:181) made by this rank (a subset of
+                                 * svo_frame_layout.corners when tile_world >= 3) */
     uint64_t fine_rays;         /* raymarch calls of renderTile (Main.cpp:118) by this rank */
     uint64_t tiles_rendered;
     uint64_t tiles_total;       /* tiles owned by this rank */
@@ -190,7 +193,8 @@ typedef struct svo_frame_stats {
 
 /* Geometry of the reference's strip / tile decomposition for one configuration
  * (Main.cpp:351-362), host only. The depth buffer has `corners` floats; tiles are numbered
- * strip by strip, row by row; with a tile interleave tile t belongs to rank t % tile_world. */
+ * strip by strip, row by row (tile t is in column t % tile_cols); with a tile interleave tile t
+ * belongs to rank (t % tile_cols) % tile_world. */
 typedef struct svo_frame_layout {
     int32_t n_strips;           /* strips that own at least one row */
     int32_t strip_rows;         /* rows per strip ("stride", Main.cpp:351) */
@@ -204,6 +208,8 @@ typedef struct svo_frame_layout {
 SVO_API int svo_frame_get_layout(int width, int height, int strips, svo_frame_layout *out);
 /* Pixel rectangle [x0,x1) x [y0,y1) of tile `tile` (clipped to its strip and the image). */
 SVO_API int svo_frame_tile_rect(int width, int height, int strips, int tile, int32_t rect[4]);
+/* Rank that renders tile `tile` under an interleave over `tile_world` ranks; < 0 on bad arguments. */
+SVO_API int svo_frame_tile_owner(int width, int height, int strips, int tile, int tile_world);
 
 /* Host-buffer variant: rgba (width*height uint32, the reference's backBuffer
  * layout 0xFF000000|b<<16|g<<8|r, Main.cpp:128-134; pitch = width*4) and the

@@ -65,42 +65,52 @@ struct DeviceScope {
     DeviceScope scope_(device);                                \
     if (scope_.error != cudaSuccess) return failCuda(scope_.error, "cudaSetDevice")
 
-// Everything one (width, height, strips) configuration needs on the device. Frames are
-// double-buffered (slot = frame number & 1) so that the beam pass of frame i+1 can run on the
-// tree's high-priority internal stream while the fine pass of frame i is still busy, and so
-// that the device->host copy of frame i overlaps the rendering of frame i+1.
+// Everything one (width, height, strips) configuration needs on the device. Frames cycle through a
+// ring of kRing slots (depth buffer, tile list, counters) so that the beam passes of the next frames
+// can run ahead on the tree's two high-priority internal streams while earlier fine passes are
+// still busy -- the beam pass is latency-bound (its longest ray), and with several GPUs sharing a
+// frame it would otherwise be the critical path. Host-buffer frames additionally alternate between
+// two staging framebuffers so the device->host copy of frame i overlaps the rendering of frame i+1.
+constexpr int kRing = 4;
+
 struct FramePlan {
     svo::FramePlanDev dev{};
     float *dTables = nullptr;              // dxCoarse | dyCoarse | dxFine | dyFine
-    float *dDepth[2] = {nullptr, nullptr}; // totalCorners floats each
-    svo::TileRecord *dTiles[2] = {nullptr, nullptr};   // totalTiles records each (worst case: every tile rendered)
-    svo::FrameCounters *dCounters[2] = {nullptr, nullptr};
-    svo::FrameCounters *hCounters = nullptr;            // pinned, 2 entries
-    uint32_t *dRgba[2] = {nullptr, nullptr};            // host-buffer entry points only (lazy)
-    cudaEvent_t coarseDone[2] = {nullptr, nullptr};     // beam pass of the slot finished (internal stream)
-    cudaEvent_t fineDone[2] = {nullptr, nullptr};       // last fine pass that read the slot's depth / tile list
-    cudaEvent_t copyDone[2] = {nullptr, nullptr};       // device->host copy out of dRgba[slot] finished
-    cudaEvent_t timing[2][4] = {};                      // coarse start/end, fine start/end (stats only)
-    bool fineRecorded[2] = {false, false};
+    float *dDepth[kRing] = {};             // totalCorners floats each
+    svo::TileRecord *dTiles[kRing] = {};   // totalTiles records each (worst case: every tile rendered)
+    svo::FrameCounters *dCounters[kRing] = {};
+    svo::FrameCounters *hCounters = nullptr;            // pinned, kRing entries
+    cudaEvent_t coarseDone[kRing] = {};    // beam pass of the slot finished (internal stream)
+    cudaEvent_t fineDone[kRing] = {};      // last fine pass that read the slot's depth / tile list
+    cudaEvent_t timing[kRing][4] = {};     // coarse start/end, fine start/end (stats only)
+    bool fineRecorded[kRing] = {};
+    uint64_t frameNumber = 0;
+
+    // host-buffer entry points only
+    uint32_t *dRgba[2] = {nullptr, nullptr};            // staging framebuffers (lazy)
+    cudaEvent_t copyDone[2] = {nullptr, nullptr};       // device->host copy out of dRgba[i] finished
     bool copyRecorded[2] = {false, false};
     bool pending[2] = {false, false};                   // svo_render_frame_async issued, not yet waited for
     bool pendingStats[2] = {false, false};
+    int pendingRing[2] = {0, 0};
     uint32_t pendingLaunches[2] = {0, 0};
     svo_frame_desc pendingDesc[2] = {};
-    uint64_t frameNumber = 0;
+    uint64_t hostFrameNumber = 0;
 
     void destroy() {
         if (dTables) cudaFree(dTables);
         if (hCounters) cudaFreeHost(hCounters);
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < kRing; ++b) {
             if (dDepth[b]) cudaFree(dDepth[b]);
             if (dTiles[b]) cudaFree(dTiles[b]);
             if (dCounters[b]) cudaFree(dCounters[b]);
-            if (dRgba[b]) cudaFree(dRgba[b]);
             if (coarseDone[b]) cudaEventDestroy(coarseDone[b]);
             if (fineDone[b]) cudaEventDestroy(fineDone[b]);
-            if (copyDone[b]) cudaEventDestroy(copyDone[b]);
             for (int k = 0; k < 4; ++k) if (timing[b][k]) cudaEventDestroy(timing[b][k]);
+        }
+        for (int b = 0; b < 2; ++b) {
+            if (dRgba[b]) cudaFree(dRgba[b]);
+            if (copyDone[b]) cudaEventDestroy(copyDone[b]);
         }
         *this = FramePlan();
     }
@@ -134,7 +144,7 @@ struct svo_tree {
     float center[3] = {0, 0, 0};
     uint32_t depth = 0;
     cudaStream_t stream = nullptr;          // rendering for the host-buffer entry points
-    cudaStream_t coarseStream = nullptr;    // beam passes, high priority (overlaps the previous frame's fine pass)
+    cudaStream_t coarseStream[2] = {nullptr, nullptr};  // beam passes, high priority, alternating per frame
     cudaStream_t copyStream = nullptr;      // device->host frame copies
     std::mutex mutex;
     std::map<std::tuple<int, int, int>, FramePlan> plans;
@@ -202,7 +212,7 @@ int createTree(const uint32_t *words, uint64_t nWords, const float center[3], in
     auto cleanup = [&](cudaError_t err, const char *what) {
         if (tree->dWords) cudaFree(tree->dWords);
         if (tree->stream) cudaStreamDestroy(tree->stream);
-        if (tree->coarseStream) cudaStreamDestroy(tree->coarseStream);
+        for (int i = 0; i < 2; ++i) if (tree->coarseStream[i]) cudaStreamDestroy(tree->coarseStream[i]);
         if (tree->copyStream) cudaStreamDestroy(tree->copyStream);
         return failCuda(err, what);
     };
@@ -213,7 +223,9 @@ int createTree(const uint32_t *words, uint64_t nWords, const float center[3], in
     int prioLow = 0, prioHigh = 0;
     if ((e = cudaDeviceGetStreamPriorityRange(&prioLow, &prioHigh)) != cudaSuccess) return cleanup(e, "cudaDeviceGetStreamPriorityRange");
     if ((e = cudaStreamCreateWithFlags(&tree->stream, cudaStreamNonBlocking)) != cudaSuccess) return cleanup(e, "cudaStreamCreate");
-    if ((e = cudaStreamCreateWithPriority(&tree->coarseStream, cudaStreamNonBlocking, prioHigh)) != cudaSuccess) return cleanup(e, "cudaStreamCreate(coarse)");
+    for (int i = 0; i < 2; ++i)
+        if ((e = cudaStreamCreateWithPriority(&tree->coarseStream[i], cudaStreamNonBlocking, prioHigh)) != cudaSuccess)
+            return cleanup(e, "cudaStreamCreate(coarse)");
     if ((e = cudaStreamCreateWithFlags(&tree->copyStream, cudaStreamNonBlocking)) != cudaSuccess) return cleanup(e, "cudaStreamCreate(copy)");
     *out = tree.release();
     return SVO_OK;
@@ -271,17 +283,17 @@ int buildPlan(svo_tree *tree, int width, int height, int strips, FramePlan &plan
 
     SVO_CUDA(cudaMalloc(&plan.dTables, tables.size()*sizeof(float)));
     SVO_CUDA(cudaMemcpy(plan.dTables, tables.data(), tables.size()*sizeof(float), cudaMemcpyHostToDevice));
-    SVO_CUDA(cudaMallocHost(&plan.hCounters, 2*sizeof(svo::FrameCounters)));
-    for (int b = 0; b < 2; ++b) {
+    SVO_CUDA(cudaMallocHost(&plan.hCounters, kRing*sizeof(svo::FrameCounters)));
+    for (int b = 0; b < kRing; ++b) {
         SVO_CUDA(cudaMalloc(&plan.dDepth[b], size_t(p.totalCorners)*sizeof(float)));
         SVO_CUDA(cudaMalloc(&plan.dTiles[b], size_t(p.totalTiles > 0 ? p.totalTiles : 1)*sizeof(svo::TileRecord)));
         SVO_CUDA(cudaMalloc(&plan.dCounters[b], sizeof(svo::FrameCounters)));
         SVO_CUDA(cudaMemset(plan.dCounters[b], 0, sizeof(svo::FrameCounters)));
         SVO_CUDA(cudaEventCreateWithFlags(&plan.coarseDone[b], cudaEventDisableTiming));
         SVO_CUDA(cudaEventCreateWithFlags(&plan.fineDone[b], cudaEventDisableTiming));
-        SVO_CUDA(cudaEventCreateWithFlags(&plan.copyDone[b], cudaEventDisableTiming));
         for (int k = 0; k < 4; ++k) SVO_CUDA(cudaEventCreate(&plan.timing[b][k]));
     }
+    for (int b = 0; b < 2; ++b) SVO_CUDA(cudaEventCreateWithFlags(&plan.copyDone[b], cudaEventDisableTiming));
     p.dxCoarse = plan.dTables;
     p.dyCoarse = p.dxCoarse + nDxC;
     p.dxFine = p.dyCoarse + nDyC;
@@ -340,15 +352,16 @@ int enqueueFrame(svo_tree *tree, FramePlan *plan, const svo_camera *cam, const s
     svo_frame_constants c;
     svo::frameConstants(*cam, tree->center, desc->width, desc->height, desc->strips, c);
     svo::FrameConsts f = toDeviceConsts(c);
-    const int b = int(plan->frameNumber++ & 1);
+    const int b = int(plan->frameNumber++ % kRing);
     float *depth = userDepth ? userDepth : plan->dDepth[b];
-    cudaStream_t cs = userDepth ? stream : tree->coarseStream;
+    cudaStream_t cs = userDepth ? stream : tree->coarseStream[b & 1];
     uint32_t n = 0;
 
-    // the slot's depth buffer, tile list and counters are free once the fine pass of two frames ago is done
+    // the slot's depth buffer, tile list and counters are free once the fine pass of kRing frames ago is done
     if (!userDepth && plan->fineRecorded[b]) SVO_CUDA(cudaStreamWaitEvent(cs, plan->fineDone[b], 0));
     if (wantStats) SVO_CUDA(cudaEventRecord(plan->timing[b][0], cs));
-    SVO_CUDA(svo::launchCoarsePass(tree->dev(), plan->dev, f, desc->flavour, depth, plan->dCounters[b], cs));
+    SVO_CUDA(svo::launchCoarsePass(tree->dev(), plan->dev, f, desc->flavour, depth, plan->dCounters[b], desc->tile_rank,
+                                   desc->tile_world, cs));
     ++n;
     if (wantStats) SVO_CUDA(cudaEventRecord(plan->timing[b][1], cs));
     if (!userDepth) {
@@ -376,11 +389,18 @@ int enqueueFrame(svo_tree *tree, FramePlan *plan, const svo_camera *cam, const s
 
 // Valid once the frame's stream work has completed (caller synchronised).
 void fillStats(const FramePlan *plan, int slot, const svo_frame_desc *desc, uint32_t launches, svo_frame_stats *stats) {
-    stats->coarse_rays = uint64_t(plan->dev.totalCorners);
+    const svo::FramePlanDev &p = plan->dev;
+    const int world = desc->tile_world, rank = desc->tile_rank;
+    // corner columns this rank traces: all of them up to two ranks, else those next to its tile columns
+    int cols = 0;
+    for (int cx = 0; cx < p.tilesX; ++cx)
+        if (world <= 2 || cx % world == rank || (cx > 0 && (cx - 1) % world == rank)) ++cols;
+    const int cornerRows = (p.nStrips - 1)*p.tilesYFull + p.tilesYLast;
+    stats->coarse_rays = uint64_t(cols)*uint64_t(cornerRows);
     stats->fine_rays = plan->hCounters[slot].fineRays;
     stats->tiles_rendered = plan->hCounters[slot].tilesRendered;
-    int owned = (plan->dev.totalTiles - desc->tile_rank + desc->tile_world - 1)/desc->tile_world;
-    stats->tiles_total = owned > 0 ? uint64_t(owned) : 0;
+    const int ownedCols = p.tileCols > rank ? (p.tileCols - rank + world - 1)/world : 0;
+    stats->tiles_total = uint64_t(ownedCols)*uint64_t(p.totalTileRows);
     stats->kernel_launches = launches;
     stats->reserved = 0;
     stats->coarse_ms = stats->fine_ms = 0.0f;
@@ -500,7 +520,7 @@ int svo_tree_destroy(svo_tree *tree) {
         tree->batchOut.release();
         if (tree->dWords) cudaFree(tree->dWords);
         if (tree->stream) cudaStreamDestroy(tree->stream);
-        if (tree->coarseStream) cudaStreamDestroy(tree->coarseStream);
+        for (int i = 0; i < 2; ++i) if (tree->coarseStream[i]) cudaStreamDestroy(tree->coarseStream[i]);
         if (tree->copyStream) cudaStreamDestroy(tree->copyStream);
     }
     delete tree;
@@ -603,6 +623,18 @@ int svo_frame_get_layout(int width, int height, int strips, svo_frame_layout *ou
     return SVO_OK;
 }
 
+int svo_frame_tile_owner(int width, int height, int strips, int tile, int tile_world) {
+    svo_frame_desc d = {width, height, strips, SVO_FLAVOUR_VALIDATION, 0, tile_world, {0, 0}};
+    if (checkDesc(&d) != SVO_OK) return -1;
+    svo::FramePlanDev p{};
+    planGeometry(width, height, strips, p);
+    if (tile < 0 || tile >= p.totalTiles) {
+        fail(SVO_ERR_INVALID_ARGUMENT, "tile %d out of range [0, %d)", tile, p.totalTiles);
+        return -1;
+    }
+    return (tile % p.tileCols) % tile_world;
+}
+
 int svo_frame_tile_rect(int width, int height, int strips, int tile, int32_t rect[4]) {
     if (!rect) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_frame_tile_rect: null argument");
     svo_frame_desc d = {width, height, strips, SVO_FLAVOUR_VALIDATION, 0, 1, {0, 0}};
@@ -654,7 +686,7 @@ int svo_render_frame_async(svo_tree *tree, const svo_camera *cam, const svo_fram
     std::lock_guard<std::mutex> lock(tree->mutex);
     FramePlan *plan = nullptr;
     if ((st = getPlan(tree, desc->width, desc->height, desc->strips, &plan)) != SVO_OK) return st;
-    const int b = int(plan->frameNumber & 1);     // the slot enqueueFrame is about to use
+    const int b = int(plan->hostFrameNumber & 1);  // staging framebuffer / ticket of this frame
     if (plan->pending[b])
         return fail(SVO_ERR_INVALID_ARGUMENT, "two frames are already in flight for this configuration: call svo_frame_wait first");
     size_t frameBytes = size_t(desc->width)*size_t(desc->height)*sizeof(uint32_t);
@@ -663,25 +695,26 @@ int svo_render_frame_async(svo_tree *tree, const svo_camera *cam, const svo_fram
         SVO_CUDA(cudaMemset(plan->dRgba[b], 0, frameBytes));
     }
     cudaStream_t s = tree->stream;
-    // the slot's staging framebuffer is free once its previous device->host copy has finished
+    // the staging framebuffer is free once its previous device->host copy has finished
     if (plan->copyRecorded[b]) SVO_CUDA(cudaStreamWaitEvent(s, plan->copyDone[b], 0));
     uint32_t launches = 0;
     int slot = 0;
     if ((st = enqueueFrame(tree, plan, cam, desc, plan->dRgba[b], nullptr, s, want_stats != 0, &launches, &slot)) != SVO_OK) return st;
     // copies run on their own stream so that the next frame's kernels are not queued behind them
     SVO_CUDA(cudaStreamWaitEvent(tree->copyStream, plan->fineDone[slot], 0));
-    SVO_CUDA(cudaMemcpyAsync(rgba, plan->dRgba[slot], frameBytes, cudaMemcpyDeviceToHost, tree->copyStream));
+    SVO_CUDA(cudaMemcpyAsync(rgba, plan->dRgba[b], frameBytes, cudaMemcpyDeviceToHost, tree->copyStream));
     if (depth)
         SVO_CUDA(cudaMemcpyAsync(depth, plan->dDepth[slot], size_t(plan->dev.totalCorners)*sizeof(float),
                                  cudaMemcpyDeviceToHost, tree->copyStream));
-    SVO_CUDA(cudaEventRecord(plan->copyDone[slot], tree->copyStream));
-    plan->copyRecorded[slot] = true;
-    plan->pending[slot] = true;
-    plan->pendingStats[slot] = want_stats != 0;
-    plan->pendingLaunches[slot] = launches;
-    plan->pendingDesc[slot] = *desc;
-    // ticket: slot in bit 0, configuration in the rest (so that svo_frame_wait can find the plan)
-    *ticket = slot;
+    SVO_CUDA(cudaEventRecord(plan->copyDone[b], tree->copyStream));
+    ++plan->hostFrameNumber;
+    plan->copyRecorded[b] = true;
+    plan->pending[b] = true;
+    plan->pendingStats[b] = want_stats != 0;
+    plan->pendingRing[b] = slot;
+    plan->pendingLaunches[b] = launches;
+    plan->pendingDesc[b] = *desc;
+    *ticket = b;
     return SVO_OK;
 }
 
@@ -699,7 +732,7 @@ int svo_frame_wait(svo_tree *tree, const svo_frame_desc *desc, int ticket, svo_f
     if (stats) {
         if (!plan->pendingStats[ticket])
             return fail(SVO_ERR_INVALID_ARGUMENT, "svo_frame_wait: statistics were not requested for this frame");
-        fillStats(plan, ticket, &plan->pendingDesc[ticket], plan->pendingLaunches[ticket], stats);
+        fillStats(plan, plan->pendingRing[ticket], &plan->pendingDesc[ticket], plan->pendingLaunches[ticket], stats);
     }
     return SVO_OK;
 }

@@ -47,26 +47,32 @@ raymarchBatchKernel(const uint32_t *__restrict__ octree, uint64_t n, const float
 
 // ---- K2 -------------------------------------------------------------------
 
+// Tile (tx, ty) belongs to rank tx % world (vertical stripes one tile wide), so a rank needs only
+// the corner columns cx with cx % world == rank or (cx - 1) % world == rank: 2/world of the beam
+// pass for world >= 3. Threads enumerate exactly those corners, densely: column slot j of a corner
+// row maps to cx = (j >> 1)*world + rank + (j & 1).
 template <typename IdxT>
 __global__ void __launch_bounds__(kCoarseThreads)
 coarsePassKernel(const uint32_t *__restrict__ octree, FramePlanDev plan, FrameConsts f, float *__restrict__ depth,
-                 FrameCounters *__restrict__ counters) {
+                 FrameCounters *__restrict__ counters, int tileRank, int tileWorld, int colSlots, int totalSlots) {
     extern __shared__ __align__(16) unsigned char smem[];
     SmemStack<IdxT, kCoarseThreads> stack;
     stack.init(smem);
 
-    int i = blockIdx.x*blockDim.x + threadIdx.x;
-    if (i == 0) {
+    int k = blockIdx.x*blockDim.x + threadIdx.x;
+    if (k == 0) {
         counters->tilesRendered = 0;
         counters->fineRays = 0;
     }
-    if (i >= plan.totalCorners) return;
+    if (k >= totalSlots) return;
 
-    int cellsFull = plan.tilesX*plan.tilesYFull;
-    int strip = min(i/cellsFull, plan.nStrips - 1);
-    int rem = i - strip*cellsFull;
-    int y = rem/plan.tilesX;
-    int x = rem - y*plan.tilesX;
+    int row = k/colSlots;                 // corner row over all strips
+    int j = k - row*colSlots;
+    int x = tileWorld <= 2 ? j : (j >> 1)*tileWorld + tileRank + (j & 1);
+    if (x >= plan.tilesX) return;
+    int strip = min(row/plan.tilesYFull, plan.nStrips - 1);
+    int y = row - strip*plan.tilesYFull;
+    int i = strip*plan.tilesX*plan.tilesYFull + y*plan.tilesX + x;
 
     float dx = __ldg(plan.dxCoarse + x);
     float dy = __ldg(plan.dyCoarse + strip*plan.tilesYFull + y);
@@ -85,7 +91,7 @@ coarsePassKernel(const uint32_t *__restrict__ octree, FramePlanDev plan, FrameCo
 
 __global__ void __launch_bounds__(kClassifyThreads)
 classifyTilesKernel(FramePlanDev plan, float beamBias, const float *__restrict__ depth, uint32_t *__restrict__ rgba,
-                    int tileRank, int tileWorld, int ownedTiles, TileRecord *__restrict__ tiles,
+                    int tileRank, int tileWorld, int ownedCols, int ownedTiles, TileRecord *__restrict__ tiles,
                     FrameCounters *__restrict__ counters) {
     int k = blockIdx.x*blockDim.x + threadIdx.x;
     bool active = k < ownedTiles;
@@ -93,9 +99,8 @@ classifyTilesKernel(FramePlanDev plan, float beamBias, const float *__restrict__
     int x0 = 0, y0 = 0, yEnd = 0;
     float minT = kTreeMiss;
     if (active) {
-        int tile = k*tileWorld + tileRank;
-        int tileRow = tile/plan.tileCols;
-        int tx = tile - tileRow*plan.tileCols;
+        int tileRow = k/ownedCols;                              // this rank owns tile columns tx % world == rank
+        int tx = (k - tileRow*ownedCols)*tileWorld + tileRank;
         int strip = min(tileRow/plan.tileRowsFull, plan.nStrips - 1);
         int ty = tileRow - strip*plan.tileRowsFull;
         int stripY0 = strip*plan.stripRows;
@@ -184,8 +189,11 @@ cudaError_t ensureSmem(K kernel, size_t bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
 }
 
+inline int ownedCols(const FramePlanDev &plan, int tileRank, int tileWorld) {
+    return plan.tileCols > tileRank ? (plan.tileCols - tileRank + tileWorld - 1)/tileWorld : 0;
+}
 inline int ownedTiles(const FramePlanDev &plan, int tileRank, int tileWorld) {
-    return (plan.totalTiles - tileRank + tileWorld - 1)/tileWorld;
+    return ownedCols(plan, tileRank, tileWorld)*plan.totalTileRows;
 }
 
 template <bool FAST, bool LOD, typename IdxT>
@@ -203,13 +211,18 @@ cudaError_t launchBatchT(const TreeDev &tree, uint64_t n, const float *o, const 
 
 template <typename IdxT>
 cudaError_t launchCoarseT(const TreeDev &tree, const FramePlanDev &plan, const FrameConsts &consts, float *depth,
-                          FrameCounters *counters, cudaStream_t stream) {
+                          FrameCounters *counters, int tileRank, int tileWorld, cudaStream_t stream) {
     size_t smem = SmemStack<IdxT, kCoarseThreads>::bytes(stackSlots(tree));
     auto kernel = coarsePassKernel<IdxT>;
     cudaError_t e = ensureSmem(kernel, smem);
     if (e != cudaSuccess) return e;
-    int blocks = (plan.totalCorners + kCoarseThreads - 1)/kCoarseThreads;
-    kernel<<<blocks, kCoarseThreads, smem, stream>>>(tree.words, plan, consts, depth, counters);
+    // world <= 2: every corner column is needed by every rank
+    int colSlots = tileWorld <= 2 ? plan.tilesX : 2*((plan.tilesX + tileWorld - 1)/tileWorld);
+    int cornerRows = (plan.nStrips - 1)*plan.tilesYFull + plan.tilesYLast;
+    int totalSlots = colSlots*cornerRows;
+    int blocks = (totalSlots + kCoarseThreads - 1)/kCoarseThreads;
+    kernel<<<blocks, kCoarseThreads, smem, stream>>>(tree.words, plan, consts, depth, counters, tileRank, tileWorld,
+                                                     colSlots, totalSlots);
     return cudaGetLastError();
 }
 
@@ -243,15 +256,16 @@ cudaError_t launchRaymarchBatch(const TreeDev &tree, uint64_t n, const float *o,
 }
 
 cudaError_t launchCoarsePass(const TreeDev &tree, const FramePlanDev &plan, const FrameConsts &consts, int flavour,
-                             float *depth, FrameCounters *counters, cudaStream_t stream) {
+                             float *depth, FrameCounters *counters, int tileRank, int tileWorld,
+                             cudaStream_t stream) {
     // The beam pass is individually rounded in BOTH flavours: its depths feed
     // `minT - 0.03` (Main.cpp:197) and the tile-skip test (Main.cpp:191), so a
     // last-bit change here moves every ray origin of a tile or drops / adds a
     // whole tile. It is < 5 % of the rays; FAST only changes the fine pass.
     (void)flavour;
     bool wide = tree.nWords >= (1ull << 32);
-    return wide ? launchCoarseT<uint64_t>(tree, plan, consts, depth, counters, stream)
-                : launchCoarseT<uint32_t>(tree, plan, consts, depth, counters, stream);
+    return wide ? launchCoarseT<uint64_t>(tree, plan, consts, depth, counters, tileRank, tileWorld, stream)
+                : launchCoarseT<uint32_t>(tree, plan, consts, depth, counters, tileRank, tileWorld, stream);
 }
 
 cudaError_t launchClassifyTiles(const FramePlanDev &plan, const FrameConsts &consts, const float *depth,
@@ -260,7 +274,8 @@ cudaError_t launchClassifyTiles(const FramePlanDev &plan, const FrameConsts &con
     int owned = ownedTiles(plan, tileRank, tileWorld);
     if (owned <= 0) return cudaSuccess;
     classifyTilesKernel<<<(owned + kClassifyThreads - 1)/kClassifyThreads, kClassifyThreads, 0, stream>>>(
-        plan, consts.beamBias, depth, rgba, tileRank, tileWorld, owned, tiles, counters);
+        plan, consts.beamBias, depth, rgba, tileRank, tileWorld, ownedCols(plan, tileRank, tileWorld), owned, tiles,
+        counters);
     return cudaGetLastError();
 }
 

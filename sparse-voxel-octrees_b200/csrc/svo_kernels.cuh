@@ -57,8 +57,10 @@ cudaError_t launchRaymarchBatch(const TreeDev &tree, uint64_t n, const float *o,
                                 cudaStream_t stream);
 
 // Beam pass; also zeroes `counters` for the classifier that follows on the same stream.
+// With tileWorld >= 3 only the corners next to this rank's tile columns are traced.
 cudaError_t launchCoarsePass(const TreeDev &tree, const FramePlanDev &plan, const FrameConsts &consts, int flavour,
-                             float *depth, FrameCounters *counters, cudaStream_t stream);
+                             float *depth, FrameCounters *counters, int tileRank, int tileWorld,
+                             cudaStream_t stream);
 
 // Per owned tile: min of the four corner depths; skipped tiles are zero-filled (the strip memset,
 // Main.cpp:165), rendered tiles are appended to `tiles` (capacity = owned tiles) and counted.

@@ -133,6 +133,7 @@ def lib():
         "svo_frame_constants_from_camera": (i32, [P(Camera), P(f32), i32, i32, i32, P(FrameConstants)]),
         "svo_frame_get_layout": (i32, [i32, i32, i32, P(FrameLayout)]),
         "svo_frame_tile_rect": (i32, [i32, i32, i32, i32, P(C.c_int32)]),
+        "svo_frame_tile_owner": (i32, [i32, i32, i32, i32, i32]),
         "svo_render_frame": (i32, [vp, P(Camera), P(FrameDesc), vp, vp, P(FrameStats)]),
         "svo_render_frame_device": (i32, [vp, P(Camera), P(FrameDesc), vp, vp, vp, P(FrameStats), i32]),
         "svo_render_frame_async": (i32, [vp, P(Camera), P(FrameDesc), vp, vp, i32, P(i32)]),
@@ -430,6 +431,13 @@ def tile_rect(width, height, strips, tile):
     r = (C.c_int32 * 4)()
     _check(lib().svo_frame_tile_rect(width, height, strips, int(tile), r))
     return tuple(r)
+
+
+def tile_owner(width, height, strips, tile, world):
+    r = lib().svo_frame_tile_owner(width, height, strips, int(tile), int(world))
+    if r < 0:
+        raise SvoError(1, lib().svo_last_error().decode(errors="replace"))
+    return r
 
 
 def strip_layout(width, height, strips, tile=8):

@@ -1,5 +1,5 @@
 """CPU, world_size 2 over gloo: the host-side logic of the multi-GPU path -- the tile interleave that
-svo_frame_desc.tile_rank / tile_world select (tile t -> rank t % world) partitions every pixel exactly once,
+svo_frame_desc.tile_rank / tile_world select (tile column tx -> rank tx % world) partitions every pixel exactly once,
 and the per-rank ray counts the bench all-reduces add up. No device compute."""
 import os
 import socket
@@ -31,7 +31,8 @@ def _worker(rank, world, port, cases, out_queue):
         lay = pysvo.frame_layout(W, H, S)
         cover = np.zeros((H, W), np.int32)
         owned_pixels = 0
-        for t in range(rank, lay.tiles, world):          # the tiles this rank's kernels would take
+        mine = [t for t in range(lay.tiles) if pysvo.tile_owner(W, H, S, t, world) == rank]
+        for t in mine:                                   # the tiles this rank's kernels take
             x0, y0, x1, y1 = pysvo.tile_rect(W, H, S, t)
             cover[y0:y1, x0:x1] += 1
             owned_pixels += (x1 - x0) * (y1 - y0)
@@ -40,10 +41,11 @@ def _worker(rank, world, port, cases, out_queue):
         px = torch.tensor([owned_pixels], dtype=torch.int64)
         dist.all_reduce(px)
         ok = ok and bool((total == 1).all()) and int(px.item()) == W * H and int(cover.max()) <= 1
-        # load balance of the interleave: ranks differ by at most one tile
+        # load balance of the interleave (tile columns dealt round-robin): ranks differ by at most one column
         counts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
-        dist.all_gather(counts, torch.tensor([len(range(rank, lay.tiles, world))], dtype=torch.int64))
-        ok = ok and max(int(c) for c in counts) - min(int(c) for c in counts) <= 1
+        dist.all_gather(counts, torch.tensor([len(mine)], dtype=torch.int64))
+        rows = lay.tiles // lay.tile_cols
+        ok = ok and max(int(c) for c in counts) - min(int(c) for c in counts) <= rows
     if rank == 0:
         out_queue.put(ok)
     dist.barrier()
