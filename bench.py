@@ -319,26 +319,63 @@ def run_own(args):
         st = frame(k, want_stats=True)
         fine[k] = int(st.fine_rays)
         kernel_ms.append((st.coarse_ms, st.fine_ms))
+    if os.environ.get("SVO_BENCH_DEBUG"):
+        km = np.array(kernel_ms)
+        print(f"[rank {rank}] beam pass {km[:, 0].mean():.4f} ms, classify+fine {km[:, 1].mean():.4f} ms "
+              f"(min {km[:, 1].min():.4f}, max {km[:, 1].max():.4f}) over {len(km)} cameras", file=sys.stderr, flush=True)
     if world > 1:
         dist.all_reduce(fine)
     fine = fine.cpu().numpy()
     rays_of = lambda k: coarse + int(fine[k % ORBIT])  # noqa: E731
 
-    # ---- timed region: W warm-up frames, then exactly K frames between device events
+    # ---- timed region: W warm-up frames, then exactly K frames between device events.
+    # Double-buffered like a swap chain: frame k renders into framebuffer k & 1 on stream k & 1, so the
+    # long-ray tail of one fine pass overlaps the start of the next frame (each frame is still complete,
+    # in rank 0's memory, when its stream reaches the frame barrier).
+    main = torch.cuda.current_stream()
+    lanes = [torch.cuda.Stream(), torch.cuda.Stream()]
+    comm = torch.cuda.Stream() if world > 1 else None
+    gate = [None, None]
+
+    def pipelined_frame(k):
+        slot = k & 1
+        with torch.cuda.stream(lanes[slot]):
+            tree.render_frame_device(cams[k % ORBIT], W, H, fb_ptrs[slot], strips=STRIPS, flavour=flavour,
+                                     tile_rank=rank, tile_world=world, stream=lanes[slot].cuda_stream)
+            if world > 1:
+                done = torch.cuda.Event()
+                done.record(lanes[slot])
+                comm.wait_event(done)
+                with torch.cuda.stream(comm):
+                    dist.all_reduce(flag)          # frame barrier: every rank's tiles are in rank 0's framebuffer
+                    gate[slot] = torch.cuda.Event()
+                    gate[slot].record(comm)
+                lanes[slot].wait_event(gate[slot])  # the slot is reused (frame k+2) only after the barrier
+
+    def run_frames(first, count):
+        start = torch.cuda.Event(enable_timing=True)
+        stop = torch.cuda.Event(enable_timing=True)
+        start.record(main)
+        for ln in lanes:
+            ln.wait_event(start)
+        for k in range(first, first + count):
+            pipelined_frame(k)
+        for ln in lanes:
+            main.wait_stream(ln)
+        if comm is not None:
+            main.wait_stream(comm)
+        stop.record(main)
+        return start, stop
+
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    for k in range(warmup):
-        frame(k)
+    run_frames(0, warmup)
     torch.cuda.synchronize()
     barrier()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_begin = time.perf_counter()
-    e0.record()
-    for k in range(warmup, warmup + steps):
-        frame(k)
-    e1.record()
+    e0, e1 = run_frames(warmup, steps)
     torch.cuda.synchronize()
     barrier()
     torch.cuda.synchronize()
@@ -376,7 +413,6 @@ def run_own(args):
         hosts = [host.array, host2.array] if rank == 0 else None
         copy_stream = torch.cuda.Stream()
         copied = [None, None]
-        main = torch.cuda.current_stream()
         for k in range(warmup, warmup + e2e_steps):
             slot = k & 1
             frame(k, fb=fb_ptrs[slot], sync=False)
@@ -476,6 +512,7 @@ def run_own(args):
                    "octree_words": tree.n_words, "octree_depth": tree.depth,
                    "parallelism": "replicated octree, interleaved 8x8 tiles, fine-pass stores into rank 0's framebuffer over NVLink" if world > 1 else "single GPU",
                    "l2": f"no flush: octree {tree.n_words * 4 / 1e6:.0f} MB vs 126 MB L2, camera moves every step",
+                   "pipelining": "two frames in flight (framebuffer k & 1 on stream k & 1); beam passes run ahead on internal streams",
                    "rays_per_frame_mean": total_rays / steps, "ms_per_frame": total_ms / steps},
         "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 128, "d2h_bytes_per_step": nbytes,
                 "steps": e2e_steps, "ms_per_step": float(e2e_s.item()) / e2e_steps * 1e3,

@@ -143,7 +143,8 @@ struct svo_tree {
     uint64_t nWords = 0;
     float center[3] = {0, 0, 0};
     uint32_t depth = 0;
-    cudaStream_t stream = nullptr;          // rendering for the host-buffer entry points
+    cudaStream_t stream = nullptr;          // batches; classifier + fine pass of even host-buffer frames
+    cudaStream_t stream2 = nullptr;         // ... of odd host-buffer frames (so that consecutive fine passes overlap)
     cudaStream_t coarseStream[2] = {nullptr, nullptr};  // beam passes, high priority, alternating per frame
     cudaStream_t copyStream = nullptr;      // device->host frame copies
     std::mutex mutex;
@@ -212,6 +213,7 @@ int createTree(const uint32_t *words, uint64_t nWords, const float center[3], in
     auto cleanup = [&](cudaError_t err, const char *what) {
         if (tree->dWords) cudaFree(tree->dWords);
         if (tree->stream) cudaStreamDestroy(tree->stream);
+        if (tree->stream2) cudaStreamDestroy(tree->stream2);
         for (int i = 0; i < 2; ++i) if (tree->coarseStream[i]) cudaStreamDestroy(tree->coarseStream[i]);
         if (tree->copyStream) cudaStreamDestroy(tree->copyStream);
         return failCuda(err, what);
@@ -223,6 +225,7 @@ int createTree(const uint32_t *words, uint64_t nWords, const float center[3], in
     int prioLow = 0, prioHigh = 0;
     if ((e = cudaDeviceGetStreamPriorityRange(&prioLow, &prioHigh)) != cudaSuccess) return cleanup(e, "cudaDeviceGetStreamPriorityRange");
     if ((e = cudaStreamCreateWithFlags(&tree->stream, cudaStreamNonBlocking)) != cudaSuccess) return cleanup(e, "cudaStreamCreate");
+    if ((e = cudaStreamCreateWithFlags(&tree->stream2, cudaStreamNonBlocking)) != cudaSuccess) return cleanup(e, "cudaStreamCreate");
     for (int i = 0; i < 2; ++i)
         if ((e = cudaStreamCreateWithPriority(&tree->coarseStream[i], cudaStreamNonBlocking, prioHigh)) != cudaSuccess)
             return cleanup(e, "cudaStreamCreate(coarse)");
@@ -391,16 +394,19 @@ int enqueueFrame(svo_tree *tree, FramePlan *plan, const svo_camera *cam, const s
 void fillStats(const FramePlan *plan, int slot, const svo_frame_desc *desc, uint32_t launches, svo_frame_stats *stats) {
     const svo::FramePlanDev &p = plan->dev;
     const int world = desc->tile_world, rank = desc->tile_rank;
-    // corner columns this rank traces: all of them up to two ranks, else those next to its tile columns
+    // corner columns this rank traces: those on either side of its tile-column runs
+    const int run = svo::tileRunLength(world);
     int cols = 0;
-    for (int cx = 0; cx < p.tilesX; ++cx)
-        if (world <= 2 || cx % world == rank || (cx > 0 && (cx - 1) % world == rank)) ++cols;
+    for (int cx = 0; cx < p.tilesX; ++cx) {
+        bool right = cx < p.tileCols && (cx/run) % world == rank;        // tile column to the right of the corner
+        bool left = cx > 0 && ((cx - 1)/run) % world == rank;            // ... to the left
+        if (world == 1 || right || left) ++cols;
+    }
     const int cornerRows = (p.nStrips - 1)*p.tilesYFull + p.tilesYLast;
     stats->coarse_rays = uint64_t(cols)*uint64_t(cornerRows);
     stats->fine_rays = plan->hCounters[slot].fineRays;
     stats->tiles_rendered = plan->hCounters[slot].tilesRendered;
-    const int ownedCols = p.tileCols > rank ? (p.tileCols - rank + world - 1)/world : 0;
-    stats->tiles_total = uint64_t(ownedCols)*uint64_t(p.totalTileRows);
+    stats->tiles_total = uint64_t(svo::ownedTileColumns(p.tileCols, rank, world))*uint64_t(p.totalTileRows);
     stats->kernel_launches = launches;
     stats->reserved = 0;
     stats->coarse_ms = stats->fine_ms = 0.0f;
@@ -520,6 +526,7 @@ int svo_tree_destroy(svo_tree *tree) {
         tree->batchOut.release();
         if (tree->dWords) cudaFree(tree->dWords);
         if (tree->stream) cudaStreamDestroy(tree->stream);
+        if (tree->stream2) cudaStreamDestroy(tree->stream2);
         for (int i = 0; i < 2; ++i) if (tree->coarseStream[i]) cudaStreamDestroy(tree->coarseStream[i]);
         if (tree->copyStream) cudaStreamDestroy(tree->copyStream);
     }
@@ -632,7 +639,7 @@ int svo_frame_tile_owner(int width, int height, int strips, int tile, int tile_w
         fail(SVO_ERR_INVALID_ARGUMENT, "tile %d out of range [0, %d)", tile, p.totalTiles);
         return -1;
     }
-    return (tile % p.tileCols) % tile_world;
+    return ((tile % p.tileCols)/svo::tileRunLength(tile_world)) % tile_world;
 }
 
 int svo_frame_tile_rect(int width, int height, int strips, int tile, int32_t rect[4]) {
@@ -694,7 +701,9 @@ int svo_render_frame_async(svo_tree *tree, const svo_camera *cam, const svo_fram
         SVO_CUDA(cudaMalloc(&plan->dRgba[b], frameBytes));
         SVO_CUDA(cudaMemset(plan->dRgba[b], 0, frameBytes));
     }
-    cudaStream_t s = tree->stream;
+    // even and odd frames render on different streams into different staging framebuffers, so the
+    // long-ray tail of one fine pass overlaps the start of the next
+    cudaStream_t s = b ? tree->stream2 : tree->stream;
     // the staging framebuffer is free once its previous device->host copy has finished
     if (plan->copyRecorded[b]) SVO_CUDA(cudaStreamWaitEvent(s, plan->copyDone[b], 0));
     uint32_t launches = 0;

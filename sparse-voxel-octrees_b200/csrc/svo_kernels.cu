@@ -8,6 +8,8 @@
 // instruction issue and SIMT divergence long before HBM bandwidth.
 #include "svo_kernels.cuh"
 
+#include <cstdlib>
+
 namespace svo {
 
 namespace {
@@ -54,7 +56,8 @@ raymarchBatchKernel(const uint32_t *__restrict__ octree, uint64_t n, const float
 template <typename IdxT>
 __global__ void __launch_bounds__(kCoarseThreads)
 coarsePassKernel(const uint32_t *__restrict__ octree, FramePlanDev plan, FrameConsts f, float *__restrict__ depth,
-                 FrameCounters *__restrict__ counters, int tileRank, int tileWorld, int colSlots, int totalSlots) {
+                 FrameCounters *__restrict__ counters, int tileRank, int tileWorld, int tileRun, int colSlots,
+                 int totalSlots) {
     extern __shared__ __align__(16) unsigned char smem[];
     SmemStack<IdxT, kCoarseThreads> stack;
     stack.init(smem);
@@ -68,7 +71,9 @@ coarsePassKernel(const uint32_t *__restrict__ octree, FramePlanDev plan, FrameCo
 
     int row = k/colSlots;                 // corner row over all strips
     int j = k - row*colSlots;
-    int x = tileWorld <= 2 ? j : (j >> 1)*tileWorld + tileRank + (j & 1);
+    // slot j -> corner column: run q = j / (run + 1) of this rank starts at tile column (q*world + rank)*run
+    int q = j/(tileRun + 1);
+    int x = tileWorld == 1 ? j : (q*tileWorld + tileRank)*tileRun + (j - q*(tileRun + 1));
     if (x >= plan.tilesX) return;
     int strip = min(row/plan.tilesYFull, plan.nStrips - 1);
     int y = row - strip*plan.tilesYFull;
@@ -91,16 +96,17 @@ coarsePassKernel(const uint32_t *__restrict__ octree, FramePlanDev plan, FrameCo
 
 __global__ void __launch_bounds__(kClassifyThreads)
 classifyTilesKernel(FramePlanDev plan, float beamBias, const float *__restrict__ depth, uint32_t *__restrict__ rgba,
-                    int tileRank, int tileWorld, int ownedCols, int ownedTiles, TileRecord *__restrict__ tiles,
-                    FrameCounters *__restrict__ counters) {
+                    int tileRank, int tileWorld, int tileRun, int ownedCols, int ownedTiles,
+                    TileRecord *__restrict__ tiles, FrameCounters *__restrict__ counters) {
     int k = blockIdx.x*blockDim.x + threadIdx.x;
     bool active = k < ownedTiles;
     bool rendered = false;
     int x0 = 0, y0 = 0, yEnd = 0;
     float minT = kTreeMiss;
     if (active) {
-        int tileRow = k/ownedCols;                              // this rank owns tile columns tx % world == rank
-        int tx = (k - tileRow*ownedCols)*tileWorld + tileRank;
+        int tileRow = k/ownedCols;                              // this rank owns tile columns (tx / run) % world == rank
+        int c = k - tileRow*ownedCols;                          // c-th owned column
+        int tx = ((c/tileRun)*tileWorld + tileRank)*tileRun + c%tileRun;
         int strip = min(tileRow/plan.tileRowsFull, plan.nStrips - 1);
         int ty = tileRow - strip*plan.tileRowsFull;
         int stripY0 = strip*plan.stripRows;
@@ -189,8 +195,29 @@ cudaError_t ensureSmem(K kernel, size_t bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
 }
 
+} // namespace
+
+// Tile column tx belongs to rank (tx / run) % world: vertical stripes `run` tiles wide.
+int tileRunLength(int tileWorld) {
+    static int run = [] {
+        const char *e = getenv("SVO_TILE_RUN");
+        int v = e ? atoi(e) : 0;
+        return v > 0 ? v : 4;
+    }();
+    return tileWorld > 1 ? run : 1;
+}
+
+int ownedTileColumns(int tileCols, int tileRank, int tileWorld) {
+    int run = tileRunLength(tileWorld), n = 0;
+    for (int start = tileRank*run; start < tileCols; start += tileWorld*run)
+        n += (start + run <= tileCols) ? run : tileCols - start;
+    return n;
+}
+
+namespace {
+
 inline int ownedCols(const FramePlanDev &plan, int tileRank, int tileWorld) {
-    return plan.tileCols > tileRank ? (plan.tileCols - tileRank + tileWorld - 1)/tileWorld : 0;
+    return ownedTileColumns(plan.tileCols, tileRank, tileWorld);
 }
 inline int ownedTiles(const FramePlanDev &plan, int tileRank, int tileWorld) {
     return ownedCols(plan, tileRank, tileWorld)*plan.totalTileRows;
@@ -216,13 +243,15 @@ cudaError_t launchCoarseT(const TreeDev &tree, const FramePlanDev &plan, const F
     auto kernel = coarsePassKernel<IdxT>;
     cudaError_t e = ensureSmem(kernel, smem);
     if (e != cudaSuccess) return e;
-    // world <= 2: every corner column is needed by every rank
-    int colSlots = tileWorld <= 2 ? plan.tilesX : 2*((plan.tilesX + tileWorld - 1)/tileWorld);
+    // a rank needs the corner columns on both sides of each of its runs: run + 1 per run
+    int run = tileRunLength(tileWorld);
+    int runsOwned = (plan.tileCols + tileWorld*run - 1)/(tileWorld*run);
+    int colSlots = tileWorld == 1 ? plan.tilesX : runsOwned*(run + 1);
     int cornerRows = (plan.nStrips - 1)*plan.tilesYFull + plan.tilesYLast;
     int totalSlots = colSlots*cornerRows;
     int blocks = (totalSlots + kCoarseThreads - 1)/kCoarseThreads;
     kernel<<<blocks, kCoarseThreads, smem, stream>>>(tree.words, plan, consts, depth, counters, tileRank, tileWorld,
-                                                     colSlots, totalSlots);
+                                                     run, colSlots, totalSlots);
     return cudaGetLastError();
 }
 
@@ -274,8 +303,8 @@ cudaError_t launchClassifyTiles(const FramePlanDev &plan, const FrameConsts &con
     int owned = ownedTiles(plan, tileRank, tileWorld);
     if (owned <= 0) return cudaSuccess;
     classifyTilesKernel<<<(owned + kClassifyThreads - 1)/kClassifyThreads, kClassifyThreads, 0, stream>>>(
-        plan, consts.beamBias, depth, rgba, tileRank, tileWorld, ownedCols(plan, tileRank, tileWorld), owned, tiles,
-        counters);
+        plan, consts.beamBias, depth, rgba, tileRank, tileWorld, tileRunLength(tileWorld),
+        ownedCols(plan, tileRank, tileWorld), owned, tiles, counters);
     return cudaGetLastError();
 }
 

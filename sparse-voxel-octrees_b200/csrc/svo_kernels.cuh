@@ -56,6 +56,10 @@ cudaError_t launchRaymarchBatch(const TreeDev &tree, uint64_t n, const float *o,
                                 int flavour, uint8_t *hit, float *t, uint32_t *normal, uint64_t *voxel,
                                 cudaStream_t stream);
 
+// Multi-GPU tile interleave: tile column tx belongs to rank (tx / run) % world.
+int tileRunLength(int tileWorld);
+int ownedTileColumns(int tileCols, int tileRank, int tileWorld);
+
 // Beam pass; also zeroes `counters` for the classifier that follows on the same stream.
 // With tileWorld >= 3 only the corners next to this rank's tile columns are traced.
 cudaError_t launchCoarsePass(const TreeDev &tree, const FramePlanDev &plan, const FrameConsts &consts, int flavour,

@@ -1,5 +1,5 @@
 """CPU, world_size 2 over gloo: the host-side logic of the multi-GPU path -- the tile interleave that
-svo_frame_desc.tile_rank / tile_world select (tile column tx -> rank tx % world) partitions every pixel exactly once,
+svo_frame_desc.tile_rank / tile_world select (tile column tx -> rank (tx / 4) % world) partitions every pixel exactly once,
 and the per-rank ray counts the bench all-reduces add up. No device compute."""
 import os
 import socket
@@ -41,11 +41,11 @@ def _worker(rank, world, port, cases, out_queue):
         px = torch.tensor([owned_pixels], dtype=torch.int64)
         dist.all_reduce(px)
         ok = ok and bool((total == 1).all()) and int(px.item()) == W * H and int(cover.max()) <= 1
-        # load balance of the interleave (tile columns dealt round-robin): ranks differ by at most one column
+        # load balance of the interleave (runs of 4 tile columns dealt round-robin): ranks differ by at most one run
         counts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
         dist.all_gather(counts, torch.tensor([len(mine)], dtype=torch.int64))
         rows = lay.tiles // lay.tile_cols
-        ok = ok and max(int(c) for c in counts) - min(int(c) for c in counts) <= rows
+        ok = ok and max(int(c) for c in counts) - min(int(c) for c in counts) <= 4 * rows
     if rank == 0:
         out_queue.put(ok)
     dist.barrier()
