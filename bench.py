@@ -390,28 +390,34 @@ def run_own(args):
     # ---- end to end: host-visible frame every step (pinned host memory), same cameras
     e2e_steps = min(steps, 100)
     host = pysvo.PinnedArray((H, W), np.uint32) if rank == 0 else None
+    host2 = pysvo.PinnedArray((H, W), np.uint32) if rank == 0 else None
+    hosts = [host.array, host2.array] if rank == 0 else None
+    copy_stream = torch.cuda.Stream()
     torch.cuda.synchronize()
     barrier()
     t0 = time.perf_counter()
     if world == 1:
         # pipelined host-buffer API: two frames in flight, each lands in its own pinned host buffer
-        host2 = pysvo.PinnedArray((H, W), np.uint32)
-        hosts = [host.array, host2.array]
         pending = [None, None]
+        dbg = [0.0, 0.0]
         for k in range(warmup, warmup + e2e_steps):
             slot = k & 1
+            ta = time.perf_counter()
             if pending[slot] is not None:
                 tree.frame_wait(pending[slot])          # frame k-2 is in host memory; its buffer is free again
+            tb = time.perf_counter()
             pending[slot] = tree.render_frame_async(cams[k % ORBIT], W, H, hosts[slot], strips=STRIPS, flavour=flavour)
+            dbg[0] += tb - ta
+            dbg[1] += time.perf_counter() - tb
         for pnd in pending:
             if pnd is not None:
                 tree.frame_wait(pnd)
+        if os.environ.get("SVO_BENCH_DEBUG"):
+            print(f"[e2e] wait {dbg[0] / e2e_steps * 1e3:.3f} ms/frame, issue {dbg[1] / e2e_steps * 1e3:.3f} ms/frame",
+                  file=sys.stderr, flush=True)
     else:
         # every rank stores its tiles into rank 0's framebuffer k & 1 over NVLink; after the frame barrier
         # rank 0 copies it to pinned host memory on a side stream while frame k+1 is rendered into the other one
-        host2 = pysvo.PinnedArray((H, W), np.uint32) if rank == 0 else None
-        hosts = [host.array, host2.array] if rank == 0 else None
-        copy_stream = torch.cuda.Stream()
         copied = [None, None]
         for k in range(warmup, warmup + e2e_steps):
             slot = k & 1
