@@ -166,12 +166,12 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
 
 
-def profile_traffic():
-    """dram bytes per fine-pass launch from the committed ncu --set full capture, if any."""
+def profile_traffic(workload):
+    """dram bytes per fine-pass launch of this workload from the committed ncu --set full capture, if any."""
     p = ROOT / "profiles" / "traffic.json"
     if p.exists():
         try:
-            return json.loads(p.read_text())
+            return json.loads(p.read_text()).get(workload)
         except Exception:  # noqa: BLE001
             return None
     return None
@@ -486,7 +486,7 @@ def run_own(args):
     roofline = None
     if world == 1 and fine_ms_sum > 0:
         achieved = alg_bytes / (fine_ms_sum * 1e-3) / 1e9
-        traffic = profile_traffic()
+        traffic = profile_traffic(w["name"])
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": (traffic or {}).get("dram_bytes_per_launch"),
                     "kernel": "finePassKernel<FAST>", "peak_source": peak_src,
@@ -494,8 +494,10 @@ def run_own(args):
                     "bytes_per_fine_ray": {"node_words": node_bytes_sum / max(fine_rays_sum, 1), "pixel_store": 4.0},
                     "launch_ms": fine_ms_sum / len(roof_cams),
                     "kernel_share_of_step": float(np.mean([f_ / (c_ + f_) for c_, f_ in kernel_ms])),
-                    "note": "latency/issue-bound pointer chasing: each 4 B node fetch moves a 32 B sector and "
-                            "most hit L1/L2 (see profiles/)"}
+                    "ncu": {k: (traffic or {}).get(k) for k in ("l1_hit_pct", "l2_hit_pct", "issue_active_pct",
+                                                               "threads_per_instruction", "source")},
+                    "note": "instruction-issue bound pointer chasing with SIMT divergence, not HBM-bound: node "
+                            "fetches hit L1/L2 (see profiles/ and DESIGN.md section 4)"}
 
     # ---- CPU baseline: the reference's own renderer on this box's host cores (bounded sample)
     cpu = None
