@@ -130,6 +130,35 @@ __device__ __forceinline__ uint32_t packGrey(float v) {
     return g | (g << 8) | (g << 16) | 0xFF000000u;
 }
 
+// The loop is bound by the SM's ALU pipe (integer / logic / compare / select: one warp instruction
+// per two cycles; ncu: 73 % of its peak, against 24 % on the FMA pipe, which issues every cycle).
+// So the per-axis "compare, conditionally move the position, collect a 3-bit mask" idiom spends
+// one ALU instruction per axis -- FSET, a compare that writes 1.0f / 0.0f -- and does the rest on
+// the FMA pipe: the position moves by flag*delta (exact: the product is 0 or delta) and the mask is
+// accumulated as flagX + 2*flagY + 4*flagZ + 2^23, whose low mantissa bits are the mask, instead of
+// SEL / IADD / FSEL chains.
+__device__ __forceinline__ float flagGreater(float a, float b) {
+    float r;
+    asm("set.gt.f32.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ float flagNotGreater(float a, float b) {
+    float r;
+    asm("set.le.f32.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+// p + flag*delta with flag in {0, 1}: exact product, one rounding-free add in [1, 2)
+template <bool FAST>
+__device__ __forceinline__ float moveIf(float flag, float delta, float p) {
+    if (FAST) return __fmaf_rn(flag, delta, p);
+    return __fadd_rn(__fmul_rn(flag, delta), p);
+}
+// bits 0-2 of the result = fx | fy << 1 | fz << 2 (flags are 0.0f / 1.0f; all sums are exact integers < 2^24)
+__device__ __forceinline__ uint32_t flagMask(float fx, float fy, float fz) {
+    float m = __fmaf_rn(fz, 4.0f, __fmaf_rn(fy, 2.0f, __fadd_rn(fx, 8388608.0f)));
+    return __float_as_uint(m);
+}
+
 // The scale-indexed stack (reference: StackEntry rayStack[24], VoxelOctree.cpp:208-212)
 // lives in shared memory as one (parent, maxT) pair per slot: slot s of thread t
 // is at byte s*STRIDE + t*ENTRY, so a warp touching one slot makes one
@@ -235,11 +264,12 @@ __device__ __forceinline__ int raymarch(const uint32_t *__restrict__ octree, flo
     float posX = 1.0f, posY = 1.0f, posZ = 1.0f;
     int scale = kMaxScale - 1;
     float scaleExp2 = 0.5f;
-    uint32_t sp = stack.top;                 // slot of the current scale
 
     if (A::mulsub(1.5f, dTx, bTx) > minT) { idx ^= 1; posX = 1.5f; }   // :248-250
     if (A::mulsub(1.5f, dTy, bTy) > minT) { idx ^= 2; posY = 1.5f; }
     if (A::mulsub(1.5f, dTz, bTz) > minT) { idx ^= 4; posZ = 1.5f; }
+    // the loop tracks the reference's `idx` as childShift = idx ^ octantMask (:261), which is what it uses
+    uint32_t childShift = idx ^ octantMask;
 
     for (;;) {
         if (current == 0) {
@@ -255,7 +285,6 @@ __device__ __forceinline__ int raymarch(const uint32_t *__restrict__ octree, flo
         const float cornerTZ = A::mulsub(posZ, dTz, bTz);
         const float maxTC = fminf(cornerTX, fminf(cornerTY, cornerTZ));
 
-        const uint32_t childShift = idx ^ octantMask;
         const uint32_t childMasks = current << childShift;
 
         if ((childMasks & 0x8000u) && minT <= maxT) {
@@ -283,8 +312,7 @@ __device__ __forceinline__ int raymarch(const uint32_t *__restrict__ octree, flo
                     return kHitLeaf;
                 }
 
-                Stack::store(sp, parent, maxT);                // :287-288
-                sp += Stack::kStride;
+                Stack::store(stack.slot(scale), parent, maxT);  // :287-288
 
                 // siblings before this child, doubled when the block is far-interleaved (bit 16), :290-293
                 const uint32_t siblings = uint32_t(__popc(childMasks & 127u)) << ((current >> 16) & 1u);
@@ -297,11 +325,12 @@ __device__ __forceinline__ int raymarch(const uint32_t *__restrict__ octree, flo
                 scale--;
                 scaleExp2 = half;
 
-                const bool upX = centerTX > minT, upY = centerTY > minT, upZ = centerTZ > minT;
-                posX = upX ? addRn(posX, half) : posX;
-                posY = upY ? addRn(posY, half) : posY;
-                posZ = upZ ? addRn(posZ, half) : posZ;
-                idx = (upX ? 1u : 0u) | (upY ? 2u : 0u) | (upZ ? 4u : 0u);
+                // idx = axes with centerT > minT, each of which moves to the upper half (:297-301)
+                const float upX = flagGreater(centerTX, minT), upY = flagGreater(centerTY, minT), upZ = flagGreater(centerTZ, minT);
+                posX = moveIf<FAST>(upX, half, posX);
+                posY = moveIf<FAST>(upY, half, posY);
+                posZ = moveIf<FAST>(upZ, half, posZ);
+                childShift = (flagMask(upX, upY, upZ) & 7u) ^ octantMask;
 
                 maxT = maxTV;
                 current = 0;
@@ -309,19 +338,21 @@ __device__ __forceinline__ int raymarch(const uint32_t *__restrict__ octree, flo
             }
         }
 
-        uint32_t stepMask = 0;                                  // :310-316
-        if (cornerTX <= maxTC) { stepMask |= 1; posX = subRn(posX, scaleExp2); }
-        if (cornerTY <= maxTC) { stepMask |= 2; posY = subRn(posY, scaleExp2); }
-        if (cornerTZ <= maxTC) { stepMask |= 4; posZ = subRn(posZ, scaleExp2); }
-
+        // :310-316: every axis whose plane is reached at maxTC steps down by one cell
+        const float stX = flagNotGreater(cornerTX, maxTC), stY = flagNotGreater(cornerTY, maxTC), stZ = flagNotGreater(cornerTZ, maxTC);
+        const uint32_t oldX = __float_as_uint(posX), oldY = __float_as_uint(posY), oldZ = __float_as_uint(posZ);
+        posX = moveIf<FAST>(stX, -scaleExp2, posX);
+        posY = moveIf<FAST>(stY, -scaleExp2, posY);
+        posZ = moveIf<FAST>(stZ, -scaleExp2, posZ);
+        const uint32_t stepMask = flagMask(stX, stY, stZ) & 7u;
         minT = maxTC;
-        idx ^= stepMask;
+        childShift ^= stepMask;                                 // idx ^= stepMask
 
-        if ((idx & stepMask) != 0) {                            // :318-338
-            uint32_t differingBits = 0;
-            if (stepMask & 1) differingBits |= __float_as_uint(posX) ^ __float_as_uint(addRn(posX, scaleExp2));
-            if (stepMask & 2) differingBits |= __float_as_uint(posY) ^ __float_as_uint(addRn(posY, scaleExp2));
-            if (stepMask & 4) differingBits |= __float_as_uint(posZ) ^ __float_as_uint(addRn(posZ, scaleExp2));
+        if (((childShift ^ octantMask) & stepMask) != 0) {      // (idx & stepMask) != 0, :318-338
+            // pos ^ (pos + scaleExp2) over the stepped axes (:320-322); an axis that did not step has
+            // pos == old and contributes nothing
+            const uint32_t differingBits = (__float_as_uint(posX) ^ oldX) | (__float_as_uint(posY) ^ oldY) |
+                                           (__float_as_uint(posZ) ^ oldZ);
             // reference: exponent of (float)differingBits. differingBits < 2^24
             // always (positions stay in [0.5, 2)), so that is the index of the
             // highest set bit; bit 23 set <=> the ray left the root (:341-342)
@@ -329,8 +360,7 @@ __device__ __forceinline__ int raymarch(const uint32_t *__restrict__ octree, flo
             scale = 31 - __clz(int(differingBits));
             scaleExp2 = __uint_as_float(uint32_t(scale - kMaxScale + 127) << 23);
 
-            sp = stack.slot(scale);
-            Stack::load(sp, parent, maxT);
+            Stack::load(stack.slot(scale), parent, maxT);
 
             const uint32_t shX = __float_as_uint(posX) >> scale;   // truncate positions to the `scale` grid
             const uint32_t shY = __float_as_uint(posY) >> scale;
@@ -338,7 +368,7 @@ __device__ __forceinline__ int raymarch(const uint32_t *__restrict__ octree, flo
             posX = __uint_as_float(shX << scale);
             posY = __uint_as_float(shY << scale);
             posZ = __uint_as_float(shZ << scale);
-            idx = (shX & 1u) | ((shY & 1u) << 1) | ((shZ & 1u) << 2);
+            childShift = ((shX & 1u) | ((shY & 1u) << 1) | ((shZ & 1u) << 2)) ^ octantMask;
 
             current = 0;
         }
