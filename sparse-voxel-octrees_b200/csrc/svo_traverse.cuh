@@ -271,15 +271,19 @@ __device__ __forceinline__ int raymarch(const uint32_t *__restrict__ octree, flo
     // the loop tracks the reference's `idx` as childShift = idx ^ octantMask (:261), which is what it uses
     uint32_t childShift = idx ^ octantMask;
 
-    for (;;) {
-        if (current == 0) {
-            // descriptor and its possible far word (bit 17) in flight together;
-            // the node array carries one padding word so parent + 1 is always readable
-            const uint32_t *node = octree + parent;
-            current = ldNode(node);
-            farWord = ldNode(node + 1);
-        }
+    // Descriptor and its possible far word (bit 17) are fetched together (the node array carries one
+    // padding word so parent + 1 is always readable), right where `parent` changes: before the loop,
+    // at the end of a push and at the end of a pop -- the reference's `current == 0` refetch flag
+    // (:253-254, :305, :337) never has to be tested.
+#define SVO_FETCH_NODE()                                   \
+    do {                                                   \
+        const uint32_t *node_ = octree + parent;           \
+        current = ldNode(node_);                           \
+        farWord = ldNode(node_ + 1);                       \
+    } while (0)
+    SVO_FETCH_NODE();
 
+    for (;;) {
         const float cornerTX = A::mulsub(posX, dTx, bTx);   // :256-259
         const float cornerTY = A::mulsub(posY, dTy, bTy);
         const float cornerTZ = A::mulsub(posZ, dTz, bTz);
@@ -333,14 +337,13 @@ __device__ __forceinline__ int raymarch(const uint32_t *__restrict__ octree, flo
                 childShift = (flagMask(upX, upY, upZ) & 7u) ^ octantMask;
 
                 maxT = maxTV;
-                current = 0;
+                SVO_FETCH_NODE();
                 continue;
             }
         }
 
         // :310-316: every axis whose plane is reached at maxTC steps down by one cell
         const float stX = flagNotGreater(cornerTX, maxTC), stY = flagNotGreater(cornerTY, maxTC), stZ = flagNotGreater(cornerTZ, maxTC);
-        const uint32_t oldX = __float_as_uint(posX), oldY = __float_as_uint(posY), oldZ = __float_as_uint(posZ);
         posX = moveIf<FAST>(stX, -scaleExp2, posX);
         posY = moveIf<FAST>(stY, -scaleExp2, posY);
         posZ = moveIf<FAST>(stZ, -scaleExp2, posZ);
@@ -349,10 +352,12 @@ __device__ __forceinline__ int raymarch(const uint32_t *__restrict__ octree, flo
         childShift ^= stepMask;                                 // idx ^= stepMask
 
         if (((childShift ^ octantMask) & stepMask) != 0) {      // (idx & stepMask) != 0, :318-338
-            // pos ^ (pos + scaleExp2) over the stepped axes (:320-322); an axis that did not step has
-            // pos == old and contributes nothing
-            const uint32_t differingBits = (__float_as_uint(posX) ^ oldX) | (__float_as_uint(posY) ^ oldY) |
-                                           (__float_as_uint(posZ) ^ oldZ);
+            // pos ^ (pos + scaleExp2) over the stepped axes (:320-322); an axis that did not step adds
+            // 0*scaleExp2 and contributes nothing
+            const uint32_t differingBits =
+                (__float_as_uint(posX) ^ __float_as_uint(moveIf<FAST>(stX, scaleExp2, posX))) |
+                (__float_as_uint(posY) ^ __float_as_uint(moveIf<FAST>(stY, scaleExp2, posY))) |
+                (__float_as_uint(posZ) ^ __float_as_uint(moveIf<FAST>(stZ, scaleExp2, posZ)));
             // reference: exponent of (float)differingBits. differingBits < 2^24
             // always (positions stay in [0.5, 2)), so that is the index of the
             // highest set bit; bit 23 set <=> the ray left the root (:341-342)
@@ -361,18 +366,21 @@ __device__ __forceinline__ int raymarch(const uint32_t *__restrict__ octree, flo
             scaleExp2 = __uint_as_float(uint32_t(scale - kMaxScale + 127) << 23);
 
             Stack::load(stack.slot(scale), parent, maxT);
+            SVO_FETCH_NODE();
 
-            const uint32_t shX = __float_as_uint(posX) >> scale;   // truncate positions to the `scale` grid
-            const uint32_t shY = __float_as_uint(posY) >> scale;
-            const uint32_t shZ = __float_as_uint(posZ) >> scale;
-            posX = __uint_as_float(shX << scale);
-            posY = __uint_as_float(shY << scale);
-            posZ = __uint_as_float(shZ << scale);
-            childShift = ((shX & 1u) | ((shY & 1u) << 1) | ((shZ & 1u) << 2)) ^ octantMask;
-
-            current = 0;
+            // Truncate the positions to the `scale` grid (:329-334) on the FMA pipe: adding 2^scale with
+            // round-toward-zero leaves exactly the mantissa bits >= `scale` (positions are in [1, 2), the
+            // sum is in [2^scale, 2^(scale+1))), its lowest mantissa bit is the new idx bit, and
+            // subtracting 2^scale again is exact.
+            const float big = mulRn(scaleExp2, 8388608.0f);
+            const float tX = __fadd_rz(posX, big), tY = __fadd_rz(posY, big), tZ = __fadd_rz(posZ, big);
+            posX = subRn(tX, big);
+            posY = subRn(tY, big);
+            posZ = subRn(tZ, big);
+            childShift = ((__float_as_uint(tX) & 1u) | ((__float_as_uint(tY) & 1u) << 1) | ((__float_as_uint(tZ) & 1u) << 2)) ^ octantMask;
         }
     }
+#undef SVO_FETCH_NODE
 }
 
 } // namespace svo
