@@ -16,7 +16,11 @@ namespace {
 
 constexpr int kBatchThreads = 128;
 constexpr int kCoarseThreads = 64;
-constexpr int kTileThreads = 64;   // one 8x8 tile per block: two warps of 8x4 pixels
+constexpr int kTileThreads = 64;   // an 8x8 tile = two warps of 8x4 pixels
+#ifndef SVO_TILES_PER_BLOCK
+#define SVO_TILES_PER_BLOCK 1
+#endif
+constexpr unsigned kTilesPerBlock = SVO_TILES_PER_BLOCK;
 constexpr int kClassifyThreads = 128;
 
 // ---- K1 -------------------------------------------------------------------
@@ -165,26 +169,34 @@ finePassKernel(const uint32_t *__restrict__ octree, FramePlanDev plan, FrameCons
     SmemStack<IdxT, kTileThreads> stack;
     stack.init(smem);
 
-    if (blockIdx.x >= counters->tilesRendered) return;
-    const uint4 rec = __ldg(reinterpret_cast<const uint4 *>(tiles) + blockIdx.x);
-    int px = int(rec.x & 0xFFFFu) + int(threadIdx.x & 7);
-    int py = int(rec.x >> 16) + int(threadIdx.x >> 3);
-    if (px >= plan.width || py >= int(rec.y)) return;
-    float startT = __uint_as_float(rec.z);
+    // kTilesPerBlock consecutive list entries per block: each warp renders the same 8x4 half of each of
+    // them in turn, which evens out the two warps' lifetimes (a block's warp slots are only released
+    // when its slowest warp is done) and amortises the block launch.
+    const unsigned nTiles = counters->tilesRendered;
+#pragma unroll 1
+    for (unsigned t = 0; t < kTilesPerBlock; ++t) {
+        const unsigned tile = blockIdx.x*kTilesPerBlock + t;
+        if (tile >= nTiles) return;
+        const uint4 rec = __ldg(reinterpret_cast<const uint4 *>(tiles) + tile);
+        const int px = int(rec.x & 0xFFFFu) + int(threadIdx.x & 7);
+        const int py = int(rec.x >> 16) + int(threadIdx.x >> 3);
+        if (px >= plan.width || py >= int(rec.y)) continue;
+        const float startT = __uint_as_float(rec.z);
 
-    float rx, ry, rz;
-    rayDirection(f, __ldg(plan.dxFine + px), __ldg(plan.dyFine + py), rx, ry, rz);
-    float ox = addRn(f.posX, mulRn(rx, startT));            // pos + dir*minT, Main.cpp:118
-    float oy = addRn(f.posY, mulRn(ry, startT));
-    float oz = addRn(f.posZ, mulRn(rz, startT));
+        float rx, ry, rz;
+        rayDirection(f, __ldg(plan.dxFine + px), __ldg(plan.dyFine + py), rx, ry, rz);
+        const float ox = addRn(f.posX, mulRn(rx, startT));      // pos + dir*minT, Main.cpp:118
+        const float oy = addRn(f.posY, mulRn(ry, startT));
+        const float oz = addRn(f.posZ, mulRn(rz, startT));
 
-    float tHit;
-    uint32_t material = 0;
-    uint64_t vox;
-    int code = raymarch<FAST, false, IdxT, kTileThreads>(octree, ox, oy, oz, rx, ry, rz, 0.0f, stack, tHit, material, vox);
-    uint32_t colour = 0xFF000000u;                          // Vec3() -> black, Main.cpp:117
-    if (code != kMiss) colour = packGrey(shadeMaterial(material, rx, ry, rz, f.lightX, f.lightY, f.lightZ));
-    rgba[size_t(py)*size_t(plan.width) + px] = colour;
+        float tHit;
+        uint32_t material = 0;
+        uint64_t vox;
+        const int code = raymarch<FAST, false, IdxT, kTileThreads>(octree, ox, oy, oz, rx, ry, rz, 0.0f, stack, tHit, material, vox);
+        uint32_t colour = 0xFF000000u;                          // Vec3() -> black, Main.cpp:117
+        if (code != kMiss) colour = packGrey(shadeMaterial(material, rx, ry, rz, f.lightX, f.lightY, f.lightZ));
+        rgba[size_t(py)*size_t(plan.width) + px] = colour;
+    }
 }
 
 inline uint32_t stackSlots(const TreeDev &tree) { return tree.depth > 1 ? tree.depth - 1 : 1; }
@@ -263,7 +275,8 @@ cudaError_t launchFineT(const TreeDev &tree, const FramePlanDev &plan, const Fra
     auto kernel = finePassKernel<FAST, IdxT>;
     cudaError_t e = ensureSmem(kernel, smem);
     if (e != cudaSuccess) return e;
-    kernel<<<owned, kTileThreads, smem, stream>>>(tree.words, plan, consts, tiles, counters, rgba);
+    int blocks = (owned + int(kTilesPerBlock) - 1)/int(kTilesPerBlock);
+    kernel<<<blocks, kTileThreads, smem, stream>>>(tree.words, plan, consts, tiles, counters, rgba);
     return cudaGetLastError();
 }
 
