@@ -199,6 +199,16 @@ finePassKernel(const uint32_t *__restrict__ octree, FramePlanDev plan, FrameCons
     }
 }
 
+// 64-bit word indices are needed from 2^32 words (16 GiB) on; SVO_FORCE_WIDE_INDEX=1 selects that
+// instantiation for any tree so that tests can cover it.
+inline bool wideIndex(const TreeDev &tree) {
+    static const bool force = [] {
+        const char *e = getenv("SVO_FORCE_WIDE_INDEX");
+        return e && e[0] == '1';
+    }();
+    return force || tree.nWords >= (1ull << 32);
+}
+
 inline uint32_t stackSlots(const TreeDev &tree) { return tree.depth > 1 ? tree.depth - 1 : 1; }
 
 template <typename K>
@@ -286,7 +296,7 @@ cudaError_t launchRaymarchBatch(const TreeDev &tree, uint64_t n, const float *o,
                                 int flavour, uint8_t *hit, float *t, uint32_t *normal, uint64_t *voxel,
                                 cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
-    bool wide = tree.nWords >= (1ull << 32);
+    bool wide = wideIndex(tree);
     bool lod = rayScale != 0.0f;
     bool fast = flavour != 0;
 #define SVO_BATCH(F, L) \
@@ -305,7 +315,7 @@ cudaError_t launchCoarsePass(const TreeDev &tree, const FramePlanDev &plan, cons
     // last-bit change here moves every ray origin of a tile or drops / adds a
     // whole tile. It is < 5 % of the rays; FAST only changes the fine pass.
     (void)flavour;
-    bool wide = tree.nWords >= (1ull << 32);
+    bool wide = wideIndex(tree);
     return wide ? launchCoarseT<uint64_t>(tree, plan, consts, depth, counters, tileRank, tileWorld, stream)
                 : launchCoarseT<uint32_t>(tree, plan, consts, depth, counters, tileRank, tileWorld, stream);
 }
@@ -326,7 +336,7 @@ cudaError_t launchFinePass(const TreeDev &tree, const FramePlanDev &plan, const 
                            int tileRank, int tileWorld, cudaStream_t stream) {
     int owned = ownedTiles(plan, tileRank, tileWorld);
     if (owned <= 0) return cudaSuccess;
-    bool wide = tree.nWords >= (1ull << 32);
+    bool wide = wideIndex(tree);
     if (flavour != 0)
         return wide ? launchFineT<true, uint64_t>(tree, plan, consts, tiles, counters, rgba, owned, stream)
                     : launchFineT<true, uint32_t>(tree, plan, consts, tiles, counters, rgba, owned, stream);

@@ -1,0 +1,148 @@
+"""GPU: parity on the synthetic scenes of BASELINE.json configs[1]-[4] (small instances built by the
+reference's own builder through oracle/_ref; the full-size scenes are checked by bench.py's `parity`
+field): far-pointer-heavy trees, the ambient-occlusion ray batches of configs[3], the near/far
+fly-through of configs[4], and the 64-bit-index kernel instantiation."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from oracle.pyoracle import pixel_rays
+
+pytestmark = pytest.mark.gpu
+T_MISS = np.float32(1e10)
+
+
+def _scene(pysvo, name):
+    from tools import make_scenes
+    p = make_scenes.scene_path(name)
+    if not p.exists():
+        try:
+            make_scenes.make_scene(name, verbose=False)
+        except (FileNotFoundError, OSError) as e:
+            pytest.skip(f"scene {name} not cached and oracle/_ref unavailable to build it: {e}")
+    return pysvo.oct_read(p)
+
+
+@pytest.fixture(scope="module")
+def sdf(pysvo):
+    words, center = _scene(pysvo, "sdf256")
+    tree = pysvo.VoxelOctree(words=words, center=center)
+    yield tree, words, center
+    tree.close()
+
+
+@pytest.fixture(scope="module")
+def ico(pysvo):
+    words, center = _scene(pysvo, "ico256")
+    tree = pysvo.VoxelOctree(words=words, center=center)
+    yield tree, words, center
+    tree.close()
+
+
+def _frame_pair(pysvo, port, tree, words, center, cam_args, W, H, S, flavour):
+    cam = pysvo.orbit_camera(*cam_args)
+    f = port.frame_constants(np.array(cam.model[:], np.float32), np.array(cam.view[:], np.float32), center, W, H, S)
+    want, wdepth, cc, cf = port.render_frame(words, f, want_depth=True)
+    got, depth, st = tree.render_frame(cam, W, H, strips=S, flavour=flavour, want_depth=True)
+    return want, wdepth, got, depth, st, cc, cf
+
+
+@pytest.mark.parametrize("cam_args", [(20.0, 40.0, 0.9), (20.0, 130.0, 0.5), (-30.0, 300.0, 2.0), (75.0, 10.0, 0.42)])
+def test_sdf_scene_frames_bit_exact(pysvo, port, sdf, cam_args):
+    tree, words, center = sdf
+    want, wdepth, got, depth, st, cc, cf = _frame_pair(pysvo, port, tree, words, center, cam_args, 640, 360, 8,
+                                                       pysvo.FLAVOUR_VALIDATION)
+    assert np.array_equal(depth.view(np.uint32), wdepth.view(np.uint32))
+    assert np.array_equal(got, want)
+    assert (st.coarse_rays, st.fine_rays) == (cc.rays, cf.rays)
+    fast, _, _ = tree.render_frame(pysvo.orbit_camera(*cam_args), 640, 360, strips=8, flavour=pysvo.FLAVOUR_FAST)
+    assert (fast == want).mean() >= 0.9999
+
+
+def test_flythrough_sweep_bit_exact(pysvo, port, ico):
+    """configs[4]: radius geometric 2.0 -> 0.05, yaw 0 -> 180 degrees, pitch 20 (10 of the 100 frames)."""
+    tree, words, center = ico
+    n = 10
+    for k in range(n):
+        radius = 2.0 * (0.05 / 2.0) ** (k / (n - 1))
+        yaw = 180.0 * k / (n - 1)
+        want, wdepth, got, depth, st, cc, cf = _frame_pair(pysvo, port, tree, words, center, (20.0, yaw, radius),
+                                                           480, 270, 6, pysvo.FLAVOUR_VALIDATION)
+        assert np.array_equal(depth.view(np.uint32), wdepth.view(np.uint32)), f"frame {k}"
+        assert np.array_equal(got, want), f"frame {k}: {int((got != want).sum())} pixels differ"
+
+
+def test_ambient_occlusion_batches_bit_exact(pysvo, port, sdf):
+    """configs[3]: incoherent secondary rays through the batch API (K1), validation and fast flavours."""
+    from tools.ao_rays import ao_rays
+    tree, words, center = sdf
+    cam = pysvo.orbit_camera(20.0, 40.0, 0.9)
+    f = port.frame_constants(np.array(cam.model[:], np.float32), np.array(cam.view[:], np.float32), center, 240, 135, 4)
+    o, d = pixel_rays(f)
+    prim = tree.raymarch_batch(o, d, 0.0, pysvo.FLAVOUR_VALIDATION)
+    want_prim = port.raymarch_batch(words, o, d, 0.0, t_sentinel=float(T_MISS))
+    assert np.array_equal(prim["hit"], want_prim["hit"]) and np.array_equal(prim["normal"], want_prim["normal"])
+    ao_o, ao_d, pix = ao_rays(o, d, prim["t"], prim["normal"], prim["hit"] == 1, spp=16)
+    assert ao_o.shape[0] == 16 * int((prim["hit"] == 1).sum()) and ao_o.shape[0] > 100000
+    want = port.raymarch_batch(words, ao_o, ao_d, 0.0, t_sentinel=float(T_MISS))
+    got = tree.raymarch_batch(ao_o, ao_d, 0.0, pysvo.FLAVOUR_VALIDATION)
+    assert np.array_equal(got["hit"], want["hit"])
+    assert np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32))
+    hit = want["hit"] > 0
+    assert np.array_equal(got["voxel"][hit], want["voxel"][hit])
+    assert np.array_equal(got["normal"][hit], want["normal"][hit])
+    assert 0.05 < hit.mean() < 0.95          # a real mix of occluded and unoccluded rays
+    fast = tree.raymarch_batch(ao_o, ao_d, 0.0, pysvo.FLAVOUR_FAST)
+    same = (fast["hit"] == want["hit"]) & (fast["voxel"] == np.where(hit, want["voxel"], pysvo.VOXEL_NONE))
+    assert same.mean() >= 0.9999
+
+
+def test_large_scene_frame_if_cached(pysvo, port):
+    """2048^3 SDF scene (far-pointer heavy, depth 11) when its .oct travelled with the snapshot."""
+    from tools import make_scenes
+    p = make_scenes.scene_path("sdf2048")
+    if not p.exists():
+        pytest.skip("scenes/_cache/sdf2048.oct not present")
+    words, center = pysvo.oct_read(p)
+    tree = pysvo.VoxelOctree(words=words, center=center)
+    assert tree.depth == 11
+    want, wdepth, got, depth, st, cc, cf = _frame_pair(pysvo, port, tree, words, center, (20.0, 40.0, 0.9), 960, 540, 16,
+                                                       pysvo.FLAVOUR_VALIDATION)
+    tree.close()
+    assert cf.far_fetches > 0.1 * cf.desc_fetches     # the far-word path is really exercised
+    assert np.array_equal(depth.view(np.uint32), wdepth.view(np.uint32))
+    assert np.array_equal(got, want)
+
+
+def test_wide_index_kernels_match(pysvo):
+    """The uint64-index instantiation (trees of 2^32 words and more) forced onto a small tree in a
+    subprocess (SVO_FORCE_WIDE_INDEX=1): frames and batches must equal the 32-bit kernels' output."""
+    code = r'''
+import sys, hashlib, numpy as np
+sys.path.insert(0, "%s"); sys.path.insert(0, "%s")
+import pysvo
+from oracle.pyoracle import Port, pixel_rays
+tree = pysvo.VoxelOctree("%s")
+cam = pysvo.orbit_camera(20.0, 135.0, 0.5)
+rgba, depth, st = tree.render_frame(cam, 640, 360, strips=8, flavour=pysvo.FLAVOUR_VALIDATION, want_depth=True)
+port = Port()
+f = port.frame_constants(np.array(cam.model[:], np.float32), np.array(cam.view[:], np.float32), tree.center(), 320, 180, 4)
+o, d = pixel_rays(f)
+b = tree.raymarch_batch(o, d, 0.0, pysvo.FLAVOUR_VALIDATION)
+l = tree.raymarch_batch(o, d, 0.05, pysvo.FLAVOUR_FAST)
+h = hashlib.sha256()
+for a in (rgba, depth, b["hit"], b["t"], b["normal"], b["voxel"], l["hit"], l["t"], l["voxel"]):
+    h.update(np.ascontiguousarray(a).tobytes())
+print("DIGEST", h.hexdigest())
+''' % (ROOT, ROOT / "sparse-voxel-octrees_b200", ROOT / "tests" / "golden" / "XYZRGB-Dragon.oct")
+    digests = []
+    for wide in ("0", "1"):
+        env = dict(os.environ, SVO_FORCE_WIDE_INDEX=wide)
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        digests.append([ln for ln in out.stdout.splitlines() if ln.startswith("DIGEST")][0])
+    assert digests[0] == digests[1]
