@@ -555,31 +555,40 @@ int svo_raymarch_batch(svo_tree *tree, uint64_t n, const float *o, const float *
     SVO_DEVICE(tree->device);
     std::lock_guard<std::mutex> lock(tree->mutex);
 
-    const size_t rayBytes = size_t(n)*3*sizeof(float);
-    SVO_CUDA(tree->batchIn.reserve(2*rayBytes));
-    // outputs: voxel (8) | t (4) | normal (4) | hit (1) per ray, each section 16-byte aligned
+    // Chunks alternate between two streams, each with its own staging area, so that the upload of
+    // chunk k+1 and the download of chunk k-1 overlap the traversal of chunk k (page-locked host
+    // buffers make the copies truly asynchronous; pageable ones still work).
+    const uint64_t kChunk = 1ull << 21;
+    const uint64_t chunk = n < kChunk ? n : kChunk;
     auto align16 = [](size_t v) { return (v + 15) & ~size_t(15); };
-    size_t offVoxel = 0, offT = align16(offVoxel + size_t(n)*8), offNormal = align16(offT + size_t(n)*4),
-           offHit = align16(offNormal + size_t(n)*4), total = align16(offHit + size_t(n));
-    SVO_CUDA(tree->batchOut.reserve(total));
+    const size_t inBytes = align16(size_t(chunk)*3*sizeof(float));
+    const size_t offVoxel = 0, offT = align16(offVoxel + size_t(chunk)*8), offNormal = align16(offT + size_t(chunk)*4),
+                 offHit = align16(offNormal + size_t(chunk)*4), outBytes = align16(offHit + size_t(chunk));
+    SVO_CUDA(tree->batchIn.reserve(4*inBytes));
+    SVO_CUDA(tree->batchOut.reserve(2*outBytes));
 
-    float *dO = static_cast<float *>(tree->batchIn.ptr);
-    float *dD = dO + size_t(n)*3;
-    unsigned char *base = static_cast<unsigned char *>(tree->batchOut.ptr);
-    uint64_t *dVoxel = voxel ? reinterpret_cast<uint64_t *>(base + offVoxel) : nullptr;
-    float *dT = t ? reinterpret_cast<float *>(base + offT) : nullptr;
-    uint32_t *dNormal = normal ? reinterpret_cast<uint32_t *>(base + offNormal) : nullptr;
-    uint8_t *dHit = hit ? base + offHit : nullptr;
-
-    cudaStream_t s = tree->stream;
-    SVO_CUDA(cudaMemcpyAsync(dO, o, rayBytes, cudaMemcpyHostToDevice, s));
-    SVO_CUDA(cudaMemcpyAsync(dD, d, rayBytes, cudaMemcpyHostToDevice, s));
-    SVO_CUDA(svo::launchRaymarchBatch(tree->dev(), n, dO, dD, ray_scale, flavour, dHit, dT, dNormal, dVoxel, s));
-    if (hit) SVO_CUDA(cudaMemcpyAsync(hit, dHit, size_t(n), cudaMemcpyDeviceToHost, s));
-    if (t) SVO_CUDA(cudaMemcpyAsync(t, dT, size_t(n)*4, cudaMemcpyDeviceToHost, s));
-    if (normal) SVO_CUDA(cudaMemcpyAsync(normal, dNormal, size_t(n)*4, cudaMemcpyDeviceToHost, s));
-    if (voxel) SVO_CUDA(cudaMemcpyAsync(voxel, dVoxel, size_t(n)*8, cudaMemcpyDeviceToHost, s));
-    SVO_CUDA(cudaStreamSynchronize(s));
+    cudaStream_t streams[2] = {tree->stream, tree->stream2};
+    for (uint64_t begin = 0, k = 0; begin < n; begin += chunk, ++k) {
+        const uint64_t m = n - begin < chunk ? n - begin : chunk;
+        const int slot = int(k & 1);
+        cudaStream_t s = streams[slot];
+        float *dO = reinterpret_cast<float *>(static_cast<unsigned char *>(tree->batchIn.ptr) + size_t(slot)*2*inBytes);
+        float *dD = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(dO) + inBytes);
+        unsigned char *base = static_cast<unsigned char *>(tree->batchOut.ptr) + size_t(slot)*outBytes;
+        uint64_t *dVoxel = voxel ? reinterpret_cast<uint64_t *>(base + offVoxel) : nullptr;
+        float *dT = t ? reinterpret_cast<float *>(base + offT) : nullptr;
+        uint32_t *dNormal = normal ? reinterpret_cast<uint32_t *>(base + offNormal) : nullptr;
+        uint8_t *dHit = hit ? base + offHit : nullptr;
+        SVO_CUDA(cudaMemcpyAsync(dO, o + 3*begin, size_t(m)*3*sizeof(float), cudaMemcpyHostToDevice, s));
+        SVO_CUDA(cudaMemcpyAsync(dD, d + 3*begin, size_t(m)*3*sizeof(float), cudaMemcpyHostToDevice, s));
+        SVO_CUDA(svo::launchRaymarchBatch(tree->dev(), m, dO, dD, ray_scale, flavour, dHit, dT, dNormal, dVoxel, s));
+        if (hit) SVO_CUDA(cudaMemcpyAsync(hit + begin, dHit, size_t(m), cudaMemcpyDeviceToHost, s));
+        if (t) SVO_CUDA(cudaMemcpyAsync(t + begin, dT, size_t(m)*4, cudaMemcpyDeviceToHost, s));
+        if (normal) SVO_CUDA(cudaMemcpyAsync(normal + begin, dNormal, size_t(m)*4, cudaMemcpyDeviceToHost, s));
+        if (voxel) SVO_CUDA(cudaMemcpyAsync(voxel + begin, dVoxel, size_t(m)*8, cudaMemcpyDeviceToHost, s));
+    }
+    SVO_CUDA(cudaStreamSynchronize(streams[0]));
+    SVO_CUDA(cudaStreamSynchronize(streams[1]));
     return SVO_OK;
 }
 

@@ -244,6 +244,21 @@ def test_batch_edge_cases(pysvo, port, gpu_dragon, dragon_words):
         assert np.array_equal(got["normal"][leaf], want["normal"][leaf])
 
 
+def test_batch_multi_chunk_host_api(pysvo, port, gpu_dragon, dragon_words):
+    """More than one 2 Mi-ray chunk: the double-buffered upload / trace / download pipeline of svo_raymarch_batch."""
+    words, _ = dragon_words
+    rng = np.random.default_rng(21)
+    n = (1 << 22) + 12345
+    o = rng.uniform(0.5, 2.5, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    want = port.raymarch_batch(words, o, d, 0.0, t_sentinel=float(T_MISS))
+    got = gpu_dragon.raymarch_batch(o, d, 0.0, pysvo.FLAVOUR_VALIDATION)
+    assert np.array_equal(got["hit"], want["hit"])
+    assert np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32))
+    hit = want["hit"] > 0
+    assert np.array_equal(got["voxel"][hit], want["voxel"][hit]) and np.array_equal(got["normal"][hit], want["normal"][hit])
+
+
 def test_save_oct_roundtrip_from_hbm(pysvo, gpu_dragon, dragon_words, tmp_path):
     words, center = dragon_words
     p = tmp_path / "saved.oct"
