@@ -268,7 +268,7 @@ def run_reference_ao(args, w):
             "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "reference",
                              "sample": f"first {sample} of {n} AO rays per step, {steps} step(s) after {warmup} warm-up"},
             "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_own_ao(args, w):
@@ -391,7 +391,7 @@ def run_own_ao(args, w):
                          "bytes_per_ray": b_ray}}
     if cpu:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist:
         dist.barrier()
         dist.destroy_process_group()
@@ -420,7 +420,7 @@ def run_reference(args):
         "e2e": {"value": r["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -714,13 +714,37 @@ def run_own(args):
         line["roofline"] = roofline
     if cpu is not None:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The one JSON line, on the process's real stdout."""
+    text = json.dumps(line) + "\n"
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, text.encode())
+    else:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+
+
+def quarantine_stdout():
+    """The reference's C++ code prints progress on std::cout (VoxelOctree.cpp:87, PlyLoader.cpp:465, ...), and
+    its buffer may flush at exit, after our line. Point fd 1 at stderr for the whole run and keep the real
+    stdout for the single JSON line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
 def main():
+    quarantine_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
