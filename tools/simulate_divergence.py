@@ -173,3 +173,47 @@ if __name__ == "__main__" and len(sys.argv) > 5 and sys.argv[5] == "vote":
     print(f"single loop {t0 / rays:.1f}  eff {useful / t0:.3f}")
     for mode in ("majority", "step-first"):
         print(mode, f"{scheme_vote(ops, counts, now, mode) / rays:.1f}")
+
+
+def scheme_deferred_pop(ops, counts, c, threshold):
+    """Single loop, but lanes whose advance needs a pop wait (idle) until at least `threshold` lanes of the
+    warp are waiting for one -- or nothing else can run -- and then all pop together."""
+    total = 0.0
+    for w in range(ops.shape[0]):
+        n = counts[w].astype(np.int64)
+        if n.max() == 0:
+            continue
+        pos = np.zeros(32, np.int64)
+        o = ops[w]
+        ar = np.arange(32)
+        pend = np.zeros(32, bool)       # advanced, pop still owed
+        total += c['pro']
+        while True:
+            live = pos < n
+            if not (live | pend).any():
+                break
+            cur = np.where(live & ~pend, o[ar, np.minimum(pos, np.maximum(n - 1, 0))], 0)
+            run = live & ~pend
+            isP, isL = run & (cur == P), run & (cur == Lf)
+            isA = run & ((cur == A) | (cur == Q) | (cur == X))
+            isQ = run & ((cur == Q) | (cur == X))
+            if run.any():
+                total += c['H'] + ((c['V']) if (isP | isL).any() else 0) + (c['P'] if isP.any() else 0) \
+                    + (c['L'] if isL.any() else 0) + (c['A'] if isA.any() else 0)
+                pos = pos + (isP | isL | (isA & ~isQ))
+                pend = pend | isQ
+            if pend.sum() >= threshold or (pend.any() and not ((pos < n) & ~pend).any()):
+                total += c['Q']
+                pos = pos + pend
+                pend[:] = False
+    return total
+
+
+if __name__ == "__main__" and len(sys.argv) > 5 and sys.argv[5] == "defer":
+    ops, counts = trace(sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]))
+    rays = int((counts > 0).sum())
+    now = dict(H=15, V=8, P=27, A=15, Q=37, L=105, pro=150)
+    t0, useful, trips = scheme_single_loop(ops, counts, now)
+    print(f"single loop {t0 / rays:.1f}  eff {useful / t0:.3f}")
+    for th in (1, 4, 8, 12, 16, 24):
+        print("defer pops until", th, f"lanes: {scheme_deferred_pop(ops, counts, now, th) / rays:.1f}")
