@@ -41,6 +41,14 @@ WORKLOADS = {
                           text="configs[1] scene at 3840x2160"),
     "c1_dragon_720p": dict(scene=None, width=1280, height=720, pitch=0.0, yaw0=0.0, yaw_step=3.6, radius=1.0,
                            text="configs[0]: models/XYZRGB-Dragon.oct (256^3), 1280x720 primary rays, orbit radius 1"),
+    "c5_flythrough_ico8192": dict(scene="ico8192", width=3840, height=2160, path="flythrough", pitch=20.0, yaw0=0.0,
+                                  yaw_step=0.0, radius=2.0,
+                                  text="configs[4]: camera fly-through, 100 frames, radius geometric 2.0 -> 0.05, yaw 0 -> 180 "
+                                       "degrees, pitch 20, on the 8192^3 octree at 3840x2160"),
+    "c5_flythrough_sdf2048": dict(scene="sdf2048", width=3840, height=2160, path="flythrough", pitch=20.0, yaw0=0.0,
+                                  yaw_step=0.0, radius=2.0,
+                                  text="configs[4] camera path (100 frames, radius 2.0 -> 0.05, yaw 0 -> 180, pitch 20) on "
+                                       "the 2048^3 SDF scene at 3840x2160"),
     "c4_ao_sdf2048": dict(scene="sdf2048", kind="ao", width=1920, height=1080, spp=16, pitch=20.0, yaw0=40.0, yaw_step=3.6,
                           radius=0.9,
                           text="configs[3]: incoherent ambient-occlusion rays, 16 random hemisphere directions per primary "
@@ -86,9 +94,14 @@ def ensure_scene(w, rank, barrier):
 
 
 def cameras(pysvo_or_none, w, count):
+    """(pitch, yaw, radius) of step k; both paths repeat after ORBIT = 100 distinct cameras."""
     out = []
     for k in range(count):
-        out.append((w["pitch"], w["yaw0"] + w["yaw_step"] * (k % ORBIT), w["radius"]))
+        j = k % ORBIT
+        if w.get("path") == "flythrough":       # SURVEY.md section 8d, C5
+            out.append((w["pitch"], 180.0 * j / (ORBIT - 1), 2.0 * (0.05 / 2.0) ** (j / (ORBIT - 1))))
+        else:
+            out.append((w["pitch"], w["yaw0"] + w["yaw_step"] * j, w["radius"]))
     return out
 
 
