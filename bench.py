@@ -41,11 +41,11 @@ WORKLOADS = {
                           text="configs[1] scene at 3840x2160"),
     "c1_dragon_720p": dict(scene=None, width=1280, height=720, pitch=0.0, yaw0=0.0, yaw_step=3.6, radius=1.0,
                            text="configs[0]: models/XYZRGB-Dragon.oct (256^3), 1280x720 primary rays, orbit radius 1"),
-    "c5_flythrough_ico8192": dict(scene="ico8192", width=3840, height=2160, path="flythrough", pitch=20.0, yaw0=0.0,
+    "c5_flythrough_ico8192": dict(scene="ico8192", width=3840, height=2160, camera_path="flythrough", pitch=20.0, yaw0=0.0,
                                   yaw_step=0.0, radius=2.0,
                                   text="configs[4]: camera fly-through, 100 frames, radius geometric 2.0 -> 0.05, yaw 0 -> 180 "
                                        "degrees, pitch 20, on the 8192^3 octree at 3840x2160"),
-    "c5_flythrough_sdf2048": dict(scene="sdf2048", width=3840, height=2160, path="flythrough", pitch=20.0, yaw0=0.0,
+    "c5_flythrough_sdf2048": dict(scene="sdf2048", width=3840, height=2160, camera_path="flythrough", pitch=20.0, yaw0=0.0,
                                   yaw_step=0.0, radius=2.0,
                                   text="configs[4] camera path (100 frames, radius 2.0 -> 0.05, yaw 0 -> 180, pitch 20) on "
                                        "the 2048^3 SDF scene at 3840x2160"),
@@ -98,7 +98,7 @@ def cameras(pysvo_or_none, w, count):
     out = []
     for k in range(count):
         j = k % ORBIT
-        if w.get("path") == "flythrough":
+        if w.get("camera_path") == "flythrough":
             out.append((w["pitch"], 180.0 * j / (ORBIT - 1), 2.0 * (0.05 / 2.0) ** (j / (ORBIT - 1))))
         else:
             out.append((w["pitch"], w["yaw0"] + w["yaw_step"] * j, w["radius"]))
