@@ -279,3 +279,53 @@ def test_frame_against_reference_object_code(pysvo, ref, gpu_dragon, dragon_word
     ref.tree_destroy(h)
     assert np.array_equal(depth.view(np.uint32), wdepth.view(np.uint32))
     assert np.array_equal(rgba, want)
+
+
+def test_cpp_facade_and_headless_driver(pysvo, port, gpu_dragon, dragon_words, tmp_path):
+    """The reference-signature C++ facade (host/VoxelOctree.hpp) and the SDL-free driver, built with g++ here."""
+    import subprocess
+    from conftest import DRAGON, ROOT
+    pkg = ROOT / "sparse-voxel-octrees_b200"
+    exe = tmp_path / "facade_test"
+    subprocess.check_call(["g++", "-std=c++17", "-O1", f"-I{ROOT / 'include'}", f"-I{pkg / 'host'}",
+                           str(ROOT / "tests" / "cpp" / "facade_test.cpp"), "-o", str(exe), f"-L{pkg}", "-lsvo_b200",
+                           f"-Wl,-rpath,{pkg}"])
+    saved = tmp_path / "saved.oct"
+    out = subprocess.run([str(exe), str(DRAGON), str(saved)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.splitlines()
+    words, center = dragon_words
+    assert lines[0].split()[:4] == ["center", "0.5", "0.2265625", "0.33203125"] and "words 119887 depth 8" in lines[0]
+    o = [float(center[0]) + 1.0, float(center[1]) + 1.0, float(center[2])]
+    dirs = [[0.0, 0.0, 1.0], [0.0, 1.0, 0.0], [0.05, -0.02, 1.0], [-0.3, 0.1, 1.0]]
+    scales = [0.0, 0.0, 0.05, 0.0]
+    for i in range(4):
+        code, t, n, _, _ = port.raymarch(words, o, dirs[i], scales[i], normal_sentinel=0xABCD1234, t_sentinel=-7.0)
+        want = f"ray {i} hit {1 if code else 0} normal {n:08x} tbits {int(np.float32(t).view(np.uint32)):08x}"
+        assert lines[1 + i] == want
+    assert lines[5] == "reload words 119887"
+    w2, _ = pysvo.oct_read(saved)
+    assert np.array_equal(w2, words)
+    rgba, _, st = gpu_dragon.render_frame(pysvo.orbit_camera(20.0, 135.0, 0.7), 160, 90, strips=4,
+                                          flavour=pysvo.FLAVOUR_VALIDATION)
+    fnv = 0
+    for v in rgba.reshape(-1):
+        fnv = (fnv * 1099511628211 + int(v)) & 0xFFFFFFFFFFFFFFFF
+    assert lines[6] == f"frame rays {st.rays} fnv {fnv:016x}"
+    assert lines[7] == "missing: threw"
+
+    # headless driver: PPM of frame 0 equals the library's frame
+    subprocess.check_call(["make", "-C", str(pkg), "headless"], stdout=subprocess.DEVNULL)
+    prefix = tmp_path / "hl"
+    out = subprocess.run([str(pkg / "svo_headless"), str(DRAGON), "--size", "320x180", "--strips", "4", "--frames", "2",
+                          "--validation", "--radius", "0.8", "--pitch", "10", "--yaw0", "30", "--out", str(prefix)],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    ppm = (tmp_path / "hl_0.ppm").read_bytes()
+    header, rest = ppm.split(b"255\n", 1)
+    assert header == b"P6\n320 180\n"
+    img = np.frombuffer(rest, np.uint8).reshape(180, 320, 3)
+    want, _, _ = gpu_dragon.render_frame(pysvo.orbit_camera(10.0, 30.0, 0.8), 320, 180, strips=4,
+                                         flavour=pysvo.FLAVOUR_VALIDATION)
+    assert np.array_equal(img[..., 0], (want & 0xFF).astype(np.uint8))
+    assert np.array_equal(img[..., 2], ((want >> 16) & 0xFF).astype(np.uint8))

@@ -217,3 +217,35 @@ if __name__ == "__main__" and len(sys.argv) > 5 and sys.argv[5] == "defer":
     print(f"single loop {t0 / rays:.1f}  eff {useful / t0:.3f}")
     for th in (1, 4, 8, 12, 16, 24):
         print("defer pops until", th, f"lanes: {scheme_deferred_pop(ops, counts, now, th) / rays:.1f}")
+
+
+if __name__ == "__main__" and len(sys.argv) > 5 and sys.argv[5] == "regroup":
+    ops, counts = trace(sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]))
+    rays = int((counts > 0).sum())
+    now = dict(H=15, V=8, P=27, A=15, Q=37, L=105, pro=150)
+    t0, useful, trips = scheme_single_loop(ops, counts, now)
+    print(f"8x4 halves: {t0 / rays:.1f} warp-instr/ray, eff {useful / t0:.3f}")
+    # oracle-knowledge regrouping of each tile's 64 rays into two warps (upper bounds on any predictor)
+    nt = ops.shape[0] // 2
+    o64 = ops[:2 * nt].reshape(nt, 64, -1)
+    c64 = counts[:2 * nt].reshape(nt, 64)
+    for name, key in (("by trip count", lambda o, c: c),
+                      ("by first divergence position", None),
+                      ("4x4 quads interleaved (checkerboard)", "quad")):
+        if key == "quad":
+            lane = np.arange(64)
+            x, y = lane % 8, lane // 8
+            order = np.argsort(((x // 4 + y // 4) % 2) * 64 + lane, kind="stable")
+            oo = o64[:, order]
+            cc = c64[:, order]
+        elif key is None:
+            # sort by the op string itself (lexicographic on the first 48 trips)
+            keys = [np.lexsort(o64[t, :, :48].T[::-1]) for t in range(nt)]
+            oo = np.stack([o64[t, keys[t]] for t in range(nt)])
+            cc = np.stack([c64[t, keys[t]] for t in range(nt)])
+        else:
+            idx = np.argsort(c64, axis=1, kind="stable")
+            oo = np.take_along_axis(o64, idx[:, :, None], axis=1)
+            cc = np.take_along_axis(c64, idx, axis=1)
+        t1, u1, _ = scheme_single_loop(oo.reshape(2 * nt, 32, -1), cc.reshape(2 * nt, 32), now)
+        print(f"{name}: {t1 / rays:.1f} warp-instr/ray ({t0 / t1:.3f}x), eff {u1 / t1:.3f}")
