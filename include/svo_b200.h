@@ -219,7 +219,7 @@ SVO_API int svo_frame_tile_owner(int width, int height, int strips, int tile, in
  * constants, renders, copies the frame back and synchronises. Pass memory from
  * svo_host_alloc for full-speed copies. With tile_world > 1 pixels of tiles
  * owned by other ranks are returned as they were in the internal buffer
- * (zero on a fresh handle). */
+ * (zero on a fresh handle) and only this rank's corners of `depth` are valid. */
 SVO_API int svo_render_frame(svo_tree *tree, const svo_camera *cam, const svo_frame_desc *desc,
                              uint32_t *rgba, float *depth, svo_frame_stats *stats);
 /* Pipelined host-buffer variant: enqueues the frame and its device->host copies and returns at
@@ -235,12 +235,15 @@ SVO_API int svo_frame_wait(svo_tree *tree, const svo_frame_desc *desc, int ticke
  * write -- local HBM or a peer GPU's framebuffer mapped with svo_ipc_open, in
  * which case finished tiles travel over NVLink as the kernel stores them.
  * Asynchronous: the tile classifier and the fine pass run on `stream`; the beam
- * pass runs on the tree's internal high-priority stream (it only touches
- * internal buffers) and `stream` waits for it, so consecutive calls overlap the
- * beam pass of frame i+1 with the fine pass of frame i. If d_depth is given
- * (device pointer, receives the coarse depth buffer) the beam pass runs on
- * `stream` too. `stats` (optional, host) is filled only when `sync_stats` != 0,
- * which synchronises the stream. */
+ * pass runs on one of the tree's two internal high-priority streams (it only
+ * touches internal buffers, a ring of four frames deep) and `stream` waits for
+ * it, so consecutive calls overlap the beam passes of the next frames with the
+ * fine pass of the current one. Frames issued on different streams into
+ * different framebuffers may overlap entirely (bench.py alternates two). If
+ * d_depth is given (device pointer, receives the coarse depth buffer; with
+ * tile_world > 1 only the corners this rank needs are written) the beam pass
+ * runs on `stream` too. `stats` (optional, host) is filled only when
+ * `sync_stats` != 0, which synchronises the stream. */
 SVO_API int svo_render_frame_device(svo_tree *tree, const svo_camera *cam, const svo_frame_desc *desc,
                                     uint32_t *d_rgba, float *d_depth, void *stream,
                                     svo_frame_stats *stats, int sync_stats);

@@ -249,3 +249,52 @@ if __name__ == "__main__" and len(sys.argv) > 5 and sys.argv[5] == "regroup":
             cc = np.take_along_axis(c64, idx, axis=1)
         t1, u1, _ = scheme_single_loop(oo.reshape(2 * nt, 32, -1), cc.reshape(2 * nt, 32), now)
         print(f"{name}: {t1 / rays:.1f} warp-instr/ray ({t0 / t1:.3f}x), eff {u1 / t1:.3f}")
+
+
+def scheme_refill(ops, counts, c, batch):
+    """One warp per tile (64 rays): lanes whose ray ended wait until `batch` lanes are free (or no ray is
+    running), then set up the next rays of the tile together (cost pro) -- bounded lane re-fill."""
+    total = 0.0
+    nt = ops.shape[0] // 2
+    for t in range(nt):
+        o = ops[2 * t:2 * t + 2].reshape(64, -1)
+        n = counts[2 * t:2 * t + 2].reshape(64).astype(np.int64)
+        if n.max() == 0:
+            continue
+        queue = list(np.nonzero(n > 0)[0])
+        lane_ray = -np.ones(32, np.int64)
+        pos = np.zeros(32, np.int64)
+        while True:
+            free = np.nonzero(lane_ray < 0)[0]
+            running = lane_ray >= 0
+            if queue and (len(free) >= batch or not running.any()):
+                total += c['pro']
+                for ln in free:
+                    if not queue:
+                        break
+                    lane_ray[ln] = queue.pop(0)
+                    pos[ln] = 0
+                running = lane_ray >= 0
+            if not running.any():
+                break
+            lr = np.where(running, lane_ray, 0)
+            cur = np.where(running, o[lr, np.minimum(pos, n[lr] - 1)], 0)
+            isP, isL = running & (cur == P), running & (cur == Lf)
+            isA = running & ((cur == A) | (cur == Q) | (cur == X))
+            isQ = running & ((cur == Q) | (cur == X))
+            total += c['H'] + (c['V'] if (isP | isL).any() else 0) + (c['P'] if isP.any() else 0) \
+                + (c['L'] if isL.any() else 0) + (c['A'] if isA.any() else 0) + (c['Q'] if isQ.any() else 0)
+            pos = pos + running
+            done = running & (pos >= n[lr])
+            lane_ray[done] = -1
+    return total
+
+
+if __name__ == "__main__" and len(sys.argv) > 5 and sys.argv[5] == "refill":
+    ops, counts = trace(sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]))
+    rays = int((counts > 0).sum())
+    now = dict(H=15, V=8, P=27, A=15, Q=37, L=105, pro=150)
+    t0, useful, trips = scheme_single_loop(ops, counts, now)
+    print(f"two warps per tile, no refill: {t0 / rays:.1f} warp-instr/ray")
+    for b in (1, 4, 8, 16, 32):
+        print(f"one warp per tile, refill when {b} lanes free: {scheme_refill(ops, counts, now, b) / rays:.1f}")
