@@ -71,16 +71,23 @@ coarsePassKernel(const uint32_t *__restrict__ octree, FramePlanDev plan, FrameCo
         counters->tilesRendered = 0;
         counters->fineRays = 0;
     }
-    if (k >= totalSlots) return;
-
-    int row = k/colSlots;                 // corner row over all strips
-    int j = k - row*colSlots;
+    // A warp takes an 8 x 4 block of this rank's corner grid (column slots x corner rows of one
+    // strip) rather than 32 corners of one row: neighbouring beams walk the same nodes.
+    const int lane = threadIdx.x & 31;
+    const int warp = k >> 5;
+    const int groupsX = (colSlots + 7) >> 3;
+    const int groupsPerStrip = groupsX*((plan.tilesYFull + 3) >> 2);
+    const int strip = warp/groupsPerStrip;
+    if (strip >= plan.nStrips) return;
+    const int g = warp - strip*groupsPerStrip;
+    const int gy = g/groupsX;
+    const int j = (g - gy*groupsX)*8 + (lane & 7);
+    const int y = gy*4 + (lane >> 3);
+    if (j >= colSlots || y >= (strip == plan.nStrips - 1 ? plan.tilesYLast : plan.tilesYFull)) return;
     // slot j -> corner column: run q = j / (run + 1) of this rank starts at tile column (q*world + rank)*run
     int q = j/(tileRun + 1);
     int x = tileWorld == 1 ? j : (q*tileWorld + tileRank)*tileRun + (j - q*(tileRun + 1));
     if (x >= plan.tilesX) return;
-    int strip = min(row/plan.tilesYFull, plan.nStrips - 1);
-    int y = row - strip*plan.tilesYFull;
     int i = strip*plan.tilesX*plan.tilesYFull + y*plan.tilesX + x;
 
     float dx = __ldg(plan.dxCoarse + x);
@@ -269,8 +276,8 @@ cudaError_t launchCoarseT(const TreeDev &tree, const FramePlanDev &plan, const F
     int run = tileRunLength(tileWorld);
     int runsOwned = (plan.tileCols + tileWorld*run - 1)/(tileWorld*run);
     int colSlots = tileWorld == 1 ? plan.tilesX : runsOwned*(run + 1);
-    int cornerRows = (plan.nStrips - 1)*plan.tilesYFull + plan.tilesYLast;
-    int totalSlots = colSlots*cornerRows;
+    int groupsPerStrip = ((colSlots + 7)/8)*((plan.tilesYFull + 3)/4);      // 8 x 4 corners per warp
+    int totalSlots = groupsPerStrip*plan.nStrips*32;
     int blocks = (totalSlots + kCoarseThreads - 1)/kCoarseThreads;
     kernel<<<blocks, kCoarseThreads, smem, stream>>>(tree.words, plan, consts, depth, counters, tileRank, tileWorld,
                                                      run, colSlots, totalSlots);
