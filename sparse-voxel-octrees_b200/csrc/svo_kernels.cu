@@ -168,7 +168,7 @@ classifyTilesKernel(FramePlanDev plan, float beamBias, const float *__restrict__
 // ---- K3 -------------------------------------------------------------------
 
 template <bool FAST, typename IdxT>
-__global__ void __launch_bounds__(kTileThreads)
+__global__ void __launch_bounds__(kTileThreads, 32)
 finePassKernel(const uint32_t *__restrict__ octree, FramePlanDev plan, FrameConsts f,
                const TileRecord *__restrict__ tiles, const FrameCounters *__restrict__ counters,
                uint32_t *__restrict__ rgba) {
