@@ -344,8 +344,8 @@ def run_own_ao(args, w):
     # end to end: host rays in, host results out, every step (pinned buffers, chunked double-buffered copies)
     ho, hd = pysvo.PinnedArray((n, 3), np.float32), pysvo.PinnedArray((n, 3), np.float32)
     ho.array[:], hd.array[:] = ao_o, ao_d
-    out = dict(hit=pysvo.PinnedArray(n, np.uint8).array, t=pysvo.PinnedArray(n, np.float32).array,
-               normal=pysvo.PinnedArray(n, np.uint32).array, voxel=None)
+    pinned_out = [pysvo.PinnedArray(n, np.uint8), pysvo.PinnedArray(n, np.float32), pysvo.PinnedArray(n, np.uint32)]
+    out = dict(hit=pinned_out[0].array, t=pinned_out[1].array, normal=pinned_out[2].array, voxel=None)
     e2e_steps = min(steps, 5)
     tree.raymarch_batch(ho.array, hd.array, 0.0, flavour, out=out)
     if dist:

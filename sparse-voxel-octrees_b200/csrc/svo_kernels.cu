@@ -26,7 +26,7 @@ constexpr int kClassifyThreads = 128;
 // ---- K1 -------------------------------------------------------------------
 
 template <bool FAST, bool LOD, typename IdxT>
-__global__ void __launch_bounds__(kBatchThreads)
+__global__ void __launch_bounds__(kBatchThreads, 16)
 raymarchBatchKernel(const uint32_t *__restrict__ octree, uint64_t n, const float *__restrict__ o,
                     const float *__restrict__ d, float rayScale, uint8_t *__restrict__ hit,
                     float *__restrict__ t, uint32_t *__restrict__ normal, uint64_t *__restrict__ voxel) {
