@@ -534,7 +534,7 @@ def run_own(args):
         with torch.cuda.stream(lanes[slot]):
             tree.render_frame_device(cams[k % ORBIT], W, H, fb_ptrs[slot], strips=STRIPS, flavour=flavour,
                                      tile_rank=rank, tile_world=world, stream=lanes[slot].cuda_stream)
-            if world > 1:
+            if world > 1 and not os.environ.get("SVO_BENCH_NO_BARRIER"):   # (experiment switch, never set by default)
                 done = torch.cuda.Event()
                 done.record(lanes[slot])
                 comm.wait_event(done)

@@ -572,6 +572,17 @@ int64_t svo_oracle_trace_fine_warps(const uint32_t *octree, const svo_oracle_fra
     return nWarps;
 }
 
+/* Kernel design tool: loop-trip traces of arbitrary rays (batch mode). ops: [n][maxOps], counts: [n]. */
+void svo_oracle_trace_rays(const uint32_t *octree, uint64_t n, const float *o, const float *d, float rayScale,
+        uint8_t *ops, uint32_t maxOps, uint32_t *counts) {
+    for (uint64_t i = 0; i < n; ++i) {
+        uint32_t material = 0, cnt = 0;
+        float t = 0.0f;
+        raymarchImpl(octree, o + 3*i, d + 3*i, rayScale, &material, &t, NULL, NULL, ops + i*maxOps, maxOps, &cnt);
+        counts[i] = cnt < maxOps ? cnt : maxOps;
+    }
+}
+
 /* ---- tree walk (App. A.1) --------------------------------------------------- */
 
 static int walkNode(const uint32_t *oct, uint64_t words, uint64_t p, uint32_t level, svo_oracle_tree_stats *st) {

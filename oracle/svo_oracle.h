@@ -93,6 +93,9 @@ int svo_oracle_render_frame(const uint32_t *octree, const svo_oracle_frame *f, u
 int64_t svo_oracle_trace_fine_warps(const uint32_t *octree, const svo_oracle_frame *f, int tileStride,
         uint8_t *ops, uint32_t maxOps, uint32_t *counts, int64_t maxWarps);
 
+void svo_oracle_trace_rays(const uint32_t *octree, uint64_t n, const float *o, const float *d, float rayScale,
+        uint8_t *ops, uint32_t maxOps, uint32_t *counts);
+
 /* Tree statistics by a full walk from the root (App. A.1). */
 typedef struct {
     uint64_t descriptors, leaves, far_words, far_blocks;
