@@ -217,8 +217,12 @@ enum : int { kMiss = 0, kHitLeaf = 1, kHitLod = 2 };
 
 // reference src/VoxelOctree.cpp:207-346. Returns kMiss / kHitLeaf / kHitLod.
 //   tOut      written on a hit only
-//   normalOut written on a leaf hit only
-//   voxelOut  leaf word index, or parent | childShift << 60 for LOD exits
+//   voxelOut  leaf word index (the caller fetches the material word octree[voxelOut], :282, AFTER the
+//             warp has reconverged), or parent | childShift << 60 for LOD exits
+// The loop has ONE exit: every way out records its result and breaks, and a warp barrier follows the
+// loop. Without it the compiler threads whatever the caller does with a hit (material fetch + ~100
+// instructions of shading) into the leaf branch inside the loop, where it runs once per distinct exit
+// trip of the warp (8-10 times per warp, with 3 lanes active) instead of once with all lanes.
 // LOD == false elides the rayScale test (rayScale == 0 can never pass it:
 // maxTC*0 is +-0 or NaN, scaleExp2 > 0).
 //
@@ -229,7 +233,7 @@ template <bool FAST, bool LOD, typename IdxT, int THREADS>
 __device__ __forceinline__ int raymarch(const uint32_t *__restrict__ octree, float ox, float oy, float oz,
                                         float dx, float dy, float dz, float rayScale,
                                         const SmemStack<IdxT, THREADS> &stack,
-                                        float &tOut, uint32_t &normalOut, uint64_t &voxelOut) {
+                                        float &tOut, uint64_t &voxelOut) {
     typedef Arith<FAST> A;
     typedef SmemStack<IdxT, THREADS> Stack;
 
@@ -283,6 +287,7 @@ __device__ __forceinline__ int raymarch(const uint32_t *__restrict__ octree, flo
     } while (0)
     SVO_FETCH_NODE();
 
+    int code = kMiss;
     for (;;) {
         const float cornerTX = A::mulsub(posX, dTx, bTx);   // :256-259
         const float cornerTY = A::mulsub(posY, dTy, bTy);
@@ -295,7 +300,8 @@ __device__ __forceinline__ int raymarch(const uint32_t *__restrict__ octree, flo
             if (LOD && mulRn(maxTC, rayScale) >= scaleExp2) {   // :265-268
                 tOut = maxTC;
                 voxelOut = uint64_t(parent) | (uint64_t(childShift) << 60);
-                return kHitLod;
+                code = kHitLod;
+                break;
             }
 
             const float maxTV = fminf(maxT, maxTC);
@@ -310,10 +316,10 @@ __device__ __forceinline__ int raymarch(const uint32_t *__restrict__ octree, flo
 
                 if (!(childMasks & 0x80u)) {                   // leaf, :281-285
                     IdxT leaf = childOffset + parent + IdxT(__popc(((childMasks >> (8 + childShift)) << childShift) & 127u));
-                    normalOut = ldNode(octree + leaf);
                     voxelOut = uint64_t(leaf);
                     tOut = minT;
-                    return kHitLeaf;
+                    code = kHitLeaf;
+                    break;
                 }
 
                 Stack::store(stack.slot(scale), parent, maxT);  // :287-288
@@ -361,7 +367,7 @@ __device__ __forceinline__ int raymarch(const uint32_t *__restrict__ octree, flo
             // reference: exponent of (float)differingBits. differingBits < 2^24
             // always (positions stay in [0.5, 2)), so that is the index of the
             // highest set bit; bit 23 set <=> the ray left the root (:341-342)
-            if (differingBits > 0x7FFFFFu) return kMiss;
+            if (differingBits > 0x7FFFFFu) break;
             scale = 31 - __clz(int(differingBits));
             scaleExp2 = __uint_as_float(uint32_t(scale - kMaxScale + 127) << 23);
 
@@ -381,6 +387,8 @@ __device__ __forceinline__ int raymarch(const uint32_t *__restrict__ octree, flo
         }
     }
 #undef SVO_FETCH_NODE
+    __syncwarp();   // exited lanes do not take part; see the note on the single exit above
+    return code;
 }
 
 } // namespace svo
