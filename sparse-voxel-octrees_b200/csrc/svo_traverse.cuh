@@ -359,7 +359,8 @@ __device__ __forceinline__ int raymarch(const uint32_t *__restrict__ octree, flo
 
         if (((childShift ^ octantMask) & stepMask) != 0) {      // (idx & stepMask) != 0, :318-338
             // pos ^ (pos + scaleExp2) over the stepped axes (:320-322); an axis that did not step adds
-            // 0*scaleExp2 and contributes nothing
+            // 0*scaleExp2 and contributes nothing. (Keeping the pre-step positions instead costs three
+            // register moves on EVERY trip: ptxas copies them at the loop head.)
             const uint32_t differingBits =
                 (__float_as_uint(posX) ^ __float_as_uint(moveIf<FAST>(stX, scaleExp2, posX))) |
                 (__float_as_uint(posY) ^ __float_as_uint(moveIf<FAST>(stY, scaleExp2, posY))) |
@@ -378,12 +379,15 @@ __device__ __forceinline__ int raymarch(const uint32_t *__restrict__ octree, flo
             // round-toward-zero leaves exactly the mantissa bits >= `scale` (positions are in [1, 2), the
             // sum is in [2^scale, 2^(scale+1))), its lowest mantissa bit is the new idx bit, and
             // subtracting 2^scale again is exact.
-            const float big = mulRn(scaleExp2, 8388608.0f);
+            const float big = __uint_as_float(uint32_t(scale + 127) << 23);
             const float tX = __fadd_rz(posX, big), tY = __fadd_rz(posY, big), tZ = __fadd_rz(posZ, big);
             posX = subRn(tX, big);
             posY = subRn(tY, big);
             posZ = subRn(tZ, big);
-            childShift = ((__float_as_uint(tX) & 1u) | ((__float_as_uint(tY) & 1u) << 1) | ((__float_as_uint(tZ) & 1u) << 2)) ^ octantMask;
+            // idx = bit 0 of tX | bit 0 of tY << 1 | bit 0 of tZ << 2, by two bit-selects
+            const uint32_t xy = (__float_as_uint(tX) & 1u) | ((__float_as_uint(tY) << 1) & ~1u);
+            const uint32_t xyz = (xy & 3u) | ((__float_as_uint(tZ) << 2) & ~3u);
+            childShift = (xyz ^ octantMask) & 7u;
         }
     }
 #undef SVO_FETCH_NODE
