@@ -185,14 +185,10 @@ int measureDepth(const uint32_t *words, uint64_t nWords, uint32_t &depthOut) {
     return SVO_OK;
 }
 
-int createTree(const uint32_t *words, uint64_t nWords, const float center[3], int device, svo_tree **out) {
-    if (!words || !center || !out) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_tree_create: null argument");
+// Device, node-array allocation (+1 zeroed padding word: the traversal reads words[p + 1] next to
+// every descriptor) and streams; the node array itself is filled by the caller.
+int allocTree(uint64_t nWords, const float center[3], int device, std::unique_ptr<svo_tree> &treeOut) {
     if (nWords < 2) return fail(SVO_ERR_FORMAT, "node array too small (%llu words)", (unsigned long long)nWords);
-    *out = nullptr;
-    uint32_t depth = 0;
-    int st = measureDepth(words, nWords, depth);
-    if (st != SVO_OK) return st;
-
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0)
@@ -205,10 +201,8 @@ int createTree(const uint32_t *words, uint64_t nWords, const float center[3], in
     if (!tree) return fail(SVO_ERR_OUT_OF_MEMORY, "out of host memory");
     tree->device = device;
     tree->nWords = nWords;
-    tree->depth = depth;
     memcpy(tree->center, center, sizeof(float)*3);
 
-    // +1 padding word: the traversal reads words[p + 1] next to every descriptor
     size_t bytes = size_t(nWords + 1)*sizeof(uint32_t);
     auto cleanup = [&](cudaError_t err, const char *what) {
         if (tree->dWords) cudaFree(tree->dWords);
@@ -219,8 +213,6 @@ int createTree(const uint32_t *words, uint64_t nWords, const float center[3], in
         return failCuda(err, what);
     };
     if ((e = cudaMalloc(&tree->dWords, bytes)) != cudaSuccess) return cleanup(e, "cudaMalloc(node array)");
-    if ((e = cudaMemcpy(tree->dWords, words, size_t(nWords)*sizeof(uint32_t), cudaMemcpyHostToDevice)) != cudaSuccess)
-        return cleanup(e, "cudaMemcpy(node array)");
     if ((e = cudaMemset(tree->dWords + nWords, 0, sizeof(uint32_t))) != cudaSuccess) return cleanup(e, "cudaMemset(padding)");
     int prioLow = 0, prioHigh = 0;
     if ((e = cudaDeviceGetStreamPriorityRange(&prioLow, &prioHigh)) != cudaSuccess) return cleanup(e, "cudaDeviceGetStreamPriorityRange");
@@ -230,6 +222,26 @@ int createTree(const uint32_t *words, uint64_t nWords, const float center[3], in
         if ((e = cudaStreamCreateWithPriority(&tree->coarseStream[i], cudaStreamNonBlocking, prioHigh)) != cudaSuccess)
             return cleanup(e, "cudaStreamCreate(coarse)");
     if ((e = cudaStreamCreateWithFlags(&tree->copyStream, cudaStreamNonBlocking)) != cudaSuccess) return cleanup(e, "cudaStreamCreate(copy)");
+    treeOut = std::move(tree);
+    return SVO_OK;
+}
+
+int createTree(const uint32_t *words, uint64_t nWords, const float center[3], int device, svo_tree **out) {
+    if (!words || !center || !out) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_tree_create: null argument");
+    if (nWords < 2) return fail(SVO_ERR_FORMAT, "node array too small (%llu words)", (unsigned long long)nWords);
+    *out = nullptr;
+    uint32_t depth = 0;
+    int st = measureDepth(words, nWords, depth);
+    if (st != SVO_OK) return st;
+    std::unique_ptr<svo_tree> tree;
+    if ((st = allocTree(nWords, center, device, tree)) != SVO_OK) return st;
+    tree->depth = depth;
+    SVO_DEVICE(device);
+    cudaError_t e = cudaMemcpy(tree->dWords, words, size_t(nWords)*sizeof(uint32_t), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        svo_tree_destroy(tree.release());
+        return failCuda(e, "cudaMemcpy(node array)");
+    }
     *out = tree.release();
     return SVO_OK;
 }
@@ -477,16 +489,50 @@ int svo_tree_create_from_words(const uint32_t *words, uint64_t n_words, const fl
     return createTree(words, n_words, center, device, out);
 }
 
+// Decode and upload are pipelined: the reader's worker threads decode the
+// 64 MiB LZ4 slices while this thread copies every finished slice to the device, in file order.
 int svo_tree_load_oct(const char *path, int device, svo_tree **out) {
     if (!path || !out) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_tree_load_oct: null argument");
     *out = nullptr;
-    svo::OctFile f;
+    svo::OctReader reader;
     std::string err;
     int status = 0;
-    if (!svo::readOctFile(path, f, err, status)) return fail(status, "%s", err.c_str());
-    int st = createTree(f.words, f.nWords, f.center, device, out);
-    free(f.words);
-    return st;
+    if (!reader.open(path, err, status)) return fail(status, "%s", err.c_str());
+    std::unique_ptr<svo_tree> tree;
+    int st = allocTree(reader.nWords, reader.center, device, tree);
+    if (st != SVO_OK) return st;
+    SVO_DEVICE(device);
+    uint32_t *words = svo::allocNodeArray(reader.nWords);
+    if (!words) {
+        svo_tree_destroy(tree.release());
+        return fail(SVO_ERR_OUT_OF_MEMORY, "out of host memory for the node array");
+    }
+    cudaError_t copyErr = cudaSuccess;
+    auto upload = [&](uint64_t firstWord, uint64_t wordCount) {
+        copyErr = cudaMemcpyAsync(tree->dWords + firstWord, words + firstWord, size_t(wordCount)*sizeof(uint32_t),
+                                  cudaMemcpyHostToDevice, tree->copyStream);
+        return copyErr == cudaSuccess;
+    };
+    bool ok = reader.decode(words, upload, err, status);
+    if (copyErr == cudaSuccess) copyErr = cudaStreamSynchronize(tree->copyStream);
+    uint32_t depth = 0;
+    if (ok && copyErr == cudaSuccess) st = measureDepth(words, reader.nWords, depth);
+    free(words);
+    if (copyErr != cudaSuccess) {
+        svo_tree_destroy(tree.release());
+        return failCuda(copyErr, "cudaMemcpyAsync(node array slice)");
+    }
+    if (!ok) {
+        svo_tree_destroy(tree.release());
+        return fail(status, "%s", err.c_str());
+    }
+    if (st != SVO_OK) {
+        svo_tree_destroy(tree.release());
+        return st;
+    }
+    tree->depth = depth;
+    *out = tree.release();
+    return SVO_OK;
 }
 
 int svo_tree_download_words(const svo_tree *tree, uint32_t *words_out, uint64_t n_words) {

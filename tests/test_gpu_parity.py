@@ -267,6 +267,34 @@ def test_save_oct_roundtrip_from_hbm(pysvo, gpu_dragon, dragon_words, tmp_path):
     assert np.array_equal(w2, words) and np.array_equal(c2, center)
 
 
+def test_load_oct_pipelined_multi_slice(pysvo, tmp_path, monkeypatch):
+    """svo_tree_load_oct uploads slice k while slices k+1.. are still being decoded (row f1): the words in
+    HBM must be the file's words for chained (literal-only here: trivially independent) and compressed
+    slices and any thread count, and a file broken in a late slice must not leave a tree behind."""
+    n_words = 2 * (64 << 20) // 4 + 4321
+    rng = np.random.default_rng(3)
+    words = np.repeat(rng.integers(0, 2**32, n_words // 8 + 1, dtype=np.uint64).astype(np.uint32), 8)[:n_words].copy()
+    words[rng.integers(0, n_words, n_words // 7)] = 0xDEADBEEF
+    words[0] = (1 << 18) | 0x0100          # root with one leaf child: passes the node-array checks
+    center = np.array([0.5, 0.25, 0.5], np.float32)
+    for compress in (True, False):
+        p = tmp_path / f"multi_{int(compress)}.oct"
+        pysvo.oct_write(p, words, center, compress=compress)
+        for threads in ("1", "3"):
+            monkeypatch.setenv("SVO_IO_THREADS", threads)
+            tree = pysvo.VoxelOctree(p)
+            assert tree.n_words == n_words and tree.depth == 1
+            assert np.array_equal(tree.words(), words)
+            tree.close()
+    raw = bytearray(p.read_bytes())
+    raw = raw[:len(raw) - 1000]
+    bad = tmp_path / "short.oct"
+    bad.write_bytes(bytes(raw))
+    with pytest.raises(pysvo.SvoError) as e:
+        pysvo.VoxelOctree(bad)
+    assert e.value.status == 3
+
+
 def test_frame_against_reference_object_code(pysvo, ref, gpu_dragon, dragon_words):
     """Straight against oracle/_ref (travels to the GPU box prebuilt), a camera outside the golden set."""
     words, center = dragon_words

@@ -107,6 +107,56 @@ def test_oct_multi_slice_interop_with_reference(pysvo, ref, tmp_path):
     assert np.array_equal(w2, words)
 
 
+def test_oct_parallel_decode(pysvo, ref, tmp_path, monkeypatch):
+    """Row f1: slices decode concurrently. Files this library writes have independent slices (workers never
+    block); files the reference writes chain through LZ4's streaming window (a worker blocks at its first
+    cross-slice match until the predecessor is done). Both must give the same words for any thread count,
+    and a broken slice must surface as a format error, not a hang."""
+    n_words = 3 * (64 << 20) // 4 + 7777
+    rng = np.random.default_rng(11)
+    words = _synthetic_words(rng, n_words)
+    for k in (1, 2, 3):   # the start of every later slice repeats the end of its predecessor
+        b = k * (64 << 20) // 4
+        words[b:b + 3000] = words[b - 3000:b]
+    center = np.array([0.5, 0.5, 0.25], np.float32)
+    ours = tmp_path / "ours.oct"
+    monkeypatch.setenv("SVO_IO_THREADS", "4")
+    pysvo.oct_write(ours, words, center, compress=True)
+    h = ref.tree_load(ours)                       # the reference reads what the threaded writer wrote
+    assert np.array_equal(ref.tree_words_view(h), words)
+    theirs = tmp_path / "theirs.oct"
+    ref.tree_save(h, theirs)                      # ... and writes a file with cross-slice matches
+    ref.tree_destroy(h)
+    for threads in ("1", "2", "4", "7"):
+        monkeypatch.setenv("SVO_IO_THREADS", threads)
+        for path in (ours, theirs):
+            w2, c2 = pysvo.oct_read(path)
+            assert np.array_equal(w2, words) and np.array_equal(c2, center), (threads, path.name)
+    # single-threaded writer produces the same bytes as the threaded one
+    monkeypatch.setenv("SVO_IO_THREADS", "1")
+    again = tmp_path / "again.oct"
+    pysvo.oct_write(again, words, center, compress=True)
+    assert again.read_bytes() == ours.read_bytes()
+    # damage the second slice of each file: every thread count reports it
+    for path in (ours, theirs):
+        raw = bytearray(path.read_bytes())
+        first = struct.unpack_from("<Q", raw, 20)[0]
+        second_payload = 28 + first + 8
+        raw[second_payload + 100:second_payload + 100 + 64] = bytes(64)   # zero offsets are invalid
+        bad = tmp_path / ("bad_" + path.name)
+        bad.write_bytes(bytes(raw))
+        for threads in ("1", "4"):
+            monkeypatch.setenv("SVO_IO_THREADS", threads)
+            with pytest.raises(pysvo.SvoError) as e:
+                pysvo.oct_read(bad)
+            assert e.value.status == 3
+        trunc = tmp_path / ("trunc_" + path.name)
+        trunc.write_bytes(bytes(path.read_bytes()[:second_payload + 1000]))
+        with pytest.raises(pysvo.SvoError) as e:
+            pysvo.oct_read(trunc)
+        assert e.value.status == 3
+
+
 def test_oct_errors_are_reported(pysvo, tmp_path, dragon_words):
     with pytest.raises(pysvo.SvoError) as e:
         pysvo.oct_read(tmp_path / "missing.oct")
