@@ -119,6 +119,36 @@ SVO_API int svo_tree_get_info(const svo_tree *tree, svo_tree_info *out);
 SVO_API int svo_tree_download_words(const svo_tree *tree, uint32_t *words_out, uint64_t n_words);
 SVO_API int svo_tree_destroy(svo_tree *tree);
 
+/* ---- construction on the GPU -------------------- *
+ * Replace VoxelOctree(VoxelData *voxels) / buildOctree (VoxelOctree.cpp:125-205): the node array is
+ * built in HBM, word for word the array the reference builds from the same voxels, and stays there.
+ * A voxel is filled iff its uint32 material word is non-zero (VoxelData.hpp:106-138). As in the
+ * reference, the last z-plane of an odd-depth volume is not seen (VoxelData.cpp:160-163). */
+
+/* Dense grid in host memory, w*h*d words, x fastest: the payload of a raw .voxel file. */
+SVO_API int svo_tree_build_from_voxels(const uint32_t *voxels, int w, int h, int d, int device, svo_tree **out);
+/* VoxelData(const char *path, size_t mem) + VoxelOctree(VoxelData*), Main.cpp:318-319: raw .voxel file
+ * (int32 w, h, d, then the grid; VoxelData.cpp:36-48, 183-201), streamed; no memory budget argument. */
+SVO_API int svo_tree_build_from_voxel_file(const char *path, int device, svo_tree **out);
+/* The same volume given as n filled voxels: xyz = n (x, y, z) triples, values = n material words, both in
+ * host memory. Zero words and coordinates outside w x h x d are ignored; a coordinate named twice is an
+ * error. For volumes whose dense form does not fit anywhere (8192^3 = 2 TiB). */
+SVO_API int svo_tree_build_from_sparse(const uint32_t *xyz, const uint32_t *values, uint64_t n, int w, int h, int d,
+                                       int device, svo_tree **out);
+
+typedef struct svo_build_stats {
+    uint64_t voxels;            /* filled voxels in the tree */
+    uint64_t nodes;             /* descriptors */
+    uint64_t far_blocks;        /* child blocks with far words (VoxelOctree.cpp:182-193) */
+    uint64_t words;             /* node array length */
+    float gather_ms;            /* device time: voxels -> (Morton key, material) list */
+    float sort_ms;
+    float levels_ms;            /* bottom-up sweep */
+    float emit_ms;              /* top-down sweep */
+} svo_build_stats;
+/* Statistics of the calling thread's last successful svo_tree_build_* call. */
+SVO_API int svo_build_last_stats(svo_build_stats *out);
+
 /* ---- traversal: VoxelOctree::raymarch (VoxelOctree.cpp:207-346), batched ---- *
  * Ray i: origin o[3i..3i+2], direction d[3i..3i+2] (need not be unit; the
  * octree occupies [1,2]^3), common rayScale. Outputs (any may be NULL):

@@ -308,6 +308,10 @@ class Port:
                                               C.POINTER(Counters), C.c_int]
         L.svo_oracle_tree_walk.restype = C.c_int
         L.svo_oracle_tree_walk.argtypes = [_u32p, C.c_uint64, C.POINTER(TreeStats)]
+        L.svo_oracle_build_octree.restype = C.POINTER(C.c_uint32)
+        L.svo_oracle_build_octree.argtypes = [_u32p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64), _f32p]
+        L.svo_oracle_free.restype = None
+        L.svo_oracle_free.argtypes = [C.c_void_p]
 
     def raymarch(self, words, o, d, ray_scale=0.0, normal_sentinel=0xDEADBEEF, t_sentinel=-1.0):
         n = C.c_uint32(normal_sentinel)
@@ -376,6 +380,18 @@ class Port:
 
     def inv_sqrt(self, x):
         return np.float32(self.lib.svo_oracle_inv_sqrt(float(x)))
+
+    def build_octree(self, voxels):
+        """Row f2. voxels: uint32[D, H, W] (x fastest, 0 = empty) -> (words, center), VoxelOctree.cpp:125-205."""
+        voxels = np.ascontiguousarray(voxels, np.uint32)
+        d, h, w = voxels.shape
+        n = C.c_uint64(0)
+        center = np.zeros(3, np.float32)
+        ptr = self.lib.svo_oracle_build_octree(voxels.reshape(-1), w, h, d, C.byref(n), center)
+        try:
+            return np.ctypeslib.as_array(ptr, shape=(n.value,)).copy(), center
+        finally:
+            self.lib.svo_oracle_free(ptr)
 
     def tree_walk(self, words):
         st = TreeStats()

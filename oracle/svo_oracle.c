@@ -622,3 +622,154 @@ int svo_oracle_tree_walk(const uint32_t *octree, uint64_t words, svo_oracle_tree
     if (words == 0) return -1;
     return walkNode(octree, words, 0, 0, out);
 }
+
+/* ---- octree construction (row f2) --------------------------------------------
+ * Restatement of VoxelOctree::VoxelOctree(VoxelData*) / buildOctree (reference
+ * src/VoxelOctree.cpp:125-205) over a dense in-memory grid, with the voxel source
+ * reduced to what buildOctree observes of VoxelData (src/VoxelData.hpp:106-138,
+ * src/VoxelData.cpp:158-175): a cube "contains voxels" iff the occupancy pyramid
+ * says so, and the pyramid's finest level is filled from z-planes
+ * [0, (depth/2)*2) only (buildLowLut's thread partition, VoxelData.cpp:160-163),
+ * so the last plane of an odd-depth volume is invisible. ChunkedAllocator's
+ * deferred insert()/finalize() (src/ChunkedAllocator.hpp:73-116) is restated as
+ * an insertion list merged at the end.                                           */
+
+typedef struct {
+    uint32_t *data; uint64_t size, cap;
+    uint64_t *insIdx; uint32_t *insVal; uint64_t insCount, insCap;
+    const uint32_t *vox; int w, h, d;
+    uint8_t **lut; int levels;          /* lut[k]: occupancy of cubes of edge 2^k, (side >> k)^3 cells */
+    int side;
+} builder;
+
+static void bPush(builder *b, uint32_t v) {
+    if (b->size == b->cap) { b->cap = b->cap ? b->cap*2 : 4096; b->data = (uint32_t *)realloc(b->data, b->cap*sizeof(uint32_t)); }
+    b->data[b->size++] = v;
+}
+static void bInsert(builder *b, uint64_t idx, uint32_t v) {
+    if (b->insCount == b->insCap) {
+        b->insCap = b->insCap ? b->insCap*2 : 1024;
+        b->insIdx = (uint64_t *)realloc(b->insIdx, b->insCap*sizeof(uint64_t));
+        b->insVal = (uint32_t *)realloc(b->insVal, b->insCap*sizeof(uint32_t));
+    }
+    b->insIdx[b->insCount] = idx; b->insVal[b->insCount++] = v;
+}
+static uint32_t bVoxel(const builder *b, int x, int y, int z) {            /* VoxelData.hpp:106-111 */
+    if (x >= b->w || y >= b->h || z >= b->d) return 0;
+    return b->vox[(size_t)x + (size_t)b->w*((size_t)y + (size_t)b->h*(size_t)z)];
+}
+static int bContains(const builder *b, int x, int y, int z, int size) {    /* VoxelData.hpp:122-138 */
+    if (x >= b->w || y >= b->h || z >= b->d) return 0;
+    if (size == 1) return bVoxel(b, x, y, z) != 0;
+    int k = 0; while ((1 << k) < size) ++k;
+    size_t n = (size_t)(b->side >> k);
+    return b->lut[k][(size_t)(x >> k) + n*((size_t)(y >> k) + n*(size_t)(z >> k))] != 0;
+}
+
+static uint64_t bBuild(builder *b, int x, int y, int z, int size, uint64_t descriptorIndex) {   /* VoxelOctree.cpp:139-205 */
+    int half = size >> 1;
+    int posX[8] = {x + half, x, x + half, x, x + half, x, x + half, x};
+    int posY[8] = {y + half, y + half, y, y, y + half, y + half, y, y};
+    int posZ[8] = {z + half, z + half, z + half, z + half, z, z, z, z};
+    uint64_t childOffset = b->size - descriptorIndex;
+    int childCount = 0, childIndices[8];
+    uint32_t childMask = 0;
+    for (int i = 0; i < 8; ++i)
+        if (bContains(b, posX[i], posY[i], posZ[i], half)) { childMask |= 128u >> i; childIndices[childCount++] = i; }
+    int hasLarge = 0;
+    uint32_t leafMask;
+    if (half == 1) {
+        leafMask = 0;
+        for (int i = 0; i < childCount; ++i) {
+            int idx = childIndices[childCount - i - 1];
+            bPush(b, bVoxel(b, posX[idx], posY[idx], posZ[idx]));
+        }
+    } else {
+        leafMask = childMask;
+        for (int i = 0; i < childCount; ++i) bPush(b, 0);
+        uint64_t grand[8], delta = 0, ins = b->insCount;
+        for (int i = 0; i < childCount; ++i) {
+            int idx = childIndices[childCount - i - 1];
+            grand[i] = delta + bBuild(b, posX[idx], posY[idx], posZ[idx], half, descriptorIndex + childOffset + (uint64_t)i);
+            delta += b->insCount - ins;
+            ins = b->insCount;
+            if (grand[i] > 0x3FFF) hasLarge = 1;
+        }
+        for (int i = 0; i < childCount; ++i) {
+            uint64_t childIndex = descriptorIndex + childOffset + (uint64_t)i, offset = grand[i];
+            if (hasLarge) {
+                offset += (uint64_t)(childCount - i);
+                bInsert(b, childIndex + 1, (uint32_t)offset);
+                b->data[childIndex] |= 0x20000u;
+                offset >>= 32;
+            }
+            b->data[childIndex] |= (uint32_t)(offset << 18);
+        }
+    }
+    b->data[descriptorIndex] = (childMask << 8) | leafMask;
+    if (hasLarge) b->data[descriptorIndex] |= 0x10000u;
+    return childOffset;
+}
+
+static int cmpU64Pair(const void *a, const void *b) {
+    uint64_t x = ((const uint64_t *)a)[0], y = ((const uint64_t *)b)[0];
+    return x < y ? -1 : x > y;
+}
+
+/* voxels: w*h*d words, x fastest (the raw .voxel layout, VoxelData.cpp:183-201). Returns a malloc'ed
+ * node array (free with svo_oracle_free) and its length; NULL on allocation failure. */
+uint32_t *svo_oracle_build_octree(const uint32_t *voxels, int w, int h, int d, uint64_t *nWordsOut, float center[3]) {
+    builder b;
+    memset(&b, 0, sizeof b);
+    b.vox = voxels; b.w = w; b.h = h; b.d = d;
+    int side = 1;
+    while (side < w || side < h || side < d) side <<= 1;       /* roundToPow2 + sideLength, VoxelData.cpp:204-207,293-295 */
+    b.side = side;
+    int levels = 0; while ((1 << levels) < side) ++levels;
+    b.levels = levels;
+    b.lut = (uint8_t **)calloc((size_t)levels + 1, sizeof(uint8_t *));
+    for (int k = 1; k <= levels; ++k) {
+        size_t n = (size_t)(side >> k);
+        b.lut[k] = (uint8_t *)calloc(n*n*n, 1);
+    }
+    if (levels >= 1) {
+        size_t n = (size_t)(side >> 1);
+        int zEnd = (d/2)*2;                                     /* VoxelData.cpp:160-163 */
+        for (int z = 0; z < zEnd; ++z) for (int y = 0; y < h; ++y) for (int x = 0; x < w; ++x)
+            if (bVoxel(&b, x, y, z)) b.lut[1][(size_t)(x/2) + n*((size_t)(y/2) + n*(size_t)(z/2))] = 1;
+    }
+    for (int k = 2; k <= levels; ++k) {                         /* upsampleLutLevel, VoxelData.cpp:87-120 */
+        size_t n = (size_t)(side >> k), m = n*2;
+        for (size_t z = 0; z < n; ++z) for (size_t y = 0; y < n; ++y) for (size_t x = 0; x < n; ++x) {
+            int v = 0;
+            for (int c = 0; c < 8; ++c)
+                v |= b.lut[k - 1][(2*x + (c & 1)) + m*((2*y + ((c >> 1) & 1)) + m*(2*z + (c >> 2)))];
+            b.lut[k][x + n*(y + n*z)] = (uint8_t)(v != 0);
+        }
+    }
+    bPush(&b, 0);                                               /* VoxelOctree.cpp:128-132 */
+    bBuild(&b, 0, 0, 0, side, 0);
+    b.data[0] |= 1u << 18;
+
+    /* ChunkedAllocator::finalize */
+    uint64_t total = b.size + b.insCount;
+    uint32_t *out = (uint32_t *)malloc((total + 1)*sizeof(uint32_t));
+    uint64_t *pairs = (uint64_t *)malloc((b.insCount + 1)*2*sizeof(uint64_t));
+    for (uint64_t i = 0; i < b.insCount; ++i) { pairs[2*i] = b.insIdx[i]; pairs[2*i + 1] = b.insVal[i]; }
+    qsort(pairs, b.insCount, 2*sizeof(uint64_t), cmpU64Pair);
+    uint64_t o = 0, k = 0;
+    for (uint64_t i = 0; i < b.size; ++i) {
+        while (k < b.insCount && pairs[2*k] == i) out[o++] = (uint32_t)pairs[2*k++ + 1];
+        out[o++] = b.data[i];
+    }
+    free(pairs);
+    for (int kk = 1; kk <= levels; ++kk) free(b.lut[kk]);
+    free(b.lut); free(b.data); free(b.insIdx); free(b.insVal);
+    *nWordsOut = total;
+    if (center) {                                               /* VoxelData::getCenter, VoxelData.cpp:297-303 */
+        center[0] = (float)w*0.5f/(float)side; center[1] = (float)h*0.5f/(float)side; center[2] = (float)d*0.5f/(float)side;
+    }
+    return out;
+}
+
+void svo_oracle_free(void *p) { free(p); }

@@ -105,6 +105,11 @@ typedef struct {
 } svo_oracle_tree_stats;
 int svo_oracle_tree_walk(const uint32_t *octree, uint64_t words, svo_oracle_tree_stats *out);
 
+/* Row f2: VoxelOctree(VoxelData*) / buildOctree (reference src/VoxelOctree.cpp:125-205) over a dense
+ * w*h*d grid (x fastest, 0 = empty). malloc'ed result, released with svo_oracle_free. */
+uint32_t *svo_oracle_build_octree(const uint32_t *voxels, int w, int h, int d, uint64_t *nWordsOut, float center[3]);
+void svo_oracle_free(void *p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,6 +3,7 @@
 // device entry point needs a CUDA device and says so when there is none.
 #include "../../include/svo_b200.h"
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -19,6 +20,7 @@
 
 #include "camera.hpp"
 #include "oct_io.hpp"
+#include "svo_build.cuh"
 #include "svo_kernels.cuh"
 
 namespace {
@@ -187,7 +189,8 @@ int measureDepth(const uint32_t *words, uint64_t nWords, uint32_t &depthOut) {
 
 // Device, node-array allocation (+1 zeroed padding word: the traversal reads words[p + 1] next to
 // every descriptor) and streams; the node array itself is filled by the caller.
-int allocTree(uint64_t nWords, const float center[3], int device, std::unique_ptr<svo_tree> &treeOut) {
+int allocTree(uint64_t nWords, const float center[3], int device, std::unique_ptr<svo_tree> &treeOut,
+              uint32_t *adoptWords = nullptr) {
     if (nWords < 2) return fail(SVO_ERR_FORMAT, "node array too small (%llu words)", (unsigned long long)nWords);
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
@@ -212,8 +215,12 @@ int allocTree(uint64_t nWords, const float center[3], int device, std::unique_pt
         if (tree->copyStream) cudaStreamDestroy(tree->copyStream);
         return failCuda(err, what);
     };
-    if ((e = cudaMalloc(&tree->dWords, bytes)) != cudaSuccess) return cleanup(e, "cudaMalloc(node array)");
-    if ((e = cudaMemset(tree->dWords + nWords, 0, sizeof(uint32_t))) != cudaSuccess) return cleanup(e, "cudaMemset(padding)");
+    if (adoptWords) {
+        tree->dWords = adoptWords;   // built in place on this device, padding word included (svo_build.cu)
+    } else {
+        if ((e = cudaMalloc(&tree->dWords, bytes)) != cudaSuccess) return cleanup(e, "cudaMalloc(node array)");
+        if ((e = cudaMemset(tree->dWords + nWords, 0, sizeof(uint32_t))) != cudaSuccess) return cleanup(e, "cudaMemset(padding)");
+    }
     int prioLow = 0, prioHigh = 0;
     if ((e = cudaDeviceGetStreamPriorityRange(&prioLow, &prioHigh)) != cudaSuccess) return cleanup(e, "cudaDeviceGetStreamPriorityRange");
     if ((e = cudaStreamCreateWithFlags(&tree->stream, cudaStreamNonBlocking)) != cudaSuccess) return cleanup(e, "cudaStreamCreate");
@@ -532,6 +539,156 @@ int svo_tree_load_oct(const char *path, int device, svo_tree **out) {
     }
     tree->depth = depth;
     *out = tree.release();
+    return SVO_OK;
+}
+
+/* ---- construction (row f2) ---------------------------------------------------- */
+
+namespace {
+
+thread_local svo_build_stats g_buildStats = {};
+
+int requireDevice(int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(SVO_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(SVO_ERR_INVALID_ARGUMENT, "device %d out of range [0, %d)", device, count);
+    return SVO_OK;
+}
+
+int finishBuild(svo::OctreeBuilder &builder, int device, svo_tree **out) {
+    svo::BuildResult r;
+    std::string err;
+    if (!builder.finish(r, err)) return fail(SVO_ERR_FORMAT, "octree construction: %s", err.c_str());
+    std::unique_ptr<svo_tree> tree;
+    int st = allocTree(r.nWords, r.center, device, tree, r.dWords);
+    if (st != SVO_OK) {
+        cudaFree(r.dWords);
+        return st;
+    }
+    tree->depth = r.depth;
+    g_buildStats.voxels = r.stats.voxels;
+    g_buildStats.nodes = r.stats.nodes;
+    g_buildStats.far_blocks = r.stats.farBlocks;
+    g_buildStats.words = r.nWords;
+    g_buildStats.gather_ms = r.stats.gatherMs;
+    g_buildStats.sort_ms = r.stats.sortMs;
+    g_buildStats.levels_ms = r.stats.levelsMs;
+    g_buildStats.emit_ms = r.stats.emitMs;
+    *out = tree.release();
+    return SVO_OK;
+}
+
+constexpr uint64_t kBuildChunkVoxels = 16ull << 20;   // 64 MiB of voxels per upload
+
+} // namespace
+
+int svo_tree_build_from_voxels(const uint32_t *voxels, int w, int h, int d, int device, svo_tree **out) {
+    if (!voxels || !out) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_tree_build_from_voxels: null argument");
+    *out = nullptr;
+    int st = requireDevice(device);
+    if (st != SVO_OK) return st;
+    SVO_DEVICE(device);
+    svo::OctreeBuilder builder;
+    std::string err;
+    if (!builder.begin(w, h, d, err)) return fail(SVO_ERR_INVALID_ARGUMENT, "octree construction: %s", err.c_str());
+    const uint64_t total = uint64_t(w)*uint64_t(h)*uint64_t(d);
+    uint32_t *dChunk = nullptr;
+    SVO_CUDA(cudaMalloc(&dChunk, size_t(std::min(total, kBuildChunkVoxels))*sizeof(uint32_t)));
+    for (uint64_t first = 0; first < total; first += kBuildChunkVoxels) {
+        const uint64_t count = std::min(kBuildChunkVoxels, total - first);
+        cudaError_t e = cudaMemcpy(dChunk, voxels + first, size_t(count)*sizeof(uint32_t), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { cudaFree(dChunk); return failCuda(e, "cudaMemcpy(voxel chunk)"); }
+        if (!builder.addDenseChunk(dChunk, first, count, err)) { cudaFree(dChunk); return fail(SVO_ERR_CUDA, "octree construction: %s", err.c_str()); }
+    }
+    cudaFree(dChunk);
+    return finishBuild(builder, device, out);
+}
+
+// Raw .voxel file: int32 w, h, d, then w*h*d uint32 voxels, x fastest (reference src/VoxelData.cpp:36-48,
+// 183-201). Streamed through two pinned buffers: the read of chunk k+1 overlaps the upload and gather of chunk k.
+int svo_tree_build_from_voxel_file(const char *path, int device, svo_tree **out) {
+    if (!path || !out) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_tree_build_from_voxel_file: null argument");
+    *out = nullptr;
+    int st = requireDevice(device);
+    if (st != SVO_OK) return st;
+    FILE *fp = fopen(path, "rb");
+    if (!fp) return fail(SVO_ERR_IO, "cannot open %s", path);
+    std::unique_ptr<FILE, int (*)(FILE *)> closer(fp, fclose);
+    int32_t dims[3] = {0, 0, 0};
+    if (fread(dims, sizeof(int32_t), 3, fp) != 3) return fail(SVO_ERR_FORMAT, "short read in the header of %s", path);
+    SVO_DEVICE(device);
+    svo::OctreeBuilder builder;
+    std::string err;
+    if (!builder.begin(dims[0], dims[1], dims[2], err)) return fail(SVO_ERR_FORMAT, "%s: %s", path, err.c_str());
+    const uint64_t total = uint64_t(dims[0])*uint64_t(dims[1])*uint64_t(dims[2]);
+    const uint64_t chunk = std::min(total, kBuildChunkVoxels);
+    uint32_t *hBuf[2] = {nullptr, nullptr}, *dBuf[2] = {nullptr, nullptr};
+    cudaEvent_t uploaded[2] = {nullptr, nullptr};
+    auto release = [&]() {
+        for (int i = 0; i < 2; ++i) {
+            if (hBuf[i]) cudaFreeHost(hBuf[i]);
+            if (dBuf[i]) cudaFree(dBuf[i]);
+            if (uploaded[i]) cudaEventDestroy(uploaded[i]);
+        }
+    };
+    for (int i = 0; i < 2; ++i) {
+        cudaError_t e = cudaMallocHost(&hBuf[i], size_t(chunk)*sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaMalloc(&dBuf[i], size_t(chunk)*sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&uploaded[i], cudaEventDisableTiming);
+        if (e != cudaSuccess) { release(); return failCuda(e, "voxel staging buffers"); }
+    }
+    int k = 0;
+    for (uint64_t first = 0; first < total; first += chunk, ++k) {
+        const int b = k & 1;
+        const uint64_t count = std::min(chunk, total - first);
+        cudaEventSynchronize(uploaded[b]);     // the copy out of this pinned buffer two chunks ago
+        if (fread(hBuf[b], sizeof(uint32_t), size_t(count), fp) != size_t(count)) {
+            release();
+            return fail(SVO_ERR_FORMAT, "%s: short read (voxel %llu of %llu)", path, (unsigned long long)first, (unsigned long long)total);
+        }
+        // default stream: ordered after the previous chunk's gather, overlapping the next fread
+        cudaError_t e = cudaMemcpyAsync(dBuf[b], hBuf[b], size_t(count)*sizeof(uint32_t), cudaMemcpyHostToDevice, 0);
+        if (e == cudaSuccess) e = cudaEventRecord(uploaded[b], 0);
+        if (e != cudaSuccess) { release(); return failCuda(e, "cudaMemcpyAsync(voxel chunk)"); }
+        if (!builder.addDenseChunk(dBuf[b], first, count, err)) { release(); return fail(SVO_ERR_CUDA, "octree construction: %s", err.c_str()); }
+    }
+    release();
+    return finishBuild(builder, device, out);
+}
+
+int svo_tree_build_from_sparse(const uint32_t *xyz, const uint32_t *values, uint64_t n, int w, int h, int d,
+                               int device, svo_tree **out) {
+    if ((n && (!xyz || !values)) || !out) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_tree_build_from_sparse: null argument");
+    *out = nullptr;
+    int st = requireDevice(device);
+    if (st != SVO_OK) return st;
+    SVO_DEVICE(device);
+    svo::OctreeBuilder builder;
+    std::string err;
+    if (!builder.begin(w, h, d, err)) return fail(SVO_ERR_INVALID_ARGUMENT, "octree construction: %s", err.c_str());
+    const uint64_t chunk = std::min<uint64_t>(n ? n : 1, kBuildChunkVoxels);
+    uint32_t *dXyz = nullptr, *dVal = nullptr;
+    SVO_CUDA(cudaMalloc(&dXyz, size_t(chunk)*3*sizeof(uint32_t)));
+    cudaError_t e = cudaMalloc(&dVal, size_t(chunk)*sizeof(uint32_t));
+    if (e != cudaSuccess) { cudaFree(dXyz); return failCuda(e, "cudaMalloc(sparse chunk)"); }
+    for (uint64_t first = 0; first < n; first += chunk) {
+        const uint64_t count = std::min(chunk, n - first);
+        e = cudaMemcpy(dXyz, xyz + 3*first, size_t(count)*3*sizeof(uint32_t), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(dVal, values + first, size_t(count)*sizeof(uint32_t), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { cudaFree(dXyz); cudaFree(dVal); return failCuda(e, "cudaMemcpy(sparse chunk)"); }
+        if (!builder.addSparse(dXyz, dVal, count, err)) { cudaFree(dXyz); cudaFree(dVal); return fail(SVO_ERR_CUDA, "octree construction: %s", err.c_str()); }
+    }
+    cudaFree(dXyz);
+    cudaFree(dVal);
+    return finishBuild(builder, device, out);
+}
+
+int svo_build_last_stats(svo_build_stats *out) {
+    if (!out) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_build_last_stats: null argument");
+    *out = g_buildStats;
     return SVO_OK;
 }
 

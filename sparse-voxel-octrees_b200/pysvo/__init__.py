@@ -87,6 +87,11 @@ class TreeInfo(C.Structure):
                 ("device_bytes", C.c_uint64)]
 
 
+class BuildStats(C.Structure):
+    _fields_ = [("voxels", C.c_uint64), ("nodes", C.c_uint64), ("far_blocks", C.c_uint64), ("words", C.c_uint64),
+                ("gather_ms", C.c_float), ("sort_ms", C.c_float), ("levels_ms", C.c_float), ("emit_ms", C.c_float)]
+
+
 def build_library(force: bool = False) -> Path:
     """make -C sparse-voxel-octrees_b200 (nvcc, sm_100a). Cross-compiles without a GPU."""
     args = ["make", "-C", str(PKG_DIR), "-j8"]
@@ -126,6 +131,10 @@ def lib():
         "svo_tree_get_info": (i32, [vp, P(TreeInfo)]),
         "svo_tree_download_words": (i32, [vp, vp, u64]),
         "svo_tree_destroy": (i32, [vp]),
+        "svo_tree_build_from_voxels": (i32, [vp, i32, i32, i32, i32, P(vp)]),
+        "svo_tree_build_from_voxel_file": (i32, [C.c_char_p, i32, P(vp)]),
+        "svo_tree_build_from_sparse": (i32, [vp, vp, u64, i32, i32, i32, i32, P(vp)]),
+        "svo_build_last_stats": (i32, [P(BuildStats)]),
         "svo_raymarch_batch": (i32, [vp, u64, vp, vp, f32, i32, vp, vp, vp, vp]),
         "svo_raymarch_batch_device": (i32, [vp, u64, vp, vp, f32, i32, vp, vp, vp, vp, vp]),
         "svo_raymarch": (i32, [vp, P(f32), P(f32), f32, P(C.c_uint32), P(f32), P(i32)]),
@@ -307,9 +316,11 @@ def device_synchronize(device=0):
 class VoxelOctree:
     """GPU-resident octree with the reference's VoxelOctree surface (VoxelOctree.hpp:48-57)."""
 
-    def __init__(self, path=None, *, words=None, center=None, device=0):
+    def __init__(self, path=None, *, words=None, center=None, device=0, _handle=None):
         h = C.c_void_p()
-        if path is not None:
+        if _handle is not None:
+            h = _handle
+        elif path is not None:
             _check(lib().svo_tree_load_oct(str(path).encode(), int(device), C.byref(h)))
         else:
             if words is None or center is None:
@@ -320,6 +331,41 @@ class VoxelOctree:
         self.info = TreeInfo()
         _check(lib().svo_tree_get_info(self._h, C.byref(self.info)))
         self.device = int(self.info.device)
+
+    # construction on the GPU: VoxelOctree(VoxelData*), VoxelOctree.cpp:125-205
+    @classmethod
+    def build_from_voxels(cls, voxels, device=0):
+        """voxels: uint32[D, H, W] (x fastest, 0 = empty), host memory."""
+        voxels = np.ascontiguousarray(voxels, np.uint32)
+        d, hh, w = voxels.shape
+        h = C.c_void_p()
+        _check(lib().svo_tree_build_from_voxels(_ptr(voxels), w, hh, d, int(device), C.byref(h)))
+        return cls(_handle=h)
+
+    @classmethod
+    def build_from_voxel_file(cls, path, device=0):
+        """Raw .voxel file (VoxelData.cpp:36-48)."""
+        h = C.c_void_p()
+        _check(lib().svo_tree_build_from_voxel_file(str(path).encode(), int(device), C.byref(h)))
+        return cls(_handle=h)
+
+    @classmethod
+    def build_from_sparse(cls, xyz, values, dims, device=0):
+        """xyz: uint32[n, 3] (x, y, z); values: uint32[n]; dims = (w, h, d)."""
+        xyz = np.ascontiguousarray(xyz, np.uint32).reshape(-1, 3)
+        values = np.ascontiguousarray(values, np.uint32).reshape(-1)
+        if xyz.shape[0] != values.shape[0]:
+            raise ValueError("xyz and values differ in length")
+        h = C.c_void_p()
+        _check(lib().svo_tree_build_from_sparse(_ptr(xyz), _ptr(values), values.size, int(dims[0]), int(dims[1]),
+                                                int(dims[2]), int(device), C.byref(h)))
+        return cls(_handle=h)
+
+    @staticmethod
+    def last_build_stats():
+        st = BuildStats()
+        _check(lib().svo_build_last_stats(C.byref(st)))
+        return st
 
     # reference surface
     def save(self, path, compress=True):

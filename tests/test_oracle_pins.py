@@ -148,3 +148,46 @@ def test_port_shading_helpers_match_reference(port, ref):
         assert np.array_equal(n_r.view(np.uint32), n_p.view(np.uint32)) and s_r == s_p
     for x in rng.uniform(1e-6, 1e6, 200):
         assert ref.inv_sqrt(x) == port.inv_sqrt(x)
+
+
+# ---- row f2: the builder restatement ------------------------------------------------------------
+
+def _volume(seed, w, h, d, p):
+    rng = np.random.default_rng(seed)
+    vox = ((rng.random((d, h, w)) < p) * rng.integers(1, 2**32, (d, h, w), dtype=np.uint64)).astype(np.uint32)
+    vox[0, 0, 0] = 1
+    return vox
+
+
+BUILD_CASES = [(1, 8, 8, 8, 0.3), (2, 20, 12, 6, 0.2), (3, 33, 17, 10, 0.1), (4, 7, 9, 5, 0.5), (5, 64, 64, 64, 1.0),
+               (6, 100, 60, 30, 0.03), (7, 2, 2, 2, 1.0)]
+
+
+def test_builder_port_equals_golden(port):
+    """svo_oracle_build_octree against hashes minted from the reference builder (make_build_golden.py)."""
+    build_pins = json.loads((GOLDEN / "build_pins.json").read_text())
+    assert len(build_pins["builder"]) == len(BUILD_CASES)
+    for case, pin in zip(BUILD_CASES, build_pins["builder"]):
+        assert list(case) == pin["case"]
+        words, center = port.build_octree(_volume(*case))
+        assert words.size == pin["n_words"] and sha(words) == pin["words_sha256"], case
+        assert [float(x) for x in center] == pin["center"]
+
+
+def test_builder_port_equals_reference_object_code(port, ref, tmp_path):
+    """VoxelData(path, mem) + VoxelOctree(VoxelData*) (VoxelOctree.cpp:125-205) on raw .voxel files, with
+    the whole volume in one cache block and with 16^3 cache blocks (even depths: see svo_build.cu)."""
+    import struct
+    for case in BUILD_CASES + [(8, 48, 40, 36, 0.15)]:
+        vox = _volume(*case)
+        d, h, w = vox.shape
+        path = tmp_path / "v.voxel"
+        with open(path, "wb") as fp:
+            fp.write(struct.pack("<iii", w, h, d))
+            fp.write(vox.tobytes())
+        got, center = port.build_octree(vox)
+        for mem in ((1 << 30,) if d % 2 else (1 << 30, 1 << 17)):
+            hnd = ref.tree_build_voxel_file(path, mem)
+            assert np.array_equal(ref.tree_words_view(hnd), got), (case, mem)
+            assert np.array_equal(ref.tree_center(hnd), center)
+            ref.tree_destroy(hnd)

@@ -1,0 +1,96 @@
+#!/usr/bin/env python
+"""Row f2: octree construction, raw .voxel file -> node array.
+
+    python tools/bench_build.py [--res 512] [--no-reference]
+
+Generates the benchmark's SDF scene (sphere + fBm, tools/scene_gen.c) as a raw .voxel file, then times
+  * the reference: VoxelData(path, mem) + VoxelOctree(VoxelData*) (reference src/Main.cpp:318-319) through
+    oracle/_ref on this host's cores -- the CPU baseline of this row, and the parity check;
+  * this library: svo_tree_build_from_voxel_file (file streamed to the GPU, tree built in HBM), with the
+    device-side phase times, and svo_tree_build_from_sparse on the same voxels (no dense read).
+Prints one JSON object; words must be identical.
+"""
+import argparse
+import json
+import os
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "sparse-voxel-octrees_b200"))
+
+import numpy as np  # noqa: E402
+
+import pysvo  # noqa: E402
+from tools import make_scenes  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--res", type=int, default=512)
+    ap.add_argument("--no-reference", action="store_true")
+    ap.add_argument("--dir", default=None)
+    a = ap.parse_args()
+    tmp = Path(a.dir or tempfile.mkdtemp(prefix="svo_build_"))
+    raw = tmp / f"sdf{a.res}.voxel"
+    t = time.perf_counter()
+    filled = make_scenes.gen_lib().svo_scene_sdf_voxel_file(str(raw).encode(), a.res, make_scenes.SEED)
+    out = {"scene": f"sdf{a.res}", "resolution": a.res, "filled_voxels": int(filled), "dense_bytes": 4 * a.res ** 3,
+           "host_cores": os.cpu_count(), "generate_s": round(time.perf_counter() - t, 3)}
+    want = None
+    if not a.no_reference:
+        from oracle.pyoracle import Ref
+        ref = Ref()
+        t = time.perf_counter()
+        h = ref.tree_build_voxel_file(raw, make_scenes.builder_memory_budget())
+        out["reference_build_s"] = round(time.perf_counter() - t, 3)
+        want = ref.tree_words(h)
+        ref.tree_destroy(h)
+        out["words"] = int(want.size)
+    pysvo.VoxelOctree(ROOT / "tests" / "golden" / "XYZRGB-Dragon.oct").close()      # context creation is not build time
+    best = None
+    for _ in range(2):
+        t = time.perf_counter()
+        tree = pysvo.VoxelOctree.build_from_voxel_file(raw)
+        dt = time.perf_counter() - t
+        st = pysvo.VoxelOctree.last_build_stats()
+        if best is None or dt < best[0]:
+            best = (dt, {k: getattr(st, k) for k, _ in st._fields_})
+        got = tree.words()
+        tree.close()
+    out["gpu_build_from_file_s"] = round(best[0], 3)
+    out["gpu_phases"] = {k: (round(v, 3) if isinstance(v, float) else v) for k, v in best[1].items()}
+    out["gpu_device_ms"] = round(sum(best[1][k] for k in ("gather_ms", "sort_ms", "levels_ms", "emit_ms")), 3)
+    if want is not None:
+        out["identical_words"] = bool(got.size == want.size and np.array_equal(got, want))
+    # the same voxels as a sparse list: what a voxeliser would hand over, no dense volume anywhere
+    vox = np.memmap(raw, np.uint32, "r", offset=12)
+    idx = np.flatnonzero(vox)
+    vals = np.array(vox[idx])
+    del vox
+    z, rem = np.divmod(idx, a.res * a.res)
+    y, x = np.divmod(rem, a.res)
+    xyz = np.stack([x, y, z], 1).astype(np.uint32)
+    best = None
+    for _ in range(2):
+        t = time.perf_counter()
+        tree = pysvo.VoxelOctree.build_from_sparse(xyz, vals, (a.res, a.res, a.res))
+        dt = time.perf_counter() - t
+        st = pysvo.VoxelOctree.last_build_stats()
+        if best is None or dt < best[0]:
+            best = (dt, sum(getattr(st, k) for k in ("gather_ms", "sort_ms", "levels_ms", "emit_ms")))
+        got2 = tree.words()
+        tree.close()
+    out["gpu_build_from_sparse_s"] = round(best[0], 4)
+    out["gpu_sparse_device_ms"] = round(best[1], 3)
+    out["sparse_identical"] = bool(np.array_equal(got, got2))
+    out["Mvoxels_per_s_device"] = round(filled / best[1] / 1e3, 1)
+    raw.unlink()
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
