@@ -136,6 +136,15 @@ SVO_API int svo_tree_build_from_voxel_file(const char *path, int device, svo_tre
 SVO_API int svo_tree_build_from_sparse(const uint32_t *xyz, const uint32_t *values, uint64_t n, int w, int h, int d,
                                        int device, svo_tree **out);
 
+/* The inverse: the filled voxels of a tree, in the builder's (Morton) order. Call with xyz_out ==
+ * values_out == NULL to get the count in *n_out, then with host buffers of `capacity` >= count voxels
+ * (xyz_out: 3 words per voxel). Coordinates are in the 2^depth grid the tree spans. */
+SVO_API int svo_tree_extract_voxels(const svo_tree *tree, uint32_t *xyz_out, uint32_t *values_out, uint64_t capacity,
+                                    uint64_t *n_out);
+/* build(extract(tree)) without leaving HBM, for a volume of w x h x d voxels (each <= 2^depth). A tree
+ * made by the reference's builder or by svo_tree_build_* comes back word for word. */
+SVO_API int svo_tree_rebuild(const svo_tree *tree, int w, int h, int d, svo_tree **out);
+
 typedef struct svo_build_stats {
     uint64_t voxels;            /* filled voxels in the tree */
     uint64_t nodes;             /* descriptors */

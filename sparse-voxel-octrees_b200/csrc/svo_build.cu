@@ -475,4 +475,120 @@ bool OctreeBuilder::finish(BuildResult &out, std::string &err) {
     return true;
 }
 
+// ---- the inverse: node array -> filled voxels --------------------------------------------------
+// Walks the tree breadth-first, one frontier of (descriptor index, Morton prefix) per level, expanding
+// every node into its children by the same rules the traversal uses (descriptor layout: SURVEY.md
+// App. A.1; reference src/VoxelOctree.cpp:253-293): valid mask in bits 8-15, ascending octant order in
+// the child block, stride 2 when the block is far-interleaved (bit 16), far word after the descriptor
+// (bit 17). The last level emits (x, y, z, material word). With the builder above this gives a
+// size-independent round-trip property: build(extract(tree)) == tree.
+
+namespace {
+
+__device__ __forceinline__ uint32_t compact3(uint64_t x) {
+    x &= 0x1249249249249249ull;
+    x = (x ^ (x >> 2)) & 0x10c30c30c30c30c3ull;
+    x = (x ^ (x >> 4)) & 0x100f00f00f00f00full;
+    x = (x ^ (x >> 8)) & 0x1f0000ff0000ffull;
+    x = (x ^ (x >> 16)) & 0x1f00000000ffffull;
+    x = (x ^ (x >> 32)) & 0x1fffffull;
+    return uint32_t(x);
+}
+
+__global__ void __launch_bounds__(kThreads)
+countChildrenKernel(const uint32_t *__restrict__ words, const uint64_t *__restrict__ addr, uint32_t n, uint32_t *counts) {
+    const uint32_t j = blockIdx.x*blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    counts[j] = uint32_t(__popc((words[addr[j]] >> 8) & 0xFFu));
+}
+
+// leaf == false: children are descriptors -> next frontier; leaf == true: children are voxels -> output
+__global__ void __launch_bounds__(kThreads)
+expandKernel(const uint32_t *__restrict__ words, const uint64_t *__restrict__ addr, const uint64_t *__restrict__ key,
+             const uint32_t *__restrict__ offsets, uint32_t n, bool leaf, uint64_t *nextAddr, uint64_t *nextKey,
+             uint32_t *xyz, uint32_t *values) {
+    const uint32_t j = blockIdx.x*blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint64_t at = addr[j];
+    const uint32_t desc = words[at];
+    uint64_t offset = desc >> 18;
+    if (desc & 0x20000u) offset = (offset << 32) | words[at + 1];
+    const uint64_t block = at + offset;
+    const uint64_t stride = (desc & 0x10000u) ? 2u : 1u;
+    uint32_t mask = (desc >> 8) & 0xFFu;
+    uint32_t out = offsets[j];
+    const uint64_t prefix = key[j] << 3;
+    for (uint32_t i = 0; mask; ++i, ++out) {
+        const uint32_t octant = uint32_t(__ffs(int(mask)) - 1);
+        mask &= mask - 1u;
+        const uint64_t k = prefix | octant;
+        if (leaf) {
+            xyz[3*uint64_t(out)] = compact3(k);
+            xyz[3*uint64_t(out) + 1] = compact3(k >> 1);
+            xyz[3*uint64_t(out) + 2] = compact3(k >> 2);
+            values[out] = words[block + i];
+        } else {
+            nextAddr[out] = block + uint64_t(i)*stride;
+            nextKey[out] = k;
+        }
+    }
+}
+
+} // namespace
+
+bool extractVoxels(const uint32_t *dWords, uint32_t depth, uint32_t **dXyzOut, uint32_t **dValuesOut, uint64_t *nOut,
+                   std::string &err) {
+    *dXyzOut = nullptr;
+    *dValuesOut = nullptr;
+    *nOut = 0;
+    if (depth < 1 || depth > 23) { err = "tree depth out of range"; return false; }
+    DevBuf<uint64_t> addr, key, nextAddr, nextKey;
+    DevBuf<uint32_t> counts, offsets;
+    DevBuf<uint8_t> temp;
+    size_t tempCap = 0;
+    SVO_BUILD_CUDA(addr.alloc(1));
+    SVO_BUILD_CUDA(key.alloc(1));
+    SVO_BUILD_CUDA(cudaMemset(addr.p, 0, sizeof(uint64_t)));
+    SVO_BUILD_CUDA(cudaMemset(key.p, 0, sizeof(uint64_t)));
+    uint32_t n = 1;
+    for (uint32_t l = 0; l < depth; ++l) {
+        const bool leaf = l + 1 == depth;
+        SVO_BUILD_CUDA(counts.alloc(n));
+        SVO_BUILD_CUDA(offsets.alloc(n));
+        countChildrenKernel<<<gridFor(n), kThreads>>>(dWords, addr.p, n, counts.p);
+        size_t bytes = 0;
+        SVO_BUILD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, counts.p, offsets.p, int(n)));
+        if (bytes > tempCap) { SVO_BUILD_CUDA(temp.alloc(bytes)); tempCap = bytes; }
+        SVO_BUILD_CUDA(cub::DeviceScan::ExclusiveSum(temp.p, bytes, counts.p, offsets.p, int(n)));
+        uint32_t lastOffset = 0, lastCount = 0;
+        SVO_BUILD_CUDA(cudaMemcpy(&lastOffset, offsets.p + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        SVO_BUILD_CUDA(cudaMemcpy(&lastCount, counts.p + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        const uint64_t total = uint64_t(lastOffset) + lastCount;
+        if (total == 0 || total >= (1ull << 32)) { err = "tree level with no or too many children"; return false; }
+        if (leaf) {
+            DevBuf<uint32_t> xyz, values;
+            SVO_BUILD_CUDA(xyz.alloc(total*3));
+            SVO_BUILD_CUDA(values.alloc(total));
+            expandKernel<<<gridFor(n), kThreads>>>(dWords, addr.p, key.p, offsets.p, n, true, nullptr, nullptr, xyz.p, values.p);
+            SVO_BUILD_CUDA(cudaGetLastError());
+            SVO_BUILD_CUDA(cudaDeviceSynchronize());
+            *dXyzOut = xyz.p;
+            *dValuesOut = values.p;
+            xyz.p = nullptr;
+            values.p = nullptr;
+            *nOut = total;
+            return true;
+        }
+        SVO_BUILD_CUDA(nextAddr.alloc(total));
+        SVO_BUILD_CUDA(nextKey.alloc(total));
+        expandKernel<<<gridFor(n), kThreads>>>(dWords, addr.p, key.p, offsets.p, n, false, nextAddr.p, nextKey.p, nullptr, nullptr);
+        SVO_BUILD_CUDA(cudaGetLastError());
+        addr = std::move(nextAddr);
+        key = std::move(nextKey);
+        n = uint32_t(total);
+    }
+    err = "unreachable";
+    return false;
+}
+
 } // namespace svo

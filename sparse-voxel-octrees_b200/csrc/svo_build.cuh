@@ -56,4 +56,10 @@ private:
     float gatherMs_ = 0.0f;
 };
 
+// The inverse of the builder: the filled voxels of a node array resident on the current device, in
+// Morton order (ascending x + 2y + 4z per level). Outputs are cudaMalloc'ed: 3 coordinates per voxel and
+// one material word per voxel.
+bool extractVoxels(const uint32_t *dWords, uint32_t depth, uint32_t **dXyzOut, uint32_t **dValuesOut, uint64_t *nOut,
+                   std::string &err);
+
 } // namespace svo

@@ -686,6 +686,52 @@ int svo_tree_build_from_sparse(const uint32_t *xyz, const uint32_t *values, uint
     return finishBuild(builder, device, out);
 }
 
+// Two calls: with xyz_out == values_out == NULL only *n_out is written (the count); with buffers of
+// `capacity` voxels the list is copied out. The extraction runs on the device either way.
+int svo_tree_extract_voxels(const svo_tree *tree, uint32_t *xyz_out, uint32_t *values_out, uint64_t capacity,
+                            uint64_t *n_out) {
+    if (!tree || !n_out || ((xyz_out == nullptr) != (values_out == nullptr)))
+        return fail(SVO_ERR_INVALID_ARGUMENT, "svo_tree_extract_voxels: null argument");
+    SVO_DEVICE(tree->device);
+    uint32_t *dXyz = nullptr, *dVal = nullptr;
+    uint64_t n = 0;
+    std::string err;
+    if (!svo::extractVoxels(tree->dWords, tree->depth, &dXyz, &dVal, &n, err)) return fail(SVO_ERR_CUDA, "voxel extraction: %s", err.c_str());
+    *n_out = n;
+    int st = SVO_OK;
+    if (xyz_out) {
+        if (capacity < n) {
+            st = fail(SVO_ERR_INVALID_ARGUMENT, "svo_tree_extract_voxels: capacity %llu < %llu voxels", (unsigned long long)capacity, (unsigned long long)n);
+        } else {
+            cudaError_t e = cudaMemcpy(xyz_out, dXyz, size_t(n)*3*sizeof(uint32_t), cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess) e = cudaMemcpy(values_out, dVal, size_t(n)*sizeof(uint32_t), cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) st = failCuda(e, "cudaMemcpy(voxel list)");
+        }
+    }
+    cudaFree(dXyz);
+    cudaFree(dVal);
+    return st;
+}
+
+// build(extract(tree)) entirely in HBM: the canonical re-layout of a tree. For a tree the reference's
+// builder (or this one) produced the result is the same array -- the round-trip property the tests use
+// at sizes no CPU oracle reaches.
+int svo_tree_rebuild(const svo_tree *tree, int w, int h, int d, svo_tree **out) {
+    if (!tree || !out) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_tree_rebuild: null argument");
+    *out = nullptr;
+    SVO_DEVICE(tree->device);
+    uint32_t *dXyz = nullptr, *dVal = nullptr;
+    uint64_t n = 0;
+    std::string err;
+    if (!svo::extractVoxels(tree->dWords, tree->depth, &dXyz, &dVal, &n, err)) return fail(SVO_ERR_CUDA, "voxel extraction: %s", err.c_str());
+    svo::OctreeBuilder builder;
+    bool ok = builder.begin(w, h, d, err) && builder.addSparse(dXyz, dVal, n, err);
+    cudaFree(dXyz);
+    cudaFree(dVal);
+    if (!ok) return fail(SVO_ERR_INVALID_ARGUMENT, "octree construction: %s", err.c_str());
+    return finishBuild(builder, tree->device, out);
+}
+
 int svo_build_last_stats(svo_build_stats *out) {
     if (!out) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_build_last_stats: null argument");
     *out = g_buildStats;

@@ -135,6 +135,8 @@ def lib():
         "svo_tree_build_from_voxel_file": (i32, [C.c_char_p, i32, P(vp)]),
         "svo_tree_build_from_sparse": (i32, [vp, vp, u64, i32, i32, i32, i32, P(vp)]),
         "svo_build_last_stats": (i32, [P(BuildStats)]),
+        "svo_tree_extract_voxels": (i32, [vp, vp, vp, u64, P(u64)]),
+        "svo_tree_rebuild": (i32, [vp, i32, i32, i32, P(vp)]),
         "svo_raymarch_batch": (i32, [vp, u64, vp, vp, f32, i32, vp, vp, vp, vp]),
         "svo_raymarch_batch_device": (i32, [vp, u64, vp, vp, f32, i32, vp, vp, vp, vp, vp]),
         "svo_raymarch": (i32, [vp, P(f32), P(f32), f32, P(C.c_uint32), P(f32), P(i32)]),
@@ -360,6 +362,23 @@ class VoxelOctree:
         _check(lib().svo_tree_build_from_sparse(_ptr(xyz), _ptr(values), values.size, int(dims[0]), int(dims[1]),
                                                 int(dims[2]), int(device), C.byref(h)))
         return cls(_handle=h)
+
+    def extract_voxels(self):
+        """-> (xyz uint32[n, 3], values uint32[n]) in Morton order."""
+        n = C.c_uint64(0)
+        _check(lib().svo_tree_extract_voxels(self._h, None, None, 0, C.byref(n)))
+        xyz = np.empty((n.value, 3), np.uint32)
+        values = np.empty(n.value, np.uint32)
+        _check(lib().svo_tree_extract_voxels(self._h, _ptr(xyz), _ptr(values), n.value, C.byref(n)))
+        return xyz, values
+
+    def rebuild(self, dims=None):
+        """build(extract(self)) in HBM; dims default to the full 2^depth cube."""
+        side = 1 << self.depth
+        w, hh, d = dims if dims is not None else (side, side, side)
+        h = C.c_void_p()
+        _check(lib().svo_tree_rebuild(self._h, int(w), int(hh), int(d), C.byref(h)))
+        return VoxelOctree(_handle=h)
 
     @staticmethod
     def last_build_stats():
