@@ -3,16 +3,19 @@
 // include/svo_b200.h. Header-only; link with -lsvo_b200.
 //
 //   VoxelOctree(const char *path)                  reference src/VoxelOctree.cpp:57
-//   VoxelOctree(VoxelData *voxels)                 reference src/VoxelOctree.cpp:125  (see adopt() below)
+//   VoxelOctree(VoxelData *voxels)                 reference src/VoxelOctree.cpp:125  (fromVoxelFile / fromVoxels /
+//                                                  fromSparse build in HBM; adopt() takes a finished array)
 //   void save(const char *path)                    reference src/VoxelOctree.cpp:92
 //   bool raymarch(o, d, rayScale, normal&, t&)     reference src/VoxelOctree.cpp:207
 //   Vec3 center() const                            reference src/VoxelOctree.hpp:55
 //
 // When this header is included after the reference's math/Vec3.hpp and
 // IntTypes.hpp it uses their Vec3 / uint32; otherwise it supplies minimal
-// stand-ins. The builder constructor is kept by delegation: build with the
-// reference's own VoxelData/VoxelOctree, then hand the node array over with
-// VoxelOctree::adopt(words, count, center) -- it is uploaded to HBM unchanged.
+// stand-ins. The builder constructor VoxelOctree(VoxelData*) becomes three
+// factories that build the same node array on the GPU from what VoxelData
+// wraps -- a raw .voxel file (VoxelData(path, mem), VoxelData.cpp:36-48), a
+// dense grid, or a list of filled voxels (what a voxeliser produces) -- and
+// adopt(words, count, center) still uploads an array built elsewhere unchanged.
 //
 // Differences a caller can observe: failures throw std::runtime_error carrying
 // svo_last_error() instead of being ignored (the reference silently continues
@@ -62,6 +65,24 @@ public:
         float c[3] = {center.x, center.y, center.z};
         svo_tree *tree = 0;
         check(svo_tree_create_from_words(words, count, c, device, &tree), "VoxelOctree::adopt");
+        return new VoxelOctree(tree);
+    }
+    // VoxelData(path, mem) + VoxelOctree(VoxelData*), Main.cpp:318-319: raw .voxel file -> tree in HBM.
+    static VoxelOctree *fromVoxelFile(const char *path, int device = 0) {
+        svo_tree *tree = 0;
+        check(svo_tree_build_from_voxel_file(path, device, &tree), "VoxelOctree::fromVoxelFile");
+        return new VoxelOctree(tree);
+    }
+    // Dense w*h*d grid of material words (x fastest, 0 = empty).
+    static VoxelOctree *fromVoxels(const uint32 *voxels, int w, int h, int d, int device = 0) {
+        svo_tree *tree = 0;
+        check(svo_tree_build_from_voxels(voxels, w, h, d, device, &tree), "VoxelOctree::fromVoxels");
+        return new VoxelOctree(tree);
+    }
+    // n filled voxels: xyz = n (x, y, z) triples, values = n material words.
+    static VoxelOctree *fromSparse(const uint32 *xyz, const uint32 *values, uint64 n, int w, int h, int d, int device = 0) {
+        svo_tree *tree = 0;
+        check(svo_tree_build_from_sparse(xyz, values, n, w, h, d, device, &tree), "VoxelOctree::fromSparse");
         return new VoxelOctree(tree);
     }
     ~VoxelOctree() { svo_tree_destroy(_tree); }

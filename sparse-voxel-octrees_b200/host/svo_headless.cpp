@@ -4,6 +4,11 @@
 //
 //   svo_headless <in.oct> [--size WxH] [--strips N] [--frames K] [--radius R] [--pitch P]
 //                [--yaw0 Y] [--yaw-step S] [--validation] [--out prefix]
+//   svo_headless -builder <in.voxel> <out.oct>
+//
+// The second form is the reference's `-builder` mode for a raw voxel volume (the on-disk path of
+// reference src/Main.cpp:313-319 after PlyLoader::convertToVolume): VoxelData(path) + VoxelOctree(VoxelData*)
+// + save, with the tree built in HBM.
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -33,6 +38,26 @@ int main(int argc, char **argv) {
         fprintf(stderr, "usage: %s <in.oct> [--size WxH] [--strips N] [--frames K] [--radius R] [--pitch P] "
                         "[--yaw0 Y] [--yaw-step S] [--validation] [--out prefix]\n", argv[0]);
         return 2;
+    }
+    if (std::string(argv[1]) == "-builder") {
+        if (argc != 4) { fprintf(stderr, "usage: %s -builder <in.voxel> <out.oct>\n", argv[0]); return 2; }
+        try {
+            auto t0 = std::chrono::steady_clock::now();
+            VoxelOctree *tree = VoxelOctree::fromVoxelFile(argv[2]);
+            svo_build_stats st;
+            svo_build_last_stats(&st);
+            tree->save(argv[3]);
+            double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            printf("built %s: %llu voxels -> %llu words (depth %u, %llu far blocks), device %.3f ms; "
+                   "Octree initialization took %.3f s\n", argv[3], (unsigned long long)st.voxels,
+                   (unsigned long long)tree->wordCount(), tree->depth(), (unsigned long long)st.far_blocks,
+                   st.gather_ms + st.sort_ms + st.levels_ms + st.emit_ms, s);
+            delete tree;
+        } catch (const std::exception &e) {
+            fprintf(stderr, "error: %s\n", e.what());
+            return 1;
+        }
+        return 0;
     }
     int w = 1280, h = 720, strips = 16, frames = 1, flavour = SVO_FLAVOUR_FAST; /* Main.cpp:57-60 defaults */
     float radius = 1.0f, pitch = 0.0f, yaw0 = 0.0f, yawStep = 3.6f;

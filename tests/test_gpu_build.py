@@ -201,3 +201,24 @@ def test_rebuild_reproduces_reference_built_tree(pysvo, name):
     assert st.words == words.size
     again.close()
     tree.close()
+
+
+def test_headless_builder_mode(pysvo, port, tmp_path):
+    """`svo_headless -builder in.voxel out.oct`: the reference's -builder mode for a raw volume
+    (reference src/Main.cpp:313-319) through the C++ facade's VoxelOctree::fromVoxelFile + save."""
+    import subprocess
+    pkg = ROOT / "sparse-voxel-octrees_b200"
+    subprocess.check_call(["make", "-C", str(pkg), "headless"], stdout=subprocess.DEVNULL)
+    vox = random_volume(np.random.default_rng(31), 40, 36, 30, 0.1)
+    raw, out = tmp_path / "in.voxel", tmp_path / "out.oct"
+    write_voxel_file(raw, vox)
+    res = subprocess.run([str(pkg / "svo_headless"), "-builder", str(raw), str(out)], capture_output=True, text=True,
+                         timeout=300)
+    assert res.returncode == 0, res.stderr
+    want, wcenter = port.build_octree(vox)
+    words, center = pysvo.oct_read(out)
+    assert np.array_equal(words, want) and np.array_equal(center, wcenter)
+    assert f"-> {want.size} words" in res.stdout
+    res = subprocess.run([str(pkg / "svo_headless"), "-builder", str(tmp_path / "nope.voxel"), str(out)],
+                         capture_output=True, text=True, timeout=300)
+    assert res.returncode == 1 and "cannot open" in res.stderr
