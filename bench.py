@@ -58,6 +58,9 @@ WORKLOADS = {
 }
 STRIPS = 16            # the reference's NumThreads (Main.cpp:57): part of the image definition
 ORBIT = 100            # distinct cameras (3.6 degrees apart)
+LANES = 4              # frames in flight per rank (SVO_BENCH_LANES overrides): hides the fine pass's long-ray tail and,
+                       # with several GPUs, the frame barrier. Measured 2 / 4 / 6 lanes, 2048^3 @ 4K: N=8 48.6 / 61.6 / 63.0
+                       # Grays/s, N=4 31.2 / 34.6 / -, N=1 9.30 / 9.37 / - (profiles/experiments/r01_lanes.md)
 DRAGON = ROOT / "tests" / "golden" / "XYZRGB-Dragon.oct"
 
 
@@ -480,10 +483,11 @@ def run_own(args):
 
     # ---- framebuffer: rank 0 owns it; other ranks map it and store their tiles into it over NVLink
     nbytes = W * H * 4
+    n_lanes = min(int(os.environ.get("SVO_BENCH_LANES", "0")) or LANES, 8)    # the library's frame ring is 8 deep
     fbs = []
-    fb_ptrs = [0, 0]
+    fb_ptrs = [0] * n_lanes
     if rank == 0:
-        for i in range(2):          # two framebuffers: frame k is copied out while frame k+1 is rendered
+        for i in range(n_lanes):    # one framebuffer per frame in flight: frame k is consumed while k+1.. are rendered
             fbs.append(pysvo.DeviceBuffer(local_rank, nbytes))
             fbs[i].zero()
             fb_ptrs[i] = fbs[i].ptr
@@ -525,12 +529,12 @@ def run_own(args):
     # long-ray tail of one fine pass overlaps the start of the next frame (each frame is still complete,
     # in rank 0's memory, when its stream reaches the frame barrier).
     main = torch.cuda.current_stream()
-    lanes = [torch.cuda.Stream(), torch.cuda.Stream()]
+    lanes = [torch.cuda.Stream() for _ in range(n_lanes)]
     comm = torch.cuda.Stream() if world > 1 else None
-    gate = [None, None]
+    gate = [None] * n_lanes
 
     def pipelined_frame(k):
-        slot = k & 1
+        slot = k % n_lanes
         with torch.cuda.stream(lanes[slot]):
             tree.render_frame_device(cams[k % ORBIT], W, H, fb_ptrs[slot], strips=STRIPS, flavour=flavour,
                                      tile_rank=rank, tile_world=world, stream=lanes[slot].cuda_stream)
@@ -712,7 +716,7 @@ def run_own(args):
                    "octree_words": tree.n_words, "octree_depth": tree.depth,
                    "parallelism": "replicated octree, interleaved 8x8 tiles, fine-pass stores into rank 0's framebuffer over NVLink" if world > 1 else "single GPU",
                    "l2": f"no flush: octree {tree.n_words * 4 / 1e6:.0f} MB vs 126 MB L2, camera moves every step",
-                   "pipelining": "two frames in flight (framebuffer k & 1 on stream k & 1); beam passes run ahead on internal streams",
+                   "pipelining": f"{n_lanes} frames in flight (framebuffer k % {n_lanes} on stream k % {n_lanes}); beam passes run ahead on internal streams",
                    "rays_per_frame_mean": total_rays / steps, "ms_per_frame": total_ms / steps},
         "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 128, "d2h_bytes_per_step": nbytes,
                 "steps": e2e_steps, "ms_per_step": float(e2e_s.item()) / e2e_steps * 1e3,

@@ -275,7 +275,7 @@ SVO_API int svo_frame_wait(svo_tree *tree, const svo_frame_desc *desc, int ticke
  * which case finished tiles travel over NVLink as the kernel stores them.
  * Asynchronous: the tile classifier and the fine pass run on `stream`; the beam
  * pass runs on one of the tree's two internal high-priority streams (it only
- * touches internal buffers, a ring of four frames deep) and `stream` waits for
+ * touches internal buffers, a ring of eight frames deep) and `stream` waits for
  * it, so consecutive calls overlap the beam passes of the next frames with the
  * fine pass of the current one. Frames issued on different streams into
  * different framebuffers may overlap entirely (bench.py alternates two). If

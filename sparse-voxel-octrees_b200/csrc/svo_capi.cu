@@ -73,7 +73,7 @@ struct DeviceScope {
 // still busy -- the beam pass is latency-bound (its longest ray), and with several GPUs sharing a
 // frame it would otherwise be the critical path. Host-buffer frames additionally alternate between
 // two staging framebuffers so the device->host copy of frame i overlaps the rendering of frame i+1.
-constexpr int kRing = 4;
+constexpr int kRing = 8;
 
 struct FramePlan {
     svo::FramePlanDev dev{};
