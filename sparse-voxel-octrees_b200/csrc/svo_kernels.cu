@@ -41,8 +41,9 @@ raymarchBatchKernel(const uint32_t *__restrict__ octree, uint64_t n, const float
     float dx = __ldg(d + 3*i), dy = __ldg(d + 3*i + 1), dz = __ldg(d + 3*i + 2);
 
     float tHit = kTreeMiss;
-    uint64_t vox = ~uint64_t(0);
+    uint64_t vox;
     int code = raymarch<FAST, LOD, IdxT, kBatchThreads>(octree, ox, oy, oz, dx, dy, dz, rayScale, stack, tHit, vox);
+    if (code == kMiss) vox = ~uint64_t(0);
     uint32_t material = code == kHitLeaf ? ldNode(octree + vox) : 0u;   // VoxelOctree.cpp:282
 
     if (hit) hit[i] = uint8_t(code);
@@ -196,11 +197,11 @@ finePassKernel(const uint32_t *__restrict__ octree, FramePlanDev plan, FrameCons
         const float oz = addRn(f.posZ, mulRn(rz, startT));
 
         float tHit;
-        uint64_t vox = 0;
+        uint64_t vox;
         const int code = raymarch<FAST, false, IdxT, kTileThreads>(octree, ox, oy, oz, rx, ry, rz, 0.0f, stack, tHit, vox);
         // the warp is convergent again here: one material fetch and one pass through the shading code
-        // for all its hits together (misses read word 0, the root, and discard the result)
-        const uint32_t material = ldNode(octree + (code != kMiss ? IdxT(vox) : IdxT(0)));   // VoxelOctree.cpp:282
+        // for all its hits together (misses read some descriptor and discard the result)
+        const uint32_t material = ldNode(octree + IdxT(vox));   // VoxelOctree.cpp:282
         uint32_t colour = packGrey(shadeMaterial(material, rx, ry, rz, f.lightX, f.lightY, f.lightZ));
         if (code == kMiss) colour = 0xFF000000u;                // Vec3() -> black, Main.cpp:117
         rgba[size_t(py)*size_t(plan.width) + px] = colour;

@@ -218,7 +218,8 @@ enum : int { kMiss = 0, kHitLeaf = 1, kHitLod = 2 };
 // reference src/VoxelOctree.cpp:207-346. Returns kMiss / kHitLeaf / kHitLod.
 //   tOut      written on a hit only
 //   voxelOut  leaf word index (the caller fetches the material word octree[voxelOut], :282, AFTER the
-//             warp has reconverged), or parent | childShift << 60 for LOD exits
+//             warp has reconverged), or parent | childShift << 60 for LOD exits; on a miss some valid
+//             word index (so that callers can fetch octree[voxelOut] without a select)
 // The loop has ONE exit: every way out records its result and breaks, and a warp barrier follows the
 // loop. Without it the compiler threads whatever the caller does with a hit (material fetch + ~100
 // instructions of shading) into the leaf branch inside the loop, where it runs once per distinct exit
@@ -287,7 +288,10 @@ __device__ __forceinline__ int raymarch(const uint32_t *__restrict__ octree, flo
     } while (0)
     SVO_FETCH_NODE();
 
-    int code = kMiss;
+    // How the loop was left is recorded in childShift (always < 8 inside the loop): a separate result
+    // flag would have to be set on the pop path, which every pop executes, for the sake of the one
+    // pop per ray that leaves the root.
+    constexpr uint32_t kExitLeaf = 8u, kExitLod = 16u;
     for (;;) {
         const float cornerTX = A::mulsub(posX, dTx, bTx);   // :256-259
         const float cornerTY = A::mulsub(posY, dTy, bTy);
@@ -300,7 +304,7 @@ __device__ __forceinline__ int raymarch(const uint32_t *__restrict__ octree, flo
             if (LOD && mulRn(maxTC, rayScale) >= scaleExp2) {   // :265-268
                 tOut = maxTC;
                 voxelOut = uint64_t(parent) | (uint64_t(childShift) << 60);
-                code = kHitLod;
+                childShift = kExitLod;
                 break;
             }
 
@@ -318,7 +322,7 @@ __device__ __forceinline__ int raymarch(const uint32_t *__restrict__ octree, flo
                     IdxT leaf = childOffset + parent + IdxT(__popc(((childMasks >> (8 + childShift)) << childShift) & 127u));
                     voxelOut = uint64_t(leaf);
                     tOut = minT;
-                    code = kHitLeaf;
+                    childShift = kExitLeaf;
                     break;
                 }
 
@@ -355,9 +359,11 @@ __device__ __forceinline__ int raymarch(const uint32_t *__restrict__ octree, flo
         posZ = moveIf<FAST>(stZ, -scaleExp2, posZ);
         const uint32_t stepMask = flagMask(stX, stY, stZ) & 7u;
         minT = maxTC;
-        childShift ^= stepMask;                                 // idx ^= stepMask
+        // idx ^= stepMask; pop if (idx & stepMask) != 0 (:316-318)  <=>  a stepped axis had its idx bit clear
+        const bool leavesParent = (~(childShift ^ octantMask) & stepMask) != 0;
+        childShift ^= stepMask;
 
-        if (((childShift ^ octantMask) & stepMask) != 0) {      // (idx & stepMask) != 0, :318-338
+        if (leavesParent) {                                     // :318-338
             // pos ^ (pos + scaleExp2) over the stepped axes (:320-322); an axis that did not step adds
             // 0*scaleExp2 and contributes nothing. (Keeping the pre-step positions instead costs three
             // register moves on EVERY trip: ptxas copies them at the loop head.)
@@ -368,8 +374,11 @@ __device__ __forceinline__ int raymarch(const uint32_t *__restrict__ octree, flo
             // reference: exponent of (float)differingBits. differingBits < 2^24
             // always (positions stay in [0.5, 2)), so that is the index of the
             // highest set bit; bit 23 set <=> the ray left the root (:341-342)
-            if (differingBits > 0x7FFFFFu) break;
-            scale = 31 - __clz(int(differingBits));
+            if (differingBits > 0x7FFFFFu) {
+                voxelOut = uint64_t(parent);   // any valid word index: the caller may fetch it unconditionally
+                break;
+            }
+            asm("bfind.u32 %0, %1;" : "=r"(scale) : "r"(differingBits));   // FLO: index of the highest set bit
             scaleExp2 = __uint_as_float(uint32_t(scale - kMaxScale + 127) << 23);
 
             Stack::load(stack.slot(scale), parent, maxT);
@@ -392,7 +401,7 @@ __device__ __forceinline__ int raymarch(const uint32_t *__restrict__ octree, flo
     }
 #undef SVO_FETCH_NODE
     __syncwarp();   // exited lanes do not take part; see the note on the single exit above
-    return code;
+    return childShift == kExitLeaf ? kHitLeaf : (LOD && childShift == kExitLod) ? kHitLod : kMiss;
 }
 
 } // namespace svo
