@@ -176,13 +176,16 @@ struct SmemStack<uint32_t, THREADS> {
         top = uint32_t(__cvta_generic_to_shared(smem)) + threadIdx.x*kEntry;
         asm volatile("" : "+r"(top));   // keep it in a register; ptxas would re-derive it at every pop
     }
-    __device__ __forceinline__ uint32_t slot(int scale) const { return top + uint32_t(kMaxScale - 1 - scale)*kStride; }
+    // The slot of `scale` is top + (22 - scale)*kStride = slot(scale) + kBias: one IMAD for the register
+    // part, the constant part rides in the instruction's immediate offset.
+    static constexpr uint32_t kBias = uint32_t(kMaxScale - 1)*kStride;
+    __device__ __forceinline__ uint32_t slot(int scale) const { return top - uint32_t(scale)*kStride; }
     static __device__ __forceinline__ void store(uint32_t addr, uint32_t parent, float maxT) {
-        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(parent), "r"(__float_as_uint(maxT)) : "memory");
+        asm volatile("st.shared.v2.b32 [%0+%3], {%1, %2};" ::"r"(addr), "r"(parent), "r"(__float_as_uint(maxT)), "n"(kBias) : "memory");
     }
     static __device__ __forceinline__ void load(uint32_t addr, uint32_t &parent, float &maxT) {
         uint32_t m;
-        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(parent), "=r"(m) : "r"(addr) : "memory");
+        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2+%3];" : "=r"(parent), "=r"(m) : "r"(addr), "n"(kBias) : "memory");
         maxT = __uint_as_float(m);
     }
     static size_t bytes(uint32_t slots) { return size_t(slots)*kStride; }
@@ -197,14 +200,15 @@ struct SmemStack<uint64_t, THREADS> {   // trees of 2^32 words and more: 16-byte
         top = uint32_t(__cvta_generic_to_shared(smem)) + threadIdx.x*kEntry;
         asm volatile("" : "+r"(top));
     }
-    __device__ __forceinline__ uint32_t slot(int scale) const { return top + uint32_t(kMaxScale - 1 - scale)*kStride; }
+    static constexpr uint32_t kBias = uint32_t(kMaxScale - 1)*kStride;
+    __device__ __forceinline__ uint32_t slot(int scale) const { return top - uint32_t(scale)*kStride; }
     static __device__ __forceinline__ void store(uint32_t addr, uint64_t parent, float maxT) {
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(uint32_t(parent)),
-                     "r"(uint32_t(parent >> 32)), "r"(__float_as_uint(maxT)), "r"(0u) : "memory");
+        asm volatile("st.shared.v4.b32 [%0+%5], {%1, %2, %3, %4};" ::"r"(addr), "r"(uint32_t(parent)),
+                     "r"(uint32_t(parent >> 32)), "r"(__float_as_uint(maxT)), "r"(0u), "n"(kBias) : "memory");
     }
     static __device__ __forceinline__ void load(uint32_t addr, uint64_t &parent, float &maxT) {
         uint32_t lo, hi, m, pad;
-        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(hi), "=r"(m), "=r"(pad) : "r"(addr) : "memory");
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4+%5];" : "=r"(lo), "=r"(hi), "=r"(m), "=r"(pad) : "r"(addr), "n"(kBias) : "memory");
         parent = (uint64_t(hi) << 32) | lo;
         maxT = __uint_as_float(m);
     }
@@ -329,7 +333,10 @@ __device__ __forceinline__ int raymarch(const uint32_t *__restrict__ octree, flo
                 Stack::store(stack.slot(scale), parent, maxT);  // :287-288
 
                 // siblings before this child, doubled when the block is far-interleaved (bit 16), :290-293
-                const uint32_t siblings = uint32_t(__popc(childMasks & 127u)) << ((current >> 16) & 1u);
+                uint32_t siblings = uint32_t(__popc(childMasks & 127u));
+                // one predicate test + one predicated shift (the C forms compile to three or four instructions)
+                asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %1, 0x10000;\n\tsetp.ne.u32 p, t, 0;\n\t@p shl.b32 %0, %0, 1;\n\t}"
+                    : "+r"(siblings) : "r"(current));
                 parent += childOffset + IdxT(siblings);
 
                 const float half = mulRn(scaleExp2, 0.5f);
