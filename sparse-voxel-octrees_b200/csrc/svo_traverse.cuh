@@ -304,16 +304,21 @@ __device__ __forceinline__ int raymarch(const uint32_t *__restrict__ octree, flo
 
         const uint32_t childMasks = current << childShift;
 
-        if ((childMasks & 0x8000u) && minT <= maxT) {
-            if (LOD && mulRn(maxTC, rayScale) >= scaleExp2) {   // :265-268
+        // :263-273. Without the LOD test in between, `minT <= maxT && minT <= min(maxT, maxTC)` is just its
+        // second half (min(maxT, maxTC) <= maxT), so the rays of the fine pass make one comparison here.
+        const float maxTV = fminf(maxT, maxTC);
+        bool descend = (childMasks & 0x8000u) != 0;
+        if (LOD) {
+            descend = descend && minT <= maxT;
+            if (descend && mulRn(maxTC, rayScale) >= scaleExp2) {   // :265-268
                 tOut = maxTC;
                 voxelOut = uint64_t(parent) | (uint64_t(childShift) << 60);
                 childShift = kExitLod;
                 break;
             }
-
-            const float maxTV = fminf(maxT, maxTC);
-            if (minT <= maxTV) {
+        }
+        {
+            if (descend && minT <= maxTV) {
                 IdxT childOffset = IdxT(current >> 18);
                 if (current & 0x20000u) {                      // :278-279
                     if (sizeof(IdxT) == 8)
