@@ -326,6 +326,7 @@ bool OctReader::decode(uint32_t *words, const SliceSink &sink, std::string &err,
         FilePtr f(fopen(path.c_str(), "rb"));   // own handle: own file position
         std::vector<uint8_t> comp;
         if (!f) { fail("cannot reopen " + path); return; }
+        try {
         for (;;) {
             size_t k = next.fetch_add(1);
             if (k >= n) return;
@@ -357,6 +358,9 @@ bool OctReader::decode(uint32_t *words, const SliceSink &sink, std::string &err,
                 done[k] = 1;
             }
             cv.notify_all();
+        }
+        } catch (const std::exception &e) {     // e.g. bad_alloc for a slice payload: report, do not terminate
+            fail(std::string("slice decoder: ") + e.what());
         }
     };
 

@@ -12,8 +12,9 @@
 //   gather    every non-empty voxel becomes (Morton key, material word); x is the lowest key bit,
 //             because buildOctree visits the children of a node in the order -x-y-z ... +x+y+z reversed
 //             (VoxelOctree.cpp:144-146,164,177), i.e. ascending x + 2y + 4z. One radix sort.
-//   bottom-up level l = depth-1 .. 0: a node is a run of child keys with equal key >> 3. Per node:
-//             valid mask, child count c, and -- with F(child) = number of words everything below that
+//   bottom-up level l = depth-1 .. 0: a node is a run of child keys with equal key >> 3: one reduce-by-key
+//             (OR of the children's octant bits) gives parents and valid masks, the scan of the masks'
+//             popcounts where their children start. Per node: child count c, and -- with F(child) = number of words everything below that
 //             child's descriptor occupies, prefix-summed over the child level --
 //               G_last = 1 + sum of F over all children but the last   (VoxelOctree.cpp:176-184; G_i =
 //                        c - i + sum_{j<i} F_j is the distance from child descriptor i to its own
@@ -41,7 +42,9 @@
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_reduce.cuh>
 #include <cub/device/device_scan.cuh>
+#include <thrust/iterator/transform_iterator.h>
 
 namespace svo {
 
@@ -68,27 +71,40 @@ __device__ __forceinline__ uint64_t mortonKey(uint32_t x, uint32_t y, uint32_t z
     return spread3(x) | (spread3(y) << 1) | (spread3(z) << 2);
 }
 
-// Warp-aggregated append of the lanes with `keep` set.
+// Block-aggregated append of the threads with `keep` set: one atomic on the global cursor per block and
+// iteration (a single cursor takes ~1 atomic per ns; one per warp made the gather atomics-bound at
+// 300 M voxels). Every thread of the block must call it the same number of times.
 __device__ __forceinline__ void appendEntry(bool keep, uint64_t key, uint32_t value, uint64_t *keys, uint32_t *vals,
                                             unsigned long long *cursor) {
+    __shared__ unsigned warpCount[kThreads/32];
+    __shared__ unsigned long long blockBase;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const unsigned mask = __ballot_sync(0xffffffffu, keep);
-    if (mask == 0) return;
-    const unsigned lane = threadIdx.x & 31u;
-    unsigned long long base = 0;
-    if (lane == unsigned(__ffs(int(mask)) - 1)) base = atomicAdd(cursor, (unsigned long long)__popc(mask));
-    base = __shfl_sync(0xffffffffu, base, __ffs(int(mask)) - 1);
+    if (lane == 0) warpCount[warp] = unsigned(__popc(mask));
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned total = 0;
+        for (int w = 0; w < kThreads/32; ++w) {
+            const unsigned c = warpCount[w];
+            warpCount[w] = total;           // exclusive prefix
+            total += c;
+        }
+        blockBase = total ? atomicAdd(cursor, (unsigned long long)total) : 0ull;
+    }
+    __syncthreads();
     if (keep) {
-        const unsigned long long at = base + __popc(mask & ((1u << lane) - 1u));
+        const unsigned long long at = blockBase + warpCount[warp] + __popc(mask & ((1u << lane) - 1u));
         keys[at] = key;
         vals[at] = value;
     }
+    __syncthreads();                        // warpCount / blockBase are rewritten by the next call
 }
 
 __global__ void __launch_bounds__(kThreads)
 gatherDenseKernel(const uint32_t *__restrict__ voxels, uint64_t first, uint64_t count, Dims dims, uint64_t *keys,
                   uint32_t *vals, unsigned long long *cursor) {
     const uint64_t stride = uint64_t(gridDim.x)*blockDim.x;
-    const uint64_t rounded = (count + 31u) & ~uint64_t(31);     // whole warps take part in the ballot
+    const uint64_t rounded = (count + (kThreads - 1)) & ~uint64_t(kThreads - 1);   // whole blocks take part in the append
     for (uint64_t i = uint64_t(blockIdx.x)*blockDim.x + threadIdx.x; i < rounded; i += stride) {
         uint32_t v = i < count ? __ldg(voxels + i) : 0u;
         uint64_t key = 0;
@@ -110,7 +126,7 @@ __global__ void __launch_bounds__(kThreads)
 gatherSparseKernel(const uint32_t *__restrict__ xyz, const uint32_t *__restrict__ values, uint64_t n, Dims dims,
                    uint64_t *keys, uint32_t *vals, unsigned long long *cursor) {
     const uint64_t stride = uint64_t(gridDim.x)*blockDim.x;
-    const uint64_t rounded = (n + 31u) & ~uint64_t(31);
+    const uint64_t rounded = (n + (kThreads - 1)) & ~uint64_t(kThreads - 1);
     for (uint64_t i = uint64_t(blockIdx.x)*blockDim.x + threadIdx.x; i < rounded; i += stride) {
         bool keep = false;
         uint64_t key = 0;
@@ -125,41 +141,39 @@ gatherSparseKernel(const uint32_t *__restrict__ xyz, const uint32_t *__restrict_
     }
 }
 
-// flags[k] = 1 where a new parent starts; duplicates[0] counts equal neighbours (sparse input must be unique)
-__global__ void __launch_bounds__(kThreads)
-markHeadsKernel(const uint64_t *__restrict__ keys, uint32_t m, uint32_t *flags, unsigned long long *duplicates) {
-    const uint32_t k = blockIdx.x*blockDim.x + threadIdx.x;
-    if (k >= m) return;
-    const uint64_t key = keys[k];
-    const bool head = k == 0 || (key >> 3) != (keys[k - 1] >> 3);
-    flags[k] = head ? 1u : 0u;
-    if (duplicates && k > 0 && key == keys[k - 1]) atomicAdd(duplicates, 1ull);
-}
-
-__global__ void __launch_bounds__(kThreads)
-scatterNodesKernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ flags,
-                   const uint32_t *__restrict__ index, uint32_t m, uint32_t nNodes, uint64_t *nodeKeys,
-                   uint32_t *childStart) {
-    const uint32_t k = blockIdx.x*blockDim.x + threadIdx.x;
-    if (k == 0) childStart[nNodes] = m;
-    if (k >= m || !flags[k]) return;
-    const uint32_t j = index[k];
-    nodeKeys[j] = keys[k] >> 3;
-    childStart[j] = k;
-}
+// A level is one reduce-by-key over the sorted child keys: parent key = key >> 3, value = the child's
+// octant bit, reduction = OR. That yields the parents' keys and valid masks in one pass; a parent's
+// child count is the popcount of its mask (children are unique), and the exclusive scan of those
+// counts is where each parent's children start in the child arrays.
+struct ParentKey {
+    __host__ __device__ __forceinline__ uint64_t operator()(uint64_t key) const { return key >> 3; }
+};
+struct OctantBit {
+    __host__ __device__ __forceinline__ uint32_t operator()(uint64_t key) const { return 1u << uint32_t(key & 7u); }
+};
+struct BitOr {
+    __host__ __device__ __forceinline__ uint32_t operator()(uint32_t a, uint32_t b) const { return a | b; }
+};
+struct PopCount {
+    __host__ __device__ __forceinline__ uint32_t operator()(uint32_t mask) const {
+#ifdef __CUDA_ARCH__
+        return uint32_t(__popc(mask));
+#else
+        uint32_t n = 0;
+        for (; mask; mask &= mask - 1u) ++n;
+        return n;
+#endif
+    }
+};
 
 // childPrefix == nullptr: leaf parents (children are voxels)
 __global__ void __launch_bounds__(kThreads)
-nodeStatsKernel(const uint64_t *__restrict__ childKeys, const uint32_t *__restrict__ childStart, uint32_t nNodes,
-                const uint64_t *__restrict__ childPrefix, uint8_t *mask, uint8_t *far, uint64_t *subtree,
-                unsigned long long *farBlocks) {
+nodeStatsKernel(const uint32_t *__restrict__ childStart, uint32_t nNodes, const uint64_t *__restrict__ childPrefix,
+                uint8_t *far, uint64_t *subtree, unsigned long long *farBlocks) {
     const uint32_t j = blockIdx.x*blockDim.x + threadIdx.x;
     bool isFar = false;
     if (j < nNodes) {
         const uint32_t s = childStart[j], e = childStart[j + 1];
-        uint32_t m = 0;
-        for (uint32_t c = s; c < e; ++c) m |= 1u << uint32_t(childKeys[c] & 7u);
-        mask[j] = uint8_t(m);
         const uint64_t count = e - s;
         uint64_t f = count;
         if (childPrefix) {
@@ -179,7 +193,7 @@ nodeStatsKernel(const uint64_t *__restrict__ childKeys, const uint32_t *__restri
 __global__ void __launch_bounds__(kThreads)
 emitLevelKernel(uint32_t nNodes, const uint32_t *__restrict__ childStart, const uint8_t *__restrict__ far,
                 const uint64_t *__restrict__ blockBase, const uint64_t *__restrict__ childPrefix,
-                const uint8_t *__restrict__ childMask, const uint8_t *__restrict__ childFar, bool childIsLeafParent,
+                const uint32_t *__restrict__ childMask, const uint8_t *__restrict__ childFar, bool childIsLeafParent,
                 const uint32_t *__restrict__ voxelValues, uint64_t *childBlockBase, uint32_t *out) {
     const uint32_t j = blockIdx.x*blockDim.x + threadIdx.x;
     if (j >= nNodes) return;
@@ -210,11 +224,36 @@ emitLevelKernel(uint32_t nNodes, const uint32_t *__restrict__ childStart, const 
     }
 }
 
-__global__ void emitRootKernel(const uint8_t *mask, const uint8_t *far, bool rootIsLeafParent, uint32_t *out,
+__global__ void emitRootKernel(const uint32_t *mask, const uint8_t *far, bool rootIsLeafParent, uint32_t *out,
                                uint64_t *blockBase) {
     const uint32_t m = mask[0];
     out[0] = (m << 8) | (rootIsLeafParent ? 0u : m) | (far[0] ? 0x10000u : 0u) | (1u << 18);   // :128-132
     blockBase[0] = 1;
+}
+
+// Scratch memory comes from a private stream-ordered pool (one per device): a build makes some sixty
+// allocations of up to gigabytes, level after level, and plain cudaMalloc / cudaFree (map, unmap and a
+// device synchronisation each) cost more than the kernels between them. Blocks freed by one level are
+// reused by the next; the pool is trimmed when the build is over.
+cudaMemPool_t scratchPool() {
+    static cudaMemPool_t pools[64] = {};
+    int device = 0;
+    if (cudaGetDevice(&device) != cudaSuccess || device < 0 || device >= 64) return nullptr;
+    if (!pools[device]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        if (cudaMemPoolCreate(&pools[device], &props) != cudaSuccess) { pools[device] = nullptr; return nullptr; }
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pools[device], cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    return pools[device];
+}
+
+void trimScratchPool() {
+    if (cudaMemPool_t pool = scratchPool()) cudaMemPoolTrimTo(pool, size_t(256) << 20);
 }
 
 template <typename T>
@@ -228,16 +267,21 @@ struct DevBuf {
     ~DevBuf() { release(); }
     cudaError_t alloc(uint64_t n) {
         release();
-        return cudaMalloc(&p, size_t(n ? n : 1)*sizeof(T));
+        const size_t bytes = size_t(n ? n : 1)*sizeof(T);
+        cudaMemPool_t pool = scratchPool();
+        if (!pool) return cudaMalloc(&p, bytes);
+        return cudaMallocFromPoolAsync(reinterpret_cast<void **>(&p), bytes, pool, 0);
     }
-    void release() { if (p) cudaFree(p); p = nullptr; }
+    void release() { if (p) cudaFreeAsync(p, 0); p = nullptr; }   // cudaFreeAsync also takes cudaMalloc'ed blocks
+    T *detach() { T *q = p; p = nullptr; return q; }
 };
 
 struct Level {
     uint32_t n = 0;
     DevBuf<uint64_t> keys;       // n; released once the parent level is built
     DevBuf<uint32_t> childStart; // n + 1
-    DevBuf<uint8_t> mask, far;   // n
+    DevBuf<uint32_t> mask;       // n (+ 1 zero behind the last, for the scan)
+    DevBuf<uint8_t> far;         // n
     DevBuf<uint64_t> prefix;     // n + 1: exclusive prefix sum of F over this level
 };
 
@@ -347,7 +391,7 @@ bool OctreeBuilder::addSparse(const uint32_t *dXyz, const uint32_t *dValues, uin
 bool OctreeBuilder::finish(BuildResult &out, std::string &err) {
     if (!dCursor_) { err = "OctreeBuilder::begin was not called"; return false; }
     if (count_ == 0) { err = "the volume has no visible non-empty voxel: nothing to build"; return false; }
-    if (count_ >= (1ull << 32)) { err = "more than 2^32 - 1 voxels are not supported"; return false; }
+    if (count_ >= (1ull << 31)) { err = "more than 2^31 - 1 voxels are not supported (32-bit item counts in the scans)"; return false; }
     const uint32_t nVoxels = uint32_t(count_);
     BuildStats stats;
     stats.voxels = count_;
@@ -373,52 +417,64 @@ bool OctreeBuilder::finish(BuildResult &out, std::string &err) {
 
     // ---- bottom-up
     timer.start();
-    DevBuf<unsigned long long> counters;     // [0] duplicates, [1] far blocks
-    SVO_BUILD_CUDA(counters.alloc(2));
-    SVO_BUILD_CUDA(cudaMemset(counters.p, 0, 2*sizeof(unsigned long long)));
+    DevBuf<unsigned long long> counters;     // [0] far blocks
+    SVO_BUILD_CUDA(counters.alloc(1));
+    SVO_BUILD_CUDA(cudaMemset(counters.p, 0, sizeof(unsigned long long)));
+    DevBuf<uint32_t> numRuns;
+    SVO_BUILD_CUDA(numRuns.alloc(1));
     std::vector<Level> level(static_cast<size_t>(levels_));
-    DevBuf<uint32_t> flags, index;
-    SVO_BUILD_CUDA(flags.alloc(nVoxels));
-    SVO_BUILD_CUDA(index.alloc(nVoxels));
-    size_t scanBytes = 0;
-    {
-        size_t a = 0, b = 0;
-        SVO_BUILD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, a, flags.p, index.p, int(nVoxels)));
-        SVO_BUILD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, b, (uint64_t *)nullptr, (uint64_t *)nullptr, int(nVoxels) + 1));
-        scanBytes = std::max(a, b);
-    }
-    DevBuf<uint8_t> scanTemp;
-    SVO_BUILD_CUDA(scanTemp.alloc(scanBytes));
+    DevBuf<uint8_t> cubTemp;
+    size_t cubTempCap = 0;
+    auto needTemp = [&](size_t bytes) -> cudaError_t {
+        if (bytes <= cubTempCap) return cudaSuccess;
+        cudaError_t e = cubTemp.alloc(bytes);
+        cubTempCap = e == cudaSuccess ? bytes : 0;
+        return e;
+    };
 
     const uint64_t *childKeys = voxelKeys;
     uint32_t m = nVoxels;
     for (int l = levels_ - 1; l >= 0; --l) {
         Level &lv = level[size_t(l)];
         const bool leafParent = l == levels_ - 1;
-        markHeadsKernel<<<gridFor(m), kThreads>>>(childKeys, m, flags.p, leafParent ? counters.p : nullptr);
-        size_t bytes = scanBytes;
-        SVO_BUILD_CUDA(cub::DeviceScan::ExclusiveSum(scanTemp.p, bytes, flags.p, index.p, int(m)));
-        uint32_t lastIndex = 0, lastFlag = 0;
-        SVO_BUILD_CUDA(cudaMemcpy(&lastIndex, index.p + (m - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost));
-        SVO_BUILD_CUDA(cudaMemcpy(&lastFlag, flags.p + (m - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost));
-        lv.n = lastIndex + lastFlag;
-        if (leafParent) {
-            unsigned long long dup = 0;
-            SVO_BUILD_CUDA(cudaMemcpy(&dup, counters.p, sizeof dup, cudaMemcpyDeviceToHost));
-            if (dup) { err = "sparse voxel list names " + std::to_string(dup) + " coordinate(s) more than once"; return false; }
-        }
-        SVO_BUILD_CUDA(lv.keys.alloc(lv.n));
+        // parents' keys and masks: at most m of them
+        SVO_BUILD_CUDA(lv.keys.alloc(m));
+        SVO_BUILD_CUDA(lv.mask.alloc(uint64_t(m) + 1));
+        thrust::transform_iterator<ParentKey, const uint64_t *> parentKeys(childKeys, ParentKey());
+        thrust::transform_iterator<OctantBit, const uint64_t *> octantBits(childKeys, OctantBit());
+        size_t bytes = 0;
+        SVO_BUILD_CUDA(cub::DeviceReduce::ReduceByKey(nullptr, bytes, parentKeys, lv.keys.p, octantBits, lv.mask.p,
+                                                      numRuns.p, BitOr(), int(m)));
+        SVO_BUILD_CUDA(needTemp(bytes));
+        SVO_BUILD_CUDA(cub::DeviceReduce::ReduceByKey(cubTemp.p, bytes, parentKeys, lv.keys.p, octantBits, lv.mask.p,
+                                                      numRuns.p, BitOr(), int(m)));
+        SVO_BUILD_CUDA(cudaMemcpy(&lv.n, numRuns.p, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        // where each parent's children start: exclusive scan of popcount(mask), n + 1 items (the last is 0)
+        SVO_BUILD_CUDA(cudaMemsetAsync(lv.mask.p + lv.n, 0, sizeof(uint32_t)));
         SVO_BUILD_CUDA(lv.childStart.alloc(uint64_t(lv.n) + 1));
-        SVO_BUILD_CUDA(lv.mask.alloc(lv.n));
+        thrust::transform_iterator<PopCount, const uint32_t *> childCounts(lv.mask.p, PopCount());
+        bytes = 0;
+        SVO_BUILD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, childCounts, lv.childStart.p, int(lv.n) + 1));
+        SVO_BUILD_CUDA(needTemp(bytes));
+        SVO_BUILD_CUDA(cub::DeviceScan::ExclusiveSum(cubTemp.p, bytes, childCounts, lv.childStart.p, int(lv.n) + 1));
+        if (leafParent) {
+            // children of one parent are unique, so the popcounts add up to m unless a coordinate was named twice
+            uint32_t covered = 0;
+            SVO_BUILD_CUDA(cudaMemcpy(&covered, lv.childStart.p + lv.n, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+            if (covered != m) {
+                err = "sparse voxel list names " + std::to_string(m - covered) + " coordinate(s) more than once";
+                return false;
+            }
+        }
         SVO_BUILD_CUDA(lv.far.alloc(lv.n));
         SVO_BUILD_CUDA(lv.prefix.alloc(uint64_t(lv.n) + 1));
-        scatterNodesKernel<<<gridFor(m), kThreads>>>(childKeys, flags.p, index.p, m, lv.n, lv.keys.p, lv.childStart.p);
         SVO_BUILD_CUDA(cudaMemsetAsync(lv.prefix.p + lv.n, 0, sizeof(uint64_t)));
-        nodeStatsKernel<<<gridFor(lv.n), kThreads>>>(childKeys, lv.childStart.p, lv.n,
-                                                     leafParent ? nullptr : level[size_t(l) + 1].prefix.p, lv.mask.p,
-                                                     lv.far.p, lv.prefix.p, counters.p + 1);
-        bytes = scanBytes;
-        SVO_BUILD_CUDA(cub::DeviceScan::ExclusiveSum(scanTemp.p, bytes, lv.prefix.p, lv.prefix.p, int(lv.n) + 1));
+        nodeStatsKernel<<<gridFor(lv.n), kThreads>>>(lv.childStart.p, lv.n, leafParent ? nullptr : level[size_t(l) + 1].prefix.p,
+                                                     lv.far.p, lv.prefix.p, counters.p);
+        bytes = 0;
+        SVO_BUILD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, lv.prefix.p, lv.prefix.p, int(lv.n) + 1));
+        SVO_BUILD_CUDA(needTemp(bytes));
+        SVO_BUILD_CUDA(cub::DeviceScan::ExclusiveSum(cubTemp.p, bytes, lv.prefix.p, lv.prefix.p, int(lv.n) + 1));
         SVO_BUILD_CUDA(cudaGetLastError());
         if (!leafParent) level[size_t(l) + 1].keys.release();
         childKeys = lv.keys.p;
@@ -429,10 +485,8 @@ bool OctreeBuilder::finish(BuildResult &out, std::string &err) {
     uint64_t rootSubtree = 0;
     SVO_BUILD_CUDA(cudaMemcpy(&rootSubtree, level[0].prefix.p + 1, sizeof(uint64_t), cudaMemcpyDeviceToHost));
     unsigned long long farBlocks = 0;
-    SVO_BUILD_CUDA(cudaMemcpy(&farBlocks, counters.p + 1, sizeof farBlocks, cudaMemcpyDeviceToHost));
+    SVO_BUILD_CUDA(cudaMemcpy(&farBlocks, counters.p, sizeof farBlocks, cudaMemcpyDeviceToHost));
     stats.farBlocks = farBlocks;
-    flags.release();
-    index.release();
     stats.levelsMs = timer.stop();
 
     // ---- top-down
@@ -463,6 +517,16 @@ bool OctreeBuilder::finish(BuildResult &out, std::string &err) {
     }
     stats.emitMs = timer.stop();
     SVO_BUILD_CUDA(cudaDeviceSynchronize());
+    for (Level &lv : level) lv = Level();
+    base.release();
+    keysAlt.release();
+    valsAlt.release();
+    temp.release();
+    cubTemp.release();
+    counters.release();
+    numRuns.release();
+    cudaStreamSynchronize(0);
+    trimScratchPool();
 
     out.dWords = guard.p;
     guard.p = nullptr;
@@ -564,7 +628,7 @@ bool extractVoxels(const uint32_t *dWords, uint32_t depth, uint32_t **dXyzOut, u
         SVO_BUILD_CUDA(cudaMemcpy(&lastOffset, offsets.p + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost));
         SVO_BUILD_CUDA(cudaMemcpy(&lastCount, counts.p + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost));
         const uint64_t total = uint64_t(lastOffset) + lastCount;
-        if (total == 0 || total >= (1ull << 32)) { err = "tree level with no or too many children"; return false; }
+        if (total == 0 || total >= (1ull << 31)) { err = "tree level with no or too many (>= 2^31) children"; return false; }
         if (leaf) {
             DevBuf<uint32_t> xyz, values;
             SVO_BUILD_CUDA(xyz.alloc(total*3));
