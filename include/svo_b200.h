@@ -263,9 +263,9 @@ SVO_API int svo_render_frame(svo_tree *tree, const svo_camera *cam, const svo_fr
                              uint32_t *rgba, float *depth, svo_frame_stats *stats);
 /* Pipelined host-buffer variant: enqueues the frame and its device->host copies and returns at
  * once with a ticket; svo_frame_wait(ticket) blocks until `rgba` (and `depth`) hold the frame.
- * Up to TWO frames may be in flight per (width, height, strips) configuration, so the copy of
- * frame i overlaps the rendering of frame i+1 (and the beam pass of frame i+1 overlaps the fine
- * pass of frame i). Host buffers must stay valid, and should be page-locked (svo_host_alloc),
+ * Up to FOUR frames may be in flight per (width, height, strips) configuration (a fifth is refused),
+ * so the copy of frame i and the long-ray tail of its fine pass overlap the rendering of frames
+ * i+1.. (and the beam passes of later frames overlap the fine passes of earlier ones). Host buffers must stay valid, and should be page-locked (svo_host_alloc),
  * until the wait returns. svo_render_frame == svo_render_frame_async + svo_frame_wait. */
 SVO_API int svo_render_frame_async(svo_tree *tree, const svo_camera *cam, const svo_frame_desc *desc,
                                    uint32_t *rgba, float *depth, int want_stats, int *ticket);

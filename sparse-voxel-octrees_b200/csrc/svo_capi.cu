@@ -74,6 +74,7 @@ struct DeviceScope {
 // frame it would otherwise be the critical path. Host-buffer frames additionally alternate between
 // two staging framebuffers so the device->host copy of frame i overlaps the rendering of frame i+1.
 constexpr int kRing = 8;
+constexpr int kHostLanes = 4;   // host-buffer frames in flight (staging framebuffers, render streams, tickets)
 
 struct FramePlan {
     svo::FramePlanDev dev{};
@@ -89,14 +90,14 @@ struct FramePlan {
     uint64_t frameNumber = 0;
 
     // host-buffer entry points only
-    uint32_t *dRgba[2] = {nullptr, nullptr};            // staging framebuffers (lazy)
-    cudaEvent_t copyDone[2] = {nullptr, nullptr};       // device->host copy out of dRgba[i] finished
-    bool copyRecorded[2] = {false, false};
-    bool pending[2] = {false, false};                   // svo_render_frame_async issued, not yet waited for
-    bool pendingStats[2] = {false, false};
-    int pendingRing[2] = {0, 0};
-    uint32_t pendingLaunches[2] = {0, 0};
-    svo_frame_desc pendingDesc[2] = {};
+    uint32_t *dRgba[kHostLanes] = {};                   // staging framebuffers (lazy)
+    cudaEvent_t copyDone[kHostLanes] = {};              // device->host copy out of dRgba[i] finished
+    bool copyRecorded[kHostLanes] = {};
+    bool pending[kHostLanes] = {};                      // svo_render_frame_async issued, not yet waited for
+    bool pendingStats[kHostLanes] = {};
+    int pendingRing[kHostLanes] = {};
+    uint32_t pendingLaunches[kHostLanes] = {};
+    svo_frame_desc pendingDesc[kHostLanes] = {};
     uint64_t hostFrameNumber = 0;
 
     void destroy() {
@@ -110,7 +111,7 @@ struct FramePlan {
             if (fineDone[b]) cudaEventDestroy(fineDone[b]);
             for (int k = 0; k < 4; ++k) if (timing[b][k]) cudaEventDestroy(timing[b][k]);
         }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < kHostLanes; ++b) {
             if (dRgba[b]) cudaFree(dRgba[b]);
             if (copyDone[b]) cudaEventDestroy(copyDone[b]);
         }
@@ -146,7 +147,8 @@ struct svo_tree {
     float center[3] = {0, 0, 0};
     uint32_t depth = 0;
     cudaStream_t stream = nullptr;          // batches; classifier + fine pass of even host-buffer frames
-    cudaStream_t stream2 = nullptr;         // ... of odd host-buffer frames (so that consecutive fine passes overlap)
+    cudaStream_t stream2 = nullptr;         // ... of host-buffer frames 1 mod 4 (so that consecutive fine passes overlap)
+    cudaStream_t stream34[2] = {nullptr, nullptr};      // ... 2 and 3 mod 4
     cudaStream_t coarseStream[2] = {nullptr, nullptr};  // beam passes, high priority, alternating per frame
     cudaStream_t copyStream = nullptr;      // device->host frame copies
     std::mutex mutex;
@@ -211,6 +213,7 @@ int allocTree(uint64_t nWords, const float center[3], int device, std::unique_pt
         if (tree->dWords) cudaFree(tree->dWords);
         if (tree->stream) cudaStreamDestroy(tree->stream);
         if (tree->stream2) cudaStreamDestroy(tree->stream2);
+        for (int i = 0; i < 2; ++i) if (tree->stream34[i]) cudaStreamDestroy(tree->stream34[i]);
         for (int i = 0; i < 2; ++i) if (tree->coarseStream[i]) cudaStreamDestroy(tree->coarseStream[i]);
         if (tree->copyStream) cudaStreamDestroy(tree->copyStream);
         return failCuda(err, what);
@@ -225,6 +228,8 @@ int allocTree(uint64_t nWords, const float center[3], int device, std::unique_pt
     if ((e = cudaDeviceGetStreamPriorityRange(&prioLow, &prioHigh)) != cudaSuccess) return cleanup(e, "cudaDeviceGetStreamPriorityRange");
     if ((e = cudaStreamCreateWithFlags(&tree->stream, cudaStreamNonBlocking)) != cudaSuccess) return cleanup(e, "cudaStreamCreate");
     if ((e = cudaStreamCreateWithFlags(&tree->stream2, cudaStreamNonBlocking)) != cudaSuccess) return cleanup(e, "cudaStreamCreate");
+    for (int i = 0; i < 2; ++i)
+        if ((e = cudaStreamCreateWithFlags(&tree->stream34[i], cudaStreamNonBlocking)) != cudaSuccess) return cleanup(e, "cudaStreamCreate");
     for (int i = 0; i < 2; ++i)
         if ((e = cudaStreamCreateWithPriority(&tree->coarseStream[i], cudaStreamNonBlocking, prioHigh)) != cudaSuccess)
             return cleanup(e, "cudaStreamCreate(coarse)");
@@ -315,7 +320,7 @@ int buildPlan(svo_tree *tree, int width, int height, int strips, FramePlan &plan
         SVO_CUDA(cudaEventCreateWithFlags(&plan.fineDone[b], cudaEventDisableTiming));
         for (int k = 0; k < 4; ++k) SVO_CUDA(cudaEventCreate(&plan.timing[b][k]));
     }
-    for (int b = 0; b < 2; ++b) SVO_CUDA(cudaEventCreateWithFlags(&plan.copyDone[b], cudaEventDisableTiming));
+    for (int b = 0; b < kHostLanes; ++b) SVO_CUDA(cudaEventCreateWithFlags(&plan.copyDone[b], cudaEventDisableTiming));
     p.dxCoarse = plan.dTables;
     p.dyCoarse = p.dxCoarse + nDxC;
     p.dxFine = p.dyCoarse + nDyC;
@@ -776,6 +781,7 @@ int svo_tree_destroy(svo_tree *tree) {
         if (tree->dWords) cudaFree(tree->dWords);
         if (tree->stream) cudaStreamDestroy(tree->stream);
         if (tree->stream2) cudaStreamDestroy(tree->stream2);
+        for (int i = 0; i < 2; ++i) if (tree->stream34[i]) cudaStreamDestroy(tree->stream34[i]);
         for (int i = 0; i < 2; ++i) if (tree->coarseStream[i]) cudaStreamDestroy(tree->coarseStream[i]);
         if (tree->copyStream) cudaStreamDestroy(tree->copyStream);
     }
@@ -951,17 +957,17 @@ int svo_render_frame_async(svo_tree *tree, const svo_camera *cam, const svo_fram
     std::lock_guard<std::mutex> lock(tree->mutex);
     FramePlan *plan = nullptr;
     if ((st = getPlan(tree, desc->width, desc->height, desc->strips, &plan)) != SVO_OK) return st;
-    const int b = int(plan->hostFrameNumber & 1);  // staging framebuffer / ticket of this frame
+    const int b = int(plan->hostFrameNumber % kHostLanes);  // staging framebuffer / ticket of this frame
     if (plan->pending[b])
-        return fail(SVO_ERR_INVALID_ARGUMENT, "two frames are already in flight for this configuration: call svo_frame_wait first");
+        return fail(SVO_ERR_INVALID_ARGUMENT, "%d frames are already in flight for this configuration: call svo_frame_wait first", kHostLanes);
     size_t frameBytes = size_t(desc->width)*size_t(desc->height)*sizeof(uint32_t);
     if (!plan->dRgba[b]) {
         SVO_CUDA(cudaMalloc(&plan->dRgba[b], frameBytes));
         SVO_CUDA(cudaMemset(plan->dRgba[b], 0, frameBytes));
     }
-    // even and odd frames render on different streams into different staging framebuffers, so the
-    // long-ray tail of one fine pass overlaps the start of the next
-    cudaStream_t s = b ? tree->stream2 : tree->stream;
+    // consecutive frames render on different streams into different staging framebuffers, so the
+    // long-ray tail of one fine pass overlaps the start of the next ones
+    cudaStream_t s = b == 0 ? tree->stream : b == 1 ? tree->stream2 : tree->stream34[b - 2];
     // the staging framebuffer is free once its previous device->host copy has finished
     if (plan->copyRecorded[b]) SVO_CUDA(cudaStreamWaitEvent(s, plan->copyDone[b], 0));
     uint32_t launches = 0;
@@ -987,7 +993,7 @@ int svo_render_frame_async(svo_tree *tree, const svo_camera *cam, const svo_fram
 
 int svo_frame_wait(svo_tree *tree, const svo_frame_desc *desc, int ticket, svo_frame_stats *stats) {
     if (!tree || !desc) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_frame_wait: null argument");
-    if (ticket != 0 && ticket != 1) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_frame_wait: bad ticket %d", ticket);
+    if (ticket < 0 || ticket >= kHostLanes) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_frame_wait: bad ticket %d", ticket);
     SVO_DEVICE(tree->device);
     std::lock_guard<std::mutex> lock(tree->mutex);
     auto it = tree->plans.find(std::make_tuple(desc->width, desc->height, desc->strips));

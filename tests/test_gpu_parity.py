@@ -176,23 +176,26 @@ def test_frame_tile_interleave_reassembles(pysvo, gpu_dragon, pins):
 
 
 def test_pipelined_frames_match_synchronous(pysvo, gpu_dragon, pins):
-    """svo_render_frame_async: two frames in flight, beam pass of frame i+1 overlapping the fine pass of
-    frame i, copies on their own stream -- every frame must equal the synchronous result."""
+    """svo_render_frame_async: four frames in flight, beam passes running ahead of the fine passes,
+    copies on their own stream -- every frame must equal the synchronous result."""
+    lanes = 4
     cams = [_cam(pysvo, e) for e in pins["cameras"]] * 3
     want = [gpu_dragon.render_frame(c, 1280, 720, strips=16, flavour=pysvo.FLAVOUR_VALIDATION, want_stats=True) for c in cams[:5]]
-    bufs = [pysvo.PinnedArray((720, 1280), np.uint32) for _ in range(2)]
-    pending = [None, None]
+    bufs = [pysvo.PinnedArray((720, 1280), np.uint32) for _ in range(lanes)]
+    pending = [None] * lanes
     got = []
     for k, c in enumerate(cams):
-        slot = k & 1
+        slot = k % lanes
         if pending[slot] is not None:
             st = gpu_dragon.frame_wait(pending[slot], want_stats=True)
             got.append((bufs[slot].array.copy(), st))
         pending[slot] = gpu_dragon.render_frame_async(c, 1280, 720, bufs[slot].array, strips=16,
                                                       flavour=pysvo.FLAVOUR_VALIDATION, want_stats=True)
-    with pytest.raises(pysvo.SvoError):     # a third frame in flight is refused, not silently serialised
-        gpu_dragon.render_frame_async(cams[0], 1280, 720, bufs[len(cams) & 1].array, strips=16)
-    for slot in ((len(cams)) & 1, (len(cams) + 1) & 1):
+    extra = pysvo.PinnedArray((720, 1280), np.uint32)
+    with pytest.raises(pysvo.SvoError):     # a fifth frame in flight is refused, not silently serialised
+        gpu_dragon.render_frame_async(cams[0], 1280, 720, extra.array, strips=16)
+    for j in range(lanes):
+        slot = (len(cams) + j) % lanes
         st = gpu_dragon.frame_wait(pending[slot], want_stats=True)
         got.append((bufs[slot].array.copy(), st))
     assert len(got) == len(cams)
