@@ -154,6 +154,7 @@ struct svo_tree {
     std::mutex mutex;
     std::map<std::tuple<int, int, int>, FramePlan> plans;
     GrowBuffer batchIn, batchOut;
+    std::vector<cudaStream_t> l2WindowStreams;   // streams that already carry the access-policy window (experiment)
 
     svo::TreeDev dev() const { return svo::TreeDev{dWords, nWords, depth}; }
 };
@@ -369,6 +370,42 @@ svo::FrameConsts toDeviceConsts(const svo_frame_constants &c) {
     return f;
 }
 
+// EXPERIMENT SWITCH (off unless SVO_L2_PERSIST_MB is set; measured and left off): an L2
+// access-policy window over the start of the node array, persisting hits. The window is limited to
+// cudaDevAttrMaxAccessPolicyWindowSize bytes and the array is in depth-first block order, so "the upper
+// levels" are not a contiguous range that a window could cover.
+int l2PersistMegabytes() {
+    static const int mb = [] {
+        const char *e = getenv("SVO_L2_PERSIST_MB");
+        return e ? atoi(e) : 0;
+    }();
+    return mb;
+}
+
+void applyL2Window(svo_tree *tree, cudaStream_t s) {
+    const int mb = l2PersistMegabytes();
+    if (mb <= 0) return;
+    for (cudaStream_t seen : tree->l2WindowStreams) if (seen == s) return;
+    tree->l2WindowStreams.push_back(s);
+    int maxWindow = 0, maxPersist = 0;
+    cudaDeviceGetAttribute(&maxWindow, cudaDevAttrMaxAccessPolicyWindowSize, tree->device);
+    cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, tree->device);
+    size_t persist = std::min(size_t(mb) << 20, size_t(maxPersist));
+    if (tree->l2WindowStreams.size() == 1) {
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist);
+        fprintf(stderr, "[svo] L2 persisting window: %zu MB set aside (max %d MB), window <= %d MB\n", persist >> 20,
+                maxPersist >> 20, maxWindow >> 20);
+    }
+    cudaStreamAttrValue attr = {};
+    attr.accessPolicyWindow.base_ptr = tree->dWords;
+    attr.accessPolicyWindow.num_bytes = std::min(size_t(tree->nWords)*sizeof(uint32_t), size_t(maxWindow));
+    attr.accessPolicyWindow.hitRatio = float(std::min(1.0, double(persist)/double(attr.accessPolicyWindow.num_bytes)));
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr);
+    cudaGetLastError();
+}
+
 // Enqueues one frame. The beam pass goes to the tree's high-priority internal stream (unless the
 // caller wants the depth buffer in its own memory, which must be ordered on `stream`), the tile
 // classifier and the fine pass to `stream`. Returns the double-buffer slot used. Caller holds
@@ -382,6 +419,8 @@ int enqueueFrame(svo_tree *tree, FramePlan *plan, const svo_camera *cam, const s
     const int b = int(plan->frameNumber++ % kRing);
     float *depth = userDepth ? userDepth : plan->dDepth[b];
     cudaStream_t cs = userDepth ? stream : tree->coarseStream[b & 1];
+    applyL2Window(tree, stream);
+    applyL2Window(tree, cs);
     uint32_t n = 0;
 
     // the slot's depth buffer, tile list and counters are free once the fine pass of kRing frames ago is done
