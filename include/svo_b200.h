@@ -216,7 +216,11 @@ typedef struct svo_frame_desc {
      * of those stripes (5/4 of 1/tile_world of the corners).
      * Single GPU: tile_rank = 0, tile_world = 1. */
     int32_t tile_rank, tile_world;
-    int32_t reserved[2];
+    /* renderTile's stride (Main.cpp:92-106): 0 or 1 = every pixel is traced; 3 = the reference's
+     * renderHalfSize preview (Main.cpp:161, while the mouse drags): inside every 8x8 tile only pixels at
+     * offsets 0, 3, 6 are traced and each other pixel repeats the traced pixel up-left of it. */
+    int32_t pixel_stride;
+    int32_t reserved;
 } svo_frame_desc;
 
 typedef struct svo_frame_stats {

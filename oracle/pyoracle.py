@@ -107,6 +107,8 @@ class Ref:
         L.svoref_render_frames_subset.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _f32p,
                                                   C.c_int, _u32p, C.c_void_p, C.c_void_p]
         L.svoref_hardware_threads.restype = C.c_int
+        L.svoref_set_half_size.restype = None
+        L.svoref_set_half_size.argtypes = [C.c_int]
 
     # -- trees
     def tree_load(self, path):
@@ -196,9 +198,12 @@ class Ref:
         return hit, t, normal, secs
 
     # -- frame loop
-    def render_frames(self, h, W, H, strips, models, views, threads=None, want_depth=False, strip_modulo=1):
+    def render_frames(self, h, W, H, strips, models, views, threads=None, want_depth=False, strip_modulo=1,
+                      half_size=False):
         """Renders len(models) frames; returns (rgba u32[H,W] of the last frame, depth or None, seconds[f]).
-        strip_modulo > 1 renders only every strip_modulo-th strip (bounded timing sample)."""
+        strip_modulo > 1 renders only every strip_modulo-th strip (bounded timing sample); half_size sets
+        the reference's renderHalfSize (stride-3 preview, Main.cpp:161)."""
+        self.lib.svoref_set_half_size(1 if half_size else 0)
         models = np.ascontiguousarray(models, np.float32).reshape(-1, 16)
         views = np.ascontiguousarray(views, np.float32).reshape(-1, 16)
         nf = models.shape[0]
@@ -211,6 +216,7 @@ class Ref:
             depth = np.zeros(coarse_cells(W, H, strips), np.float32)
         rc = self.lib.svoref_render_frames_subset(h, W, H, strips, int(strip_modulo), nf, models, views, int(threads),
                                                   rgba.reshape(-1), _null_or(depth), _null_or(secs))
+        self.lib.svoref_set_half_size(0)
         if rc != 0:
             raise ValueError("svoref_render_frames: bad arguments")
         return rgba, depth, secs
@@ -308,6 +314,9 @@ class Port:
                                               C.POINTER(Counters), C.c_int]
         L.svo_oracle_tree_walk.restype = C.c_int
         L.svo_oracle_tree_walk.argtypes = [_u32p, C.c_uint64, C.POINTER(TreeStats)]
+        L.svo_oracle_render_frame_strided.restype = C.c_int
+        L.svo_oracle_render_frame_strided.argtypes = [_u32p, C.POINTER(Frame), C.c_int, _u32p, C.c_void_p,
+                                                      C.POINTER(Counters), C.POINTER(Counters), C.c_int]
         L.svo_oracle_build_octree.restype = C.POINTER(C.c_uint32)
         L.svo_oracle_build_octree.argtypes = [_u32p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64), _f32p]
         L.svo_oracle_free.restype = None
@@ -351,16 +360,17 @@ class Port:
         self.lib.svo_oracle_orbit_camera(float(pitch_deg), float(yaw_deg), float(radius), m, v)
         return m, v
 
-    def render_frame(self, words, frame, threads=None, want_depth=False):
-        """Returns (rgba u32[H,W], depth or None, coarse Counters, fine Counters)."""
+    def render_frame(self, words, frame, threads=None, want_depth=False, pixel_stride=1):
+        """Returns (rgba u32[H,W], depth or None, coarse Counters, fine Counters). pixel_stride 3 = the
+        reference's renderHalfSize preview (Main.cpp:101-106, 161)."""
         W, H = frame.width, frame.height
         rgba = np.zeros((H, W), np.uint32)
         depth = np.zeros(coarse_cells(W, H, frame.strips), np.float32) if want_depth else None
         cc, cf = Counters(), Counters()
         if threads is None:
             threads = os.cpu_count() or 1
-        rc = self.lib.svo_oracle_render_frame(words, C.byref(frame), rgba.reshape(-1), _null_or(depth),
-                                              C.byref(cc), C.byref(cf), int(threads))
+        rc = self.lib.svo_oracle_render_frame_strided(words, C.byref(frame), int(pixel_stride), rgba.reshape(-1),
+                                                      _null_or(depth), C.byref(cc), C.byref(cf), int(threads))
         if rc != 0:
             raise ValueError("svo_oracle_render_frame: bad arguments")
         return rgba, depth, cc, cf

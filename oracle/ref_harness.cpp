@@ -266,6 +266,11 @@ void svoref_inv_modelview(const float *model16, const float *view16, float *out1
 int svoref_render_frames_subset(void *h, int W, int H, int strips, int stripModulo, int numFrames, const float *models,
         const float *views, int threads, uint32_t *rgba, float *depth, double *frameSeconds);
 
+/* Main.cpp:69,161: renderHalfSize (set while the mouse drags, Main.cpp:246-253) makes renderTile trace
+ * every third pixel of a tile and replicate it (stride 3). Sticky until changed. */
+static bool g_halfSize = false;
+void svoref_set_half_size(int on) { g_halfSize = on != 0; }
+
 int svoref_render_frames(void *h, int W, int H, int strips, int numFrames, const float *models,
         const float *views, int threads, uint32_t *rgba, float *depth, double *frameSeconds) {
     return svoref_render_frames_subset(h, W, H, strips, 1, numFrames, models, views, threads, rgba, depth, frameSeconds);
@@ -285,7 +290,7 @@ int svoref_render_frames_subset(void *h, int W, int H, int strips, int stripModu
     GWidth = W;
     GHeight = H;
     AspectRatio = GHeight/(float)GWidth; /* Main.cpp:62 */
-    renderHalfSize = false;
+    renderHalfSize = g_halfSize;
     doTerminate = false;
 
     SDL_Surface surface;

@@ -383,6 +383,7 @@ typedef struct {
     const uint64_t *depthOffset;
     atomic_int *next;
     svo_oracle_counters coarse, fine;
+    int pixelStride;
 } FrameJob;
 
 static void rayDir(const svo_oracle_frame *f, float dx, float dy, float *dir) {
@@ -393,13 +394,20 @@ static void rayDir(const svo_oracle_frame *f, float dx, float dy, float *dir) {
     dir[0] *= s; dir[1] *= s; dir[2] *= s;
 }
 
-/* Main.cpp:92-137, stride == 1 */
+/* Main.cpp:92-137; stride 1, or 3 while renderHalfSize is set (Main.cpp:161) */
 static void renderTile(FrameJob *j, int x0, int y0, int x1, int y1, float minT) {
     const svo_oracle_frame *f = j->f;
+    const int stride = j->pixelStride > 1 ? j->pixelStride : 1;
     float dy = f->aspect - y0*f->scale;
     for (int y = y0; y < y1; ++y, dy -= f->scale) {
         float dx = -1.0f + x0*f->scale;
         for (int x = x0; x < x1; ++x, dx += f->scale) {
+            int cornerX = x - ((x - x0) % stride);          /* :101-106 */
+            int cornerY = y - ((y - y0) % stride);
+            if (cornerX != x || cornerY != y) {
+                j->rgba[x + (size_t)y*(size_t)f->width] = j->rgba[cornerX + (size_t)cornerY*(size_t)f->width];
+                continue;
+            }
             float dir[3], org[3];
             rayDir(f, dx, dy, dir);
             for (int a = 0; a < 3; ++a) org[a] = f->pos[a] + dir[a]*minT;
@@ -470,6 +478,11 @@ static void *frameWorker(void *arg) {
 
 int svo_oracle_render_frame(const uint32_t *octree, const svo_oracle_frame *f, uint32_t *rgba,
         float *depth, svo_oracle_counters *coarse, svo_oracle_counters *fine, int threads) {
+    return svo_oracle_render_frame_strided(octree, f, 1, rgba, depth, coarse, fine, threads);
+}
+
+int svo_oracle_render_frame_strided(const uint32_t *octree, const svo_oracle_frame *f, int pixelStride, uint32_t *rgba,
+        float *depth, svo_oracle_counters *coarse, svo_oracle_counters *fine, int threads) {
     if (!octree || !f || !rgba || f->width < 1 || f->height < 1 || f->strips < 1) return -1;
     if (threads < 1) threads = 1;
     if (threads > f->strips) threads = f->strips;
@@ -496,6 +509,7 @@ int svo_oracle_render_frame(const uint32_t *octree, const svo_oracle_frame *f, u
         jobs[k].depth = depth;
         jobs[k].depthOffset = offsets;
         jobs[k].next = &next;
+        jobs[k].pixelStride = pixelStride;
         if (k > 0) pthread_create(&tids[k], NULL, frameWorker, &jobs[k]);
     }
     frameWorker(&jobs[0]);

@@ -88,6 +88,9 @@ float svo_oracle_inv_sqrt(float x);
  * coarse/fine (optional): counters for the two ray classes. */
 int svo_oracle_render_frame(const uint32_t *octree, const svo_oracle_frame *f, uint32_t *rgba,
         float *depth, svo_oracle_counters *coarse, svo_oracle_counters *fine, int threads);
+/* Same with renderTile's pixel stride (Main.cpp:92-106): 1, or 3 = the reference's renderHalfSize preview. */
+int svo_oracle_render_frame_strided(const uint32_t *octree, const svo_oracle_frame *f, int pixelStride, uint32_t *rgba,
+        float *depth, svo_oracle_counters *coarse, svo_oracle_counters *fine, int threads);
 
 /* Kernel design tool: per-ray loop-trip traces of the fine pass in GPU warp order (see svo_oracle.c). */
 int64_t svo_oracle_trace_fine_warps(const uint32_t *octree, const svo_oracle_frame *f, int tileStride,

@@ -356,6 +356,8 @@ int checkDesc(const svo_frame_desc *desc) {
         return fail(SVO_ERR_INVALID_ARGUMENT, "unknown flavour %d", desc->flavour);
     if (desc->tile_world < 1 || desc->tile_rank < 0 || desc->tile_rank >= desc->tile_world)
         return fail(SVO_ERR_INVALID_ARGUMENT, "bad tile interleave rank %d of %d", desc->tile_rank, desc->tile_world);
+    if (desc->pixel_stride < 0 || desc->pixel_stride > 8)
+        return fail(SVO_ERR_INVALID_ARGUMENT, "pixel_stride must be in [0, 8] (got %d)", desc->pixel_stride);
     return SVO_OK;
 }
 
@@ -435,11 +437,11 @@ int enqueueFrame(svo_tree *tree, FramePlan *plan, const svo_camera *cam, const s
         SVO_CUDA(cudaStreamWaitEvent(stream, plan->coarseDone[b], 0));
     }
     if (wantStats) SVO_CUDA(cudaEventRecord(plan->timing[b][2], stream));
-    SVO_CUDA(svo::launchClassifyTiles(plan->dev, f, depth, dRgba, desc->tile_rank, desc->tile_world, plan->dTiles[b],
-                                      plan->dCounters[b], stream));
+    SVO_CUDA(svo::launchClassifyTiles(plan->dev, f, depth, dRgba, desc->tile_rank, desc->tile_world, desc->pixel_stride,
+                                      plan->dTiles[b], plan->dCounters[b], stream));
     ++n;
     SVO_CUDA(svo::launchFinePass(tree->dev(), plan->dev, f, desc->flavour, plan->dTiles[b], plan->dCounters[b], dRgba,
-                                 desc->tile_rank, desc->tile_world, stream));
+                                 desc->tile_rank, desc->tile_world, desc->pixel_stride, stream));
     ++n;
     if (wantStats) {
         SVO_CUDA(cudaEventRecord(plan->timing[b][3], stream));
@@ -917,7 +919,7 @@ int svo_frame_constants_from_camera(const svo_camera *cam, const float center[3]
 
 int svo_frame_get_layout(int width, int height, int strips, svo_frame_layout *out) {
     if (!out) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_frame_get_layout: null argument");
-    svo_frame_desc d = {width, height, strips, SVO_FLAVOUR_VALIDATION, 0, 1, {0, 0}};
+    svo_frame_desc d = {width, height, strips, SVO_FLAVOUR_VALIDATION, 0, 1, 0, 0};
     int st = checkDesc(&d);
     if (st != SVO_OK) return st;
     svo::FramePlanDev p{};
@@ -934,7 +936,7 @@ int svo_frame_get_layout(int width, int height, int strips, svo_frame_layout *ou
 }
 
 int svo_frame_tile_owner(int width, int height, int strips, int tile, int tile_world) {
-    svo_frame_desc d = {width, height, strips, SVO_FLAVOUR_VALIDATION, 0, tile_world, {0, 0}};
+    svo_frame_desc d = {width, height, strips, SVO_FLAVOUR_VALIDATION, 0, tile_world, 0, 0};
     if (checkDesc(&d) != SVO_OK) return -1;
     svo::FramePlanDev p{};
     planGeometry(width, height, strips, p);
@@ -947,7 +949,7 @@ int svo_frame_tile_owner(int width, int height, int strips, int tile, int tile_w
 
 int svo_frame_tile_rect(int width, int height, int strips, int tile, int32_t rect[4]) {
     if (!rect) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_frame_tile_rect: null argument");
-    svo_frame_desc d = {width, height, strips, SVO_FLAVOUR_VALIDATION, 0, 1, {0, 0}};
+    svo_frame_desc d = {width, height, strips, SVO_FLAVOUR_VALIDATION, 0, 1, 0, 0};
     int st = checkDesc(&d);
     if (st != SVO_OK) return st;
     svo::FramePlanDev p{};

@@ -107,7 +107,7 @@ coarsePassKernel(const uint32_t *__restrict__ octree, FramePlanDev plan, FrameCo
 
 __global__ void __launch_bounds__(kClassifyThreads)
 classifyTilesKernel(FramePlanDev plan, float beamBias, const float *__restrict__ depth, uint32_t *__restrict__ rgba,
-                    int tileRank, int tileWorld, int tileRun, int ownedCols, int ownedTiles,
+                    int tileRank, int tileWorld, int tileRun, int ownedCols, int ownedTiles, int pixelStride,
                     TileRecord *__restrict__ tiles, FrameCounters *__restrict__ counters) {
     int k = blockIdx.x*blockDim.x + threadIdx.x;
     bool active = k < ownedTiles;
@@ -136,7 +136,9 @@ classifyTilesKernel(FramePlanDev plan, float beamBias, const float *__restrict__
     unsigned mask = __ballot_sync(0xffffffffu, rendered);
     int w = min(x0 + 8, plan.width) - x0;
     int h = min(y0 + 8, yEnd) - y0;
-    unsigned pixels = __reduce_add_sync(0xffffffffu, rendered ? unsigned(w*h) : 0u);
+    // fine rays of the tile: every pixelStride-th pixel of every pixelStride-th row (Main.cpp:101-106)
+    const int raysX = (w + pixelStride - 1)/pixelStride, raysY = (h + pixelStride - 1)/pixelStride;
+    unsigned pixels = __reduce_add_sync(0xffffffffu, rendered ? unsigned(raysX*raysY) : 0u);
     unsigned base = 0;
     if (lane == 0 && mask) {
         base = atomicAdd(&counters->tilesRendered, unsigned(__popc(mask)));
@@ -206,6 +208,47 @@ finePassKernel(const uint32_t *__restrict__ octree, FramePlanDev plan, FrameCons
         if (code == kMiss) colour = 0xFF000000u;                // Vec3() -> black, Main.cpp:117
         rgba[size_t(py)*size_t(plan.width) + px] = colour;
     }
+}
+
+// renderTile with stride > 1 (the reference's renderHalfSize preview: stride 3, Main.cpp:101-106,161):
+// only pixels whose offsets inside the tile are multiples of the stride are traced; every other pixel
+// copies its block's corner pixel. One block per tile: the corner colours go through shared memory. Every
+// thread runs the traversal (its __syncwarp needs whole warps) -- the ones without a pixel of their own
+// on a ray that starts behind the volume and leaves it in two trips.
+template <bool FAST, typename IdxT>
+__global__ void __launch_bounds__(kTileThreads)
+finePassStridedKernel(const uint32_t *__restrict__ octree, FramePlanDev plan, FrameConsts f,
+                      const TileRecord *__restrict__ tiles, const FrameCounters *__restrict__ counters,
+                      uint32_t *__restrict__ rgba, int pixelStride) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ uint32_t corner[64];
+    SmemStack<IdxT, kTileThreads> stack;
+    stack.init(smem);
+    const unsigned tile = blockIdx.x;
+    if (tile >= counters->tilesRendered) return;
+    const uint4 rec = __ldg(reinterpret_cast<const uint4 *>(tiles) + tile);
+    const int lx = int(threadIdx.x & 7), ly = int(threadIdx.x >> 3);
+    const int px = int(rec.x & 0xFFFFu) + lx, py = int(rec.x >> 16) + ly;
+    const bool inside = px < plan.width && py < int(rec.y);
+    const bool traces = inside && lx % pixelStride == 0 && ly % pixelStride == 0;
+    const float startT = __uint_as_float(rec.z);
+
+    float rx = 1.0f, ry = 1.0f, rz = 1.0f, ox = 3.0f, oy = 3.0f, oz = 3.0f;
+    if (traces) {
+        rayDirection(f, __ldg(plan.dxFine + px), __ldg(plan.dyFine + py), rx, ry, rz);
+        ox = addRn(f.posX, mulRn(rx, startT));
+        oy = addRn(f.posY, mulRn(ry, startT));
+        oz = addRn(f.posZ, mulRn(rz, startT));
+    }
+    float tHit;
+    uint64_t vox;
+    const int code = raymarch<FAST, false, IdxT, kTileThreads>(octree, ox, oy, oz, rx, ry, rz, 0.0f, stack, tHit, vox);
+    const uint32_t material = ldNode(octree + IdxT(vox));
+    uint32_t colour = packGrey(shadeMaterial(material, rx, ry, rz, f.lightX, f.lightY, f.lightZ));
+    if (code == kMiss) colour = 0xFF000000u;
+    if (traces) corner[threadIdx.x] = colour;
+    __syncthreads();
+    if (inside) rgba[size_t(py)*size_t(plan.width) + px] = corner[(ly - ly % pixelStride)*8 + (lx - lx % pixelStride)];
 }
 
 // 64-bit word indices are needed from 2^32 words (16 GiB) on; SVO_FORCE_WIDE_INDEX=1 selects that
@@ -289,8 +332,15 @@ cudaError_t launchCoarseT(const TreeDev &tree, const FramePlanDev &plan, const F
 template <bool FAST, typename IdxT>
 cudaError_t launchFineT(const TreeDev &tree, const FramePlanDev &plan, const FrameConsts &consts,
                         const TileRecord *tiles, const FrameCounters *counters, uint32_t *rgba, int owned,
-                        cudaStream_t stream) {
+                        int pixelStride, cudaStream_t stream) {
     size_t smem = SmemStack<IdxT, kTileThreads>::bytes(stackSlots(tree));
+    if (pixelStride > 1) {
+        auto strided = finePassStridedKernel<FAST, IdxT>;
+        cudaError_t es = ensureSmem(strided, smem);
+        if (es != cudaSuccess) return es;
+        strided<<<owned, kTileThreads, smem, stream>>>(tree.words, plan, consts, tiles, counters, rgba, pixelStride);
+        return cudaGetLastError();
+    }
     auto kernel = finePassKernel<FAST, IdxT>;
     cudaError_t e = ensureSmem(kernel, smem);
     if (e != cudaSuccess) return e;
@@ -330,27 +380,27 @@ cudaError_t launchCoarsePass(const TreeDev &tree, const FramePlanDev &plan, cons
 }
 
 cudaError_t launchClassifyTiles(const FramePlanDev &plan, const FrameConsts &consts, const float *depth,
-                                uint32_t *rgba, int tileRank, int tileWorld, TileRecord *tiles,
+                                uint32_t *rgba, int tileRank, int tileWorld, int pixelStride, TileRecord *tiles,
                                 FrameCounters *counters, cudaStream_t stream) {
     int owned = ownedTiles(plan, tileRank, tileWorld);
     if (owned <= 0) return cudaSuccess;
     classifyTilesKernel<<<(owned + kClassifyThreads - 1)/kClassifyThreads, kClassifyThreads, 0, stream>>>(
         plan, consts.beamBias, depth, rgba, tileRank, tileWorld, tileRunLength(tileWorld),
-        ownedCols(plan, tileRank, tileWorld), owned, tiles, counters);
+        ownedCols(plan, tileRank, tileWorld), owned, pixelStride > 1 ? pixelStride : 1, tiles, counters);
     return cudaGetLastError();
 }
 
 cudaError_t launchFinePass(const TreeDev &tree, const FramePlanDev &plan, const FrameConsts &consts, int flavour,
                            const TileRecord *tiles, const FrameCounters *counters, uint32_t *rgba,
-                           int tileRank, int tileWorld, cudaStream_t stream) {
+                           int tileRank, int tileWorld, int pixelStride, cudaStream_t stream) {
     int owned = ownedTiles(plan, tileRank, tileWorld);
     if (owned <= 0) return cudaSuccess;
     bool wide = wideIndex(tree);
     if (flavour != 0)
-        return wide ? launchFineT<true, uint64_t>(tree, plan, consts, tiles, counters, rgba, owned, stream)
-                    : launchFineT<true, uint32_t>(tree, plan, consts, tiles, counters, rgba, owned, stream);
-    return wide ? launchFineT<false, uint64_t>(tree, plan, consts, tiles, counters, rgba, owned, stream)
-                : launchFineT<false, uint32_t>(tree, plan, consts, tiles, counters, rgba, owned, stream);
+        return wide ? launchFineT<true, uint64_t>(tree, plan, consts, tiles, counters, rgba, owned, pixelStride, stream)
+                    : launchFineT<true, uint32_t>(tree, plan, consts, tiles, counters, rgba, owned, pixelStride, stream);
+    return wide ? launchFineT<false, uint64_t>(tree, plan, consts, tiles, counters, rgba, owned, pixelStride, stream)
+                : launchFineT<false, uint32_t>(tree, plan, consts, tiles, counters, rgba, owned, pixelStride, stream);
 }
 
 } // namespace svo

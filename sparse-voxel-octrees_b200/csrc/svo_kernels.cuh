@@ -69,12 +69,13 @@ cudaError_t launchCoarsePass(const TreeDev &tree, const FramePlanDev &plan, cons
 // Per owned tile: min of the four corner depths; skipped tiles are zero-filled (the strip memset,
 // Main.cpp:165), rendered tiles are appended to `tiles` (capacity = owned tiles) and counted.
 cudaError_t launchClassifyTiles(const FramePlanDev &plan, const FrameConsts &consts, const float *depth,
-                                uint32_t *rgba, int tileRank, int tileWorld, TileRecord *tiles,
+                                uint32_t *rgba, int tileRank, int tileWorld, int pixelStride, TileRecord *tiles,
                                 FrameCounters *counters, cudaStream_t stream);
 
 // Fine pass over the tile list (grid covers the worst case; blocks past the list length exit).
+// pixelStride > 1: renderTile's preview mode (Main.cpp:101-106), one ray per stride x stride block of a tile.
 cudaError_t launchFinePass(const TreeDev &tree, const FramePlanDev &plan, const FrameConsts &consts, int flavour,
                            const TileRecord *tiles, const FrameCounters *counters, uint32_t *rgba,
-                           int tileRank, int tileWorld, cudaStream_t stream);
+                           int tileRank, int tileWorld, int pixelStride, cudaStream_t stream);
 
 } // namespace svo

@@ -110,9 +110,10 @@ public:
     }
 
     // One frame of the reference's renderBatch loop over `strips` strips (Main.cpp:139-202, 351-362).
+    // pixelStride 3 = renderTile's preview mode while dragging (Main.cpp:101-106, 161).
     svo_frame_stats renderFrame(const svo_camera &cam, int width, int height, int strips, uint32 *rgba,
-                                int flavour = SVO_FLAVOUR_FAST) {
-        svo_frame_desc desc = {width, height, strips, flavour, 0, 1, {0, 0}};
+                                int flavour = SVO_FLAVOUR_FAST, int pixelStride = 1) {
+        svo_frame_desc desc = {width, height, strips, flavour, 0, 1, pixelStride, 0};
         svo_frame_stats stats;
         check(svo_render_frame(_tree, &cam, &desc, rgba, 0, &stats), "VoxelOctree::renderFrame");
         return stats;

@@ -3,7 +3,7 @@
 // the GPU with the reference's strip/tile/beam semantics and writes PPM images.
 //
 //   svo_headless <in.oct> [--size WxH] [--strips N] [--frames K] [--radius R] [--pitch P]
-//                [--yaw0 Y] [--yaw-step S] [--validation] [--out prefix]
+//                [--yaw0 Y] [--yaw-step S] [--validation] [--preview] [--out prefix]
 //   svo_headless -builder <in.voxel> <out.oct>
 //
 // The second form is the reference's `-builder` mode for a raw voxel volume (the on-disk path of
@@ -61,6 +61,7 @@ int main(int argc, char **argv) {
     }
     int w = 1280, h = 720, strips = 16, frames = 1, flavour = SVO_FLAVOUR_FAST; /* Main.cpp:57-60 defaults */
     float radius = 1.0f, pitch = 0.0f, yaw0 = 0.0f, yawStep = 3.6f;
+    int stride = 1;
     std::string out;
     for (int i = 2; i < argc; ++i) {
         std::string a = argv[i];
@@ -73,6 +74,7 @@ int main(int argc, char **argv) {
         else if (a == "--yaw0") yaw0 = float(atof(next()));
         else if (a == "--yaw-step") yawStep = float(atof(next()));
         else if (a == "--validation") flavour = SVO_FLAVOUR_VALIDATION;
+        else if (a == "--preview") stride = 3;   /* the reference's renderHalfSize while dragging, Main.cpp:161 */
         else if (a == "--out") out = next();
         else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
@@ -87,7 +89,7 @@ int main(int argc, char **argv) {
             svo_camera cam;
             svo_orbit_camera(pitch, yaw0 + yawStep*k, radius, &cam);
             auto t0 = std::chrono::steady_clock::now();
-            svo_frame_stats st = tree.renderFrame(cam, w, h, strips, rgba, flavour);
+            svo_frame_stats st = tree.renderFrame(cam, w, h, strips, rgba, flavour, stride);
             double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
             if (k > 0 || frames == 1) { totalMs += ms; rays += st.coarse_rays + st.fine_rays; }
             if (!out.empty()) writePpm(out + "_" + std::to_string(k) + ".ppm", rgba, w, h);

@@ -64,7 +64,7 @@ class FrameConstants(C.Structure):
 
 class FrameDesc(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("strips", C.c_int32), ("flavour", C.c_int32),
-                ("tile_rank", C.c_int32), ("tile_world", C.c_int32), ("reserved", C.c_int32 * 2)]
+                ("tile_rank", C.c_int32), ("tile_world", C.c_int32), ("pixel_stride", C.c_int32), ("reserved", C.c_int32)]
 
 
 class FrameStats(C.Structure):
@@ -437,9 +437,10 @@ class VoxelOctree:
                                                vp(d_voxel or None), vp(stream or None)))
 
     def render_frame(self, cam: Camera, width, height, strips=16, flavour=FLAVOUR_VALIDATION, tile_rank=0,
-                     tile_world=1, rgba=None, want_depth=False, want_stats=True):
-        """HOST buffers (copies inside, synchronous). Returns (rgba uint32[H,W], depth|None, FrameStats|None)."""
-        desc = FrameDesc(width, height, strips, flavour, tile_rank, tile_world)
+                     tile_world=1, rgba=None, want_depth=False, want_stats=True, pixel_stride=1):
+        """HOST buffers (copies inside, synchronous). Returns (rgba uint32[H,W], depth|None, FrameStats|None).
+        pixel_stride=3 is the reference's renderHalfSize preview (Main.cpp:101-106, 161)."""
+        desc = FrameDesc(width, height, strips, flavour, tile_rank, tile_world, pixel_stride)
         if rgba is None:
             rgba = np.empty((height, width), np.uint32)
         depth = np.empty(coarse_cells(width, height, strips), np.float32) if want_depth else None
@@ -450,7 +451,7 @@ class VoxelOctree:
 
     def render_frame_async(self, cam: Camera, width, height, rgba, strips=16, flavour=FLAVOUR_FAST, depth=None,
                            want_stats=False):
-        """Pipelined host-buffer variant: returns a (desc, ticket) pair for frame_wait. Up to two in flight."""
+        """Pipelined host-buffer variant: returns a (desc, ticket) pair for frame_wait. Up to four in flight."""
         desc = FrameDesc(width, height, strips, flavour, 0, 1)
         ticket = C.c_int(0)
         _check(lib().svo_render_frame_async(self._h, C.byref(cam), C.byref(desc), _ptr(rgba), _ptr(depth),
@@ -464,9 +465,9 @@ class VoxelOctree:
         return stats
 
     def render_frame_device(self, cam: Camera, width, height, d_rgba, strips=16, flavour=FLAVOUR_FAST, tile_rank=0,
-                            tile_world=1, d_depth=0, stream=0, want_stats=False):
+                            tile_world=1, d_depth=0, stream=0, want_stats=False, pixel_stride=1):
         """DEVICE framebuffer pointer (int; may be a peer mapping); asynchronous unless want_stats."""
-        desc = FrameDesc(width, height, strips, flavour, tile_rank, tile_world)
+        desc = FrameDesc(width, height, strips, flavour, tile_rank, tile_world, pixel_stride)
         stats = FrameStats() if want_stats else None
         vp = C.c_void_p
         _check(lib().svo_render_frame_device(self._h, C.byref(cam), C.byref(desc), vp(d_rgba), vp(d_depth or None),

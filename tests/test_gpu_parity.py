@@ -360,3 +360,32 @@ def test_cpp_facade_and_headless_driver(pysvo, port, gpu_dragon, dragon_words, t
                                          flavour=pysvo.FLAVOUR_VALIDATION)
     assert np.array_equal(img[..., 0], (want & 0xFF).astype(np.uint8))
     assert np.array_equal(img[..., 2], ((want >> 16) & 0xFF).astype(np.uint8))
+
+
+@pytest.mark.parametrize("shape", [(1280, 720, 16), (333, 187, 5), (64, 40, 3)])
+def test_frame_preview_stride_vs_oracle(pysvo, port, ref, gpu_dragon, dragon_words, shape):
+    """renderTile's stride-3 mode (the reference's renderHalfSize while dragging, Main.cpp:101-106, 161): one
+    ray per 3x3 block of a tile, replicated. Bit-exact against the restatement and the reference's own object
+    code; stride 1 and 0 are the normal frame; fine-ray counts follow the stride."""
+    W, H, S = shape
+    words, center = dragon_words
+    h = ref.tree_from_words(words, center)
+    for cam_args in [(20.0, 135.0, 0.5), (0.0, 0.0, 1.0)]:
+        cam = pysvo.orbit_camera(*cam_args)
+        model, view = np.array(cam.model[:], np.float32), np.array(cam.view[:], np.float32)
+        f = port.frame_constants(model, view, center, W, H, S)
+        want, _, cc, cf = port.render_frame(words, f, pixel_stride=3)
+        theirs, _, _ = ref.render_frames(h, W, H, S, model, view, half_size=True)
+        assert np.array_equal(want, theirs)
+        for flavour in (pysvo.FLAVOUR_VALIDATION, pysvo.FLAVOUR_FAST):
+            got, _, st = gpu_dragon.render_frame(cam, W, H, strips=S, flavour=flavour, pixel_stride=3)
+            assert np.array_equal(got, want), f"{int((got != want).sum())} pixels differ"
+            assert st.fine_rays == cf.rays and st.coarse_rays == cc.rays
+        full, _, _ = gpu_dragon.render_frame(cam, W, H, strips=S, flavour=pysvo.FLAVOUR_VALIDATION)
+        zero, _, _ = gpu_dragon.render_frame(cam, W, H, strips=S, flavour=pysvo.FLAVOUR_VALIDATION, pixel_stride=0)
+        assert np.array_equal(full, zero) and not np.array_equal(full, want)
+        other, _, _ = gpu_dragon.render_frame(cam, W, H, strips=S, flavour=pysvo.FLAVOUR_VALIDATION, pixel_stride=2)
+        assert np.array_equal(other, port.render_frame(words, f, pixel_stride=2)[0])
+    ref.tree_destroy(h)
+    with pytest.raises(pysvo.SvoError):
+        gpu_dragon.render_frame(pysvo.orbit_camera(0, 0, 1), W, H, strips=S, pixel_stride=9)

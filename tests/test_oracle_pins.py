@@ -191,3 +191,19 @@ def test_builder_port_equals_reference_object_code(port, ref, tmp_path):
             assert np.array_equal(ref.tree_words_view(hnd), got), (case, mem)
             assert np.array_equal(ref.tree_center(hnd), center)
             ref.tree_destroy(hnd)
+
+
+def test_port_preview_stride_equals_reference(port, ref, dragon_words):
+    """renderTile with stride 3 (renderHalfSize, Main.cpp:101-106, 161): restatement == reference object code."""
+    words, center = dragon_words
+    h = ref.tree_from_words(words, center)
+    for cam in [(0.0, 0.0, 1.0), (20.0, 135.0, 0.5)]:
+        for (W, H, S) in [(320, 180, 4), (333, 187, 5)]:
+            model, view = ref.orbit_camera(*cam)
+            theirs, _, _ = ref.render_frames(h, W, H, S, model, view, half_size=True)
+            f = port.frame_constants(model, view, center, W, H, S)
+            ours, _, _, cf = port.render_frame(words, f, pixel_stride=3)
+            full, _, _, cf_full = port.render_frame(words, f)
+            assert np.array_equal(ours, theirs)
+            assert cf.rays < cf_full.rays / 6 and not np.array_equal(ours, full)
+    ref.tree_destroy(h)
