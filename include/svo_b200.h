@@ -179,6 +179,15 @@ SVO_API int svo_raymarch_batch_device(svo_tree *tree, uint64_t n, const float *d
 SVO_API int svo_raymarch(svo_tree *tree, const float o[3], const float d[3], float ray_scale,
                          uint32_t *normal, float *t, int *hit_out);
 
+/* ---- shading: shade + pixel pack (Main.cpp:81-90, 128-132), batched ---------- *
+ * For ray i with hit code hit[i] (NULL = every ray hit), material word normal[i] (Util.hpp:86-100) and
+ * direction d[3i..] (the direction raymarch was called with), rgba[i] = the reference's pixel:
+ * 0xFF000000 | g << 16 | g << 8 | g with g = uint32(min(shade, 1) * 255.0); misses give 0xFF000000, the
+ * value renderTile stores for them (Main.cpp:115-118). `light` is the per-frame light vector
+ * (Main.cpp:163; svo_frame_constants.light). Host buffers; runs on the tree's device. */
+SVO_API int svo_shade_batch(svo_tree *tree, uint64_t n, const uint8_t *hit, const uint32_t *normal, const float *d,
+                            const float light[3], uint32_t *rgba);
+
 /* ---- camera: what renderBatch reads from the matrix stacks ------------------ */
 
 typedef struct svo_camera {

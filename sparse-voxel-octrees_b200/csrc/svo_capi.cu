@@ -1059,6 +1059,35 @@ int svo_render_frame(svo_tree *tree, const svo_camera *cam, const svo_frame_desc
     return svo_frame_wait(tree, desc, ticket, stats);
 }
 
+/* ---- shading ------------------------------------------------------------------ */
+
+int svo_shade_batch(svo_tree *tree, uint64_t n, const uint8_t *hit, const uint32_t *normal, const float *d,
+                    const float light[3], uint32_t *rgba) {
+    if (!tree || !light || (n && (!normal || !d || !rgba))) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_shade_batch: null argument");
+    if (n == 0) return SVO_OK;
+    SVO_DEVICE(tree->device);
+    std::lock_guard<std::mutex> lock(tree->mutex);
+    const uint64_t chunk = 4ull << 20;
+    const size_t inBytes = size_t(std::min(n, chunk))*(1 + 4 + 12), outBytes = size_t(std::min(n, chunk))*4;
+    SVO_CUDA(tree->batchIn.reserve(inBytes));
+    SVO_CUDA(tree->batchOut.reserve(outBytes));
+    for (uint64_t first = 0; first < n; first += chunk) {
+        const uint64_t m = std::min(chunk, n - first);
+        float *dD = static_cast<float *>(tree->batchIn.ptr);
+        uint32_t *dNormal = reinterpret_cast<uint32_t *>(dD + 3*m);
+        uint8_t *dHit = reinterpret_cast<uint8_t *>(dNormal + m);
+        uint32_t *dRgba = static_cast<uint32_t *>(tree->batchOut.ptr);
+        cudaStream_t s = tree->stream;
+        SVO_CUDA(cudaMemcpyAsync(dD, d + 3*first, size_t(m)*12, cudaMemcpyHostToDevice, s));
+        SVO_CUDA(cudaMemcpyAsync(dNormal, normal + first, size_t(m)*4, cudaMemcpyHostToDevice, s));
+        if (hit) SVO_CUDA(cudaMemcpyAsync(dHit, hit + first, size_t(m), cudaMemcpyHostToDevice, s));
+        SVO_CUDA(svo::launchShadeBatch(m, hit ? dHit : nullptr, dNormal, dD, light, dRgba, s));
+        SVO_CUDA(cudaMemcpyAsync(rgba + first, dRgba, size_t(m)*4, cudaMemcpyDeviceToHost, s));
+        SVO_CUDA(cudaStreamSynchronize(s));
+    }
+    return SVO_OK;
+}
+
 /* ---- device memory + peer mapping -------------------------------------------- */
 
 int svo_device_alloc(int device, size_t bytes, void **out) {

@@ -52,6 +52,18 @@ raymarchBatchKernel(const uint32_t *__restrict__ octree, uint64_t n, const float
     if (voxel) voxel[i] = vox;
 }
 
+// shade + pack for arbitrary rays (Main.cpp:81-90, 128-132)
+__global__ void __launch_bounds__(kBatchThreads)
+shadeBatchKernel(uint64_t n, const uint8_t *__restrict__ hit, const uint32_t *__restrict__ normal,
+                 const float *__restrict__ d, float lx, float ly, float lz, uint32_t *__restrict__ rgba) {
+    uint64_t i = uint64_t(blockIdx.x)*blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t colour = 0xFF000000u;
+    if (!hit || hit[i] != kMiss)
+        colour = packGrey(shadeMaterial(__ldg(normal + i), __ldg(d + 3*i), __ldg(d + 3*i + 1), __ldg(d + 3*i + 2), lx, ly, lz));
+    rgba[i] = colour;
+}
+
 // ---- K2 -------------------------------------------------------------------
 
 // Tile (tx, ty) belongs to rank tx % world (vertical stripes one tile wide), so a rank needs only
@@ -364,6 +376,15 @@ cudaError_t launchRaymarchBatch(const TreeDev &tree, uint64_t n, const float *o,
     if (fast) return lod ? SVO_BATCH(true, true) : SVO_BATCH(true, false);
     return lod ? SVO_BATCH(false, true) : SVO_BATCH(false, false);
 #undef SVO_BATCH
+}
+
+cudaError_t launchShadeBatch(uint64_t n, const uint8_t *hit, const uint32_t *normal, const float *d, const float light[3],
+                             uint32_t *rgba, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    uint64_t blocks = (n + kBatchThreads - 1)/kBatchThreads;
+    if (blocks > 0x7FFFFFFFull) return cudaErrorInvalidValue;
+    shadeBatchKernel<<<unsigned(blocks), kBatchThreads, 0, stream>>>(n, hit, normal, d, light[0], light[1], light[2], rgba);
+    return cudaGetLastError();
 }
 
 cudaError_t launchCoarsePass(const TreeDev &tree, const FramePlanDev &plan, const FrameConsts &consts, int flavour,

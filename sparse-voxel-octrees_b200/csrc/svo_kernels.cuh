@@ -56,6 +56,10 @@ cudaError_t launchRaymarchBatch(const TreeDev &tree, uint64_t n, const float *o,
                                 int flavour, uint8_t *hit, float *t, uint32_t *normal, uint64_t *voxel,
                                 cudaStream_t stream);
 
+// shade + pack per ray (Main.cpp:81-90, 128-132); hit may be null (every ray shaded). Device pointers.
+cudaError_t launchShadeBatch(uint64_t n, const uint8_t *hit, const uint32_t *normal, const float *d, const float light[3],
+                             uint32_t *rgba, cudaStream_t stream);
+
 // Multi-GPU tile interleave: tile column tx belongs to rank (tx / run) % world.
 int tileRunLength(int tileWorld);
 int ownedTileColumns(int tileCols, int tileRank, int tileWorld);

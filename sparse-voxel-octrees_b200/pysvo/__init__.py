@@ -140,6 +140,7 @@ def lib():
         "svo_raymarch_batch": (i32, [vp, u64, vp, vp, f32, i32, vp, vp, vp, vp]),
         "svo_raymarch_batch_device": (i32, [vp, u64, vp, vp, f32, i32, vp, vp, vp, vp, vp]),
         "svo_raymarch": (i32, [vp, P(f32), P(f32), f32, P(C.c_uint32), P(f32), P(i32)]),
+        "svo_shade_batch": (i32, [vp, u64, vp, vp, vp, P(f32), vp]),
         "svo_orbit_camera": (None, [f32, f32, f32, P(Camera)]),
         "svo_frame_constants_from_camera": (i32, [P(Camera), P(f32), i32, i32, i32, P(FrameConstants)]),
         "svo_frame_get_layout": (i32, [i32, i32, i32, P(FrameLayout)]),
@@ -435,6 +436,16 @@ class VoxelOctree:
         _check(lib().svo_raymarch_batch_device(self._h, int(n), vp(d_o), vp(d_d), float(ray_scale), int(flavour),
                                                vp(d_hit or None), vp(d_t or None), vp(d_normal or None),
                                                vp(d_voxel or None), vp(stream or None)))
+
+    def shade_batch(self, normal, d, light, hit=None):
+        """shade + pixel pack per ray (Main.cpp:81-90, 128-132) -> rgba uint32[n]."""
+        normal = np.ascontiguousarray(normal, np.uint32).reshape(-1)
+        d = np.ascontiguousarray(d, np.float32).reshape(-1, 3)
+        if hit is not None:
+            hit = np.ascontiguousarray(hit, np.uint8).reshape(-1)
+        rgba = np.empty(normal.size, np.uint32)
+        _check(lib().svo_shade_batch(self._h, normal.size, _ptr(hit), _ptr(normal), _ptr(d), _f3(light), _ptr(rgba)))
+        return rgba
 
     def render_frame(self, cam: Camera, width, height, strips=16, flavour=FLAVOUR_VALIDATION, tile_rank=0,
                      tile_world=1, rgba=None, want_depth=False, want_stats=True, pixel_stride=1):

@@ -389,3 +389,25 @@ def test_frame_preview_stride_vs_oracle(pysvo, port, ref, gpu_dragon, dragon_wor
     ref.tree_destroy(h)
     with pytest.raises(pysvo.SvoError):
         gpu_dragon.render_frame(pysvo.orbit_camera(0, 0, 1), W, H, strips=S, pixel_stride=9)
+
+
+def test_shade_batch_vs_oracle(pysvo, port, gpu_dragon, dragon_words):
+    """shade + decompressMaterial + pixel pack (Main.cpp:81-90, 128-132, Util.hpp:86-100) per ray: material
+    words from real hits and random words (all faces / signs / shades), bit-exact."""
+    words, center = dragon_words
+    rng = np.random.default_rng(17)
+    n = 6000
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+    normal = rng.integers(0, 2**32, n, dtype=np.uint64).astype(np.uint32)
+    leaves = words[words > 0xFFFF][:n // 2]
+    normal[:leaves.size] = leaves
+    hit = rng.integers(0, 3, n).astype(np.uint8)
+    light = np.array([-0.57735026, 0.57735026, -0.57735026], np.float32)
+    got = gpu_dragon.shade_batch(normal, d, light, hit)
+    want = np.array([port.pack(port.shade(int(normal[i]), d[i], light)) if hit[i] else 0xFF000000 for i in range(n)],
+                    np.uint32)
+    assert np.array_equal(got, want)
+    every = gpu_dragon.shade_batch(normal, d, light)          # hit == NULL: every ray is shaded
+    assert np.array_equal(every[hit > 0], want[hit > 0]) and (every[hit == 0] != 0).all()
+    assert gpu_dragon.shade_batch(np.zeros(0, np.uint32), np.zeros((0, 3), np.float32), light).size == 0
