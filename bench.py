@@ -305,6 +305,8 @@ def run_own_ao(args, w):
     words, center = pysvo.oct_read(w["path"])
     tree = pysvo.VoxelOctree(words=words, center=center, device=local_rank)
     flavour = pysvo.FLAVOUR_VALIDATION if args.validation else pysvo.FLAVOUR_FAST
+    if not os.environ.get("SVO_BENCH_NO_COHERENCE_ORDER"):     # (experiment switch, never set by default)
+        flavour |= pysvo.BATCH_COHERENCE_ORDER               # direction-binned thread order, inside the timed call
     ao_o, ao_d = ao_workload_rays(w, tree, words, center)
     n_total = ao_o.shape[0]
     lo, hi = n_total * rank // world, n_total * (rank + 1) // world
@@ -396,11 +398,14 @@ def run_own_ao(args, w):
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": w["name"], "description": w["text"], "rays": n_total, "spp": w["spp"],
                        "flavour": "validation" if args.validation else "fast",
+                       "thread_order": "direction-binned (SVO_BATCH_COHERENCE_ORDER: key pass + one 6-bit radix pass "
+                                       "inside every timed call)" if flavour & pysvo.BATCH_COHERENCE_ORDER else "submission order",
                        "l2": f"no flush: ray + result arrays {n_total * 41 / 1e6:.0f} MB per step exceed the 126 MB L2",
                        "parallelism": "rays sharded contiguously over ranks, octree replicated" if world > 1 else "single GPU"},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": n_total * 24, "d2h_bytes_per_step": n_total * 9,
                     "steps": e2e_steps, "note": "svo_raymarch_batch with pinned host arrays: 2 Mi-ray chunks alternate between two streams"},
-            "gpu_launches": steps * world, "clocks": sampler.summary(t_begin, t_end),
+            "gpu_launches": steps * world * (1 + (4 if flavour & pysvo.BATCH_COHERENCE_ORDER else 0)),
+            "clocks": sampler.summary(t_begin, t_end),
             "parity": {"identical_rays_fast_vs_oracle": identical, "sample": sample},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": "raymarchBatchKernel<FAST>", "peak_source": peak_src,

@@ -62,6 +62,12 @@ typedef enum svo_status {
  *   Ray generation, shading and the beam (coarse) pass are individually
  *   rounded in both flavours. Bar: >= 99.99 % identical pixels. */
 typedef enum svo_flavour { SVO_FLAVOUR_VALIDATION = 0, SVO_FLAVOUR_FAST = 1 } svo_flavour;
+/* OR into `flavour` of svo_raymarch_batch[_device] for INCOHERENT batches (secondary rays: ambient
+ * occlusion, reflections): threads take the rays in a direction-binned order (one stable 6-bit radix
+ * pass over the directions) instead of submission order, so that a warp's rays share their octant and
+ * roughly their direction. Results are identical and land at the rays' own indices; only the speed
+ * changes (faster on incoherent batches, a few percent slower on already coherent ones). */
+#define SVO_BATCH_COHERENCE_ORDER 0x100
 
 /* Ray result codes written to `hit[]`. Non-zero == the reference's `true`. */
 enum { SVO_MISS = 0, SVO_HIT_LEAF = 1, SVO_HIT_LOD = 2 };

@@ -154,6 +154,7 @@ struct svo_tree {
     std::mutex mutex;
     std::map<std::tuple<int, int, int>, FramePlan> plans;
     GrowBuffer batchIn, batchOut;
+    GrowBuffer orderWorkspace;               // svo_raymarch_batch_device with SVO_BATCH_COHERENCE_ORDER
     std::vector<cudaStream_t> l2WindowStreams;   // streams that already carry the access-policy window (experiment)
 
     svo::TreeDev dev() const { return svo::TreeDev{dWords, nWords, depth}; }
@@ -818,6 +819,7 @@ int svo_tree_destroy(svo_tree *tree) {
         cudaDeviceSynchronize();
         for (auto &kv : tree->plans) kv.second.destroy();
         tree->batchIn.release();
+        tree->orderWorkspace.release();
         tree->batchOut.release();
         if (tree->dWords) cudaFree(tree->dWords);
         if (tree->stream) cudaStreamDestroy(tree->stream);
@@ -836,9 +838,18 @@ int svo_raymarch_batch_device(svo_tree *tree, uint64_t n, const float *d_o, cons
                               int flavour, uint8_t *d_hit, float *d_t, uint32_t *d_normal, uint64_t *d_voxel,
                               void *stream) {
     if (!tree || (n && (!d_o || !d_d))) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_raymarch_batch_device: null argument");
+    const bool reorder = (flavour & SVO_BATCH_COHERENCE_ORDER) != 0;
+    flavour &= ~SVO_BATCH_COHERENCE_ORDER;
     if (flavour != SVO_FLAVOUR_VALIDATION && flavour != SVO_FLAVOUR_FAST) return fail(SVO_ERR_INVALID_ARGUMENT, "unknown flavour %d", flavour);
     SVO_DEVICE(tree->device);
-    SVO_CUDA(svo::launchRaymarchBatch(tree->dev(), n, d_o, d_d, ray_scale, flavour, d_hit, d_t, d_normal, d_voxel,
+    const uint32_t *order = nullptr;
+    if (reorder && n >= 4096) {
+        // one workspace per tree: calls with the coherence order on one tree are ordered by the caller's stream
+        std::lock_guard<std::mutex> lock(tree->mutex);
+        SVO_CUDA(tree->orderWorkspace.reserve(svo::coherenceOrderBytes(n)));
+        SVO_CUDA(svo::buildCoherenceOrder(n, d_d, tree->orderWorkspace.ptr, &order, static_cast<cudaStream_t>(stream)));
+    }
+    SVO_CUDA(svo::launchRaymarchBatch(tree->dev(), n, d_o, d_d, ray_scale, flavour, d_hit, d_t, d_normal, d_voxel, order,
                                       static_cast<cudaStream_t>(stream)));
     return SVO_OK;
 }
@@ -846,6 +857,8 @@ int svo_raymarch_batch_device(svo_tree *tree, uint64_t n, const float *d_o, cons
 int svo_raymarch_batch(svo_tree *tree, uint64_t n, const float *o, const float *d, float ray_scale, int flavour,
                        uint8_t *hit, float *t, uint32_t *normal, uint64_t *voxel) {
     if (!tree || (n && (!o || !d))) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_raymarch_batch: null argument");
+    const bool reorder = (flavour & SVO_BATCH_COHERENCE_ORDER) != 0;
+    flavour &= ~SVO_BATCH_COHERENCE_ORDER;
     if (flavour != SVO_FLAVOUR_VALIDATION && flavour != SVO_FLAVOUR_FAST) return fail(SVO_ERR_INVALID_ARGUMENT, "unknown flavour %d", flavour);
     if (n == 0) return SVO_OK;
     SVO_DEVICE(tree->device);
@@ -862,6 +875,8 @@ int svo_raymarch_batch(svo_tree *tree, uint64_t n, const float *o, const float *
                  offHit = align16(offNormal + size_t(chunk)*4), outBytes = align16(offHit + size_t(chunk));
     SVO_CUDA(tree->batchIn.reserve(4*inBytes));
     SVO_CUDA(tree->batchOut.reserve(2*outBytes));
+    const size_t orderBytes = (reorder && chunk >= 4096) ? ((svo::coherenceOrderBytes(chunk) + 255) & ~size_t(255)) : 0;
+    if (orderBytes) SVO_CUDA(tree->orderWorkspace.reserve(2*orderBytes));
 
     cudaStream_t streams[2] = {tree->stream, tree->stream2};
     for (uint64_t begin = 0, k = 0; begin < n; begin += chunk, ++k) {
@@ -877,7 +892,10 @@ int svo_raymarch_batch(svo_tree *tree, uint64_t n, const float *o, const float *
         uint8_t *dHit = hit ? base + offHit : nullptr;
         SVO_CUDA(cudaMemcpyAsync(dO, o + 3*begin, size_t(m)*3*sizeof(float), cudaMemcpyHostToDevice, s));
         SVO_CUDA(cudaMemcpyAsync(dD, d + 3*begin, size_t(m)*3*sizeof(float), cudaMemcpyHostToDevice, s));
-        SVO_CUDA(svo::launchRaymarchBatch(tree->dev(), m, dO, dD, ray_scale, flavour, dHit, dT, dNormal, dVoxel, s));
+        const uint32_t *order = nullptr;
+        if (orderBytes && m >= 4096)
+            SVO_CUDA(svo::buildCoherenceOrder(m, dD, static_cast<unsigned char *>(tree->orderWorkspace.ptr) + size_t(slot)*orderBytes, &order, s));
+        SVO_CUDA(svo::launchRaymarchBatch(tree->dev(), m, dO, dD, ray_scale, flavour, dHit, dT, dNormal, dVoxel, order, s));
         if (hit) SVO_CUDA(cudaMemcpyAsync(hit + begin, dHit, size_t(m), cudaMemcpyDeviceToHost, s));
         if (t) SVO_CUDA(cudaMemcpyAsync(t + begin, dT, size_t(m)*4, cudaMemcpyDeviceToHost, s));
         if (normal) SVO_CUDA(cudaMemcpyAsync(normal + begin, dNormal, size_t(m)*4, cudaMemcpyDeviceToHost, s));

@@ -52,9 +52,14 @@ struct TreeDev {
     uint32_t depth;
 };
 
+// order == nullptr: thread k traces ray k. Otherwise thread k traces ray order[k] (see buildCoherenceOrder).
 cudaError_t launchRaymarchBatch(const TreeDev &tree, uint64_t n, const float *o, const float *d, float rayScale,
                                 int flavour, uint8_t *hit, float *t, uint32_t *normal, uint64_t *voxel,
-                                cudaStream_t stream);
+                                const uint32_t *order, cudaStream_t stream);
+
+// Direction-binned submission order for incoherent batches (one stable 6-bit radix pass).
+size_t coherenceOrderBytes(uint64_t n);
+cudaError_t buildCoherenceOrder(uint64_t n, const float *d, void *workspace, const uint32_t **orderOut, cudaStream_t stream);
 
 // shade + pack per ray (Main.cpp:81-90, 128-132); hit may be null (every ray shaded). Device pointers.
 cudaError_t launchShadeBatch(uint64_t n, const uint8_t *hit, const uint32_t *normal, const float *d, const float light[3],

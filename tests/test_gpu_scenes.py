@@ -99,6 +99,20 @@ def test_ambient_occlusion_batches_bit_exact(pysvo, port, sdf):
     fast = tree.raymarch_batch(ao_o, ao_d, 0.0, pysvo.FLAVOUR_FAST)
     same = (fast["hit"] == want["hit"]) & (fast["voxel"] == np.where(hit, want["voxel"], pysvo.VOXEL_NONE))
     assert same.mean() >= 0.9999
+    # SVO_BATCH_COHERENCE_ORDER: threads take the rays direction bin by direction bin; every output must be
+    # the same word at the same index, in both flavours, also with LOD exits and non-unit directions
+    for flavour, base in ((pysvo.FLAVOUR_VALIDATION, got), (pysvo.FLAVOUR_FAST, fast)):
+        re = tree.raymarch_batch(ao_o, ao_d, 0.0, flavour | pysvo.BATCH_COHERENCE_ORDER)
+        for key in ("hit", "normal", "voxel"):
+            assert np.array_equal(re[key], base[key]), key
+        assert np.array_equal(re["t"].view(np.uint32), base["t"].view(np.uint32))
+    scaled = (ao_d * np.linspace(0.25, 7.0, ao_d.shape[0], dtype=np.float32)[:, None]).astype(np.float32)
+    a = tree.raymarch_batch(ao_o, scaled, 0.01, pysvo.FLAVOUR_VALIDATION)
+    b = tree.raymarch_batch(ao_o, scaled, 0.01, pysvo.FLAVOUR_VALIDATION | pysvo.BATCH_COHERENCE_ORDER)
+    assert (a["hit"] == 2).any()
+    for key in ("hit", "normal", "voxel"):
+        assert np.array_equal(a[key], b[key]), key
+    assert np.array_equal(a["t"].view(np.uint32), b["t"].view(np.uint32))
 
 
 def test_large_scene_frame_if_cached(pysvo, port):
