@@ -3,7 +3,11 @@
 // the GPU with the reference's strip/tile/beam semantics and writes PPM images.
 //
 //   svo_headless <in.oct> [--size WxH] [--strips N] [--frames K] [--radius R] [--pitch P]
-//                [--yaw0 Y] [--yaw-step S] [--validation] [--preview] [--out prefix]
+//                [--yaw0 Y] [--yaw-step S] [--validation] [--preview] [--out prefix] [--raw file|-]
+//
+// --raw streams every frame as packed RGB24 (row-major, no header) to a file or to stdout ("-"), the
+// input format of `ffmpeg -f rawvideo -pix_fmt rgb24 -s WxH -i -`: the streamed stand-in for the
+// reference's interactive SDL window; status text goes to stderr then.
 //   svo_headless -builder <in.voxel> <out.oct>
 //
 // The second form is the reference's `-builder` mode for a raw voxel volume (the on-disk path of
@@ -62,7 +66,7 @@ int main(int argc, char **argv) {
     int w = 1280, h = 720, strips = 16, frames = 1, flavour = SVO_FLAVOUR_FAST; /* Main.cpp:57-60 defaults */
     float radius = 1.0f, pitch = 0.0f, yaw0 = 0.0f, yawStep = 3.6f;
     int stride = 1;
-    std::string out;
+    std::string out, raw;
     for (int i = 2; i < argc; ++i) {
         std::string a = argv[i];
         auto next = [&]() -> const char * { return i + 1 < argc ? argv[++i] : ""; };
@@ -76,11 +80,16 @@ int main(int argc, char **argv) {
         else if (a == "--validation") flavour = SVO_FLAVOUR_VALIDATION;
         else if (a == "--preview") stride = 3;   /* the reference's renderHalfSize while dragging, Main.cpp:161 */
         else if (a == "--out") out = next();
+        else if (a == "--raw") raw = next();
         else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
     try {
         VoxelOctree tree(argv[1]);
-        printf("loaded %s: %llu words, depth %u\n", argv[1], (unsigned long long)tree.wordCount(), tree.depth());
+        FILE *info = raw == "-" ? stderr : stdout;
+        FILE *rawFile = raw.empty() ? 0 : raw == "-" ? stdout : fopen(raw.c_str(), "wb");
+        if (!raw.empty() && !rawFile) throw std::runtime_error("cannot write " + raw);
+        std::vector<unsigned char> rgb(raw.empty() ? 0 : size_t(w)*h*3);
+        fprintf(info, "loaded %s: %llu words, depth %u\n", argv[1], (unsigned long long)tree.wordCount(), tree.depth());
         uint32_t *rgba = 0;
         if (svo_host_alloc(size_t(w)*h*4, reinterpret_cast<void **>(&rgba)) != SVO_OK) throw std::runtime_error(svo_last_error());
         double totalMs = 0.0;
@@ -93,10 +102,17 @@ int main(int argc, char **argv) {
             double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
             if (k > 0 || frames == 1) { totalMs += ms; rays += st.coarse_rays + st.fine_rays; }
             if (!out.empty()) writePpm(out + "_" + std::to_string(k) + ".ppm", rgba, w, h);
+            if (rawFile) {
+                for (size_t p = 0; p < size_t(w)*h; ++p) {
+                    rgb[3*p] = rgba[p] & 255; rgb[3*p + 1] = (rgba[p] >> 8) & 255; rgb[3*p + 2] = (rgba[p] >> 16) & 255;
+                }
+                if (fwrite(rgb.data(), 1, rgb.size(), rawFile) != rgb.size()) throw std::runtime_error("short write on the raw stream");
+            }
         }
         int timed = frames > 1 ? frames - 1 : 1;
-        printf("%d frame(s) %dx%d, %d strips: %.3f ms/frame end to end (host buffer), %.1f Mrays/s\n", timed, w, h,
-               strips, totalMs/timed, rays/(totalMs*1e3));
+        fprintf(info, "%d frame(s) %dx%d, %d strips: %.3f ms/frame end to end (host buffer), %.1f Mrays/s\n", timed, w, h,
+                strips, totalMs/timed, rays/(totalMs*1e3));
+        if (rawFile && rawFile != stdout) fclose(rawFile);
         svo_host_free(rgba);
     } catch (const std::exception &e) {
         fprintf(stderr, "error: %s\n", e.what());

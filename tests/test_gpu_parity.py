@@ -360,6 +360,17 @@ def test_cpp_facade_and_headless_driver(pysvo, port, gpu_dragon, dragon_words, t
                                          flavour=pysvo.FLAVOUR_VALIDATION)
     assert np.array_equal(img[..., 0], (want & 0xFF).astype(np.uint8))
     assert np.array_equal(img[..., 2], ((want >> 16) & 0xFF).astype(np.uint8))
+    # --raw: the same frames as a headerless RGB24 stream (what a video encoder reads from a pipe)
+    stream = tmp_path / "frames.rgb"
+    out = subprocess.run([str(pkg / "svo_headless"), str(DRAGON), "--size", "320x180", "--strips", "4", "--frames", "2",
+                          "--validation", "--radius", "0.8", "--pitch", "10", "--yaw0", "30", "--raw", str(stream)],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    frames = np.frombuffer(stream.read_bytes(), np.uint8).reshape(2, 180, 320, 3)
+    assert np.array_equal(frames[0], img)
+    out = subprocess.run([str(pkg / "svo_headless"), str(DRAGON), "--size", "320x180", "--strips", "4", "--validation",
+                          "--radius", "0.8", "--pitch", "10", "--yaw0", "30", "--raw", "-"], capture_output=True, timeout=300)
+    assert out.returncode == 0 and np.array_equal(np.frombuffer(out.stdout, np.uint8).reshape(180, 320, 3), img)
 
 
 @pytest.mark.parametrize("shape", [(1280, 720, 16), (333, 187, 5), (64, 40, 3)])
