@@ -411,6 +411,8 @@ def test_shade_batch_vs_oracle(pysvo, port, gpu_dragon, dragon_words):
     d = rng.normal(size=(n, 3)).astype(np.float32)
     d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
     normal = rng.integers(0, 2**32, n, dtype=np.uint64).astype(np.uint32)
+    face = rng.integers(0, 3, n).astype(np.uint32)           # compressMaterial only ever writes faces 0..2 (Util.hpp:64-84)
+    normal = (normal & np.uint32(0x9FFFFFFF)) | (face << np.uint32(29))
     leaves = words[words > 0xFFFF][:n // 2]
     normal[:leaves.size] = leaves
     hit = rng.integers(0, 3, n).astype(np.uint8)
