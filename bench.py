@@ -699,6 +699,16 @@ def run_own(args):
                                                                "threads_per_instruction", "source")},
                     "note": "instruction-issue bound pointer chasing with SIMT divergence, not HBM-bound: node "
                             "fetches hit L1/L2 (see profiles/ and DESIGN.md section 4)"}
+        # the bound that does bind: one warp instruction per SM sub-partition per cycle (148 SMs x 4)
+        if traffic and traffic.get("warp_instructions") and traffic.get("sm_cycles_elapsed"):
+            slots = 148 * 4 * float(traffic["sm_cycles_elapsed"])
+            roofline["issue_roofline"] = {
+                "warp_instructions_per_launch": traffic["warp_instructions"],
+                "issue_slots_per_launch": slots, "frac": traffic["warp_instructions"] / slots,
+                "threads_per_instruction": traffic.get("threads_per_instruction"),
+                "source": traffic.get("source"),
+                "note": "fraction of the SMs' issue slots (148 SMs x 4 schedulers x elapsed cycles of the ncu capture) "
+                        "that issued an instruction of this kernel: the limit this pass actually runs against"}
 
     # ---- CPU baseline: the reference's own renderer on this box's host cores (bounded sample)
     cpu = None
