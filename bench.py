@@ -737,7 +737,7 @@ def run_own(args):
                 "steps": e2e_steps, "ms_per_step": float(e2e_s.item()) / e2e_steps * 1e3,
                 "note": "per-step input is the 128 B camera (kernel parameters); the octree stays resident; "
                         "svo_render_frame_async, four frames in flight, every frame copied to pinned host memory"},
-        "gpu_launches": 2 * steps * world,
+        "gpu_launches": 3 * steps * world,       # beam pass + tile classifier + fine pass per frame and rank
         "clocks": clocks,
         "parity": parity,
         "bytes_per_ray": {"coarse_node": coarse_b_ray, "fine_node": fine_b_ray},
