@@ -165,25 +165,32 @@ bool lz4DecodeBlock(const uint8_t *src, size_t srcSize, uint8_t *out, uint64_t o
     }
 }
 
-inline void putLength(std::vector<uint8_t> &out, size_t len) {
-    while (len >= 255) { out.push_back(255); len -= 255; }
-    out.push_back(uint8_t(len));
-}
+// Output cursor over a buffer sized for the worst case (an incompressible slice is one literal run:
+// size + size/255 + 16 bytes; a match never costs more bytes than the 4+ it replaces).
+struct ByteSink {
+    uint8_t *p;
+    inline void put(uint8_t v) { *p++ = v; }
+    inline void length(size_t len) {
+        while (len >= 255) { *p++ = 255; len -= 255; }
+        *p++ = uint8_t(len);
+    }
+    inline void literals(const uint8_t *lit, size_t n) { memcpy(p, lit, n); p += n; }
+};
 
-void emitSequence(std::vector<uint8_t> &out, const uint8_t *lit, size_t litLen, size_t offset, size_t matchLen) {
+inline void emitSequence(ByteSink &out, const uint8_t *lit, size_t litLen, size_t offset, size_t matchLen) {
     size_t ml = matchLen - kMinMatch;
-    out.push_back(uint8_t((litLen >= 15 ? 15 : litLen) << 4 | (ml >= 15 ? 15 : ml)));
-    if (litLen >= 15) putLength(out, litLen - 15);
-    out.insert(out.end(), lit, lit + litLen);
-    out.push_back(uint8_t(offset & 255));
-    out.push_back(uint8_t(offset >> 8));
-    if (ml >= 15) putLength(out, ml - 15);
+    out.put(uint8_t((litLen >= 15 ? 15 : litLen) << 4 | (ml >= 15 ? 15 : ml)));
+    if (litLen >= 15) out.length(litLen - 15);
+    out.literals(lit, litLen);
+    out.put(uint8_t(offset & 255));
+    out.put(uint8_t(offset >> 8));
+    if (ml >= 15) out.length(ml - 15);
 }
 
-void emitLastLiterals(std::vector<uint8_t> &out, const uint8_t *lit, size_t litLen) {
-    out.push_back(uint8_t((litLen >= 15 ? 15 : litLen) << 4));
-    if (litLen >= 15) putLength(out, litLen - 15);
-    out.insert(out.end(), lit, lit + litLen);
+inline void emitLastLiterals(ByteSink &out, const uint8_t *lit, size_t litLen) {
+    out.put(uint8_t((litLen >= 15 ? 15 : litLen) << 4));
+    if (litLen >= 15) out.length(litLen - 15);
+    out.literals(lit, litLen);
 }
 
 // Greedy single-pass LZ4 block encoder over data[begin, end) with a 64 KiB
@@ -192,38 +199,48 @@ void emitLastLiterals(std::vector<uint8_t> &out, const uint8_t *lit, size_t litL
 // matches.
 class Lz4Encoder {
     static constexpr int kHashBits = 16;
-    std::vector<uint64_t> table_; // position + 1 of the last occurrence; 0 = none
+    std::vector<uint32_t> table_; // (position - begin) + 1 of the last occurrence; 0 = none (slices are <= 64 MiB)
     static inline uint32_t hash(uint32_t v) { return (v*2654435761u) >> (32 - kHashBits); }
 
 public:
     Lz4Encoder() : table_(size_t(1) << kHashBits, 0) {}
 
-    void encodeSlice(const uint8_t *data, uint64_t begin, uint64_t end, bool compress, std::vector<uint8_t> &out) {
-        out.clear();
+    void encodeSlice(const uint8_t *data, uint64_t begin, uint64_t end, bool compress, std::vector<uint8_t> &buf) {
         const uint64_t size = end - begin;
+        buf.resize(size_t(size + size/255 + 64));
+        ByteSink out{buf.data()};
         if (!compress || size < kMfLimit + 1) {
             emitLastLiterals(out, data + begin, size_t(size));
+            buf.resize(size_t(out.p - buf.data()));
             return;
         }
-        // entries older than the window are filtered by the offset check
-        const uint64_t matchStartLimit = end - kMfLimit;   // last position a match may start at
-        const uint64_t matchEndLimit = end - kLastLiterals;
-        uint64_t anchor = begin, ip = begin;
+        const uint8_t *base = data + begin;                 // positions below are relative to the slice
+        const uint64_t matchStartLimit = size - kMfLimit;   // last position a match may start at
+        const uint64_t matchEndLimit = size - kLastLiterals;
+        uint64_t anchor = 0, ip = 0;
         unsigned misses = 0;
         while (ip <= matchStartLimit) {
-            uint32_t seq = read32(data + ip);
-            uint32_t h = hash(seq);
-            uint64_t cand = table_[h];
-            table_[h] = ip + 1;
-            // candidates before `begin` are skipped: slices this writer produces never refer to each
-            // other's plaintext, so the reader can decode them concurrently
-            if (cand != 0 && cand - 1 >= begin && ip - (cand - 1) <= kMaxOffset && read32(data + cand - 1) == seq) {
-                uint64_t m = cand - 1;
+            const uint32_t seq = read32(base + ip);
+            const uint32_t h = hash(seq);
+            const uint32_t cand = table_[h];
+            table_[h] = uint32_t(ip) + 1;
+            // the table only ever holds positions of this slice: slices this writer produces never refer to
+            // each other's plaintext, so the reader can decode them concurrently
+            if (cand != 0 && ip - (cand - 1) <= kMaxOffset && read32(base + cand - 1) == seq) {
+                const uint64_t m = cand - 1;
                 uint64_t len = kMinMatch;
-                while (ip + len < matchEndLimit && data[m + len] == data[ip + len]) ++len;
-                emitSequence(out, data + anchor, size_t(ip - anchor), size_t(ip - m), size_t(len));
+                while (ip + len + 8 <= matchEndLimit) {     // eight bytes at a time, then the tail
+                    uint64_t x, y;
+                    memcpy(&x, base + m + len, 8);
+                    memcpy(&y, base + ip + len, 8);
+                    if (x != y) { len += uint64_t(__builtin_ctzll(x ^ y)) >> 3; goto matched; }
+                    len += 8;
+                }
+                while (ip + len < matchEndLimit && base[m + len] == base[ip + len]) ++len;
+            matched:
+                emitSequence(out, base + anchor, size_t(ip - anchor), size_t(ip - m), size_t(len));
                 // index a position inside the match so that long runs keep finding themselves
-                if (ip + len - 2 <= matchStartLimit) table_[hash(read32(data + ip + len - 2))] = ip + len - 2 + 1;
+                if (ip + len - 2 <= matchStartLimit) table_[hash(read32(base + ip + len - 2))] = uint32_t(ip + len - 2) + 1;
                 ip += len;
                 anchor = ip;
                 misses = 0;
@@ -231,7 +248,8 @@ public:
                 ip += 1 + (misses++ >> 6);
             }
         }
-        emitLastLiterals(out, data + anchor, size_t(end - anchor));
+        emitLastLiterals(out, base + anchor, size_t(size - anchor));
+        buf.resize(size_t(out.p - buf.data()));
     }
 };
 
