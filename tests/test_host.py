@@ -216,3 +216,23 @@ def test_strip_layout_matches_reference_formula(pysvo):
     assert len(lay) == 16 and lay[0] == (0, 45, 161, 7) and lay[-1] == (675, 720, 161, 7)
     assert pysvo.coarse_cells(1280, 720, 16) == 18032
     assert pysvo.coarse_cells(3840, 2160, 16) == 138528
+
+
+def test_oct_beyond_two_gib(pysvo, tmp_path):
+    """Trees of 2 GiB and more: the reference's loader truncates the remaining byte count to int
+    (VoxelOctree.cpp:79) and cannot read them; this reader / writer count in 64 bits.
+    33 slices, the last one 12 bytes long."""
+    n_words = (2 << 30) // 4 + 3
+    words = np.zeros(n_words, np.uint32)
+    words[0] = (1 << 18) | 0x0100
+    marks = np.arange(0, n_words, 9973, dtype=np.int64)
+    words[marks] = (marks * 2654435761 & 0xFFFFFFFF).astype(np.uint32)
+    words[-3:] = [0xAAAAAAAA, 0xBBBBBBBB, 0xCCCCCCCC]
+    center = np.array([0.5, 0.5, 0.5], np.float32)
+    p = tmp_path / "big.oct"
+    pysvo.oct_write(p, words, center, compress=True)
+    assert p.stat().st_size < n_words * 4 // 20                 # really compressed
+    w2, c2 = pysvo.oct_read(p)
+    assert w2.size == n_words and np.array_equal(c2, center)
+    assert np.array_equal(w2[marks], words[marks]) and np.array_equal(w2[-3:], words[-3:])
+    assert int(np.count_nonzero(w2)) == int(np.count_nonzero(words))
