@@ -35,12 +35,12 @@ _u64p = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
 
 def build_port(force: bool = False) -> Path:
     """gcc the C restatement (seconds). -ffp-contract=off is load-bearing."""
-    src = HERE / "svo_oracle.c"
+    srcs = [HERE / "svo_oracle.c", HERE / "svo_oracle_ply.c"]
     if force or not PORT_SO.exists() or PORT_SO.stat().st_mtime < max(
-            src.stat().st_mtime, (HERE / "svo_oracle.h").stat().st_mtime):
+            [s.stat().st_mtime for s in srcs] + [(HERE / "svo_oracle.h").stat().st_mtime]):
         subprocess.check_call([
             "gcc", "-std=c11", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-pthread",
-            "-Wall", "-Wextra", "-o", str(PORT_SO), str(src), "-lm"])
+            "-Wall", "-Wextra", "-o", str(PORT_SO)] + [str(s) for s in srcs] + ["-lm"])
     return PORT_SO
 
 
@@ -126,6 +126,11 @@ class Ref:
         if not h:
             raise FileNotFoundError(path)
         return h
+
+    def ply_to_voxel_file(self, ply, out, resolution, mem=1 << 30):
+        """PlyLoader(ply).convertToVolume(out, resolution, mem) (PlyLoader.cpp:505-534)."""
+        if self.lib.svoref_ply_to_voxel_file(str(ply).encode(), str(out).encode(), int(resolution), int(mem)) != 0:
+            raise FileNotFoundError(ply)
 
     def tree_build_ply(self, path, resolution, mem=1 << 30):
         h = self.lib.svoref_tree_build_ply(str(path).encode(), int(resolution), int(mem))
@@ -321,6 +326,10 @@ class Port:
         L.svo_oracle_build_octree.argtypes = [_u32p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64), _f32p]
         L.svo_oracle_free.restype = None
         L.svo_oracle_free.argtypes = [C.c_void_p]
+        L.svo_oracle_voxelize_ply.restype = C.POINTER(C.c_uint32)
+        L.svo_oracle_voxelize_ply.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int * 3), C.POINTER(C.c_uint64)]
+        L.svo_oracle_tree_to_volume.restype = None
+        L.svo_oracle_tree_to_volume.argtypes = [_u32p, C.c_int, _u32p, C.c_int, C.c_int, C.c_int]
 
     def raymarch(self, words, o, d, ray_scale=0.0, normal_sentinel=0xDEADBEEF, t_sentinel=-1.0):
         n = C.c_uint32(normal_sentinel)
@@ -402,6 +411,27 @@ class Port:
             return np.ctypeslib.as_array(ptr, shape=(n.value,)).copy(), center
         finally:
             self.lib.svo_oracle_free(ptr)
+
+    def voxelize_ply(self, path, resolution, threads):
+        """Row f3 (oracle only so far): PlyLoader(path) + VoxelData(loader, resolution, mem) with the volume in one
+        cache block (PlyLoader.cpp:64-474). -> (voxels uint32[D, H, W], triangle count)."""
+        dims = (C.c_int * 3)()
+        ntri = C.c_uint64(0)
+        ptr = self.lib.svo_oracle_voxelize_ply(str(path).encode(), int(resolution), int(threads), C.byref(dims), C.byref(ntri))
+        if not ptr:
+            raise ValueError(f"svo_oracle_voxelize_ply: cannot read {path}")
+        try:
+            w, h, d = dims[0], dims[1], dims[2]
+            return np.ctypeslib.as_array(ptr, shape=(d, h, w)).copy(), int(ntri.value)
+        finally:
+            self.lib.svo_oracle_free(ptr)
+
+    def tree_to_volume(self, words, side, dims):
+        """Material words of a node array spanning side^3 voxels as a dense (d, h, w) volume."""
+        w, h, d = dims
+        vol = np.zeros((d, h, w), np.uint32)
+        self.lib.svo_oracle_tree_to_volume(np.ascontiguousarray(words, np.uint32), int(side), vol.reshape(-1), w, h, d)
+        return vol
 
     def tree_walk(self, words):
         st = TreeStats()

@@ -113,6 +113,14 @@ int svo_oracle_tree_walk(const uint32_t *octree, uint64_t words, svo_oracle_tree
 uint32_t *svo_oracle_build_octree(const uint32_t *voxels, int w, int h, int d, uint64_t *nWordsOut, float center[3]);
 void svo_oracle_free(void *p);
 
+/* Row f3 (oracle/svo_oracle_ply.c): PlyLoader(path) + what VoxelData(loader, sideLength, mem) hands to
+ * buildOctree (reference src/PlyLoader.cpp:64-474, src/VoxelData.cpp:50-56,178-181) with the whole volume in
+ * one cache block; threadCount = size of the reference's thread pool (it shapes the sub-block partition the
+ * result depends on). malloc'ed w*h*d volume (svo_oracle_free) or NULL. */
+uint32_t *svo_oracle_voxelize_ply(const char *plyPath, int sideLength, int threadCount, int dims[3], uint64_t *nTrianglesOut);
+/* The filled voxels of a node array spanning side^3 voxels, written into vol (w*h*d, x fastest, pre-zeroed). */
+void svo_oracle_tree_to_volume(const uint32_t *octree, int side, uint32_t *vol, int w, int h, int d);
+
 #ifdef __cplusplus
 }
 #endif
