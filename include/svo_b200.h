@@ -142,6 +142,36 @@ SVO_API int svo_tree_build_from_voxel_file(const char *path, int device, svo_tre
 SVO_API int svo_tree_build_from_sparse(const uint32_t *xyz, const uint32_t *values, uint64_t n, int w, int h, int d,
                                        int device, svo_tree **out);
 
+/* PlyLoader(const char *path) + PlyLoader::tris() (PlyLoader.cpp:64-226, PlyLoader.hpp:110): the mesh as the
+ * voxeliser sees it. Host only. *tris receives n x 33 floats (pos[3][3], normal[3][3], color[3][3],
+ * lower[3], upper[3] per triangle; positions rescaled to the unit box), released with svo_free. */
+SVO_API int svo_ply_read_triangles(const char *path, float **tris, uint64_t *n, float lower[3], float upper[3]);
+/* Mesh -> tree: PlyLoader(path) + VoxelData(loader, resolution, mem) +
+ * VoxelOctree(VoxelData*) -- the in-memory path of the reference's -builder mode (Main.cpp:320-325,
+ * PlyLoader.cpp:64-474). The PLY file (ASCII or binary; x y z [nx ny nz] [red green blue]; faces as
+ * vertex_indices lists, fans for polygons) is voxelised on the GPU at `resolution` (the reference's
+ * --resolution, default 256) and the tree built in HBM. The reference's result also depends on its memory
+ * budget (cache block size) and on the size of its thread pool (the cache block is cut into per-thread
+ * sub-blocks, and triangle lists and cell centres are computed per sub-block): pass the values the reference
+ * run would have used -- mem_budget 0 = its 1 GiB default (Main.cpp:269), threads 0 = this host's hardware
+ * thread count (ThreadUtils::idealThreadCount) -- and the node array is the reference's, word for word. */
+SVO_API int svo_tree_build_from_ply(const char *path, int resolution, uint64_t mem_budget, int threads, int device,
+                                    svo_tree **out);
+
+typedef struct svo_voxelize_stats {
+    uint64_t triangles;
+    uint64_t cell_records;      /* (cell, triangle) overlaps */
+    uint64_t voxels;            /* filled cells */
+    int32_t dims[3];            /* volume the reference derives from the mesh (PlyLoader::suggestedDimensions) */
+    int32_t cache_block;        /* edge of the reference's cache block for the budget (VoxelData.cpp:203-262) */
+    int32_t sub_block[3];       /* per-thread sub-block (PlyLoader.cpp:381-440) */
+    int32_t reserved;
+    float overlap_ms, sort_ms, fold_ms;   /* device time of the voxeliser's three phases */
+    float reserved2;
+} svo_voxelize_stats;
+/* Statistics of the calling thread's last successful svo_tree_build_from_ply call. */
+SVO_API int svo_voxelize_last_stats(svo_voxelize_stats *out);
+
 /* The inverse: the filled voxels of a tree, in the builder's (Morton) order. Call with xyz_out ==
  * values_out == NULL to get the count in *n_out, then with host buffers of `capacity` >= count voxels
  * (xyz_out: 3 words per voxel). Coordinates are in the 2^depth grid the tree spans. */

@@ -328,6 +328,8 @@ class Port:
         L.svo_oracle_free.argtypes = [C.c_void_p]
         L.svo_oracle_voxelize_ply.restype = C.POINTER(C.c_uint32)
         L.svo_oracle_voxelize_ply.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int * 3), C.POINTER(C.c_uint64)]
+        L.svo_oracle_ply_triangles.restype = C.POINTER(C.c_float)
+        L.svo_oracle_ply_triangles.argtypes = [C.c_char_p, C.POINTER(C.c_uint64), _f32p, _f32p]
         L.svo_oracle_tree_to_volume.restype = None
         L.svo_oracle_tree_to_volume.argtypes = [_u32p, C.c_int, _u32p, C.c_int, C.c_int, C.c_int]
 
@@ -423,6 +425,18 @@ class Port:
         try:
             w, h, d = dims[0], dims[1], dims[2]
             return np.ctypeslib.as_array(ptr, shape=(d, h, w)).copy(), int(ntri.value)
+        finally:
+            self.lib.svo_oracle_free(ptr)
+
+    def ply_triangles(self, path):
+        """-> (float32[n, 33], lower[3], upper[3]): PlyLoader's triangle list after its constructor."""
+        n = C.c_uint64(0)
+        lo, hi = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        ptr = self.lib.svo_oracle_ply_triangles(str(path).encode(), C.byref(n), lo, hi)
+        if not ptr:
+            raise ValueError(f"svo_oracle_ply_triangles: cannot read {path}")
+        try:
+            return np.ctypeslib.as_array(ptr, shape=(n.value, 33)).copy(), lo, hi
         finally:
             self.lib.svo_oracle_free(ptr)
 

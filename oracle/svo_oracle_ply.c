@@ -493,6 +493,23 @@ uint32_t *svo_oracle_voxelize_ply(const char *plyPath, int sideLength, int threa
     return data;
 }
 
+/* The triangle list PlyLoader holds after its constructor, 33 floats per triangle: pos[3][3], normal[3][3],
+ * color[3][3], lower[3], upper[3] (malloc'ed, svo_oracle_free); lower/upper: the rescaled mesh bounds. */
+float *svo_oracle_ply_triangles(const char *plyPath, uint64_t *nOut, float lower[3], float upper[3]) {
+    size_t n = 0;
+    Tri *tris = loadPly(plyPath, &n, lower, upper);
+    if (!tris) return NULL;
+    float *out = (float *)malloc(sizeof(float)*33*(n ? n : 1));
+    for (size_t i = 0; i < n; ++i) {
+        float *o = out + 33*i;
+        for (int v = 0; v < 3; ++v) { memcpy(o + 3*v, tris[i].v[v].pos, 12); memcpy(o + 9 + 3*v, tris[i].v[v].normal, 12); memcpy(o + 18 + 3*v, tris[i].v[v].color, 12); }
+        memcpy(o + 27, tris[i].lower, 12); memcpy(o + 30, tris[i].upper, 12);
+    }
+    free(tris);
+    *nOut = n;
+    return out;
+}
+
 /* ---- node array -> voxels (to compare a reference-built tree with a volume) ------------------------- */
 
 static void walkVoxels(const uint32_t *oct, uint64_t p, int x, int y, int z, int size, uint32_t *vol, int w, int h, int d) {

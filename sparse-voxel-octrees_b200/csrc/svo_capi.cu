@@ -20,8 +20,12 @@
 
 #include "camera.hpp"
 #include "oct_io.hpp"
+#include "ply_io.hpp"
 #include "svo_build.cuh"
 #include "svo_kernels.cuh"
+#include "svo_voxelize.cuh"
+
+#include <thread>
 
 namespace {
 
@@ -731,6 +735,65 @@ int svo_tree_build_from_sparse(const uint32_t *xyz, const uint32_t *values, uint
     cudaFree(dXyz);
     cudaFree(dVal);
     return finishBuild(builder, device, out);
+}
+
+namespace {
+thread_local svo_voxelize_stats g_voxelizeStats = {};
+}
+
+int svo_ply_read_triangles(const char *path, float **tris, uint64_t *n, float lower[3], float upper[3]) {
+    if (!path || !tris || !n || !lower || !upper) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_ply_read_triangles: null argument");
+    *tris = nullptr;
+    *n = 0;
+    svo::Mesh mesh;
+    std::string err;
+    int status = 0;
+    if (!svo::readPlyMesh(path, mesh, err, status)) return fail(status, "%s", err.c_str());
+    static_assert(sizeof(svo::MeshTriangle) == 33*sizeof(float), "MeshTriangle is 33 packed floats");
+    float *out = static_cast<float *>(malloc(mesh.tris.size()*sizeof(svo::MeshTriangle)));
+    if (!out) return fail(SVO_ERR_OUT_OF_MEMORY, "out of host memory for the triangle list");
+    memcpy(out, mesh.tris.data(), mesh.tris.size()*sizeof(svo::MeshTriangle));
+    *tris = out;
+    *n = mesh.tris.size();
+    memcpy(lower, mesh.lower, 12);
+    memcpy(upper, mesh.upper, 12);
+    return SVO_OK;
+}
+
+int svo_tree_build_from_ply(const char *path, int resolution, uint64_t mem_budget, int threads, int device, svo_tree **out) {
+    if (!path || !out) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_tree_build_from_ply: null argument");
+    *out = nullptr;
+    int st = requireDevice(device);
+    if (st != SVO_OK) return st;
+    svo::Mesh mesh;
+    std::string err;
+    int status = 0;
+    if (!svo::readPlyMesh(path, mesh, err, status)) return fail(status, "%s", err.c_str());
+    if (mem_budget == 0) mem_budget = uint64_t(1024)*1024*1024;                   // Main.cpp:269
+    if (threads <= 0) threads = int(std::thread::hardware_concurrency());
+    if (threads <= 0) threads = 1;
+    SVO_DEVICE(device);
+    svo::OctreeBuilder builder;
+    svo::VoxelizeStats vs;
+    if (!svo::voxelizeMesh(mesh, resolution, mem_budget, threads, builder, vs, err))
+        return fail(SVO_ERR_INVALID_ARGUMENT, "voxelisation: %s", err.c_str());
+    st = finishBuild(builder, device, out);
+    if (st != SVO_OK) return st;
+    g_voxelizeStats.triangles = vs.triangles;
+    g_voxelizeStats.cell_records = vs.cellRecords;
+    g_voxelizeStats.voxels = vs.voxels;
+    for (int i = 0; i < 3; ++i) { g_voxelizeStats.dims[i] = vs.dims[i]; g_voxelizeStats.sub_block[i] = vs.subBlock[i]; }
+    g_voxelizeStats.cache_block = vs.cacheBlock;
+    g_voxelizeStats.overlap_ms = vs.overlapMs;
+    g_voxelizeStats.sort_ms = vs.sortMs;
+    g_voxelizeStats.fold_ms = vs.foldMs;
+    return SVO_OK;
+}
+
+int svo_voxelize_last_stats(svo_voxelize_stats *out) {
+    if (!out) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_voxelize_last_stats: null argument");
+    *out = g_voxelizeStats;
+    return SVO_OK;
 }
 
 // Two calls: with xyz_out == values_out == NULL only *n_out is written (the count); with buffers of

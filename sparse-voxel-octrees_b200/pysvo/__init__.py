@@ -93,6 +93,12 @@ class BuildStats(C.Structure):
                 ("gather_ms", C.c_float), ("sort_ms", C.c_float), ("levels_ms", C.c_float), ("emit_ms", C.c_float)]
 
 
+class VoxelizeStats(C.Structure):
+    _fields_ = [("triangles", C.c_uint64), ("cell_records", C.c_uint64), ("voxels", C.c_uint64), ("dims", C.c_int32 * 3),
+                ("cache_block", C.c_int32), ("sub_block", C.c_int32 * 3), ("reserved", C.c_int32),
+                ("overlap_ms", C.c_float), ("sort_ms", C.c_float), ("fold_ms", C.c_float), ("reserved2", C.c_float)]
+
+
 def build_library(force: bool = False) -> Path:
     """make -C sparse-voxel-octrees_b200 (nvcc, sm_100a). Cross-compiles without a GPU."""
     args = ["make", "-C", str(PKG_DIR), "-j8"]
@@ -136,6 +142,9 @@ def lib():
         "svo_tree_build_from_voxel_file": (i32, [C.c_char_p, i32, P(vp)]),
         "svo_tree_build_from_sparse": (i32, [vp, vp, u64, i32, i32, i32, i32, P(vp)]),
         "svo_build_last_stats": (i32, [P(BuildStats)]),
+        "svo_tree_build_from_ply": (i32, [C.c_char_p, i32, u64, i32, i32, P(vp)]),
+        "svo_ply_read_triangles": (i32, [C.c_char_p, P(P(f32)), P(u64), P(f32), P(f32)]),
+        "svo_voxelize_last_stats": (i32, [P(VoxelizeStats)]),
         "svo_tree_extract_voxels": (i32, [vp, vp, vp, u64, P(u64)]),
         "svo_tree_rebuild": (i32, [vp, i32, i32, i32, P(vp)]),
         "svo_raymarch_batch": (i32, [vp, u64, vp, vp, f32, i32, vp, vp, vp, vp]),
@@ -203,6 +212,19 @@ def oct_read(path):
     finally:
         lib().svo_free(words)
     return arr, np.array(list(center), np.float32)
+
+
+def ply_read_triangles(path):
+    """-> (float32[n, 33], lower[3], upper[3]). Replaces PlyLoader(path) + tris(), PlyLoader.cpp:64-226."""
+    tris = C.POINTER(C.c_float)()
+    n = C.c_uint64(0)
+    lo, hi = (C.c_float * 3)(), (C.c_float * 3)()
+    _check(lib().svo_ply_read_triangles(str(path).encode(), C.byref(tris), C.byref(n), lo, hi))
+    try:
+        arr = np.ctypeslib.as_array(tris, shape=(n.value, 33)).copy()
+    finally:
+        lib().svo_free(tris)
+    return arr, np.array(list(lo), np.float32), np.array(list(hi), np.float32)
 
 
 def oct_write(path, words, center, compress=True):
@@ -352,6 +374,21 @@ class VoxelOctree:
         h = C.c_void_p()
         _check(lib().svo_tree_build_from_voxel_file(str(path).encode(), int(device), C.byref(h)))
         return cls(_handle=h)
+
+    @classmethod
+    def build_from_ply(cls, path, resolution=256, mem_budget=0, threads=0, device=0):
+        """PlyLoader + VoxelData(loader, resolution, mem) + VoxelOctree(VoxelData*), Main.cpp:320-325; threads =
+        size of the reference's thread pool the result is to match (0 = this host's hardware threads)."""
+        h = C.c_void_p()
+        _check(lib().svo_tree_build_from_ply(str(path).encode(), int(resolution), int(mem_budget), int(threads),
+                                             int(device), C.byref(h)))
+        return cls(_handle=h)
+
+    @staticmethod
+    def last_voxelize_stats():
+        st = VoxelizeStats()
+        _check(lib().svo_voxelize_last_stats(C.byref(st)))
+        return st
 
     @classmethod
     def build_from_sparse(cls, xyz, values, dims, device=0):

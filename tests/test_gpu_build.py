@@ -222,3 +222,42 @@ def test_headless_builder_mode(pysvo, port, tmp_path):
     res = subprocess.run([str(pkg / "svo_headless"), "-builder", str(tmp_path / "nope.voxel"), str(out)],
                          capture_output=True, text=True, timeout=300)
     assert res.returncode == 1 and "cannot open" in res.stderr
+
+
+def _ico_ply(path, freq):
+    from tools import make_scenes
+    assert make_scenes.gen_lib().svo_scene_icosphere_ply(str(path).encode(), freq, make_scenes.SEED) > 0
+    return path
+
+
+def test_build_from_ply_equals_reference(pysvo, port, ref, tmp_path):
+    """Row f3 + f2 end to end: PLY -> voxels (GPU) -> tree (GPU) against the reference's own
+    PlyLoader + VoxelData + VoxelOctree run (in-memory -builder path, Main.cpp:320-325) with the same pool size:
+    identical node arrays for the benchmark's icosphere at three resolutions and for the ASCII / normals /
+    colours / polygon variants; a small memory budget (several cache blocks) must give the same tree too."""
+    from ply_meshes import write_variants
+    threads = ref.hardware_threads()
+    cases = [(_ico_ply(tmp_path / "ico6.ply", 6), 64, 1 << 30), (_ico_ply(tmp_path / "ico20.ply", 20), 128, 1 << 30),
+             (_ico_ply(tmp_path / "ico50.ply", 50), 256, 1 << 30), (tmp_path / "ico20.ply", 128, 1 << 20)]
+    cases += [(p, res, 1 << 30) for name, p in write_variants(tmp_path) if not name.startswith("be_") for res in (48, 128)]
+    for ply, res, mem in cases:
+        h = ref.tree_build_ply(ply, res, mem)
+        want, wcenter = ref.tree_words(h), ref.tree_center(h)
+        ref.tree_destroy(h)
+        tree = pysvo.VoxelOctree.build_from_ply(ply, res, mem_budget=mem, threads=threads)
+        st = pysvo.VoxelOctree.last_voxelize_stats()
+        got = tree.words()
+        assert got.size == want.size and np.array_equal(got, want), (ply.name, res, mem, list(st.sub_block), st.cache_block)
+        assert np.array_equal(tree.center(), wcenter)
+        assert st.voxels > 0 and st.cell_records >= st.voxels and st.triangles > 0
+        tree.close()
+    # the oracle's volume, for a pool size other than this host's
+    for other in (1, 3, 64):
+        vol, _ = port.voxelize_ply(tmp_path / "ico20.ply", 128, other)
+        want, _ = port.build_octree(vol)
+        tree = pysvo.VoxelOctree.build_from_ply(tmp_path / "ico20.ply", 128, threads=other)
+        assert np.array_equal(tree.words(), want), other
+        tree.close()
+    with pytest.raises(pysvo.SvoError) as e:
+        pysvo.VoxelOctree.build_from_ply(tmp_path / "missing.ply", 64)
+    assert e.value.status == 2

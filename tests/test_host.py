@@ -236,3 +236,31 @@ def test_oct_beyond_two_gib(pysvo, tmp_path):
     assert w2.size == n_words and np.array_equal(c2, center)
     assert np.array_equal(w2[marks], words[marks]) and np.array_equal(w2[-3:], words[-3:])
     assert int(np.count_nonzero(w2)) == int(np.count_nonzero(words))
+
+
+def test_ply_reader_matches_oracle(pysvo, port, tmp_path):
+    """svo_ply_read_triangles (the product's PLY reader + PlyLoader's vertex rescaling, fans and face normals,
+    PlyLoader.cpp:64-226) against the restatement the voxeliser oracle is built on, bit for bit, for every
+    container variant; malformed files are reported."""
+    from ply_meshes import write_variants
+    from tools import make_scenes
+    ico = tmp_path / "ico5.ply"
+    assert make_scenes.gen_lib().svo_scene_icosphere_ply(str(ico).encode(), 5, 7) > 0
+    for name, p in [("ico5", ico)] + write_variants(tmp_path):
+        a, lo, hi = pysvo.ply_read_triangles(p)
+        b, lo2, hi2 = port.ply_triangles(p)
+        assert a.shape == b.shape and a.shape[0] > 100, name
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), name
+        assert np.array_equal(lo, lo2) and np.array_equal(hi, hi2), name
+        assert (a[:, :9].min() >= 0.0) and (a[:, :9].max() <= 1.0)          # rescaled to the unit box
+    with pytest.raises(pysvo.SvoError) as e:
+        pysvo.ply_read_triangles(tmp_path / "missing.ply")
+    assert e.value.status == 2
+    raw = ico.read_bytes()
+    for name, blob in [("notply.ply", b"plx\n" + raw[4:]), ("short.ply", raw[:len(raw) // 2]),
+                       ("nofaces.ply", raw.replace(b"element face", b"element fac_"))]:
+        q = tmp_path / name
+        q.write_bytes(blob)
+        with pytest.raises(pysvo.SvoError) as e:
+            pysvo.ply_read_triangles(q)
+        assert e.value.status == 3, name

@@ -207,3 +207,37 @@ def test_port_preview_stride_equals_reference(port, ref, dragon_words):
             assert np.array_equal(ours, theirs)
             assert cf.rays < cf_full.rays / 6 and not np.array_equal(ours, full)
     ref.tree_destroy(h)
+
+
+# ---- row f3: the voxeliser restatement (oracle/svo_oracle_ply.c) ----------------------------------
+
+def _ico_ply(path, freq):
+    from tools import make_scenes
+    assert make_scenes.gen_lib().svo_scene_icosphere_ply(str(path).encode(), freq, make_scenes.SEED) > 0
+    return path
+
+
+def test_voxeliser_port_equals_reference(port, ref, tmp_path):
+    """PlyLoader + VoxelData(loader, res, mem) + VoxelOctree (reference src/Main.cpp:320-325): the volume the
+    restatement voxelises must hold exactly the voxels of the tree the reference builds from the same PLY (same
+    thread-pool size: the result depends on it), and the builder restatement must turn it into the same node
+    array -- for the benchmark's icosphere and for ASCII / big-endian / normals / colours / polygon variants."""
+    from ply_meshes import write_variants
+    threads = ref.hardware_threads()
+    cases = [(_ico_ply(tmp_path / "ico6.ply", 6), 64), (_ico_ply(tmp_path / "ico20.ply", 20), 128)]
+    # (not the big-endian variant: the reference's plyfile moves raw big-endian floats through a double, which
+    # quiets the byte-swapped patterns that happen to be signalling NaNs and so alters a few coordinates)
+    cases += [(p, res) for name, p in write_variants(tmp_path) if not name.startswith("be_") for res in (48, 128)]
+    for ply, res in cases:
+        h = ref.tree_build_ply(ply, res, 1 << 30)
+        words, center = ref.tree_words(h), ref.tree_center(h)
+        ref.tree_destroy(h)
+        vol, ntri = port.voxelize_ply(ply, res, threads)
+        d, hh, w = vol.shape
+        side = 1
+        while side < max(w, hh, d):
+            side *= 2
+        assert np.array_equal(vol, port.tree_to_volume(words, side, (w, hh, d))), (ply.name, res)
+        built, bcenter = port.build_octree(vol)
+        assert np.array_equal(built, words) and np.array_equal(bcenter, center), (ply.name, res)
+        assert ntri > 0 and int(np.count_nonzero(vol)) > 100
