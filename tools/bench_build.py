@@ -59,13 +59,73 @@ def rebuild_bench(scene):
     print(json.dumps(out))
 
 
+def ply_scene_bench(scene, live_reference):
+    """Row f3 + f2: the benchmark's mesh (tools/scene_gen.c icosphere PLY) -> tree in HBM, against the tree the
+    reference's PlyLoader + VoxelData + VoxelOctree made from the same PLY (cached scene, or a live run)."""
+    kind, res, freq = make_scenes.SCENES[scene]
+    assert kind == "ico", "not a mesh scene"
+    tmp = Path(tempfile.mkdtemp(prefix="svo_ply_"))
+    ply = tmp / f"{scene}.ply"
+    t = time.perf_counter()
+    tris = make_scenes.gen_lib().svo_scene_icosphere_ply(str(ply).encode(), freq, make_scenes.SEED)
+    out = {"scene": scene, "resolution": res, "triangles": int(tris), "ply_bytes": ply.stat().st_size,
+           "generate_ply_s": round(time.perf_counter() - t, 2), "host_cores": os.cpu_count()}
+    meta_path = make_scenes.scene_path(scene).with_suffix(".json")
+    meta = json.loads(meta_path.read_text()) if meta_path.exists() else {}
+    mem = int(meta.get("builder_mem", make_scenes.builder_memory_budget()))
+    threads = int(meta.get("builder_threads", 8))       # the cached scenes were built on an 8-thread host
+    want = None
+    if live_reference:
+        from oracle.pyoracle import Ref
+        ref = Ref()
+        threads = ref.hardware_threads()
+        t = time.perf_counter()
+        h = ref.tree_build_ply(ply, res, mem)
+        out["reference_build_s"] = round(time.perf_counter() - t, 2)
+        want = ref.tree_words(h)
+        ref.tree_destroy(h)
+    elif make_scenes.scene_available(scene):
+        want, _ = make_scenes.load_scene(scene)
+        out["reference_build_s_when_the_scene_was_made"] = meta.get("seconds", {}).get("reference_builder")
+    out["reference_pool_threads"] = threads
+    out["reference_mem_budget"] = mem
+    pysvo.VoxelOctree(ROOT / "tests" / "golden" / "XYZRGB-Dragon.oct").close()
+    best = None
+    for _ in range(2):
+        t = time.perf_counter()
+        tree = pysvo.VoxelOctree.build_from_ply(ply, res, mem_budget=mem, threads=threads)
+        dt = time.perf_counter() - t
+        vs, bs = pysvo.VoxelOctree.last_voxelize_stats(), pysvo.VoxelOctree.last_build_stats()
+        if best is None or dt < best[0]:
+            best = (dt, {"overlap_ms": vs.overlap_ms, "sort_ms": vs.sort_ms, "fold_ms": vs.fold_ms,
+                         "cell_records": int(vs.cell_records), "voxels": int(vs.voxels), "dims": list(vs.dims),
+                         "cache_block": int(vs.cache_block), "sub_block": list(vs.sub_block)},
+                    {k: getattr(bs, k) for k, _ in bs._fields_})
+        got = tree.words()
+        tree.close()
+    out["gpu_ply_to_tree_s"] = round(best[0], 3)
+    out["voxelize"] = {k: (round(v, 3) if isinstance(v, float) else v) for k, v in best[1].items()}
+    out["build"] = {k: (round(v, 3) if isinstance(v, float) else v) for k, v in best[2].items()}
+    out["voxelize_device_ms"] = round(best[1]["overlap_ms"] + best[1]["sort_ms"] + best[1]["fold_ms"], 3)
+    out["build_device_ms"] = round(sum(best[2][k] for k in ("gather_ms", "sort_ms", "levels_ms", "emit_ms")), 3)
+    out["words"] = int(got.size)
+    if want is not None:
+        out["identical_words"] = bool(got.size == want.size and np.array_equal(got, want))
+    ply.unlink()
+    print(json.dumps(out))
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--ply-scene", default=None, help="mesh scene name (ico256 .. ico8192): PLY -> tree on the GPU")
+    ap.add_argument("--live-reference", action="store_true", help="with --ply-scene: run the reference builder now")
     ap.add_argument("--rebuild", default=None, help="scene name: time extract + build of a cached reference-built tree")
     ap.add_argument("--res", type=int, default=512)
     ap.add_argument("--no-reference", action="store_true")
     ap.add_argument("--dir", default=None)
     a = ap.parse_args()
+    if a.ply_scene:
+        return ply_scene_bench(a.ply_scene, a.live_reference)
     if a.rebuild:
         return rebuild_bench(a.rebuild)
     tmp = Path(a.dir or tempfile.mkdtemp(prefix="svo_build_"))

@@ -99,7 +99,7 @@ def make_scene(name: str, scratch: str | None = None, verbose: bool = True) -> P
         t2 = time.time()
         tmp_out = str(out) + ".tmp"
         ref.tree_save(h, tmp_out)          # the reference's own VoxelOctree::save
-        meta.update(n_words=int(ref.lib.svoref_tree_word_count(h)), builder_mem=mem,
+        meta.update(n_words=int(ref.lib.svoref_tree_word_count(h)), builder_mem=mem, builder_threads=ref.hardware_threads(),
                     seconds={"generate_input": round(t1 - t0, 2), "reference_builder": round(t2 - t1, 2),
                              "save": round(time.time() - t2, 2)})
         ref.tree_destroy(h)
