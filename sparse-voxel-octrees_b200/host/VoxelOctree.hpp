@@ -73,6 +73,13 @@ public:
         check(svo_tree_build_from_voxel_file(path, device, &tree), "VoxelOctree::fromVoxelFile");
         return new VoxelOctree(tree);
     }
+    // PlyLoader(path) + VoxelData(loader, resolution, mem) + VoxelOctree(VoxelData*), Main.cpp:320-325. memBudget 0 =
+    // the reference's 1 GiB, threads 0 = this host's hardware threads (the reference's pool size shapes the result).
+    static VoxelOctree *fromPly(const char *path, int resolution = 256, uint64 memBudget = 0, int threads = 0, int device = 0) {
+        svo_tree *tree = 0;
+        check(svo_tree_build_from_ply(path, resolution, memBudget, threads, device, &tree), "VoxelOctree::fromPly");
+        return new VoxelOctree(tree);
+    }
     // Dense w*h*d grid of material words (x fastest, 0 = empty).
     static VoxelOctree *fromVoxels(const uint32 *voxels, int w, int h, int d, int device = 0) {
         svo_tree *tree = 0;
