@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <thread>
 
 namespace svo {
 
@@ -39,20 +40,42 @@ struct Element { std::string name; long long count = 0; std::vector<Property> pr
 
 struct FileCloser { void operator()(FILE *f) const { if (f) fclose(f); } };
 
+// Cursor over the element data, which is held in memory as a whole: a 10 M-triangle file is 55 M scalars,
+// and one fread per scalar costs more than everything the GPU does with the mesh afterwards.
 class Reader {
 public:
-    Reader(FILE *fp, int format) : fp_(fp), format_(format) {}
+    Reader(const uint8_t *begin, const uint8_t *end, int format) : p_(begin), end_(end), format_(format) {}
     bool ok = true;
+    const uint8_t *position() const { return p_; }
     double scalar(PlyType type) {
         if (format_ == 0) {
-            double v = 0.0;
-            if (fscanf(fp_, "%lf", &v) != 1) ok = false;
+            while (p_ < end_ && (*p_ == ' ' || *p_ == '\n' || *p_ == '\r' || *p_ == '\t')) ++p_;
+            if (p_ >= end_) { ok = false; return 0.0; }
+            char *stop = nullptr;
+            const double v = strtod(reinterpret_cast<const char *>(p_), &stop);   // the buffer is NUL-terminated
+            if (stop == reinterpret_cast<const char *>(p_)) { ok = false; return 0.0; }
+            p_ = reinterpret_cast<const uint8_t *>(stop);
             return v;
         }
+        const int n = kSize[type];
+        if (end_ - p_ < n) { ok = false; return 0.0; }
+        const double v = decode(p_, type, format_);
+        p_ += n;
+        return v;
+    }
+    void skip(const Property &p) {
+        if (p.isList) {
+            const long long n = (long long)scalar(p.countType);
+            for (long long k = 0; k < n && ok; ++k) scalar(p.type);
+        } else {
+            scalar(p.type);
+        }
+    }
+    static double decode(const uint8_t *src, PlyType type, int format) {
         unsigned char b[8];
         const int n = kSize[type];
-        if (fread(b, 1, size_t(n), fp_) != size_t(n)) { ok = false; return 0.0; }
-        if (format_ == 2) for (int i = 0; i < n/2; ++i) std::swap(b[i], b[n - 1 - i]);
+        memcpy(b, src, size_t(n));
+        if (format == 2) for (int i = 0; i < n/2; ++i) std::swap(b[i], b[n - 1 - i]);
         switch (type) {
         case kChar: return double(static_cast<signed char>(b[0]));
         case kUchar: return double(b[0]);
@@ -64,17 +87,9 @@ public:
         default: { double v; memcpy(&v, b, 8); return v; }
         }
     }
-    void skip(const Property &p) {
-        if (p.isList) {
-            const long long n = (long long)scalar(p.countType);
-            for (long long k = 0; k < n && ok; ++k) scalar(p.type);
-        } else {
-            scalar(p.type);
-        }
-    }
 
 private:
-    FILE *fp_;
+    const uint8_t *p_, *end_;
     int format_;
 };
 
@@ -82,6 +97,43 @@ inline float minStd(float a, float b) { return (b < a) ? b : a; }   // std::min(
 inline float maxStd(float a, float b) { return (a < b) ? b : a; }   // std::max(a, b)
 
 struct Vertex { float pos[3], normal[3], color[3]; };
+
+int workerCount(size_t items) {
+    int n = int(std::thread::hardware_concurrency());
+    if (n > 16) n = 16;
+    if (n < 1 || items < 65536) n = 1;
+    return n;
+}
+
+template <class Fn>
+void parallelRanges(size_t items, Fn fn) {      // fn(threadIndex, begin, end)
+    const int n = workerCount(items);
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n; ++t) pool.emplace_back(fn, t, items*size_t(t)/size_t(n), items*size_t(t + 1)/size_t(n));
+    fn(0, size_t(0), items/size_t(n));
+    for (auto &th : pool) th.join();
+}
+
+// Triangle::Triangle (:40-54) + the face normal of meshes without vertex normals (:213-218)
+inline void makeTriangle(const Vertex &a, const Vertex &b, const Vertex &c, bool hasNormals, MeshTriangle &t) {
+    const Vertex *vs[3] = {&a, &b, &c};
+    for (int w = 0; w < 3; ++w) {
+        memcpy(t.pos[w], vs[w]->pos, 12);
+        memcpy(t.normal[w], vs[w]->normal, 12);
+        memcpy(t.color[w], vs[w]->color, 12);
+    }
+    for (int q = 0; q < 3; ++q) {
+        t.lower[q] = minStd(t.pos[0][q], minStd(t.pos[1][q], t.pos[2][q]));
+        t.upper[q] = maxStd(t.pos[0][q], maxStd(t.pos[1][q], t.pos[2][q]));
+    }
+    if (!hasNormals) {
+        float e1[3], e2[3];
+        for (int q = 0; q < 3; ++q) { e1[q] = t.pos[1][q] - t.pos[0][q]; e2[q] = t.pos[2][q] - t.pos[0][q]; }
+        const float n[3] = {e1[1]*e2[2] - e1[2]*e2[1], e1[2]*e2[0] - e1[0]*e2[2], e1[0]*e2[1] - e1[1]*e2[0]};
+        const float inv = 1.0f/std::sqrt(n[0]*n[0] + n[1]*n[1] + n[2]*n[2]);
+        for (int w = 0; w < 3; ++w) { t.normal[w][0] = n[0]*inv; t.normal[w][1] = n[1]*inv; t.normal[w][2] = n[2]*inv; }
+    }
+}
 
 } // namespace
 
@@ -121,36 +173,76 @@ bool readPlyMesh(const char *path, Mesh &out, std::string &err, int &status) {
     for (const Element &e : elements) { hasVerts |= e.name == "vertex"; hasFaces |= e.name == "face"; }
     if (!hasVerts || !hasFaces) { err = "PLY file has to have triangles and vertices"; status = 3; return false; }   // :100
 
+    // the element data, whole, NUL-terminated for strtod
+    const off_t dataStart = ftello(fp.get());
+    fseeko(fp.get(), 0, SEEK_END);
+    const off_t fileEnd = ftello(fp.get());
+    fseeko(fp.get(), dataStart, SEEK_SET);
+    std::vector<uint8_t> data(size_t(fileEnd - dataStart) + 1, 0);
+    if (fread(data.data(), 1, data.size() - 1, fp.get()) != data.size() - 1) { err = std::string("cannot read ") + path; status = 2; return false; }
+    fp.reset();
+    const uint8_t *const dataEnd = data.data() + data.size() - 1;
+
     static const char *vpNames[9] = {"x", "y", "z", "nx", "ny", "nz", "red", "green", "blue"};
     const float vertDefault[9] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 255.0f, 255.0f, 255.0f};
     std::vector<Vertex> verts;
     bool vertsRead = false, hasNormals = false;
     float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
-    Reader in(fp.get(), format);
+    Reader in(data.data(), dataEnd, format);
     out.tris.clear();
 
     for (const Element &e : elements) {
         if (e.name == "vertex") {
             std::vector<int> slot(e.props.size(), -1);
             bool avail[9] = {false};
-            for (size_t p = 0; p < e.props.size(); ++p)
+            bool fixedSize = format != 0;
+            size_t stride = 0;
+            std::vector<size_t> offsets(e.props.size(), 0);
+            for (size_t p = 0; p < e.props.size(); ++p) {
                 for (int t = 0; t < 9; ++t)
                     if (!e.props[p].isList && e.props[p].name == vpNames[t]) { slot[p] = t; avail[t] = true; break; }
+                if (e.props[p].isList) fixedSize = false;
+                offsets[p] = stride;
+                stride += size_t(kSize[e.props[p].type]);
+            }
             hasNormals = avail[3] && avail[4] && avail[5];
             if (e.count < 0 || e.count > 0x7FFFFFFF) { err = "bad vertex count"; status = 3; return false; }
             verts.resize(size_t(e.count));
-            for (long long i = 0; i < e.count; ++i) {
-                float data[9];
-                memcpy(data, vertDefault, sizeof data);
-                for (size_t p = 0; p < e.props.size(); ++p) {
-                    if (slot[p] >= 0) data[slot[p]] = float(in.scalar(e.props[p].type));
-                    else in.skip(e.props[p]);
+            auto store = [&](size_t i, const float *v9, float *tlo, float *thi) {
+                memcpy(verts[i].pos, v9, 12);
+                memcpy(verts[i].normal, v9 + 3, 12);
+                memcpy(verts[i].color, v9 + 6, 12);
+                for (int t = 0; t < 3; ++t) { tlo[t] = minStd(tlo[t], v9[t]); thi[t] = maxStd(thi[t], v9[t]); }   // :160-163
+            };
+            if (fixedSize) {
+                // binary records of one size: decoded on all cores (min / max do not depend on the order)
+                const uint8_t *base = in.position();
+                if (size_t(dataEnd - base) < stride*size_t(e.count)) { err = std::string(path) + ": short read in the vertex data"; status = 3; return false; }
+                std::vector<float> los(16*3, 1e30f), his(16*3, -1e30f);
+                parallelRanges(size_t(e.count), [&](int th, size_t begin, size_t end) {
+                    for (size_t i = begin; i < end; ++i) {
+                        float v9[9];
+                        memcpy(v9, vertDefault, sizeof v9);
+                        const uint8_t *rec = base + i*stride;
+                        for (size_t p = 0; p < e.props.size(); ++p)
+                            if (slot[p] >= 0) v9[slot[p]] = float(Reader::decode(rec + offsets[p], e.props[p].type, format));
+                        store(i, v9, &los[size_t(th)*3], &his[size_t(th)*3]);
+                    }
+                });
+                for (int th = 0; th < 16; ++th)
+                    for (int t = 0; t < 3; ++t) { lo[t] = minStd(lo[t], los[size_t(th)*3 + t]); hi[t] = maxStd(hi[t], his[size_t(th)*3 + t]); }
+                in = Reader(base + stride*size_t(e.count), dataEnd, format);
+            } else {
+                for (long long i = 0; i < e.count; ++i) {
+                    float v9[9];
+                    memcpy(v9, vertDefault, sizeof v9);
+                    for (size_t p = 0; p < e.props.size(); ++p) {
+                        if (slot[p] >= 0) v9[slot[p]] = float(in.scalar(e.props[p].type));
+                        else in.skip(e.props[p]);
+                    }
+                    if (!in.ok) { err = std::string(path) + ": short read in the vertex data"; status = 3; return false; }
+                    store(size_t(i), v9, lo, hi);
                 }
-                if (!in.ok) { err = std::string(path) + ": short read in the vertex data"; status = 3; return false; }
-                memcpy(verts[size_t(i)].pos, data, 12);
-                memcpy(verts[size_t(i)].normal, data + 3, 12);
-                memcpy(verts[size_t(i)].color, data + 6, 12);
-                for (int t = 0; t < 3; ++t) { lo[t] = minStd(lo[t], data[t]); hi[t] = maxStd(hi[t], data[t]); }
             }
             // rescaleVertices, :167-181
             const float diff[3] = {hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]};
@@ -158,46 +250,67 @@ bool readPlyMesh(const char *path, Mesh &out, std::string &err, int &status) {
             if (diff[0] > diff[1] && diff[0] > diff[2]) largest = 0;
             else if (diff[1] > diff[2]) largest = 1;
             const float factor = 1.0f/diff[largest];
-            for (Vertex &v : verts)
-                for (int t = 0; t < 3; ++t) v.pos[t] = (v.pos[t] - lo[t])*factor;
+            parallelRanges(verts.size(), [&](int, size_t begin, size_t end) {
+                for (size_t i = begin; i < end; ++i)
+                    for (int t = 0; t < 3; ++t) verts[i].pos[t] = (verts[i].pos[t] - lo[t])*factor;
+            });
             for (int t = 0; t < 3; ++t) { hi[t] *= factor; lo[t] *= factor; }
             vertsRead = true;
         } else if (e.name == "face") {
             if (!vertsRead) { err = "PLY faces before vertices are not supported"; status = 3; return false; }
+            if (e.count < 0) { err = "bad face count"; status = 3; return false; }
+            // pass 1 (sequential, cheap): where every face's index list starts, how long it is, and where
+            // its triangles go (a polygon of k vertices is a fan of k - 2 triangles, :207-221)
+            struct FaceRef { const uint8_t *indices; uint32_t count; uint64_t firstTriangle; };
+            std::vector<FaceRef> faces;
+            std::vector<long long> asciiIndices;        // ASCII: indices parsed in pass 1
+            faces.reserve(size_t(e.count));
+            const Property *listProp = nullptr;
+            uint64_t nTriangles = 0;
             for (long long i = 0; i < e.count; ++i) {
+                FaceRef f = {nullptr, 0, nTriangles};
                 for (const Property &pr : e.props) {
                     if (!(pr.isList && pr.name == "vertex_indices")) { in.skip(pr); continue; }
+                    listProp = &pr;
                     const long long cnt = (long long)in.scalar(pr.countType);
-                    long long v0 = 0, v1 = 0;
-                    for (long long k = 0; k < cnt && in.ok; ++k) {
-                        const long long idx = (long long)in.scalar(pr.type);
-                        if (idx < 0 || size_t(idx) >= verts.size()) { err = "PLY face refers to a vertex that does not exist"; status = 3; return false; }
-                        if (k == 0) { v0 = idx; continue; }
-                        if (k == 1) { v1 = idx; continue; }
-                        MeshTriangle t;
-                        const Vertex *vs[3] = {&verts[size_t(v0)], &verts[size_t(v1)], &verts[size_t(idx)]};
-                        for (int w = 0; w < 3; ++w) {
-                            memcpy(t.pos[w], vs[w]->pos, 12);
-                            memcpy(t.normal[w], vs[w]->normal, 12);
-                            memcpy(t.color[w], vs[w]->color, 12);
-                        }
-                        for (int q = 0; q < 3; ++q) {                                   // Triangle::Triangle, :40-54
-                            t.lower[q] = minStd(t.pos[0][q], minStd(t.pos[1][q], t.pos[2][q]));
-                            t.upper[q] = maxStd(t.pos[0][q], maxStd(t.pos[1][q], t.pos[2][q]));
-                        }
-                        if (!hasNormals) {                                              // :213-218
-                            float e1[3], e2[3];
-                            for (int q = 0; q < 3; ++q) { e1[q] = t.pos[1][q] - t.pos[0][q]; e2[q] = t.pos[2][q] - t.pos[0][q]; }
-                            const float n[3] = {e1[1]*e2[2] - e1[2]*e2[1], e1[2]*e2[0] - e1[0]*e2[2], e1[0]*e2[1] - e1[1]*e2[0]};
-                            const float inv = 1.0f/std::sqrt(n[0]*n[0] + n[1]*n[1] + n[2]*n[2]);
-                            for (int w = 0; w < 3; ++w) { t.normal[w][0] = n[0]*inv; t.normal[w][1] = n[1]*inv; t.normal[w][2] = n[2]*inv; }
-                        }
-                        out.tris.push_back(t);
-                        v1 = idx;
+                    if (!in.ok || cnt < 0 || cnt > 0x7FFFFFFF) { in.ok = false; break; }
+                    f.count = uint32_t(cnt);
+                    if (format == 0) {
+                        f.indices = reinterpret_cast<const uint8_t *>(uintptr_t(asciiIndices.size()));
+                        for (long long k = 0; k < cnt && in.ok; ++k) asciiIndices.push_back((long long)in.scalar(pr.type));
+                    } else {
+                        f.indices = in.position();
+                        const size_t bytes = size_t(cnt)*size_t(kSize[pr.type]);
+                        if (size_t(dataEnd - in.position()) < bytes) { in.ok = false; break; }
+                        in = Reader(in.position() + bytes, dataEnd, format);
                     }
                 }
                 if (!in.ok) { err = std::string(path) + ": short read in the face data"; status = 3; return false; }
+                if (f.count >= 3) nTriangles += f.count - 2;
+                faces.push_back(f);
             }
+            // pass 2 (all cores): assemble the triangles in place
+            const size_t firstOut = out.tris.size();
+            out.tris.resize(firstOut + size_t(nTriangles));
+            std::vector<char> bad(16, 0);
+            parallelRanges(faces.size(), [&](int th, size_t begin, size_t end) {
+                for (size_t i = begin; i < end; ++i) {
+                    const FaceRef &f = faces[i];
+                    long long v0 = 0, v1 = 0;
+                    for (uint32_t k = 0; k < f.count; ++k) {
+                        long long idx;
+                        if (format == 0) idx = asciiIndices[size_t(uintptr_t(f.indices)) + k];
+                        else idx = (long long)Reader::decode(f.indices + size_t(k)*size_t(kSize[listProp->type]), listProp->type, format);
+                        if (idx < 0 || size_t(idx) >= verts.size()) { bad[size_t(th)] = 1; break; }
+                        if (k == 0) { v0 = idx; continue; }
+                        if (k == 1) { v1 = idx; continue; }
+                        makeTriangle(verts[size_t(v0)], verts[size_t(v1)], verts[size_t(idx)], hasNormals,
+                                     out.tris[firstOut + size_t(f.firstTriangle) + (k - 2)]);
+                        v1 = idx;
+                    }
+                }
+            });
+            for (char b : bad) if (b) { err = "PLY face refers to a vertex that does not exist"; status = 3; return false; }
         } else {
             for (long long i = 0; i < e.count && in.ok; ++i)
                 for (const Property &pr : e.props) in.skip(pr);

@@ -25,6 +25,7 @@
 #include "svo_kernels.cuh"
 #include "svo_voxelize.cuh"
 
+#include <chrono>
 #include <thread>
 
 namespace {
@@ -768,16 +769,25 @@ int svo_tree_build_from_ply(const char *path, int resolution, uint64_t mem_budge
     svo::Mesh mesh;
     std::string err;
     int status = 0;
+    const bool debugTiming = getenv("SVO_BUILD_DEBUG") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto since = [](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t).count(); };
+    auto t0 = now();
     if (!svo::readPlyMesh(path, mesh, err, status)) return fail(status, "%s", err.c_str());
+    if (debugTiming) fprintf(stderr, "[svo] PLY read + triangle assembly: %.3f s (%zu triangles)\n", since(t0), mesh.tris.size());
     if (mem_budget == 0) mem_budget = uint64_t(1024)*1024*1024;                   // Main.cpp:269
     if (threads <= 0) threads = int(std::thread::hardware_concurrency());
     if (threads <= 0) threads = 1;
     SVO_DEVICE(device);
     svo::OctreeBuilder builder;
     svo::VoxelizeStats vs;
+    t0 = now();
     if (!svo::voxelizeMesh(mesh, resolution, mem_budget, threads, builder, vs, err))
         return fail(SVO_ERR_INVALID_ARGUMENT, "voxelisation: %s", err.c_str());
+    if (debugTiming) fprintf(stderr, "[svo] upload + voxelise (wall): %.3f s\n", since(t0));
+    t0 = now();
     st = finishBuild(builder, device, out);
+    if (debugTiming) fprintf(stderr, "[svo] octree build (wall): %.3f s\n", since(t0));
     if (st != SVO_OK) return st;
     g_voxelizeStats.triangles = vs.triangles;
     g_voxelizeStats.cell_records = vs.cellRecords;

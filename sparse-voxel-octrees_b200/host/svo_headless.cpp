@@ -8,11 +8,12 @@
 // --raw streams every frame as packed RGB24 (row-major, no header) to a file or to stdout ("-"), the
 // input format of `ffmpeg -f rawvideo -pix_fmt rgb24 -s WxH -i -`: the streamed stand-in for the
 // reference's interactive SDL window; status text goes to stderr then.
-//   svo_headless -builder <in.voxel> <out.oct>
+//   svo_headless -builder [--resolution r --mode m] <in.ply | in.voxel> <out.oct>
 //
-// The second form is the reference's `-builder` mode for a raw voxel volume (the on-disk path of
-// reference src/Main.cpp:313-319 after PlyLoader::convertToVolume): VoxelData(path) + VoxelOctree(VoxelData*)
-// + save, with the tree built in HBM.
+// The second form is the reference's `-builder` mode with its own argument layout (reference
+// src/Main.cpp:291-330): a PLY mesh is voxelised and the tree built on the GPU (PlyLoader + VoxelData +
+// VoxelOctree, :320-325; the mode flag is accepted and ignored: nothing goes through the disk), a raw
+// .voxel volume takes the on-disk path's second half (VoxelData(path) + VoxelOctree, :318-319); then save.
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -44,16 +45,23 @@ int main(int argc, char **argv) {
         return 2;
     }
     if (std::string(argv[1]) == "-builder") {
-        if (argc != 4) { fprintf(stderr, "usage: %s -builder <in.voxel> <out.oct>\n", argv[0]); return 2; }
+        // the reference's argument forms (Main.cpp:291-300): -builder --resolution r --mode m in out | -builder in out
+        int resolution = 256;
+        const char *input = 0, *output = 0;
+        if (argc == 8) { resolution = atoi(argv[3]); input = argv[6]; output = argv[7]; }
+        else if (argc == 4) { input = argv[2]; output = argv[3]; }
+        else { fprintf(stderr, "usage: %s -builder [--resolution r --mode m] <in.ply | in.voxel> <out.oct>\n", argv[0]); return 2; }
         try {
             auto t0 = std::chrono::steady_clock::now();
-            VoxelOctree *tree = VoxelOctree::fromVoxelFile(argv[2]);
+            const std::string in = input;
+            const bool isPly = in.size() >= 4 && in.compare(in.size() - 4, 4, ".ply") == 0;
+            VoxelOctree *tree = isPly ? VoxelOctree::fromPly(input, resolution) : VoxelOctree::fromVoxelFile(input);
             svo_build_stats st;
             svo_build_last_stats(&st);
-            tree->save(argv[3]);
+            tree->save(output);
             double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
             printf("built %s: %llu voxels -> %llu words (depth %u, %llu far blocks), device %.3f ms; "
-                   "Octree initialization took %.3f s\n", argv[3], (unsigned long long)st.voxels,
+                   "Octree initialization took %.3f s\n", output, (unsigned long long)st.voxels,
                    (unsigned long long)tree->wordCount(), tree->depth(), (unsigned long long)st.far_blocks,
                    st.gather_ms + st.sort_ms + st.levels_ms + st.emit_ms, s);
             delete tree;

@@ -222,6 +222,15 @@ def test_headless_builder_mode(pysvo, port, tmp_path):
     res = subprocess.run([str(pkg / "svo_headless"), "-builder", str(tmp_path / "nope.voxel"), str(out)],
                          capture_output=True, text=True, timeout=300)
     assert res.returncode == 1 and "cannot open" in res.stderr
+    # the reference's long form with a mesh: -builder --resolution r --mode m in.ply out.oct
+    ply, out2 = _ico_ply(tmp_path / "ico10.ply", 10), tmp_path / "mesh.oct"
+    res = subprocess.run([str(pkg / "svo_headless"), "-builder", "--resolution", "96", "--mode", "0", str(ply), str(out2)],
+                         capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr
+    tree = pysvo.VoxelOctree.build_from_ply(ply, 96)
+    words2, _ = pysvo.oct_read(out2)
+    assert np.array_equal(words2, tree.words())
+    tree.close()
 
 
 def _ico_ply(path, freq):

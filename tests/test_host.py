@@ -246,7 +246,9 @@ def test_ply_reader_matches_oracle(pysvo, port, tmp_path):
     from tools import make_scenes
     ico = tmp_path / "ico5.ply"
     assert make_scenes.gen_lib().svo_scene_icosphere_ply(str(ico).encode(), 5, 7) > 0
-    for name, p in [("ico5", ico)] + write_variants(tmp_path):
+    big = tmp_path / "ico100.ply"       # 200,000 triangles: the reader's multi-threaded paths
+    assert make_scenes.gen_lib().svo_scene_icosphere_ply(str(big).encode(), 100, 7) > 0
+    for name, p in [("ico5", ico), ("ico100", big)] + write_variants(tmp_path):
         a, lo, hi = pysvo.ply_read_triangles(p)
         b, lo2, hi2 = port.ply_triangles(p)
         assert a.shape == b.shape and a.shape[0] > 100, name
