@@ -18,8 +18,13 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <memory>
 #include <thread>
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <unistd.h>
 
 namespace svo {
 
@@ -96,8 +101,6 @@ private:
 inline float minStd(float a, float b) { return (b < a) ? b : a; }   // std::min(a, b)
 inline float maxStd(float a, float b) { return (a < b) ? b : a; }   // std::max(a, b)
 
-struct Vertex { float pos[3], normal[3], color[3]; };
-
 int workerCount(size_t items) {
     int n = int(std::thread::hardware_concurrency());
     if (n > 16) n = 16;
@@ -115,8 +118,8 @@ void parallelRanges(size_t items, Fn fn) {      // fn(threadIndex, begin, end)
 }
 
 // Triangle::Triangle (:40-54) + the face normal of meshes without vertex normals (:213-218)
-inline void makeTriangle(const Vertex &a, const Vertex &b, const Vertex &c, bool hasNormals, MeshTriangle &t) {
-    const Vertex *vs[3] = {&a, &b, &c};
+inline void makeTriangle(const MeshVertex &a, const MeshVertex &b, const MeshVertex &c, bool hasNormals, MeshTriangle &t) {
+    const MeshVertex *vs[3] = {&a, &b, &c};
     for (int w = 0; w < 3; ++w) {
         memcpy(t.pos[w], vs[w]->pos, 12);
         memcpy(t.normal[w], vs[w]->normal, 12);
@@ -135,7 +138,55 @@ inline void makeTriangle(const Vertex &a, const Vertex &b, const Vertex &c, bool
     }
 }
 
+// The element data, whole: binary files are mapped (no copy; the kernel's page cache is the buffer), ASCII
+// files are read into a NUL-terminated buffer for strtod.
+class FileData {
+public:
+    ~FileData() {
+        if (map_ && map_ != MAP_FAILED) munmap(map_, mapBytes_);
+    }
+    bool open(const char *path, off_t dataStart, off_t fileEnd, bool binary) {
+        const size_t n = size_t(fileEnd - dataStart);
+        if (binary && n > 0) {
+            const int fd = ::open(path, O_RDONLY);
+            if (fd < 0) return false;
+            map_ = mmap(nullptr, size_t(fileEnd), PROT_READ, MAP_PRIVATE, fd, 0);
+            ::close(fd);
+            if (map_ == MAP_FAILED) { map_ = nullptr; return false; }
+            mapBytes_ = size_t(fileEnd);
+            madvise(map_, mapBytes_, MADV_WILLNEED);
+            begin_ = static_cast<const uint8_t *>(map_) + dataStart;
+            end_ = begin_ + n;
+            return true;
+        }
+        std::unique_ptr<FILE, FileCloser> fp(fopen(path, "rb"));
+        if (!fp || fseeko(fp.get(), dataStart, SEEK_SET) != 0) return false;
+        text_.assign(n + 1, 0);
+        if (fread(text_.data(), 1, n, fp.get()) != n) return false;
+        begin_ = text_.data();
+        end_ = begin_ + n;
+        return true;
+    }
+    const uint8_t *begin() const { return begin_; }
+    const uint8_t *end() const { return end_; }
+
+private:
+    void *map_ = nullptr;
+    size_t mapBytes_ = 0;
+    std::vector<uint8_t> text_;
+    const uint8_t *begin_ = nullptr, *end_ = nullptr;
+};
+
 } // namespace
+
+void assembleTriangles(const Mesh &mesh, MeshTriangle *out) {
+    const uint32_t *idx = mesh.indices.data();
+    const MeshVertex *v = mesh.verts.data();
+    parallelRanges(mesh.triangleCount(), [&](int, size_t begin, size_t end) {
+        for (size_t i = begin; i < end; ++i)
+            makeTriangle(v[idx[3*i]], v[idx[3*i + 1]], v[idx[3*i + 2]], mesh.hasNormals, out[i]);
+    });
+}
 
 bool readPlyMesh(const char *path, Mesh &out, std::string &err, int &status) {
     status = 0;
@@ -173,23 +224,26 @@ bool readPlyMesh(const char *path, Mesh &out, std::string &err, int &status) {
     for (const Element &e : elements) { hasVerts |= e.name == "vertex"; hasFaces |= e.name == "face"; }
     if (!hasVerts || !hasFaces) { err = "PLY file has to have triangles and vertices"; status = 3; return false; }   // :100
 
-    // the element data, whole, NUL-terminated for strtod
     const off_t dataStart = ftello(fp.get());
     fseeko(fp.get(), 0, SEEK_END);
     const off_t fileEnd = ftello(fp.get());
-    fseeko(fp.get(), dataStart, SEEK_SET);
-    std::vector<uint8_t> data(size_t(fileEnd - dataStart) + 1, 0);
-    if (fread(data.data(), 1, data.size() - 1, fp.get()) != data.size() - 1) { err = std::string("cannot read ") + path; status = 2; return false; }
     fp.reset();
-    const uint8_t *const dataEnd = data.data() + data.size() - 1;
+    FileData data;
+    if (dataStart < 0 || fileEnd < dataStart || !data.open(path, dataStart, fileEnd, format != 0)) {
+        err = std::string("cannot read ") + path; status = 2; return false;
+    }
+    const uint8_t *const dataEnd = data.end();
 
     static const char *vpNames[9] = {"x", "y", "z", "nx", "ny", "nz", "red", "green", "blue"};
     const float vertDefault[9] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 255.0f, 255.0f, 255.0f};
-    std::vector<Vertex> verts;
-    bool vertsRead = false, hasNormals = false;
+    PodArray<MeshVertex> &verts = out.verts;
+    bool vertsRead = false;
     float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
-    Reader in(data.data(), dataEnd, format);
-    out.tris.clear();
+    Reader in(data.begin(), dataEnd, format);
+    out.indices.resize(0);
+    out.hasNormals = false;
+    size_t nIndices = 0;
+    const char *const noMemory = "out of host memory for the mesh";
 
     for (const Element &e : elements) {
         if (e.name == "vertex") {
@@ -205,9 +259,9 @@ bool readPlyMesh(const char *path, Mesh &out, std::string &err, int &status) {
                 offsets[p] = stride;
                 stride += size_t(kSize[e.props[p].type]);
             }
-            hasNormals = avail[3] && avail[4] && avail[5];
+            out.hasNormals = avail[3] && avail[4] && avail[5];
             if (e.count < 0 || e.count > 0x7FFFFFFF) { err = "bad vertex count"; status = 3; return false; }
-            verts.resize(size_t(e.count));
+            if (!verts.resize(size_t(e.count))) { err = noMemory; status = 4; return false; }
             auto store = [&](size_t i, const float *v9, float *tlo, float *thi) {
                 memcpy(verts[i].pos, v9, 12);
                 memcpy(verts[i].normal, v9 + 3, 12);
@@ -220,14 +274,17 @@ bool readPlyMesh(const char *path, Mesh &out, std::string &err, int &status) {
                 if (size_t(dataEnd - base) < stride*size_t(e.count)) { err = std::string(path) + ": short read in the vertex data"; status = 3; return false; }
                 std::vector<float> los(16*3, 1e30f), his(16*3, -1e30f);
                 parallelRanges(size_t(e.count), [&](int th, size_t begin, size_t end) {
+                    float tlo[3] = {1e30f, 1e30f, 1e30f}, thi[3] = {-1e30f, -1e30f, -1e30f};
                     for (size_t i = begin; i < end; ++i) {
                         float v9[9];
                         memcpy(v9, vertDefault, sizeof v9);
                         const uint8_t *rec = base + i*stride;
                         for (size_t p = 0; p < e.props.size(); ++p)
                             if (slot[p] >= 0) v9[slot[p]] = float(Reader::decode(rec + offsets[p], e.props[p].type, format));
-                        store(i, v9, &los[size_t(th)*3], &his[size_t(th)*3]);
+                        store(i, v9, tlo, thi);
                     }
+                    memcpy(&los[size_t(th)*3], tlo, 12);
+                    memcpy(&his[size_t(th)*3], thi, 12);
                 });
                 for (int th = 0; th < 16; ++th)
                     for (int t = 0; t < 3; ++t) { lo[t] = minStd(lo[t], los[size_t(th)*3 + t]); hi[t] = maxStd(hi[t], his[size_t(th)*3 + t]); }
@@ -259,57 +316,97 @@ bool readPlyMesh(const char *path, Mesh &out, std::string &err, int &status) {
         } else if (e.name == "face") {
             if (!vertsRead) { err = "PLY faces before vertices are not supported"; status = 3; return false; }
             if (e.count < 0) { err = "bad face count"; status = 3; return false; }
-            // pass 1 (sequential, cheap): where every face's index list starts, how long it is, and where
-            // its triangles go (a polygon of k vertices is a fan of k - 2 triangles, :207-221)
-            struct FaceRef { const uint8_t *indices; uint32_t count; uint64_t firstTriangle; };
-            std::vector<FaceRef> faces;
-            std::vector<long long> asciiIndices;        // ASCII: indices parsed in pass 1
-            faces.reserve(size_t(e.count));
             const Property *listProp = nullptr;
-            uint64_t nTriangles = 0;
-            for (long long i = 0; i < e.count; ++i) {
-                FaceRef f = {nullptr, 0, nTriangles};
-                for (const Property &pr : e.props) {
-                    if (!(pr.isList && pr.name == "vertex_indices")) { in.skip(pr); continue; }
-                    listProp = &pr;
-                    const long long cnt = (long long)in.scalar(pr.countType);
-                    if (!in.ok || cnt < 0 || cnt > 0x7FFFFFFF) { in.ok = false; break; }
-                    f.count = uint32_t(cnt);
-                    if (format == 0) {
-                        f.indices = reinterpret_cast<const uint8_t *>(uintptr_t(asciiIndices.size()));
-                        for (long long k = 0; k < cnt && in.ok; ++k) asciiIndices.push_back((long long)in.scalar(pr.type));
-                    } else {
-                        f.indices = in.position();
-                        const size_t bytes = size_t(cnt)*size_t(kSize[pr.type]);
-                        if (size_t(dataEnd - in.position()) < bytes) { in.ok = false; break; }
-                        in = Reader(in.position() + bytes, dataEnd, format);
-                    }
-                }
-                if (!in.ok) { err = std::string(path) + ": short read in the face data"; status = 3; return false; }
-                if (f.count >= 3) nTriangles += f.count - 2;
-                faces.push_back(f);
-            }
-            // pass 2 (all cores): assemble the triangles in place
-            const size_t firstOut = out.tris.size();
-            out.tris.resize(firstOut + size_t(nTriangles));
+            for (const Property &pr : e.props) if (pr.isList && pr.name == "vertex_indices") listProp = &pr;
             std::vector<char> bad(16, 0);
-            parallelRanges(faces.size(), [&](int th, size_t begin, size_t end) {
-                for (size_t i = begin; i < end; ++i) {
-                    const FaceRef &f = faces[i];
-                    long long v0 = 0, v1 = 0;
-                    for (uint32_t k = 0; k < f.count; ++k) {
-                        long long idx;
-                        if (format == 0) idx = asciiIndices[size_t(uintptr_t(f.indices)) + k];
-                        else idx = (long long)Reader::decode(f.indices + size_t(k)*size_t(kSize[listProp->type]), listProp->type, format);
-                        if (idx < 0 || size_t(idx) >= verts.size()) { bad[size_t(th)] = 1; break; }
-                        if (k == 0) { v0 = idx; continue; }
-                        if (k == 1) { v1 = idx; continue; }
-                        makeTriangle(verts[size_t(v0)], verts[size_t(v1)], verts[size_t(idx)], hasNormals,
-                                     out.tris[firstOut + size_t(f.firstTriangle) + (k - 2)]);
-                        v1 = idx;
+            const size_t nVerts = verts.size();
+
+            // Fast path -- what mesh exporters write: binary, the index list is the only property and every face
+            // is a triangle. If the face data is exactly count * (count field + 3 indices) bytes long and every
+            // count field AT THOSE STRIDES reads 3, then (by induction from the first record) that is the parse;
+            // checked and decoded on all cores in one sweep. Anything else takes the general path below.
+            bool fastDone = false;
+            if (format != 0 && listProp && e.props.size() == 1 && &e == &elements.back() && e.count > 0) {
+                const size_t cs = size_t(kSize[listProp->countType]), is = size_t(kSize[listProp->type]), rec = cs + 3*is;
+                const uint8_t *base = in.position();
+                if (size_t(dataEnd - base) == rec*size_t(e.count)) {
+                    if (!out.indices.resize(nIndices + 3*size_t(e.count))) { err = noMemory; status = 4; return false; }
+                    uint32_t *dst = out.indices.data() + nIndices;
+                    std::vector<char> notTriangles(16, 0);
+                    parallelRanges(size_t(e.count), [&](int th, size_t begin, size_t end) {
+                        for (size_t i = begin; i < end; ++i) {
+                            const uint8_t *r = base + i*rec;
+                            if (Reader::decode(r, listProp->countType, format) != 3.0) { notTriangles[size_t(th)] = 1; return; }
+                            for (int k = 0; k < 3; ++k) {
+                                const long long idx = (long long)Reader::decode(r + cs + size_t(k)*is, listProp->type, format);
+                                if (idx < 0 || size_t(idx) >= nVerts) { bad[size_t(th)] = 1; return; }
+                                dst[3*i + size_t(k)] = uint32_t(idx);
+                            }
+                        }
+                    });
+                    bool allTriangles = true;
+                    for (char c : notTriangles) allTriangles &= !c;
+                    if (allTriangles) {
+                        nIndices += 3*size_t(e.count);
+                        in = Reader(dataEnd, dataEnd, format);
+                        fastDone = true;
+                    } else {
+                        out.indices.resize(nIndices);
+                        std::fill(bad.begin(), bad.end(), 0);
                     }
                 }
-            });
+            }
+            if (!fastDone) {
+                // pass 1 (sequential, cheap): where every face's index list starts, how long it is, and where
+                // its triangles go (a polygon of k vertices is a fan of k - 2 triangles, :207-221)
+                struct FaceRef { const uint8_t *indices; uint32_t count; uint64_t firstTriangle; };
+                std::vector<FaceRef> faces;
+                std::vector<long long> asciiIndices;        // ASCII: indices parsed in pass 1
+                faces.reserve(size_t(e.count));
+                uint64_t nTriangles = 0;
+                for (long long i = 0; i < e.count; ++i) {
+                    FaceRef f = {nullptr, 0, nTriangles};
+                    for (const Property &pr : e.props) {
+                        if (&pr != listProp) { in.skip(pr); continue; }
+                        const long long cnt = (long long)in.scalar(pr.countType);
+                        if (!in.ok || cnt < 0 || cnt > 0x7FFFFFFF) { in.ok = false; break; }
+                        f.count = uint32_t(cnt);
+                        if (format == 0) {
+                            f.indices = reinterpret_cast<const uint8_t *>(uintptr_t(asciiIndices.size()));
+                            for (long long k = 0; k < cnt && in.ok; ++k) asciiIndices.push_back((long long)in.scalar(pr.type));
+                        } else {
+                            f.indices = in.position();
+                            const size_t bytes = size_t(cnt)*size_t(kSize[pr.type]);
+                            if (size_t(dataEnd - in.position()) < bytes) { in.ok = false; break; }
+                            in = Reader(in.position() + bytes, dataEnd, format);
+                        }
+                    }
+                    if (!in.ok) { err = std::string(path) + ": short read in the face data"; status = 3; return false; }
+                    if (f.count >= 3) nTriangles += f.count - 2;
+                    faces.push_back(f);
+                }
+                // pass 2 (all cores): the fans' index triples, in file order
+                if (!out.indices.resize(nIndices + 3*size_t(nTriangles))) { err = noMemory; status = 4; return false; }
+                uint32_t *dst = out.indices.data() + nIndices;
+                parallelRanges(faces.size(), [&](int th, size_t begin, size_t end) {
+                    for (size_t i = begin; i < end; ++i) {
+                        const FaceRef &f = faces[i];
+                        long long v0 = 0, v1 = 0;
+                        for (uint32_t k = 0; k < f.count; ++k) {
+                            long long idx;
+                            if (format == 0) idx = asciiIndices[size_t(uintptr_t(f.indices)) + k];
+                            else idx = (long long)Reader::decode(f.indices + size_t(k)*size_t(kSize[listProp->type]), listProp->type, format);
+                            if (idx < 0 || size_t(idx) >= nVerts) { bad[size_t(th)] = 1; break; }
+                            if (k == 0) { v0 = idx; continue; }
+                            if (k == 1) { v1 = idx; continue; }
+                            uint32_t *tri = dst + 3*(size_t(f.firstTriangle) + (k - 2));
+                            tri[0] = uint32_t(v0); tri[1] = uint32_t(v1); tri[2] = uint32_t(idx);
+                            v1 = idx;
+                        }
+                    }
+                });
+                nIndices += 3*size_t(nTriangles);
+            }
             for (char b : bad) if (b) { err = "PLY face refers to a vertex that does not exist"; status = 3; return false; }
         } else {
             for (long long i = 0; i < e.count && in.ok; ++i)
@@ -317,7 +414,7 @@ bool readPlyMesh(const char *path, Mesh &out, std::string &err, int &status) {
             if (!in.ok) { err = std::string(path) + ": short read in element " + e.name; status = 3; return false; }
         }
     }
-    if (out.tris.empty()) { err = std::string(path) + ": no triangles"; status = 3; return false; }
+    if (out.indices.empty()) { err = std::string(path) + ": no triangles"; status = 3; return false; }
     memcpy(out.lower, lo, 12);
     memcpy(out.upper, hi, 12);
     return true;

@@ -751,11 +751,11 @@ int svo_ply_read_triangles(const char *path, float **tris, uint64_t *n, float lo
     int status = 0;
     if (!svo::readPlyMesh(path, mesh, err, status)) return fail(status, "%s", err.c_str());
     static_assert(sizeof(svo::MeshTriangle) == 33*sizeof(float), "MeshTriangle is 33 packed floats");
-    float *out = static_cast<float *>(malloc(mesh.tris.size()*sizeof(svo::MeshTriangle)));
+    float *out = static_cast<float *>(malloc(mesh.triangleCount()*sizeof(svo::MeshTriangle)));
     if (!out) return fail(SVO_ERR_OUT_OF_MEMORY, "out of host memory for the triangle list");
-    memcpy(out, mesh.tris.data(), mesh.tris.size()*sizeof(svo::MeshTriangle));
+    svo::assembleTriangles(mesh, reinterpret_cast<svo::MeshTriangle *>(out));
     *tris = out;
-    *n = mesh.tris.size();
+    *n = mesh.triangleCount();
     memcpy(lower, mesh.lower, 12);
     memcpy(upper, mesh.upper, 12);
     return SVO_OK;
@@ -774,7 +774,7 @@ int svo_tree_build_from_ply(const char *path, int resolution, uint64_t mem_budge
     auto since = [](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t).count(); };
     auto t0 = now();
     if (!svo::readPlyMesh(path, mesh, err, status)) return fail(status, "%s", err.c_str());
-    if (debugTiming) fprintf(stderr, "[svo] PLY read + triangle assembly: %.3f s (%zu triangles)\n", since(t0), mesh.tris.size());
+    if (debugTiming) fprintf(stderr, "[svo] PLY read: %.3f s (%zu vertices, %zu triangles)\n", since(t0), mesh.verts.size(), mesh.triangleCount());
     if (mem_budget == 0) mem_budget = uint64_t(1024)*1024*1024;                   // Main.cpp:269
     if (threads <= 0) threads = int(std::thread::hardware_concurrency());
     if (threads <= 0) threads = 1;

@@ -302,6 +302,38 @@ foldCellsKernel(Partition P, uint32_t n, const uint64_t *__restrict__ keys, cons
     values[at] = data;
 }
 
+// Triangle::Triangle (reference src/PlyLoader.hpp:40-54) and, for meshes without vertex normals, the face
+// normal of PlyLoader::readTriangles (:213-218), one thread per triangle from the uploaded vertices and index
+// triples: the same float operations in the same order as ply_io.cpp::makeTriangle (explicitly rounded, IEEE
+// square root and divide), so the triangles are the ones the host-side assembly produces, bit for bit.
+__global__ void __launch_bounds__(kThreads)
+assembleTrianglesKernel(const MeshVertex *__restrict__ verts, const uint32_t *__restrict__ indices, uint32_t nTris,
+                        int hasNormals, MeshTriangle *__restrict__ tris) {
+    const uint32_t i = blockIdx.x*kThreads + threadIdx.x;
+    if (i >= nTris) return;
+    MeshTriangle t;
+    for (int w = 0; w < 3; ++w) {
+        const MeshVertex v = verts[indices[3*size_t(i) + w]];
+        for (int q = 0; q < 3; ++q) { t.pos[w][q] = v.pos[q]; t.normal[w][q] = v.normal[q]; t.color[w][q] = v.color[q]; }
+    }
+    for (int q = 0; q < 3; ++q) {
+        t.lower[q] = minStd(t.pos[0][q], minStd(t.pos[1][q], t.pos[2][q]));
+        t.upper[q] = maxStd(t.pos[0][q], maxStd(t.pos[1][q], t.pos[2][q]));
+    }
+    if (!hasNormals) {
+        float e1[3], e2[3], n[3];
+        for (int q = 0; q < 3; ++q) { e1[q] = __fsub_rn(t.pos[1][q], t.pos[0][q]); e2[q] = __fsub_rn(t.pos[2][q], t.pos[0][q]); }
+        n[0] = __fsub_rn(__fmul_rn(e1[1], e2[2]), __fmul_rn(e1[2], e2[1]));
+        n[1] = __fsub_rn(__fmul_rn(e1[2], e2[0]), __fmul_rn(e1[0], e2[2]));
+        n[2] = __fsub_rn(__fmul_rn(e1[0], e2[1]), __fmul_rn(e1[1], e2[0]));
+        const float len2 = __fadd_rn(__fadd_rn(__fmul_rn(n[0], n[0]), __fmul_rn(n[1], n[1])), __fmul_rn(n[2], n[2]));
+        const float inv = __fdiv_rn(1.0f, __fsqrt_rn(len2));
+        for (int w = 0; w < 3; ++w)
+            for (int q = 0; q < 3; ++q) t.normal[w][q] = __fmul_rn(n[q], inv);
+    }
+    tris[i] = t;
+}
+
 template <typename T>
 struct Dev {
     T *p = nullptr;
@@ -345,8 +377,8 @@ bool voxelizeMesh(const Mesh &mesh, int sideLength, uint64_t memoryBudget, int t
                   VoxelizeStats &stats, std::string &err) {
     if (sideLength < 8 || sideLength > (1 << 21)) { err = "resolution must be in [8, 2^21]"; return false; }
     if (threadCount < 1) { err = "thread count must be positive"; return false; }
-    if (mesh.tris.empty()) { err = "mesh has no triangles"; return false; }
-    if (mesh.tris.size() >= (1ull << 31)) { err = "more than 2^31 - 1 triangles are not supported"; return false; }
+    if (mesh.triangleCount() == 0) { err = "mesh has no triangles"; return false; }
+    if (mesh.triangleCount() >= (1ull << 31)) { err = "more than 2^31 - 1 triangles are not supported"; return false; }
 
     // PlyLoader::suggestedDimensions (:498-503)
     const float sx = (mesh.upper[0] - mesh.lower[0])*float(sideLength - 2), sy = (mesh.upper[1] - mesh.lower[1])*float(sideLength - 2),
@@ -385,22 +417,32 @@ bool voxelizeMesh(const Mesh &mesh, int sideLength, uint64_t memoryBudget, int t
     P.realW = P.partW*((w + P.block - 1)/P.block);
     P.realH = P.partH*((h + P.block - 1)/P.block);
     P.realD = P.partD*((d + P.block - 1)/P.block);
-    stats.triangles = mesh.tris.size();
+    stats.triangles = mesh.triangleCount();
     stats.dims[0] = w; stats.dims[1] = h; stats.dims[2] = d;
     stats.cacheBlock = P.block;
     stats.subBlock[0] = P.subW; stats.subBlock[1] = P.subH; stats.subBlock[2] = P.subD;
 
-    const uint32_t nTris = uint32_t(mesh.tris.size());
+    const uint32_t nTris = uint32_t(mesh.triangleCount());
+    const unsigned blocks = (nTris + kThreads - 1)/kThreads;
     Dev<MeshTriangle> dTris;
     Dev<uint64_t> dCounts;
     SVO_VOX_CUDA(dTris.alloc(nTris));
-    SVO_VOX_CUDA(cudaMemcpy(dTris.p, mesh.tris.data(), size_t(nTris)*sizeof(MeshTriangle), cudaMemcpyHostToDevice));
+    {   // vertices + index triples up (48 B per triangle instead of 132), triangles assembled in HBM
+        Dev<MeshVertex> dVerts;
+        Dev<uint32_t> dIndices;
+        SVO_VOX_CUDA(dVerts.alloc(mesh.verts.size()));
+        SVO_VOX_CUDA(dIndices.alloc(mesh.indices.size()));
+        SVO_VOX_CUDA(cudaMemcpyAsync(dVerts.p, mesh.verts.data(), mesh.verts.size()*sizeof(MeshVertex), cudaMemcpyHostToDevice, 0));
+        SVO_VOX_CUDA(cudaMemcpyAsync(dIndices.p, mesh.indices.data(), mesh.indices.size()*sizeof(uint32_t), cudaMemcpyHostToDevice, 0));
+        assembleTrianglesKernel<<<blocks, kThreads>>>(dVerts.p, dIndices.p, nTris, mesh.hasNormals ? 1 : 0, dTris.p);
+        SVO_VOX_CUDA(cudaGetLastError());
+        SVO_VOX_CUDA(cudaStreamSynchronize(0));
+    }
     SVO_VOX_CUDA(dCounts.alloc(uint64_t(nTris) + 1));
     SVO_VOX_CUDA(cudaMemset(dCounts.p + nTris, 0, sizeof(uint64_t)));
 
     Timer timer;
     timer.start();
-    const unsigned blocks = (nTris + kThreads - 1)/kThreads;
     countCellsKernel<<<blocks, kThreads>>>(P, dTris.p, nTris, dCounts.p);
     SVO_VOX_CUDA(cudaGetLastError());
     Dev<uint8_t> temp;

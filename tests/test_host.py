@@ -248,7 +248,21 @@ def test_ply_reader_matches_oracle(pysvo, port, tmp_path):
     assert make_scenes.gen_lib().svo_scene_icosphere_ply(str(ico).encode(), 5, 7) > 0
     big = tmp_path / "ico100.ply"       # 200,000 triangles: the reader's multi-threaded paths
     assert make_scenes.gen_lib().svo_scene_icosphere_ply(str(big).encode(), 100, 7) > 0
-    for name, p in [("ico5", ico), ("ico100", big)] + write_variants(tmp_path):
+    # a quad and a two-index face among 70,000 triangles: the face data is exactly as long as if every face were
+    # a triangle, so the reader's all-triangles fast path has to notice the counts and fall back
+    import struct
+    rng = np.random.default_rng(3)
+    v = rng.random((500, 3)).astype(np.float32)
+    faces = [list(map(int, rng.choice(500, 3, replace=False))) for _ in range(70000)]
+    faces[40000:40002] = [[5, 9, 13, 17], [2, 3]]
+    mixed = tmp_path / "mixed_counts.ply"
+    with open(mixed, "wb") as fp:
+        fp.write(("ply\nformat binary_little_endian 1.0\nelement vertex 500\nproperty float x\nproperty float y\n"
+                  "property float z\nelement face %d\nproperty list uchar int vertex_indices\nend_header\n" % len(faces)).encode())
+        fp.write(v.tobytes())
+        for f in faces:
+            fp.write(struct.pack("<B%di" % len(f), len(f), *f))
+    for name, p in [("ico5", ico), ("ico100", big), ("mixed_counts", mixed)] + write_variants(tmp_path):
         a, lo, hi = pysvo.ply_read_triangles(p)
         b, lo2, hi2 = port.ply_triangles(p)
         assert a.shape == b.shape and a.shape[0] > 100, name
@@ -259,8 +273,10 @@ def test_ply_reader_matches_oracle(pysvo, port, tmp_path):
         pysvo.ply_read_triangles(tmp_path / "missing.ply")
     assert e.value.status == 2
     raw = ico.read_bytes()
+    bigraw = bytearray(big.read_bytes())
+    bigraw[-4:] = struct.pack("<i", 10**8)          # the last face's last index points past the vertices
     for name, blob in [("notply.ply", b"plx\n" + raw[4:]), ("short.ply", raw[:len(raw) // 2]),
-                       ("nofaces.ply", raw.replace(b"element face", b"element fac_"))]:
+                       ("nofaces.ply", raw.replace(b"element face", b"element fac_")), ("badindex.ply", bytes(bigraw))]:
         q = tmp_path / name
         q.write_bytes(blob)
         with pytest.raises(pysvo.SvoError) as e:
