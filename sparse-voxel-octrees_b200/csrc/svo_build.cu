@@ -39,6 +39,9 @@
 #include "svo_build.cuh"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -397,6 +400,9 @@ bool OctreeBuilder::finish(BuildResult &out, std::string &err) {
     stats.voxels = count_;
     stats.gatherMs = gatherMs_;
     Timer timer;
+    const bool debugTiming = getenv("SVO_BUILD_DEBUG") != nullptr;
+    const auto wall0 = std::chrono::steady_clock::now();
+    auto wallMs = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count(); };
 
     // ---- sort by Morton key
     timer.start();
@@ -517,6 +523,7 @@ bool OctreeBuilder::finish(BuildResult &out, std::string &err) {
     }
     stats.emitMs = timer.stop();
     SVO_BUILD_CUDA(cudaDeviceSynchronize());
+    const double builtAt = wallMs();
     for (Level &lv : level) lv = Level();
     base.release();
     keysAlt.release();
@@ -526,7 +533,11 @@ bool OctreeBuilder::finish(BuildResult &out, std::string &err) {
     counters.release();
     numRuns.release();
     cudaStreamSynchronize(0);
+    const double releasedAt = wallMs();
     trimScratchPool();
+    if (debugTiming)
+        fprintf(stderr, "[svo] OctreeBuilder::finish: %.1f ms to the last kernel (device %.1f ms), %.1f ms releasing scratch, %.1f ms trimming the pool\n",
+                builtAt, stats.sortMs + stats.levelsMs + stats.emitMs, releasedAt - builtAt, wallMs() - releasedAt);
 
     out.dWords = guard.p;
     guard.p = nullptr;

@@ -24,6 +24,9 @@
 #include "svo_voxelize.cuh"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -334,11 +337,19 @@ assembleTrianglesKernel(const MeshVertex *__restrict__ verts, const uint32_t *__
     tris[i] = t;
 }
 
+// Scratch arrays: plain cudaMalloc / cudaFree. Allocating them from the builder's stream-ordered pool instead
+// (so that the build reuses what the voxeliser releases) was measured on the 8192^3 mesh and is slower and
+// erratic: growing the pool by tens of GB costs more than cudaMalloc (overlap stage 56 -> 105 ms, one build in
+// three stalled 1.9 s in the pool).
 template <typename T>
 struct Dev {
     T *p = nullptr;
-    ~Dev() { if (p) cudaFree(p); }
-    cudaError_t alloc(uint64_t n) { if (p) cudaFree(p); p = nullptr; return cudaMalloc(&p, size_t(n ? n : 1)*sizeof(T)); }
+    Dev() = default;
+    Dev(const Dev &) = delete;
+    Dev &operator=(const Dev &) = delete;
+    ~Dev() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; }
+    cudaError_t alloc(uint64_t n) { release(); return cudaMalloc(&p, size_t(n ? n : 1)*sizeof(T)); }
 };
 
 struct Timer {
@@ -422,6 +433,9 @@ bool voxelizeMesh(const Mesh &mesh, int sideLength, uint64_t memoryBudget, int t
     stats.cacheBlock = P.block;
     stats.subBlock[0] = P.subW; stats.subBlock[1] = P.subH; stats.subBlock[2] = P.subD;
 
+    const bool debugTiming = getenv("SVO_BUILD_DEBUG") != nullptr;
+    const auto wall0 = std::chrono::steady_clock::now();
+    auto wallMs = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count(); };
     const uint32_t nTris = uint32_t(mesh.triangleCount());
     const unsigned blocks = (nTris + kThreads - 1)/kThreads;
     Dev<MeshTriangle> dTris;
@@ -436,8 +450,9 @@ bool voxelizeMesh(const Mesh &mesh, int sideLength, uint64_t memoryBudget, int t
         SVO_VOX_CUDA(cudaMemcpyAsync(dIndices.p, mesh.indices.data(), mesh.indices.size()*sizeof(uint32_t), cudaMemcpyHostToDevice, 0));
         assembleTrianglesKernel<<<blocks, kThreads>>>(dVerts.p, dIndices.p, nTris, mesh.hasNormals ? 1 : 0, dTris.p);
         SVO_VOX_CUDA(cudaGetLastError());
-        SVO_VOX_CUDA(cudaStreamSynchronize(0));
+        SVO_VOX_CUDA(cudaStreamSynchronize(0));      // the host arrays may go once this returns
     }
+    const double uploadedAt = wallMs();
     SVO_VOX_CUDA(dCounts.alloc(uint64_t(nTris) + 1));
     SVO_VOX_CUDA(cudaMemset(dCounts.p + nTris, 0, sizeof(uint64_t)));
 
@@ -464,6 +479,8 @@ bool voxelizeMesh(const Mesh &mesh, int sideLength, uint64_t memoryBudget, int t
     writeCellsKernel<<<blocks, kThreads>>>(P, dTris.p, nTris, dCounts.p, keys.p, records.p);
     SVO_VOX_CUDA(cudaGetLastError());
     stats.overlapMs = timer.stop();
+    dTris.release();
+    dCounts.release();
 
     // stable sort of record indices by cell: triangle order survives inside every cell
     timer.start();
@@ -495,7 +512,12 @@ bool voxelizeMesh(const Mesh &mesh, int sideLength, uint64_t memoryBudget, int t
     stats.foldMs = timer.stop();
     stats.voxels = nVoxels;
     if (nVoxels == 0) { err = "the mesh produced no filled cell"; return false; }
-    return builder.addSparse(xyz.p, values.p, nVoxels, err);
+    const double foldedAt = wallMs();
+    const bool ok = builder.addSparse(xyz.p, values.p, nVoxels, err);
+    if (debugTiming)
+        fprintf(stderr, "[svo] voxelizeMesh: %.1f ms upload + assembly, %.1f ms to the fold's end (device %.1f ms), %.1f ms handing %llu voxels to the builder\n",
+                uploadedAt, foldedAt - uploadedAt, stats.overlapMs + stats.sortMs + stats.foldMs, wallMs() - foldedAt, nVoxels);
+    return ok;
 }
 
 } // namespace svo
