@@ -234,6 +234,42 @@ typedef struct svo_camera {
 /* Main.cpp:212-213,244-245: MODEL = rotXYZ(pitch,0,0)*rotXYZ(0,yaw,0), VIEW = translate(0,0,-radius). */
 SVO_API void svo_orbit_camera(float pitch_deg, float yaw_deg, float radius, svo_camera *out);
 
+/* ---- interactive viewer ------------------------
+ * The camera control of the reference's `-viewer` mode without SDL: the mouse / key state of
+ * src/Events.cpp:28-77 and renderLoop's event handling (src/Main.cpp:229-252) as a state machine the
+ * host application feeds with its own window system's events (or with a script: svo_headless --events).
+ * Event numbers are SDL 1.2's, the ones the reference receives. */
+enum svo_event_type {
+    SVO_EVENT_KEY_DOWN = 2, SVO_EVENT_KEY_UP = 3, SVO_EVENT_MOUSE_MOTION = 4, SVO_EVENT_BUTTON_DOWN = 5, SVO_EVENT_BUTTON_UP = 6
+};
+enum { SVO_BUTTON_LEFT = 1, SVO_BUTTON_RIGHT = 3, SVO_KEY_ESCAPE = 27 };
+enum svo_viewer_action {
+    SVO_VIEWER_WAIT = 0,        /* keep waiting: mouse motion with no button held (Main.cpp:229) */
+    SVO_VIEWER_FRAME = 1,       /* render the next frame with state.camera / state.preview */
+    SVO_VIEWER_QUIT = 2         /* Escape is down: doTerminate (Main.cpp:231-234) */
+};
+typedef struct svo_viewer_event {
+    int32_t type;               /* svo_event_type */
+    int32_t code;               /* button (SVO_BUTTON_*) or key */
+    int32_t dx, dy;             /* relative motion of SVO_EVENT_MOUSE_MOTION (SDL's xrel / yrel) */
+} svo_viewer_event;
+typedef struct svo_viewer_state {
+    float radius, pitch, yaw;   /* Main.cpp:207-209: 1, 0, 0 */
+    int32_t mouse_down[2];      /* left, right (Events.cpp:34) */
+    int32_t mouse_dx, mouse_dy; /* the last motion not yet read (Events.cpp:31-32, read-and-clear :110-124): motion
+                                   that arrives while no button is held is applied by the next button press */
+    int32_t escape_down;
+    int32_t preview;            /* renderHalfSize (Main.cpp:246,251,253): render with svo_frame_desc.pixel_stride 3 */
+    int32_t quit;
+    svo_camera camera;          /* MODEL / VIEW for the next frame: identity / translate(0, 0, -1) at first
+                                   (Main.cpp:212-213); a drag with the left button replaces MODEL (:244-245), with
+                                   the right button VIEW (:250) */
+} svo_viewer_state;
+
+SVO_API void svo_viewer_init(svo_viewer_state *state);
+/* One event. Returns a svo_viewer_action (negative svo_status on a null argument, sign flipped). */
+SVO_API int svo_viewer_feed(svo_viewer_state *state, const svo_viewer_event *event);
+
 /* The scalars renderBatch derives before its loops (Main.cpp:149-163). */
 typedef struct svo_frame_constants {
     int32_t width, height, strips, tile_size;

@@ -45,6 +45,12 @@ for f in VoxelOctree.cpp VoxelData.cpp PlyLoader.cpp Util.cpp Debug.cpp \
     g++ $CXXFLAGS -I"$src" -c "$src/$f" -o "$o" &
     objs+=("$o")
 done
+# the interactive path (row f4): the reference's event state and frame barrier, against the shim's SDL
+for f in Events.cpp ThreadBarrier.cpp; do
+    o="$tmp/$f.o"
+    g++ $CXXFLAGS -I"$here/ref_shim" -I"$src" -c "$src/$f" -o "$o" &
+    objs+=("$o")
+done
 for f in third-party/lz4.c third-party/plyfile.c third-party/tribox3.c; do
     o="$tmp/$(echo "$f" | tr '/' '_').o"
     gcc $CFLAGS -I"$src" -c "$src/$f" -o "$o" &

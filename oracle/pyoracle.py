@@ -107,6 +107,9 @@ class Ref:
         L.svoref_render_frames_subset.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _f32p,
                                                   C.c_int, _u32p, C.c_void_p, C.c_void_p]
         L.svoref_hardware_threads.restype = C.c_int
+        L.svoref_viewer_run.restype = C.c_int
+        L.svoref_viewer_run.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.svoref_set_half_size.restype = None
         L.svoref_set_half_size.argtypes = [C.c_int]
 
@@ -228,6 +231,28 @@ class Ref:
 
     def hardware_threads(self):
         return int(self.lib.svoref_hardware_threads())
+
+    # -- the interactive viewer (row f4)
+    def viewer_run(self, oct_path, W, H, strips, events, max_frames=None, want_pixels=True):
+        """The reference's own `main -viewer oct_path` (Main.cpp:332-376, renderLoop :204-258, Events.cpp,
+        ThreadBarrier.cpp) run against a scripted SDL: `events` is a list of (type, code, xrel, yrel) in SDL 1.2's
+        numbering (2 key down, 3 key up, 4 mouse motion, 5 button down, 6 button up; buttons 1 left, 3 right);
+        Escape is pressed when the script runs out. Returns a dict of per-presented-frame arrays: rgba
+        [n, H, W], model [n, 16], view [n, 16], half [n] (renderHalfSize the frame was rendered with) and
+        events_taken [n] (script events consumed when the frame was shown)."""
+        ev = np.ascontiguousarray(np.asarray(events, np.int32).reshape(-1, 4))
+        mf = int(max_frames or ev.shape[0] + 2)
+        rgba = np.zeros((mf, H, W), np.uint32) if want_pixels else None
+        models, views = np.zeros((mf, 16), np.float32), np.zeros((mf, 16), np.float32)
+        half, taken = np.zeros(mf, np.int32), np.zeros(mf, np.int32)
+        p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        n = self.lib.svoref_viewer_run(str(oct_path).encode(), W, H, strips, ev.shape[0], p(ev), mf, p(rgba), p(models),
+                                       p(views), p(half), p(taken))
+        if n < 0:
+            raise ValueError("svoref_viewer_run: bad arguments")
+        n = min(n, mf)
+        return {"rgba": None if rgba is None else rgba[:n], "model": models[:n], "view": views[:n], "half": half[:n],
+                "events_taken": taken[:n]}
 
 
 def strip_layout(W, H, strips, tile=8):

@@ -55,27 +55,63 @@
 #include "VoxelOctree.hpp"
 #undef class
 
-/* Main.cpp includes ThreadBarrier.hpp (SDL mutex + semaphores). The headless
- * harness never runs renderLoop, so a declaration is enough. */
-#define THREADBARRIER_HPP_
-class ThreadBarrier {
-public:
-    ThreadBarrier(int) {}
-    void waitPre() {}
-    void waitPost() {}
-    void releaseAll() {}
-};
-
 #define main reference_main
 #include SVO_REF_MAIN_CPP
 #undef main
 
-/* Events.cpp needs SDL proper; renderLoop (never run) references these. */
-int waitEvent() { return 0; }
-int getMouseDown(int) { return 0; }
-int getKeyDown(int) { return 0; }
-int getMouseXSpeed() { return 0; }
-int getMouseYSpeed() { return 0; }
+/* ---- the scripted SDL behind oracle/ref_shim/SDL.h (row f4) ---------------
+ * src/Events.cpp, src/ThreadBarrier.cpp and Main.cpp's `-viewer` main loop are
+ * the reference's own object code; what they see of SDL is an event queue filled
+ * from a script and a window whose every SDL_UpdateRect is recorded. */
+namespace {
+struct ViewerRun {
+    std::deque<SDL_Event> queue;
+    SDL_Surface *surface = nullptr;
+    int W = 0, H = 0, maxFrames = 0, frames = 0;
+    int eventsTaken = 0;
+    uint32_t *rgba = nullptr;       /* maxFrames x W x H, optional */
+    float *models = nullptr, *views = nullptr;
+    int32_t *half = nullptr, *eventsAtFrame = nullptr;
+};
+ViewerRun *g_viewer = nullptr;
+
+SDL_Event escapeKey(int type) {
+    SDL_Event e;
+    std::memset(&e, 0, sizeof e);
+    e.key.type = (unsigned char)type;
+    e.key.keysym.sym = SDLK_ESCAPE;
+    return e;
+}
+} // namespace
+
+extern "C" int svo_shim_wait_event(SDL_Event *event) {
+    /* an exhausted script presses Escape: the only way out of renderLoop (Main.cpp:231-234) */
+    if (!g_viewer || g_viewer->queue.empty()) { *event = escapeKey(SDL_KEYDOWN); return 1; }
+    *event = g_viewer->queue.front();
+    g_viewer->queue.pop_front();
+    g_viewer->eventsTaken++;
+    return 1;
+}
+extern "C" int svo_shim_poll_event(SDL_Event *event) {
+    if (!g_viewer || g_viewer->queue.empty()) return 0;
+    *event = g_viewer->queue.front();
+    g_viewer->queue.pop_front();
+    return 1;
+}
+extern "C" void svo_shim_surface_created(SDL_Surface *surface) { if (g_viewer) g_viewer->surface = surface; }
+extern "C" void svo_shim_present(SDL_Surface *surface) {
+    ViewerRun *v = g_viewer;
+    if (!v || v->frames >= v->maxFrames) { if (v) v->frames++; return; }
+    const int k = v->frames++;
+    if (v->rgba) std::memcpy(v->rgba + size_t(k)*v->W*v->H, surface->pixels, size_t(v->W)*v->H*4);
+    Mat4 model, view;
+    MatrixStack::get(MODEL_STACK, model);
+    MatrixStack::get(VIEW_STACK, view);
+    if (v->models) std::memcpy(v->models + 16*k, model.a, 64);
+    if (v->views) std::memcpy(v->views + 16*k, view.a, 64);
+    if (v->half) v->half[k] = renderHalfSize ? 1 : 0;      /* what the frame was rendered with */
+    if (v->eventsAtFrame) v->eventsAtFrame[k] = v->eventsTaken;
+}
 
 namespace {
 
@@ -359,6 +395,68 @@ int svoref_render_frames_subset(void *h, int W, int H, int strips, int stripModu
     }
     backBuffer = nullptr;
     return 0;
+}
+
+/* ---- row f4: the reference's interactive viewer, run headless ------------
+ * Runs the reference's own `main -viewer <path>` (Main.cpp:332-376): its loader, its NumThreads render
+ * threads and ThreadBarrier, renderLoop's event handling (Main.cpp:204-258) and Events.cpp's mouse state,
+ * against the scripted SDL above. `events` is nEvents x 4 int32: {SDL type (2 key down, 3 key up, 4 mouse
+ * motion, 5 button down, 6 button up), button (1 left, 3 right) or key, xrel, yrel}; when the script runs
+ * out Escape is pressed. Every frame the viewer presents is recorded (up to maxFrames): pixels, the MODEL
+ * and VIEW matrices and renderHalfSize it was rendered with, and how many script events had been consumed
+ * when it was shown. Returns the number of frames presented, or -1. */
+int svoref_viewer_run(const char *octPath, int W, int H, int strips, int nEvents, const int32_t *events, int maxFrames,
+                      uint32_t *rgba, float *models, float *views, int32_t *half, int32_t *eventsAtFrame) {
+    if (!octPath || W < 1 || H < 1 || strips < 1 || nEvents < 0 || maxFrames < 1 || g_viewer) return -1;
+    FILE *fp = fopen(octPath, "rb");
+    if (!fp) return -1;
+    fclose(fp);
+    ViewerRun run;
+    run.W = W; run.H = H; run.maxFrames = maxFrames;
+    run.rgba = rgba; run.models = models; run.views = views; run.half = half; run.eventsAtFrame = eventsAtFrame;
+    for (int i = 0; i < nEvents; ++i) {
+        SDL_Event e;
+        std::memset(&e, 0, sizeof e);
+        const int32_t *ev = events + 4*i;
+        switch (ev[0]) {
+        case SDL_MOUSEMOTION: e.motion.type = SDL_MOUSEMOTION; e.motion.xrel = ev[2]; e.motion.yrel = ev[3]; break;
+        case SDL_MOUSEBUTTONDOWN: case SDL_MOUSEBUTTONUP: e.button.type = (unsigned char)ev[0]; e.button.button = (unsigned char)ev[1]; break;
+        case SDL_KEYDOWN: case SDL_KEYUP:
+            if (ev[1] < 0 || ev[1] >= SDLK_LAST) return -1;
+            e.key.type = (unsigned char)ev[0]; e.key.keysym.sym = ev[1]; break;
+        default: return -1;       /* SDL_QUIT would exit() the process (Events.cpp:75-76) */
+        }
+        run.queue.push_back(e);
+    }
+    NumThreads = strips;
+    GWidth = W;
+    GHeight = H;
+    AspectRatio = GHeight/(float)GWidth;     /* Main.cpp:62 */
+    renderHalfSize = false;                  /* a fresh process: static storage */
+    g_viewer = &run;
+    std::string path(octPath);
+    char arg0[] = "sparse-voxel-octrees", arg1[] = "-viewer";
+    char *argv[] = {arg0, arg1, &path[0], nullptr};
+    reference_main(3, argv);
+    /* Events.cpp keeps its state in statics: release Escape and the buttons, read the speeds away */
+    run.queue.clear();
+    run.queue.push_back(escapeKey(SDL_KEYUP));
+    for (int b : {SDL_BUTTON_LEFT, SDL_BUTTON_RIGHT}) {
+        SDL_Event e;
+        std::memset(&e, 0, sizeof e);
+        e.button.type = SDL_MOUSEBUTTONUP;
+        e.button.button = (unsigned char)b;
+        run.queue.push_back(e);
+    }
+    checkEvents();
+    getMouseXSpeed();
+    getMouseYSpeed();
+    g_viewer = nullptr;
+    if (run.surface) { free(run.surface->pixels); free(run.surface); }
+    backBuffer = nullptr;
+    delete barrier;
+    barrier = nullptr;
+    return run.frames;
 }
 
 } // extern "C"

@@ -122,4 +122,60 @@ void frameConstants(const svo_camera &cam, const float center[3], int width, int
     out.beam_bias = 0.03f;                               // :197
 }
 
+// ---- the viewer's camera control (row f4) ------------------------------------------------------------
+// Events.cpp's processEvent (:38-77) and read-and-clear speed getters (:110-124), followed by what renderLoop
+// does once waitEvent returns something other than idle mouse motion (Main.cpp:229-252). Float operations in
+// the reference's order (std::fmod / std::fabs / std::min / std::max on floats).
+
+void viewerInit(svo_viewer_state &s) {
+    std::memset(&s, 0, sizeof s);
+    s.radius = 1.0f;                                                  // Main.cpp:207-209
+    const M4 model = identity(), view = translation(0.0f, 0.0f, -s.radius);   // :212-213
+    std::memcpy(s.camera.model, model.a, sizeof s.camera.model);
+    std::memcpy(s.camera.view, view.a, sizeof s.camera.view);
+}
+
+int viewerFeed(svo_viewer_state &s, const svo_viewer_event &e) {
+    if (s.quit) return SVO_VIEWER_QUIT;
+    switch (e.type) {                                                 // Events.cpp:38-77
+    case SVO_EVENT_MOUSE_MOTION: s.mouse_dx = e.dx; s.mouse_dy = e.dy; break;
+    case SVO_EVENT_BUTTON_DOWN:
+        if (e.code == SVO_BUTTON_LEFT) s.mouse_down[0] = 1;
+        else if (e.code == SVO_BUTTON_RIGHT) s.mouse_down[1] = 1;
+        break;
+    case SVO_EVENT_BUTTON_UP:
+        if (e.code == SVO_BUTTON_LEFT) s.mouse_down[0] = 0;
+        else if (e.code == SVO_BUTTON_RIGHT) s.mouse_down[1] = 0;
+        break;
+    case SVO_EVENT_KEY_DOWN: if (e.code == SVO_KEY_ESCAPE) s.escape_down = 1; break;
+    case SVO_EVENT_KEY_UP: if (e.code == SVO_KEY_ESCAPE) s.escape_down = 0; break;
+    default: break;
+    }
+    if (e.type == SVO_EVENT_MOUSE_MOTION && !s.mouse_down[0] && !s.mouse_down[1]) return SVO_VIEWER_WAIT;   // Main.cpp:229
+    if (s.escape_down) s.quit = 1;                                    // :231-234
+    const float mx = float(s.mouse_dx), my = float(s.mouse_dy);       // :236-237 (the getters clear the speeds)
+    s.mouse_dx = s.mouse_dy = 0;
+    if (s.mouse_down[0] && (mx != 0 || my != 0)) {                    // :238-246
+        s.pitch = std::fmod(s.pitch - my, 360.0f);
+        s.yaw = std::fmod(s.yaw + (std::fabs(s.pitch) > 90.0f ? mx : -mx), 360.0f);
+        if (s.pitch > 180.0f) s.pitch -= 360.0f;
+        else if (s.pitch < -180.0f) s.pitch += 360.0f;
+        const M4 model = mul(rotationXYZ(s.pitch, 0.0f, 0.0f), rotationXYZ(0.0f, s.yaw, 0.0f));
+        std::memcpy(s.camera.model, model.a, sizeof s.camera.model);
+        s.preview = 1;
+    } else if (s.mouse_down[1] && my != 0) {                          // :247-251
+        const float lo = 1.0f - my*0.01f;
+        const float clampedLo = (lo < 0.5f) ? 0.5f : lo;              // std::max(lo, 0.5f)
+        const float factor = (1.5f < clampedLo) ? 1.5f : clampedLo;   // std::min(.., 1.5f)
+        s.radius *= factor;
+        s.radius = (25.0f < s.radius) ? 25.0f : s.radius;             // std::min(radius, 25.0f)
+        const M4 view = translation(0.0f, 0.0f, -s.radius);
+        std::memcpy(s.camera.view, view.a, sizeof s.camera.view);
+        s.preview = 1;
+    } else {
+        s.preview = 0;                                                // :252-254
+    }
+    return s.quit ? SVO_VIEWER_QUIT : SVO_VIEWER_FRAME;
+}
+
 } // namespace svo

@@ -998,6 +998,15 @@ void svo_orbit_camera(float pitch_deg, float yaw_deg, float radius, svo_camera *
     if (out) svo::orbitCamera(pitch_deg, yaw_deg, radius, *out);
 }
 
+void svo_viewer_init(svo_viewer_state *state) {
+    if (state) svo::viewerInit(*state);
+}
+
+int svo_viewer_feed(svo_viewer_state *state, const svo_viewer_event *event) {
+    if (!state || !event) return -fail(SVO_ERR_INVALID_ARGUMENT, "svo_viewer_feed: null argument");
+    return svo::viewerFeed(*state, *event);
+}
+
 int svo_frame_constants_from_camera(const svo_camera *cam, const float center[3], int width, int height, int strips,
                                     svo_frame_constants *out) {
     if (!cam || !center || !out) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_frame_constants_from_camera: null argument");

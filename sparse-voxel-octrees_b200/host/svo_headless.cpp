@@ -8,6 +8,11 @@
 // --raw streams every frame as packed RGB24 (row-major, no header) to a file or to stdout ("-"), the
 // input format of `ffmpeg -f rawvideo -pix_fmt rgb24 -s WxH -i -`: the streamed stand-in for the
 // reference's interactive SDL window; status text goes to stderr then.
+// --events replays a script of window events through the reference viewer's camera control
+// (svo_viewer_feed: Events.cpp's mouse state + renderLoop's event handling, Main.cpp:229-252): one frame at
+// the start and one after every event the reference would redraw for, in preview resolution (stride 3) while
+// a drag is going on -- the frames the reference's window shows for the same input. Script lines:
+//   motion <dx> <dy> | down left|right|<n> | up left|right|<n> | key esc|<code> | keyup esc|<code> | # comment
 //   svo_headless -builder [--resolution r --mode m] <in.ply | in.voxel> <out.oct>
 //
 // The second form is the reference's `-builder` mode with its own argument layout (reference
@@ -18,6 +23,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -36,6 +42,32 @@ static void writePpm(const std::string &path, const uint32_t *rgba, int w, int h
         fwrite(row.data(), 1, row.size(), fp);
     }
     fclose(fp);
+}
+
+static std::vector<svo_viewer_event> readEventScript(const std::string &path) {
+    FILE *fp = fopen(path.c_str(), "r");
+    if (!fp) throw std::runtime_error("cannot read " + path);
+    std::vector<svo_viewer_event> out;
+    char line[256];
+    int lineNo = 0;
+    auto code = [](const char *w) { return !strcmp(w, "left") ? int(SVO_BUTTON_LEFT) : !strcmp(w, "right") ? int(SVO_BUTTON_RIGHT) :
+                                           !strcmp(w, "esc") ? int(SVO_KEY_ESCAPE) : atoi(w); };
+    while (fgets(line, sizeof line, fp)) {
+        ++lineNo;
+        char kind[32] = "", arg[32] = "";
+        int dx = 0, dy = 0;
+        svo_viewer_event e = {0, 0, 0, 0};
+        if (sscanf(line, " %31s", kind) != 1 || kind[0] == '#') continue;
+        if (!strcmp(kind, "motion") && sscanf(line, " %*s %d %d", &dx, &dy) == 2) { e.type = SVO_EVENT_MOUSE_MOTION; e.dx = dx; e.dy = dy; }
+        else if (!strcmp(kind, "down") && sscanf(line, " %*s %31s", arg) == 1) { e.type = SVO_EVENT_BUTTON_DOWN; e.code = code(arg); }
+        else if (!strcmp(kind, "up") && sscanf(line, " %*s %31s", arg) == 1) { e.type = SVO_EVENT_BUTTON_UP; e.code = code(arg); }
+        else if (!strcmp(kind, "key") && sscanf(line, " %*s %31s", arg) == 1) { e.type = SVO_EVENT_KEY_DOWN; e.code = code(arg); }
+        else if (!strcmp(kind, "keyup") && sscanf(line, " %*s %31s", arg) == 1) { e.type = SVO_EVENT_KEY_UP; e.code = code(arg); }
+        else { fclose(fp); throw std::runtime_error(path + ":" + std::to_string(lineNo) + ": cannot parse event: " + line); }
+        out.push_back(e);
+    }
+    fclose(fp);
+    return out;
 }
 
 int main(int argc, char **argv) {
@@ -74,7 +106,7 @@ int main(int argc, char **argv) {
     int w = 1280, h = 720, strips = 16, frames = 1, flavour = SVO_FLAVOUR_FAST; /* Main.cpp:57-60 defaults */
     float radius = 1.0f, pitch = 0.0f, yaw0 = 0.0f, yawStep = 3.6f;
     int stride = 1;
-    std::string out, raw;
+    std::string out, raw, events;
     for (int i = 2; i < argc; ++i) {
         std::string a = argv[i];
         auto next = [&]() -> const char * { return i + 1 < argc ? argv[++i] : ""; };
@@ -89,6 +121,7 @@ int main(int argc, char **argv) {
         else if (a == "--preview") stride = 3;   /* the reference's renderHalfSize while dragging, Main.cpp:161 */
         else if (a == "--out") out = next();
         else if (a == "--raw") raw = next();
+        else if (a == "--events") events = next();
         else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
     try {
@@ -102,9 +135,25 @@ int main(int argc, char **argv) {
         if (svo_host_alloc(size_t(w)*h*4, reinterpret_cast<void **>(&rgba)) != SVO_OK) throw std::runtime_error(svo_last_error());
         double totalMs = 0.0;
         unsigned long long rays = 0;
+        std::vector<svo_viewer_event> script;
+        if (!events.empty()) script = readEventScript(events);
+        svo_viewer_state viewer;
+        svo_viewer_init(&viewer);
+        size_t nextEvent = 0;
+        if (!events.empty()) frames = int(script.size()) + 1;      // at most one frame per event, plus the first
         for (int k = 0; k < frames; ++k) {
             svo_camera cam;
-            svo_orbit_camera(pitch, yaw0 + yawStep*k, radius, &cam);
+            if (events.empty()) {
+                svo_orbit_camera(pitch, yaw0 + yawStep*k, radius, &cam);
+            } else {
+                if (k > 0) {                                       // wait for an event that redraws (Main.cpp:229)
+                    int action = SVO_VIEWER_WAIT;
+                    while (action == SVO_VIEWER_WAIT && nextEvent < script.size()) action = svo_viewer_feed(&viewer, &script[nextEvent++]);
+                    if (action != SVO_VIEWER_FRAME) { frames = k; break; }   // Escape, or the script ran out
+                }
+                cam = viewer.camera;
+                stride = viewer.preview ? 3 : 1;
+            }
             auto t0 = std::chrono::steady_clock::now();
             svo_frame_stats st = tree.renderFrame(cam, w, h, strips, rgba, flavour, stride);
             double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();

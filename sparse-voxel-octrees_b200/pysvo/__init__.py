@@ -50,6 +50,22 @@ class Camera(C.Structure):
         return cam
 
 
+class ViewerEvent(C.Structure):
+    _fields_ = [("type", C.c_int32), ("code", C.c_int32), ("dx", C.c_int32), ("dy", C.c_int32)]
+
+
+class ViewerState(C.Structure):
+    """svo_viewer_state: the reference viewer's camera control (Events.cpp + Main.cpp:229-252)."""
+    _fields_ = [("radius", C.c_float), ("pitch", C.c_float), ("yaw", C.c_float),
+                ("mouse_down", C.c_int32 * 2), ("mouse_dx", C.c_int32), ("mouse_dy", C.c_int32),
+                ("escape_down", C.c_int32), ("preview", C.c_int32), ("quit", C.c_int32), ("camera", Camera)]
+
+
+EVENT_KEY_DOWN, EVENT_KEY_UP, EVENT_MOUSE_MOTION, EVENT_BUTTON_DOWN, EVENT_BUTTON_UP = 2, 3, 4, 5, 6
+BUTTON_LEFT, BUTTON_RIGHT, KEY_ESCAPE = 1, 3, 27
+VIEWER_WAIT, VIEWER_FRAME, VIEWER_QUIT = 0, 1, 2
+
+
 class FrameConstants(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("strips", C.c_int32), ("tile_size", C.c_int32),
                 ("pos", C.c_float * 3),
@@ -152,6 +168,8 @@ def lib():
         "svo_raymarch": (i32, [vp, P(f32), P(f32), f32, P(C.c_uint32), P(f32), P(i32)]),
         "svo_shade_batch": (i32, [vp, u64, vp, vp, vp, P(f32), vp]),
         "svo_orbit_camera": (None, [f32, f32, f32, P(Camera)]),
+        "svo_viewer_init": (None, [P(ViewerState)]),
+        "svo_viewer_feed": (i32, [P(ViewerState), P(ViewerEvent)]),
         "svo_frame_constants_from_camera": (i32, [P(Camera), P(f32), i32, i32, i32, P(FrameConstants)]),
         "svo_frame_get_layout": (i32, [i32, i32, i32, P(FrameLayout)]),
         "svo_frame_tile_rect": (i32, [i32, i32, i32, i32, P(C.c_int32)]),
@@ -239,6 +257,21 @@ def orbit_camera(pitch_deg, yaw_deg, radius) -> Camera:
     cam = Camera()
     lib().svo_orbit_camera(float(pitch_deg), float(yaw_deg), float(radius), C.byref(cam))
     return cam
+
+
+def viewer_init() -> ViewerState:
+    st = ViewerState()
+    lib().svo_viewer_init(C.byref(st))
+    return st
+
+
+def viewer_feed(state: ViewerState, type_, code=0, dx=0, dy=0) -> int:
+    """-> VIEWER_WAIT / VIEWER_FRAME / VIEWER_QUIT; `state` is updated in place."""
+    ev = ViewerEvent(int(type_), int(code), int(dx), int(dy))
+    r = lib().svo_viewer_feed(C.byref(state), C.byref(ev))
+    if r < 0:
+        _check(-r)
+    return r
 
 
 def frame_constants(cam: Camera, center, width, height, strips) -> FrameConstants:

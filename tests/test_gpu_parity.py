@@ -424,3 +424,48 @@ def test_shade_batch_vs_oracle(pysvo, port, gpu_dragon, dragon_words):
     every = gpu_dragon.shade_batch(normal, d, light)          # hit == NULL: every ray is shaded
     assert np.array_equal(every[hit > 0], want[hit > 0]) and (every[hit == 0] != 0).all()
     assert gpu_dragon.shade_batch(np.zeros(0, np.uint32), np.zeros((0, 3), np.float32), light).size == 0
+
+
+def test_viewer_replay_frames_equal_reference_viewer(pysvo, ref, gpu_dragon, tmp_path):
+    """Row f4 end to end: the frames the reference's own `-viewer` loop presents for a scripted mouse session
+    (oracle/_ref: Main.cpp's main + renderLoop, Events.cpp, ThreadBarrier.cpp on a scripted SDL) against the frames
+    of (a) svo_viewer_feed + svo_render_frame and (b) `svo_headless --events`, pixel for pixel: full-resolution
+    frames when idle, stride-3 preview frames while a drag is going on."""
+    import subprocess
+    from conftest import DRAGON, ROOT
+    W, H, S = 160, 96, 4
+    ev = [(4, 0, 3, 2), (5, 1, 0, 0), (4, 0, 25, -10), (4, 0, 40, -35), (6, 1, 0, 0), (4, 0, 9, 9), (5, 3, 0, 0),
+          (4, 0, 0, 30), (4, 0, 2, -45), (6, 3, 0, 0), (5, 1, 0, 0), (4, 0, -15, 120), (6, 1, 0, 0)]
+    want = ref.viewer_run(DRAGON, W, H, S, ev)
+    n = len(want["half"])
+    assert n >= 10 and want["half"].sum() >= 5 and (want["half"] == 0).sum() >= 3
+    st = pysvo.viewer_init()
+    frames = []
+
+    def draw():
+        rgba, _, _ = gpu_dragon.render_frame(st.camera, W, H, strips=S, flavour=pysvo.FLAVOUR_VALIDATION,
+                                             pixel_stride=3 if st.preview else 1)
+        frames.append(rgba.copy())
+    draw()
+    for e in ev:
+        if pysvo.viewer_feed(st, *e) == pysvo.VIEWER_FRAME:
+            draw()
+    assert len(frames) == n
+    for k in range(n):
+        assert np.array_equal(frames[k], want["rgba"][k]), (k, int((frames[k] != want["rgba"][k]).sum()))
+    # the same session through the headless driver's event script
+    names = {1: "left", 3: "right"}
+    script = tmp_path / "session.events"
+    script.write_text("# recorded session\n" + "".join(
+        f"motion {dx} {dy}\n" if t == 4 else f"{'down' if t == 5 else 'up'} {names[c]}\n" for t, c, dx, dy in ev))
+    pkg = ROOT / "sparse-voxel-octrees_b200"
+    subprocess.check_call(["make", "-C", str(pkg), "headless"], stdout=subprocess.DEVNULL)
+    stream = tmp_path / "session.rgb"
+    out = subprocess.run([str(pkg / "svo_headless"), str(DRAGON), "--size", f"{W}x{H}", "--strips", str(S), "--validation",
+                          "--events", str(script), "--raw", str(stream)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    rgb = np.frombuffer(stream.read_bytes(), np.uint8).reshape(-1, H, W, 3)
+    assert rgb.shape[0] == n
+    for k in range(n):
+        assert np.array_equal(rgb[k, ..., 0], (want["rgba"][k] & 0xFF).astype(np.uint8)), k
+        assert np.array_equal(rgb[k, ..., 1], ((want["rgba"][k] >> 8) & 0xFF).astype(np.uint8)), k

@@ -282,3 +282,50 @@ def test_ply_reader_matches_oracle(pysvo, port, tmp_path):
         with pytest.raises(pysvo.SvoError) as e:
             pysvo.ply_read_triangles(q)
         assert e.value.status == 3, name
+
+
+def _viewer_script(rng, n):
+    """Random window events: motion with and without buttons held, presses and releases of both buttons (and of
+    buttons / keys the viewer ignores, which still wake it up)."""
+    ev = []
+    for _ in range(n):
+        r = rng.random()
+        if r < 0.55:
+            ev.append((4, 0, int(rng.integers(-40, 41)), int(rng.integers(-60, 61))))
+        elif r < 0.75:
+            ev.append((5, int(rng.choice([1, 3, 2, 4])), 0, 0))
+        elif r < 0.95:
+            ev.append((6, int(rng.choice([1, 3])), 0, 0))
+        else:
+            ev.append((2, int(rng.choice([32, 97])), 0, 0))
+    return ev
+
+
+def test_viewer_camera_control_matches_reference_viewer(pysvo, ref):
+    """Row f4: svo_viewer_feed (Events.cpp's mouse state + renderLoop's event handling, Main.cpp:229-252) against
+    the reference's own `-viewer` main loop run headless on a scripted SDL (oracle/_ref, svoref_viewer_run): the
+    same number of presented frames, each after the same number of consumed events, with bit-identical MODEL /
+    VIEW matrices and the same renderHalfSize -- including the reference's quirk that motion received while no
+    button is held is applied by the next button press, pitch wrapping, the yaw direction flip beyond 90 degrees of
+    pitch and the zoom clamps."""
+    from conftest import DRAGON
+    rng = np.random.default_rng(11)
+    scripts = [_viewer_script(rng, 150) for _ in range(3)]
+    scripts.append([(5, 3, 0, 0)] + [(4, 0, 0, -70)] * 12 + [(4, 0, 0, 90)] * 6 + [(6, 3, 0, 0)])      # zoom out to the 25 cap, in by the 0.5 clamp
+    scripts.append([(5, 1, 0, 0)] + [(4, 0, 7, -50)] * 9 + [(4, 0, -300, 0), (6, 1, 0, 0), (4, 0, 5, 5), (2, 27, 0, 0), (4, 0, 1, 1)])
+    for ev in scripts:
+        want = ref.viewer_run(DRAGON, 16, 16, 2, ev, want_pixels=False)
+        st = pysvo.viewer_init()
+        got = [(np.array(st.camera.model[:], np.float32), np.array(st.camera.view[:], np.float32), st.preview, 0)]
+        for i, e in enumerate(ev):
+            action = pysvo.viewer_feed(st, *e)
+            if action == pysvo.VIEWER_FRAME:
+                got.append((np.array(st.camera.model[:], np.float32), np.array(st.camera.view[:], np.float32), st.preview, i + 1))
+            elif action == pysvo.VIEWER_QUIT:
+                break
+        assert len(got) == len(want["half"])
+        for k, (m, v, half, taken) in enumerate(got):
+            assert np.array_equal(m.view(np.uint32), want["model"][k].view(np.uint32)), k
+            assert np.array_equal(v.view(np.uint32), want["view"][k].view(np.uint32)), k
+            assert half == want["half"][k] and taken == want["events_taken"][k], k
+    assert st.quit == 1 and pysvo.viewer_feed(st, 4, 0, 1, 1) == pysvo.VIEWER_QUIT
