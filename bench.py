@@ -598,6 +598,40 @@ def run_own(args):
         # untimed: the library creates its staging framebuffers on first use
         for k in range(len(hosts)):
             tree.frame_wait(tree.render_frame_async(cams[k % ORBIT], W, H, hosts[k], strips=STRIPS, flavour=flavour))
+    e2e_mode = "single"
+    e2e_lanes = min(n_lanes, 4)
+    frame_done = [None] * e2e_lanes
+    shared_host = None
+    per_rank = [world > 1 and not os.environ.get("SVO_BENCH_E2E_VIA_RANK0")]
+    if world > 1:
+        if rank == 0 and per_rank[0]:
+            try:        # the shared host frames live in /dev/shm (like NCCL's own shared-memory segments)
+                vfs = os.statvfs("/dev/shm")
+                per_rank[0] = vfs.f_bavail * vfs.f_frsize > 2 * e2e_lanes * nbytes
+            except OSError:
+                per_rank[0] = False
+        dist.broadcast_object_list(per_rank, src=0)
+    per_rank = bool(per_rank[0])
+    if per_rank:
+        # untimed set-up of the per-rank path: the shared host frames (one per frame in flight) and local framebuffers
+        name = [f"/dev/shm/svo_bench_{os.getpid()}.frames" if rank == 0 else None]
+        dist.broadcast_object_list(name, src=0)
+        if rank == 0:
+            shared_host = np.memmap(name[0], dtype=np.uint32, mode="w+", shape=(e2e_lanes, H, W))
+            shared_host[:] = 0
+        barrier()
+        if rank != 0:
+            shared_host = np.memmap(name[0], dtype=np.uint32, mode="r+", shape=(e2e_lanes, H, W))
+        shared_dev = pysvo.host_register(local_rank, shared_host)
+        if rank == 0:
+            local_fbs = fb_ptrs[:e2e_lanes]
+        else:
+            own = [pysvo.DeviceBuffer(local_rank, nbytes) for _ in range(e2e_lanes)]
+            for b in own:
+                b.zero()
+            local_fbs = [b.ptr for b in own]
+        for k in range(e2e_lanes):      # first use of the copy kernel / the mapping, untimed
+            pysvo.frame_copy_owned_tiles(local_rank, W, H, STRIPS, rank, world, local_fbs[k], shared_dev + k * nbytes, stream)
     torch.cuda.synchronize()
     barrier()
     t0 = time.perf_counter()
@@ -620,7 +654,8 @@ def run_own(args):
         if os.environ.get("SVO_BENCH_DEBUG"):
             print(f"[e2e] wait {dbg[0] / e2e_steps * 1e3:.3f} ms/frame, issue {dbg[1] / e2e_steps * 1e3:.3f} ms/frame",
                   file=sys.stderr, flush=True)
-    else:
+    elif not per_rank:
+        e2e_mode = "rank0"
         # every rank stores its tiles into rank 0's framebuffer k & 1 over NVLink; after the frame barrier
         # rank 0 copies it to pinned host memory on a side stream while frame k+1 is rendered into the other one
         copied = [None, None]
@@ -641,6 +676,31 @@ def run_own(args):
             for ev in copied:
                 if ev is not None:
                     ev.synchronize()
+    else:
+        # every rank renders its tiles into its OWN framebuffer and ships them itself (svo_frame_copy_owned_tiles)
+        # into one page-locked host frame that all ranks have mapped (a shared-memory segment): 1 / world of the
+        # frame per PCIe link instead of all of it over rank 0's. Four frames in flight, like the N = 1 path; the
+        # frame barrier (all-reduce enqueued behind each rank's copy) tells rank 0 that a host frame is complete.
+        e2e_mode = "per-rank"
+        for k in range(warmup, warmup + e2e_steps):
+            slot = k % e2e_lanes
+            if frame_done[slot] is not None:
+                frame_done[slot].synchronize()      # frame k-4 is complete in host memory: its slot is free again
+            with torch.cuda.stream(lanes[slot]):
+                tree.render_frame_device(cams[k % ORBIT], W, H, local_fbs[slot], strips=STRIPS, flavour=flavour,
+                                         tile_rank=rank, tile_world=world, stream=lanes[slot].cuda_stream)
+                pysvo.frame_copy_owned_tiles(local_rank, W, H, STRIPS, rank, world, local_fbs[slot],
+                                             shared_dev + slot * nbytes, lanes[slot].cuda_stream)
+                shipped = torch.cuda.Event()
+                shipped.record(lanes[slot])
+            comm.wait_event(shipped)
+            with torch.cuda.stream(comm):
+                dist.all_reduce(flag)
+                frame_done[slot] = torch.cuda.Event()
+                frame_done[slot].record(comm)
+        for ev in frame_done:
+            if ev is not None:
+                ev.synchronize()
     torch.cuda.synchronize()
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
@@ -648,6 +708,20 @@ def run_own(args):
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_rays = sum(rays_of(k) for k in range(warmup, warmup + e2e_steps))
     e2e_value = e2e_rays / float(e2e_s.item()) / 1e6
+    e2e_frame_identical = None
+    if shared_host is not None:
+        if rank == 0:
+            # the last host frame, assembled by all ranks, against the same camera rendered by rank 0 alone
+            k_last = warmup + e2e_steps - 1
+            tree.render_frame_device(cams[k_last % ORBIT], W, H, fb_ptrs[0], strips=STRIPS, flavour=flavour, stream=stream)
+            torch.cuda.synchronize()
+            alone = fbs[0].to_host(np.uint32).reshape(H, W)
+            e2e_frame_identical = bool(np.array_equal(alone, shared_host[k_last % e2e_lanes]))
+        barrier()
+        pysvo.host_unregister(shared_host)
+        del shared_host
+        if rank == 0:
+            os.unlink(name[0])
     if sampler:
         sampler.stop()
 
@@ -739,11 +813,17 @@ def run_own(args):
                    "rays_per_frame_mean": total_rays / steps, "ms_per_frame": total_ms / steps},
         "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 128, "d2h_bytes_per_step": nbytes,
                 "steps": e2e_steps, "ms_per_step": float(e2e_s.item()) / e2e_steps * 1e3,
-                "note": "per-step input is the 128 B camera (kernel parameters); the octree stays resident; "
-                        "svo_render_frame_async, four frames in flight, every frame copied to pinned host memory"},
+                "note": "per-step input is the 128 B camera (kernel parameters); the octree stays resident; " + {
+                    "single": "svo_render_frame_async, four frames in flight, every frame copied to pinned host memory",
+                    "per-rank": "every rank ships the tiles it rendered into ONE page-locked host frame shared by all ranks "
+                                "(svo_frame_copy_owned_tiles: 1 / world of the frame per PCIe link), four frames in flight, "
+                                "frame barrier behind the copies",
+                    "rank0": "tiles gathered in rank 0's HBM over NVLink, rank 0 copies every frame to pinned host memory",
+                }[e2e_mode]},
         "gpu_launches": 3 * steps * world,       # beam pass + tile classifier + fine pass per frame and rank
         "clocks": clocks,
-        "parity": parity,
+        "parity": dict(parity, **({"e2e_host_frame_identical_to_single_rank": e2e_frame_identical}
+                                  if e2e_frame_identical is not None else {})),
         "bytes_per_ray": {"coarse_node": coarse_b_ray, "fine_node": fine_b_ray},
     }
     if roofline is not None:

@@ -372,6 +372,19 @@ SVO_API int svo_render_frame_device(svo_tree *tree, const svo_camera *cam, const
                                     uint32_t *d_rgba, float *d_depth, void *stream,
                                     svo_frame_stats *stats, int sync_stats);
 
+/* The host-visible leg of a multi-GPU frame (bench.py `e2e` at N > 1; the reference has one address space and
+ * no counterpart): every rank copies the pixels of the tiles IT owns (desc->tile_rank / tile_world) from its
+ * framebuffer `d_src` to `d_dst`, a framebuffer of the same layout that may be local HBM, a peer mapping
+ * (svo_ipc_open) or page-locked host memory shared by all ranks and mapped with svo_host_register -- then each
+ * GPU ships 1 / world of the frame over its own PCIe link, 128 contiguous bytes per warp, instead of rank 0's
+ * link carrying all of it. Asynchronous on `stream`. */
+SVO_API int svo_frame_copy_owned_tiles(int device, const svo_frame_desc *desc, const uint32_t *d_src, uint32_t *d_dst,
+                                       void *stream);
+/* Page-locks and maps existing host memory (e.g. a shared-memory segment every rank has mapped) for `device`;
+ * *device_ptr is the address kernels and copies use. */
+SVO_API int svo_host_register(int device, void *p, size_t bytes, void **device_ptr);
+SVO_API int svo_host_unregister(void *p);
+
 /* ---- device memory + peer mapping (multi-GPU gather over NVLink) ----------- */
 
 SVO_API int svo_device_alloc(int device, size_t bytes, void **out);

@@ -518,6 +518,24 @@ int svo_host_free(void *p) {
     return SVO_OK;
 }
 
+int svo_host_register(int device, void *p, size_t bytes, void **device_ptr) {
+    if (!p || !bytes || !device_ptr) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_host_register: null argument");
+    *device_ptr = nullptr;
+    SVO_DEVICE(device);
+    SVO_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+    cudaError_t e = cudaHostGetDevicePointer(device_ptr, p, 0);
+    if (e != cudaSuccess) {
+        cudaHostUnregister(p);
+        return failCuda(e, "cudaHostGetDevicePointer");
+    }
+    return SVO_OK;
+}
+
+int svo_host_unregister(void *p) {
+    if (p) SVO_CUDA(cudaHostUnregister(p));
+    return SVO_OK;
+}
+
 /* ---- .oct ------------------------------------------------------------------ */
 
 int svo_oct_read(const char *path, uint32_t **words, uint64_t *n_words, float center[3]) {
@@ -1086,6 +1104,18 @@ int svo_render_frame_device(svo_tree *tree, const svo_camera *cam, const svo_fra
         SVO_CUDA(cudaStreamSynchronize(s));
         fillStats(plan, slot, desc, launches, stats);
     }
+    return SVO_OK;
+}
+
+int svo_frame_copy_owned_tiles(int device, const svo_frame_desc *desc, const uint32_t *d_src, uint32_t *d_dst, void *stream) {
+    if (!d_src || !d_dst) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_frame_copy_owned_tiles: null argument");
+    int st = checkDesc(desc);
+    if (st != SVO_OK) return st;
+    SVO_DEVICE(device);
+    svo::FramePlanDev p{};
+    planGeometry(desc->width, desc->height, desc->strips, p);
+    SVO_CUDA(svo::launchCopyOwnedColumns(p, desc->width, desc->height, d_src, d_dst, desc->tile_rank, desc->tile_world,
+                                         static_cast<cudaStream_t>(stream)));
     return SVO_OK;
 }
 

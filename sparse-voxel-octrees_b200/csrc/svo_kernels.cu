@@ -468,4 +468,31 @@ cudaError_t launchFinePass(const TreeDev &tree, const FramePlanDev &plan, const 
                 : launchFineT<false, uint32_t>(tree, plan, consts, tiles, counters, rgba, owned, pixelStride, stream);
 }
 
+// The pixels of the tile columns a rank owns, from one framebuffer to another of the same pitch: thread k of a
+// row moves pixel k of the rank's columns laid side by side, so a warp moves one run of four tile columns =
+// 32 pixels = 128 contiguous bytes on both sides -- one full-width PCIe write when `dst` is mapped host memory.
+__global__ void __launch_bounds__(256)
+copyOwnedColumnsKernel(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int width, int height,
+                       int ownedPixels, int run, int tileRank, int tileWorld) {
+    const uint32_t k = blockIdx.x*256u + threadIdx.x;
+    const int y = int(blockIdx.y);
+    if (k >= uint32_t(ownedPixels) || y >= height) return;
+    const uint32_t slot = k >> 3;                        // which of the rank's tile columns
+    const uint32_t tx = (slot/uint32_t(run))*uint32_t(tileWorld*run) + uint32_t(tileRank*run) + slot%uint32_t(run);
+    const uint32_t x = tx*8u + (k & 7u);
+    if (x >= uint32_t(width)) return;
+    const size_t at = size_t(y)*size_t(width) + x;
+    dst[at] = src[at];
+}
+
+cudaError_t launchCopyOwnedColumns(const FramePlanDev &plan, int width, int height, const uint32_t *src, uint32_t *dst,
+                                   int tileRank, int tileWorld, cudaStream_t stream) {
+    const int ownedPixels = ownedCols(plan, tileRank, tileWorld)*8;
+    if (ownedPixels <= 0) return cudaSuccess;
+    dim3 grid(unsigned((ownedPixels + 255)/256), unsigned(height));
+    copyOwnedColumnsKernel<<<grid, 256, 0, stream>>>(src, dst, width, height, ownedPixels, tileRunLength(tileWorld),
+                                                     tileRank, tileWorld);
+    return cudaGetLastError();
+}
+
 } // namespace svo

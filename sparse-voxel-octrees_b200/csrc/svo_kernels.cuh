@@ -87,4 +87,9 @@ cudaError_t launchFinePass(const TreeDev &tree, const FramePlanDev &plan, const 
                            const TileRecord *tiles, const FrameCounters *counters, uint32_t *rgba,
                            int tileRank, int tileWorld, int pixelStride, cudaStream_t stream);
 
+// The owned tile columns' pixels from `src` to `dst` (both width x height, pitch = width): the per-rank
+// device -> host leg of a multi-GPU frame when `dst` is mapped page-locked host memory.
+cudaError_t launchCopyOwnedColumns(const FramePlanDev &plan, int width, int height, const uint32_t *src, uint32_t *dst,
+                                   int tileRank, int tileWorld, cudaStream_t stream);
+
 } // namespace svo

@@ -145,6 +145,9 @@ def lib():
         "svo_device_count": (i32, [P(i32)]),
         "svo_free": (None, [vp]),
         "svo_host_alloc": (i32, [C.c_size_t, P(vp)]),
+        "svo_host_register": (i32, [i32, vp, C.c_size_t, P(vp)]),
+        "svo_host_unregister": (i32, [vp]),
+        "svo_frame_copy_owned_tiles": (i32, [i32, P(FrameDesc), vp, vp, vp]),
         "svo_host_free": (i32, [vp]),
         "svo_oct_read": (i32, [C.c_char_p, P(P(C.c_uint32)), P(u64), P(f32)]),
         "svo_oct_write": (i32, [C.c_char_p, vp, u64, P(f32), i32]),
@@ -364,6 +367,26 @@ def ipc_close(device, ptr: int):
 def device_to_host_async(device, host_array, device_ptr, nbytes, stream=0):
     _check(lib().svo_device_to_host_async(int(device), _ptr(host_array), C.c_void_p(device_ptr), int(nbytes),
                                           C.c_void_p(stream or None)))
+
+
+def host_register(device, array) -> int:
+    """Page-locks and maps an existing host array (e.g. a shared-memory segment) for `device`; returns the device
+    address kernels and copies use. Undo with host_unregister(array) before the array goes away."""
+    out = C.c_void_p()
+    _check(lib().svo_host_register(int(device), _ptr(array), int(array.nbytes), C.byref(out)))
+    return int(out.value)
+
+
+def host_unregister(array):
+    _check(lib().svo_host_unregister(_ptr(array)))
+
+
+def frame_copy_owned_tiles(device, width, height, strips, tile_rank, tile_world, src_ptr, dst_ptr, stream=0):
+    """The pixels of the tiles (tile_rank of tile_world) owns, from framebuffer src_ptr to framebuffer dst_ptr
+    (device addresses: HBM, a peer mapping, or host memory mapped with host_register). Asynchronous on `stream`."""
+    desc = FrameDesc(width, height, strips, FLAVOUR_VALIDATION, tile_rank, tile_world, 1)
+    _check(lib().svo_frame_copy_owned_tiles(int(device), C.byref(desc), C.c_void_p(src_ptr), C.c_void_p(dst_ptr),
+                                            C.c_void_p(stream or None)))
 
 
 def device_synchronize(device=0):

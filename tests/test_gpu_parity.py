@@ -175,6 +175,36 @@ def test_frame_tile_interleave_reassembles(pysvo, gpu_dragon, pins):
         buf.free()
 
 
+@pytest.mark.parametrize("shape", [(1280, 720, 16), (333, 187, 5)])
+def test_owned_tiles_to_mapped_host_frame(pysvo, gpu_dragon, pins, shape):
+    """The host-visible leg of a multi-GPU frame, on one device: every rank renders its tiles into its OWN
+    framebuffer and ships them with svo_frame_copy_owned_tiles into one page-locked host frame that was mapped with
+    svo_host_register (a plain numpy array here, a shared-memory segment in bench.py); the host frame ends up equal
+    to the single-rank frame and no rank touches another rank's pixels."""
+    W, H, S = shape
+    cam = _cam(pysvo, pins["cameras"][0])
+    full, _, _ = gpu_dragon.render_frame(cam, W, H, strips=S, flavour=pysvo.FLAVOUR_VALIDATION)
+    dev = gpu_dragon.device
+    for world in (2, 8, 3):
+        host = np.full((H, W), 0xDEADBEEF, np.uint32)
+        mapped = pysvo.host_register(dev, host)
+        try:
+            for rank in range(world):
+                local = pysvo.DeviceBuffer(dev, W * H * 4)
+                local.from_host(np.full(W * H, 0x01010101 * (rank + 1), np.uint32))
+                gpu_dragon.render_frame_device(cam, W, H, local.ptr, strips=S, flavour=pysvo.FLAVOUR_VALIDATION,
+                                               tile_rank=rank, tile_world=world)
+                pysvo.frame_copy_owned_tiles(dev, W, H, S, rank, world, local.ptr, mapped)
+                pysvo.device_synchronize(dev)
+                local.free()
+                if rank < world - 1:
+                    assert (host == 0xDEADBEEF).any()
+                assert not np.isin(host, [0x01010101 * (r + 1) for r in range(world)]).any()   # only owned pixels moved
+            assert np.array_equal(host, full), world
+        finally:
+            pysvo.host_unregister(host)
+
+
 def test_pipelined_frames_match_synchronous(pysvo, gpu_dragon, pins):
     """svo_render_frame_async: four frames in flight, beam passes running ahead of the fine passes,
     copies on their own stream -- every frame must equal the synchronous result."""
