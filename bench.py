@@ -623,6 +623,13 @@ def run_own(args):
         if rank != 0:
             shared_host = np.memmap(name[0], dtype=np.uint32, mode="r+", shape=(e2e_lanes, H, W))
         shared_dev = pysvo.host_register(local_rank, shared_host)
+        # wider stripes for this leg: a rank's rows of pixels are what one PCIe write burst carries (measured: 128-byte
+        # runs 28 GB/s, whole rows 50 GB/s); the widest run <= 16 tile columns that still deals every rank the same
+        # number of columns, else the default of 4. The image does not depend on it.
+        tile_cols = (W - 1) // 8 + 1
+        e2e_run = int(os.environ.get("SVO_BENCH_E2E_RUN", "0")) or next(
+            (r for r in range(16, 4, -1) if tile_cols % (world * r) == 0), 4)
+        pysvo.frame_set_tile_run(e2e_run)
         if rank == 0:
             local_fbs = fb_ptrs[:e2e_lanes]
         else:
@@ -718,6 +725,7 @@ def run_own(args):
             alone = fbs[0].to_host(np.uint32).reshape(H, W)
             e2e_frame_identical = bool(np.array_equal(alone, shared_host[k_last % e2e_lanes]))
         barrier()
+        pysvo.frame_set_tile_run(0)
         pysvo.host_unregister(shared_host)
         del shared_host
         if rank == 0:
@@ -816,7 +824,8 @@ def run_own(args):
                 "note": "per-step input is the 128 B camera (kernel parameters); the octree stays resident; " + {
                     "single": "svo_render_frame_async, four frames in flight, every frame copied to pinned host memory",
                     "per-rank": "every rank ships the tiles it rendered into ONE page-locked host frame shared by all ranks "
-                                "(svo_frame_copy_owned_tiles: 1 / world of the frame per PCIe link), four frames in flight, "
+                                "(svo_frame_copy_owned_tiles: 1 / world of the frame per PCIe link, stripes "
+                                f"{e2e_run if world > 1 and per_rank else 4} tile columns wide), four frames in flight, "
                                 "frame barrier behind the copies",
                     "rank0": "tiles gathered in rank 0's HBM over NVLink, rank 0 copies every frame to pinned host memory",
                 }[e2e_mode]},

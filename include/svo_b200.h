@@ -335,6 +335,12 @@ SVO_API int svo_frame_get_layout(int width, int height, int strips, svo_frame_la
 SVO_API int svo_frame_tile_rect(int width, int height, int strips, int tile, int32_t rect[4]);
 /* Rank that renders tile `tile` under an interleave over `tile_world` ranks; < 0 on bad arguments. */
 SVO_API int svo_frame_tile_owner(int width, int height, int strips, int tile, int tile_world);
+/* Width, in 8-pixel tile columns, of the vertical stripes the ranks are dealt (default 4 = 32 pixels; the
+ * environment variable SVO_TILE_RUN sets the initial value; run <= 0 restores the default). Process-wide, to be
+ * called by every rank with the same value while no frame is in flight. The image does not depend on it. Wider
+ * stripes make each rank's rows of pixels longer -- what svo_frame_copy_owned_tiles moves per PCIe write burst:
+ * measured on B200, 128-byte runs (the default) reach 28 GB/s into mapped host memory, whole rows 50 GB/s. */
+SVO_API int svo_frame_set_tile_run(int run);
 
 /* Host-buffer variant: rgba (width*height uint32, the reference's backBuffer
  * layout 0xFF000000|b<<16|g<<8|r, Main.cpp:128-134; pitch = width*4) and the

@@ -42,6 +42,8 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -255,8 +257,30 @@ cudaMemPool_t scratchPool() {
     return pools[device];
 }
 
-void trimScratchPool() {
-    if (cudaMemPool_t pool = scratchPool()) cudaMemPoolTrimTo(pool, size_t(256) << 20);
+// Trimming the pool (unmapping and freeing tens of GB) takes 0.1 - 2 s, none of which the caller of a build
+// has to wait for: it runs on a background thread, which the next build (or process exit) joins first.
+struct PoolTrimmer {
+    std::mutex lock;
+    std::thread worker;
+    void wait() {
+        std::lock_guard<std::mutex> g(lock);
+        if (worker.joinable()) worker.join();
+    }
+    void start() {
+        cudaMemPool_t pool = scratchPool();
+        int device = 0;
+        if (!pool || cudaGetDevice(&device) != cudaSuccess) return;
+        std::lock_guard<std::mutex> g(lock);
+        if (worker.joinable()) worker.join();
+        worker = std::thread([pool, device] {
+            if (cudaSetDevice(device) == cudaSuccess) cudaMemPoolTrimTo(pool, size_t(256) << 20);
+        });
+    }
+    ~PoolTrimmer() { if (worker.joinable()) worker.join(); }
+};
+PoolTrimmer &poolTrimmer() {
+    static PoolTrimmer t;
+    return t;
 }
 
 template <typename T>
@@ -315,6 +339,8 @@ struct Timer {
 
 } // namespace
 
+cudaMemPool_t buildScratchPool() { return scratchPool(); }
+
 OctreeBuilder::~OctreeBuilder() {
     if (dKeys_) cudaFree(dKeys_);
     if (dVals_) cudaFree(dVals_);
@@ -322,6 +348,7 @@ OctreeBuilder::~OctreeBuilder() {
 }
 
 bool OctreeBuilder::begin(int w, int h, int d, std::string &err) {
+    poolTrimmer().wait();      // a trim left over from the previous build would take back what this one reuses
     if (w <= 0 || h <= 0 || d <= 0) { err = "volume dimensions must be positive"; return false; }
     if (w > (1 << 21) || h > (1 << 21) || d > (1 << 21)) { err = "volume dimensions above 2^21 are not supported"; return false; }
     w_ = w; h_ = h; d_ = d;
@@ -534,9 +561,9 @@ bool OctreeBuilder::finish(BuildResult &out, std::string &err) {
     numRuns.release();
     cudaStreamSynchronize(0);
     const double releasedAt = wallMs();
-    trimScratchPool();
+    poolTrimmer().start();
     if (debugTiming)
-        fprintf(stderr, "[svo] OctreeBuilder::finish: %.1f ms to the last kernel (device %.1f ms), %.1f ms releasing scratch, %.1f ms trimming the pool\n",
+        fprintf(stderr, "[svo] OctreeBuilder::finish: %.1f ms to the last kernel (device %.1f ms), %.1f ms releasing scratch, %.1f ms handing the pool to the trimmer\n",
                 builtAt, stats.sortMs + stats.levelsMs + stats.emitMs, releasedAt - builtAt, wallMs() - releasedAt);
 
     out.dWords = guard.p;

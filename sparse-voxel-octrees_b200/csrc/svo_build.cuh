@@ -56,6 +56,12 @@ private:
     float gatherMs_ = 0.0f;
 };
 
+// The builder's private stream-ordered memory pool on the current device (nullptr if pools are unavailable).
+// The voxeliser allocates from it too, so the tens of GB it releases are what the build that follows reuses.
+// OctreeBuilder::finish hands the pool to a background thread for trimming (giving 40 GB back to the driver
+// takes up to 2 s); the next build waits for that thread first.
+cudaMemPool_t buildScratchPool();
+
 // The inverse of the builder: the filled voxels of a node array resident on the current device, in
 // Morton order (ascending x + 2y + 4z per level). Outputs are cudaMalloc'ed: 3 coordinates per voxel and
 // one material word per voxel.

@@ -1065,6 +1065,12 @@ int svo_frame_tile_owner(int width, int height, int strips, int tile, int tile_w
     return ((tile % p.tileCols)/svo::tileRunLength(tile_world)) % tile_world;
 }
 
+int svo_frame_set_tile_run(int run) {
+    if (run > 4096) return fail(SVO_ERR_INVALID_ARGUMENT, "tile run %d is out of range", run);
+    svo::setTileRunLength(run);
+    return SVO_OK;
+}
+
 int svo_frame_tile_rect(int width, int height, int strips, int tile, int32_t rect[4]) {
     if (!rect) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_frame_tile_rect: null argument");
     svo_frame_desc d = {width, height, strips, SVO_FLAVOUR_VALIDATION, 0, 1, 0, 0};

@@ -8,6 +8,8 @@
 // instruction issue and SIMT divergence long before HBM bandwidth.
 #include "svo_kernels.cuh"
 
+#include <atomic>
+
 #include <cstdlib>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -288,14 +290,20 @@ cudaError_t ensureSmem(K kernel, size_t bytes) {
 } // namespace
 
 // Tile column tx belongs to rank (tx / run) % world: vertical stripes `run` tiles wide.
-int tileRunLength(int tileWorld) {
-    static int run = [] {
+namespace {
+std::atomic<int> &tileRunSetting() {
+    static std::atomic<int> run([] {
         const char *e = getenv("SVO_TILE_RUN");
         int v = e ? atoi(e) : 0;
         return v > 0 ? v : 4;
-    }();
-    return tileWorld > 1 ? run : 1;
+    }());
+    return run;
 }
+} // namespace
+
+int tileRunLength(int tileWorld) { return tileWorld > 1 ? tileRunSetting().load(std::memory_order_relaxed) : 1; }
+
+void setTileRunLength(int run) { tileRunSetting().store(run > 0 ? run : 4, std::memory_order_relaxed); }
 
 int ownedTileColumns(int tileCols, int tileRank, int tileWorld) {
     int run = tileRunLength(tileWorld), n = 0;

@@ -67,6 +67,7 @@ cudaError_t launchShadeBatch(uint64_t n, const uint8_t *hit, const uint32_t *nor
 
 // Multi-GPU tile interleave: tile column tx belongs to rank (tx / run) % world.
 int tileRunLength(int tileWorld);
+void setTileRunLength(int run);      // process-wide; <= 0 restores the default of four
 int ownedTileColumns(int tileCols, int tileRank, int tileWorld);
 
 // Beam pass; also zeroes `counters` for the classifier that follows on the same stream.

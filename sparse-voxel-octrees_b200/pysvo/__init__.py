@@ -177,6 +177,7 @@ def lib():
         "svo_frame_get_layout": (i32, [i32, i32, i32, P(FrameLayout)]),
         "svo_frame_tile_rect": (i32, [i32, i32, i32, i32, P(C.c_int32)]),
         "svo_frame_tile_owner": (i32, [i32, i32, i32, i32, i32]),
+        "svo_frame_set_tile_run": (i32, [i32]),
         "svo_render_frame": (i32, [vp, P(Camera), P(FrameDesc), vp, vp, P(FrameStats)]),
         "svo_render_frame_device": (i32, [vp, P(Camera), P(FrameDesc), vp, vp, vp, P(FrameStats), i32]),
         "svo_render_frame_async": (i32, [vp, P(Camera), P(FrameDesc), vp, vp, i32, P(i32)]),
@@ -367,6 +368,11 @@ def ipc_close(device, ptr: int):
 def device_to_host_async(device, host_array, device_ptr, nbytes, stream=0):
     _check(lib().svo_device_to_host_async(int(device), _ptr(host_array), C.c_void_p(device_ptr), int(nbytes),
                                           C.c_void_p(stream or None)))
+
+
+def frame_set_tile_run(run):
+    """Width of the ranks' vertical stripes in tile columns (process-wide; <= 0 restores the default of 4)."""
+    _check(lib().svo_frame_set_tile_run(int(run)))
 
 
 def host_register(device, array) -> int:

@@ -185,7 +185,8 @@ def test_owned_tiles_to_mapped_host_frame(pysvo, gpu_dragon, pins, shape):
     cam = _cam(pysvo, pins["cameras"][0])
     full, _, _ = gpu_dragon.render_frame(cam, W, H, strips=S, flavour=pysvo.FLAVOUR_VALIDATION)
     dev = gpu_dragon.device
-    for world in (2, 8, 3):
+    for world, run in ((2, 4), (8, 4), (3, 4), (2, 16), (4, 15), (3, 7)):
+        pysvo.frame_set_tile_run(run)       # stripe width in tile columns: the partition changes, the image does not
         host = np.full((H, W), 0xDEADBEEF, np.uint32)
         mapped = pysvo.host_register(dev, host)
         try:
@@ -197,11 +198,12 @@ def test_owned_tiles_to_mapped_host_frame(pysvo, gpu_dragon, pins, shape):
                 pysvo.frame_copy_owned_tiles(dev, W, H, S, rank, world, local.ptr, mapped)
                 pysvo.device_synchronize(dev)
                 local.free()
-                if rank < world - 1:
-                    assert (host == 0xDEADBEEF).any()
+                if rank == 0:
+                    assert (host == 0xDEADBEEF).any()          # rank 1 always owns something at these sizes
                 assert not np.isin(host, [0x01010101 * (r + 1) for r in range(world)]).any()   # only owned pixels moved
-            assert np.array_equal(host, full), world
+            assert np.array_equal(host, full), (world, run)
         finally:
+            pysvo.frame_set_tile_run(0)
             pysvo.host_unregister(host)
 
 

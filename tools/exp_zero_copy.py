@@ -31,9 +31,11 @@ def timed(fn, n=50):
     return a.elapsed_time(b) / n
 
 
-for world in (1, 2, 4, 8):
+for world, run in ((1, 4), (2, 4), (4, 4), (8, 4), (2, 8), (2, 16), (4, 15), (8, 15), (2, 60)):
+    pysvo.frame_set_tile_run(run)
     ms = timed(lambda: pysvo.frame_copy_owned_tiles(dev, W, H, S, 0, world, fb.ptr, mapped, stream))
-    print(f"zero-copy kernel, rank 0 of {world}: {ms:.4f} ms, {nbytes / world / ms / 1e6:.1f} GB/s")
+    print(f"zero-copy kernel, rank 0 of {world}, stripes of {run} tile columns ({run * 32} B): {ms:.4f} ms, {nbytes / world / ms / 1e6:.1f} GB/s")
+pysvo.frame_set_tile_run(0)
 assert np.array_equal(host[:, :32], np.arange(W * H, dtype=np.uint32).reshape(H, W)[:, :32])
 ms = timed(lambda: pysvo.device_to_host_async(dev, pinned.array, fb.ptr, nbytes, stream))
 print(f"copy engine, whole frame: {ms:.4f} ms, {nbytes / ms / 1e6:.1f} GB/s")
