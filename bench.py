@@ -616,13 +616,34 @@ def run_own(args):
         # untimed set-up of the per-rank path: the shared host frames (one per frame in flight) and local framebuffers
         name = [f"/dev/shm/svo_bench_{os.getpid()}.frames" if rank == 0 else None]
         dist.broadcast_object_list(name, src=0)
-        if rank == 0:
-            shared_host = np.memmap(name[0], dtype=np.uint32, mode="w+", shape=(e2e_lanes, H, W))
-            shared_host[:] = 0
+        ok, registered = True, False
+        try:
+            if rank == 0:
+                shared_host = np.memmap(name[0], dtype=np.uint32, mode="w+", shape=(e2e_lanes, H, W))
+                shared_host[:] = 0
+        except Exception as e:  # noqa: BLE001
+            ok = False
+            print(f"[rank {rank}] shared host frame: {e!r}", file=sys.stderr, flush=True)
         barrier()
-        if rank != 0:
-            shared_host = np.memmap(name[0], dtype=np.uint32, mode="r+", shape=(e2e_lanes, H, W))
-        shared_dev = pysvo.host_register(local_rank, shared_host)
+        try:
+            if rank != 0:
+                shared_host = np.memmap(name[0], dtype=np.uint32, mode="r+", shape=(e2e_lanes, H, W))
+            shared_dev = pysvo.host_register(local_rank, shared_host)
+            registered = True
+        except Exception as e:  # noqa: BLE001
+            ok = False
+            print(f"[rank {rank}] mapping the shared host frame: {e!r}", file=sys.stderr, flush=True)
+        all_ok = torch.tensor([1 if ok else 0], device="cuda", dtype=torch.int32)
+        dist.all_reduce(all_ok, op=dist.ReduceOp.MIN)
+        if not int(all_ok.item()):       # some rank could not map it: every rank takes the rank-0 path instead
+            if registered:
+                pysvo.host_unregister(shared_host)
+            shared_host = None
+            per_rank = False
+            barrier()
+            if rank == 0 and os.path.exists(name[0]):
+                os.unlink(name[0])
+    if per_rank:
         # wider stripes for this leg: a rank's rows of pixels are what one PCIe write burst carries (measured: 128-byte
         # runs 28 GB/s, whole rows 50 GB/s); the widest run <= 16 tile columns that still deals every rank the same
         # number of columns, else the default of 4. The image does not depend on it.
