@@ -329,3 +329,33 @@ def test_viewer_camera_control_matches_reference_viewer(pysvo, ref):
             assert np.array_equal(v.view(np.uint32), want["view"][k].view(np.uint32)), k
             assert half == want["half"][k] and taken == want["events_taken"][k], k
     assert st.quit == 1 and pysvo.viewer_feed(st, 4, 0, 1, 1) == pysvo.VIEWER_QUIT
+
+
+def test_viewer_camera_control_matches_golden_sessions(pysvo, port, dragon_words):
+    """The same check against the committed vectors (tests/golden/viewer_sessions.npz, minted from the reference's own
+    viewer by tests/golden/make_viewer_golden.py), which needs no reference build; and the oracle restatement's frames
+    for the recorded matrices equal the frames the reference's window showed (full-resolution and stride-3 previews)."""
+    from conftest import GOLDEN
+    g = np.load(GOLDEN / "viewer_sessions.npz")
+    n_sessions = sum(1 for k in g.files if k.startswith("events_"))
+    assert n_sessions >= 5
+    for i in range(n_sessions):
+        st = pysvo.viewer_init()
+        got = [(np.array(st.camera.model[:], np.float32), np.array(st.camera.view[:], np.float32), st.preview, 0)]
+        for j, e in enumerate(g[f"events_{i}"]):
+            action = pysvo.viewer_feed(st, *[int(v) for v in e])
+            if action == pysvo.VIEWER_FRAME:
+                got.append((np.array(st.camera.model[:], np.float32), np.array(st.camera.view[:], np.float32), st.preview, j + 1))
+            elif action == pysvo.VIEWER_QUIT:
+                break
+        assert len(got) == len(g[f"half_{i}"]), i
+        for k, (m, v, half, taken) in enumerate(got):
+            assert np.array_equal(m.view(np.uint32), g[f"model_{i}"][k].view(np.uint32)), (i, k)
+            assert np.array_equal(v.view(np.uint32), g[f"view_{i}"][k].view(np.uint32)), (i, k)
+            assert half == g[f"half_{i}"][k] and taken == g[f"taken_{i}"][k], (i, k)
+    words, center = dragon_words
+    W, H, S = (int(v) for v in g["frame_shape"])
+    for k in range(len(g["half_0"])):
+        f = port.frame_constants(g["model_0"][k], g["view_0"][k], center, W, H, S)
+        img = port.render_frame(words, f, pixel_stride=3 if g["half_0"][k] else 1)[0]
+        assert np.array_equal(img, g["rgba_0"][k]), k
