@@ -72,8 +72,9 @@ static std::vector<svo_viewer_event> readEventScript(const std::string &path) {
 
 int main(int argc, char **argv) {
     if (argc < 2) {
-        fprintf(stderr, "usage: %s <in.oct> [--size WxH] [--strips N] [--frames K] [--radius R] [--pitch P] "
-                        "[--yaw0 Y] [--yaw-step S] [--validation] [--out prefix]\n", argv[0]);
+        fprintf(stderr, "usage: %s <in.oct> [--size WxH] [--strips N] [--frames K] [--radius R] [--pitch P] [--yaw0 Y] "
+                        "[--yaw-step S] [--validation] [--preview] [--events script] [--out prefix] [--raw file|-]\n"
+                        "       %s -builder [--resolution r --mode m] <in.ply | in.voxel> <out.oct>\n", argv[0], argv[0]);
         return 2;
     }
     if (std::string(argv[1]) == "-builder") {
@@ -125,6 +126,8 @@ int main(int argc, char **argv) {
         else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
     try {
+        std::vector<svo_viewer_event> script;
+        if (!events.empty()) script = readEventScript(events);     // before anything touches the GPU: a bad script fails fast
         VoxelOctree tree(argv[1]);
         FILE *info = raw == "-" ? stderr : stdout;
         FILE *rawFile = raw.empty() ? 0 : raw == "-" ? stdout : fopen(raw.c_str(), "wb");
@@ -135,8 +138,6 @@ int main(int argc, char **argv) {
         if (svo_host_alloc(size_t(w)*h*4, reinterpret_cast<void **>(&rgba)) != SVO_OK) throw std::runtime_error(svo_last_error());
         double totalMs = 0.0;
         unsigned long long rays = 0;
-        std::vector<svo_viewer_event> script;
-        if (!events.empty()) script = readEventScript(events);
         svo_viewer_state viewer;
         svo_viewer_init(&viewer);
         size_t nextEvent = 0;

@@ -359,3 +359,28 @@ def test_viewer_camera_control_matches_golden_sessions(pysvo, port, dragon_words
         f = port.frame_constants(g["model_0"][k], g["view_0"][k], center, W, H, S)
         img = port.render_frame(words, f, pixel_stride=3 if g["half_0"][k] else 1)[0]
         assert np.array_equal(img, g["rgba_0"][k]), k
+
+
+def test_headless_driver_reports_errors_without_a_gpu(pysvo, tmp_path):
+    """svo_headless: a malformed or missing event script fails before anything touches the GPU; without a device the
+    driver says so (no CPU fallback) instead of rendering anything."""
+    import subprocess
+    from conftest import DRAGON, ROOT
+    pkg = ROOT / "sparse-voxel-octrees_b200"
+    subprocess.check_call(["make", "-C", str(pkg), "headless"], stdout=subprocess.DEVNULL)
+    exe = str(pkg / "svo_headless")
+    bad = tmp_path / "bad.events"
+    bad.write_text("# session\nmotion 1 2\nwiggle 3\n")
+    out = subprocess.run([exe, str(DRAGON), "--events", str(bad)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 1 and "bad.events:3: cannot parse event" in out.stderr
+    out = subprocess.run([exe, str(DRAGON), "--events", str(tmp_path / "none.events")], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 1 and "cannot read" in out.stderr
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 2 and "--events script" in out.stderr and "-builder" in out.stderr
+    out = subprocess.run([exe, str(DRAGON), "--bogus"], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 2 and "unknown option" in out.stderr
+    if pysvo.device_count() < 1:
+        good = tmp_path / "ok.events"
+        good.write_text("down left\nmotion 4 -3\nup left\n")
+        out = subprocess.run([exe, str(DRAGON), "--events", str(good)], capture_output=True, text=True, timeout=60)
+        assert out.returncode == 1 and "no CPU fallback" in out.stderr
