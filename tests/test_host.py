@@ -384,3 +384,15 @@ def test_headless_driver_reports_errors_without_a_gpu(pysvo, tmp_path):
         good.write_text("down left\nmotion 4 -3\nup left\n")
         out = subprocess.run([exe, str(DRAGON), "--events", str(good)], capture_output=True, text=True, timeout=60)
         assert out.returncode == 1 and "no CPU fallback" in out.stderr
+
+
+def test_readers_survive_mutated_files(pysvo, tmp_path):
+    """.oct and PLY readers on 150 mutated files each (tests/fuzz_readers.py, in a child process): every file decodes
+    or is rejected with a status -- no crash, no hang."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    out = subprocess.run([sys.executable, str(ROOT / "tests" / "fuzz_readers.py"), "5", "150", str(tmp_path)],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, (out.returncode, out.stderr[-2000:])
+    assert "fuzz done" in out.stdout and "'ply rejected': 0" not in out.stdout and "'oct rejected': 0" not in out.stdout
