@@ -45,6 +45,49 @@ struct Element { std::string name; long long count = 0; std::vector<Property> pr
 
 struct FileCloser { void operator()(FILE *f) const { if (f) fclose(f); } };
 
+inline bool isSpace(uint8_t c) { return c == ' ' || c == '\n' || c == '\r' || c == '\t'; }
+
+// strtod for the tokens mesh files are made of, exactly: [-+]digits[.digits][e[-+]digits] with at most 15 significant
+// digits and a decimal exponent within +-22. Then the digits are an integer below 2^53 and the power of ten is a double
+// too, so ONE correctly rounded multiply or divide gives the correctly rounded result -- what strtod returns
+// (Clinger's fast path). Anything else (more digits, inf / nan, hex, junk) is left to strtod.
+inline bool fastDecimal(const uint8_t *p, double &out, const uint8_t **end = nullptr) {
+    static const double pow10[23] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15,
+                                     1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+    bool negative = false;
+    if (*p == '-' || *p == '+') { negative = *p == '-'; ++p; }
+    uint64_t mantissa = 0;
+    int digits = 0, significant = 0, exponent = 0;
+    for (; *p >= '0' && *p <= '9'; ++p, ++digits) {
+        if (significant > 0 || *p != '0') { if (++significant > 15) return false; }
+        mantissa = mantissa*10 + uint64_t(*p - '0');
+    }
+    if (*p == '.') {
+        ++p;
+        for (; *p >= '0' && *p <= '9'; ++p, ++digits, --exponent) {
+            if (significant > 0 || *p != '0') { if (++significant > 15) return false; }
+            mantissa = mantissa*10 + uint64_t(*p - '0');
+        }
+    }
+    if (digits == 0) return false;
+    if (*p == 'e' || *p == 'E') {
+        ++p;
+        bool expNegative = false;
+        if (*p == '-' || *p == '+') { expNegative = *p == '-'; ++p; }
+        int e = 0, expDigits = 0;
+        for (; *p >= '0' && *p <= '9' && expDigits < 4; ++p, ++expDigits) e = e*10 + (*p - '0');
+        if (expDigits == 0 || (*p >= '0' && *p <= '9')) return false;
+        exponent += expNegative ? -e : e;
+    }
+    if (*p != 0 && !isSpace(*p)) return false;
+    if (exponent < -22 || exponent > 22) return false;
+    double v = double(mantissa);                          // exact: below 10^15 < 2^53
+    v = exponent < 0 ? v/pow10[-exponent] : v*pow10[exponent];
+    out = negative ? -v : v;
+    if (end) *end = p;
+    return true;
+}
+
 // Cursor over the element data, which is held in memory as a whole: a 10 M-triangle file is 55 M scalars,
 // and one fread per scalar costs more than everything the GPU does with the mesh afterwards.
 class Reader {
@@ -56,6 +99,9 @@ public:
         if (format_ == 0) {
             while (p_ < end_ && (*p_ == ' ' || *p_ == '\n' || *p_ == '\r' || *p_ == '\t')) ++p_;
             if (p_ >= end_) { ok = false; return 0.0; }
+            double fast;
+            const uint8_t *after;
+            if (fastDecimal(p_, fast, &after)) { p_ = after; return fast; }
             char *stop = nullptr;
             const double v = strtod(reinterpret_cast<const char *>(p_), &stop);   // the buffer is NUL-terminated
             if (stop == reinterpret_cast<const char *>(p_)) { ok = false; return 0.0; }
@@ -101,16 +147,17 @@ private:
 inline float minStd(float a, float b) { return (b < a) ? b : a; }   // std::min(a, b)
 inline float maxStd(float a, float b) { return (a < b) ? b : a; }   // std::max(a, b)
 
-int workerCount(size_t items) {
+int workerCount(size_t items, size_t worthIt = 65536) {
     int n = int(std::thread::hardware_concurrency());
     if (n > 16) n = 16;
-    if (n < 1 || items < 65536) n = 1;
+    if (n < 1 || items < worthIt) n = 1;
+    if (size_t(n) > items && items > 0) n = int(items);
     return n;
 }
 
 template <class Fn>
-void parallelRanges(size_t items, Fn fn) {      // fn(threadIndex, begin, end)
-    const int n = workerCount(items);
+void parallelRanges(size_t items, Fn fn, size_t worthIt = 65536) {      // fn(threadIndex, begin, end)
+    const int n = workerCount(items, worthIt);
     std::vector<std::thread> pool;
     for (int t = 1; t < n; ++t) pool.emplace_back(fn, t, items*size_t(t)/size_t(n), items*size_t(t + 1)/size_t(n));
     fn(0, size_t(0), items/size_t(n));
@@ -175,6 +222,84 @@ private:
     size_t mapBytes_ = 0;
     std::vector<uint8_t> text_;
     const uint8_t *begin_ = nullptr, *end_ = nullptr;
+};
+
+
+// ASCII element data as a stream of whitespace-separated tokens, cut into chunks at token boundaries with the
+// global index of every chunk's first token known (one parallel counting sweep). An element whose records have a
+// fixed number of tokens -- scalar properties only, or faces that all turn out to be triangles -- can then be
+// parsed on all cores: a token's global index says which record and which property it is.
+
+class AsciiTokens {
+public:
+    AsciiTokens(const uint8_t *begin, const uint8_t *end) {
+        const size_t bytes = size_t(end - begin);
+        const int chunks = workerCount(bytes/8)*4;
+        starts_.push_back(begin);
+        for (int k = 1; k < chunks; ++k) {
+            const uint8_t *p = begin + bytes*size_t(k)/size_t(chunks);
+            while (p < end && !isSpace(*p)) ++p;          // a token belongs to the chunk it starts in
+            if (p > starts_.back()) starts_.push_back(p);
+        }
+        starts_.push_back(end);
+        const size_t n = starts_.size() - 1;
+        first_.assign(n + 1, 0);
+        parallelRanges(n, [&](int, size_t a, size_t b) {
+            for (size_t c = a; c < b; ++c) {
+                uint64_t count = 0;
+                bool inToken = false;                     // every chunk starts at the data start or on whitespace
+                for (const uint8_t *p = starts_[c]; p < starts_[c + 1]; ++p) {
+                    const bool sp = isSpace(*p);
+                    count += (!sp && !inToken);
+                    inToken = !sp;
+                }
+                first_[c + 1] = count;
+            }
+        }, 1);
+        for (size_t c = 0; c < n; ++c) first_[c + 1] += first_[c];
+    }
+    uint64_t total() const { return first_.back(); }
+    // fn(globalIndex, pointer to the token) for every token with index in [t0, t1), on all cores
+    template <class Fn>
+    void forRange(uint64_t t0, uint64_t t1, Fn fn) const {
+        const size_t n = starts_.size() - 1;
+        parallelRanges(n, [&](int th, size_t a, size_t b) {
+            for (size_t c = a; c < b; ++c) {
+                if (first_[c + 1] <= t0 || first_[c] >= t1) continue;
+                uint64_t g = first_[c];
+                bool inToken = false;
+                for (const uint8_t *p = starts_[c]; p < starts_[c + 1] && g < t1; ++p) {
+                    const bool sp = isSpace(*p);
+                    if (!sp && !inToken) {
+                        if (g >= t0) fn(th, g, p);
+                        ++g;
+                    }
+                    inToken = !sp;
+                }
+            }
+        }, 1);
+    }
+    // where token `t` starts (the end of the data for t == total())
+    const uint8_t *position(uint64_t t) const {
+        if (t >= total()) return starts_.back();
+        size_t c = 0;
+        while (first_[c + 1] <= t) ++c;
+        uint64_t g = first_[c];
+        bool inToken = false;
+        for (const uint8_t *p = starts_[c]; p < starts_[c + 1]; ++p) {
+            const bool sp = isSpace(*p);
+            if (!sp && !inToken) {
+                if (g == t) return p;
+                ++g;
+            }
+            inToken = !sp;
+        }
+        return starts_.back();
+    }
+
+private:
+    std::vector<const uint8_t *> starts_;
+    std::vector<uint64_t> first_;
 };
 
 } // namespace
@@ -244,18 +369,30 @@ bool readPlyMesh(const char *path, Mesh &out, std::string &err, int &status) {
     out.hasNormals = false;
     size_t nIndices = 0;
     const char *const noMemory = "out of host memory for the mesh";
+    // ASCII: the token index of the current element's first token, for as long as every element so far had a fixed
+    // number of tokens per record (see AsciiTokens)
+    std::unique_ptr<AsciiTokens> tokens;
+    uint64_t tokenCursor = 0;
+    bool tokenCursorValid = format == 0;
+    if (format == 0) tokens.reset(new AsciiTokens(data.begin(), dataEnd));
+    auto parseToken = [](const uint8_t *p, double &v) {       // one whole token, like Reader::scalar would take it
+        if (fastDecimal(p, v)) return true;
+        char *stop = nullptr;
+        v = strtod(reinterpret_cast<const char *>(p), &stop);
+        return stop != reinterpret_cast<const char *>(p) && (*stop == 0 || isSpace(uint8_t(*stop)));
+    };
 
     for (const Element &e : elements) {
         if (e.name == "vertex") {
             std::vector<int> slot(e.props.size(), -1);
             bool avail[9] = {false};
-            bool fixedSize = format != 0;
+            bool fixedSize = format != 0, hasList = false;
             size_t stride = 0;
             std::vector<size_t> offsets(e.props.size(), 0);
             for (size_t p = 0; p < e.props.size(); ++p) {
                 for (int t = 0; t < 9; ++t)
                     if (!e.props[p].isList && e.props[p].name == vpNames[t]) { slot[p] = t; avail[t] = true; break; }
-                if (e.props[p].isList) fixedSize = false;
+                if (e.props[p].isList) { fixedSize = false; hasList = true; }
                 offsets[p] = stride;
                 stride += size_t(kSize[e.props[p].type]);
             }
@@ -289,7 +426,37 @@ bool readPlyMesh(const char *path, Mesh &out, std::string &err, int &status) {
                 for (int th = 0; th < 16; ++th)
                     for (int t = 0; t < 3; ++t) { lo[t] = minStd(lo[t], los[size_t(th)*3 + t]); hi[t] = maxStd(hi[t], his[size_t(th)*3 + t]); }
                 in = Reader(base + stride*size_t(e.count), dataEnd, format);
+            } else if (tokenCursorValid && !hasList && tokens->total() >= tokenCursor + uint64_t(e.count)*e.props.size()) {
+                // ASCII, scalar properties only: token g of the element is property g % n of vertex g / n
+                const uint64_t np = e.props.size(), t0 = tokenCursor, t1 = t0 + uint64_t(e.count)*np;
+                parallelRanges(verts.size(), [&](int, size_t begin, size_t end) {
+                    for (size_t i = begin; i < end; ++i) memcpy(&verts[i], vertDefault, sizeof vertDefault);
+                });
+                static_assert(sizeof(MeshVertex) == 9*sizeof(float), "MeshVertex is nine packed floats");
+                std::vector<char> badNumber(16, 0);
+                tokens->forRange(t0, t1, [&](int th, uint64_t g, const uint8_t *p) {
+                    const uint64_t rel = g - t0;
+                    const int sl = slot[size_t(rel % np)];
+                    if (sl < 0) return;
+                    double v;
+                    if (!parseToken(p, v)) { badNumber[size_t(th)] = 1; return; }
+                    reinterpret_cast<float *>(&verts[size_t(rel/np)])[sl] = float(v);
+                });
+                for (char b : badNumber) if (b) { err = std::string(path) + ": short read in the vertex data"; status = 3; return false; }
+                std::vector<float> los(16*3, 1e30f), his(16*3, -1e30f);
+                parallelRanges(verts.size(), [&](int th, size_t begin, size_t end) {
+                    float tlo[3] = {1e30f, 1e30f, 1e30f}, thi[3] = {-1e30f, -1e30f, -1e30f};
+                    for (size_t i = begin; i < end; ++i)
+                        for (int t = 0; t < 3; ++t) { tlo[t] = minStd(tlo[t], verts[i].pos[t]); thi[t] = maxStd(thi[t], verts[i].pos[t]); }
+                    memcpy(&los[size_t(th)*3], tlo, 12);
+                    memcpy(&his[size_t(th)*3], thi, 12);
+                });
+                for (int th = 0; th < 16; ++th)
+                    for (int t = 0; t < 3; ++t) { lo[t] = minStd(lo[t], los[size_t(th)*3 + t]); hi[t] = maxStd(hi[t], his[size_t(th)*3 + t]); }
+                tokenCursor = t1;
+                in = Reader(tokens->position(tokenCursor), dataEnd, format);
             } else {
+                tokenCursorValid = false;
                 for (long long i = 0; i < e.count; ++i) {
                     float v9[9];
                     memcpy(v9, vertDefault, sizeof v9);
@@ -356,7 +523,40 @@ bool readPlyMesh(const char *path, Mesh &out, std::string &err, int &status) {
                     }
                 }
             }
+            // The same idea for ASCII files: if every face is a triangle, token g of the element is field g % 4 of face
+            // g / 4 -- true by induction as soon as every token at a multiple of 4 reads 3.
+            if (!fastDone && tokenCursorValid && listProp && e.props.size() == 1 && e.count > 0 &&
+                tokens->total() >= tokenCursor + 4*uint64_t(e.count)) {
+                const uint64_t t0 = tokenCursor, t1 = t0 + 4*uint64_t(e.count);
+                if (!out.indices.resize(nIndices + 3*size_t(e.count))) { err = noMemory; status = 4; return false; }
+                uint32_t *dst = out.indices.data() + nIndices;
+                std::vector<char> notTriangles(16, 0);
+                tokens->forRange(t0, t1, [&](int th, uint64_t g, const uint8_t *p) {
+                    const uint64_t rel = g - t0;
+                    double v;
+                    if (!parseToken(p, v)) { notTriangles[size_t(th)] = 1; return; }     // let the general path report it
+                    if ((rel & 3) == 0) {
+                        if (v != 3.0) notTriangles[size_t(th)] = 1;
+                        return;
+                    }
+                    const long long idx = (long long)v;
+                    if (idx < 0 || size_t(idx) >= nVerts) { bad[size_t(th)] = 1; return; }
+                    dst[3*size_t(rel >> 2) + size_t(rel & 3) - 1] = uint32_t(idx);
+                });
+                bool allTriangles = true;
+                for (char c : notTriangles) allTriangles &= !c;
+                if (allTriangles) {
+                    nIndices += 3*size_t(e.count);
+                    tokenCursor = t1;
+                    in = Reader(tokens->position(tokenCursor), dataEnd, format);
+                    fastDone = true;
+                } else {
+                    out.indices.resize(nIndices);
+                    std::fill(bad.begin(), bad.end(), 0);
+                }
+            }
             if (!fastDone) {
+                tokenCursorValid = false;
                 // pass 1 (sequential, cheap): where every face's index list starts, how long it is, and where
                 // its triangles go (a polygon of k vertices is a fan of k - 2 triangles, :207-221)
                 struct FaceRef { const uint8_t *indices; uint32_t count; uint64_t firstTriangle; };
@@ -409,6 +609,14 @@ bool readPlyMesh(const char *path, Mesh &out, std::string &err, int &status) {
             }
             for (char b : bad) if (b) { err = "PLY face refers to a vertex that does not exist"; status = 3; return false; }
         } else {
+            bool scalarOnly = true;
+            for (const Property &pr : e.props) scalarOnly &= !pr.isList;
+            if (tokenCursorValid && scalarOnly && e.count >= 0 && tokens->total() >= tokenCursor + uint64_t(e.count)*e.props.size()) {
+                tokenCursor += uint64_t(e.count)*e.props.size();
+                in = Reader(tokens->position(tokenCursor), dataEnd, format);
+                continue;
+            }
+            tokenCursorValid = false;
             for (long long i = 0; i < e.count && in.ok; ++i)
                 for (const Property &pr : e.props) in.skip(pr);
             if (!in.ok) { err = std::string(path) + ": short read in element " + e.name; status = 3; return false; }

@@ -262,7 +262,33 @@ def test_ply_reader_matches_oracle(pysvo, port, tmp_path):
         fp.write(v.tobytes())
         for f in faces:
             fp.write(struct.pack("<B%di" % len(f), len(f), *f))
-    for name, p in [("ico5", ico), ("ico100", big), ("mixed_counts", mixed)] + write_variants(tmp_path):
+    # the 200,000-triangle mesh as ASCII: vertices and faces go through the token-indexed parallel paths (every face a
+    # triangle), with an ignored vertex property in the middle and a scalar-only element behind the faces
+    raw_big = big.read_bytes()
+    h = raw_big.index(b"end_header\n") + 11
+    header = raw_big[:h].decode()
+    nv, nf = int(header.split("element vertex ")[1].split()[0]), int(header.split("element face ")[1].split()[0])
+    bv = np.frombuffer(raw_big[h:h + nv * 12], np.float32).reshape(nv, 3)
+    bf = np.frombuffer(raw_big[h + nv * 12:], np.uint8).reshape(nf, 13)[:, 1:].copy().view(np.int32).reshape(nf, 3)
+    ascii_big = tmp_path / "ico100_ascii.ply"
+    with open(ascii_big, "w") as fp:
+        fp.write("ply\nformat ascii 1.0\nelement vertex %d\nproperty float x\nproperty float quality\nproperty float y\n"
+                 "property float z\nelement face %d\nproperty list uchar int vertex_indices\nelement edge 2\nproperty int a\n"
+                 "property int b\nend_header\n" % (nv, nf))
+        np.savetxt(fp, np.column_stack([bv[:, 0], np.full(nv, 0.25), bv[:, 1], bv[:, 2]]), fmt="%.9g")
+        np.savetxt(fp, np.hstack([np.full((nf, 1), 3), bf]), fmt="%d")
+        fp.write("0 1\n1 2\n")
+    a, lo, hi = pysvo.ply_read_triangles(ascii_big)
+    b, _, _ = pysvo.ply_read_triangles(big)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))            # same mesh as the binary file, bit for bit
+    # ... and with one quad among the triangles: the token-indexed face path has to notice and fall back
+    ascii_quad = tmp_path / "ico100_ascii_quad.ply"
+    lines = ascii_big.read_text().split("\n")
+    first_face = lines.index("end_header") + 1 + nv
+    lines[first_face + 1000] = "4 0 1 2 3"
+    ascii_quad.write_text("\n".join(lines))
+    for name, p in [("ico5", ico), ("ico100", big), ("mixed_counts", mixed), ("ico100_ascii", ascii_big),
+                    ("ico100_ascii_quad", ascii_quad)] + write_variants(tmp_path):
         a, lo, hi = pysvo.ply_read_triangles(p)
         b, lo2, hi2 = port.ply_triangles(p)
         assert a.shape == b.shape and a.shape[0] > 100, name
@@ -276,7 +302,10 @@ def test_ply_reader_matches_oracle(pysvo, port, tmp_path):
     bigraw = bytearray(big.read_bytes())
     bigraw[-4:] = struct.pack("<i", 10**8)          # the last face's last index points past the vertices
     for name, blob in [("notply.ply", b"plx\n" + raw[4:]), ("short.ply", raw[:len(raw) // 2]),
-                       ("nofaces.ply", raw.replace(b"element face", b"element fac_")), ("badindex.ply", bytes(bigraw))]:
+                       ("nofaces.ply", raw.replace(b"element face", b"element fac_")), ("badindex.ply", bytes(bigraw)),
+                       ("ascii_junk.ply", ascii_big.read_bytes().replace(b"\n3 ", b"\n3 x", 1)),
+                       ("ascii_short.ply", ascii_big.read_bytes()[:-60000]),
+                       ("ascii_badindex.ply", ascii_big.read_bytes().replace(b"\n0 1\n1 2\n", b"").rsplit(b" ", 1)[0] + b" 99999999\n0 1\n1 2\n")]:
         q = tmp_path / name
         q.write_bytes(blob)
         with pytest.raises(pysvo.SvoError) as e:
