@@ -3,7 +3,10 @@
 // the GPU with the reference's strip/tile/beam semantics and writes PPM images.
 //
 //   svo_headless <in.oct> [--size WxH] [--strips N] [--frames K] [--radius R] [--pitch P]
-//                [--yaw0 Y] [--yaw-step S] [--validation] [--preview] [--out prefix] [--raw file|-]
+//                [--yaw0 Y] [--yaw-step S] [--validation] [--preview] [--events script]
+//                [--out prefix] [--png prefix] [--raw file|-]
+//
+// --out writes prefix_<k>.ppm, --png prefix_<k>.png (8-bit RGB, host/png_write.hpp) for every frame.
 //
 // --raw streams every frame as packed RGB24 (row-major, no header) to a file or to stdout ("-"), the
 // input format of `ffmpeg -f rawvideo -pix_fmt rgb24 -s WxH -i -`: the streamed stand-in for the
@@ -28,6 +31,7 @@
 #include <vector>
 
 #include "VoxelOctree.hpp"
+#include "png_write.hpp"
 
 static void writePpm(const std::string &path, const uint32_t *rgba, int w, int h) {
     FILE *fp = fopen(path.c_str(), "wb");
@@ -73,7 +77,7 @@ static std::vector<svo_viewer_event> readEventScript(const std::string &path) {
 int main(int argc, char **argv) {
     if (argc < 2) {
         fprintf(stderr, "usage: %s <in.oct> [--size WxH] [--strips N] [--frames K] [--radius R] [--pitch P] [--yaw0 Y] "
-                        "[--yaw-step S] [--validation] [--preview] [--events script] [--out prefix] [--raw file|-]\n"
+                        "[--yaw-step S] [--validation] [--preview] [--events script] [--out prefix] [--png prefix] [--raw file|-]\n"
                         "       %s -builder [--resolution r --mode m] <in.ply | in.voxel> <out.oct>\n", argv[0], argv[0]);
         return 2;
     }
@@ -107,7 +111,7 @@ int main(int argc, char **argv) {
     int w = 1280, h = 720, strips = 16, frames = 1, flavour = SVO_FLAVOUR_FAST; /* Main.cpp:57-60 defaults */
     float radius = 1.0f, pitch = 0.0f, yaw0 = 0.0f, yawStep = 3.6f;
     int stride = 1;
-    std::string out, raw, events;
+    std::string out, raw, events, png;
     for (int i = 2; i < argc; ++i) {
         std::string a = argv[i];
         auto next = [&]() -> const char * { return i + 1 < argc ? argv[++i] : ""; };
@@ -122,6 +126,7 @@ int main(int argc, char **argv) {
         else if (a == "--preview") stride = 3;   /* the reference's renderHalfSize while dragging, Main.cpp:161 */
         else if (a == "--out") out = next();
         else if (a == "--raw") raw = next();
+        else if (a == "--png") png = next();
         else if (a == "--events") events = next();
         else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
@@ -160,6 +165,8 @@ int main(int argc, char **argv) {
             double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
             if (k > 0 || frames == 1) { totalMs += ms; rays += st.coarse_rays + st.fine_rays; }
             if (!out.empty()) writePpm(out + "_" + std::to_string(k) + ".ppm", rgba, w, h);
+            if (!png.empty() && !svo_png::writeRgb(png + "_" + std::to_string(k) + ".png", rgba, w, h))
+                throw std::runtime_error("cannot write " + png + "_" + std::to_string(k) + ".png");
             if (rawFile) {
                 for (size_t p = 0; p < size_t(w)*h; ++p) {
                     rgb[3*p] = rgba[p] & 255; rgb[3*p + 1] = (rgba[p] >> 8) & 255; rgb[3*p + 2] = (rgba[p] >> 16) & 255;

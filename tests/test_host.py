@@ -425,3 +425,36 @@ def test_readers_survive_mutated_files(pysvo, tmp_path):
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, (out.returncode, out.stderr[-2000:])
     assert "fuzz done" in out.stdout and "'ply rejected': 0" not in out.stdout and "'oct rejected': 0" not in out.stdout
+
+
+def test_headless_png_writer(tmp_path):
+    """host/png_write.hpp (svo_headless --png): signature, chunk CRCs, IHDR, and the pixels after inflating the IDAT
+    stream, for a ragged and a larger-than-one-deflate-block frame."""
+    import struct
+    import subprocess
+    import zlib
+    from conftest import ROOT
+    exe = tmp_path / "png_test"
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-I", str(ROOT / "sparse-voxel-octrees_b200" / "host"),
+                           str(ROOT / "tests" / "cpp" / "png_test.cpp"), "-o", str(exe)])
+    for w, h in ((333, 187), (5, 3), (640, 360)):
+        path = tmp_path / f"f_{w}x{h}.png"
+        subprocess.check_call([str(exe), str(path), str(w), str(h)])
+        b = path.read_bytes()
+        assert b[:8] == b"\x89PNG\r\n\x1a\n"
+        pos, chunks = 8, []
+        while pos < len(b):
+            n, = struct.unpack(">I", b[pos:pos + 4])
+            kind, data = b[pos + 4:pos + 8], b[pos + 8:pos + 8 + n]
+            assert zlib.crc32(kind + data) == struct.unpack(">I", b[pos + 8 + n:pos + 12 + n])[0], kind
+            chunks.append((kind, data))
+            pos += 12 + n
+        assert [k for k, _ in chunks] == [b"IHDR", b"IDAT", b"IEND"]
+        assert struct.unpack(">IIBBBBB", chunks[0][1]) == (w, h, 8, 2, 0, 0, 0)
+        rows = np.frombuffer(zlib.decompress(chunks[1][1]), np.uint8).reshape(h, 1 + 3 * w)
+        assert (rows[:, 0] == 0).all()
+        px = rows[:, 1:].reshape(h, w, 3)
+        y, x = np.mgrid[0:h, 0:w]
+        assert np.array_equal(px[..., 0], ((x * 7 + y * 3) & 255).astype(np.uint8))
+        assert np.array_equal(px[..., 1], ((x ^ y) & 255).astype(np.uint8))
+        assert np.array_equal(px[..., 2], ((x * y) & 255).astype(np.uint8))
