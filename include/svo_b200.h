@@ -114,6 +114,23 @@ typedef struct svo_tree_info {
 /* Adopts a node array (e.g. the one the reference's builder produced,
  * VoxelOctree.cpp:125-137) and uploads it unchanged to `device`'s HBM.
  * The words are copied; the caller keeps ownership of `words`. */
+/* Full check of a node array on the host (the reference has none: VoxelOctree.cpp:57-90 loads whatever the file holds
+ * and raymarch follows child pointers unchecked, :253-293 -- and so do the kernels here, which size their stack from
+ * the depth of the first-child chain). Walks every reachable descriptor: child blocks strictly behind their parent,
+ * every descriptor, far word and leaf word inside the array, no branch deeper than the first-child chain, no node
+ * reachable more often than the array has words. SVO_ERR_FORMAT + svo_last_error() name the first violation.
+ * svo_tree_create_from_words and svo_tree_load_oct run it when the environment variable SVO_VALIDATE_TREES is set
+ * (files from an untrusted source); it costs one pass over the array on one host thread. */
+typedef struct svo_words_report {
+    uint64_t descriptors;       /* reachable descriptors (Dragon: 29,156) */
+    uint64_t leaves;            /* reachable leaf words (Dragon: 90,707) */
+    uint64_t far_words;         /* descriptors that carry a far word (Dragon: 24) */
+    uint32_t min_leaf_depth, max_leaf_depth;    /* level of the leaves' parents, root = 1: equal in a builder-made tree */
+    uint32_t depth;             /* levels of the first-child chain: what the traversal sizes its stack from */
+    uint32_t reserved;
+} svo_words_report;
+SVO_API int svo_words_validate(const uint32_t *words, uint64_t n_words, svo_words_report *report);
+
 SVO_API int svo_tree_create_from_words(const uint32_t *words, uint64_t n_words, const float center[3],
                                        int device, svo_tree **out);
 /* VoxelOctree(const char *path), VoxelOctree.cpp:57-90. */

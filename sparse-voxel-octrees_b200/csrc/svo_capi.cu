@@ -245,6 +245,61 @@ int allocTree(uint64_t nWords, const float center[3], int device, std::unique_pt
     return SVO_OK;
 }
 
+// Full walk of a node array on the host: every descriptor, far word and leaf word a ray can be led to lies inside
+// the array, child blocks lie strictly behind their parent (no cycles), no node is reachable more often than the array
+// has words (not a tree), and no branch is deeper than `maxDepth` levels -- the traversal kernels size their stack
+// from the depth of the first-child chain (measureDepth) and read words[parent + offset] unchecked, exactly like the
+// reference (VoxelOctree.cpp:253-293), so a damaged array would otherwise mean an illegal address on the device.
+// Child addressing as in SURVEY.md App. A.1: child bit b of descriptor p sits at p + offset + rank*(1 + far16) with
+// rank = popcount(non-leaf mask below b) when it is a node, at p + offset + popcount(valid mask below b) when it is a
+// leaf word.
+int validateWords(const uint32_t *words, uint64_t n, uint32_t maxDepth, svo_words_report *report) {
+    struct Item { uint64_t p; uint32_t depth; };
+    std::vector<Item> stack;
+    stack.push_back({0, 1});
+    svo_words_report r = {};
+    r.min_leaf_depth = ~0u;
+    while (!stack.empty()) {
+        const Item it = stack.back();
+        stack.pop_back();
+        const uint64_t p = it.p;
+        if (p >= n) return fail(SVO_ERR_FORMAT, "node array: descriptor index %llu past the end (%llu words)", (unsigned long long)p, (unsigned long long)n);
+        if (++r.descriptors > n) return fail(SVO_ERR_FORMAT, "node array: not a tree (more reachable descriptors than words)");
+        if (it.depth > maxDepth) return fail(SVO_ERR_FORMAT, "node array: a branch at word %llu is deeper than %u levels", (unsigned long long)p, maxDepth);
+        const uint32_t d = words[p];
+        const uint32_t valid = (d >> 8) & 0xFFu, nonLeaf = d & 0xFFu;
+        if (valid == 0) continue;                                  // nothing below: rays step over it
+        uint64_t offset = d >> 18;
+        if (d & 0x20000u) {
+            if (p + 1 >= n) return fail(SVO_ERR_FORMAT, "node array: far word of descriptor %llu past the end", (unsigned long long)p);
+            offset = (offset << 32) | words[p + 1];
+            ++r.far_words;
+        }
+        if (offset == 0) return fail(SVO_ERR_FORMAT, "node array: zero child offset at %llu", (unsigned long long)p);
+        const uint64_t base = p + offset, stride = (d & 0x10000u) ? 2 : 1;
+        for (uint32_t b = 0; b < 8; ++b) {
+            if (!((valid >> b) & 1u)) continue;
+            const uint32_t below = (1u << b) - 1u;
+            if ((nonLeaf >> b) & 1u) {
+                stack.push_back({base + uint64_t(__builtin_popcount(nonLeaf & below))*stride, it.depth + 1});
+            } else {
+                const uint64_t leaf = base + uint64_t(__builtin_popcount(valid & below));
+                if (leaf >= n) return fail(SVO_ERR_FORMAT, "node array: leaf word %llu of descriptor %llu past the end", (unsigned long long)leaf, (unsigned long long)p);
+                ++r.leaves;
+                if (it.depth < r.min_leaf_depth) r.min_leaf_depth = it.depth;
+                if (it.depth > r.max_leaf_depth) r.max_leaf_depth = it.depth;
+            }
+        }
+    }
+    if (report) *report = r;
+    return SVO_OK;
+}
+
+bool validationRequested() {
+    const char *e = getenv("SVO_VALIDATE_TREES");
+    return e && *e && *e != '0';
+}
+
 int createTree(const uint32_t *words, uint64_t nWords, const float center[3], int device, svo_tree **out) {
     if (!words || !center || !out) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_tree_create: null argument");
     if (nWords < 2) return fail(SVO_ERR_FORMAT, "node array too small (%llu words)", (unsigned long long)nWords);
@@ -252,6 +307,7 @@ int createTree(const uint32_t *words, uint64_t nWords, const float center[3], in
     uint32_t depth = 0;
     int st = measureDepth(words, nWords, depth);
     if (st != SVO_OK) return st;
+    if (validationRequested() && (st = validateWords(words, nWords, depth, nullptr)) != SVO_OK) return st;
     std::unique_ptr<svo_tree> tree;
     if ((st = allocTree(nWords, center, device, tree)) != SVO_OK) return st;
     tree->depth = depth;
@@ -562,6 +618,17 @@ int svo_oct_write(const char *path, const uint32_t *words, uint64_t n_words, con
 
 /* ---- trees ----------------------------------------------------------------- */
 
+int svo_words_validate(const uint32_t *words, uint64_t n_words, svo_words_report *report) {
+    if (!words) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_words_validate: null argument");
+    if (n_words < 2) return fail(SVO_ERR_FORMAT, "node array too small (%llu words)", (unsigned long long)n_words);
+    uint32_t depth = 0;
+    int st = measureDepth(words, n_words, depth);
+    if (st != SVO_OK) return st;
+    if ((st = validateWords(words, n_words, depth, report)) != SVO_OK) return st;
+    if (report) report->depth = depth;
+    return SVO_OK;
+}
+
 int svo_tree_create_from_words(const uint32_t *words, uint64_t n_words, const float center[3], int device, svo_tree **out) {
     return createTree(words, n_words, center, device, out);
 }
@@ -594,6 +661,7 @@ int svo_tree_load_oct(const char *path, int device, svo_tree **out) {
     if (copyErr == cudaSuccess) copyErr = cudaStreamSynchronize(tree->copyStream);
     uint32_t depth = 0;
     if (ok && copyErr == cudaSuccess) st = measureDepth(words, reader.nWords, depth);
+    if (ok && copyErr == cudaSuccess && st == SVO_OK && validationRequested()) st = validateWords(words, reader.nWords, depth, nullptr);
     free(words);
     if (copyErr != cudaSuccess) {
         svo_tree_destroy(tree.release());

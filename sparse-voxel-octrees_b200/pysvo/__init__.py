@@ -79,6 +79,11 @@ class FrameConstants(C.Structure):
         return np.frombuffer(bytes(self), dtype=np.float32, offset=16).copy()
 
 
+class WordsReport(C.Structure):
+    _fields_ = [("descriptors", C.c_uint64), ("leaves", C.c_uint64), ("far_words", C.c_uint64),
+                ("min_leaf_depth", C.c_uint32), ("max_leaf_depth", C.c_uint32), ("depth", C.c_uint32), ("reserved", C.c_uint32)]
+
+
 class FrameDesc(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("strips", C.c_int32), ("flavour", C.c_int32),
                 ("tile_rank", C.c_int32), ("tile_world", C.c_int32), ("pixel_stride", C.c_int32), ("reserved", C.c_int32)]
@@ -144,6 +149,7 @@ def lib():
         "svo_last_error": (C.c_char_p, []),
         "svo_device_count": (i32, [P(i32)]),
         "svo_free": (None, [vp]),
+        "svo_words_validate": (i32, [vp, u64, P(WordsReport)]),
         "svo_host_alloc": (i32, [C.c_size_t, P(vp)]),
         "svo_host_register": (i32, [i32, vp, C.c_size_t, P(vp)]),
         "svo_host_unregister": (i32, [vp]),
@@ -368,6 +374,14 @@ def ipc_close(device, ptr: int):
 def device_to_host_async(device, host_array, device_ptr, nbytes, stream=0):
     _check(lib().svo_device_to_host_async(int(device), _ptr(host_array), C.c_void_p(device_ptr), int(nbytes),
                                           C.c_void_p(stream or None)))
+
+
+def words_validate(words) -> WordsReport:
+    """Full host-side check of a node array (svo_words_validate); raises SvoError(status 3) naming the first violation."""
+    words = np.ascontiguousarray(words, np.uint32)
+    rep = WordsReport()
+    _check(lib().svo_words_validate(_ptr(words), words.size, C.byref(rep)))
+    return rep
 
 
 def frame_set_tile_run(run):

@@ -458,3 +458,85 @@ def test_headless_png_writer(tmp_path):
         assert np.array_equal(px[..., 0], ((x * 7 + y * 3) & 255).astype(np.uint8))
         assert np.array_equal(px[..., 1], ((x ^ y) & 255).astype(np.uint8))
         assert np.array_equal(px[..., 2], ((x * y) & 255).astype(np.uint8))
+
+
+def test_words_validate(pysvo, dragon_words, monkeypatch):
+    """svo_words_validate: the full host-side walk of a node array. The sample tree gives the survey's counts and
+    accounts for every word; damaged arrays are rejected with the first violation named (and never crash the walk);
+    with SVO_VALIDATE_TREES set the tree constructors run it before anything is uploaded."""
+    words, center = dragon_words
+    rep = pysvo.words_validate(words)
+    assert (rep.descriptors, rep.leaves, rep.far_words, rep.depth) == (29156, 90707, 24, 8)
+    assert rep.min_leaf_depth == rep.max_leaf_depth == 8
+    assert rep.descriptors + rep.leaves + rep.far_words == words.size          # depth-first by block: no unused word
+
+    def rejected(w, needle):
+        with pytest.raises(pysvo.SvoError) as e:
+            pysvo.words_validate(w)
+        assert e.value.status == 3 and needle in str(e.value), str(e.value)
+
+    # a descriptor deep in the tree whose children are leaves, found by walking first children from the root
+    p, chain = 0, []
+    while words[p] & 0xFF:
+        chain.append(p)
+        off = int(words[p]) >> 18
+        if words[p] & 0x20000:
+            off = (off << 32) | int(words[p + 1])
+        p += off
+    chain.append(p)
+    leaf_parent, inner = chain[-1], chain[-3]
+    w = words.copy(); w[inner] = (w[inner] & 0x3FFFF) | (0x3FFF << 18)          # child block far behind the array's end?
+    w[inner] &= ~np.uint32(0x20000)
+    if inner + 0x3FFF < words.size:                                             # (the Dragon is big enough: make it a far pointer instead)
+        w[inner] |= np.uint32(0x20000); w[inner + 1] = np.uint32(words.size + 5)
+    rejected(w, "past the end")
+    w = words.copy(); w[inner] &= np.uint32(0x3FFFF)                            # zero offset: a node that is its own child
+    rejected(w, "zero child offset")
+    # a leaf parent OFF the first-child chain (the chain is what the depth is measured along): second child of the
+    # lowest ancestor that has two, then first children down to the leaves' parent
+    def child_block(q):
+        off = int(words[q]) >> 18
+        if words[q] & 0x20000:
+            off = (off << 32) | int(words[q + 1])
+        return q + off, (2 if words[q] & 0x10000 else 1)
+    other = None
+    for anc in reversed(chain[:-1]):
+        if bin(int(words[anc]) & 0xFF).count("1") >= 2:
+            base, stride = child_block(anc)
+            other = base + stride
+            break
+    assert other is not None
+    while words[other] & 0xFF:
+        other = child_block(other)[0]
+    w = words.copy(); w[other] |= np.uint32((int(w[other]) >> 8) & 0xFF)        # its leaves turned into nodes: one level too deep
+    rejected(w, "deeper than 8 levels")
+    w = words.copy(); w[0] = (w[0] & ~np.uint32(0xFF00)) | np.uint32(0)         # root without children
+    rejected(w, "no children")
+    rng = np.random.default_rng(9)
+    outcomes = {True: 0, False: 0}
+    for _ in range(300):
+        w = words.copy()
+        for _ in range(int(rng.integers(1, 6))):
+            w[int(rng.integers(0, w.size))] = np.uint32(rng.integers(0, 2**32))
+        try:
+            pysvo.words_validate(w)
+            outcomes[True] += 1
+        except pysvo.SvoError as e:
+            assert e.status == 3
+            outcomes[False] += 1
+    assert outcomes[True] > 0 and outcomes[False] > 0                           # damaged leaf words pass, damaged descriptors mostly do not
+    if pysvo.device_count() < 1:
+        # the constructors: validation (when asked for) comes before the device is needed. The damage is off the
+        # first-child chain, so nothing but the full walk can see it.
+        bad = words.copy(); bad[other] |= np.uint32((int(bad[other]) >> 8) & 0xFF)
+        monkeypatch.setenv("SVO_VALIDATE_TREES", "1")
+        with pytest.raises(pysvo.SvoError) as e:
+            pysvo.VoxelOctree(words=bad, center=center)
+        assert e.value.status == 3
+        with pytest.raises(pysvo.SvoError) as e:
+            pysvo.VoxelOctree(words=words, center=center)
+        assert e.value.status == 6
+        monkeypatch.delenv("SVO_VALIDATE_TREES")
+        with pytest.raises(pysvo.SvoError) as e:
+            pysvo.VoxelOctree(words=bad, center=center)
+        assert e.value.status == 6
