@@ -120,7 +120,7 @@ typedef struct svo_tree_info {
  * every descriptor, far word and leaf word inside the array, no branch deeper than the first-child chain, no node
  * reachable more often than the array has words. SVO_ERR_FORMAT + svo_last_error() name the first violation.
  * svo_tree_create_from_words and svo_tree_load_oct run it when the environment variable SVO_VALIDATE_TREES is set
- * (files from an untrusted source); it costs one pass over the array on one host thread. */
+ * (files from an untrusted source); subtrees are walked on all host cores (the 1.6 GB array of an 8192^3 tree: 1.9 s on 8). */
 typedef struct svo_words_report {
     uint64_t descriptors;       /* reachable descriptors (Dragon: 29,156) */
     uint64_t leaves;            /* reachable leaf words (Dragon: 90,707) */

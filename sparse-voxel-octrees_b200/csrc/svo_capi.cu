@@ -13,6 +13,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <atomic>
 #include <tuple>
 #include <vector>
 
@@ -253,29 +254,41 @@ int allocTree(uint64_t nWords, const float center[3], int device, std::unique_pt
 // Child addressing as in SURVEY.md App. A.1: child bit b of descriptor p sits at p + offset + rank*(1 + far16) with
 // rank = popcount(non-leaf mask below b) when it is a node, at p + offset + popcount(valid mask below b) when it is a
 // leaf word.
-int validateWords(const uint32_t *words, uint64_t n, uint32_t maxDepth, svo_words_report *report) {
-    struct Item { uint64_t p; uint32_t depth; };
-    std::vector<Item> stack;
-    stack.push_back({0, 1});
-    svo_words_report r = {};
-    r.min_leaf_depth = ~0u;
-    while (!stack.empty()) {
-        const Item it = stack.back();
-        stack.pop_back();
+struct WalkItem { uint64_t p; uint32_t depth; };
+
+// One depth-first walk from `stack`'s items; stops expanding once `splitAt` items are pending (the caller hands them
+// to threads) when splitAt != 0. Violations go to `err` (first one wins); `visited` is shared by all walkers.
+bool walkWords(const uint32_t *words, uint64_t n, uint32_t maxDepth, std::vector<WalkItem> &stack, size_t splitAt,
+               std::atomic<uint64_t> &visited, svo_words_report &r, std::string &err) {
+    char msg[160];
+    auto bad = [&](const char *fmt, unsigned long long a, unsigned long long b) {
+        snprintf(msg, sizeof msg, fmt, a, b);
+        err = msg;
+        return false;
+    };
+    uint64_t local = 0;
+    size_t head = 0;            // splitAt != 0: breadth first (FIFO), so that the pending items are subtrees of similar size
+    while (head < stack.size() && (splitAt == 0 || stack.size() - head < splitAt)) {
+        WalkItem it;
+        if (splitAt) { it = stack[head++]; } else { it = stack.back(); stack.pop_back(); }
         const uint64_t p = it.p;
-        if (p >= n) return fail(SVO_ERR_FORMAT, "node array: descriptor index %llu past the end (%llu words)", (unsigned long long)p, (unsigned long long)n);
-        if (++r.descriptors > n) return fail(SVO_ERR_FORMAT, "node array: not a tree (more reachable descriptors than words)");
-        if (it.depth > maxDepth) return fail(SVO_ERR_FORMAT, "node array: a branch at word %llu is deeper than %u levels", (unsigned long long)p, maxDepth);
+        if (p >= n) return bad("node array: descriptor index %llu past the end (%llu words)", p, n);
+        ++r.descriptors;
+        if (++local == 4096) {
+            if (visited.fetch_add(local, std::memory_order_relaxed) + local > n) return bad("node array: not a tree (more reachable descriptors than its %llu words)%.0llu", n, 0);
+            local = 0;
+        }
+        if (it.depth > maxDepth) return bad("node array: a branch at word %llu is deeper than %llu levels", p, maxDepth);
         const uint32_t d = words[p];
         const uint32_t valid = (d >> 8) & 0xFFu, nonLeaf = d & 0xFFu;
         if (valid == 0) continue;                                  // nothing below: rays step over it
         uint64_t offset = d >> 18;
         if (d & 0x20000u) {
-            if (p + 1 >= n) return fail(SVO_ERR_FORMAT, "node array: far word of descriptor %llu past the end", (unsigned long long)p);
+            if (p + 1 >= n) return bad("node array: far word of descriptor %llu past the end (%llu words)", p, n);
             offset = (offset << 32) | words[p + 1];
             ++r.far_words;
         }
-        if (offset == 0) return fail(SVO_ERR_FORMAT, "node array: zero child offset at %llu", (unsigned long long)p);
+        if (offset == 0) return bad("node array: zero child offset at %llu%.0llu", p, 0);
         const uint64_t base = p + offset, stride = (d & 0x10000u) ? 2 : 1;
         for (uint32_t b = 0; b < 8; ++b) {
             if (!((valid >> b) & 1u)) continue;
@@ -284,14 +297,58 @@ int validateWords(const uint32_t *words, uint64_t n, uint32_t maxDepth, svo_word
                 stack.push_back({base + uint64_t(__builtin_popcount(nonLeaf & below))*stride, it.depth + 1});
             } else {
                 const uint64_t leaf = base + uint64_t(__builtin_popcount(valid & below));
-                if (leaf >= n) return fail(SVO_ERR_FORMAT, "node array: leaf word %llu of descriptor %llu past the end", (unsigned long long)leaf, (unsigned long long)p);
+                if (leaf >= n) return bad("node array: leaf word %llu of descriptor %llu past the end", leaf, p);
                 ++r.leaves;
                 if (it.depth < r.min_leaf_depth) r.min_leaf_depth = it.depth;
                 if (it.depth > r.max_leaf_depth) r.max_leaf_depth = it.depth;
             }
         }
     }
-    if (report) *report = r;
+    if (head) stack.erase(stack.begin(), stack.begin() + long(head));
+    if (visited.fetch_add(local, std::memory_order_relaxed) + local > n) return bad("node array: not a tree (more reachable descriptors than its %llu words)%.0llu", n, 0);
+    return true;
+}
+
+int validateWords(const uint32_t *words, uint64_t n, uint32_t maxDepth, svo_words_report *report) {
+    std::atomic<uint64_t> visited(0);
+    svo_words_report total = {};
+    total.min_leaf_depth = ~0u;
+    std::string err;
+    // the top of the tree on this thread until there is enough pending work to share, then subtrees on all cores
+    int threads = int(std::thread::hardware_concurrency());
+    threads = threads < 1 ? 1 : threads > 16 ? 16 : threads;
+    if (n < (uint64_t(1) << 20)) threads = 1;
+    std::vector<WalkItem> top;
+    top.push_back({0, 1});
+    if (!walkWords(words, n, maxDepth, top, threads > 1 ? size_t(threads)*64 : 0, visited, total, err)) return fail(SVO_ERR_FORMAT, "%s", err.c_str());
+    if (!top.empty()) {
+        std::vector<svo_words_report> parts((size_t(threads)), svo_words_report{});
+        const size_t nThreads = size_t(threads);
+        std::vector<std::string> errs(nThreads);
+        std::atomic<size_t> next(0);
+        std::vector<std::thread> pool;
+        auto work = [&](int t) {
+            parts[size_t(t)].min_leaf_depth = ~0u;
+            for (;;) {
+                const size_t k = next.fetch_add(1);
+                if (k >= top.size() || !errs[size_t(t)].empty()) return;
+                std::vector<WalkItem> mine(1, top[k]);
+                if (!walkWords(words, n, maxDepth, mine, 0, visited, parts[size_t(t)], errs[size_t(t)])) return;
+            }
+        };
+        for (int t = 1; t < threads; ++t) pool.emplace_back(work, t);
+        work(0);
+        for (auto &th : pool) th.join();
+        for (int t = 0; t < threads; ++t) {
+            if (!errs[size_t(t)].empty()) return fail(SVO_ERR_FORMAT, "%s", errs[size_t(t)].c_str());
+            total.descriptors += parts[size_t(t)].descriptors;
+            total.leaves += parts[size_t(t)].leaves;
+            total.far_words += parts[size_t(t)].far_words;
+            if (parts[size_t(t)].min_leaf_depth < total.min_leaf_depth) total.min_leaf_depth = parts[size_t(t)].min_leaf_depth;
+            if (parts[size_t(t)].max_leaf_depth > total.max_leaf_depth) total.max_leaf_depth = parts[size_t(t)].max_leaf_depth;
+        }
+    }
+    if (report) *report = total;
     return SVO_OK;
 }
 
