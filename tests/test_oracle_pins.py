@@ -217,6 +217,32 @@ def _ico_ply(path, freq):
     return path
 
 
+def voxelise_cases(directory):
+    """(name, ply path, resolution) of the meshes the f3 pins are minted on (tests/golden/make_voxelise_golden.py)."""
+    from ply_meshes import write_variants
+    cases = [("ico6", _ico_ply(directory / "ico6.ply", 6), 64), ("ico20", _ico_ply(directory / "ico20.ply", 20), 128)]
+    cases += [(name, p, res) for name, p in write_variants(directory) if not name.startswith("be_") for res in (48, 128)]
+    return cases
+
+
+def test_voxeliser_port_equals_golden(port, tmp_path):
+    """The same pin without a reference build: the node arrays the reference produced for these meshes when the vectors
+    were minted (tests/golden/voxelise_pins.json, with the thread-pool size of that run), against the restatement run
+    with that pool size."""
+    import hashlib
+    pins = json.loads((GOLDEN / "voxelise_pins.json").read_text())
+    by_key = {(c["name"], c["resolution"]): c for c in pins["cases"]}
+    assert len(by_key) >= 6
+    for name, ply, res in voxelise_cases(tmp_path):
+        pin = by_key[(name, res)]
+        assert hashlib.sha256(ply.read_bytes()).hexdigest() == pin["ply_sha256"], name       # same mesh file as minted
+        vol, _ = port.voxelize_ply(ply, res, pins["pool_threads"])
+        words, center = port.build_octree(vol)
+        assert words.size == pin["words"], (name, res)
+        assert hashlib.sha256(np.ascontiguousarray(words).tobytes()).hexdigest() == pin["sha256"], (name, res)
+        assert np.array_equal(center, np.array(pin["center"], np.float32)), (name, res)
+
+
 def test_voxeliser_port_equals_reference(port, ref, tmp_path):
     """PlyLoader + VoxelData(loader, res, mem) + VoxelOctree (reference src/Main.cpp:320-325): the volume the
     restatement voxelises must hold exactly the voxels of the tree the reference builds from the same PLY (same
