@@ -4,8 +4,10 @@
 //
 //   svo_headless <in.oct> [--size WxH] [--strips N] [--frames K] [--radius R] [--pitch P]
 //                [--yaw0 Y] [--yaw-step S] [--validation] [--preview] [--events script]
-//                [--out prefix] [--png prefix] [--raw file|-]
+//                [--out prefix] [--png prefix] [--raw file|-] [--check]
 //
+// --check decodes the file and walks its whole node array on the host (svo_words_validate: every pointer in bounds, no
+// cycles, no branch deeper than the kernels' stack), prints the counts and exits; no GPU is needed.
 // --out writes prefix_<k>.ppm, --png prefix_<k>.png (8-bit RGB, host/png_write.hpp) for every frame.
 //
 // --raw streams every frame as packed RGB24 (row-major, no header) to a file or to stdout ("-"), the
@@ -77,7 +79,7 @@ static std::vector<svo_viewer_event> readEventScript(const std::string &path) {
 int main(int argc, char **argv) {
     if (argc < 2) {
         fprintf(stderr, "usage: %s <in.oct> [--size WxH] [--strips N] [--frames K] [--radius R] [--pitch P] [--yaw0 Y] "
-                        "[--yaw-step S] [--validation] [--preview] [--events script] [--out prefix] [--png prefix] [--raw file|-]\n"
+                        "[--yaw-step S] [--validation] [--preview] [--events script] [--out prefix] [--png prefix] [--raw file|-] [--check]\n"
                         "       %s -builder [--resolution r --mode m] <in.ply | in.voxel> <out.oct>\n", argv[0], argv[0]);
         return 2;
     }
@@ -112,6 +114,7 @@ int main(int argc, char **argv) {
     float radius = 1.0f, pitch = 0.0f, yaw0 = 0.0f, yawStep = 3.6f;
     int stride = 1;
     std::string out, raw, events, png;
+    bool check = false;
     for (int i = 2; i < argc; ++i) {
         std::string a = argv[i];
         auto next = [&]() -> const char * { return i + 1 < argc ? argv[++i] : ""; };
@@ -127,8 +130,27 @@ int main(int argc, char **argv) {
         else if (a == "--out") out = next();
         else if (a == "--raw") raw = next();
         else if (a == "--png") png = next();
+        else if (a == "--check") check = true;
         else if (a == "--events") events = next();
         else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
+    }
+    if (check) {
+        // host only: decode the file and walk the whole node array (svo_words_validate); no GPU is touched
+        uint32_t *words = 0;
+        uint64_t n = 0;
+        float center[3];
+        svo_words_report rep;
+        if (svo_oct_read(argv[1], &words, &n, center) != SVO_OK || svo_words_validate(words, n, &rep) != SVO_OK) {
+            fprintf(stderr, "error: %s: %s\n", argv[1], svo_last_error());
+            svo_free(words);
+            return 1;
+        }
+        printf("%s: ok -- %llu words = %llu descriptors + %llu far words + %llu leaf words%s, depth %u, centre (%g, %g, %g)\n", argv[1],
+               (unsigned long long)n, (unsigned long long)rep.descriptors, (unsigned long long)rep.far_words,
+               (unsigned long long)rep.leaves, rep.descriptors + rep.far_words + rep.leaves == n ? "" : " (+ unreachable words)",
+               rep.depth, center[0], center[1], center[2]);
+        svo_free(words);
+        return 0;
     }
     try {
         std::vector<svo_viewer_event> script;

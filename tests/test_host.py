@@ -408,6 +408,16 @@ def test_headless_driver_reports_errors_without_a_gpu(pysvo, tmp_path):
     assert out.returncode == 2 and "--events script" in out.stderr and "-builder" in out.stderr
     out = subprocess.run([exe, str(DRAGON), "--bogus"], capture_output=True, text=True, timeout=60)
     assert out.returncode == 2 and "unknown option" in out.stderr
+    # --check: the file's node array walked on the host, no GPU involved
+    out = subprocess.run([exe, str(DRAGON), "--check"], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and "119887 words = 29156 descriptors + 24 far words + 90707 leaf words, depth 8" in out.stdout
+    damaged = tmp_path / "damaged.oct"
+    words, center = pysvo.oct_read(DRAGON)
+    words = words.copy()
+    words[1] &= np.uint32(0x3FFFF)          # the root's first child: a node that is its own child
+    pysvo.oct_write(damaged, words, center, compress=True)
+    out = subprocess.run([exe, str(damaged), "--check"], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 1 and "zero child offset at 1" in out.stderr
     if pysvo.device_count() < 1:
         good = tmp_path / "ok.events"
         good.write_text("down left\nmotion 4 -3\nup left\n")
