@@ -414,7 +414,7 @@ def test_headless_driver_reports_errors_without_a_gpu(pysvo, tmp_path):
     damaged = tmp_path / "damaged.oct"
     words, center = pysvo.oct_read(DRAGON)
     words = words.copy()
-    words[1] &= np.uint32(0x3FFFF)          # the root's first child: a node that is its own child
+    words[1] &= np.uint32(0x1FFFF)          # the root's first child loses its (far) pointer: a node that is its own child
     pysvo.oct_write(damaged, words, center, compress=True)
     out = subprocess.run([exe, str(damaged), "--check"], capture_output=True, text=True, timeout=60)
     assert out.returncode == 1 and "zero child offset at 1" in out.stderr
