@@ -308,8 +308,9 @@ typedef struct svo_frame_desc {
     int32_t strips;             /* the reference's NumThreads (Main.cpp:57): the image depends on it */
     int32_t flavour;            /* svo_flavour */
     /* Multi-GPU tile interleave: this call renders only the 8x8 tiles whose
-     * column index tx satisfies (tx / 4) % tile_world == tile_rank (vertical
-     * stripes four tiles = 32 pixels wide, dealt round-robin) and touches no
+     * column index tx satisfies (tx / run) % tile_world == tile_rank (vertical
+     * stripes `run` tiles wide, dealt round-robin; run = 4 = 32 pixels unless
+     * svo_frame_set_tile_run changed it) and touches no
      * other pixel; its beam pass traces only the tile corners on either side
      * of those stripes (5/4 of 1/tile_world of the corners).
      * Single GPU: tile_rank = 0, tile_world = 1. */
@@ -336,7 +337,7 @@ typedef struct svo_frame_stats {
 /* Geometry of the reference's strip / tile decomposition for one configuration
  * (Main.cpp:351-362), host only. The depth buffer has `corners` floats; tiles are numbered
  * strip by strip, row by row (tile t is in column t % tile_cols); with a tile interleave tile t
- * belongs to rank ((t % tile_cols) / 4) % tile_world (svo_frame_tile_owner). */
+ * belongs to rank ((t % tile_cols) / run) % tile_world (svo_frame_tile_owner; run = 4 by default). */
 typedef struct svo_frame_layout {
     int32_t n_strips;           /* strips that own at least one row */
     int32_t strip_rows;         /* rows per strip ("stride", Main.cpp:351) */
