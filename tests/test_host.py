@@ -550,3 +550,19 @@ def test_words_validate(pysvo, dragon_words, monkeypatch):
         with pytest.raises(pysvo.SvoError) as e:
             pysvo.VoxelOctree(words=bad, center=center)
         assert e.value.status == 6
+
+
+def test_plain_c_example_builds_against_the_abi(pysvo, tmp_path):
+    """host/example_render.c: the boundary is usable from pedantic C99 (no C++ in the header), links against the
+    library, and without a device fails with the library's message instead of doing anything else."""
+    import subprocess
+    from conftest import DRAGON, ROOT
+    pkg = ROOT / "sparse-voxel-octrees_b200"
+    exe = tmp_path / "example_render"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", str(ROOT / "include"),
+                           str(pkg / "host" / "example_render.c"), "-L", str(pkg), "-lsvo_b200", f"-Wl,-rpath,{pkg}", "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 2 and "usage" in out.stderr
+    if pysvo.device_count() < 1:
+        out = subprocess.run([str(exe), str(DRAGON), str(tmp_path / "x.ppm")], capture_output=True, text=True, timeout=60)
+        assert out.returncode == 1 and "no CPU fallback" in out.stderr
