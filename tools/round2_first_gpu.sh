@@ -17,6 +17,11 @@ if [ "$1" = "one" ]; then
   for i in 1 2; do python tools/exp_ply.py ico8192 2>&1 | grep -v "voxelizeMesh\|OctreeBuilder" | tail -12; done | tee gpurun_out/${tag}_ply_first_call.txt
 else
   N=$1
+  # configs[4]: the fly-through sweep on the 8192^3 tree at N ranks (ms per frame; the L2 hit rate comes from the ncu capture at N = 1)
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus $N \
+      --workload c5_flythrough_ico8192 --steps 300 --warmup 10 --no-cpu-baseline 2>gpurun_out/${tag}_c5_n$N.err | tail -1 > gpurun_out/${tag}_c5_n$N.json
+  python -c "
+import json; d=json.load(open('gpurun_out/${tag}_c5_n$N.json')); print('N=$N', d['config']['workload'], round(d['value']), 'Mrays/s', round(d['ms_per_step'],4), 'ms; e2e', round(d['e2e']['value']), d['parity'])" || tail -5 gpurun_out/${tag}_c5_n$N.err
   python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N \
       --steps 300 --warmup 10 --no-cpu-baseline 2>gpurun_out/${tag}_c3_n$N.err | tail -1 > gpurun_out/${tag}_c3_n$N.json
   python -c "
