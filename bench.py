@@ -201,17 +201,36 @@ def profile_traffic(workload):
 # reference arm
 # ------------------------------------------------------------------------------------------------
 
-def reference_sample(w, steps, warmup, budget_s, quiet=False):
-    """Times the reference's own renderer (oracle/_ref) on all host cores. Returns dict(value, ...)."""
+def reference_tree(ref, w):
+    """The workload's node array as a tree handle of the reference's own code (oracle/_ref) -- WITHOUT loading
+    libsvo_b200.so: the reference arm must not touch the product. The xz transport sidecar is read with
+    lzma + numpy (tools/make_scenes.unpack_scene) and adopted through the reference's constructor; a plain
+    .oct goes through the reference's own loader (VoxelOctree.cpp:57-90; every scene here is below the 2 GiB
+    where its int truncation starts, App. E.1). Returns (handle, words or None, center)."""
+    from tools import make_scenes
+    path = Path(w["path"])
+    if w["scene"] is not None and not path.exists() and make_scenes.packed_path(w["scene"]).exists():
+        words, center = make_scenes.unpack_scene(w["scene"])
+        return ref.tree_from_words(words, center), words, np.asarray(center, np.float32)
+    if not path.exists():
+        make_scenes.make_scene(w["scene"], verbose=False)        # the reference builder, also without the product
+    h = ref.tree_load(path)
+    return h, None, ref.tree_center(h)
+
+
+def reference_sample(w, steps, warmup, budget_s, strips=None, ref=None, tree=None):
+    """Times the reference's own renderer (oracle/_ref) on the host cores: `strips` strips = OS threads (the
+    reference's NumThreads, Main.cpp:57,351-367); default STRIPS, the GPU arm's configuration, so that both arms
+    render the same image. Returns dict(value, ...)."""
     from oracle.pyoracle import Ref, strip_layout
-    import pysvo  # host-only .oct reader (64-bit safe; the reference loader truncates >= 2 GiB, App. E.1)
-    ref = Ref()
+    own_tree = tree is None
+    if ref is None:
+        ref = Ref()
     cores = os.cpu_count() or 1
     H = w["height"]
-    strips = max(1, min(cores, H // 8))       # BASELINE.md 3.2: strips = OS threads = nproc
-    words, center = pysvo.oct_read(w["path"])
-    h = ref.tree_from_words(words, center)
-    del words
+    strips = STRIPS if strips is None else max(1, min(strips, H // 8))
+    threads = min(cores, strips)
+    h = reference_tree(ref, w)[0] if own_tree else tree
     cams = cameras(None, w, warmup + steps)
     mv = [ref.orbit_camera(*c) for c in cams]
     models = np.stack([m for m, _ in mv])
@@ -219,29 +238,30 @@ def reference_sample(w, steps, warmup, budget_s, quiet=False):
     # size the per-step sample: probe one frame on every 8th strip, then pick the modulo
     modulo = 1
     t0 = time.perf_counter()
-    ref.render_frames(h, w["width"], H, strips, models[:1], views[:1], threads=cores, strip_modulo=8)
-    probe = (time.perf_counter() - t0) * 8.0
+    ref.render_frames(h, w["width"], H, strips, models[:1], views[:1], threads=threads, strip_modulo=min(8, strips))
+    probe = (time.perf_counter() - t0) * min(8, strips)
     while modulo < 64 and probe * (steps + warmup) / modulo > budget_s and strips // (modulo * 2) >= 1:
         modulo *= 2
     rgba, _, secs = ref.render_frames(h, w["width"], H, strips, models[:warmup] if warmup else models[:1],
-                                      views[:warmup] if warmup else views[:1], threads=cores, strip_modulo=modulo)
+                                      views[:warmup] if warmup else views[:1], threads=threads, strip_modulo=modulo)
     total_rays = 0
     total_s = 0.0
     lay = strip_layout(w["width"], H, strips)
     for k in range(steps):
         rgba, _, secs = ref.render_frames(h, w["width"], H, strips, models[warmup + k:warmup + k + 1],
-                                          views[warmup + k:warmup + k + 1], threads=cores, strip_modulo=modulo)
+                                          views[warmup + k:warmup + k + 1], threads=threads, strip_modulo=modulo)
         rays = 0
         for s, (y0, y1, tx, ty) in enumerate(lay):
             if s % modulo == 0:
                 rays += tx * ty + int((rgba[y0:y1] != 0).sum())
         total_rays += rays
         total_s += float(secs[0])
-    ref.tree_destroy(h)
+    if own_tree:
+        ref.tree_destroy(h)
     sample = (f"{steps} frame(s) after {warmup} warm-up, every strip" if modulo == 1 else
               f"{steps} frame(s) after {warmup} warm-up, every {modulo}th of {strips} strips per frame")
-    return dict(value=total_rays / total_s / 1e6, seconds=total_s, rays=total_rays, cores=cores, strips=strips,
-                sample=sample, ms_per_step=total_s / steps * 1e3, modulo=modulo)
+    return dict(value=total_rays / total_s / 1e6, seconds=total_s, rays=total_rays, cores=threads, host_cores=cores,
+                strips=strips, sample=sample, ms_per_step=total_s / steps * 1e3, modulo=modulo)
 
 
 def ao_workload_rays(w, tree_or_none, words, center):
@@ -261,12 +281,12 @@ def ao_workload_rays(w, tree_or_none, words, center):
 
 def run_reference_ao(args, w):
     from oracle.pyoracle import Ref
-    import pysvo
     ref = Ref()
     cores = os.cpu_count() or 1
-    words, center = pysvo.oct_read(w["path"])
+    h, words, center = reference_tree(ref, w)
+    if words is None:
+        words = ref.tree_words(h)
     ao_o, ao_d = ao_workload_rays(w, None, words, center)
-    h = ref.tree_from_words(words, center)
     steps = args.steps if args.steps is not None else 2
     warmup = args.warmup if args.warmup is not None else 1
     n = ao_o.shape[0]
@@ -300,6 +320,7 @@ def run_own_ao(args, w):
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ensure_scene(w, rank, dist.barrier if dist else (lambda: None))
     steps = args.steps if args.steps is not None else 20
     warmup = max(args.warmup if args.warmup is not None else 3, 3)
     words, center = pysvo.oct_read(w["path"])
@@ -419,28 +440,43 @@ def run_own_ao(args, w):
 
 
 def run_reference(args):
+    """The reference's own CPU renderer on this box's host cores; never loads libsvo_b200.so."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     w = pick_workload(args.workload)
-    ensure_scene(w, 0, lambda: None)
     if w.get("kind") == "ao":
         return run_reference_ao(args, w)
+    from oracle.pyoracle import Ref
+    ref = Ref()
     steps = args.steps if args.steps is not None else 3
     warmup = args.warmup if args.warmup is not None else 1
-    r = reference_sample(w, steps, warmup, budget_s=150.0)
+    h = reference_tree(ref, w)[0]
+    # the ratio's arm: the GPU arm's configuration (16 strips = the reference's NumThreads, Main.cpp:57 -- the image
+    # depends on it), its 16 render threads on this box's cores
+    r = reference_sample(w, steps, warmup, budget_s=120.0, strips=STRIPS, ref=ref, tree=h)
+    # beside it: every host core busy (strips = threads = nproc, BASELINE.md 3.2) -- a slightly different image
+    cores = os.cpu_count() or 1
+    allc = None
+    if cores != STRIPS:
+        a = reference_sample(w, steps, warmup, budget_s=60.0, strips=cores, ref=ref, tree=h)
+        allc = {"value": a["value"], "unit": "Mrays/s", "strips": a["strips"], "threads": a["cores"], "sample": a["sample"],
+                "note": "strips = threads = nproc: not the GPU arm's image (tile grids are anchored per strip)"}
+    ref.tree_destroy(h)
     line = {
         "impl": "reference", "metric": "Mrays/s ESVO traversal (coarse + fine raymarch calls per frame / time)",
         "value": r["value"], "unit": "Mrays/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": w["name"], "description": w["text"], "width": w["width"], "height": w["height"],
-                   "strips": r["strips"], "host_threads": r["cores"]},
+                   "strips": r["strips"], "host_threads": r["cores"], "host_cores": r["host_cores"]},
         "cpu_baseline": {"value": r["value"], "unit": "Mrays/s", "cores": r["cores"], "kind": "reference",
                          "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if allc is not None:
+        line["all_cores"] = allc
     emit(line)
 
 
@@ -448,7 +484,29 @@ def run_reference(args):
 # own arm
 # ------------------------------------------------------------------------------------------------
 
+def kernel_source_hash():
+    """sha256 over the kernel sources: ties an ncu capture under profiles/ to the code it was taken from."""
+    import hashlib
+    h = hashlib.sha256()
+    for name in ("svo_traverse.cuh", "svo_kernels.cu", "svo_kernels.cuh"):
+        h.update((ROOT / "sparse-voxel-octrees_b200" / "csrc" / name).read_bytes())
+    return h.hexdigest()[:16]
+
+
+def git_head():
+    try:
+        import subprocess
+        return subprocess.run(["git", "-C", str(ROOT), "rev-parse", "--short", "HEAD"], capture_output=True, text=True,
+                              timeout=10).stdout.strip() or None
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def run_own(args):
+    """Frame workloads. ONE process drives all N GPUs through the library's multi-GPU handle (svo_multi_*: replicated
+    octree, interleaved tile columns, worker thread per device, CUDA-event frame barrier, fine passes storing into
+    device 0's framebuffer over NVLink). Under torchrun the other ranks initialise NCCL, meet rank 0 at the barriers
+    and take part in the max-over-ranks reduction of the timing, but issue no work: their GPUs are driven by rank 0."""
     import torch
     import pysvo
 
@@ -459,375 +517,187 @@ def run_own(args):
         raise SystemExit(f"{pysvo.LIB_PATH} missing: run __graft_entry__.build() first (no fallback exists)")
     if pysvo.device_count() < 1:
         raise SystemExit("no CUDA device: this benchmark has no CPU fallback (use --impl reference for the CPU arm)")
+    w = pick_workload(args.workload)
+    if w.get("kind") == "ao":
+        return run_own_ao(args, w)
     torch.cuda.set_device(local_rank)
-    dist = None
+    dist = idle = None
     if world > 1:
+        import datetime
         import torch.distributed as dist_mod
         dist = dist_mod
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(minutes=30))
+        probe = torch.ones(1, device="cuda")
+        dist.all_reduce(probe)                       # NCCL up on all N ranks / GPUs
+        assert int(probe.item()) == world
+        # the long waits (rank 0 renders, the others idle) go through a CPU group: a pending NCCL barrier would be a
+        # spinning kernel on every idle rank's GPU -- the GPUs rank 0 is timing
+        idle = dist.new_group(backend="gloo", timeout=datetime.timedelta(minutes=30))
 
     def barrier():
         if dist is not None:
-            dist.barrier()
+            torch.cuda.synchronize()
+            dist.barrier(group=idle)
+
+    def max_over_ranks(x):
+        if dist is None:
+            return float(x)
+        t = torch.tensor([float(x)], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=idle)
+        return float(t.item())
 
     steps = args.steps if args.steps is not None else 300
-    warmup = args.warmup if args.warmup is not None else 10
-    warmup = max(warmup, 3)
-
-    w = pick_workload(args.workload)
-    ensure_scene(w, rank, barrier)
-    if w.get("kind") == "ao":
-        if dist is not None:
-            dist.destroy_process_group()
-        return run_own_ao(args, w)
-    W, H = w["width"], w["height"]
-    tree = pysvo.VoxelOctree(w["path"], device=local_rank)
-    flavour = pysvo.FLAVOUR_VALIDATION if args.validation else pysvo.FLAVOUR_FAST
-    stream = torch.cuda.current_stream().cuda_stream
-    cams = [pysvo.orbit_camera(*c) for c in cameras(pysvo, w, ORBIT)]
-
-    # ---- framebuffer: rank 0 owns it; other ranks map it and store their tiles into it over NVLink
-    nbytes = W * H * 4
-    n_lanes = min(int(os.environ.get("SVO_BENCH_LANES", "0")) or LANES, 8)    # the library's frame ring is 8 deep
-    fbs = []
-    fb_ptrs = [0] * n_lanes
-    if rank == 0:
-        for i in range(n_lanes):    # one framebuffer per frame in flight: frame k is consumed while k+1.. are rendered
-            fbs.append(pysvo.DeviceBuffer(local_rank, nbytes))
-            fbs[i].zero()
-            fb_ptrs[i] = fbs[i].ptr
-    if world > 1:
-        handle = [[f.ipc_export() for f in fbs] if rank == 0 else None]
-        dist.broadcast_object_list(handle, src=0)
-        if rank != 0:
-            fb_ptrs = [pysvo.ipc_open(local_rank, hdl) for hdl in handle[0]]
-    fb_ptr = fb_ptrs[0]
-    flag = torch.zeros(1, device="cuda", dtype=torch.int32) if world > 1 else None
-
-    def frame(k, want_stats=False, fb=None, sync=True):
-        st = tree.render_frame_device(cams[k % ORBIT], W, H, fb or fb_ptr, strips=STRIPS, flavour=flavour,
-                                      tile_rank=rank, tile_world=world, stream=stream, want_stats=want_stats)
-        if world > 1 and sync:
-            dist.all_reduce(flag)      # frame complete on every rank before rank 0 may use it
-        return st
-
-    # ---- rays per camera (untimed): coarse once per frame, fine summed over ranks
-    n_distinct = min(ORBIT, steps + warmup)
-    fine = torch.zeros(ORBIT, dtype=torch.int64, device="cuda")
-    coarse = int(pysvo.frame_layout(W, H, STRIPS).corners)   # beam rays of the frame as the reference issues them
-    kernel_ms = []
-    for k in range(n_distinct):
-        st = frame(k, want_stats=True)
-        fine[k] = int(st.fine_rays)
-        kernel_ms.append((st.coarse_ms, st.fine_ms))
-    if os.environ.get("SVO_BENCH_DEBUG"):
-        km = np.array(kernel_ms)
-        print(f"[rank {rank}] beam pass {km[:, 0].mean():.4f} ms, classify+fine {km[:, 1].mean():.4f} ms "
-              f"(min {km[:, 1].min():.4f}, max {km[:, 1].max():.4f}) over {len(km)} cameras", file=sys.stderr, flush=True)
-    if world > 1:
-        dist.all_reduce(fine)
-    fine = fine.cpu().numpy()
-    rays_of = lambda k: coarse + int(fine[k % ORBIT])  # noqa: E731
-
-    # ---- timed region: W warm-up frames, then exactly K frames between device events.
-    # Double-buffered like a swap chain: frame k renders into framebuffer k & 1 on stream k & 1, so the
-    # long-ray tail of one fine pass overlaps the start of the next frame (each frame is still complete,
-    # in rank 0's memory, when its stream reaches the frame barrier).
-    main = torch.cuda.current_stream()
-    lanes = [torch.cuda.Stream() for _ in range(n_lanes)]
-    comm = torch.cuda.Stream() if world > 1 else None
-    gate = [None] * n_lanes
-
-    def pipelined_frame(k):
-        slot = k % n_lanes
-        with torch.cuda.stream(lanes[slot]):
-            tree.render_frame_device(cams[k % ORBIT], W, H, fb_ptrs[slot], strips=STRIPS, flavour=flavour,
-                                     tile_rank=rank, tile_world=world, stream=lanes[slot].cuda_stream)
-            if world > 1 and not os.environ.get("SVO_BENCH_NO_BARRIER"):   # (experiment switch, never set by default)
-                done = torch.cuda.Event()
-                done.record(lanes[slot])
-                comm.wait_event(done)
-                with torch.cuda.stream(comm):
-                    dist.all_reduce(flag)          # frame barrier: every rank's tiles are in rank 0's framebuffer
-                    gate[slot] = torch.cuda.Event()
-                    gate[slot].record(comm)
-                lanes[slot].wait_event(gate[slot])  # the slot is reused (frame k+2) only after the barrier
-
-    def run_frames(first, count):
-        start = torch.cuda.Event(enable_timing=True)
-        stop = torch.cuda.Event(enable_timing=True)
-        start.record(main)
-        for ln in lanes:
-            ln.wait_event(start)
-        for k in range(first, first + count):
-            pipelined_frame(k)
-        for ln in lanes:
-            main.wait_stream(ln)
-        if comm is not None:
-            main.wait_stream(comm)
-        stop.record(main)
-        return start, stop
-
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    run_frames(0, warmup)
-    torch.cuda.synchronize()
-    barrier()
-    torch.cuda.synchronize()
-    t_begin = time.perf_counter()
-    e0, e1 = run_frames(warmup, steps)
-    torch.cuda.synchronize()
-    barrier()
-    torch.cuda.synchronize()
-    t_end = time.perf_counter()
-    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    total_ms = float(ms.item())
-    total_rays = sum(rays_of(k) for k in range(warmup, warmup + steps))
-    value = total_rays / (total_ms * 1e-3) / 1e6
-
-    # ---- end to end: host-visible frame every step (pinned host memory), same cameras
-    e2e_steps = min(steps, 300)
-    host_bufs = [pysvo.PinnedArray((H, W), np.uint32) for _ in range(4)] if rank == 0 else None
-    host = host_bufs[0] if rank == 0 else None
-    hosts = [h.array for h in host_bufs] if rank == 0 else None
-    copy_stream = torch.cuda.Stream()
-    if world == 1:
-        # untimed: the library creates its staging framebuffers on first use
-        for k in range(len(hosts)):
-            tree.frame_wait(tree.render_frame_async(cams[k % ORBIT], W, H, hosts[k], strips=STRIPS, flavour=flavour))
-    e2e_mode = "single"
-    e2e_lanes = min(n_lanes, 4)
-    frame_done = [None] * e2e_lanes
-    shared_host = None
-    per_rank = [world > 1 and not os.environ.get("SVO_BENCH_E2E_VIA_RANK0")]
-    if world > 1:
-        if rank == 0 and per_rank[0]:
-            try:        # the shared host frames live in /dev/shm (like NCCL's own shared-memory segments)
-                vfs = os.statvfs("/dev/shm")
-                per_rank[0] = vfs.f_bavail * vfs.f_frsize > 2 * e2e_lanes * nbytes
-            except OSError:
-                per_rank[0] = False
-        dist.broadcast_object_list(per_rank, src=0)
-    per_rank = bool(per_rank[0])
-    if per_rank:
-        # untimed set-up of the per-rank path: the shared host frames (one per frame in flight) and local framebuffers
-        name = [f"/dev/shm/svo_bench_{os.getpid()}.frames" if rank == 0 else None]
-        dist.broadcast_object_list(name, src=0)
-        ok, registered = True, False
-        try:
-            if rank == 0:
-                shared_host = np.memmap(name[0], dtype=np.uint32, mode="w+", shape=(e2e_lanes, H, W))
-                shared_host[:] = 0
-        except Exception as e:  # noqa: BLE001
-            ok = False
-            print(f"[rank {rank}] shared host frame: {e!r}", file=sys.stderr, flush=True)
-        barrier()
-        try:
-            if rank != 0:
-                shared_host = np.memmap(name[0], dtype=np.uint32, mode="r+", shape=(e2e_lanes, H, W))
-            shared_dev = pysvo.host_register(local_rank, shared_host)
-            registered = True
-        except Exception as e:  # noqa: BLE001
-            ok = False
-            print(f"[rank {rank}] mapping the shared host frame: {e!r}", file=sys.stderr, flush=True)
-        all_ok = torch.tensor([1 if ok else 0], device="cuda", dtype=torch.int32)
-        dist.all_reduce(all_ok, op=dist.ReduceOp.MIN)
-        if not int(all_ok.item()):       # some rank could not map it: every rank takes the rank-0 path instead
-            if registered:
-                pysvo.host_unregister(shared_host)
-            shared_host = None
-            per_rank = False
-            barrier()
-            if rank == 0 and os.path.exists(name[0]):
-                os.unlink(name[0])
-    if per_rank:
-        # wider stripes for this leg: a rank's rows of pixels are what one PCIe write burst carries (measured: 128-byte
-        # runs 28 GB/s, whole rows 50 GB/s); the widest run <= 16 tile columns that still deals every rank the same
-        # number of columns, else the default of 4. The image does not depend on it.
-        tile_cols = (W - 1) // 8 + 1
-        e2e_run = int(os.environ.get("SVO_BENCH_E2E_RUN", "0")) or next(
-            (r for r in range(16, 4, -1) if tile_cols % (world * r) == 0), 4)
-        pysvo.frame_set_tile_run(e2e_run)
-        if rank == 0:
-            local_fbs = fb_ptrs[:e2e_lanes]
-        else:
-            own = [pysvo.DeviceBuffer(local_rank, nbytes) for _ in range(e2e_lanes)]
-            for b in own:
-                b.zero()
-            local_fbs = [b.ptr for b in own]
-        for k in range(e2e_lanes):      # first use of the copy kernel / the mapping, untimed
-            pysvo.frame_copy_owned_tiles(local_rank, W, H, STRIPS, rank, world, local_fbs[k], shared_dev + k * nbytes, stream)
-    torch.cuda.synchronize()
-    barrier()
-    t0 = time.perf_counter()
-    if world == 1:
-        # pipelined host-buffer API: four frames in flight, each lands in its own pinned host buffer
-        pending = [None] * len(hosts)
-        dbg = [0.0, 0.0]
-        for k in range(warmup, warmup + e2e_steps):
-            slot = k % len(hosts)
-            ta = time.perf_counter()
-            if pending[slot] is not None:
-                tree.frame_wait(pending[slot])          # frame k-4 is in host memory; its buffer is free again
-            tb = time.perf_counter()
-            pending[slot] = tree.render_frame_async(cams[k % ORBIT], W, H, hosts[slot], strips=STRIPS, flavour=flavour)
-            dbg[0] += tb - ta
-            dbg[1] += time.perf_counter() - tb
-        for pnd in pending:
-            if pnd is not None:
-                tree.frame_wait(pnd)
-        if os.environ.get("SVO_BENCH_DEBUG"):
-            print(f"[e2e] wait {dbg[0] / e2e_steps * 1e3:.3f} ms/frame, issue {dbg[1] / e2e_steps * 1e3:.3f} ms/frame",
-                  file=sys.stderr, flush=True)
-    elif not per_rank:
-        e2e_mode = "rank0"
-        # every rank stores its tiles into rank 0's framebuffer k & 1 over NVLink; after the frame barrier
-        # rank 0 copies it to pinned host memory on a side stream while frame k+1 is rendered into the other one
-        copied = [None, None]
-        for k in range(warmup, warmup + e2e_steps):
-            slot = k & 1
-            frame(k, fb=fb_ptrs[slot], sync=False)
-            if rank == 0 and copied[slot ^ 1] is not None:
-                main.wait_event(copied[slot ^ 1])   # framebuffer slot^1 is rewritten by frame k+1 after this barrier
-            dist.all_reduce(flag)
-            if rank == 0:
-                if copied[slot] is not None:
-                    copied[slot].synchronize()      # frame k-2 is in host memory: its pinned buffer is free again
-                copy_stream.wait_stream(main)
-                pysvo.device_to_host_async(local_rank, hosts[slot], fb_ptrs[slot], nbytes, copy_stream.cuda_stream)
-                copied[slot] = torch.cuda.Event()
-                copied[slot].record(copy_stream)
-        if rank == 0:
-            for ev in copied:
-                if ev is not None:
-                    ev.synchronize()
-    else:
-        # every rank renders its tiles into its OWN framebuffer and ships them itself (svo_frame_copy_owned_tiles)
-        # into one page-locked host frame that all ranks have mapped (a shared-memory segment): 1 / world of the
-        # frame per PCIe link instead of all of it over rank 0's. Four frames in flight, like the N = 1 path; the
-        # frame barrier (all-reduce enqueued behind each rank's copy) tells rank 0 that a host frame is complete.
-        e2e_mode = "per-rank"
-        for k in range(warmup, warmup + e2e_steps):
-            slot = k % e2e_lanes
-            if frame_done[slot] is not None:
-                frame_done[slot].synchronize()      # frame k-4 is complete in host memory: its slot is free again
-            with torch.cuda.stream(lanes[slot]):
-                tree.render_frame_device(cams[k % ORBIT], W, H, local_fbs[slot], strips=STRIPS, flavour=flavour,
-                                         tile_rank=rank, tile_world=world, stream=lanes[slot].cuda_stream)
-                pysvo.frame_copy_owned_tiles(local_rank, W, H, STRIPS, rank, world, local_fbs[slot],
-                                             shared_dev + slot * nbytes, lanes[slot].cuda_stream)
-                shipped = torch.cuda.Event()
-                shipped.record(lanes[slot])
-            comm.wait_event(shipped)
-            with torch.cuda.stream(comm):
-                dist.all_reduce(flag)
-                frame_done[slot] = torch.cuda.Event()
-                frame_done[slot].record(comm)
-        for ev in frame_done:
-            if ev is not None:
-                ev.synchronize()
-    torch.cuda.synchronize()
-    barrier()
-    e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_rays = sum(rays_of(k) for k in range(warmup, warmup + e2e_steps))
-    e2e_value = e2e_rays / float(e2e_s.item()) / 1e6
-    e2e_frame_identical = None
-    if shared_host is not None:
-        if rank == 0:
-            # the last host frame, assembled by all ranks, against the same camera rendered by rank 0 alone
-            k_last = warmup + e2e_steps - 1
-            tree.render_frame_device(cams[k_last % ORBIT], W, H, fb_ptrs[0], strips=STRIPS, flavour=flavour, stream=stream)
-            torch.cuda.synchronize()
-            alone = fbs[0].to_host(np.uint32).reshape(H, W)
-            e2e_frame_identical = bool(np.array_equal(alone, shared_host[k_last % e2e_lanes]))
-        barrier()
-        pysvo.frame_set_tile_run(0)
-        pysvo.host_unregister(shared_host)
-        del shared_host
-        if rank == 0:
-            os.unlink(name[0])
-    if sampler:
-        sampler.stop()
-
+    warmup = max(args.warmup if args.warmup is not None else 10, 3)
     if rank != 0:
-        if world > 1:
-            barrier()
-            dist.destroy_process_group()
+        barrier()                 # scene ready, octree replicated, warm-up done
+        barrier()                 # timed region over
+        max_over_ranks(0.0)
+        barrier()                 # e2e over
+        max_over_ranks(0.0)
+        barrier()
+        dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (fine pass): algorithmic bytes from the instrumented oracle
+    ensure_scene(w, 0, lambda: None)
+    W, H = w["width"], w["height"]
+    flavour = pysvo.FLAVOUR_VALIDATION if args.validation else pysvo.FLAVOUR_FAST
+    multi = pysvo.MultiOctree(w["path"], devices=tuple(range(world)))
+    tree = multi.tree(0)
+    cams = [pysvo.orbit_camera(*c) for c in cameras(pysvo, w, ORBIT)]
+    path = lambda first, count: [cams[k % ORBIT] for k in range(first, first + count)]  # noqa: E731
+    nbytes = W * H * 4
+
+    # ---- device-timed: W warm-up frames, then rounds of exactly K frames (one svo_multi_render_sequence call each:
+    # four frames in flight, CUDA events on device 0 around the round). Rounds repeat until the timed region is
+    # >= 0.6 s so that the clock sampler sees it; the MEDIAN round is reported.
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    multi.render_sequence(path(0, warmup), W, H, strips=STRIPS, flavour=flavour, output=pysvo.OUTPUT_DEVICE)
+    barrier()
+    t_begin = time.perf_counter()
+    rounds = []
+    while (not rounds or sum(r.device_ms for r in rounds) < 600.0) and len(rounds) < 400:
+        rounds.append(multi.render_sequence(path(warmup, steps), W, H, strips=STRIPS, flavour=flavour,
+                                            output=pysvo.OUTPUT_DEVICE))
+    t_end = time.perf_counter()
+    barrier()
+    rounds.sort(key=lambda r: r.device_ms)
+    med = rounds[len(rounds) // 2]
+    total_ms = max_over_ranks(med.device_ms)
+    total_rays = med.rays
+    value = total_rays / (total_ms * 1e-3) / 1e6
+    device_launches = int(med.kernel_launches)
+    n_lanes, dev_run = int(med.lanes), int(med.tile_run)
+
+    # ---- end to end: every frame of the same camera path lands in page-locked host memory (ring of four frames);
+    # with N > 1 every GPU ships the stripes it rendered over its own PCIe link. Host clock around the call.
+    e2e_steps = min(steps, 300)
+    ring = [pysvo.PinnedArray((H, W), np.uint32) for _ in range(4)]
+    hosts = [r.array for r in ring]
+    multi.render_sequence(path(0, 8), W, H, strips=STRIPS, flavour=flavour, output=pysvo.OUTPUT_HOST, host_frames=hosts)
+    e2e_rounds = []
+    while (not e2e_rounds or sum(r.wall_ms for r in e2e_rounds) < 600.0) and len(e2e_rounds) < 100:
+        e2e_rounds.append(multi.render_sequence(path(warmup, e2e_steps), W, H, strips=STRIPS, flavour=flavour,
+                                                output=pysvo.OUTPUT_HOST, host_frames=hosts))
+    barrier()
+    e2e_rounds.sort(key=lambda r: r.wall_ms)
+    e2e_med = e2e_rounds[len(e2e_rounds) // 2]
+    e2e_ms = max_over_ranks(e2e_med.wall_ms)
+    e2e_value = e2e_med.rays / (e2e_ms * 1e-3) / 1e6
+    k_last = warmup + e2e_steps - 1
+    last_host = hosts[(e2e_steps - 1) % len(hosts)].copy()       # the last e2e frame, as assembled by all devices
+    sampler.stop()
+
+    # ---- parity on the benchmark's own scene and size: the frame all N devices assemble against the oracle
     from oracle.pyoracle import Port
     port = Port()
     words, center = pysvo.oct_read(w["path"])
-    roof_cams = [0, min(25, n_distinct - 1)] if world == 1 else [0]
-    alg_bytes, fine_ms_sum, px_sum, fine_rays_sum, node_bytes_sum = 0.0, 0.0, 0, 0, 0
+    roof_cams = [0, 25] if world == 1 else [0]
     parity = {}
-    for k in roof_cams:
-        cam = cams[k]
-        f = port.frame_constants(np.array(cam.model[:], np.float32), np.array(cam.view[:], np.float32), center, W, H, STRIPS)
-        want, _, cc, cf = port.render_frame(words, f)
-        node_bytes = 4 * cf.words
-        if world == 1:
-            alg_bytes += node_bytes + 4 * cf.rays
-            fine_ms_sum += kernel_ms[k][1]
-            px_sum += cf.rays
-            fine_rays_sum += cf.rays
-            node_bytes_sum += node_bytes
-        if k == roof_cams[0]:
-            got, _, _ = tree.render_frame(cam, W, H, strips=STRIPS, flavour=pysvo.FLAVOUR_FAST, rgba=host.array,
-                                          want_stats=False) if world == 1 else (None, None, None)
-            if got is not None:
-                parity["fast_identical_pixels"] = float((got == want).mean())
-                val, _, _ = tree.render_frame(cam, W, H, strips=STRIPS, flavour=pysvo.FLAVOUR_VALIDATION,
-                                              rgba=host.array, want_stats=False)
-                parity["validation_identical_pixels"] = float((val == want).mean())
-            parity["oracle_rays"] = int(cc.rays + cf.rays)
-            parity["gpu_rays"] = rays_of(k)
-            coarse_b_ray = 4.0 * cc.words / max(cc.rays, 1)
-            fine_b_ray = 4.0 * cf.words / max(cf.rays, 1)
+    cam = cams[k_last % ORBIT]
+    f = port.frame_constants(np.array(cam.model[:], np.float32), np.array(cam.view[:], np.float32), center, W, H, STRIPS)
+    want, _, cc, cf = port.render_frame(words, f)
+    parity["e2e_last_frame_identical_pixels"] = float((last_host == want).mean())
+    val, vst = multi.render_frame(cam, W, H, strips=STRIPS, flavour=pysvo.FLAVOUR_VALIDATION, rgba=hosts[0])
+    parity["validation_identical_pixels"] = float((val == want).mean())
+    fast, _ = multi.render_frame(cam, W, H, strips=STRIPS, flavour=pysvo.FLAVOUR_FAST, rgba=hosts[1])
+    parity["fast_identical_pixels"] = float((fast == want).mean())
+    parity["oracle_rays"] = int(cc.rays + cf.rays)
+    parity["gpu_rays"] = int(vst.coarse_rays + vst.fine_rays)
+    if world > 1:
+        alone, _, _ = tree.render_frame(cam, W, H, strips=STRIPS, flavour=flavour)
+        parity["e2e_host_frame_identical_to_single_rank"] = bool(np.array_equal(alone, last_host))
+    coarse_b_ray = 4.0 * cc.words / max(cc.rays, 1)
+    fine_b_ray = 4.0 * cf.words / max(cf.rays, 1)
+
+    # ---- roofline of the dominant kernel (fine pass), N = 1: algorithmic bytes from the instrumented oracle on the
+    # same cameras / the kernel's own duration (CUDA events around classifier + fine pass on the launching stream,
+    # svo_frame_stats.fine_ms), both measured in this run
     peak, peak_src = measured_peak()
     roofline = None
-    if world == 1 and fine_ms_sum > 0:
+    if world == 1:
+        fb = pysvo.DeviceBuffer(local_rank, nbytes)
+        stream = torch.cuda.current_stream().cuda_stream
+        alg_bytes, fine_ms_sum, fine_rays_sum, node_bytes_sum, shares = 0.0, 0.0, 0, 0, []
+        for k in roof_cams:
+            ck = cams[k]
+            fk = port.frame_constants(np.array(ck.model[:], np.float32), np.array(ck.view[:], np.float32), center, W, H, STRIPS)
+            _, _, _, cfk = port.render_frame(words, fk)
+            samples = []
+            for _ in range(5):
+                st = tree.render_frame_device(ck, W, H, fb.ptr, strips=STRIPS, flavour=flavour, stream=stream, want_stats=True)
+                samples.append((st.coarse_ms, st.fine_ms))
+            samples.sort(key=lambda x: x[1])
+            c_ms, f_ms = samples[len(samples) // 2]
+            alg_bytes += 4 * cfk.words + 4 * cfk.rays
+            node_bytes_sum += 4 * cfk.words
+            fine_rays_sum += cfk.rays
+            fine_ms_sum += f_ms
+            shares.append(f_ms / (c_ms + f_ms))
         achieved = alg_bytes / (fine_ms_sum * 1e-3) / 1e9
-        traffic = profile_traffic(w["name"])
+        traffic = profile_traffic(w["name"]) or {}
+        src_hash = kernel_source_hash()
+        fresh = traffic.get("kernel_source_hash") == src_hash
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": (traffic or {}).get("dram_bytes_per_launch"),
+                    "traffic": traffic.get("dram_bytes_per_launch") if fresh else None,
                     "kernel": "finePassKernel<FAST>", "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes / len(roof_cams),
                     "bytes_per_fine_ray": {"node_words": node_bytes_sum / max(fine_rays_sum, 1), "pixel_store": 4.0},
                     "launch_ms": fine_ms_sum / len(roof_cams),
-                    "kernel_share_of_step": float(np.mean([f_ / (c_ + f_) for c_, f_ in kernel_ms])),
-                    "ncu": {k: (traffic or {}).get(k) for k in ("l1_hit_pct", "l2_hit_pct", "issue_active_pct",
-                                                               "threads_per_instruction", "source")},
+                    "kernel_share_of_step": float(np.mean(shares)),
+                    "kernel_source_hash": src_hash, "source_commit": git_head(),
+                    "ncu_capture": {"fresh": fresh, "capture_kernel_source_hash": traffic.get("kernel_source_hash"),
+                                    "capture_commit": traffic.get("commit"), "source": traffic.get("source")},
                     "note": "instruction-issue bound pointer chasing with SIMT divergence, not HBM-bound: node "
                             "fetches hit L1/L2 (see profiles/ and DESIGN.md section 4)"}
-        # the bound that does bind: one warp instruction per SM sub-partition per cycle (148 SMs x 4)
-        if traffic and traffic.get("warp_instructions") and traffic.get("sm_cycles_elapsed"):
-            slots = 148 * 4 * float(traffic["sm_cycles_elapsed"])
-            roofline["issue_roofline"] = {
-                "warp_instructions_per_launch": traffic["warp_instructions"],
-                "issue_slots_per_launch": slots, "frac": traffic["warp_instructions"] / slots,
-                "threads_per_instruction": traffic.get("threads_per_instruction"),
-                "source": traffic.get("source"),
-                "note": "fraction of the SMs' issue slots (148 SMs x 4 schedulers x elapsed cycles of the ncu capture) "
-                        "that issued an instruction of this kernel: the limit this pass actually runs against"}
+        if fresh:
+            roofline["ncu"] = {k: traffic.get(k) for k in ("l1_hit_pct", "l2_hit_pct", "issue_active_pct", "threads_per_instruction",
+                                                         "l2_throughput_pct", "l1_throughput_pct")}
+            if traffic.get("warp_instructions") and traffic.get("sm_cycles_elapsed"):
+                slots = 148 * 4 * float(traffic["sm_cycles_elapsed"])
+                roofline["issue_roofline"] = {
+                    "warp_instructions_per_launch": traffic["warp_instructions"], "issue_slots_per_launch": slots,
+                    "frac": traffic["warp_instructions"] / slots,
+                    "note": "fraction of the SMs' issue slots (148 SMs x 4 schedulers x elapsed cycles of the ncu capture) "
+                            "that issued an instruction of this kernel: the limit this pass actually runs against"}
+        else:
+            roofline["ncu_capture"]["note"] = ("profiles/traffic.json was captured from other kernel sources (or is absent): "
+                                               "traffic / ncu counters are withheld rather than reported stale")
+        fb.free()
 
-    # ---- CPU baseline: the reference's own renderer on this box's host cores (bounded sample)
+    # ---- CPU baseline: the reference's own renderer on this box's host cores (bounded sample, ~10-30 s)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
-            r = reference_sample(w, steps=2, warmup=1, budget_s=25.0)
-            cpu = {"value": r["value"], "unit": "Mrays/s", "cores": r["cores"], "kind": "reference", "sample": r["sample"]}
+            r = reference_sample(w, steps=20, warmup=2, budget_s=25.0, strips=STRIPS)
+            cpu = {"value": r["value"], "unit": "Mrays/s", "cores": r["cores"], "kind": "reference", "sample": r["sample"],
+                   "strips": r["strips"], "host_cores": r["host_cores"]}
         except Exception as e:  # noqa: BLE001
             cpu = {"value": None, "unit": "Mrays/s", "cores": os.cpu_count(), "kind": "reference",
                    "sample": f"unavailable: {e!r}"}
 
     clocks = sampler.summary(t_begin, t_end)
+    e2e_launches = int(e2e_med.kernel_launches)
     line = {
         "metric": "Mrays/s ESVO traversal (coarse + fine raymarch calls per frame / time)",
         "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": steps, "warmup": warmup,
@@ -836,24 +706,27 @@ def run_own(args):
         "config": {"workload": w["name"], "description": w["text"], "width": W, "height": H, "strips": STRIPS,
                    "flavour": "validation" if args.validation else "fast",
                    "octree_words": tree.n_words, "octree_depth": tree.depth,
-                   "parallelism": "replicated octree, interleaved 8x8 tiles, fine-pass stores into rank 0's framebuffer over NVLink" if world > 1 else "single GPU",
+                   "parallelism": ("one process, svo_multi_*: replicated octree, tile columns dealt in stripes of "
+                                   f"{dev_run} to {world} GPUs, fine passes store into GPU 0's framebuffer over NVLink, "
+                                   "CUDA-event frame barrier (no NCCL on the data path)") if world > 1 else "single GPU",
                    "l2": f"no flush: octree {tree.n_words * 4 / 1e6:.0f} MB vs 126 MB L2, camera moves every step",
-                   "pipelining": f"{n_lanes} frames in flight (framebuffer k % {n_lanes} on stream k % {n_lanes}); beam passes run ahead on internal streams",
+                   "pipelining": f"{n_lanes} frames in flight; beam passes run ahead on internal streams",
+                   "timed_region": {"rounds": len(rounds), "reported": "median round", "steps_per_round": steps,
+                                    "seconds": (t_end - t_begin),
+                                    "round_ms_min_med_max": [rounds[0].device_ms, med.device_ms, rounds[-1].device_ms]},
                    "rays_per_frame_mean": total_rays / steps, "ms_per_frame": total_ms / steps},
         "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 128, "d2h_bytes_per_step": nbytes,
-                "steps": e2e_steps, "ms_per_step": float(e2e_s.item()) / e2e_steps * 1e3,
-                "note": "per-step input is the 128 B camera (kernel parameters); the octree stays resident; " + {
-                    "single": "svo_render_frame_async, four frames in flight, every frame copied to pinned host memory",
-                    "per-rank": "every rank ships the tiles it rendered into ONE page-locked host frame shared by all ranks "
-                                "(svo_frame_copy_owned_tiles: 1 / world of the frame per PCIe link, stripes "
-                                f"{e2e_run if world > 1 and per_rank else 4} tile columns wide), four frames in flight, "
-                                "frame barrier behind the copies",
-                    "rank0": "tiles gathered in rank 0's HBM over NVLink, rank 0 copies every frame to pinned host memory",
-                }[e2e_mode]},
-        "gpu_launches": 3 * steps * world,       # beam pass + tile classifier + fine pass per frame and rank
+                "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "rounds": len(e2e_rounds),
+                "note": "svo_multi_render_sequence(SVO_OUTPUT_HOST): per-step input is the 128 B camera (kernel parameters), "
+                        "the octree stays resident; every frame is copied to page-locked host memory, " + (
+                            "copy engine, four frames in flight" if world == 1 else
+                            f"every GPU ships the stripes it rendered ({int(e2e_med.tile_run)} tile columns wide) into the ONE "
+                            "host frame itself (1 / N of the frame per PCIe link), four frames in flight")},
+        "gpu_launches": device_launches,
+        "gpu_launches_note": "kernels of the reported device-timed round, all GPUs (beam pass + tile classifier + fine pass "
+                             f"per frame and GPU); the e2e round launched {e2e_launches}",
         "clocks": clocks,
-        "parity": dict(parity, **({"e2e_host_frame_identical_to_single_rank": e2e_frame_identical}
-                                  if e2e_frame_identical is not None else {})),
+        "parity": parity,
         "bytes_per_ray": {"coarse_node": coarse_b_ray, "fine_node": fine_b_ray},
     }
     if roofline is not None:
@@ -861,6 +734,7 @@ def run_own(args):
     if cpu is not None:
         line["cpu_baseline"] = cpu
     emit(line)
+    multi.close()
     if world > 1:
         barrier()
         dist.destroy_process_group()

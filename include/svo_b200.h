@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define SVO_ABI_VERSION 1
+#define SVO_ABI_VERSION 2
 
 typedef enum svo_status {
     SVO_OK = 0,
@@ -119,8 +119,9 @@ typedef struct svo_tree_info {
  * the depth of the first-child chain). Walks every reachable descriptor: child blocks strictly behind their parent,
  * every descriptor, far word and leaf word inside the array, no branch deeper than the first-child chain, no node
  * reachable more often than the array has words. SVO_ERR_FORMAT + svo_last_error() name the first violation.
- * svo_tree_create_from_words and svo_tree_load_oct run it when the environment variable SVO_VALIDATE_TREES is set
- * (files from an untrusted source); subtrees are walked on all host cores (the 1.6 GB array of an 8192^3 tree: 1.9 s on 8). */
+ * svo_tree_create_from_words and svo_tree_load_oct run it BY DEFAULT before a tree is handed out (overlapped with the
+ * upload; the environment variable SVO_VALIDATE_TREES=0 opts out for trusted arrays); subtrees are walked on all host
+ * cores (the 1.6 GB array of an 8192^3 tree: 1.9 s on 8). */
 typedef struct svo_words_report {
     uint64_t descriptors;       /* reachable descriptors (Dragon: 29,156) */
     uint64_t leaves;            /* reachable leaf words (Dragon: 90,707) */
@@ -408,6 +409,66 @@ SVO_API int svo_frame_copy_owned_tiles(int device, const svo_frame_desc *desc, c
  * *device_ptr is the address kernels and copies use. */
 SVO_API int svo_host_register(int device, void *p, size_t bytes, void **device_ptr);
 SVO_API int svo_host_unregister(void *p);
+
+/* ---- several GPUs of one node, ONE process ----------------------------------------------------------------
+ * Replaces what the reference's viewer does with its strip threads: the strip set-up and thread spawn
+ * (Main.cpp:351-367) and the two-phase barrier around every frame (Main.cpp:217-219, ThreadBarrier.cpp:41-59).
+ * The node array is replicated into the HBM of every listed device; one worker thread per device enqueues that
+ * device's share of every frame (the tile columns (tx / run) % n_devices == index: beam pass of the corners next
+ * to them, tile classifier, fine pass); frames are ordered by CUDA events, across devices too -- there is no NCCL,
+ * no second process and no host-side wait inside a frame sequence. Up to four frames are in flight.
+ *   SVO_OUTPUT_DEVICE  every device's fine pass stores its finished pixels straight into a framebuffer in
+ *                      devices[0]'s HBM over NVLink (peer access; the gather is fused into the kernel); the frame
+ *                      barrier is devices[0]'s gather stream waiting for every device's frame event.
+ *   SVO_OUTPUT_HOST    every device renders its tile columns into a local framebuffer and ships them itself into
+ *                      the caller's page-locked host frame (svo_host_alloc): 1 / n_devices of the frame per PCIe
+ *                      link, no device-to-device traffic at all.
+ * A device may be listed more than once (replicas that share a GPU: how a one-GPU box exercises this path). */
+typedef struct svo_multi svo_multi;
+enum { SVO_OUTPUT_DEVICE = 0, SVO_OUTPUT_HOST = 1 };
+
+SVO_API int svo_multi_create_from_words(const uint32_t *words, uint64_t n_words, const float center[3],
+                                        const int *devices, int n_devices, svo_multi **out);
+/* VoxelOctree(const char *path), VoxelOctree.cpp:57-90, once; then replicated. */
+SVO_API int svo_multi_load_oct(const char *path, const int *devices, int n_devices, svo_multi **out);
+SVO_API int svo_multi_destroy(svo_multi *m);
+SVO_API int svo_multi_device_count(const svo_multi *m);
+/* The replica on devices[index] (owned by the handle): for svo_raymarch_batch*, svo_tree_get_info, ... */
+SVO_API svo_tree *svo_multi_tree(svo_multi *m, int index);
+
+typedef struct svo_sequence_stats {
+    uint64_t frames;
+    uint64_t coarse_rays;       /* beam rays as the reference issues them: svo_frame_layout.corners per frame */
+    uint64_t fine_rays;         /* renderTile's raymarch calls, all devices, all frames */
+    uint64_t kernel_launches;   /* kernels enqueued, all devices */
+    float device_ms;            /* SVO_OUTPUT_DEVICE: CUDA events on devices[0] around the whole sequence
+                                 * (first frame issued ... last frame gathered); SVO_OUTPUT_HOST: 0 */
+    float wall_ms;              /* host clock: call entered ... last frame complete (in HBM / in host memory) */
+    int32_t lanes;              /* frames in flight */
+    int32_t tile_run;           /* width of the devices' stripes in 8-pixel tile columns */
+} svo_sequence_stats;
+
+/* Called on the calling thread when frame `frame` is complete in host memory, before its buffer is reused. */
+typedef void (*svo_frame_callback)(void *user, int frame, const uint32_t *rgba);
+
+/* Renders cams[0 .. n_frames) back to back (the reference's renderLoop, Main.cpp:204-262, over a camera path).
+ * desc->tile_rank / tile_world are ignored (the handle deals the tiles). SVO_OUTPUT_HOST: frame k lands in
+ * host_frames[k % n_host_frames] (page-locked, width*height words each); min(4, n_host_frames) frames are in
+ * flight; on_frame (optional) sees every frame. SVO_OUTPUT_DEVICE: host_frames is ignored; the last frames stay
+ * in devices[0]'s HBM (svo_multi_device_frame). `stats` is optional. */
+SVO_API int svo_multi_render_sequence(svo_multi *m, const svo_camera *cams, int n_frames, const svo_frame_desc *desc,
+                                      int output, uint32_t *const *host_frames, int n_host_frames,
+                                      svo_frame_callback on_frame, void *user, svo_sequence_stats *stats);
+/* One frame into host memory (any host pointer; page-locked is faster): renderBatch over all strips, all devices. */
+SVO_API int svo_multi_render_frame(svo_multi *m, const svo_camera *cam, const svo_frame_desc *desc, uint32_t *rgba,
+                                   svo_frame_stats *stats);
+/* devices[0]'s framebuffer holding frame (n_frames - 1 - back), back in [0, lanes), of the last
+ * SVO_OUTPUT_DEVICE sequence; valid until the next sequence. */
+SVO_API int svo_multi_device_frame(svo_multi *m, int back, uint32_t **d_rgba);
+/* svo_raymarch_batch with the rays dealt to the devices in contiguous ranges (no exchange: results land in the
+ * caller's arrays at the rays' own indices). */
+SVO_API int svo_multi_raymarch_batch(svo_multi *m, uint64_t n, const float *o, const float *d, float ray_scale,
+                                     int flavour, uint8_t *hit, float *t, uint32_t *normal, uint64_t *voxel);
 
 /* ---- device memory + peer mapping (multi-GPU gather over NVLink) ----------- */
 

@@ -24,147 +24,13 @@
 #include "ply_io.hpp"
 #include "svo_build.cuh"
 #include "svo_kernels.cuh"
+#include "svo_capi_internal.hpp"
 #include "svo_voxelize.cuh"
 
 #include <chrono>
 #include <thread>
 
-namespace {
-
 thread_local std::string g_lastError;
-
-int fail(int status, const char *fmt, ...) {
-    char buf[1024];
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(buf, sizeof buf, fmt, ap);
-    va_end(ap);
-    g_lastError = buf;
-    return status;
-}
-
-int failCuda(cudaError_t e, const char *what) {
-    int status = (e == cudaErrorMemoryAllocation) ? SVO_ERR_OUT_OF_MEMORY
-               : (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? SVO_ERR_NO_DEVICE : SVO_ERR_CUDA;
-    return fail(status, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
-}
-
-#define SVO_CUDA(call)                                         \
-    do {                                                       \
-        cudaError_t e_ = (call);                               \
-        if (e_ != cudaSuccess) return failCuda(e_, #call);     \
-    } while (0)
-
-// Makes `device` current for the scope, restoring the caller's device after.
-struct DeviceScope {
-    int previous = -1;
-    cudaError_t error = cudaSuccess;
-    explicit DeviceScope(int device) {
-        error = cudaGetDevice(&previous);
-        if (error == cudaSuccess && previous != device) error = cudaSetDevice(device);
-    }
-    ~DeviceScope() {
-        int now = -1;
-        if (previous >= 0 && cudaGetDevice(&now) == cudaSuccess && now != previous) cudaSetDevice(previous);
-    }
-};
-
-#define SVO_DEVICE(device)                                     \
-    DeviceScope scope_(device);                                \
-    if (scope_.error != cudaSuccess) return failCuda(scope_.error, "cudaSetDevice")
-
-// Everything one (width, height, strips) configuration needs on the device. Frames cycle through a
-// ring of kRing slots (depth buffer, tile list, counters) so that the beam passes of the next frames
-// can run ahead on the tree's two high-priority internal streams while earlier fine passes are
-// still busy -- the beam pass is latency-bound (its longest ray), and with several GPUs sharing a
-// frame it would otherwise be the critical path. Host-buffer frames additionally alternate between
-// two staging framebuffers so the device->host copy of frame i overlaps the rendering of frame i+1.
-constexpr int kRing = 8;
-constexpr int kHostLanes = 4;   // host-buffer frames in flight (staging framebuffers, render streams, tickets)
-
-struct FramePlan {
-    svo::FramePlanDev dev{};
-    float *dTables = nullptr;              // dxCoarse | dyCoarse | dxFine | dyFine
-    float *dDepth[kRing] = {};             // totalCorners floats each
-    svo::TileRecord *dTiles[kRing] = {};   // totalTiles records each (worst case: every tile rendered)
-    svo::FrameCounters *dCounters[kRing] = {};
-    svo::FrameCounters *hCounters = nullptr;            // pinned, kRing entries
-    cudaEvent_t coarseDone[kRing] = {};    // beam pass of the slot finished (internal stream)
-    cudaEvent_t fineDone[kRing] = {};      // last fine pass that read the slot's depth / tile list
-    cudaEvent_t timing[kRing][4] = {};     // coarse start/end, fine start/end (stats only)
-    bool fineRecorded[kRing] = {};
-    uint64_t frameNumber = 0;
-
-    // host-buffer entry points only
-    uint32_t *dRgba[kHostLanes] = {};                   // staging framebuffers (lazy)
-    cudaEvent_t copyDone[kHostLanes] = {};              // device->host copy out of dRgba[i] finished
-    bool copyRecorded[kHostLanes] = {};
-    bool pending[kHostLanes] = {};                      // svo_render_frame_async issued, not yet waited for
-    bool pendingStats[kHostLanes] = {};
-    int pendingRing[kHostLanes] = {};
-    uint32_t pendingLaunches[kHostLanes] = {};
-    svo_frame_desc pendingDesc[kHostLanes] = {};
-    uint64_t hostFrameNumber = 0;
-
-    void destroy() {
-        if (dTables) cudaFree(dTables);
-        if (hCounters) cudaFreeHost(hCounters);
-        for (int b = 0; b < kRing; ++b) {
-            if (dDepth[b]) cudaFree(dDepth[b]);
-            if (dTiles[b]) cudaFree(dTiles[b]);
-            if (dCounters[b]) cudaFree(dCounters[b]);
-            if (coarseDone[b]) cudaEventDestroy(coarseDone[b]);
-            if (fineDone[b]) cudaEventDestroy(fineDone[b]);
-            for (int k = 0; k < 4; ++k) if (timing[b][k]) cudaEventDestroy(timing[b][k]);
-        }
-        for (int b = 0; b < kHostLanes; ++b) {
-            if (dRgba[b]) cudaFree(dRgba[b]);
-            if (copyDone[b]) cudaEventDestroy(copyDone[b]);
-        }
-        *this = FramePlan();
-    }
-};
-
-struct GrowBuffer {
-    void *ptr = nullptr;
-    size_t bytes = 0;
-    cudaError_t reserve(size_t want) {
-        if (want <= bytes) return cudaSuccess;
-        if (ptr) cudaFree(ptr);
-        ptr = nullptr;
-        bytes = 0;
-        cudaError_t e = cudaMalloc(&ptr, want);
-        if (e == cudaSuccess) bytes = want;
-        return e;
-    }
-    void release() {
-        if (ptr) cudaFree(ptr);
-        ptr = nullptr;
-        bytes = 0;
-    }
-};
-
-} // namespace
-
-struct svo_tree {
-    int device = 0;
-    uint32_t *dWords = nullptr;
-    uint64_t nWords = 0;
-    float center[3] = {0, 0, 0};
-    uint32_t depth = 0;
-    cudaStream_t stream = nullptr;          // batches; classifier + fine pass of even host-buffer frames
-    cudaStream_t stream2 = nullptr;         // ... of host-buffer frames 1 mod 4 (so that consecutive fine passes overlap)
-    cudaStream_t stream34[2] = {nullptr, nullptr};      // ... 2 and 3 mod 4
-    cudaStream_t coarseStream[2] = {nullptr, nullptr};  // beam passes, high priority, alternating per frame
-    cudaStream_t copyStream = nullptr;      // device->host frame copies
-    std::mutex mutex;
-    std::map<std::tuple<int, int, int>, FramePlan> plans;
-    GrowBuffer batchIn, batchOut;
-    GrowBuffer orderWorkspace;               // svo_raymarch_batch_device with SVO_BATCH_COHERENCE_ORDER
-    std::vector<cudaStream_t> l2WindowStreams;   // streams that already carry the access-policy window (experiment)
-
-    svo::TreeDev dev() const { return svo::TreeDev{dWords, nWords, depth}; }
-};
 
 namespace {
 
@@ -352,28 +218,46 @@ int validateWords(const uint32_t *words, uint64_t n, uint32_t maxDepth, svo_word
     return SVO_OK;
 }
 
+// On unless SVO_VALIDATE_TREES=0: a node array from a file or a caller is walked in full before a kernel may follow
+// its child pointers (the kernels size their shared-memory stack from the tree's depth and read
+// words[parent + offset] unchecked, like the reference).
 bool validationRequested() {
     const char *e = getenv("SVO_VALIDATE_TREES");
-    return e && *e && *e != '0';
+    return !(e && *e == '0');
 }
 
-int createTree(const uint32_t *words, uint64_t nWords, const float center[3], int device, svo_tree **out) {
+int createTree(const uint32_t *words, uint64_t nWords, const float center[3], int device, svo_tree **out, bool validate = true) {
     if (!words || !center || !out) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_tree_create: null argument");
     if (nWords < 2) return fail(SVO_ERR_FORMAT, "node array too small (%llu words)", (unsigned long long)nWords);
     *out = nullptr;
     uint32_t depth = 0;
     int st = measureDepth(words, nWords, depth);
     if (st != SVO_OK) return st;
-    if (validationRequested() && (st = validateWords(words, nWords, depth, nullptr)) != SVO_OK) return st;
+    // The full host-side walk (all cores) runs on this thread while a helper thread allocates and uploads the array;
+    // no kernel can see the tree before both are done, and a format error wins over a device error (so a damaged
+    // array is reported as such even on a box without a GPU).
     std::unique_ptr<svo_tree> tree;
-    if ((st = allocTree(nWords, center, device, tree)) != SVO_OK) return st;
-    tree->depth = depth;
-    SVO_DEVICE(device);
-    cudaError_t e = cudaMemcpy(tree->dWords, words, size_t(nWords)*sizeof(uint32_t), cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) {
-        svo_tree_destroy(tree.release());
-        return failCuda(e, "cudaMemcpy(node array)");
+    int upStatus = SVO_OK;
+    std::string upError;
+    std::thread uploader([&] {
+        upStatus = allocTree(nWords, center, device, tree);
+        if (upStatus == SVO_OK) {
+            DeviceScope scope(device);
+            cudaError_t e = scope.error;
+            if (e == cudaSuccess) e = cudaMemcpy(tree->dWords, words, size_t(nWords)*sizeof(uint32_t), cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) upStatus = failCuda(e, "cudaMemcpy(node array)");
+        }
+        if (upStatus != SVO_OK) upError = g_lastError;      // thread-local: carry it over to the caller's thread
+    });
+    if (validate && validationRequested()) st = validateWords(words, nWords, depth, nullptr);
+    uploader.join();
+    if (st != SVO_OK || upStatus != SVO_OK) {
+        std::string keep = st != SVO_OK ? g_lastError : upError;
+        if (tree) svo_tree_destroy(tree.release());
+        g_lastError = keep;
+        return st != SVO_OK ? st : upStatus;
     }
+    tree->depth = depth;
     *out = tree.release();
     return SVO_OK;
 }
@@ -431,6 +315,8 @@ int buildPlan(svo_tree *tree, int width, int height, int strips, FramePlan &plan
     SVO_CUDA(cudaMalloc(&plan.dTables, tables.size()*sizeof(float)));
     SVO_CUDA(cudaMemcpy(plan.dTables, tables.data(), tables.size()*sizeof(float), cudaMemcpyHostToDevice));
     SVO_CUDA(cudaMallocHost(&plan.hCounters, kRing*sizeof(svo::FrameCounters)));
+    SVO_CUDA(cudaMalloc(&plan.dFineTotal, sizeof(unsigned long long)));
+    SVO_CUDA(cudaMemset(plan.dFineTotal, 0, sizeof(unsigned long long)));
     for (int b = 0; b < kRing; ++b) {
         SVO_CUDA(cudaMalloc(&plan.dDepth[b], size_t(p.totalCorners)*sizeof(float)));
         SVO_CUDA(cudaMalloc(&plan.dTiles[b], size_t(p.totalTiles > 0 ? p.totalTiles : 1)*sizeof(svo::TileRecord)));
@@ -537,6 +423,13 @@ int enqueueFrame(svo_tree *tree, FramePlan *plan, const svo_camera *cam, const s
     svo_frame_constants c;
     svo::frameConstants(*cam, tree->center, desc->width, desc->height, desc->strips, c);
     svo::FrameConsts f = toDeviceConsts(c);
+    // a camera with a NaN / infinite entry would make every ray of the frame spin for ever (see raymarchBatchKernel)
+    {
+        const float *v = &f.posX;
+        float sum = 0.0f;
+        for (size_t i = 0; i < sizeof(svo::FrameConsts)/sizeof(float); ++i) sum += v[i] < 0 ? -v[i] : v[i];
+        if (!(sum < 3.0e38f)) return fail(SVO_ERR_INVALID_ARGUMENT, "camera matrices contain a non-finite value");
+    }
     const int b = int(plan->frameNumber++ % kRing);
     float *depth = userDepth ? userDepth : plan->dDepth[b];
     cudaStream_t cs = userDepth ? stream : tree->coarseStream[b & 1];
@@ -545,7 +438,8 @@ int enqueueFrame(svo_tree *tree, FramePlan *plan, const svo_camera *cam, const s
     uint32_t n = 0;
 
     // the slot's depth buffer, tile list and counters are free once the fine pass of kRing frames ago is done
-    if (!userDepth && plan->fineRecorded[b]) SVO_CUDA(cudaStreamWaitEvent(cs, plan->fineDone[b], 0));
+    // (also with a caller-owned depth buffer: only the depths are the caller's, the counters and the tile list are not)
+    if (plan->fineRecorded[b]) SVO_CUDA(cudaStreamWaitEvent(cs, plan->fineDone[b], 0));
     if (wantStats) SVO_CUDA(cudaEventRecord(plan->timing[b][0], cs));
     SVO_CUDA(svo::launchCoarsePass(tree->dev(), plan->dev, f, desc->flavour, depth, plan->dCounters[b], desc->tile_rank,
                                    desc->tile_world, cs));
@@ -557,7 +451,7 @@ int enqueueFrame(svo_tree *tree, FramePlan *plan, const svo_camera *cam, const s
     }
     if (wantStats) SVO_CUDA(cudaEventRecord(plan->timing[b][2], stream));
     SVO_CUDA(svo::launchClassifyTiles(plan->dev, f, depth, dRgba, desc->tile_rank, desc->tile_world, desc->pixel_stride,
-                                      plan->dTiles[b], plan->dCounters[b], stream));
+                                      plan->dTiles[b], plan->dCounters[b], plan->dFineTotal, stream));
     ++n;
     SVO_CUDA(svo::launchFinePass(tree->dev(), plan->dev, f, desc->flavour, plan->dTiles[b], plan->dCounters[b], dRgba,
                                  desc->tile_rank, desc->tile_world, desc->pixel_stride, stream));
@@ -599,6 +493,22 @@ void fillStats(const FramePlan *plan, int slot, const svo_frame_desc *desc, uint
 }
 
 } // namespace
+
+namespace svo_detail {   // what svo_multi.cu uses of the above
+int checkDesc(const svo_frame_desc *desc) { return ::checkDesc(desc); }
+int getPlan(svo_tree *tree, int width, int height, int strips, FramePlan **out) { return ::getPlan(tree, width, height, strips, out); }
+int enqueueFrame(svo_tree *tree, FramePlan *plan, const svo_camera *cam, const svo_frame_desc *desc, uint32_t *dRgba,
+                 float *userDepth, cudaStream_t stream, bool wantStats, uint32_t *launches, int *slotOut) {
+    return ::enqueueFrame(tree, plan, cam, desc, dRgba, userDepth, stream, wantStats, launches, slotOut);
+}
+void fillStats(const FramePlan *plan, int slot, const svo_frame_desc *desc, uint32_t launches, svo_frame_stats *stats) {
+    ::fillStats(plan, slot, desc, launches, stats);
+}
+void planGeometry(int width, int height, int strips, svo::FramePlanDev &p) { ::planGeometry(width, height, strips, p); }
+int createTreeOnDevice(const uint32_t *words, uint64_t nWords, const float center[3], int device, bool validate, svo_tree **out) {
+    return ::createTree(words, nWords, center, device, out, validate);
+}
+} // namespace svo_detail
 
 extern "C" {
 

@@ -46,9 +46,18 @@ raymarchBatchKernel(const uint32_t *__restrict__ octree, uint64_t n, const float
     float ox = __ldg(o + 3*i), oy = __ldg(o + 3*i + 1), oz = __ldg(o + 3*i + 2);
     float dx = __ldg(d + 3*i), dy = __ldg(d + 3*i + 1), dz = __ldg(d + 3*i + 2);
 
+    // A ray with a NaN or infinite component never leaves the loop (every comparison is false, so no axis ever
+    // steps; the reference spins the same way, VoxelOctree.cpp:252-339, but on a CPU thread, not on a GPU that the
+    // caller then cannot get back). Such a ray is reported as a miss: it is swapped for one that starts behind the
+    // volume and leaves it in two trips, so the warp stays whole for the traversal's barrier.
+    const float magnitude = fabsf(ox) + fabsf(oy) + fabsf(oz) + fabsf(dx) + fabsf(dy) + fabsf(dz);
+    const bool finite = magnitude < __int_as_float(0x7f800000);
+    if (!finite) { ox = oy = oz = 3.0f; dx = dy = dz = 1.0f; }
+
     float tHit = kTreeMiss;
     uint64_t vox;
     int code = raymarch<FAST, LOD, IdxT, kBatchThreads>(octree, ox, oy, oz, dx, dy, dz, rayScale, stack, tHit, vox);
+    if (!finite) { code = kMiss; tHit = kTreeMiss; }
     if (code == kMiss) vox = ~uint64_t(0);
     uint32_t material = code == kHitLeaf ? ldNode(octree + vox) : 0u;   // VoxelOctree.cpp:282
 
@@ -126,7 +135,8 @@ coarsePassKernel(const uint32_t *__restrict__ octree, FramePlanDev plan, FrameCo
 __global__ void __launch_bounds__(kClassifyThreads)
 classifyTilesKernel(FramePlanDev plan, float beamBias, const float *__restrict__ depth, uint32_t *__restrict__ rgba,
                     int tileRank, int tileWorld, int tileRun, int ownedCols, int ownedTiles, int pixelStride,
-                    TileRecord *__restrict__ tiles, FrameCounters *__restrict__ counters) {
+                    TileRecord *__restrict__ tiles, FrameCounters *__restrict__ counters,
+                    unsigned long long *__restrict__ fineRaysTotal) {
     int k = blockIdx.x*blockDim.x + threadIdx.x;
     bool active = k < ownedTiles;
     bool rendered = false;
@@ -161,6 +171,7 @@ classifyTilesKernel(FramePlanDev plan, float beamBias, const float *__restrict__
     if (lane == 0 && mask) {
         base = atomicAdd(&counters->tilesRendered, unsigned(__popc(mask)));
         atomicAdd(&counters->fineRays, (unsigned long long)pixels);
+        if (fineRaysTotal) atomicAdd(fineRaysTotal, (unsigned long long)pixels);   // running total over a frame sequence
     }
     base = __shfl_sync(0xffffffffu, base, 0);
     if (rendered) {
@@ -172,7 +183,7 @@ classifyTilesKernel(FramePlanDev plan, float beamBias, const float *__restrict__
         tiles[base + __popc(mask & ((1u << lane) - 1u))] = r;
     } else if (active) {
         // skipped tile: its pixels keep the strip memset's zero (Main.cpp:165)
-        if (w == 8 && (plan.width & 3) == 0) {
+        if (w == 8 && (plan.width & 3) == 0 && (reinterpret_cast<uintptr_t>(rgba) & 15) == 0) {
             for (int r = 0; r < h; ++r) {
                 uint4 *row = reinterpret_cast<uint4 *>(rgba + size_t(y0 + r)*size_t(plan.width) + x0);
                 row[0] = make_uint4(0, 0, 0, 0);
@@ -454,12 +465,12 @@ cudaError_t launchCoarsePass(const TreeDev &tree, const FramePlanDev &plan, cons
 
 cudaError_t launchClassifyTiles(const FramePlanDev &plan, const FrameConsts &consts, const float *depth,
                                 uint32_t *rgba, int tileRank, int tileWorld, int pixelStride, TileRecord *tiles,
-                                FrameCounters *counters, cudaStream_t stream) {
+                                FrameCounters *counters, unsigned long long *fineRaysTotal, cudaStream_t stream) {
     int owned = ownedTiles(plan, tileRank, tileWorld);
     if (owned <= 0) return cudaSuccess;
     classifyTilesKernel<<<(owned + kClassifyThreads - 1)/kClassifyThreads, kClassifyThreads, 0, stream>>>(
         plan, consts.beamBias, depth, rgba, tileRank, tileWorld, tileRunLength(tileWorld),
-        ownedCols(plan, tileRank, tileWorld), owned, pixelStride > 1 ? pixelStride : 1, tiles, counters);
+        ownedCols(plan, tileRank, tileWorld), owned, pixelStride > 1 ? pixelStride : 1, tiles, counters, fineRaysTotal);
     return cudaGetLastError();
 }
 

@@ -80,7 +80,7 @@ cudaError_t launchCoarsePass(const TreeDev &tree, const FramePlanDev &plan, cons
 // Main.cpp:165), rendered tiles are appended to `tiles` (capacity = owned tiles) and counted.
 cudaError_t launchClassifyTiles(const FramePlanDev &plan, const FrameConsts &consts, const float *depth,
                                 uint32_t *rgba, int tileRank, int tileWorld, int pixelStride, TileRecord *tiles,
-                                FrameCounters *counters, cudaStream_t stream);
+                                FrameCounters *counters, unsigned long long *fineRaysTotal, cudaStream_t stream);
 
 // Fine pass over the tile list (grid covers the worst case; blocks past the list length exit).
 // pixelStride > 1: renderTile's preview mode (Main.cpp:101-106), one ray per stride x stride block of a tile.

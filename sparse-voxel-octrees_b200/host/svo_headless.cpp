@@ -4,8 +4,12 @@
 //
 //   svo_headless <in.oct> [--size WxH] [--strips N] [--frames K] [--radius R] [--pitch P]
 //                [--yaw0 Y] [--yaw-step S] [--validation] [--preview] [--events script]
-//                [--out prefix] [--png prefix] [--raw file|-] [--check]
+//                [--out prefix] [--png prefix] [--raw file|-] [--check] [--gpus N]
 //
+// --gpus N (N > 1) renders on devices 0..N-1 of this node from this one process (svo_multi_*: the node array is
+// replicated, tile columns are dealt to the devices, every device ships its own pixels to the host frame; the
+// reference's strip threads and frame barrier, Main.cpp:351-367, :217-219); the orbit is rendered as ONE pipelined
+// sequence (four frames in flight) and every finished frame is written by a callback.
 // --check decodes the file and walks its whole node array on the host (svo_words_validate: every pointer in bounds, no
 // cycles, no branch deeper than the kernels' stack), prints the counts and exits; no GPU is needed.
 // --out writes prefix_<k>.ppm, --png prefix_<k>.png (8-bit RGB, host/png_write.hpp) for every frame.
@@ -50,6 +54,26 @@ static void writePpm(const std::string &path, const uint32_t *rgba, int w, int h
     fclose(fp);
 }
 
+struct FrameSink {      // what happens to a finished host frame: PPM / PNG files, the raw RGB24 stream
+    std::string out, png;
+    FILE *rawFile = 0;
+    std::vector<unsigned char> rgb;
+    int w = 0, h = 0;
+    void write(int k, const uint32_t *rgba) {
+        if (!out.empty()) writePpm(out + "_" + std::to_string(k) + ".ppm", rgba, w, h);
+        if (!png.empty() && !svo_png::writeRgb(png + "_" + std::to_string(k) + ".png", rgba, w, h))
+            throw std::runtime_error("cannot write " + png + "_" + std::to_string(k) + ".png");
+        if (rawFile) {
+            for (size_t p = 0; p < size_t(w)*h; ++p) {
+                rgb[3*p] = rgba[p] & 255; rgb[3*p + 1] = (rgba[p] >> 8) & 255; rgb[3*p + 2] = (rgba[p] >> 16) & 255;
+            }
+            if (fwrite(rgb.data(), 1, rgb.size(), rawFile) != rgb.size()) throw std::runtime_error("short write on the raw stream");
+        }
+    }
+};
+
+static void sinkCallback(void *user, int frame, const uint32_t *rgba) { static_cast<FrameSink *>(user)->write(frame, rgba); }
+
 static std::vector<svo_viewer_event> readEventScript(const std::string &path) {
     FILE *fp = fopen(path.c_str(), "r");
     if (!fp) throw std::runtime_error("cannot read " + path);
@@ -79,7 +103,7 @@ static std::vector<svo_viewer_event> readEventScript(const std::string &path) {
 int main(int argc, char **argv) {
     if (argc < 2) {
         fprintf(stderr, "usage: %s <in.oct> [--size WxH] [--strips N] [--frames K] [--radius R] [--pitch P] [--yaw0 Y] "
-                        "[--yaw-step S] [--validation] [--preview] [--events script] [--out prefix] [--png prefix] [--raw file|-] [--check]\n"
+                        "[--yaw-step S] [--validation] [--preview] [--events script] [--out prefix] [--png prefix] [--raw file|-] [--check] [--gpus N]\n"
                         "       %s -builder [--resolution r --mode m] <in.ply | in.voxel> <out.oct>\n", argv[0], argv[0]);
         return 2;
     }
@@ -112,7 +136,7 @@ int main(int argc, char **argv) {
     }
     int w = 1280, h = 720, strips = 16, frames = 1, flavour = SVO_FLAVOUR_FAST; /* Main.cpp:57-60 defaults */
     float radius = 1.0f, pitch = 0.0f, yaw0 = 0.0f, yawStep = 3.6f;
-    int stride = 1;
+    int stride = 1, gpus = 1;
     std::string out, raw, events, png;
     bool check = false;
     for (int i = 2; i < argc; ++i) {
@@ -131,6 +155,7 @@ int main(int argc, char **argv) {
         else if (a == "--raw") raw = next();
         else if (a == "--png") png = next();
         else if (a == "--check") check = true;
+        else if (a == "--gpus") gpus = atoi(next());
         else if (a == "--events") events = next();
         else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
@@ -155,6 +180,62 @@ int main(int argc, char **argv) {
     try {
         std::vector<svo_viewer_event> script;
         if (!events.empty()) script = readEventScript(events);     // before anything touches the GPU: a bad script fails fast
+        if (gpus > 1) {
+            // several GPUs, one process: the whole orbit (or every frame of the replayed session) through svo_multi_*
+            FILE *info = raw == "-" ? stderr : stdout;
+            FrameSink sink;
+            sink.out = out; sink.png = png; sink.w = w; sink.h = h;
+            sink.rawFile = raw.empty() ? 0 : raw == "-" ? stdout : fopen(raw.c_str(), "wb");
+            if (!raw.empty() && !sink.rawFile) throw std::runtime_error("cannot write " + raw);
+            sink.rgb.resize(raw.empty() ? 0 : size_t(w)*h*3);
+            std::vector<int> devices;
+            for (int d = 0; d < gpus; ++d) devices.push_back(d);
+            svo_multi *multi = 0;
+            if (svo_multi_load_oct(argv[1], devices.data(), gpus, &multi) != SVO_OK) throw std::runtime_error(svo_last_error());
+            svo_tree_info ti;
+            svo_tree_get_info(svo_multi_tree(multi, 0), &ti);
+            fprintf(info, "loaded %s on %d GPUs: %llu words, depth %u\n", argv[1], gpus, (unsigned long long)ti.n_words, ti.depth);
+            std::vector<svo_camera> path;
+            std::vector<int> strideOf;
+            if (events.empty()) {
+                for (int k = 0; k < frames; ++k) { svo_camera c; svo_orbit_camera(pitch, yaw0 + yawStep*k, radius, &c); path.push_back(c); strideOf.push_back(stride); }
+            } else {
+                svo_viewer_state viewer;
+                svo_viewer_init(&viewer);
+                path.push_back(viewer.camera); strideOf.push_back(1);
+                for (size_t e = 0; e < script.size();) {
+                    int action = SVO_VIEWER_WAIT;
+                    while (action == SVO_VIEWER_WAIT && e < script.size()) action = svo_viewer_feed(&viewer, &script[e++]);
+                    if (action != SVO_VIEWER_FRAME) break;
+                    path.push_back(viewer.camera); strideOf.push_back(viewer.preview ? 3 : 1);
+                }
+            }
+            uint32_t *ring[4] = {0, 0, 0, 0};
+            for (int i = 0; i < 4; ++i)
+                if (svo_host_alloc(size_t(w)*h*4, reinterpret_cast<void **>(&ring[i])) != SVO_OK) throw std::runtime_error(svo_last_error());
+            double totalMs = 0.0;
+            unsigned long long rays = 0;
+            // runs of frames with the same pixel stride go out as one pipelined sequence each
+            for (size_t first = 0; first < path.size();) {
+                size_t last = first;
+                while (last < path.size() && strideOf[last] == strideOf[first]) ++last;
+                svo_frame_desc desc = {w, h, strips, flavour, 0, 1, strideOf[first], 0};
+                svo_sequence_stats st;
+                struct Shifted { FrameSink *sink; int base; } shifted = {&sink, int(first)};
+                auto cb = [](void *user, int frame, const uint32_t *rgba) { Shifted *s = static_cast<Shifted *>(user); sinkCallback(s->sink, s->base + frame, rgba); };
+                if (svo_multi_render_sequence(multi, path.data() + first, int(last - first), &desc, SVO_OUTPUT_HOST, ring, 4, cb, &shifted, &st) != SVO_OK)
+                    throw std::runtime_error(svo_last_error());
+                totalMs += st.wall_ms;
+                rays += st.coarse_rays + st.fine_rays;
+                first = last;
+            }
+            fprintf(info, "%zu frame(s) %dx%d, %d strips, %d GPUs: %.3f ms/frame end to end (host buffers, pipelined), %.1f Mrays/s\n",
+                    path.size(), w, h, strips, gpus, totalMs/double(path.size()), double(rays)/(totalMs*1e3));
+            if (sink.rawFile && sink.rawFile != stdout) fclose(sink.rawFile);
+            for (int i = 0; i < 4; ++i) svo_host_free(ring[i]);
+            svo_multi_destroy(multi);
+            return 0;
+        }
         VoxelOctree tree(argv[1]);
         FILE *info = raw == "-" ? stderr : stdout;
         FILE *rawFile = raw.empty() ? 0 : raw == "-" ? stdout : fopen(raw.c_str(), "wb");

@@ -99,6 +99,20 @@ class FrameStats(C.Structure):
         return int(self.coarse_rays + self.fine_rays)
 
 
+class SequenceStats(C.Structure):
+    _fields_ = [("frames", C.c_uint64), ("coarse_rays", C.c_uint64), ("fine_rays", C.c_uint64),
+                ("kernel_launches", C.c_uint64), ("device_ms", C.c_float), ("wall_ms", C.c_float),
+                ("lanes", C.c_int32), ("tile_run", C.c_int32)]
+
+    @property
+    def rays(self):
+        return int(self.coarse_rays + self.fine_rays)
+
+
+FRAME_CALLBACK = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_void_p)
+OUTPUT_DEVICE, OUTPUT_HOST = 0, 1
+
+
 class FrameLayout(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("n_strips", "strip_rows", "tiles_x", "tiles_y_full", "tiles_y_last",
                                          "tile_cols", "tiles", "corners")]
@@ -198,6 +212,16 @@ def lib():
         "svo_ipc_export": (i32, [i32, vp, vp]),
         "svo_ipc_open": (i32, [i32, vp, P(vp)]),
         "svo_ipc_close": (i32, [i32, vp]),
+        "svo_multi_create_from_words": (i32, [vp, u64, P(f32), P(i32), i32, P(vp)]),
+        "svo_multi_load_oct": (i32, [C.c_char_p, P(i32), i32, P(vp)]),
+        "svo_multi_destroy": (i32, [vp]),
+        "svo_multi_device_count": (i32, [vp]),
+        "svo_multi_tree": (vp, [vp, i32]),
+        "svo_multi_render_sequence": (i32, [vp, P(Camera), i32, P(FrameDesc), i32, P(vp), i32, FRAME_CALLBACK, vp,
+                                            P(SequenceStats)]),
+        "svo_multi_render_frame": (i32, [vp, P(Camera), P(FrameDesc), vp, P(FrameStats)]),
+        "svo_multi_device_frame": (i32, [vp, i32, P(vp)]),
+        "svo_multi_raymarch_batch": (i32, [vp, u64, vp, vp, f32, i32, vp, vp, vp, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)
@@ -602,7 +626,101 @@ class VoxelOctree:
 
     def close(self):
         if getattr(self, "_h", None):
-            lib().svo_tree_destroy(self._h)
+            if not getattr(self, "_borrowed", False):     # a MultiOctree's replica belongs to that handle
+                lib().svo_tree_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MultiOctree:
+    """svo_multi: the node array replicated on several GPUs of this node, driven from this one process (the
+    reference's strip threads + frame barrier, Main.cpp:351-367, :217-219). A device may be listed twice."""
+
+    def __init__(self, path=None, *, words=None, center=None, devices=(0,)):
+        self._h = None
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        if path is not None:
+            _check(lib().svo_multi_load_oct(str(path).encode(), devs, len(devices), C.byref(h)))
+        else:
+            words = np.ascontiguousarray(words, np.uint32)
+            _check(lib().svo_multi_create_from_words(_ptr(words), words.size, _f3(center), devs, len(devices), C.byref(h)))
+        self._h = h
+        self.devices = tuple(int(d) for d in devices)
+
+    @property
+    def n_devices(self):
+        return int(lib().svo_multi_device_count(self._h))
+
+    def tree(self, index=0) -> "VoxelOctree":
+        """The replica on devices[index] as a VoxelOctree that does not own its handle."""
+        h = lib().svo_multi_tree(self._h, int(index))
+        if not h:
+            _check(1)
+        t = VoxelOctree(_handle=C.c_void_p(h))
+        t._borrowed = True
+        return t
+
+    def _desc(self, width, height, strips, flavour, pixel_stride=0):
+        return FrameDesc(int(width), int(height), int(strips), int(flavour), 0, 1, int(pixel_stride), 0)
+
+    def render_frame(self, cam: Camera, width, height, strips=16, flavour=FLAVOUR_VALIDATION, rgba=None, pixel_stride=0):
+        """-> (rgba uint32[H, W], FrameStats): renderBatch over all strips, all devices, into host memory."""
+        if rgba is None:
+            rgba = np.zeros((height, width), np.uint32)
+        st = FrameStats()
+        d = self._desc(width, height, strips, flavour, pixel_stride)
+        _check(lib().svo_multi_render_frame(self._h, C.byref(cam), C.byref(d), _ptr(rgba), C.byref(st)))
+        return rgba, st
+
+    def render_sequence(self, cams, width, height, strips=16, flavour=FLAVOUR_FAST, output=OUTPUT_DEVICE, host_frames=None,
+                        on_frame=None):
+        """Renders the camera path back to back (up to four frames in flight). OUTPUT_HOST: frame k lands in
+        host_frames[k % len(host_frames)] (page-locked numpy arrays, e.g. PinnedArray.array); on_frame(k, array)
+        is called for every finished frame. -> SequenceStats."""
+        n = len(cams)
+        arr = (Camera * n)(*cams)
+        d = self._desc(width, height, strips, flavour)
+        st = SequenceStats()
+        frames, nh = None, 0
+        if output == OUTPUT_HOST:
+            nh = len(host_frames)
+            frames = (C.c_void_p * nh)(*[f.ctypes.data for f in host_frames])
+        if on_frame is not None:
+            def _cb(user, k, ptr, _frames=host_frames, _nh=nh):
+                on_frame(int(k), _frames[int(k) % _nh])
+            cb = FRAME_CALLBACK(_cb)
+        else:
+            cb = C.cast(None, FRAME_CALLBACK)
+        _check(lib().svo_multi_render_sequence(self._h, arr, n, C.byref(d), int(output), frames, nh, cb, None, C.byref(st)))
+        return st
+
+    def device_frame(self, width, height, back=0):
+        """Frame (last - back) of the last OUTPUT_DEVICE sequence, copied from devices[0]'s HBM -> uint32[H, W]."""
+        p = C.c_void_p()
+        _check(lib().svo_multi_device_frame(self._h, int(back), C.byref(p)))
+        out = np.empty((height, width), np.uint32)
+        _check(lib().svo_device_to_host(self.devices[0], _ptr(out), p, out.nbytes))
+        return out
+
+    def raymarch_batch(self, o, d, ray_scale=0.0, flavour=FLAVOUR_VALIDATION, want_voxel=True):
+        o = np.ascontiguousarray(o, np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(d, np.float32).reshape(-1, 3)
+        n = o.shape[0]
+        out = dict(hit=np.zeros(n, np.uint8), t=np.zeros(n, np.float32), normal=np.zeros(n, np.uint32),
+                   voxel=np.zeros(n, np.uint64) if want_voxel else None)
+        _check(lib().svo_multi_raymarch_batch(self._h, n, _ptr(o), _ptr(d), float(ray_scale), int(flavour), _ptr(out["hit"]),
+                                              _ptr(out["t"]), _ptr(out["normal"]), _ptr(out["voxel"])))
+        return out
+
+    def close(self):
+        if self._h is not None:
+            lib().svo_multi_destroy(self._h)
             self._h = None
 
     def __del__(self):

@@ -18,7 +18,7 @@ def test_library_exports_every_declared_symbol(pysvo):
     for name in sorted(declared):
         assert hasattr(L, name), f"{name} declared in svo_b200.h but not exported"
     assert declared == set(L._svo_symbols), "pysvo binds a different symbol set than the header declares"
-    assert L.svo_abi_version() == 1
+    assert L.svo_abi_version() == 2
 
 
 def test_no_device_fails_loudly(pysvo, dragon_words):
@@ -473,7 +473,7 @@ def test_headless_png_writer(tmp_path):
 def test_words_validate(pysvo, dragon_words, monkeypatch):
     """svo_words_validate: the full host-side walk of a node array. The sample tree gives the survey's counts and
     accounts for every word; damaged arrays are rejected with the first violation named (and never crash the walk);
-    with SVO_VALIDATE_TREES set the tree constructors run it before anything is uploaded."""
+    the tree constructors run it by default (SVO_VALIDATE_TREES=0 opts out) before a tree is handed out."""
     words, center = dragon_words
     rep = pysvo.words_validate(words)
     assert (rep.descriptors, rep.leaves, rep.far_words, rep.depth) == (29156, 90707, 24, 8)
@@ -536,17 +536,17 @@ def test_words_validate(pysvo, dragon_words, monkeypatch):
             outcomes[False] += 1
     assert outcomes[True] > 0 and outcomes[False] > 0                           # damaged leaf words pass, damaged descriptors mostly do not
     if pysvo.device_count() < 1:
-        # the constructors: validation (when asked for) comes before the device is needed. The damage is off the
-        # first-child chain, so nothing but the full walk can see it.
+        # the constructors validate by default (SVO_VALIDATE_TREES=0 opts out), and a format error wins over the
+        # missing device. The damage is off the first-child chain, so nothing but the full walk can see it.
         bad = words.copy(); bad[other] |= np.uint32((int(bad[other]) >> 8) & 0xFF)
-        monkeypatch.setenv("SVO_VALIDATE_TREES", "1")
+        monkeypatch.delenv("SVO_VALIDATE_TREES", raising=False)
         with pytest.raises(pysvo.SvoError) as e:
             pysvo.VoxelOctree(words=bad, center=center)
         assert e.value.status == 3
         with pytest.raises(pysvo.SvoError) as e:
             pysvo.VoxelOctree(words=words, center=center)
         assert e.value.status == 6
-        monkeypatch.delenv("SVO_VALIDATE_TREES")
+        monkeypatch.setenv("SVO_VALIDATE_TREES", "0")
         with pytest.raises(pysvo.SvoError) as e:
             pysvo.VoxelOctree(words=bad, center=center)
         assert e.value.status == 6

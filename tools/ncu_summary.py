@@ -1,7 +1,11 @@
 #!/usr/bin/env python
 """Summarises an .ncu-rep (raw page) into the handful of counters DESIGN.md / bench.py quote.
 
-    python tools/ncu_summary.py gpurun_out/r01_fine_c2_4k.ncu-rep [--json out.json]
+    python tools/ncu_summary.py gpurun_out/r01_fine_c2_4k.ncu-rep [--json out.json] [--traffic WORKLOAD [--kernel REGEX]]
+
+--traffic WORKLOAD writes the capture's DRAM traffic and issue counters into profiles/traffic.json under that workload
+name, stamped with the hash of the kernel sources and the commit it was taken at: bench.py quotes the entry only while
+the kernel sources still hash to the same value (a capture of older code is withheld, not reported stale).
 """
 import csv
 import io
@@ -26,7 +30,16 @@ WANT = [
     "smsp__pcsamp_warps_issue_stalled_math_pipe_throttle", "smsp__pcsamp_warps_issue_stalled_no_instructions",
     "smsp__pcsamp_warps_issue_stalled_dispatch_stall", "smsp__pcsamp_warps_issue_stalled_lg_throttle",
     "smsp__pcsamp_warps_issue_stalled_mio_throttle", "smsp__pcsamp_warps_issue_stalled_barrier",
+    # the L1 / L2 side of the "HBM / L2 roofline", and the pipes the loop issues to
+    "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__t_bytes.sum", "lts__t_bytes.sum", "lts__t_sectors.sum", "l1tex__t_sectors.sum",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fmaheavy.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active",
+    "smsp__inst_executed.avg.per_cycle_active", "sm__cycles_active.avg",
 ]
+# plus anything about NVLink / peer / system-memory apertures (multi-GPU gather, zero-copy host frames)
+WANT_SUBSTRINGS = ("nvlrx", "nvltx", "nvlink", "aperture_peer", "aperture_sysmem", "pcie")
 
 
 def summarise(path):
@@ -37,7 +50,7 @@ def summarise(path):
     for vals in rows[2:]:
         d = {"kernel": vals[hdr.index("Kernel Name")]}
         for i, h in enumerate(hdr):
-            if h in WANT:
+            if h in WANT or any(x in h for x in WANT_SUBSTRINGS):
                 try:
                     v = float(vals[i].replace(",", ""))
                 except ValueError:
@@ -54,6 +67,46 @@ if __name__ == "__main__":
             json.dump(res, fp, indent=1)
     for d in res:
         print(d["kernel"][:110])
-        for k in WANT:
+        for k in list(WANT) + sorted(k for k in d if k not in WANT and k != "kernel"):
             if k in d:
                 print(f"  {k:72s} {d[k]['value']:>16} {d[k]['unit']}")
+    if "--traffic" in sys.argv:
+        import hashlib
+        import re
+        from pathlib import Path
+        root = Path(__file__).resolve().parent.parent
+        workload = sys.argv[sys.argv.index("--traffic") + 1]
+        pattern = sys.argv[sys.argv.index("--kernel") + 1] if "--kernel" in sys.argv else "finePass"
+        pick = [d for d in res if re.search(pattern, d["kernel"])]
+        if not pick:
+            raise SystemExit(f"no kernel matching {pattern!r} in {sys.argv[1]}")
+        d = pick[0]
+        g = lambda k: d[k]["value"] if k in d else None  # noqa: E731
+        to_ms = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
+        h = hashlib.sha256()
+        for name in ("svo_traverse.cuh", "svo_kernels.cu", "svo_kernels.cuh"):
+            h.update((root / "sparse-voxel-octrees_b200" / "csrc" / name).read_bytes())
+        commit = subprocess.run(["git", "-C", str(root), "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+        entry = {
+            "source": f"{sys.argv[1]} (ncu --set full --clock-control none, one launch)", "kernel": d["kernel"][:80],
+            "kernel_source_hash": h.hexdigest()[:16], "commit": commit or None,
+            "dram_bytes_per_launch": (g("dram__bytes_read.sum") or 0) + (g("dram__bytes_write.sum") or 0),
+            "dram_bytes_read": g("dram__bytes_read.sum"), "dram_bytes_write": g("dram__bytes_write.sum"),
+            "l1_hit_pct": g("l1tex__t_sector_hit_rate.pct"), "l2_hit_pct": g("lts__t_sector_hit_rate.pct"),
+            "l1_throughput_pct": g("l1tex__throughput.avg.pct_of_peak_sustained_elapsed"),
+            "l2_throughput_pct": g("lts__throughput.avg.pct_of_peak_sustained_elapsed"),
+            "l2_bytes": g("lts__t_bytes.sum"), "l1_bytes": g("l1tex__t_bytes.sum"),
+            "issue_active_pct": g("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+            "threads_per_instruction": g("smsp__thread_inst_executed_per_inst_executed.ratio"),
+            "warp_instructions": g("smsp__inst_executed.sum"),
+            "pipe_alu_pct": g("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+            "pipe_fma_pct": g("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+            "pipe_lsu_pct": g("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"),
+            "ncu_duration_ms": (g("gpu__time_duration.sum") or 0) * to_ms.get(d.get("gpu__time_duration.sum", {}).get("unit", "ns"), 1e-6),
+            "sm_cycles_elapsed": g("sm__cycles_elapsed.max"),
+        }
+        tp = root / "profiles" / "traffic.json"
+        table = json.loads(tp.read_text()) if tp.exists() else {}
+        table[workload] = entry
+        tp.write_text(json.dumps(table, indent=1) + "\n")
+        print(f"profiles/traffic.json[{workload}] <- {entry['kernel'][:50]} at {entry['commit']} ({entry['kernel_source_hash']})")
