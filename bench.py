@@ -235,13 +235,16 @@ def reference_sample(w, steps, warmup, budget_s, strips=None, ref=None, tree=Non
     mv = [ref.orbit_camera(*c) for c in cams]
     models = np.stack([m for m, _ in mv])
     views = np.stack([v for _, v in mv])
-    # size the per-step sample: probe one frame on every 8th strip, then pick the modulo
+    # size the sample: one whole frame as a probe (also the first warm-up), then as many of the requested steps as fit
+    # the budget; strips are only sub-sampled (every modulo-th strip, which also idles threads) when a single frame
+    # does not fit
     modulo = 1
     t0 = time.perf_counter()
-    ref.render_frames(h, w["width"], H, strips, models[:1], views[:1], threads=threads, strip_modulo=min(8, strips))
-    probe = (time.perf_counter() - t0) * min(8, strips)
-    while modulo < 64 and probe * (steps + warmup) / modulo > budget_s and strips // (modulo * 2) >= 1:
+    ref.render_frames(h, w["width"], H, strips, models[:1], views[:1], threads=threads)
+    probe = time.perf_counter() - t0
+    while modulo < 64 and probe * (2 + warmup) / modulo > budget_s and strips // (modulo * 2) >= 1:
         modulo *= 2
+    steps = max(2, min(steps, int(budget_s * modulo / max(probe, 1e-6)) - warmup))
     rgba, _, secs = ref.render_frames(h, w["width"], H, strips, models[:warmup] if warmup else models[:1],
                                       views[:warmup] if warmup else views[:1], threads=threads, strip_modulo=modulo)
     total_rays = 0
@@ -328,6 +331,8 @@ def run_own_ao(args, w):
     flavour = pysvo.FLAVOUR_VALIDATION if args.validation else pysvo.FLAVOUR_FAST
     if not os.environ.get("SVO_BENCH_NO_COHERENCE_ORDER"):     # (experiment switch, never set by default)
         flavour |= pysvo.BATCH_COHERENCE_ORDER               # direction-binned thread order, inside the timed call
+    if not os.environ.get("SVO_BENCH_NO_LANE_REFILL"):        # (experiment switch, never set by default)
+        flavour |= pysvo.BATCH_LANE_REFILL                   # persistent warps, finished lanes take the next rays
     ao_o, ao_d = ao_workload_rays(w, tree, words, center)
     n_total = ao_o.shape[0]
     lo, hi = n_total * rank // world, n_total * (rank + 1) // world
@@ -421,11 +426,12 @@ def run_own_ao(args, w):
                        "flavour": "validation" if args.validation else "fast",
                        "thread_order": "direction-binned (SVO_BATCH_COHERENCE_ORDER: key pass + one 6-bit radix pass "
                                        "inside every timed call)" if flavour & pysvo.BATCH_COHERENCE_ORDER else "submission order",
+                       "lane_refill": bool(flavour & pysvo.BATCH_LANE_REFILL),
                        "l2": f"no flush: ray + result arrays {n_total * 41 / 1e6:.0f} MB per step exceed the 126 MB L2",
                        "parallelism": "rays sharded contiguously over ranks, octree replicated" if world > 1 else "single GPU"},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": n_total * 24, "d2h_bytes_per_step": n_total * 9,
                     "steps": e2e_steps, "note": "svo_raymarch_batch with pinned host arrays: 2 Mi-ray chunks alternate between two streams"},
-            "gpu_launches": steps * world * (1 + (4 if flavour & pysvo.BATCH_COHERENCE_ORDER else 0)),
+            "gpu_launches": steps * world * (1 + (3 if flavour & pysvo.BATCH_COHERENCE_ORDER else 0)),
             "clocks": sampler.summary(t_begin, t_end),
             "parity": {"identical_rays_fast_vs_oracle": identical, "sample": sample},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -546,6 +552,9 @@ def run_own(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=idle)
         return float(t.item())
 
+    # GPUs rendering every frame: the torchrun world size, or --gpus when launched as a plain process (no NCCL then:
+    # the frame barrier is the library's, CUDA events across devices)
+    n_dev = world if world > 1 else max(1, min(args.gpus, pysvo.device_count()))
     steps = args.steps if args.steps is not None else 300
     warmup = max(args.warmup if args.warmup is not None else 10, 3)
     if rank != 0:
@@ -561,7 +570,7 @@ def run_own(args):
     ensure_scene(w, 0, lambda: None)
     W, H = w["width"], w["height"]
     flavour = pysvo.FLAVOUR_VALIDATION if args.validation else pysvo.FLAVOUR_FAST
-    multi = pysvo.MultiOctree(w["path"], devices=tuple(range(world)))
+    multi = pysvo.MultiOctree(w["path"], devices=tuple(range(n_dev)))
     tree = multi.tree(0)
     cams = [pysvo.orbit_camera(*c) for c in cameras(pysvo, w, ORBIT)]
     path = lambda first, count: [cams[k % ORBIT] for k in range(first, first + count)]  # noqa: E731
@@ -612,7 +621,7 @@ def run_own(args):
     from oracle.pyoracle import Port
     port = Port()
     words, center = pysvo.oct_read(w["path"])
-    roof_cams = [0, 25] if world == 1 else [0]
+    roof_cams = [0, 25] if n_dev == 1 else [0]
     parity = {}
     cam = cams[k_last % ORBIT]
     f = port.frame_constants(np.array(cam.model[:], np.float32), np.array(cam.view[:], np.float32), center, W, H, STRIPS)
@@ -624,7 +633,7 @@ def run_own(args):
     parity["fast_identical_pixels"] = float((fast == want).mean())
     parity["oracle_rays"] = int(cc.rays + cf.rays)
     parity["gpu_rays"] = int(vst.coarse_rays + vst.fine_rays)
-    if world > 1:
+    if n_dev > 1:
         alone, _, _ = tree.render_frame(cam, W, H, strips=STRIPS, flavour=flavour)
         parity["e2e_host_frame_identical_to_single_rank"] = bool(np.array_equal(alone, last_host))
     coarse_b_ray = 4.0 * cc.words / max(cc.rays, 1)
@@ -635,7 +644,7 @@ def run_own(args):
     # svo_frame_stats.fine_ms), both measured in this run
     peak, peak_src = measured_peak()
     roofline = None
-    if world == 1:
+    if n_dev == 1:
         fb = pysvo.DeviceBuffer(local_rank, nbytes)
         stream = torch.cuda.current_stream().cuda_stream
         alg_bytes, fine_ms_sum, fine_rays_sum, node_bytes_sum, shares = 0.0, 0.0, 0, 0, []
@@ -687,7 +696,7 @@ def run_own(args):
 
     # ---- CPU baseline: the reference's own renderer on this box's host cores (bounded sample, ~10-30 s)
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if n_dev == 1 and not args.no_cpu_baseline:
         try:
             r = reference_sample(w, steps=20, warmup=2, budget_s=25.0, strips=STRIPS)
             cpu = {"value": r["value"], "unit": "Mrays/s", "cores": r["cores"], "kind": "reference", "sample": r["sample"],
@@ -700,15 +709,15 @@ def run_own(args):
     e2e_launches = int(e2e_med.kernel_launches)
     line = {
         "metric": "Mrays/s ESVO traversal (coarse + fine raymarch calls per frame / time)",
-        "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+        "value": value, "unit": "Mrays/s", "n_gpus": n_dev, "steps": steps, "warmup": warmup,
         "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": w["name"], "description": w["text"], "width": W, "height": H, "strips": STRIPS,
                    "flavour": "validation" if args.validation else "fast",
                    "octree_words": tree.n_words, "octree_depth": tree.depth,
                    "parallelism": ("one process, svo_multi_*: replicated octree, tile columns dealt in stripes of "
-                                   f"{dev_run} to {world} GPUs, fine passes store into GPU 0's framebuffer over NVLink, "
-                                   "CUDA-event frame barrier (no NCCL on the data path)") if world > 1 else "single GPU",
+                                   f"{dev_run} to {n_dev} GPUs, fine passes store into GPU 0's framebuffer over NVLink, "
+                                   "CUDA-event frame barrier (no NCCL on the data path)") if n_dev > 1 else "single GPU",
                    "l2": f"no flush: octree {tree.n_words * 4 / 1e6:.0f} MB vs 126 MB L2, camera moves every step",
                    "pipelining": f"{n_lanes} frames in flight; beam passes run ahead on internal streams",
                    "timed_region": {"rounds": len(rounds), "reported": "median round", "steps_per_round": steps,
@@ -719,7 +728,7 @@ def run_own(args):
                 "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "rounds": len(e2e_rounds),
                 "note": "svo_multi_render_sequence(SVO_OUTPUT_HOST): per-step input is the 128 B camera (kernel parameters), "
                         "the octree stays resident; every frame is copied to page-locked host memory, " + (
-                            "copy engine, four frames in flight" if world == 1 else
+                            "copy engine, four frames in flight" if n_dev == 1 else
                             f"every GPU ships the stripes it rendered ({int(e2e_med.tile_run)} tile columns wide) into the ONE "
                             "host frame itself (1 / N of the frame per PCIe link), four frames in flight")},
         "gpu_launches": device_launches,

@@ -68,6 +68,11 @@ typedef enum svo_flavour { SVO_FLAVOUR_VALIDATION = 0, SVO_FLAVOUR_FAST = 1 } sv
  * roughly their direction. Results are identical and land at the rays' own indices; only the speed
  * changes (faster on incoherent batches, a few percent slower on already coherent ones). */
 #define SVO_BATCH_COHERENCE_ORDER 0x100
+/* Also for incoherent batches, and independent of the order above: LANE REFILL. Persistent warps pull rays from a
+ * cursor with one atomic per 256 rays, every lane keeps its traversal state in registers, and once eight lanes of a
+ * warp have finished their rays those lanes store their results and start the next rays while the other lanes carry on
+ * -- instead of the whole warp waiting for its longest ray. Same words at the same indices. */
+#define SVO_BATCH_LANE_REFILL 0x200
 
 /* Ray result codes written to `hit[]`. Non-zero == the reference's `true`. */
 enum { SVO_MISS = 0, SVO_HIT_LEAF = 1, SVO_HIT_LOD = 2 };

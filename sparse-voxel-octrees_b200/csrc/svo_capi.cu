@@ -946,6 +946,7 @@ int svo_tree_destroy(svo_tree *tree) {
         for (auto &kv : tree->plans) kv.second.destroy();
         tree->batchIn.release();
         tree->orderWorkspace.release();
+        tree->refillCursors.release();
         tree->batchOut.release();
         if (tree->dWords) cudaFree(tree->dWords);
         if (tree->stream) cudaStreamDestroy(tree->stream);
@@ -965,18 +966,27 @@ int svo_raymarch_batch_device(svo_tree *tree, uint64_t n, const float *d_o, cons
                               void *stream) {
     if (!tree || (n && (!d_o || !d_d))) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_raymarch_batch_device: null argument");
     const bool reorder = (flavour & SVO_BATCH_COHERENCE_ORDER) != 0;
-    flavour &= ~SVO_BATCH_COHERENCE_ORDER;
+    const bool refill = (flavour & SVO_BATCH_LANE_REFILL) != 0;
+    flavour &= ~(SVO_BATCH_COHERENCE_ORDER | SVO_BATCH_LANE_REFILL);
     if (flavour != SVO_FLAVOUR_VALIDATION && flavour != SVO_FLAVOUR_FAST) return fail(SVO_ERR_INVALID_ARGUMENT, "unknown flavour %d", flavour);
     SVO_DEVICE(tree->device);
     const uint32_t *order = nullptr;
-    if (reorder && n >= 4096) {
-        // one workspace per tree: calls with the coherence order on one tree are ordered by the caller's stream
+    unsigned long long *cursor = nullptr;
+    if ((reorder && n >= 4096) || refill) {
+        // one workspace per tree: calls with these flags on one tree are ordered by the caller's stream (the refill
+        // cursors rotate through a ring of eight, so up to eight such batches may be in flight)
         std::lock_guard<std::mutex> lock(tree->mutex);
-        SVO_CUDA(tree->orderWorkspace.reserve(svo::coherenceOrderBytes(n)));
-        SVO_CUDA(svo::buildCoherenceOrder(n, d_d, tree->orderWorkspace.ptr, &order, static_cast<cudaStream_t>(stream)));
+        if (reorder && n >= 4096) {
+            SVO_CUDA(tree->orderWorkspace.reserve(svo::coherenceOrderBytes(n)));
+            SVO_CUDA(svo::buildCoherenceOrder(n, d_d, tree->orderWorkspace.ptr, &order, static_cast<cudaStream_t>(stream)));
+        }
+        if (refill) {
+            SVO_CUDA(tree->refillCursors.reserve(8*sizeof(unsigned long long)));
+            cursor = static_cast<unsigned long long *>(tree->refillCursors.ptr) + (tree->refillCursorNext++ & 7u);
+        }
     }
     SVO_CUDA(svo::launchRaymarchBatch(tree->dev(), n, d_o, d_d, ray_scale, flavour, d_hit, d_t, d_normal, d_voxel, order,
-                                      static_cast<cudaStream_t>(stream)));
+                                      cursor, static_cast<cudaStream_t>(stream)));
     return SVO_OK;
 }
 
@@ -984,7 +994,8 @@ int svo_raymarch_batch(svo_tree *tree, uint64_t n, const float *o, const float *
                        uint8_t *hit, float *t, uint32_t *normal, uint64_t *voxel) {
     if (!tree || (n && (!o || !d))) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_raymarch_batch: null argument");
     const bool reorder = (flavour & SVO_BATCH_COHERENCE_ORDER) != 0;
-    flavour &= ~SVO_BATCH_COHERENCE_ORDER;
+    const bool refill = (flavour & SVO_BATCH_LANE_REFILL) != 0;
+    flavour &= ~(SVO_BATCH_COHERENCE_ORDER | SVO_BATCH_LANE_REFILL);
     if (flavour != SVO_FLAVOUR_VALIDATION && flavour != SVO_FLAVOUR_FAST) return fail(SVO_ERR_INVALID_ARGUMENT, "unknown flavour %d", flavour);
     if (n == 0) return SVO_OK;
     SVO_DEVICE(tree->device);
@@ -1003,6 +1014,7 @@ int svo_raymarch_batch(svo_tree *tree, uint64_t n, const float *o, const float *
     SVO_CUDA(tree->batchOut.reserve(2*outBytes));
     const size_t orderBytes = (reorder && chunk >= 4096) ? ((svo::coherenceOrderBytes(chunk) + 255) & ~size_t(255)) : 0;
     if (orderBytes) SVO_CUDA(tree->orderWorkspace.reserve(2*orderBytes));
+    if (refill) SVO_CUDA(tree->refillCursors.reserve(8*sizeof(unsigned long long)));
 
     cudaStream_t streams[2] = {tree->stream, tree->stream2};
     for (uint64_t begin = 0, k = 0; begin < n; begin += chunk, ++k) {
@@ -1021,7 +1033,8 @@ int svo_raymarch_batch(svo_tree *tree, uint64_t n, const float *o, const float *
         const uint32_t *order = nullptr;
         if (orderBytes && m >= 4096)
             SVO_CUDA(svo::buildCoherenceOrder(m, dD, static_cast<unsigned char *>(tree->orderWorkspace.ptr) + size_t(slot)*orderBytes, &order, s));
-        SVO_CUDA(svo::launchRaymarchBatch(tree->dev(), m, dO, dD, ray_scale, flavour, dHit, dT, dNormal, dVoxel, order, s));
+        unsigned long long *cursor = refill ? static_cast<unsigned long long *>(tree->refillCursors.ptr) + slot : nullptr;
+        SVO_CUDA(svo::launchRaymarchBatch(tree->dev(), m, dO, dD, ray_scale, flavour, dHit, dT, dNormal, dVoxel, order, cursor, s));
         if (hit) SVO_CUDA(cudaMemcpyAsync(hit + begin, dHit, size_t(m), cudaMemcpyDeviceToHost, s));
         if (t) SVO_CUDA(cudaMemcpyAsync(t + begin, dT, size_t(m)*4, cudaMemcpyDeviceToHost, s));
         if (normal) SVO_CUDA(cudaMemcpyAsync(normal + begin, dNormal, size_t(m)*4, cudaMemcpyDeviceToHost, s));

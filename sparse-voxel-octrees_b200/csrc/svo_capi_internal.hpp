@@ -147,6 +147,8 @@ struct svo_tree {
     std::map<std::tuple<int, int, int>, FramePlan> plans;
     GrowBuffer batchIn, batchOut;
     GrowBuffer orderWorkspace;               // svo_raymarch_batch_device with SVO_BATCH_COHERENCE_ORDER
+    GrowBuffer refillCursors;                // SVO_BATCH_LANE_REFILL: ring of eight ray cursors
+    unsigned refillCursorNext = 0;
     std::vector<cudaStream_t> l2WindowStreams;   // streams that already carry the access-policy window (experiment)
 
     svo::TreeDev dev() const { return svo::TreeDev{dWords, nWords, depth}; }

@@ -12,8 +12,6 @@
 
 #include <cstdlib>
 
-#include <cub/device/device_radix_sort.cuh>
-
 namespace svo {
 
 namespace {
@@ -65,6 +63,94 @@ raymarchBatchKernel(const uint32_t *__restrict__ octree, uint64_t n, const float
     if (t) t[i] = tHit;
     if (normal) normal[i] = material;
     if (voxel) voxel[i] = vox;
+}
+
+// K1 with lane refill: persistent warps pull rays from a cursor (one atomic per kRefillChunk rays and warp), every
+// lane keeps its traversal state in registers, and as soon as kRefillIdle lanes of a warp have finished their rays
+// those lanes write their results and take the next rays of the warp's chunk -- the other lanes' traversals are not
+// disturbed. On incoherent batches (ambient-occlusion rays: trip counts within a warp differ by 3-5x) a warp
+// otherwise runs at the pace of its longest ray with most lanes idle. Results are the same words at the same indices.
+constexpr unsigned kRefillChunk = 256;   // rays per cursor atomic: contiguous in the (direction-binned) order, so a warp's rays stay coherent
+constexpr int kRefillIdle = 8;           // refill once this many lanes are idle (SVO_REFILL_IDLE overrides: experiment switch)
+
+template <bool FAST, bool LOD, typename IdxT>
+__global__ void __launch_bounds__(kBatchThreads, 12)
+raymarchBatchRefillKernel(const uint32_t *__restrict__ octree, uint64_t n, const float *__restrict__ o,
+                          const float *__restrict__ d, float rayScale, uint8_t *__restrict__ hit,
+                          float *__restrict__ t, uint32_t *__restrict__ normal, uint64_t *__restrict__ voxel,
+                          const uint32_t *__restrict__ order, unsigned long long *__restrict__ cursor, int refillIdle) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    SmemStack<IdxT, kBatchThreads> stack;
+    stack.init(smem);
+    constexpr unsigned kFull = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned below = (1u << lane) - 1u;
+
+    // A lane is in flight while r.childShift < 8 (rayTrip leaves one of the kExit codes there when the ray ends), so
+    // "alive" costs no register and no bookkeeping in the loop.
+    RayState<IdxT> r;
+    r.childShift = kExitMiss;
+    uint64_t ray = ~uint64_t(0);        // index of the ray this lane holds (in flight, or finished and not yet written)
+    bool finite = true;
+    float tHit = kTreeMiss;
+    uint64_t vox = 0;
+    unsigned long long next = 0, end = 0;   // the warp's chunk [next, end) of the cursor's range
+    bool exhausted = false;
+
+    for (;;) {
+        // ---- finished lanes write their results, then every idle lane takes the next ray of the warp's chunk
+        const bool idleLane = r.childShift >= 8u;
+        if (idleLane && ray != ~uint64_t(0)) {
+            int code = exitCode(r.childShift, LOD);
+            if (!finite) code = kMiss;
+            if (code == kMiss) { tHit = kTreeMiss; vox = ~uint64_t(0); }
+            const uint32_t material = code == kHitLeaf ? ldNode(octree + vox) : 0u;   // VoxelOctree.cpp:282
+            if (hit) hit[ray] = uint8_t(code);
+            if (t) t[ray] = tHit;
+            if (normal) normal[ray] = material;
+            if (voxel) voxel[ray] = vox;
+            ray = ~uint64_t(0);
+        }
+        if (next >= end && !exhausted) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(cursor, (unsigned long long)kRefillChunk);
+            base = __shfl_sync(kFull, base, 0);
+            next = base;
+            end = base + kRefillChunk < n ? base + kRefillChunk : n;
+            if (base >= n) { exhausted = true; next = end = 0; }
+        }
+        const unsigned idle = __ballot_sync(kFull, idleLane);
+        if (idleLane) {
+            const unsigned long long i = next + __popc(idle & below);
+            if (i < end) {
+                ray = order ? uint64_t(__ldg(order + i)) : uint64_t(i);
+                float ox = __ldg(o + 3*ray), oy = __ldg(o + 3*ray + 1), oz = __ldg(o + 3*ray + 2);
+                float dx = __ldg(d + 3*ray), dy = __ldg(d + 3*ray + 1), dz = __ldg(d + 3*ray + 2);
+                // non-finite rays never leave the loop (see raymarchBatchKernel): swapped for a two-trip ray, reported as misses
+                const float magnitude = fabsf(ox) + fabsf(oy) + fabsf(oz) + fabsf(dx) + fabsf(dy) + fabsf(dz);
+                finite = magnitude < __int_as_float(0x7f800000);
+                if (!finite) { ox = oy = oz = 3.0f; dx = dy = dz = 1.0f; }
+                tHit = kTreeMiss;
+                rayBegin<FAST, IdxT>(octree, ox, oy, oz, dx, dy, dz, r);
+            }
+        }
+        {
+            const unsigned long long taken = next + __popc(idle);
+            next = taken < end ? taken : end;
+        }
+        const unsigned live = __ballot_sync(kFull, r.childShift < 8u);
+        if (live == 0) {
+            if (exhausted) break;
+            continue;                     // the chunk ran out exactly here: fetch the next one
+        }
+        // ---- trips, until enough lanes are idle again (or, once the cursor is exhausted, until all are done); the
+        // vote is taken every second trip
+        const int keep = (exhausted && next >= end) ? 0 : 32 - refillIdle;
+        do {
+            if (r.childShift < 8u) rayTrip<FAST, LOD, IdxT, kBatchThreads>(octree, r, rayScale, stack, tHit, vox);
+            if (r.childShift < 8u) rayTrip<FAST, LOD, IdxT, kBatchThreads>(octree, r, rayScale, stack, tHit, vox);
+        } while (__popc(__ballot_sync(kFull, r.childShift < 8u)) > keep);
+    }
 }
 
 // shade + pack for arbitrary rays (Main.cpp:81-90, 128-132)
@@ -346,6 +432,35 @@ cudaError_t launchBatchT(const TreeDev &tree, uint64_t n, const float *o, const 
     return cudaGetLastError();
 }
 
+template <bool FAST, bool LOD, typename IdxT>
+cudaError_t launchBatchRefillT(const TreeDev &tree, uint64_t n, const float *o, const float *d, float rayScale,
+                               uint8_t *hit, float *t, uint32_t *normal, uint64_t *voxel, const uint32_t *order,
+                               unsigned long long *cursor, cudaStream_t stream) {
+    size_t smem = SmemStack<IdxT, kBatchThreads>::bytes(stackSlots(tree));
+    auto kernel = raymarchBatchRefillKernel<FAST, LOD, IdxT>;
+    cudaError_t e = ensureSmem(kernel, smem);
+    if (e != cudaSuccess) return e;
+    // persistent grid: as many blocks as fit the device at once (one wave), never more than the rays need
+    static int residentBlocks = 0;
+    if (residentBlocks == 0) {
+        int device = 0, sms = 0, perSm = 0;
+        cudaGetDevice(&device);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, kBatchThreads, smem);
+        residentBlocks = sms*(perSm > 0 ? perSm : 1);
+    }
+    uint64_t blocks = (n + kBatchThreads - 1)/kBatchThreads;
+    if (blocks > uint64_t(residentBlocks)) blocks = uint64_t(residentBlocks);
+    if ((e = cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), stream)) != cudaSuccess) return e;
+    static const int refillIdle = [] {
+        const char *e = getenv("SVO_REFILL_IDLE");
+        const int v = e ? atoi(e) : 0;
+        return v >= 1 && v <= 31 ? v : kRefillIdle;
+    }();
+    kernel<<<unsigned(blocks), kBatchThreads, smem, stream>>>(tree.words, n, o, d, rayScale, hit, t, normal, voxel, order, cursor, refillIdle);
+    return cudaGetLastError();
+}
+
 template <typename IdxT>
 cudaError_t launchCoarseT(const TreeDev &tree, const FramePlanDev &plan, const FrameConsts &consts, float *depth,
                           FrameCounters *counters, int tileRank, int tileWorld, cudaStream_t stream) {
@@ -389,11 +504,19 @@ cudaError_t launchFineT(const TreeDev &tree, const FramePlanDev &plan, const Fra
 
 cudaError_t launchRaymarchBatch(const TreeDev &tree, uint64_t n, const float *o, const float *d, float rayScale,
                                 int flavour, uint8_t *hit, float *t, uint32_t *normal, uint64_t *voxel,
-                                const uint32_t *order, cudaStream_t stream) {
+                                const uint32_t *order, unsigned long long *refillCursor, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
     bool wide = wideIndex(tree);
     bool lod = rayScale != 0.0f;
     bool fast = flavour != 0;
+    if (refillCursor) {
+#define SVO_REFILL(F, L) \
+    (wide ? launchBatchRefillT<F, L, uint64_t>(tree, n, o, d, rayScale, hit, t, normal, voxel, order, refillCursor, stream) \
+          : launchBatchRefillT<F, L, uint32_t>(tree, n, o, d, rayScale, hit, t, normal, voxel, order, refillCursor, stream))
+        if (fast) return lod ? SVO_REFILL(true, true) : SVO_REFILL(true, false);
+        return lod ? SVO_REFILL(false, true) : SVO_REFILL(false, false);
+#undef SVO_REFILL
+    }
 #define SVO_BATCH(F, L) \
     (wide ? launchBatchT<F, L, uint64_t>(tree, n, o, d, rayScale, hit, t, normal, voxel, order, stream) \
           : launchBatchT<F, L, uint32_t>(tree, n, o, d, rayScale, hit, t, normal, voxel, order, stream))
@@ -403,41 +526,137 @@ cudaError_t launchRaymarchBatch(const TreeDev &tree, uint64_t n, const float *o,
 }
 
 // ---- coherence order for incoherent ray batches -------------------------------------------------
-// Rays are binned by direction (4 x 4 x 4 cells of d / max|d|) with ONE stable 6-bit radix pass, so rays
-// of a bin keep their submission order (neighbouring pixels stay neighbours). A warp then holds rays that
-// share their octant mirroring and roughly their direction: on 16-spp ambient-occlusion rays the
-// trace-driven model gives 1.65x fewer warp instructions (SIMT efficiency 0.21 -> 0.34).
-__global__ void __launch_bounds__(256)
-directionBinKernel(uint64_t n, const float *__restrict__ d, uint32_t *__restrict__ keys, uint32_t *__restrict__ index) {
-    uint64_t i = uint64_t(blockIdx.x)*blockDim.x + threadIdx.x;
-    if (i >= n) return;
+// Rays are binned by direction (4 x 4 x 4 cells of d / max|d|) with ONE stable counting sort over the 64 bins, so rays
+// of a bin keep their submission order (neighbouring pixels stay neighbours). A warp then holds rays that share their
+// octant mirroring and roughly their direction: on 16-spp ambient-occlusion rays the trace-driven model gives 1.65x
+// fewer warp instructions (SIMT efficiency 0.21 -> 0.34). Three small kernels of our own (no library sort): bin keys +
+// per-tile histograms, one scan over (bin, tile), stable scatter of the ray indices.
+constexpr int kBinThreads = 256;                 // 8 warps
+constexpr int kBinRaysPerWarp = 512;             // a warp bins a contiguous run of rays
+constexpr int kBinTile = (kBinThreads/32)*kBinRaysPerWarp;   // rays per block
+constexpr int kBins = 64;
+
+__device__ __forceinline__ uint32_t directionBin(const float *__restrict__ d, uint64_t i) {
     const float x = __ldg(d + 3*i), y = __ldg(d + 3*i + 1), z = __ldg(d + 3*i + 2);
     const float m = fmaxf(fmaxf(fabsf(x), fabsf(y)), fmaxf(fabsf(z), 1e-30f));
     auto cell = [m](float v) { return uint32_t(min(3, max(0, int((v/m + 1.0f)*2.0f)))); };
-    keys[i] = cell(x) | (cell(y) << 2) | (cell(z) << 4);
-    index[i] = uint32_t(i);
+    return cell(x) | (cell(y) << 2) | (cell(z) << 4);    // NaN directions land in cell 0 (int(NaN) == 0)
+}
+
+// keys[i] = bin of ray i; tileCounts[bin][tile] = rays of the tile in the bin
+__global__ void __launch_bounds__(kBinThreads)
+directionBinKernel(uint64_t n, const float *__restrict__ d, uint8_t *__restrict__ keys, uint32_t *__restrict__ tileCounts,
+                   uint32_t nTiles) {
+    __shared__ uint32_t hist[kBins];
+    if (threadIdx.x < kBins) hist[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t first = uint64_t(blockIdx.x)*kBinTile;
+    for (uint32_t k = threadIdx.x; k < uint32_t(kBinTile); k += kBinThreads) {
+        const uint64_t i = first + k;
+        if (i < n) {
+            const uint32_t key = directionBin(d, i);
+            keys[i] = uint8_t(key);
+            atomicAdd(&hist[key], 1u);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < kBins) tileCounts[size_t(threadIdx.x)*nTiles + blockIdx.x] = hist[threadIdx.x];
+}
+
+// exclusive scan of tileCounts in (bin, tile) order, in place: one block, a running carry over chunks of its width
+__global__ void __launch_bounds__(1024)
+scanTileCountsKernel(uint32_t *__restrict__ counts, uint32_t total) {
+    __shared__ uint32_t warpSums[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < total; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < total ? counts[i] : 0u;
+        uint32_t incl = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= unsigned(o)) incl += up;
+        }
+        if (lane == 31) warpSums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = warpSums[lane], wi = w;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= unsigned(o)) wi += up;
+            }
+            warpSums[lane] = wi - w;            // exclusive
+        }
+        __syncthreads();
+        const uint32_t c = carry;
+        if (i < total) counts[i] = c + warpSums[warp] + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = c + warpSums[31] + incl;
+        __syncthreads();
+    }
+}
+
+// order[position] = ray index, stable inside every bin: the tile's base per bin comes from the scan, warps of the tile
+// take their rays in order (each warp a contiguous run), lanes with equal keys are ranked by lane (__match_any_sync)
+__global__ void __launch_bounds__(kBinThreads)
+scatterByBinKernel(uint64_t n, const uint8_t *__restrict__ keys, const uint32_t *__restrict__ tileBase, uint32_t nTiles,
+                   uint32_t *__restrict__ order) {
+    __shared__ uint32_t warpHist[kBinThreads/32][kBins];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (uint32_t k = lane; k < uint32_t(kBins); k += 32) warpHist[warp][k] = 0;
+    __syncwarp();
+    const uint64_t first = uint64_t(blockIdx.x)*kBinTile + uint64_t(warp)*kBinRaysPerWarp;
+    for (uint32_t k = 0; k < uint32_t(kBinRaysPerWarp); k += 32) {
+        const uint64_t i = first + k + lane;
+        if (i < n) atomicAdd(&warpHist[warp][keys[i]], 1u);
+    }
+    __syncthreads();
+    // warp w's base in bin k: tile base + the counts of the warps before it
+    for (uint32_t k = threadIdx.x; k < uint32_t(kBins); k += kBinThreads) {
+        uint32_t run = __ldg(tileBase + size_t(k)*nTiles + blockIdx.x);
+        for (int w = 0; w < kBinThreads/32; ++w) {
+            const uint32_t c = warpHist[w][k];
+            warpHist[w][k] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    for (uint32_t k = 0; k < uint32_t(kBinRaysPerWarp); k += 32) {
+        const uint64_t i = first + k + lane;
+        const bool valid = i < n;
+        const uint32_t key = valid ? uint32_t(keys[i]) : 0xFFu;
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        if (valid) {
+            const uint32_t base = warpHist[warp][key];
+            order[base + __popc(peers & ((1u << lane) - 1u))] = uint32_t(i);
+        }
+        __syncwarp();
+        if (valid && (peers & ((1u << lane) - 1u)) == 0) warpHist[warp][key] += __popc(peers);   // the lowest lane of each group
+        __syncwarp();
+    }
 }
 
 size_t coherenceOrderBytes(uint64_t n) {
-    size_t temp = 0;
-    cub::DoubleBuffer<uint32_t> k(nullptr, nullptr), v(nullptr, nullptr);
-    cub::DeviceRadixSort::SortPairs(nullptr, temp, k, v, int(n), 0, 6);
-    return size_t(n)*16 + ((temp + 255) & ~size_t(255)) + 256;
+    const uint64_t nTiles = (n + kBinTile - 1)/kBinTile;
+    auto up = [](size_t v) { return (v + 255) & ~size_t(255); };
+    return up(size_t(n)*sizeof(uint32_t)) + up(size_t(n)) + up(size_t(nTiles)*kBins*sizeof(uint32_t)) + 256;
 }
 
 // workspace: coherenceOrderBytes(n) bytes on the device. *orderOut points into it.
 cudaError_t buildCoherenceOrder(uint64_t n, const float *d, void *workspace, const uint32_t **orderOut, cudaStream_t stream) {
     if (n >= (1ull << 31)) return cudaErrorInvalidValue;
-    uint32_t *base = static_cast<uint32_t *>(workspace);
-    uint32_t *keys0 = base, *keys1 = base + n, *idx0 = base + 2*n, *idx1 = base + 3*n;
-    void *temp = base + 4*n;
-    size_t tempBytes = 0;
-    cub::DoubleBuffer<uint32_t> k(keys0, keys1), v(idx0, idx1);
-    cub::DeviceRadixSort::SortPairs(nullptr, tempBytes, k, v, int(n), 0, 6, stream);
-    directionBinKernel<<<unsigned((n + 255)/256), 256, 0, stream>>>(n, d, keys0, idx0);
-    cudaError_t e = cub::DeviceRadixSort::SortPairs(temp, tempBytes, k, v, int(n), 0, 6, stream);
-    if (e != cudaSuccess) return e;
-    *orderOut = v.Current();
+    const uint32_t nTiles = uint32_t((n + kBinTile - 1)/kBinTile);
+    auto up = [](size_t v) { return (v + 255) & ~size_t(255); };
+    unsigned char *base = static_cast<unsigned char *>(workspace);
+    uint32_t *order = reinterpret_cast<uint32_t *>(base);
+    uint8_t *keys = base + up(size_t(n)*sizeof(uint32_t));
+    uint32_t *counts = reinterpret_cast<uint32_t *>(base + up(size_t(n)*sizeof(uint32_t)) + up(size_t(n)));
+    directionBinKernel<<<nTiles, kBinThreads, 0, stream>>>(n, d, keys, counts, nTiles);
+    scanTileCountsKernel<<<1, 1024, 0, stream>>>(counts, nTiles*uint32_t(kBins));
+    scatterByBinKernel<<<nTiles, kBinThreads, 0, stream>>>(n, keys, counts, nTiles, order);
+    *orderOut = order;
     return cudaGetLastError();
 }
 

@@ -53,9 +53,11 @@ struct TreeDev {
 };
 
 // order == nullptr: thread k traces ray k. Otherwise thread k traces ray order[k] (see buildCoherenceOrder).
+// refillCursor != nullptr (one device word, zeroed by the launch): the persistent lane-refill kernel -- warps pull
+// rays from the cursor and a lane that finishes takes the next ray; nullptr: one ray per thread.
 cudaError_t launchRaymarchBatch(const TreeDev &tree, uint64_t n, const float *o, const float *d, float rayScale,
                                 int flavour, uint8_t *hit, float *t, uint32_t *normal, uint64_t *voxel,
-                                const uint32_t *order, cudaStream_t stream);
+                                const uint32_t *order, unsigned long long *refillCursor, cudaStream_t stream);
 
 // Direction-binned submission order for incoherent batches (one stable 6-bit radix pass).
 size_t coherenceOrderBytes(uint64_t n);

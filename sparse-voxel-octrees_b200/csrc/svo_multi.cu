@@ -202,6 +202,7 @@ int destroyMulti(svo_multi *M) {
     M->cvJob.notify_all();
     for (auto &r : M->reps) if (r->worker.joinable()) r->worker.join();
     for (auto &r : M->reps) {
+        if (!r->tree) continue;         // never came up (e.g. a device index out of range): nothing of it exists
         DeviceScope scope(r->device);
         cudaDeviceSynchronize();
         for (int l = 0; l < kLanes; ++l) {
@@ -212,7 +213,7 @@ int destroyMulti(svo_multi *M) {
         }
         if (r->copy) cudaStreamDestroy(r->copy);
     }
-    if (!M->reps.empty()) {
+    if (!M->reps.empty() && M->reps[0]->tree) {
         DeviceScope scope(M->reps[0]->device);
         for (int l = 0; l < kLanes; ++l) {
             if (M->gather[l]) cudaFree(M->gather[l]);
@@ -224,6 +225,7 @@ int destroyMulti(svo_multi *M) {
     }
     for (auto &r : M->reps) if (r->tree) svo_tree_destroy(r->tree);
     delete M;
+    cudaGetLastError();                 // leave no stale error behind for the caller's next launch check
     return SVO_OK;
 }
 

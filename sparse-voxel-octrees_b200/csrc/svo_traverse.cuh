@@ -219,201 +219,235 @@ __device__ __forceinline__ uint32_t ldNode(const uint32_t *__restrict__ p) { ret
 
 enum : int { kMiss = 0, kHitLeaf = 1, kHitLod = 2 };
 
-// reference src/VoxelOctree.cpp:207-346. Returns kMiss / kHitLeaf / kHitLod.
+// ---- the traversal, in three pieces ------------------------------------------------------------------------------
+// reference src/VoxelOctree.cpp:207-346. RayState is the loop's state (registers), rayBegin the set-up (:214-250) with
+// the first node fetch, rayTrip ONE trip round the loop (:252-339). raymarch() below runs them to completion for one
+// ray per thread; the persistent kernels (svo_kernels.cu) keep a RayState per lane and hand a lane its next ray when it
+// finishes one ("lane refill"), so both share every instruction of the traversal itself.
+template <typename IdxT>
+struct RayState {
+    float dTx, dTy, dTz;        // 1 / -|d|, :221-223
+    float bTx, bTy, bTz;        // :225-232
+    uint32_t octantMask;
+    float minT, maxT;
+    uint32_t current, farWord;  // descriptor of `parent` and the word behind it
+    IdxT parent;
+    float posX, posY, posZ;
+    int scale;
+    float scaleExp2;
+    uint32_t childShift;        // idx ^ octantMask (:261) while the ray is alive; kExitLeaf / kExitLod / kExitMiss after
+};
+constexpr uint32_t kExitLeaf = 8u, kExitLod = 16u, kExitMiss = 32u;
+
+// Descriptor and its possible far word (bit 17) are fetched together (the node array carries one padding word so
+// parent + 1 is always readable), right where `parent` changes: at the start, at the end of a push and at the end of
+// a pop -- the reference's `current == 0` refetch flag (:253-254, :305, :337) never has to be tested.
+template <typename IdxT>
+__device__ __forceinline__ void fetchNode(const uint32_t *__restrict__ octree, RayState<IdxT> &r) {
+    const uint32_t *node = octree + r.parent;
+    r.current = ldNode(node);
+    r.farWord = ldNode(node + 1);
+}
+
+template <bool FAST, typename IdxT>
+__device__ __forceinline__ void rayBegin(const uint32_t *__restrict__ octree, float ox, float oy, float oz,
+                                         float dx, float dy, float dz, RayState<IdxT> &r) {
+    typedef Arith<FAST> A;
+    if (fabsf(dx) < 1e-4f) dx = 1e-4f;      // :217-219, sign dropped on purpose
+    if (fabsf(dy) < 1e-4f) dy = 1e-4f;
+    if (fabsf(dz) < 1e-4f) dz = 1e-4f;
+
+    r.dTx = __fdiv_rn(1.0f, -fabsf(dx));    // :221-223
+    r.dTy = __fdiv_rn(1.0f, -fabsf(dy));
+    r.dTz = __fdiv_rn(1.0f, -fabsf(dz));
+
+    r.bTx = mulRn(r.dTx, ox);               // :225-227
+    r.bTy = mulRn(r.dTy, oy);
+    r.bTz = mulRn(r.dTz, oz);
+
+    uint32_t octantMask = 7;                // :229-232
+    if (dx > 0.0f) { octantMask ^= 1; r.bTx = A::mulsub(3.0f, r.dTx, r.bTx); }
+    if (dy > 0.0f) { octantMask ^= 2; r.bTy = A::mulsub(3.0f, r.dTy, r.bTy); }
+    if (dz > 0.0f) { octantMask ^= 4; r.bTz = A::mulsub(3.0f, r.dTz, r.bTz); }
+    // keep the mask in a register: ptxas otherwise re-derives it from the
+    // direction signs on every trip round the loop (12 extra instructions)
+    asm volatile("" : "+r"(octantMask));
+    r.octantMask = octantMask;
+
+    float minT = maxStd(A::pow2mulsub(2.0f, r.dTx, r.bTx), maxStd(A::pow2mulsub(2.0f, r.dTy, r.bTy), A::pow2mulsub(2.0f, r.dTz, r.bTz)));
+    r.maxT = minStd(subRn(r.dTx, r.bTx), minStd(subRn(r.dTy, r.bTy), subRn(r.dTz, r.bTz)));
+    minT = maxStd(minT, 0.0f);
+    r.minT = minT;
+
+    r.current = 0;
+    r.farWord = 0;
+    r.parent = 0;
+    uint32_t idx = 0;
+    r.posX = 1.0f; r.posY = 1.0f; r.posZ = 1.0f;
+    r.scale = kMaxScale - 1;
+    r.scaleExp2 = 0.5f;
+
+    if (A::mulsub(1.5f, r.dTx, r.bTx) > minT) { idx ^= 1; r.posX = 1.5f; }   // :248-250
+    if (A::mulsub(1.5f, r.dTy, r.bTy) > minT) { idx ^= 2; r.posY = 1.5f; }
+    if (A::mulsub(1.5f, r.dTz, r.bTz) > minT) { idx ^= 4; r.posZ = 1.5f; }
+    // the loop tracks the reference's `idx` as childShift = idx ^ octantMask (:261), which is what it uses
+    r.childShift = idx ^ octantMask;
+    fetchNode(octree, r);
+}
+
+// One trip round the reference's loop (:252-339). Returns true when the ray is finished: r.childShift then says how
+// (kExitLeaf: tOut / voxelOut = leaf word index; kExitLod: tOut / voxelOut = parent | childShift << 60; kExitMiss:
+// voxelOut = some valid word index, so that callers can fetch octree[voxelOut] without a select).
+// How the loop was left is recorded in childShift (always < 8 while the ray is alive): a separate result flag would
+// have to be set on the pop path, which every pop executes, for the sake of the one pop per ray that leaves the root.
+// LOD == false elides the rayScale test (rayScale == 0 can never pass it: maxTC*0 is +-0 or NaN, scaleExp2 > 0).
+//
+// min/max are FMNMX in both flavours here: every operand is a finite p*dT - bT with p*dT != 0, which can be +0 but
+// never -0 or NaN, so FMNMX and the reference's (b < a) ? b : a select the same bits.
+template <bool FAST, bool LOD, typename IdxT, int THREADS>
+__device__ __forceinline__ bool rayTrip(const uint32_t *__restrict__ octree, RayState<IdxT> &r, float rayScale,
+                                        const SmemStack<IdxT, THREADS> &stack, float &tOut, uint64_t &voxelOut) {
+    typedef Arith<FAST> A;
+    typedef SmemStack<IdxT, THREADS> Stack;
+
+    const float cornerTX = A::mulsub(r.posX, r.dTx, r.bTx);   // :256-259
+    const float cornerTY = A::mulsub(r.posY, r.dTy, r.bTy);
+    const float cornerTZ = A::mulsub(r.posZ, r.dTz, r.bTz);
+    const float maxTC = fminf(cornerTX, fminf(cornerTY, cornerTZ));
+
+    const uint32_t childMasks = r.current << r.childShift;
+
+    // :263-273. Without the LOD test in between, `minT <= maxT && minT <= min(maxT, maxTC)` is just its
+    // second half (min(maxT, maxTC) <= maxT), so the rays of the fine pass make one comparison here.
+    const float maxTV = fminf(r.maxT, maxTC);
+    bool descend = (childMasks & 0x8000u) != 0;
+    if (LOD) {
+        descend = descend && r.minT <= r.maxT;
+        if (descend && mulRn(maxTC, rayScale) >= r.scaleExp2) {   // :265-268
+            tOut = maxTC;
+            voxelOut = uint64_t(r.parent) | (uint64_t(r.childShift) << 60);
+            r.childShift = kExitLod;
+            return true;
+        }
+    }
+    if (descend && r.minT <= maxTV) {
+        IdxT childOffset = IdxT(r.current >> 18);
+        if (r.current & 0x20000u) {                      // :278-279
+            if (sizeof(IdxT) == 8)
+                childOffset = IdxT((uint64_t(childOffset) << 32) | uint64_t(r.farWord));
+            else
+                childOffset = IdxT(r.farWord);           // high 14 bits are zero below 2^32 words
+        }
+
+        if (!(childMasks & 0x80u)) {                     // leaf, :281-285
+            IdxT leaf = childOffset + r.parent + IdxT(__popc(((childMasks >> (8 + r.childShift)) << r.childShift) & 127u));
+            voxelOut = uint64_t(leaf);
+            tOut = r.minT;
+            r.childShift = kExitLeaf;
+            return true;
+        }
+
+        Stack::store(stack.slot(r.scale), r.parent, r.maxT);  // :287-288
+
+        // siblings before this child, doubled when the block is far-interleaved (bit 16), :290-293
+        uint32_t siblings = uint32_t(__popc(childMasks & 127u));
+        // one predicate test + one predicated shift (the C forms compile to three or four instructions)
+        asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %1, 0x10000;\n\tsetp.ne.u32 p, t, 0;\n\t@p shl.b32 %0, %0, 1;\n\t}"
+            : "+r"(siblings) : "r"(r.current));
+        r.parent += childOffset + IdxT(siblings);
+
+        const float half = mulRn(r.scaleExp2, 0.5f);
+        const float centerTX = A::pow2muladd(half, r.dTx, cornerTX);   // half is a power of two
+        const float centerTY = A::pow2muladd(half, r.dTy, cornerTY);
+        const float centerTZ = A::pow2muladd(half, r.dTz, cornerTZ);
+        r.scale--;
+        r.scaleExp2 = half;
+
+        // idx = axes with centerT > minT, each of which moves to the upper half (:297-301)
+        const float upX = flagGreater(centerTX, r.minT), upY = flagGreater(centerTY, r.minT), upZ = flagGreater(centerTZ, r.minT);
+        r.posX = moveIf<FAST>(upX, half, r.posX);
+        r.posY = moveIf<FAST>(upY, half, r.posY);
+        r.posZ = moveIf<FAST>(upZ, half, r.posZ);
+        r.childShift = (flagMask(upX, upY, upZ) & 7u) ^ r.octantMask;
+
+        r.maxT = maxTV;
+        fetchNode(octree, r);
+        return false;
+    }
+
+    // :310-316: every axis whose plane is reached at maxTC steps down by one cell
+    const float stX = flagNotGreater(cornerTX, maxTC), stY = flagNotGreater(cornerTY, maxTC), stZ = flagNotGreater(cornerTZ, maxTC);
+    r.posX = moveIf<FAST>(stX, -r.scaleExp2, r.posX);
+    r.posY = moveIf<FAST>(stY, -r.scaleExp2, r.posY);
+    r.posZ = moveIf<FAST>(stZ, -r.scaleExp2, r.posZ);
+    const uint32_t stepMask = flagMask(stX, stY, stZ) & 7u;
+    r.minT = maxTC;
+    // idx ^= stepMask; pop if (idx & stepMask) != 0 (:316-318)  <=>  a stepped axis had its idx bit clear
+    const bool leavesParent = (~(r.childShift ^ r.octantMask) & stepMask) != 0;
+    r.childShift ^= stepMask;
+
+    if (leavesParent) {                                     // :318-338
+        // pos ^ (pos + scaleExp2) over the stepped axes (:320-322); an axis that did not step adds
+        // 0*scaleExp2 and contributes nothing. (Keeping the pre-step positions instead costs three
+        // register moves on EVERY trip: ptxas copies them at the loop head.)
+        const uint32_t differingBits =
+            (__float_as_uint(r.posX) ^ __float_as_uint(moveIf<FAST>(stX, r.scaleExp2, r.posX))) |
+            (__float_as_uint(r.posY) ^ __float_as_uint(moveIf<FAST>(stY, r.scaleExp2, r.posY))) |
+            (__float_as_uint(r.posZ) ^ __float_as_uint(moveIf<FAST>(stZ, r.scaleExp2, r.posZ)));
+        // reference: exponent of (float)differingBits. differingBits < 2^24
+        // always (positions stay in [0.5, 2)), so that is the index of the
+        // highest set bit; bit 23 set <=> the ray left the root (:341-342)
+        if (differingBits > 0x7FFFFFu) {
+            voxelOut = uint64_t(r.parent);   // any valid word index: the caller may fetch it unconditionally
+            r.childShift = kExitMiss;
+            return true;
+        }
+        asm("bfind.u32 %0, %1;" : "=r"(r.scale) : "r"(differingBits));   // FLO: index of the highest set bit
+        r.scaleExp2 = __uint_as_float(uint32_t(r.scale - kMaxScale + 127) << 23);
+
+        Stack::load(stack.slot(r.scale), r.parent, r.maxT);
+        fetchNode(octree, r);
+
+        // Truncate the positions to the `scale` grid (:329-334) on the FMA pipe: adding 2^scale with
+        // round-toward-zero leaves exactly the mantissa bits >= `scale` (positions are in [1, 2), the
+        // sum is in [2^scale, 2^(scale+1))), its lowest mantissa bit is the new idx bit, and
+        // subtracting 2^scale again is exact.
+        const float big = __uint_as_float(uint32_t(r.scale + 127) << 23);
+        const float tX = __fadd_rz(r.posX, big), tY = __fadd_rz(r.posY, big), tZ = __fadd_rz(r.posZ, big);
+        r.posX = subRn(tX, big);
+        r.posY = subRn(tY, big);
+        r.posZ = subRn(tZ, big);
+        // idx = bit 0 of tX | bit 0 of tY << 1 | bit 0 of tZ << 2, by two bit-selects
+        const uint32_t xy = (__float_as_uint(tX) & 1u) | ((__float_as_uint(tY) << 1) & ~1u);
+        const uint32_t xyz = (xy & 3u) | ((__float_as_uint(tZ) << 2) & ~3u);
+        r.childShift = (xyz ^ r.octantMask) & 7u;
+    }
+    return false;
+}
+
+__device__ __forceinline__ int exitCode(uint32_t childShift, bool lod) {
+    return childShift == kExitLeaf ? kHitLeaf : (lod && childShift == kExitLod) ? kHitLod : kMiss;
+}
+
+// One ray per thread, run to completion. Returns kMiss / kHitLeaf / kHitLod.
 //   tOut      written on a hit only
 //   voxelOut  leaf word index (the caller fetches the material word octree[voxelOut], :282, AFTER the
-//             warp has reconverged), or parent | childShift << 60 for LOD exits; on a miss some valid
-//             word index (so that callers can fetch octree[voxelOut] without a select)
+//             warp has reconverged), or parent | childShift << 60 for LOD exits; on a miss some valid word index
 // The loop has ONE exit: every way out records its result and breaks, and a warp barrier follows the
 // loop. Without it the compiler threads whatever the caller does with a hit (material fetch + ~100
 // instructions of shading) into the leaf branch inside the loop, where it runs once per distinct exit
 // trip of the warp (8-10 times per warp, with 3 lanes active) instead of once with all lanes.
-// LOD == false elides the rayScale test (rayScale == 0 can never pass it:
-// maxTC*0 is +-0 or NaN, scaleExp2 > 0).
-//
-// Inside the loop min/max are FMNMX in both flavours: every operand there is a
-// finite p*dT - bT with p*dT != 0, which can be +0 but never -0 or NaN, so
-// FMNMX and the reference's (b < a) ? b : a select the same bits.
 template <bool FAST, bool LOD, typename IdxT, int THREADS>
 __device__ __forceinline__ int raymarch(const uint32_t *__restrict__ octree, float ox, float oy, float oz,
                                         float dx, float dy, float dz, float rayScale,
                                         const SmemStack<IdxT, THREADS> &stack,
                                         float &tOut, uint64_t &voxelOut) {
-    typedef Arith<FAST> A;
-    typedef SmemStack<IdxT, THREADS> Stack;
-
-    if (fabsf(dx) < 1e-4f) dx = 1e-4f;      // :217-219, sign dropped on purpose
-    if (fabsf(dy) < 1e-4f) dy = 1e-4f;
-    if (fabsf(dz) < 1e-4f) dz = 1e-4f;
-
-    const float dTx = __fdiv_rn(1.0f, -fabsf(dx)); // :221-223
-    const float dTy = __fdiv_rn(1.0f, -fabsf(dy));
-    const float dTz = __fdiv_rn(1.0f, -fabsf(dz));
-
-    float bTx = mulRn(dTx, ox);              // :225-227
-    float bTy = mulRn(dTy, oy);
-    float bTz = mulRn(dTz, oz);
-
-    uint32_t octantMask = 7;                 // :229-232
-    if (dx > 0.0f) { octantMask ^= 1; bTx = A::mulsub(3.0f, dTx, bTx); }
-    if (dy > 0.0f) { octantMask ^= 2; bTy = A::mulsub(3.0f, dTy, bTy); }
-    if (dz > 0.0f) { octantMask ^= 4; bTz = A::mulsub(3.0f, dTz, bTz); }
-    // keep the mask in a register: ptxas otherwise re-derives it from the
-    // direction signs on every trip round the loop (12 extra instructions)
-    asm volatile("" : "+r"(octantMask));
-
-    float minT = maxStd(A::pow2mulsub(2.0f, dTx, bTx), maxStd(A::pow2mulsub(2.0f, dTy, bTy), A::pow2mulsub(2.0f, dTz, bTz)));
-    float maxT = minStd(subRn(dTx, bTx), minStd(subRn(dTy, bTy), subRn(dTz, bTz)));
-    minT = maxStd(minT, 0.0f);
-
-    uint32_t current = 0;
-    uint32_t farWord = 0;
-    IdxT parent = 0;
-    uint32_t idx = 0;
-    float posX = 1.0f, posY = 1.0f, posZ = 1.0f;
-    int scale = kMaxScale - 1;
-    float scaleExp2 = 0.5f;
-
-    if (A::mulsub(1.5f, dTx, bTx) > minT) { idx ^= 1; posX = 1.5f; }   // :248-250
-    if (A::mulsub(1.5f, dTy, bTy) > minT) { idx ^= 2; posY = 1.5f; }
-    if (A::mulsub(1.5f, dTz, bTz) > minT) { idx ^= 4; posZ = 1.5f; }
-    // the loop tracks the reference's `idx` as childShift = idx ^ octantMask (:261), which is what it uses
-    uint32_t childShift = idx ^ octantMask;
-
-    // Descriptor and its possible far word (bit 17) are fetched together (the node array carries one
-    // padding word so parent + 1 is always readable), right where `parent` changes: before the loop,
-    // at the end of a push and at the end of a pop -- the reference's `current == 0` refetch flag
-    // (:253-254, :305, :337) never has to be tested.
-#define SVO_FETCH_NODE()                                   \
-    do {                                                   \
-        const uint32_t *node_ = octree + parent;           \
-        current = ldNode(node_);                           \
-        farWord = ldNode(node_ + 1);                       \
-    } while (0)
-    SVO_FETCH_NODE();
-
-    // How the loop was left is recorded in childShift (always < 8 inside the loop): a separate result
-    // flag would have to be set on the pop path, which every pop executes, for the sake of the one
-    // pop per ray that leaves the root.
-    constexpr uint32_t kExitLeaf = 8u, kExitLod = 16u;
-    for (;;) {
-        const float cornerTX = A::mulsub(posX, dTx, bTx);   // :256-259
-        const float cornerTY = A::mulsub(posY, dTy, bTy);
-        const float cornerTZ = A::mulsub(posZ, dTz, bTz);
-        const float maxTC = fminf(cornerTX, fminf(cornerTY, cornerTZ));
-
-        const uint32_t childMasks = current << childShift;
-
-        // :263-273. Without the LOD test in between, `minT <= maxT && minT <= min(maxT, maxTC)` is just its
-        // second half (min(maxT, maxTC) <= maxT), so the rays of the fine pass make one comparison here.
-        const float maxTV = fminf(maxT, maxTC);
-        bool descend = (childMasks & 0x8000u) != 0;
-        if (LOD) {
-            descend = descend && minT <= maxT;
-            if (descend && mulRn(maxTC, rayScale) >= scaleExp2) {   // :265-268
-                tOut = maxTC;
-                voxelOut = uint64_t(parent) | (uint64_t(childShift) << 60);
-                childShift = kExitLod;
-                break;
-            }
-        }
-        {
-            if (descend && minT <= maxTV) {
-                IdxT childOffset = IdxT(current >> 18);
-                if (current & 0x20000u) {                      // :278-279
-                    if (sizeof(IdxT) == 8)
-                        childOffset = IdxT((uint64_t(childOffset) << 32) | uint64_t(farWord));
-                    else
-                        childOffset = IdxT(farWord);           // high 14 bits are zero below 2^32 words
-                }
-
-                if (!(childMasks & 0x80u)) {                   // leaf, :281-285
-                    IdxT leaf = childOffset + parent + IdxT(__popc(((childMasks >> (8 + childShift)) << childShift) & 127u));
-                    voxelOut = uint64_t(leaf);
-                    tOut = minT;
-                    childShift = kExitLeaf;
-                    break;
-                }
-
-                Stack::store(stack.slot(scale), parent, maxT);  // :287-288
-
-                // siblings before this child, doubled when the block is far-interleaved (bit 16), :290-293
-                uint32_t siblings = uint32_t(__popc(childMasks & 127u));
-                // one predicate test + one predicated shift (the C forms compile to three or four instructions)
-                asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %1, 0x10000;\n\tsetp.ne.u32 p, t, 0;\n\t@p shl.b32 %0, %0, 1;\n\t}"
-                    : "+r"(siblings) : "r"(current));
-                parent += childOffset + IdxT(siblings);
-
-                const float half = mulRn(scaleExp2, 0.5f);
-                const float centerTX = A::pow2muladd(half, dTx, cornerTX);   // half is a power of two
-                const float centerTY = A::pow2muladd(half, dTy, cornerTY);
-                const float centerTZ = A::pow2muladd(half, dTz, cornerTZ);
-                scale--;
-                scaleExp2 = half;
-
-                // idx = axes with centerT > minT, each of which moves to the upper half (:297-301)
-                const float upX = flagGreater(centerTX, minT), upY = flagGreater(centerTY, minT), upZ = flagGreater(centerTZ, minT);
-                posX = moveIf<FAST>(upX, half, posX);
-                posY = moveIf<FAST>(upY, half, posY);
-                posZ = moveIf<FAST>(upZ, half, posZ);
-                childShift = (flagMask(upX, upY, upZ) & 7u) ^ octantMask;
-
-                maxT = maxTV;
-                SVO_FETCH_NODE();
-                continue;
-            }
-        }
-
-        // :310-316: every axis whose plane is reached at maxTC steps down by one cell
-        const float stX = flagNotGreater(cornerTX, maxTC), stY = flagNotGreater(cornerTY, maxTC), stZ = flagNotGreater(cornerTZ, maxTC);
-        posX = moveIf<FAST>(stX, -scaleExp2, posX);
-        posY = moveIf<FAST>(stY, -scaleExp2, posY);
-        posZ = moveIf<FAST>(stZ, -scaleExp2, posZ);
-        const uint32_t stepMask = flagMask(stX, stY, stZ) & 7u;
-        minT = maxTC;
-        // idx ^= stepMask; pop if (idx & stepMask) != 0 (:316-318)  <=>  a stepped axis had its idx bit clear
-        const bool leavesParent = (~(childShift ^ octantMask) & stepMask) != 0;
-        childShift ^= stepMask;
-
-        if (leavesParent) {                                     // :318-338
-            // pos ^ (pos + scaleExp2) over the stepped axes (:320-322); an axis that did not step adds
-            // 0*scaleExp2 and contributes nothing. (Keeping the pre-step positions instead costs three
-            // register moves on EVERY trip: ptxas copies them at the loop head.)
-            const uint32_t differingBits =
-                (__float_as_uint(posX) ^ __float_as_uint(moveIf<FAST>(stX, scaleExp2, posX))) |
-                (__float_as_uint(posY) ^ __float_as_uint(moveIf<FAST>(stY, scaleExp2, posY))) |
-                (__float_as_uint(posZ) ^ __float_as_uint(moveIf<FAST>(stZ, scaleExp2, posZ)));
-            // reference: exponent of (float)differingBits. differingBits < 2^24
-            // always (positions stay in [0.5, 2)), so that is the index of the
-            // highest set bit; bit 23 set <=> the ray left the root (:341-342)
-            if (differingBits > 0x7FFFFFu) {
-                voxelOut = uint64_t(parent);   // any valid word index: the caller may fetch it unconditionally
-                break;
-            }
-            asm("bfind.u32 %0, %1;" : "=r"(scale) : "r"(differingBits));   // FLO: index of the highest set bit
-            scaleExp2 = __uint_as_float(uint32_t(scale - kMaxScale + 127) << 23);
-
-            Stack::load(stack.slot(scale), parent, maxT);
-            SVO_FETCH_NODE();
-
-            // Truncate the positions to the `scale` grid (:329-334) on the FMA pipe: adding 2^scale with
-            // round-toward-zero leaves exactly the mantissa bits >= `scale` (positions are in [1, 2), the
-            // sum is in [2^scale, 2^(scale+1))), its lowest mantissa bit is the new idx bit, and
-            // subtracting 2^scale again is exact.
-            const float big = __uint_as_float(uint32_t(scale + 127) << 23);
-            const float tX = __fadd_rz(posX, big), tY = __fadd_rz(posY, big), tZ = __fadd_rz(posZ, big);
-            posX = subRn(tX, big);
-            posY = subRn(tY, big);
-            posZ = subRn(tZ, big);
-            // idx = bit 0 of tX | bit 0 of tY << 1 | bit 0 of tZ << 2, by two bit-selects
-            const uint32_t xy = (__float_as_uint(tX) & 1u) | ((__float_as_uint(tY) << 1) & ~1u);
-            const uint32_t xyz = (xy & 3u) | ((__float_as_uint(tZ) << 2) & ~3u);
-            childShift = (xyz ^ octantMask) & 7u;
-        }
-    }
-#undef SVO_FETCH_NODE
+    RayState<IdxT> r;
+    rayBegin<FAST, IdxT>(octree, ox, oy, oz, dx, dy, dz, r);
+    for (;;)
+        if (rayTrip<FAST, LOD, IdxT, THREADS>(octree, r, rayScale, stack, tOut, voxelOut)) break;
     __syncwarp();   // exited lanes do not take part; see the note on the single exit above
-    return childShift == kExitLeaf ? kHitLeaf : (LOD && childShift == kExitLod) ? kHitLod : kMiss;
+    return exitCode(r.childShift, LOD);
 }
 
 } // namespace svo

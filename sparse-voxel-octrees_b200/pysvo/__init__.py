@@ -24,6 +24,7 @@ LIB_PATH = PKG_DIR / "libsvo_b200.so"
 FLAVOUR_VALIDATION = 0
 FLAVOUR_FAST = 1
 BATCH_COHERENCE_ORDER = 0x100   # OR into the flavour of raymarch_batch[_device] for incoherent rays
+BATCH_LANE_REFILL = 0x200       # ... persistent warps, a lane that finishes its ray takes the next one
 MISS, HIT_LEAF, HIT_LOD = 0, 1, 2
 T_MISS = np.float32(1e10)
 VOXEL_NONE = np.uint64(0xFFFFFFFFFFFFFFFF)

@@ -110,12 +110,13 @@ def test_c4_ao_sdf2048_sample(pysvo, port, sdf2048):
     want = port.raymarch_batch(words, so, sd, 0.0, t_sentinel=float(T_MISS))
     hit = want["hit"] > 0
     assert 0.05 < hit.mean() < 0.95
-    for flavour in (pysvo.FLAVOUR_VALIDATION, pysvo.FLAVOUR_VALIDATION | pysvo.BATCH_COHERENCE_ORDER):
+    for flavour in (pysvo.FLAVOUR_VALIDATION, pysvo.FLAVOUR_VALIDATION | pysvo.BATCH_COHERENCE_ORDER,
+                    pysvo.FLAVOUR_VALIDATION | pysvo.BATCH_COHERENCE_ORDER | pysvo.BATCH_LANE_REFILL):
         got = tree.raymarch_batch(so, sd, 0.0, flavour)
         assert np.array_equal(got["hit"], want["hit"])
         assert np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32))
         assert np.array_equal(got["voxel"][hit], want["voxel"][hit])
         assert np.array_equal(got["normal"][hit], want["normal"][hit])
-    fast = tree.raymarch_batch(so, sd, 0.0, pysvo.FLAVOUR_FAST | pysvo.BATCH_COHERENCE_ORDER)
+    fast = tree.raymarch_batch(so, sd, 0.0, pysvo.FLAVOUR_FAST | pysvo.BATCH_COHERENCE_ORDER | pysvo.BATCH_LANE_REFILL)
     same = (fast["hit"] == want["hit"]) & (fast["voxel"] == np.where(hit, want["voxel"], pysvo.VOXEL_NONE))
     assert same.mean() >= 0.9999

@@ -301,16 +301,39 @@ def test_batch_nonfinite_rays_are_misses(pysvo, port, gpu_dragon, dragon_words):
     o[1000, 2] = -np.inf; bad[1000] = True
     d[4098, 0] = np.nan; bad[4098] = True
     want = port.raymarch_batch(words, o[~bad], d[~bad], 0.0, t_sentinel=float(T_MISS))
-    for flavour in (pysvo.FLAVOUR_VALIDATION, pysvo.FLAVOUR_FAST | pysvo.BATCH_COHERENCE_ORDER):
+    for flavour in (pysvo.FLAVOUR_VALIDATION, pysvo.FLAVOUR_FAST | pysvo.BATCH_COHERENCE_ORDER,
+                    pysvo.FLAVOUR_VALIDATION | pysvo.BATCH_LANE_REFILL):
         got = gpu_dragon.raymarch_batch(o, d, 0.0, flavour)
         assert (got["hit"][bad] == 0).all() and (got["t"][bad] == T_MISS).all()
         assert (got["voxel"][bad] == pysvo.VOXEL_NONE).all() and (got["normal"][bad] == 0).all()
         assert np.array_equal(got["hit"][~bad], want["hit"])
-        if flavour == pysvo.FLAVOUR_VALIDATION:
+        if (flavour & 0xFF) == pysvo.FLAVOUR_VALIDATION:
             assert np.array_equal(got["t"][~bad].view(np.uint32), want["t"].view(np.uint32))
     cam = pysvo.orbit_camera(0.0, 0.0, float("nan"))
     with pytest.raises(pysvo.SvoError):
         gpu_dragon.render_frame(cam, 64, 64, strips=2)
+
+
+@pytest.mark.parametrize("n", [1, 31, 32, 257, 4097, 100003])
+def test_batch_lane_refill_edge_sizes(pysvo, port, gpu_dragon, dragon_words, n):
+    """The persistent lane-refill kernel on ragged counts (fewer rays than a warp, one past a cursor chunk, ...), with and
+    without LOD exits: the same words at the same indices as the oracle."""
+    words, _ = dragon_words
+    rng = np.random.default_rng(100 + n)
+    o = rng.uniform(0.0, 3.0, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d[::7, 0] = 0.0
+    o[::5] = [1.5, 1.2, 1.3]
+    for rs in (0.0, 0.02):
+        want = port.raymarch_batch(words, o, d, rs, t_sentinel=float(T_MISS))
+        got = gpu_dragon.raymarch_batch(o, d, rs, pysvo.FLAVOUR_VALIDATION | pysvo.BATCH_LANE_REFILL)
+        assert np.array_equal(got["hit"], want["hit"])
+        assert np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32))
+        hit = want["hit"] > 0
+        assert np.array_equal(got["voxel"][hit], want["voxel"][hit])
+        assert np.all(got["voxel"][~hit] == pysvo.VOXEL_NONE)
+        leaf = want["hit"] == 1
+        assert np.array_equal(got["normal"][leaf], want["normal"][leaf]) and np.all(got["normal"][~leaf] == 0)
 
 
 def test_batch_multi_chunk_host_api(pysvo, port, gpu_dragon, dragon_words):

@@ -101,18 +101,21 @@ def test_ambient_occlusion_batches_bit_exact(pysvo, port, sdf):
     assert same.mean() >= 0.9999
     # SVO_BATCH_COHERENCE_ORDER: threads take the rays direction bin by direction bin; every output must be
     # the same word at the same index, in both flavours, also with LOD exits and non-unit directions
+    # SVO_BATCH_LANE_REFILL (persistent warps, a finished lane takes the next ray), alone and with the order
     for flavour, base in ((pysvo.FLAVOUR_VALIDATION, got), (pysvo.FLAVOUR_FAST, fast)):
-        re = tree.raymarch_batch(ao_o, ao_d, 0.0, flavour | pysvo.BATCH_COHERENCE_ORDER)
-        for key in ("hit", "normal", "voxel"):
-            assert np.array_equal(re[key], base[key]), key
-        assert np.array_equal(re["t"].view(np.uint32), base["t"].view(np.uint32))
+        for extra in (pysvo.BATCH_COHERENCE_ORDER, pysvo.BATCH_LANE_REFILL, pysvo.BATCH_COHERENCE_ORDER | pysvo.BATCH_LANE_REFILL):
+            re = tree.raymarch_batch(ao_o, ao_d, 0.0, flavour | extra)
+            for key in ("hit", "normal", "voxel"):
+                assert np.array_equal(re[key], base[key]), (key, extra)
+            assert np.array_equal(re["t"].view(np.uint32), base["t"].view(np.uint32)), extra
     scaled = (ao_d * np.linspace(0.25, 7.0, ao_d.shape[0], dtype=np.float32)[:, None]).astype(np.float32)
     a = tree.raymarch_batch(ao_o, scaled, 0.01, pysvo.FLAVOUR_VALIDATION)
-    b = tree.raymarch_batch(ao_o, scaled, 0.01, pysvo.FLAVOUR_VALIDATION | pysvo.BATCH_COHERENCE_ORDER)
     assert (a["hit"] == 2).any()
-    for key in ("hit", "normal", "voxel"):
-        assert np.array_equal(a[key], b[key]), key
-    assert np.array_equal(a["t"].view(np.uint32), b["t"].view(np.uint32))
+    for extra in (pysvo.BATCH_COHERENCE_ORDER, pysvo.BATCH_LANE_REFILL | pysvo.BATCH_COHERENCE_ORDER):
+        b = tree.raymarch_batch(ao_o, scaled, 0.01, pysvo.FLAVOUR_VALIDATION | extra)
+        for key in ("hit", "normal", "voxel"):
+            assert np.array_equal(a[key], b[key]), (key, extra)
+        assert np.array_equal(a["t"].view(np.uint32), b["t"].view(np.uint32)), extra
 
 
 def test_large_scene_frame_if_cached(pysvo, port):
