@@ -570,7 +570,11 @@ def run_own(args):
     ensure_scene(w, 0, lambda: None)
     W, H = w["width"], w["height"]
     flavour = pysvo.FLAVOUR_VALIDATION if args.validation else pysvo.FLAVOUR_FAST
-    multi = pysvo.MultiOctree(w["path"], devices=tuple(range(n_dev)))
+    devices = tuple(range(n_dev))
+    if os.environ.get("SVO_BENCH_DEVICES"):      # (experiment switch, never set by default: e.g. "0,0" = two replicas on one GPU)
+        devices = tuple(int(x) for x in os.environ["SVO_BENCH_DEVICES"].split(","))
+        n_dev = len(devices)
+    multi = pysvo.MultiOctree(w["path"], devices=devices)
     tree = multi.tree(0)
     cams = [pysvo.orbit_camera(*c) for c in cameras(pysvo, w, ORBIT)]
     path = lambda first, count: [cams[k % ORBIT] for k in range(first, first + count)]  # noqa: E731

@@ -8,7 +8,9 @@
 // devices too. The host never waits for the GPU inside a sequence except to hand a finished host frame to the caller.
 #include "svo_capi_internal.hpp"
 
+#include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <chrono>
 #include <condition_variable>
 #include <memory>
@@ -86,6 +88,16 @@ void relax(unsigned &spins) {
     }
 }
 
+// Host leg with several devices: strided copies on the copy engine (default) or a kernel storing into the mapped host
+// frame (SVO_MULTI_HOST_COPY=kernel; measured against each other in profiles/experiments/r02_host_leg.md).
+bool hostCopyByKernel() {
+    static const bool byKernel = [] {
+        const char *e = getenv("SVO_MULTI_HOST_COPY");
+        return e && !strcmp(e, "kernel");
+    }();
+    return byKernel;
+}
+
 // One device's share of a sequence. Runs on the device's worker thread with the device current.
 int runSequence(svo_multi *M, Replica &rep, const Job &job) {
     const int N = int(M->reps.size());
@@ -150,13 +162,22 @@ int runSequence(svo_multi *M, Replica &rep, const Job &job) {
             SVO_CUDA(cudaStreamWaitEvent(rep.copy, rep.done[l], 0));
             if (N == 1) {
                 SVO_CUDA(cudaMemcpyAsync(host, rep.fb[l], frameBytes, cudaMemcpyDeviceToHost, rep.copy));   // copy engine
-            } else {
+            } else if (hostCopyByKernel()) {
                 // this device's stripes only, stored by a kernel straight into the (mapped, page-locked) host frame
                 void *mapped = nullptr;
                 SVO_CUDA(cudaHostGetDevicePointer(&mapped, host, 0));
                 SVO_CUDA(svo::launchCopyOwnedColumns(plan->dev, desc.width, desc.height, rep.fb[l], static_cast<uint32_t *>(mapped),
                                                      rep.index, N, rep.copy));
                 ++rep.launches;
+            } else {
+                // this device's stripes only, one strided copy per stripe on the copy engine (no SM involved)
+                const int run = svo::tileRunLength(N);
+                const size_t pitch = size_t(desc.width)*sizeof(uint32_t);
+                for (int tx0 = rep.index*run; tx0 < plan->dev.tileCols; tx0 += N*run) {
+                    const int x0 = tx0*8, x1 = std::min((tx0 + run)*8, desc.width);
+                    SVO_CUDA(cudaMemcpy2DAsync(host + x0, pitch, rep.fb[l] + x0, pitch, size_t(x1 - x0)*sizeof(uint32_t),
+                                               size_t(desc.height), cudaMemcpyDeviceToHost, rep.copy));
+                }
             }
             SVO_CUDA(cudaEventRecord(rep.copied[l], rep.copy));
             rep.copiedRecorded[l] = true;
@@ -292,11 +313,16 @@ int createMulti(const uint32_t *words, uint64_t nWords, const float center[3], c
     return SVO_OK;
 }
 
-// widest stripe <= 16 tile columns that still deals every device the same number of columns (what one PCIe write
-// burst of the host leg carries: 128-byte runs reach 28 GB/s into mapped host memory, 512-byte runs 43 GB/s)
+// widest stripe <= 32 tile columns that still deals every device the same number of columns: a stripe's row is what one
+// DMA burst of the host leg carries (measured at N = 2, 4K frames, copy engine: 15 / 30 / 60 columns wide -> 60.9 / 67.9 /
+// 66.7 GB/s into host memory; wider stripes also unbalance the devices' shares of the rays)
 int hostStripeRun(int width, int nDevices) {
     const int tileCols = (width - 1)/8 + 1;
-    for (int r = 16; r > 4; --r)
+    if (const char *e = getenv("SVO_MULTI_HOST_RUN")) {      // experiment switch
+        const int v = atoi(e);
+        if (v > 0) return v;
+    }
+    for (int r = 32; r > 4; --r)
         if (tileCols % (nDevices*r) == 0) return r;
     return 4;
 }
