@@ -34,7 +34,7 @@ raymarchBatchKernel(const uint32_t *__restrict__ octree, uint64_t n, const float
                     float *__restrict__ t, uint32_t *__restrict__ normal, uint64_t *__restrict__ voxel,
                     const uint32_t *__restrict__ order) {
     extern __shared__ __align__(16) unsigned char smem[];
-    SmemStack<IdxT, kBatchThreads> stack;
+    SmemStack<IdxT, kBatchThreads, LOD> stack;
     stack.init(smem);
 
     uint64_t i = uint64_t(blockIdx.x)*blockDim.x + threadIdx.x;
@@ -80,7 +80,7 @@ raymarchBatchRefillKernel(const uint32_t *__restrict__ octree, uint64_t n, const
                           float *__restrict__ t, uint32_t *__restrict__ normal, uint64_t *__restrict__ voxel,
                           const uint32_t *__restrict__ order, unsigned long long *__restrict__ cursor, int refillIdle) {
     extern __shared__ __align__(16) unsigned char smem[];
-    SmemStack<IdxT, kBatchThreads> stack;
+    SmemStack<IdxT, kBatchThreads, LOD> stack;
     stack.init(smem);
     constexpr unsigned kFull = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
@@ -177,7 +177,7 @@ coarsePassKernel(const uint32_t *__restrict__ octree, FramePlanDev plan, FrameCo
                  FrameCounters *__restrict__ counters, int tileRank, int tileWorld, int tileRun, int colSlots,
                  int totalSlots) {
     extern __shared__ __align__(16) unsigned char smem[];
-    SmemStack<IdxT, kCoarseThreads> stack;
+    SmemStack<IdxT, kCoarseThreads, true> stack;
     stack.init(smem);
 
     int k = blockIdx.x*blockDim.x + threadIdx.x;
@@ -290,7 +290,7 @@ finePassKernel(const uint32_t *__restrict__ octree, FramePlanDev plan, FrameCons
                const TileRecord *__restrict__ tiles, const FrameCounters *__restrict__ counters,
                uint32_t *__restrict__ rgba) {
     extern __shared__ __align__(16) unsigned char smem[];
-    SmemStack<IdxT, kTileThreads> stack;
+    SmemStack<IdxT, kTileThreads, false> stack;
     stack.init(smem);
 
     // kTilesPerBlock consecutive list entries per block: each warp renders the same 8x4 half of each of
@@ -337,7 +337,7 @@ finePassStridedKernel(const uint32_t *__restrict__ octree, FramePlanDev plan, Fr
                       uint32_t *__restrict__ rgba, int pixelStride) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint32_t corner[64];
-    SmemStack<IdxT, kTileThreads> stack;
+    SmemStack<IdxT, kTileThreads, false> stack;
     stack.init(smem);
     const unsigned tile = blockIdx.x;
     if (tile >= counters->tilesRendered) return;
@@ -422,7 +422,7 @@ template <bool FAST, bool LOD, typename IdxT>
 cudaError_t launchBatchT(const TreeDev &tree, uint64_t n, const float *o, const float *d, float rayScale,
                          uint8_t *hit, float *t, uint32_t *normal, uint64_t *voxel, const uint32_t *order,
                          cudaStream_t stream) {
-    size_t smem = SmemStack<IdxT, kBatchThreads>::bytes(stackSlots(tree));
+    size_t smem = SmemStack<IdxT, kBatchThreads, LOD>::bytes(stackSlots(tree));
     auto kernel = raymarchBatchKernel<FAST, LOD, IdxT>;
     cudaError_t e = ensureSmem(kernel, smem);
     if (e != cudaSuccess) return e;
@@ -436,7 +436,7 @@ template <bool FAST, bool LOD, typename IdxT>
 cudaError_t launchBatchRefillT(const TreeDev &tree, uint64_t n, const float *o, const float *d, float rayScale,
                                uint8_t *hit, float *t, uint32_t *normal, uint64_t *voxel, const uint32_t *order,
                                unsigned long long *cursor, cudaStream_t stream) {
-    size_t smem = SmemStack<IdxT, kBatchThreads>::bytes(stackSlots(tree));
+    size_t smem = SmemStack<IdxT, kBatchThreads, LOD>::bytes(stackSlots(tree));
     auto kernel = raymarchBatchRefillKernel<FAST, LOD, IdxT>;
     cudaError_t e = ensureSmem(kernel, smem);
     if (e != cudaSuccess) return e;
@@ -464,7 +464,7 @@ cudaError_t launchBatchRefillT(const TreeDev &tree, uint64_t n, const float *o, 
 template <typename IdxT>
 cudaError_t launchCoarseT(const TreeDev &tree, const FramePlanDev &plan, const FrameConsts &consts, float *depth,
                           FrameCounters *counters, int tileRank, int tileWorld, cudaStream_t stream) {
-    size_t smem = SmemStack<IdxT, kCoarseThreads>::bytes(stackSlots(tree));
+    size_t smem = SmemStack<IdxT, kCoarseThreads, true>::bytes(stackSlots(tree));
     auto kernel = coarsePassKernel<IdxT>;
     cudaError_t e = ensureSmem(kernel, smem);
     if (e != cudaSuccess) return e;
@@ -484,7 +484,7 @@ template <bool FAST, typename IdxT>
 cudaError_t launchFineT(const TreeDev &tree, const FramePlanDev &plan, const FrameConsts &consts,
                         const TileRecord *tiles, const FrameCounters *counters, uint32_t *rgba, int owned,
                         int pixelStride, cudaStream_t stream) {
-    size_t smem = SmemStack<IdxT, kTileThreads>::bytes(stackSlots(tree));
+    size_t smem = SmemStack<IdxT, kTileThreads, false>::bytes(stackSlots(tree));
     if (pixelStride > 1) {
         auto strided = finePassStridedKernel<FAST, IdxT>;
         cudaError_t es = ensureSmem(strided, smem);

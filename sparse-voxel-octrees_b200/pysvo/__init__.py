@@ -20,6 +20,8 @@ import numpy as np
 
 PKG_DIR = Path(__file__).resolve().parent.parent
 LIB_PATH = PKG_DIR / "libsvo_b200.so"
+if os.environ.get("PYSVO_LIB"):      # A/B experiments only: another build of the same library (same ABI)
+    LIB_PATH = Path(os.environ["PYSVO_LIB"]).resolve()
 
 FLAVOUR_VALIDATION = 0
 FLAVOUR_FAST = 1
