@@ -605,7 +605,7 @@ def run_own(args):
     # ---- end to end: every frame of the same camera path lands in page-locked host memory (ring of four frames);
     # with N > 1 every GPU ships the stripes it rendered over its own PCIe link. Host clock around the call.
     e2e_steps = min(steps, 300)
-    ring = [pysvo.PinnedArray((H, W), np.uint32) for _ in range(4)]
+    ring = [pysvo.PinnedArray((H, W), np.uint32) for _ in range(max(4, int(os.environ.get("SVO_MULTI_LANES", "0") or 0)))]
     hosts = [r.array for r in ring]
     multi.render_sequence(path(0, 8), W, H, strips=STRIPS, flavour=flavour, output=pysvo.OUTPUT_HOST, host_frames=hosts)
     e2e_rounds = []

@@ -321,6 +321,8 @@ int buildPlan(svo_tree *tree, int width, int height, int strips, FramePlan &plan
         SVO_CUDA(cudaMalloc(&plan.dDepth[b], size_t(p.totalCorners)*sizeof(float)));
         SVO_CUDA(cudaMalloc(&plan.dTiles[b], size_t(p.totalTiles > 0 ? p.totalTiles : 1)*sizeof(svo::TileRecord)));
         SVO_CUDA(cudaMalloc(&plan.dCounters[b], sizeof(svo::FrameCounters)));
+        if (const int words = svo::prefixRecordWords(tree->dev()))
+            SVO_CUDA(cudaMalloc(&plan.dPrefix[b], size_t(p.totalTiles > 0 ? p.totalTiles : 1)*size_t(words)*sizeof(uint32_t)));
         SVO_CUDA(cudaMemset(plan.dCounters[b], 0, sizeof(svo::FrameCounters)));
         SVO_CUDA(cudaEventCreateWithFlags(&plan.coarseDone[b], cudaEventDisableTiming));
         SVO_CUDA(cudaEventCreateWithFlags(&plan.fineDone[b], cudaEventDisableTiming));
@@ -413,6 +415,15 @@ void applyL2Window(svo_tree *tree, cudaStream_t s) {
     cudaGetLastError();
 }
 
+// SVO_NO_PREFIX_RESTART=1 (experiment switch): the FAST fine pass starts every ray at the root, like VALIDATION.
+bool prefixRestartEnabled() {
+    static const bool on = [] {
+        const char *e = getenv("SVO_NO_PREFIX_RESTART");
+        return !(e && *e == '1');
+    }();
+    return on;
+}
+
 // Enqueues one frame. The beam pass goes to the tree's high-priority internal stream (unless the
 // caller wants the depth buffer in its own memory, which must be ordered on `stream`), the tile
 // classifier and the fine pass to `stream`. Returns the double-buffer slot used. Caller holds
@@ -453,9 +464,10 @@ int enqueueFrame(svo_tree *tree, FramePlan *plan, const svo_camera *cam, const s
     SVO_CUDA(svo::launchClassifyTiles(plan->dev, f, depth, dRgba, desc->tile_rank, desc->tile_world, desc->pixel_stride,
                                       plan->dTiles[b], plan->dCounters[b], plan->dFineTotal, stream));
     ++n;
+    uint32_t *prefix = prefixRestartEnabled() ? plan->dPrefix[b] : nullptr;
     SVO_CUDA(svo::launchFinePass(tree->dev(), plan->dev, f, desc->flavour, plan->dTiles[b], plan->dCounters[b], dRgba,
-                                 desc->tile_rank, desc->tile_world, desc->pixel_stride, stream));
-    ++n;
+                                 desc->tile_rank, desc->tile_world, desc->pixel_stride, prefix, stream));
+    n += 1 + (prefix ? svo::finePassUsesPrefix(tree->dev(), desc->flavour, desc->pixel_stride) : 0);
     if (wantStats) {
         SVO_CUDA(cudaEventRecord(plan->timing[b][3], stream));
         SVO_CUDA(cudaMemcpyAsync(plan->hCounters + b, plan->dCounters[b], sizeof(svo::FrameCounters),

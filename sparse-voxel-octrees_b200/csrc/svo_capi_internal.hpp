@@ -74,6 +74,7 @@ struct FramePlan {
     float *dDepth[kRing] = {};             // totalCorners floats each
     svo::TileRecord *dTiles[kRing] = {};   // totalTiles records each (worst case: every tile rendered)
     svo::FrameCounters *dCounters[kRing] = {};
+    uint32_t *dPrefix[kRing] = {};         // per tile: the traversal state its corner rays share (FAST fine pass)
     svo::FrameCounters *hCounters = nullptr;            // pinned, kRing entries
     unsigned long long *dFineTotal = nullptr;           // fine rays of every frame since it was last zeroed (frame sequences)
     cudaEvent_t coarseDone[kRing] = {};    // beam pass of the slot finished (internal stream)
@@ -101,6 +102,7 @@ struct FramePlan {
             if (dDepth[b]) cudaFree(dDepth[b]);
             if (dTiles[b]) cudaFree(dTiles[b]);
             if (dCounters[b]) cudaFree(dCounters[b]);
+            if (dPrefix[b]) cudaFree(dPrefix[b]);
             if (coarseDone[b]) cudaEventDestroy(coarseDone[b]);
             if (fineDone[b]) cudaEventDestroy(fineDone[b]);
             for (int k = 0; k < 4; ++k) if (timing[b][k]) cudaEventDestroy(timing[b][k]);

@@ -282,13 +282,93 @@ classifyTilesKernel(FramePlanDev plan, float beamBias, const float *__restrict__
     }
 }
 
+// ---- K2c: the traversal prefix the rays of a tile share (FAST flavour only) ----------------------------------------
+// The four corner pixels' rays of a tile are traced in lock step, four lanes per tile, for as long as all four are at
+// the same loop-head state (same node, same child cell): pushes from the root down to the first empty cell near the
+// tile's start point, and the first steps through empty space. Every other ray of the tile lies inside the cone of
+// the four, and each decision of the traversal compares the t of two axis-aligned planes along a ray from a common
+// origin -- (c1 - o.a)/d.a < (c2 - o.b)/d.b, linear in d once the octant is fixed -- so while the four corner rays
+// agree, every ray between them takes the same decisions: the fine pass starts its rays at the last shared state
+// (rayRestart) instead of at the root and skips those trips (8192^3 at 4K: 8.8 of 37 trips per ray, measured on the
+// oracle's traces; all of them coherent pushes and steps, 14 % of the pass's warp instructions). What is not covered
+// by the argument is rounding: a ray for which one of the skipped comparisons is within an ulp of a tie, or whose
+// start point (at distance startT on its own, Quake-normalised direction) is on the other side of a cell face from
+// all four corners' -- measured: 11 of 7.86 M rays take a different first cell, and those still find their voxel
+// through the normal traversal from there. That is why this is the FAST flavour only (>= 99.99 % identical pixels
+// required, 100 % measured); the VALIDATION flavour always starts at the root.
+constexpr int kPrefixThreads = 64;      // 16 tiles per block
+constexpr int kPrefixMaxTrips = 64;
+
+__global__ void __launch_bounds__(kPrefixThreads)
+tilePrefixKernel(const uint32_t *__restrict__ octree, FramePlanDev plan, FrameConsts f, const TileRecord *__restrict__ tiles,
+                 const FrameCounters *__restrict__ counters, uint32_t *__restrict__ prefix, int recordWords) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    typedef SmemStack<uint32_t, kPrefixThreads, false> Stack;
+    Stack stack;
+    stack.init(smem);
+    constexpr unsigned kFull = 0xffffffffu;
+    const unsigned nTiles = counters->tilesRendered;
+    const unsigned tile = blockIdx.x*(kPrefixThreads/4) + (threadIdx.x >> 2);
+    const unsigned corner = threadIdx.x & 3u;
+    const unsigned groupShift = threadIdx.x & 28u;          // first lane of this tile's four
+    bool active = tile < nTiles;
+    if (__ballot_sync(kFull, active) == 0) return;
+
+    RayState<uint32_t> r;
+    r.parent = 0; r.scale = 0; r.childShift = kExitMiss; r.octantMask = 0;
+    r.posX = r.posY = r.posZ = 0.0f;
+    if (active) {
+        const uint4 rec = __ldg(reinterpret_cast<const uint4 *>(tiles) + tile);
+        const int x0 = int(rec.x & 0xFFFFu), y0 = int(rec.x >> 16);
+        const int w = min(x0 + 8, plan.width) - x0, h = min(y0 + 8, int(rec.y)) - y0;
+        const int px = x0 + ((corner & 1u) ? w - 1 : 0), py = y0 + ((corner & 2u) ? h - 1 : 0);
+        const float startT = __uint_as_float(rec.z);
+        float rx, ry, rz;
+        rayDirection(f, __ldg(plan.dxFine + px), __ldg(plan.dyFine + py), rx, ry, rz);
+        rayBegin<true, uint32_t>(octree, addRn(f.posX, mulRn(rx, startT)), addRn(f.posY, mulRn(ry, startT)),
+                                 addRn(f.posZ, mulRn(rz, startT)), rx, ry, rz, r);
+    }
+    uint32_t snapParent = 0, snapPacked = 0;
+    float snapX = 0.0f, snapY = 0.0f, snapZ = 0.0f;
+    float tHit;
+    uint64_t vox;
+    for (int trip = 0; trip < kPrefixMaxTrips; ++trip) {
+        // all four rays of the tile in flight and at the same loop-head state?
+        const uint32_t key = uint32_t(r.scale) | (r.childShift << 8) | (r.octantMask << 16);
+        const unsigned alive = __ballot_sync(kFull, active && r.childShift < 8u);
+        const unsigned same = __match_any_sync(kFull, (uint64_t(r.parent) << 32) | key);
+        active = active && ((alive >> groupShift) & 0xFu) == 0xFu && ((same >> groupShift) & 0xFu) == 0xFu;
+        if (__ballot_sync(kFull, active) == 0) break;
+        if (active) {
+            snapParent = r.parent;
+            snapPacked = key | (1u << 24);
+            snapX = r.posX; snapY = r.posY; snapZ = r.posZ;
+            rayTrip<true, false, uint32_t, kPrefixThreads>(octree, r, 0.0f, stack, tHit, vox);
+        }
+    }
+    if (corner == 0 && tile < nTiles) {
+        uint32_t *out = prefix + size_t(tile)*size_t(recordWords);
+        const int scale = int(snapPacked & 0xFFu);
+        if (scale >= kMaxScale - 1) snapPacked = 0;     // nothing shared below the root: the rays start there anyway
+        *reinterpret_cast<uint4 *>(out) = make_uint4(snapParent, snapPacked, __float_as_uint(snapX), __float_as_uint(snapY));
+        out[4] = __float_as_uint(snapZ);
+        if (snapPacked)
+            for (int sc = scale + 1; sc < kMaxScale; ++sc) {        // the parents above the shared state (this lane's stack holds them)
+                uint32_t parent;
+                float unused;
+                Stack::load(stack.slot(sc), parent, unused);
+                out[kPrefixHeaderWords + (kMaxScale - 1 - sc)] = parent;
+            }
+    }
+}
+
 // ---- K3 -------------------------------------------------------------------
 
 template <bool FAST, typename IdxT>
 __global__ void __launch_bounds__(kTileThreads, 32)
 finePassKernel(const uint32_t *__restrict__ octree, FramePlanDev plan, FrameConsts f,
                const TileRecord *__restrict__ tiles, const FrameCounters *__restrict__ counters,
-               uint32_t *__restrict__ rgba) {
+               uint32_t *__restrict__ rgba, const uint32_t *__restrict__ prefix, int prefixWords) {
     extern __shared__ __align__(16) unsigned char smem[];
     SmemStack<IdxT, kTileThreads, false> stack;
     stack.init(smem);
@@ -315,7 +395,20 @@ finePassKernel(const uint32_t *__restrict__ octree, FramePlanDev plan, FrameCons
 
         float tHit;
         uint64_t vox;
-        const int code = raymarch<FAST, false, IdxT, kTileThreads>(octree, ox, oy, oz, rx, ry, rz, 0.0f, stack, tHit, vox);
+        int code;
+        if (FAST && sizeof(IdxT) == 4 && prefix) {
+            // start at the state the tile's corner rays shared last (tilePrefixKernel) instead of at the root
+            RayState<uint32_t> r;
+            raySetup<FAST, uint32_t>(ox, oy, oz, rx, ry, rz, r);
+            const SmemStack<uint32_t, kTileThreads, false> &stack32 = reinterpret_cast<const SmemStack<uint32_t, kTileThreads, false> &>(stack);
+            if (!rayRestart<FAST, kTileThreads>(octree, r, prefix + size_t(tile)*size_t(prefixWords), stack32)) rayRoot<FAST, uint32_t>(octree, r);
+            for (;;)
+                if (rayTrip<FAST, false, uint32_t, kTileThreads>(octree, r, 0.0f, stack32, tHit, vox)) break;
+            __syncwarp();
+            code = exitCode(r.childShift, false);
+        } else {
+            code = raymarch<FAST, false, IdxT, kTileThreads>(octree, ox, oy, oz, rx, ry, rz, 0.0f, stack, tHit, vox);
+        }
         // the warp is convergent again here: one material fetch and one pass through the shading code
         // for all its hits together (misses read some descriptor and discard the result)
         const uint32_t material = ldNode(octree + IdxT(vox));   // VoxelOctree.cpp:282
@@ -377,6 +470,10 @@ inline bool wideIndex(const TreeDev &tree) {
 }
 
 inline uint32_t stackSlots(const TreeDev &tree) { return tree.depth > 1 ? tree.depth - 1 : 1; }
+
+} // namespace
+int prefixRecordWords(const TreeDev &tree);
+namespace {
 
 template <typename K>
 cudaError_t ensureSmem(K kernel, size_t bytes) {
@@ -483,7 +580,7 @@ cudaError_t launchCoarseT(const TreeDev &tree, const FramePlanDev &plan, const F
 template <bool FAST, typename IdxT>
 cudaError_t launchFineT(const TreeDev &tree, const FramePlanDev &plan, const FrameConsts &consts,
                         const TileRecord *tiles, const FrameCounters *counters, uint32_t *rgba, int owned,
-                        int pixelStride, cudaStream_t stream) {
+                        int pixelStride, uint32_t *prefix, cudaStream_t stream) {
     size_t smem = SmemStack<IdxT, kTileThreads, false>::bytes(stackSlots(tree));
     if (pixelStride > 1) {
         auto strided = finePassStridedKernel<FAST, IdxT>;
@@ -496,7 +593,18 @@ cudaError_t launchFineT(const TreeDev &tree, const FramePlanDev &plan, const Fra
     cudaError_t e = ensureSmem(kernel, smem);
     if (e != cudaSuccess) return e;
     int blocks = (owned + int(kTilesPerBlock) - 1)/int(kTilesPerBlock);
-    kernel<<<blocks, kTileThreads, smem, stream>>>(tree.words, plan, consts, tiles, counters, rgba);
+    const int prefixWords = prefixRecordWords(tree);
+    if (!FAST || sizeof(IdxT) != 4 || prefixWords == 0) prefix = nullptr;
+    if (prefix) {
+        // K2c: the tile's shared traversal prefix, four corner rays per tile in lock step
+        const size_t psmem = SmemStack<uint32_t, kPrefixThreads, false>::bytes(stackSlots(tree));
+        if ((e = ensureSmem(tilePrefixKernel, psmem)) != cudaSuccess) return e;
+        const int tilesPerBlock = kPrefixThreads/4;
+        tilePrefixKernel<<<(owned + tilesPerBlock - 1)/tilesPerBlock, kPrefixThreads, psmem, stream>>>(
+            tree.words, plan, consts, tiles, counters, prefix, prefixWords);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    kernel<<<blocks, kTileThreads, smem, stream>>>(tree.words, plan, consts, tiles, counters, rgba, prefix, prefixWords);
     return cudaGetLastError();
 }
 
@@ -695,15 +803,33 @@ cudaError_t launchClassifyTiles(const FramePlanDev &plan, const FrameConsts &con
 
 cudaError_t launchFinePass(const TreeDev &tree, const FramePlanDev &plan, const FrameConsts &consts, int flavour,
                            const TileRecord *tiles, const FrameCounters *counters, uint32_t *rgba,
-                           int tileRank, int tileWorld, int pixelStride, cudaStream_t stream) {
+                           int tileRank, int tileWorld, int pixelStride, uint32_t *prefix, cudaStream_t stream) {
     int owned = ownedTiles(plan, tileRank, tileWorld);
     if (owned <= 0) return cudaSuccess;
     bool wide = wideIndex(tree);
     if (flavour != 0)
-        return wide ? launchFineT<true, uint64_t>(tree, plan, consts, tiles, counters, rgba, owned, pixelStride, stream)
-                    : launchFineT<true, uint32_t>(tree, plan, consts, tiles, counters, rgba, owned, pixelStride, stream);
-    return wide ? launchFineT<false, uint64_t>(tree, plan, consts, tiles, counters, rgba, owned, pixelStride, stream)
-                : launchFineT<false, uint32_t>(tree, plan, consts, tiles, counters, rgba, owned, pixelStride, stream);
+        return wide ? launchFineT<true, uint64_t>(tree, plan, consts, tiles, counters, rgba, owned, pixelStride, prefix, stream)
+                    : launchFineT<true, uint32_t>(tree, plan, consts, tiles, counters, rgba, owned, pixelStride, prefix, stream);
+    return wide ? launchFineT<false, uint64_t>(tree, plan, consts, tiles, counters, rgba, owned, pixelStride, prefix, stream)
+                : launchFineT<false, uint32_t>(tree, plan, consts, tiles, counters, rgba, owned, pixelStride, prefix, stream);
+}
+
+// Words per tile of the shared-prefix records (header + one parent per stack slot, rounded to 16 bytes); 0 when the
+// tree's kernels do not use them (64-bit word indices).
+// Shallow trees do not use them either: what the restart saves is the descent from the root, and below ten levels the
+// extra launch costs more than that (measured on one box, FAST frames with / without: 8192^3 (13 levels) at 4K 9.91 /
+// 9.07 Grays/s, its fly-through 11.88 / 10.65, 2048^3 (11 levels) at 1080p 8.80 / 8.45, the 256^3 Dragon (8 levels) at
+// 720p 12.15 / 12.57).
+constexpr uint32_t kPrefixMinDepth = 10;
+
+int prefixRecordWords(const TreeDev &tree) {
+    if (wideIndex(tree) || tree.depth < kPrefixMinDepth) return 0;
+    return (kPrefixHeaderWords + int(stackSlots(tree)) + 3) & ~3;
+}
+
+// 1 when launchFinePass with these arguments and a prefix buffer launches tilePrefixKernel as well (launch counts)
+int finePassUsesPrefix(const TreeDev &tree, int flavour, int pixelStride) {
+    return flavour != 0 && pixelStride <= 1 && prefixRecordWords(tree) > 0 ? 1 : 0;
 }
 
 // The pixels of the tile columns a rank owns, from one framebuffer to another of the same pitch: thread k of a

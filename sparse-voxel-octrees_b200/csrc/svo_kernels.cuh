@@ -86,9 +86,13 @@ cudaError_t launchClassifyTiles(const FramePlanDev &plan, const FrameConsts &con
 
 // Fine pass over the tile list (grid covers the worst case; blocks past the list length exit).
 // pixelStride > 1: renderTile's preview mode (Main.cpp:101-106), one ray per stride x stride block of a tile.
+// prefix != nullptr (room for prefixRecordWords(tree) words per owned tile): in the FAST flavour the rays of a tile
+// start at the traversal state its four corner rays share (tilePrefixKernel, launched first) instead of at the root.
 cudaError_t launchFinePass(const TreeDev &tree, const FramePlanDev &plan, const FrameConsts &consts, int flavour,
                            const TileRecord *tiles, const FrameCounters *counters, uint32_t *rgba,
-                           int tileRank, int tileWorld, int pixelStride, cudaStream_t stream);
+                           int tileRank, int tileWorld, int pixelStride, uint32_t *prefix, cudaStream_t stream);
+int prefixRecordWords(const TreeDev &tree);
+int finePassUsesPrefix(const TreeDev &tree, int flavour, int pixelStride);
 
 // The owned tile columns' pixels from `src` to `dst` (both width x height, pitch = width): the per-rank
 // device -> host leg of a multi-GPU frame when `dst` is mapped page-locked host memory.

@@ -20,7 +20,18 @@
 
 namespace {
 
-constexpr int kLanes = 4;       // frames in flight: hides the fine pass's long-ray tail and the frame barrier
+constexpr int kLanes = 8;       // most frames in flight (streams, framebuffers, events per device)
+constexpr int kDefaultLanes = 4; // frames in flight: hides the fine pass's long-ray tail and the frame barrier
+
+// SVO_MULTI_LANES (experiment switch): frames in flight, 1 .. 8
+int lanesInFlight() {
+    static const int lanes = [] {
+        const char *e = getenv("SVO_MULTI_LANES");
+        const int v = e ? atoi(e) : 0;
+        return v >= 1 && v <= kLanes ? v : kDefaultLanes;
+    }();
+    return lanes;
+}
 
 struct Job {
     const svo_camera *cams = nullptr;
@@ -29,7 +40,7 @@ struct Job {
     int output = SVO_OUTPUT_DEVICE;
     uint32_t *const *hostFrames = nullptr;
     int nHost = 0;
-    int lanes = kLanes;
+    int lanes = kDefaultLanes;
 };
 
 struct Replica {
@@ -61,7 +72,7 @@ struct svo_multi {
     cudaEvent_t slotFree[kLanes] = {};  // gather[l] may be overwritten (recorded on gatherStream)
     bool slotFreeRecorded[kLanes] = {};
     cudaEvent_t seqStart = nullptr, seqStop = nullptr;
-    int lastFrames = 0, lastLanes = kLanes;
+    int lastFrames = 0, lastLanes = 4;
 
     std::mutex callMutex;               // one sequence at a time
     std::mutex m;
@@ -390,7 +401,7 @@ int svo_multi_render_sequence(svo_multi *M, const svo_camera *cams, int n_frames
     job.output = output;
     job.hostFrames = host_frames;
     job.nHost = n_host_frames;
-    job.lanes = output == SVO_OUTPUT_HOST ? std::min(kLanes, n_host_frames) : kLanes;
+    job.lanes = output == SVO_OUTPUT_HOST ? std::min(lanesInFlight(), n_host_frames) : lanesInFlight();
     const int run = N > 1 ? (output == SVO_OUTPUT_HOST ? hostStripeRun(desc.width, N) : 4) : 1;
     if (N > 1) svo::setTileRunLength(run);
 

@@ -245,9 +245,10 @@ __device__ __forceinline__ void fetchNode(const uint32_t *__restrict__ octree, R
     r.farWord = ldNode(node + 1);
 }
 
+// dT, bT and the octant mirroring of a ray (:214-232): everything about the ray that does not depend on where in the
+// tree it is.
 template <bool FAST, typename IdxT>
-__device__ __forceinline__ void rayBegin(const uint32_t *__restrict__ octree, float ox, float oy, float oz,
-                                         float dx, float dy, float dz, RayState<IdxT> &r) {
+__device__ __forceinline__ void raySetup(float ox, float oy, float oz, float dx, float dy, float dz, RayState<IdxT> &r) {
     typedef Arith<FAST> A;
     if (fabsf(dx) < 1e-4f) dx = 1e-4f;      // :217-219, sign dropped on purpose
     if (fabsf(dy) < 1e-4f) dy = 1e-4f;
@@ -269,7 +270,12 @@ __device__ __forceinline__ void rayBegin(const uint32_t *__restrict__ octree, fl
     // direction signs on every trip round the loop (12 extra instructions)
     asm volatile("" : "+r"(octantMask));
     r.octantMask = octantMask;
+}
 
+// The state at the root (:234-250) with the root's descriptor fetched.
+template <bool FAST, typename IdxT>
+__device__ __forceinline__ void rayRoot(const uint32_t *__restrict__ octree, RayState<IdxT> &r) {
+    typedef Arith<FAST> A;
     float minT = maxStd(A::pow2mulsub(2.0f, r.dTx, r.bTx), maxStd(A::pow2mulsub(2.0f, r.dTy, r.bTy), A::pow2mulsub(2.0f, r.dTz, r.bTz)));
     r.maxT = minStd(subRn(r.dTx, r.bTx), minStd(subRn(r.dTy, r.bTy), subRn(r.dTz, r.bTz)));
     minT = maxStd(minT, 0.0f);
@@ -287,8 +293,53 @@ __device__ __forceinline__ void rayBegin(const uint32_t *__restrict__ octree, fl
     if (A::mulsub(1.5f, r.dTy, r.bTy) > minT) { idx ^= 2; r.posY = 1.5f; }
     if (A::mulsub(1.5f, r.dTz, r.bTz) > minT) { idx ^= 4; r.posZ = 1.5f; }
     // the loop tracks the reference's `idx` as childShift = idx ^ octantMask (:261), which is what it uses
-    r.childShift = idx ^ octantMask;
+    r.childShift = idx ^ r.octantMask;
     fetchNode(octree, r);
+}
+
+template <bool FAST, typename IdxT>
+__device__ __forceinline__ void rayBegin(const uint32_t *__restrict__ octree, float ox, float oy, float oz,
+                                         float dx, float dy, float dz, RayState<IdxT> &r) {
+    raySetup<FAST, IdxT>(ox, oy, oz, dx, dy, dz, r);
+    rayRoot<FAST, IdxT>(octree, r);
+}
+
+// ---- shared traversal prefix of a tile (FAST flavour of the fine pass only; see tilePrefixKernel in svo_kernels.cu) ----
+// A record is kPrefixHeaderWords words -- parent, scale | childShift << 8 | octantMask << 16 | valid << 24, posX, posY,
+// posZ -- followed by the parents saved on the stack for the scales above `scale`: word[5 + 22 - sc] for sc in (scale, 22].
+constexpr int kPrefixHeaderWords = 5;
+
+// Puts a ray into the loop-head state a tile's four corner rays shared last: the ray computes its own entry t into that
+// cell (the reference's minT there is the exit plane of the cell it came from, which is this cell's entry plane on that
+// axis -- the same float expression -- or 0 when the ray starts inside) and takes over the parents above it. Returns
+// false, with `r` untouched beyond its set-up, when the record does not apply to this ray (other octant, or the ray's
+// own interval in the cell is empty): the caller then starts at the root.
+template <bool FAST, int THREADS>
+__device__ __forceinline__ bool rayRestart(const uint32_t *__restrict__ octree, RayState<uint32_t> &r,
+                                           const uint32_t *__restrict__ rec, const SmemStack<uint32_t, THREADS, false> &stack) {
+    typedef Arith<FAST> A;
+    typedef SmemStack<uint32_t, THREADS, false> Stack;
+    const uint4 head = __ldg(reinterpret_cast<const uint4 *>(rec));
+    const uint32_t packed = head.y;
+    if ((packed >> 24) == 0u || ((packed >> 16) & 7u) != r.octantMask) return false;
+    const int scale = int(packed & 0xFFu);
+    const float se = __uint_as_float(uint32_t(scale - kMaxScale + 127) << 23);
+    const float px = __uint_as_float(head.z), py = __uint_as_float(head.w), pz = __uint_as_float(__ldg(rec + 4));
+    const float exitT = fminf(A::mulsub(px, r.dTx, r.bTx), fminf(A::mulsub(py, r.dTy, r.bTy), A::mulsub(pz, r.dTz, r.bTz)));
+    const float entryT = fmaxf(fmaxf(A::mulsub(addRn(px, se), r.dTx, r.bTx), A::mulsub(addRn(py, se), r.dTy, r.bTy)),
+                               fmaxf(A::mulsub(addRn(pz, se), r.dTz, r.bTz), 0.0f));
+    if (!(entryT <= exitT)) return false;
+    r.parent = head.x;
+    r.scale = scale;
+    r.scaleExp2 = se;
+    r.childShift = (packed >> 8) & 0xFFu;
+    r.posX = px; r.posY = py; r.posZ = pz;
+    r.minT = entryT;
+    r.maxT = 0.0f;      // not carried by rays without the LOD test
+    for (int sc = scale + 1; sc < kMaxScale; ++sc)       // the same for every ray of the tile: a uniform loop of broadcast loads
+        Stack::store(stack.slot(sc), __ldg(rec + kPrefixHeaderWords + (kMaxScale - 1 - sc)), 0.0f);
+    fetchNode(octree, r);
+    return true;
 }
 
 // One trip round the reference's loop (:252-339). Returns true when the ray is finished: r.childShift then says how
