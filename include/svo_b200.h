@@ -337,7 +337,8 @@ typedef struct svo_frame_stats {
     uint32_t kernel_launches;   /* kernels this call put on the stream */
     uint32_t reserved;
     float coarse_ms;            /* device time of the beam-pass kernel (CUDA events on the call's stream) */
-    float fine_ms;              /* device time of the tile classifier + fine-pass kernel */
+    float fine_ms;              /* device time of the fine-pass kernel (+ the tile classifier when a caller-owned depth
+                                 * buffer puts every kernel on the call's stream) */
 } svo_frame_stats;
 
 /* Geometry of the reference's strip / tile decomposition for one configuration

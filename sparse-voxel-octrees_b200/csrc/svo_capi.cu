@@ -89,6 +89,7 @@ int allocTree(uint64_t nWords, const float center[3], int device, std::unique_pt
         if (tree->stream2) cudaStreamDestroy(tree->stream2);
         for (int i = 0; i < 2; ++i) if (tree->stream34[i]) cudaStreamDestroy(tree->stream34[i]);
         for (int i = 0; i < 2; ++i) if (tree->coarseStream[i]) cudaStreamDestroy(tree->coarseStream[i]);
+        for (int i = 0; i < 2; ++i) if (tree->prepStream[i]) cudaStreamDestroy(tree->prepStream[i]);
         if (tree->copyStream) cudaStreamDestroy(tree->copyStream);
         return failCuda(err, what);
     };
@@ -107,6 +108,9 @@ int allocTree(uint64_t nWords, const float center[3], int device, std::unique_pt
     for (int i = 0; i < 2; ++i)
         if ((e = cudaStreamCreateWithPriority(&tree->coarseStream[i], cudaStreamNonBlocking, prioHigh)) != cudaSuccess)
             return cleanup(e, "cudaStreamCreate(coarse)");
+    for (int i = 0; i < 2; ++i)
+        if ((e = cudaStreamCreateWithPriority(&tree->prepStream[i], cudaStreamNonBlocking, prioHigh)) != cudaSuccess)
+            return cleanup(e, "cudaStreamCreate(prep)");
     if ((e = cudaStreamCreateWithFlags(&tree->copyStream, cudaStreamNonBlocking)) != cudaSuccess) return cleanup(e, "cudaStreamCreate(copy)");
     treeOut = std::move(tree);
     return SVO_OK;
@@ -326,6 +330,8 @@ int buildPlan(svo_tree *tree, int width, int height, int strips, FramePlan &plan
         SVO_CUDA(cudaMemset(plan.dCounters[b], 0, sizeof(svo::FrameCounters)));
         SVO_CUDA(cudaEventCreateWithFlags(&plan.coarseDone[b], cudaEventDisableTiming));
         SVO_CUDA(cudaEventCreateWithFlags(&plan.fineDone[b], cudaEventDisableTiming));
+        SVO_CUDA(cudaEventCreateWithFlags(&plan.laneReady[b], cudaEventDisableTiming));
+        SVO_CUDA(cudaEventCreateWithFlags(&plan.prepDone[b], cudaEventDisableTiming));
         for (int k = 0; k < 4; ++k) SVO_CUDA(cudaEventCreate(&plan.timing[b][k]));
     }
     for (int b = 0; b < kHostLanes; ++b) SVO_CUDA(cudaEventCreateWithFlags(&plan.copyDone[b], cudaEventDisableTiming));
@@ -415,6 +421,15 @@ void applyL2Window(svo_tree *tree, cudaStream_t s) {
     cudaGetLastError();
 }
 
+// SVO_PREP_ON_LANE=1 (experiment switch): tile classifier and prefix pass on the caller's stream, as before round 2.
+bool prepOnCallerStream() {
+    static const bool on = [] {
+        const char *e = getenv("SVO_PREP_ON_LANE");
+        return e && *e == '1';
+    }();
+    return on;
+}
+
 // SVO_NO_PREFIX_RESTART=1 (experiment switch): the FAST fine pass starts every ray at the root, like VALIDATION.
 bool prefixRestartEnabled() {
     static const bool on = [] {
@@ -443,7 +458,15 @@ int enqueueFrame(svo_tree *tree, FramePlan *plan, const svo_camera *cam, const s
     }
     const int b = int(plan->frameNumber++ % kRing);
     float *depth = userDepth ? userDepth : plan->dDepth[b];
+    // Three streams per frame. The beam pass runs on a high-priority internal stream (`cs`), frames ahead of the fine
+    // passes. The tile classifier and the shared-prefix pass -- small kernels between the beam pass and the fine pass --
+    // run on a second high-priority stream (`ps`): on the caller's stream their blocks would queue behind the pending
+    // blocks of the previous frames' fine passes and only run in such a pass's tail, so the next fine pass would start
+    // two dependent launches late, once per frame (18 % of a frame when eight GPUs share it). With a caller-owned depth
+    // buffer everything is ordered on the caller's stream.
+    const bool split = !userDepth && !prepOnCallerStream();
     cudaStream_t cs = userDepth ? stream : tree->coarseStream[b & 1];
+    cudaStream_t ps = split ? tree->prepStream[b & 1] : stream;
     applyL2Window(tree, stream);
     applyL2Window(tree, cs);
     uint32_t n = 0;
@@ -458,16 +481,31 @@ int enqueueFrame(svo_tree *tree, FramePlan *plan, const svo_camera *cam, const s
     if (wantStats) SVO_CUDA(cudaEventRecord(plan->timing[b][1], cs));
     if (!userDepth) {
         SVO_CUDA(cudaEventRecord(plan->coarseDone[b], cs));
-        SVO_CUDA(cudaStreamWaitEvent(stream, plan->coarseDone[b], 0));
+        SVO_CUDA(cudaStreamWaitEvent(ps, plan->coarseDone[b], 0));
     }
-    if (wantStats) SVO_CUDA(cudaEventRecord(plan->timing[b][2], stream));
+    if (split) {
+        // the classifier zero-fills skipped tiles in the framebuffer: not before what the caller ordered on `stream`
+        SVO_CUDA(cudaEventRecord(plan->laneReady[b], stream));
+        SVO_CUDA(cudaStreamWaitEvent(ps, plan->laneReady[b], 0));
+    }
+    if (wantStats && !split) SVO_CUDA(cudaEventRecord(plan->timing[b][2], stream));
     SVO_CUDA(svo::launchClassifyTiles(plan->dev, f, depth, dRgba, desc->tile_rank, desc->tile_world, desc->pixel_stride,
-                                      plan->dTiles[b], plan->dCounters[b], plan->dFineTotal, stream));
+                                      plan->dTiles[b], plan->dCounters[b], plan->dFineTotal, ps));
     ++n;
-    uint32_t *prefix = prefixRestartEnabled() ? plan->dPrefix[b] : nullptr;
+    uint32_t *prefix = prefixRestartEnabled() && svo::finePassUsesPrefix(tree->dev(), desc->flavour, desc->pixel_stride) ? plan->dPrefix[b] : nullptr;
+    if (prefix) {
+        SVO_CUDA(svo::launchTilePrefix(tree->dev(), plan->dev, f, desc->flavour, plan->dTiles[b], plan->dCounters[b],
+                                       desc->tile_rank, desc->tile_world, desc->pixel_stride, prefix, ps));
+        ++n;
+    }
+    if (split) {
+        SVO_CUDA(cudaEventRecord(plan->prepDone[b], ps));
+        SVO_CUDA(cudaStreamWaitEvent(stream, plan->prepDone[b], 0));
+        if (wantStats) SVO_CUDA(cudaEventRecord(plan->timing[b][2], stream));
+    }
     SVO_CUDA(svo::launchFinePass(tree->dev(), plan->dev, f, desc->flavour, plan->dTiles[b], plan->dCounters[b], dRgba,
                                  desc->tile_rank, desc->tile_world, desc->pixel_stride, prefix, stream));
-    n += 1 + (prefix ? svo::finePassUsesPrefix(tree->dev(), desc->flavour, desc->pixel_stride) : 0);
+    ++n;
     if (wantStats) {
         SVO_CUDA(cudaEventRecord(plan->timing[b][3], stream));
         SVO_CUDA(cudaMemcpyAsync(plan->hCounters + b, plan->dCounters[b], sizeof(svo::FrameCounters),
@@ -965,6 +1003,7 @@ int svo_tree_destroy(svo_tree *tree) {
         if (tree->stream2) cudaStreamDestroy(tree->stream2);
         for (int i = 0; i < 2; ++i) if (tree->stream34[i]) cudaStreamDestroy(tree->stream34[i]);
         for (int i = 0; i < 2; ++i) if (tree->coarseStream[i]) cudaStreamDestroy(tree->coarseStream[i]);
+        for (int i = 0; i < 2; ++i) if (tree->prepStream[i]) cudaStreamDestroy(tree->prepStream[i]);
         if (tree->copyStream) cudaStreamDestroy(tree->copyStream);
     }
     delete tree;

@@ -79,6 +79,8 @@ struct FramePlan {
     unsigned long long *dFineTotal = nullptr;           // fine rays of every frame since it was last zeroed (frame sequences)
     cudaEvent_t coarseDone[kRing] = {};    // beam pass of the slot finished (internal stream)
     cudaEvent_t fineDone[kRing] = {};      // last fine pass that read the slot's depth / tile list
+    cudaEvent_t laneReady[kRing] = {};     // what the caller had ordered on its stream before the frame (framebuffer free)
+    cudaEvent_t prepDone[kRing] = {};      // tile list (+ prefix records) of the slot written
     cudaEvent_t timing[kRing][4] = {};     // coarse start/end, fine start/end (stats only)
     bool fineRecorded[kRing] = {};
     uint64_t frameNumber = 0;
@@ -105,6 +107,8 @@ struct FramePlan {
             if (dPrefix[b]) cudaFree(dPrefix[b]);
             if (coarseDone[b]) cudaEventDestroy(coarseDone[b]);
             if (fineDone[b]) cudaEventDestroy(fineDone[b]);
+            if (laneReady[b]) cudaEventDestroy(laneReady[b]);
+            if (prepDone[b]) cudaEventDestroy(prepDone[b]);
             for (int k = 0; k < 4; ++k) if (timing[b][k]) cudaEventDestroy(timing[b][k]);
         }
         for (int b = 0; b < kHostLanes; ++b) {
@@ -144,6 +148,7 @@ struct svo_tree {
     cudaStream_t stream2 = nullptr;         // ... of host-buffer frames 1 mod 4 (so that consecutive fine passes overlap)
     cudaStream_t stream34[2] = {nullptr, nullptr};      // ... 2 and 3 mod 4
     cudaStream_t coarseStream[2] = {nullptr, nullptr};  // beam passes, high priority, alternating per frame
+    cudaStream_t prepStream[2] = {nullptr, nullptr};    // tile classifier + shared-prefix pass, high priority
     cudaStream_t copyStream = nullptr;      // device->host frame copies
     std::mutex mutex;
     std::map<std::tuple<int, int, int>, FramePlan> plans;

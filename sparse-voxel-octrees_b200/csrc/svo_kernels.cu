@@ -595,15 +595,6 @@ cudaError_t launchFineT(const TreeDev &tree, const FramePlanDev &plan, const Fra
     int blocks = (owned + int(kTilesPerBlock) - 1)/int(kTilesPerBlock);
     const int prefixWords = prefixRecordWords(tree);
     if (!FAST || sizeof(IdxT) != 4 || prefixWords == 0) prefix = nullptr;
-    if (prefix) {
-        // K2c: the tile's shared traversal prefix, four corner rays per tile in lock step
-        const size_t psmem = SmemStack<uint32_t, kPrefixThreads, false>::bytes(stackSlots(tree));
-        if ((e = ensureSmem(tilePrefixKernel, psmem)) != cudaSuccess) return e;
-        const int tilesPerBlock = kPrefixThreads/4;
-        tilePrefixKernel<<<(owned + tilesPerBlock - 1)/tilesPerBlock, kPrefixThreads, psmem, stream>>>(
-            tree.words, plan, consts, tiles, counters, prefix, prefixWords);
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    }
     kernel<<<blocks, kTileThreads, smem, stream>>>(tree.words, plan, consts, tiles, counters, rgba, prefix, prefixWords);
     return cudaGetLastError();
 }
@@ -812,6 +803,22 @@ cudaError_t launchFinePass(const TreeDev &tree, const FramePlanDev &plan, const 
                     : launchFineT<true, uint32_t>(tree, plan, consts, tiles, counters, rgba, owned, pixelStride, prefix, stream);
     return wide ? launchFineT<false, uint64_t>(tree, plan, consts, tiles, counters, rgba, owned, pixelStride, prefix, stream)
                 : launchFineT<false, uint32_t>(tree, plan, consts, tiles, counters, rgba, owned, pixelStride, prefix, stream);
+}
+
+// K2c: the tile's shared traversal prefix, four corner rays per tile in lock step; a no-op (returns 0 launches) when
+// launchFinePass would not use the records.
+cudaError_t launchTilePrefix(const TreeDev &tree, const FramePlanDev &plan, const FrameConsts &consts, int flavour,
+                             const TileRecord *tiles, const FrameCounters *counters, int tileRank, int tileWorld,
+                             int pixelStride, uint32_t *prefix, cudaStream_t stream) {
+    const int owned = ownedTiles(plan, tileRank, tileWorld);
+    if (owned <= 0 || !prefix || !finePassUsesPrefix(tree, flavour, pixelStride)) return cudaSuccess;
+    const size_t psmem = SmemStack<uint32_t, kPrefixThreads, false>::bytes(stackSlots(tree));
+    cudaError_t e = ensureSmem(tilePrefixKernel, psmem);
+    if (e != cudaSuccess) return e;
+    const int tilesPerBlock = kPrefixThreads/4;
+    tilePrefixKernel<<<(owned + tilesPerBlock - 1)/tilesPerBlock, kPrefixThreads, psmem, stream>>>(
+        tree.words, plan, consts, tiles, counters, prefix, prefixRecordWords(tree));
+    return cudaGetLastError();
 }
 
 // Words per tile of the shared-prefix records (header + one parent per stack slot, rounded to 16 bytes); 0 when the

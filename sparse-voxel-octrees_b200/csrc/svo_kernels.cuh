@@ -86,8 +86,11 @@ cudaError_t launchClassifyTiles(const FramePlanDev &plan, const FrameConsts &con
 
 // Fine pass over the tile list (grid covers the worst case; blocks past the list length exit).
 // pixelStride > 1: renderTile's preview mode (Main.cpp:101-106), one ray per stride x stride block of a tile.
-// prefix != nullptr (room for prefixRecordWords(tree) words per owned tile): in the FAST flavour the rays of a tile
-// start at the traversal state its four corner rays share (tilePrefixKernel, launched first) instead of at the root.
+// prefix != nullptr (room for prefixRecordWords(tree) words per owned tile, filled by launchTilePrefix): in the FAST
+// flavour the rays of a tile start at the traversal state its four corner rays share instead of at the root.
+cudaError_t launchTilePrefix(const TreeDev &tree, const FramePlanDev &plan, const FrameConsts &consts, int flavour,
+                             const TileRecord *tiles, const FrameCounters *counters, int tileRank, int tileWorld,
+                             int pixelStride, uint32_t *prefix, cudaStream_t stream);
 cudaError_t launchFinePass(const TreeDev &tree, const FramePlanDev &plan, const FrameConsts &consts, int flavour,
                            const TileRecord *tiles, const FrameCounters *counters, uint32_t *rgba,
                            int tileRank, int tileWorld, int pixelStride, uint32_t *prefix, cudaStream_t stream);

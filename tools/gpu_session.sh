@@ -53,6 +53,7 @@ multi)
   timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -x -q > gpurun_out/${tag}_pytest_multi_n$N.txt 2>&1; tail -3 gpurun_out/${tag}_pytest_multi_n$N.txt
   for wl in c3_ico8192_4k c5_flythrough_ico8192; do bench gpurun_out/${tag}_${wl}_n$N.json $N --workload $wl --no-cpu-baseline; line gpurun_out/${tag}_${wl}_n$N.json torchrun; done
   bench gpurun_out/${tag}_c3_n1_same_box.json 1 --no-cpu-baseline; line gpurun_out/${tag}_c3_n1_same_box.json same-box
+  SVO_PREP_ON_LANE=1 timeout 300 python bench.py --gpus $N --no-cpu-baseline 2> gpurun_out/${tag}_preplane.err | tail -1 > gpurun_out/${tag}_c3_n${N}_prep_on_lane.json; line gpurun_out/${tag}_c3_n${N}_prep_on_lane.json prep-on-lane
   for lanes in 6 8; do SVO_MULTI_LANES=$lanes timeout 300 python bench.py --gpus $N --no-cpu-baseline 2> gpurun_out/${tag}_lanes$lanes.err | tail -1 > gpurun_out/${tag}_c3_n${N}_lanes$lanes.json; line gpurun_out/${tag}_c3_n${N}_lanes$lanes.json lanes$lanes; done
   timeout 300 ncu --devices 1 --set full --clock-control none -k regex:finePassKernel -s 30 -c 2 -f -o gpurun_out/${tag}_c5_fine_dev1_n$N \
       python bench.py --gpus $N --workload c5_flythrough_ico8192 --steps 60 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_n$N.log 2>&1
