@@ -605,7 +605,7 @@ def run_own(args):
     # ---- end to end: every frame of the same camera path lands in page-locked host memory (ring of four frames);
     # with N > 1 every GPU ships the stripes it rendered over its own PCIe link. Host clock around the call.
     e2e_steps = min(steps, 300)
-    ring = [pysvo.PinnedArray((H, W), np.uint32) for _ in range(max(4, int(os.environ.get("SVO_MULTI_LANES", "0") or 0)))]
+    ring = [pysvo.PinnedArray((H, W), np.uint32) for _ in range(int(os.environ.get("SVO_MULTI_LANES", "0") or 0) or 6)]
     hosts = [r.array for r in ring]
     multi.render_sequence(path(0, 8), W, H, strips=STRIPS, flavour=flavour, output=pysvo.OUTPUT_HOST, host_frames=hosts)
     e2e_rounds = []
@@ -732,9 +732,9 @@ def run_own(args):
                 "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "rounds": len(e2e_rounds),
                 "note": "svo_multi_render_sequence(SVO_OUTPUT_HOST): per-step input is the 128 B camera (kernel parameters), "
                         "the octree stays resident; every frame is copied to page-locked host memory, " + (
-                            "copy engine, four frames in flight" if n_dev == 1 else
+                            f"copy engine, {int(e2e_med.lanes)} frames in flight" if n_dev == 1 else
                             f"every GPU ships the stripes it rendered ({int(e2e_med.tile_run)} tile columns wide) into the ONE "
-                            "host frame itself (1 / N of the frame per PCIe link), four frames in flight")},
+                            f"host frame itself (1 / N of the frame per PCIe link, copy engine), {int(e2e_med.lanes)} frames in flight")},
         "gpu_launches": device_launches,
         "gpu_launches_note": "kernels of the reported device-timed round, all GPUs (beam pass + tile classifier + fine pass "
                              f"per frame and GPU); the e2e round launched {e2e_launches}",

@@ -422,7 +422,7 @@ SVO_API int svo_host_unregister(void *p);
  * The node array is replicated into the HBM of every listed device; one worker thread per device enqueues that
  * device's share of every frame (the tile columns (tx / run) % n_devices == index: beam pass of the corners next
  * to them, tile classifier, fine pass); frames are ordered by CUDA events, across devices too -- there is no NCCL,
- * no second process and no host-side wait inside a frame sequence. Up to four frames are in flight.
+ * no second process and no host-side wait inside a frame sequence. Up to six frames are in flight.
  *   SVO_OUTPUT_DEVICE  every device's fine pass stores its finished pixels straight into a framebuffer in
  *                      devices[0]'s HBM over NVLink (peer access; the gather is fused into the kernel); the frame
  *                      barrier is devices[0]'s gather stream waiting for every device's frame event.
@@ -459,7 +459,7 @@ typedef void (*svo_frame_callback)(void *user, int frame, const uint32_t *rgba);
 
 /* Renders cams[0 .. n_frames) back to back (the reference's renderLoop, Main.cpp:204-262, over a camera path).
  * desc->tile_rank / tile_world are ignored (the handle deals the tiles). SVO_OUTPUT_HOST: frame k lands in
- * host_frames[k % n_host_frames] (page-locked, width*height words each); min(4, n_host_frames) frames are in
+ * host_frames[k % n_host_frames] (page-locked, width*height words each); min(6, n_host_frames) frames are in
  * flight; on_frame (optional) sees every frame. SVO_OUTPUT_DEVICE: host_frames is ignored; the last frames stay
  * in devices[0]'s HBM (svo_multi_device_frame). `stats` is optional. */
 SVO_API int svo_multi_render_sequence(svo_multi *m, const svo_camera *cams, int n_frames, const svo_frame_desc *desc,
