@@ -3,8 +3,10 @@
 // include/svo_b200.h. Header-only; link with -lsvo_b200.
 //
 //   VoxelOctree(const char *path)                  reference src/VoxelOctree.cpp:57
-//   VoxelOctree(VoxelData *voxels)                 reference src/VoxelOctree.cpp:125  (fromVoxelFile / fromVoxels /
-//                                                  fromSparse build in HBM; adopt() takes a finished array)
+//   VoxelOctree(VoxelData *voxels)                 reference src/VoxelOctree.cpp:125  (with the VoxelData / PlyLoader
+//                                                  stand-ins below: the reference's two VoxelData constructors name the
+//                                                  source, the tree is voxelised / built in HBM; also fromVoxelFile /
+//                                                  fromPly / fromVoxels / fromSparse, and adopt() for a finished array)
 //   void save(const char *path)                    reference src/VoxelOctree.cpp:92
 //   bool raymarch(o, d, rayScale, normal&, t&)     reference src/VoxelOctree.cpp:207
 //   Vec3 center() const                            reference src/VoxelOctree.hpp:55
@@ -44,6 +46,40 @@ typedef std::uint32_t uint32;
 typedef std::uint64_t uint64;
 #endif
 
+// Stand-ins with the reference's constructor signatures for the two ways its `-builder` mode names a voxel source
+// (Main.cpp:315-325): they only record the source; VoxelOctree(VoxelData*) below does the work on the GPU. Not
+// defined when the reference's own PlyLoader.hpp / VoxelData.hpp were included first (their objects are CPU-side
+// voxel caches this library has no use for: build with the factories then).
+#ifndef PLYLOADER_HPP_
+class PlyLoader {                                   // reference src/PlyLoader.hpp:96, PlyLoader.cpp:64-79
+    std::string _path;
+public:
+    explicit PlyLoader(const char *path) : _path(path) {}
+    const std::string &path() const { return _path; }
+};
+#define SVO_B200_PLYLOADER_STANDIN 1
+#endif
+#ifndef VOXELDATA_HPP_
+class VoxelData {
+    std::string _path;
+    bool _isPly;
+    int _sideLength;
+    std::size_t _mem;
+public:
+    VoxelData(const char *path, std::size_t mem)                      // raw .voxel file, reference src/VoxelData.cpp:37-48
+        : _path(path), _isPly(false), _sideLength(0), _mem(mem) {}
+#ifdef SVO_B200_PLYLOADER_STANDIN
+    VoxelData(PlyLoader *loader, std::size_t sideLength, std::size_t mem)   // mesh, reference src/VoxelData.cpp:50-56
+        : _path(loader->path()), _isPly(true), _sideLength(int(sideLength)), _mem(mem) {}
+#endif
+    const std::string &path() const { return _path; }
+    bool isPly() const { return _isPly; }
+    int sideLength() const { return _sideLength; }
+    std::size_t memoryBudget() const { return _mem; }
+};
+#define SVO_B200_VOXELDATA_STANDIN 1
+#endif
+
 class VoxelOctree {
     svo_tree *_tree;
     svo_tree_info _info;
@@ -60,6 +96,18 @@ public:
         check(svo_tree_load_oct(path, device, &_tree), "VoxelOctree(path)");
         check(svo_tree_get_info(_tree, &_info), "svo_tree_get_info");
     }
+#ifdef SVO_B200_VOXELDATA_STANDIN
+    // VoxelOctree(VoxelData *voxels), reference src/VoxelOctree.cpp:125-137: the tree of the source `voxels` names,
+    // word for word the reference builder's (the memory budget shapes a mesh's result, so it is passed on).
+    explicit VoxelOctree(VoxelData *voxels, int device = 0) : _tree(0) {
+        if (voxels->isPly())
+            check(svo_tree_build_from_ply(voxels->path().c_str(), voxels->sideLength(), voxels->memoryBudget(), 0, device, &_tree),
+                  "VoxelOctree(VoxelData*)");
+        else
+            check(svo_tree_build_from_voxel_file(voxels->path().c_str(), device, &_tree), "VoxelOctree(VoxelData*)");
+        check(svo_tree_get_info(_tree, &_info), "svo_tree_get_info");
+    }
+#endif
     // Node array from the reference's builder (or anywhere else), uploaded unchanged.
     static VoxelOctree *adopt(const uint32 *words, uint64 count, const Vec3 &center, int device = 0) {
         float c[3] = {center.x, center.y, center.z};
@@ -115,6 +163,35 @@ public:
                        uint32 *normal, uint64 *voxel = 0, int flavour = SVO_FLAVOUR_VALIDATION) {
         check(svo_raymarch_batch(_tree, n, o, d, rayScale, flavour, hit, t, normal, voxel), "VoxelOctree::raymarchBatch");
     }
+
+    // For call sites written like the reference's per-pixel loop (`tree->raymarch(...)` per ray, Main.cpp:118,181): queue
+    // the rays where raymarch() was called, flush() once (one batch instead of a PCIe round trip per ray), read the
+    // results where they were used. Outputs keep the reference's semantics (normal / t untouched where it leaves them).
+    class RayQueue {
+        std::vector<float> _o, _d;
+        std::vector<uint8_t> _hit;
+        std::vector<float> _t;
+        std::vector<uint32> _normal;
+    public:
+        std::size_t push(const Vec3 &o, const Vec3 &d) {
+            _o.push_back(o.x); _o.push_back(o.y); _o.push_back(o.z);
+            _d.push_back(d.x); _d.push_back(d.y); _d.push_back(d.z);
+            return _o.size()/3 - 1;
+        }
+        std::size_t size() const { return _o.size()/3; }
+        void flush(VoxelOctree &tree, float rayScale, int flavour = SVO_FLAVOUR_VALIDATION) {
+            const std::size_t n = size();
+            _hit.assign(n, 0); _t.assign(n, 0.0f); _normal.assign(n, 0);
+            if (n) tree.raymarchBatch(n, _o.data(), _d.data(), rayScale, _hit.data(), _t.data(), _normal.data(), 0, flavour);
+        }
+        // the reference's bool raymarch(..., uint32 &normal, float &t) for queued ray i
+        bool result(std::size_t i, uint32 &normal, float &t) const {
+            if (_hit[i] != SVO_MISS) t = _t[i];
+            if (_hit[i] == SVO_HIT_LEAF) normal = _normal[i];
+            return _hit[i] != SVO_MISS;
+        }
+        void clear() { _o.clear(); _d.clear(); }
+    };
 
     // One frame of the reference's renderBatch loop over `strips` strips (Main.cpp:139-202, 351-362).
     // pixelStride 3 = renderTile's preview mode while dragging (Main.cpp:101-106, 161).

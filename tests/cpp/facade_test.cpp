@@ -50,6 +50,26 @@ int main(int argc, char **argv) {
         printf("frame rays %llu fnv %016llx\n", (unsigned long long)(st.coarse_rays + st.fine_rays), sum);
         delete adopted;
 
+        // the same four rays through the queue: one batch, the reference's untouched-output semantics
+        VoxelOctree::RayQueue queue;
+        for (int i = 0; i < 4; ++i) queue.push(o, Vec3(dirs[i][0], dirs[i][1], dirs[i][2]));
+        queue.flush(tree, 0.0f);
+        for (int i = 0; i < 4; ++i) {
+            uint32 normal = 0xABCD1234u;
+            float t = -7.0f;
+            bool hit = queue.result(size_t(i), normal, t);
+            unsigned tbits;
+            memcpy(&tbits, &t, 4);
+            printf("queued %d hit %d normal %08x tbits %08x\n", i, hit ? 1 : 0, normal, tbits);
+        }
+
+        // VoxelOctree(VoxelData*) with the reference's constructor forms (Main.cpp:318-319): a raw .voxel file
+        if (argc > 3) {
+            VoxelData data(argv[3], size_t(1) << 30);
+            VoxelOctree built(&data);
+            printf("built words %llu depth %u\n", (unsigned long long)built.wordCount(), built.depth());
+        }
+
         try {
             VoxelOctree missing("/nonexistent/file.oct");
             printf("missing: no error\n");

@@ -411,9 +411,18 @@ def test_cpp_facade_and_headless_driver(pysvo, port, gpu_dragon, dragon_words, t
                            str(ROOT / "tests" / "cpp" / "facade_test.cpp"), "-o", str(exe), f"-L{pkg}", "-lsvo_b200",
                            f"-Wl,-rpath,{pkg}"])
     saved = tmp_path / "saved.oct"
-    out = subprocess.run([str(exe), str(DRAGON), str(saved)], capture_output=True, text=True, timeout=300)
+    # a raw .voxel volume for VoxelOctree(VoxelData*): int32 w, h, d then the grid (VoxelData.cpp:36-48)
+    rng = np.random.default_rng(3)
+    vox = ((rng.random((20, 24, 28)) < 0.15) * rng.integers(1, 2**32, (20, 24, 28), dtype=np.uint64)).astype(np.uint32)
+    raw = tmp_path / "vol.voxel"
+    with open(raw, "wb") as fp:
+        fp.write(np.array([28, 24, 20], np.int32).tobytes())
+        fp.write(vox.tobytes())
+    out = subprocess.run([str(exe), str(DRAGON), str(saved), str(raw)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr
-    lines = out.stdout.splitlines()
+    lines = [ln for ln in out.stdout.splitlines() if not ln.startswith(("queued", "built"))]
+    queued = [ln for ln in out.stdout.splitlines() if ln.startswith("queued")]
+    built = [ln for ln in out.stdout.splitlines() if ln.startswith("built")]
     words, center = dragon_words
     assert lines[0].split()[:4] == ["center", "0.5", "0.2265625", "0.33203125"] and "words 119887 depth 8" in lines[0]
     o = [float(center[0]) + 1.0, float(center[1]) + 1.0, float(center[2])]
@@ -433,6 +442,12 @@ def test_cpp_facade_and_headless_driver(pysvo, port, gpu_dragon, dragon_words, t
         fnv = (fnv * 1099511628211 + int(v)) & 0xFFFFFFFFFFFFFFFF
     assert lines[6] == f"frame rays {st.rays} fnv {fnv:016x}"
     assert lines[7] == "missing: threw"
+    # RayQueue: the single-ray call sites' rays as one batch, same outputs (rayScale 0 for all four here)
+    for i in range(4):
+        code, t, n, _, _ = port.raymarch(words, o, dirs[i], 0.0, normal_sentinel=0xABCD1234, t_sentinel=-7.0)
+        assert queued[i] == f"queued {i} hit {1 if code else 0} normal {n:08x} tbits {int(np.float32(t).view(np.uint32)):08x}"
+    want_words, _ = port.build_octree(vox)
+    assert built == [f"built words {want_words.size} depth 5"]
 
     # headless driver: PPM of frame 0 equals the library's frame
     subprocess.check_call(["make", "-C", str(pkg), "headless"], stdout=subprocess.DEVNULL)
@@ -460,6 +475,14 @@ def test_cpp_facade_and_headless_driver(pysvo, port, gpu_dragon, dragon_words, t
     out = subprocess.run([str(pkg / "svo_headless"), str(DRAGON), "--size", "320x180", "--strips", "4", "--validation",
                           "--radius", "0.8", "--pitch", "10", "--yaw0", "30", "--raw", "-"], capture_output=True, timeout=300)
     assert out.returncode == 0 and np.array_equal(np.frombuffer(out.stdout, np.uint8).reshape(180, 320, 3), img)
+    # --gpus N: the same orbit through svo_multi_* (needs N real devices: the driver lists 0 .. N-1)
+    if pysvo.device_count() >= 2:
+        multi = tmp_path / "frames_multi.rgb"
+        out = subprocess.run([str(pkg / "svo_headless"), str(DRAGON), "--size", "320x180", "--strips", "4", "--frames", "2",
+                              "--validation", "--radius", "0.8", "--pitch", "10", "--yaw0", "30", "--gpus", "2", "--raw", str(multi)],
+                             capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr
+        assert np.array_equal(np.frombuffer(multi.read_bytes(), np.uint8).reshape(2, 180, 320, 3), frames)
 
 
 @pytest.mark.parametrize("shape", [(1280, 720, 16), (333, 187, 5), (64, 40, 3)])
