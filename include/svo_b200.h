@@ -188,7 +188,7 @@ typedef struct svo_voxelize_stats {
     int32_t dims[3];            /* volume the reference derives from the mesh (PlyLoader::suggestedDimensions) */
     int32_t cache_block;        /* edge of the reference's cache block for the budget (VoxelData.cpp:203-262) */
     int32_t sub_block[3];       /* per-thread sub-block (PlyLoader.cpp:381-440) */
-    int32_t reserved;
+    int32_t large_triangles;    /* triangles whose bounding box holds more than 2^15 cells: voxelised by a block each */
     float overlap_ms, sort_ms, fold_ms;   /* device time of the voxeliser's three phases */
     float reserved2;
 } svo_voxelize_stats;

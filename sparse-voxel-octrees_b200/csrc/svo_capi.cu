@@ -897,6 +897,7 @@ int svo_tree_build_from_ply(const char *path, int resolution, uint64_t mem_budge
     g_voxelizeStats.voxels = vs.voxels;
     for (int i = 0; i < 3; ++i) { g_voxelizeStats.dims[i] = vs.dims[i]; g_voxelizeStats.sub_block[i] = vs.subBlock[i]; }
     g_voxelizeStats.cache_block = vs.cacheBlock;
+    g_voxelizeStats.large_triangles = int32_t(vs.largeTriangles);
     g_voxelizeStats.overlap_ms = vs.overlapMs;
     g_voxelizeStats.sort_ms = vs.sortMs;
     g_voxelizeStats.fold_ms = vs.foldMs;

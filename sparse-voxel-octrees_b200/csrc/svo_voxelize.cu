@@ -246,10 +246,147 @@ __device__ uint32_t cellsOfTriangle(const Partition &P, const MeshTriangle &t, u
     return n;
 }
 
+// ---- large triangles: a block per triangle --------------------------------------------------------------------------
+// One thread walking every cell of a triangle's bounding box (cellsOfTriangle) is fine for meshes of small triangles --
+// the benchmark's are a few cells each -- but a low-poly mesh at a high resolution has triangles whose boxes hold 10^6 to
+// 10^9 cells: one thread would run for minutes with the rest of the GPU idle. Triangles whose box holds more than
+// kLargeCells cells are listed by countCellsKernel and handled by a whole block each: the block's threads test the
+// sub-blocks of the triangle's range in parallel, then, sub-block by sub-block, its cells. The reference's arithmetic is
+// kept to the bit: cell (and sub-block) centres are RUNNING SUMS along each axis (center += hx, :337-374 / :235-277), so
+// one thread per axis accumulates them into a shared table the way the reference's loops do and every test reads its three
+// coordinates from the tables. Records of one triangle may land in any order inside the triangle's range (a cell appears
+// at most once per triangle; the fold only depends on the order of TRIANGLES within a cell).
+constexpr uint64_t kLargeCells = 1u << 15;
+constexpr int kLargeThreads = 256;
+constexpr int kAxisTable = 1024;          // longest running-sum table per axis (sub-block range / cells of a sub-block)
+constexpr int kSubList = 2048;            // overlapping sub-blocks collected per round
+
+__device__ __forceinline__ uint64_t boxCells(const Partition &P, const MeshTriangle &t) {
+    int lx, ly, lz, ux, uy, uz;
+    pointToGrid(P, t.lower, lx, ly, lz);
+    pointToGrid(P, t.upper, ux, uy, uz);
+    if (ux < lx || uy < ly || uz < lz) return 0;
+    return uint64_t(ux - lx + 1)*uint64_t(uy - ly + 1)*uint64_t(uz - lz + 1);
+}
+
+// running sums first + k*step, k = 0 .. n-1, accumulated like `for (...; v += step)` -- by ONE thread
+__device__ __forceinline__ void runningSums(float *table, float first, float step, int n) {
+    float v = first;
+    for (int k = 0; k < n; ++k, v += step) table[k] = v;
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(kLargeThreads)
+largeTrianglesKernel(Partition P, const MeshTriangle *__restrict__ tris, const uint32_t *__restrict__ largeList,
+                     const uint32_t *__restrict__ largeCount, uint64_t *counts, const uint64_t *__restrict__ offsets,
+                     uint64_t *keys, CellRecord *records) {
+    __shared__ float subX[kAxisTable], subY[kAxisTable], subZ[kAxisTable];     // sub-block centres of the current window
+    __shared__ float tabX[kAxisTable], tabY[kAxisTable], tabZ[kAxisTable];     // cell centres of the current sub-block (window)
+    __shared__ int subList[kSubList];
+    __shared__ int subCount;
+    __shared__ unsigned long long written, blockTotal;
+    const uint32_t nLarge = *largeCount;
+    for (uint32_t item = blockIdx.x; item < nLarge; item += gridDim.x) {
+        const uint32_t ti = largeList[item];
+        const MeshTriangle &t = tris[ti];
+        int lx, ly, lz, ux, uy, uz;
+        pointToGrid(P, t.lower, lx, ly, lz);
+        pointToGrid(P, t.upper, ux, uy, uz);
+        const int lgx = lx/P.subW, lgy = ly/P.subH, lgz = lz/P.subD;
+        const int ugx = (ux + 1)/P.subW, ugy = (uy + 1)/P.subH, ugz = (uz + 1)/P.subD;
+        const bool ranged = max(ugx - lgx, max(ugy - lgy, ugz - lgz)) > 0;       // else: the one sub-block, untested (:272-276)
+        const int nx = ranged ? ugx - lgx + 1 : 1, ny = ranged ? ugy - lgy + 1 : 1, nz = ranged ? ugz - lgz + 1 : 1;
+        __syncthreads();
+        if (threadIdx.x == 0) { written = 0; blockTotal = 0; }
+        unsigned long long mine = 0;
+        const float shx = float(P.subW)/float(P.sideM2 - 2), shy = float(P.subH)/float(P.sideM2 - 2), shz = float(P.subD)/float(P.sideM2 - 2);
+        const float subHalf[3] = {0.5f*shx, 0.5f*shy, 0.5f*shz};
+        const float hx = 1.0f/float(P.sideM2 - 2);
+        const float half[3] = {0.5f*hx, 0.5f*hx, 0.5f*hx};
+        // Ranges longer than a table are walked window by window. The reference's running sum of an axis restarts at the
+        // range's first entry for every row, so a window's first value is that start plus (window offset) additions of the
+        // step -- accumulated one by one by the thread that fills the table.
+        for (int wz = 0; wz < nz; wz += kAxisTable) for (int wy = 0; wy < ny; wy += kAxisTable) for (int wx = 0; wx < nx; wx += kAxisTable) {
+            const int cxn = min(kAxisTable, nx - wx), cyn = min(kAxisTable, ny - wy), czn = min(kAxisTable, nz - wz);
+            __syncthreads();
+            if (ranged) {
+                if (threadIdx.x == 0) { float v = (float(lgx) + 0.5f)*shx; for (int k = 0; k < wx; ++k) v += shx; runningSums(subX, v, shx, cxn); }
+                if (threadIdx.x == 32) { float v = (float(lgy) + 0.5f)*shy; for (int k = 0; k < wy; ++k) v += shy; runningSums(subY, v, shy, cyn); }
+                if (threadIdx.x == 64) { float v = (float(lgz) + 0.5f)*shz; for (int k = 0; k < wz; ++k) v += shz; runningSums(subZ, v, shz, czn); }
+            }
+            __syncthreads();
+            const long long windowSubs = (long long)cxn*cyn*czn;
+            for (long long base = 0; base < windowSubs; base += kSubList) {
+                // phase A: which sub-blocks of this slice does the triangle overlap (:235-277)? all threads, one test each
+                __syncthreads();
+                if (threadIdx.x == 0) subCount = 0;
+                __syncthreads();
+                const long long sliceEnd = min(windowSubs, base + (long long)kSubList);
+                for (long long q = base + threadIdx.x; q < sliceEnd; q += kLargeThreads) {
+                    bool overlaps = true;
+                    if (ranged) {
+                        const float c[3] = {subX[int(q % cxn)], subY[int((q/cxn) % cyn)], subZ[int(q/((long long)cxn*cyn))]};
+                        overlaps = triBoxOverlap(c, subHalf, t.pos);
+                    }
+                    if (overlaps) subList[atomicAdd(&subCount, 1)] = int(q - base);
+                }
+                __syncthreads();
+                const int listed = subCount;
+                // phase B: the cells of every listed sub-block (:337-374), all threads on one sub-block at a time
+                for (int e = 0; e < listed; ++e) {
+                    const long long q = base + subList[e];
+                    const int gx = lgx + wx + int(q % cxn), gy = lgy + wy + int((q/cxn) % cyn), gz = lgz + wz + int(q/((long long)cxn*cyn));
+                    if (gx < 0 || gy < 0 || gz < 0 || gx >= P.realW || gy >= P.realH || gz >= P.realD) continue;
+                    const int bufferX = (gx/P.partW)*P.block, bufferY = (gy/P.partH)*P.block, bufferZ = (gz/P.partD)*P.block;
+                    const int bufferW = min(P.block, P.volumeW - bufferX), bufferH = min(P.block, P.volumeH - bufferY),
+                              bufferD = min(P.block, P.volumeD - bufferZ);
+                    if (bufferW <= 0 || bufferH <= 0 || bufferD <= 0) continue;
+                    const int offX = (gx % P.partW)*P.subW, offY = (gy % P.partH)*P.subH, offZ = (gz % P.partD)*P.subD;
+                    const int clx = max(lx, bufferX + offX), cly = max(ly, bufferY + offY), clz = max(lz, bufferZ + offZ);
+                    const int cux = min(ux, bufferX + min(offX + P.subW, bufferW) - 1), cuy = min(uy, bufferY + min(offY + P.subH, bufferH) - 1),
+                              cuz = min(uz, bufferZ + min(offZ + P.subD, bufferD) - 1);
+                    if (clx > cux || cly > cuy || clz > cuz) continue;      // (block-uniform: every thread takes the same branch)
+                    for (int vz = clz; vz <= cuz; vz += kAxisTable) for (int vy = cly; vy <= cuy; vy += kAxisTable) for (int vx = clx; vx <= cux; vx += kAxisTable) {
+                        const int mx = min(kAxisTable, cux - vx + 1), my = min(kAxisTable, cuy - vy + 1), mz = min(kAxisTable, cuz - vz + 1);
+                        __syncthreads();        // the cell tables of the previous sub-block are no longer read
+                        if (threadIdx.x == 96) { float v = (float(clx) - 0.5f)*hx; for (int k = clx; k < vx; ++k) v += hx; runningSums(tabX, v, hx, mx); }
+                        if (threadIdx.x == 128) { float v = (float(cly) - 0.5f)*hx; for (int k = cly; k < vy; ++k) v += hx; runningSums(tabY, v, hx, my); }
+                        if (threadIdx.x == 160) { float v = (float(clz) - 0.5f)*hx; for (int k = clz; k < vz; ++k) v += hx; runningSums(tabZ, v, hx, mz); }
+                        __syncthreads();
+                        const long long cells = (long long)mx*my*mz;
+                        for (long long c = threadIdx.x; c < cells; c += kLargeThreads) {
+                            const int ix = int(c % mx), iy = int((c/mx) % my), iz = int(c/((long long)mx*my));
+                            const float center[3] = {tabX[ix], tabY[iy], tabZ[iz]};
+                            if (!triBoxOverlap(center, half, t.pos)) continue;
+                            if (WRITE) {
+                                const unsigned long long at = offsets[ti] + atomicAdd(&written, 1ull);
+                                keys[at] = uint64_t(vx + ix) + uint64_t(P.volumeW)*(uint64_t(vy + iy) + uint64_t(P.volumeH)*uint64_t(vz + iz));
+                                cellContribution(t, center[0], center[1], center[2], records[at]);
+                            }
+                            ++mine;
+                        }
+                    }
+                }
+            }
+        }
+        if (!WRITE) {
+            atomicAdd(&blockTotal, mine);
+            __syncthreads();
+            if (threadIdx.x == 0) counts[ti] = blockTotal;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kThreads)
-countCellsKernel(Partition P, const MeshTriangle *__restrict__ tris, uint32_t nTris, uint64_t *counts) {
+countCellsKernel(Partition P, const MeshTriangle *__restrict__ tris, uint32_t nTris, uint64_t *counts, uint32_t *largeList,
+                 uint32_t *largeCount) {
     const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
     if (i >= nTris) return;
+    if (boxCells(P, tris[i]) > kLargeCells) {       // a block's job (largeTrianglesKernel)
+        largeList[atomicAdd(largeCount, 1u)] = i;
+        counts[i] = 0;
+        return;
+    }
     counts[i] = cellsOfTriangle<false>(P, tris[i], nullptr, nullptr, 0);
 }
 
@@ -258,6 +395,7 @@ writeCellsKernel(Partition P, const MeshTriangle *__restrict__ tris, uint32_t nT
                  uint64_t *keys, CellRecord *records) {
     const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
     if (i >= nTris) return;
+    if (boxCells(P, tris[i]) > kLargeCells) return; // written by largeTrianglesKernel<true>
     cellsOfTriangle<true>(P, tris[i], keys, records, offsets[i]);
 }
 
@@ -466,8 +604,20 @@ bool voxelizeMesh(const Mesh &mesh, int sideLength, uint64_t memoryBudget, int t
 
     Timer timer;
     timer.start();
-    countCellsKernel<<<blocks, kThreads>>>(P, dTris.p, nTris, dCounts.p);
+    Dev<uint32_t> largeList, largeCount;
+    SVO_VOX_CUDA(largeList.alloc(nTris));
+    SVO_VOX_CUDA(largeCount.alloc(1));
+    SVO_VOX_CUDA(cudaMemset(largeCount.p, 0, sizeof(uint32_t)));
+    countCellsKernel<<<blocks, kThreads>>>(P, dTris.p, nTris, dCounts.p, largeList.p, largeCount.p);
     SVO_VOX_CUDA(cudaGetLastError());
+    uint32_t nLarge = 0;
+    SVO_VOX_CUDA(cudaMemcpy(&nLarge, largeCount.p, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    const unsigned largeBlocks = nLarge < 148u*8u ? nLarge : 148u*8u;
+    if (nLarge) {
+        largeTrianglesKernel<false><<<largeBlocks, kLargeThreads>>>(P, dTris.p, largeList.p, largeCount.p, dCounts.p, nullptr, nullptr, nullptr);
+        SVO_VOX_CUDA(cudaGetLastError());
+    }
+    stats.largeTriangles = nLarge;
     Dev<uint8_t> temp;
     size_t tempBytes = 0;
     SVO_VOX_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tempBytes, dCounts.p, dCounts.p, int(nTris) + 1));
@@ -486,6 +636,10 @@ bool voxelizeMesh(const Mesh &mesh, int sideLength, uint64_t memoryBudget, int t
     SVO_VOX_CUDA(records.alloc(n));
     writeCellsKernel<<<blocks, kThreads>>>(P, dTris.p, nTris, dCounts.p, keys.p, records.p);
     SVO_VOX_CUDA(cudaGetLastError());
+    if (nLarge) {
+        largeTrianglesKernel<true><<<largeBlocks, kLargeThreads>>>(P, dTris.p, largeList.p, largeCount.p, nullptr, dCounts.p, keys.p, records.p);
+        SVO_VOX_CUDA(cudaGetLastError());
+    }
     stats.overlapMs = timer.stop();
     dTris.release();
     dCounts.release();

@@ -17,6 +17,7 @@ struct VoxelizeStats {
     int cacheBlock = 0;           // edge of the reference's cache block for this memory budget
     int subBlock[3] = {0, 0, 0};  // per-thread sub-block of the reference's partition
     float overlapMs = 0.0f, sortMs = 0.0f, foldMs = 0.0f;
+    uint32_t largeTriangles = 0;  // triangles handled by a whole block each (bounding box of more than 2^15 cells)
 };
 
 // The voxels the reference's PlyLoader + VoxelData(loader, sideLength, memoryBudget) hand to buildOctree,

@@ -133,7 +133,7 @@ class BuildStats(C.Structure):
 
 class VoxelizeStats(C.Structure):
     _fields_ = [("triangles", C.c_uint64), ("cell_records", C.c_uint64), ("voxels", C.c_uint64), ("dims", C.c_int32 * 3),
-                ("cache_block", C.c_int32), ("sub_block", C.c_int32 * 3), ("reserved", C.c_int32),
+                ("cache_block", C.c_int32), ("sub_block", C.c_int32 * 3), ("large_triangles", C.c_int32),
                 ("overlap_ms", C.c_float), ("sort_ms", C.c_float), ("fold_ms", C.c_float), ("reserved2", C.c_float)]
 
 

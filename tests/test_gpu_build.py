@@ -239,6 +239,42 @@ def _ico_ply(path, freq):
     return path
 
 
+def _lowpoly_ply(path):
+    """Nine triangles that are large at any resolution: a skewed, slightly rotated octahedron and one thin sliver across
+    the whole volume (binary little-endian, positions only: face normals come from the loader)."""
+    import struct
+    c, s_ = np.cos(0.3), np.sin(0.3)
+    rot = np.array([[c, -s_, 0.0], [s_, c, 0.0], [0.0, 0.0, 1.0]]) @ np.array([[1.0, 0.0, 0.0], [0.0, np.cos(0.2), -np.sin(0.2)], [0.0, np.sin(0.2), np.cos(0.2)]])
+    octa = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]], np.float64) * [1.0, 0.7, 0.85]
+    verts = np.vstack([octa @ rot.T, [[-0.9, -0.6, -0.8], [0.95, 0.62, 0.7], [0.9, 0.66, 0.74]]]).astype(np.float32)
+    faces = [(0, 2, 4), (2, 1, 4), (1, 3, 4), (3, 0, 4), (2, 0, 5), (1, 2, 5), (3, 1, 5), (0, 3, 5), (6, 7, 8)]
+    with open(path, "wb") as fp:
+        fp.write(("ply\nformat binary_little_endian 1.0\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z\n"
+                  "element face %d\nproperty list uchar int vertex_indices\nend_header\n" % (len(verts), len(faces))).encode())
+        for v in verts:
+            fp.write(struct.pack("<fff", *v))
+        for f in faces:
+            fp.write(struct.pack("<Biii", 3, *f))
+    return path
+
+
+def test_build_from_low_poly_ply_large_triangles(pysvo, ref, tmp_path):
+    """Triangles whose bounding boxes hold 10^5 .. 10^7 cells go through the block-per-triangle path of the voxeliser
+    (largeTrianglesKernel): the tree must still be the reference builder's, word for word -- one cache block and several."""
+    ply = _lowpoly_ply(tmp_path / "lowpoly.ply")
+    threads = ref.hardware_threads()
+    for res, mem in ((96, 1 << 30), (256, 1 << 30), (200, 1 << 22)):
+        h = ref.tree_build_ply(ply, res, mem)
+        want = ref.tree_words(h)
+        ref.tree_destroy(h)
+        tree = pysvo.VoxelOctree.build_from_ply(ply, res, mem_budget=mem, threads=threads)
+        st = pysvo.VoxelOctree.last_voxelize_stats()
+        got = tree.words()
+        tree.close()
+        assert st.large_triangles >= 8, (res, st.large_triangles)
+        assert got.size == want.size and np.array_equal(got, want), (res, mem, list(st.sub_block), st.cache_block)
+
+
 def test_build_from_ply_equals_reference(pysvo, port, ref, tmp_path):
     """Row f3 + f2 end to end: PLY -> voxels (GPU) -> tree (GPU) against the reference's own
     PlyLoader + VoxelData + VoxelOctree run (in-memory -builder path, Main.cpp:320-325) with the same pool size:
