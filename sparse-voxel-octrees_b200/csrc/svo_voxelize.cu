@@ -108,6 +108,25 @@ __device__ bool triBoxOverlap(const float *c, const float *h, const float (*tv)[
     return normal[0]*vmax[0] + normal[1]*vmax[1] + normal[2]*vmax[2] >= 0.0f;
 }
 
+// The last of triBoxOverlap's thirteen tests (planeBoxOverlap) on its own, same operations: true = the triangle's plane
+// misses the box, so triBoxOverlap is false. The separating-axis test is a conjunction of independent tests, so running
+// this one first changes no result; for a large triangle it rejects nearly every cell of the bounding box at a quarter
+// of the cost.
+__device__ __forceinline__ bool planeMissesBox(const float *c, const float *h, const float (*tv)[3]) {
+    float v0[3], v1[3], v2[3], e0[3], e1[3];
+    for (int q = 0; q < 3; ++q) { v0[q] = tv[0][q] - c[q]; v1[q] = tv[1][q] - c[q]; v2[q] = tv[2][q] - c[q]; }
+    for (int q = 0; q < 3; ++q) { e0[q] = v1[q] - v0[q]; e1[q] = v2[q] - v1[q]; }
+    float normal[3], vmin[3], vmax[3];
+    cross3(e0, e1, normal);
+    for (int q = 0; q < 3; ++q) {
+        const float v = v0[q];
+        if (normal[q] > 0.0f) { vmin[q] = -h[q] - v; vmax[q] = h[q] - v; }
+        else { vmin[q] = h[q] - v; vmax[q] = -h[q] - v; }
+    }
+    if (normal[0]*vmin[0] + normal[1]*vmin[1] + normal[2]*vmin[2] > 0.0f) return true;
+    return !(normal[0]*vmax[0] + normal[1]*vmax[1] + normal[2]*vmax[2] >= 0.0f);
+}
+
 // ---- material codec (reference src/Util.hpp:64-100) ----
 
 __device__ uint32_t compressMaterial(const float *n, float shade) {
@@ -278,20 +297,26 @@ __device__ __forceinline__ void runningSums(float *table, float first, float ste
 template <bool WRITE>
 __global__ void __launch_bounds__(kLargeThreads)
 largeTrianglesKernel(Partition P, const MeshTriangle *__restrict__ tris, const uint32_t *__restrict__ largeList,
-                     const uint32_t *__restrict__ largeCount, uint64_t *counts, const uint64_t *__restrict__ offsets,
-                     uint64_t *keys, CellRecord *records) {
+                     const uint32_t *__restrict__ largeCount, int slabs, uint64_t *itemCounts, const uint64_t *__restrict__ itemOffsets,
+                     const uint64_t *__restrict__ offsets, uint64_t *keys, CellRecord *records) {
     __shared__ float subX[kAxisTable], subY[kAxisTable], subZ[kAxisTable];     // sub-block centres of the current window
     __shared__ float tabX[kAxisTable], tabY[kAxisTable], tabZ[kAxisTable];     // cell centres of the current sub-block (window)
     __shared__ int subList[kSubList];
     __shared__ int subCount;
     __shared__ unsigned long long written, blockTotal;
-    const uint32_t nLarge = *largeCount;
-    for (uint32_t item = blockIdx.x; item < nLarge; item += gridDim.x) {
-        const uint32_t ti = largeList[item];
+    // a work item is (large triangle, slab): the triangle's cell range along z is cut into `slabs` pieces so that a mesh of a
+    // few huge triangles still fills the GPU; every block of a triangle repeats the (cheap) sub-block tests and takes the cells
+    // of its slab only -- with the running sums still started where the reference starts them
+    const uint32_t nItems = *largeCount*uint32_t(slabs);
+    for (uint32_t item = blockIdx.x; item < nItems; item += gridDim.x) {
+        const uint32_t ti = largeList[item/uint32_t(slabs)];
+        const int slab = int(item % uint32_t(slabs));
         const MeshTriangle &t = tris[ti];
         int lx, ly, lz, ux, uy, uz;
         pointToGrid(P, t.lower, lx, ly, lz);
         pointToGrid(P, t.upper, ux, uy, uz);
+        const long long zCells = (long long)uz - lz + 1;
+        const int slabLo = lz + int(zCells*slab/slabs), slabHi = lz + int(zCells*(slab + 1)/slabs) - 1;
         const int lgx = lx/P.subW, lgy = ly/P.subH, lgz = lz/P.subD;
         const int ugx = (ux + 1)/P.subW, ugy = (uy + 1)/P.subH, ugz = (uz + 1)/P.subD;
         const bool ranged = max(ugx - lgx, max(ugy - lgy, ugz - lgz)) > 0;       // else: the one sub-block, untested (:272-276)
@@ -326,7 +351,7 @@ largeTrianglesKernel(Partition P, const MeshTriangle *__restrict__ tris, const u
                     bool overlaps = true;
                     if (ranged) {
                         const float c[3] = {subX[int(q % cxn)], subY[int((q/cxn) % cyn)], subZ[int(q/((long long)cxn*cyn))]};
-                        overlaps = triBoxOverlap(c, subHalf, t.pos);
+                        overlaps = !planeMissesBox(c, subHalf, t.pos) && triBoxOverlap(c, subHalf, t.pos);
                     }
                     if (overlaps) subList[atomicAdd(&subCount, 1)] = int(q - base);
                 }
@@ -346,8 +371,10 @@ largeTrianglesKernel(Partition P, const MeshTriangle *__restrict__ tris, const u
                     const int cux = min(ux, bufferX + min(offX + P.subW, bufferW) - 1), cuy = min(uy, bufferY + min(offY + P.subH, bufferH) - 1),
                               cuz = min(uz, bufferZ + min(offZ + P.subD, bufferD) - 1);
                     if (clx > cux || cly > cuy || clz > cuz) continue;      // (block-uniform: every thread takes the same branch)
-                    for (int vz = clz; vz <= cuz; vz += kAxisTable) for (int vy = cly; vy <= cuy; vy += kAxisTable) for (int vx = clx; vx <= cux; vx += kAxisTable) {
-                        const int mx = min(kAxisTable, cux - vx + 1), my = min(kAxisTable, cuy - vy + 1), mz = min(kAxisTable, cuz - vz + 1);
+                    const int zlo = max(clz, slabLo), zhi = min(cuz, slabHi);
+                    if (zlo > zhi) continue;
+                    for (int vz = zlo; vz <= zhi; vz += kAxisTable) for (int vy = cly; vy <= cuy; vy += kAxisTable) for (int vx = clx; vx <= cux; vx += kAxisTable) {
+                        const int mx = min(kAxisTable, cux - vx + 1), my = min(kAxisTable, cuy - vy + 1), mz = min(kAxisTable, zhi - vz + 1);
                         __syncthreads();        // the cell tables of the previous sub-block are no longer read
                         if (threadIdx.x == 96) { float v = (float(clx) - 0.5f)*hx; for (int k = clx; k < vx; ++k) v += hx; runningSums(tabX, v, hx, mx); }
                         if (threadIdx.x == 128) { float v = (float(cly) - 0.5f)*hx; for (int k = cly; k < vy; ++k) v += hx; runningSums(tabY, v, hx, my); }
@@ -357,9 +384,9 @@ largeTrianglesKernel(Partition P, const MeshTriangle *__restrict__ tris, const u
                         for (long long c = threadIdx.x; c < cells; c += kLargeThreads) {
                             const int ix = int(c % mx), iy = int((c/mx) % my), iz = int(c/((long long)mx*my));
                             const float center[3] = {tabX[ix], tabY[iy], tabZ[iz]};
-                            if (!triBoxOverlap(center, half, t.pos)) continue;
+                            if (planeMissesBox(center, half, t.pos) || !triBoxOverlap(center, half, t.pos)) continue;
                             if (WRITE) {
-                                const unsigned long long at = offsets[ti] + atomicAdd(&written, 1ull);
+                                const unsigned long long at = offsets[ti] + itemOffsets[item] + atomicAdd(&written, 1ull);
                                 keys[at] = uint64_t(vx + ix) + uint64_t(P.volumeW)*(uint64_t(vy + iy) + uint64_t(P.volumeH)*uint64_t(vz + iz));
                                 cellContribution(t, center[0], center[1], center[2], records[at]);
                             }
@@ -372,9 +399,23 @@ largeTrianglesKernel(Partition P, const MeshTriangle *__restrict__ tris, const u
         if (!WRITE) {
             atomicAdd(&blockTotal, mine);
             __syncthreads();
-            if (threadIdx.x == 0) counts[ti] = blockTotal;
+            if (threadIdx.x == 0) itemCounts[item] = blockTotal;
         }
     }
+}
+
+// per large triangle: where each of its slabs' records start inside the triangle's range, and the triangle's total
+__global__ void __launch_bounds__(kThreads)
+largeOffsetsKernel(const uint32_t *__restrict__ largeList, const uint32_t *__restrict__ largeCount, int slabs,
+                   const uint64_t *__restrict__ itemCounts, uint64_t *itemOffsets, uint64_t *counts) {
+    const uint32_t j = blockIdx.x*blockDim.x + threadIdx.x;
+    if (j >= *largeCount) return;
+    uint64_t run = 0;
+    for (int sIdx = 0; sIdx < slabs; ++sIdx) {
+        itemOffsets[size_t(j)*slabs + sIdx] = run;
+        run += itemCounts[size_t(j)*slabs + sIdx];
+    }
+    counts[largeList[j]] = run;
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -612,9 +653,19 @@ bool voxelizeMesh(const Mesh &mesh, int sideLength, uint64_t memoryBudget, int t
     SVO_VOX_CUDA(cudaGetLastError());
     uint32_t nLarge = 0;
     SVO_VOX_CUDA(cudaMemcpy(&nLarge, largeCount.p, sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    const unsigned largeBlocks = nLarge < 148u*8u ? nLarge : 148u*8u;
+    // few large triangles: cut each into slabs along z so that there are about four blocks per SM
+    int slabs = 1;
+    if (nLarge) slabs = int(std::min<uint64_t>(64, std::max<uint64_t>(1, (148u*4u + nLarge - 1)/nLarge)));
+    const uint64_t nItems = uint64_t(nLarge)*uint64_t(slabs);
+    const unsigned largeBlocks = unsigned(std::min<uint64_t>(nItems, 148u*8u));
+    Dev<uint64_t> itemCounts, itemOffsets;
     if (nLarge) {
-        largeTrianglesKernel<false><<<largeBlocks, kLargeThreads>>>(P, dTris.p, largeList.p, largeCount.p, dCounts.p, nullptr, nullptr, nullptr);
+        SVO_VOX_CUDA(itemCounts.alloc(nItems));
+        SVO_VOX_CUDA(itemOffsets.alloc(nItems));
+        largeTrianglesKernel<false><<<largeBlocks, kLargeThreads>>>(P, dTris.p, largeList.p, largeCount.p, slabs, itemCounts.p, nullptr,
+                                                                     nullptr, nullptr, nullptr);
+        SVO_VOX_CUDA(cudaGetLastError());
+        largeOffsetsKernel<<<(nLarge + kThreads - 1)/kThreads, kThreads>>>(largeList.p, largeCount.p, slabs, itemCounts.p, itemOffsets.p, dCounts.p);
         SVO_VOX_CUDA(cudaGetLastError());
     }
     stats.largeTriangles = nLarge;
@@ -637,7 +688,8 @@ bool voxelizeMesh(const Mesh &mesh, int sideLength, uint64_t memoryBudget, int t
     writeCellsKernel<<<blocks, kThreads>>>(P, dTris.p, nTris, dCounts.p, keys.p, records.p);
     SVO_VOX_CUDA(cudaGetLastError());
     if (nLarge) {
-        largeTrianglesKernel<true><<<largeBlocks, kLargeThreads>>>(P, dTris.p, largeList.p, largeCount.p, nullptr, dCounts.p, keys.p, records.p);
+        largeTrianglesKernel<true><<<largeBlocks, kLargeThreads>>>(P, dTris.p, largeList.p, largeCount.p, slabs, nullptr, itemOffsets.p,
+                                                                    dCounts.p, keys.p, records.p);
         SVO_VOX_CUDA(cudaGetLastError());
     }
     stats.overlapMs = timer.stop();

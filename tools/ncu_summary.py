@@ -82,6 +82,10 @@ if __name__ == "__main__":
             raise SystemExit(f"no kernel matching {pattern!r} in {sys.argv[1]}")
         d = pick[0]
         g = lambda k: d[k]["value"] if k in d else None  # noqa: E731
+        byte_scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+
+        def gb(k):      # ncu prints byte counters in scaled units
+            return None if k not in d else d[k]["value"] * byte_scale.get(d[k]["unit"], 1.0)
         to_ms = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
         h = hashlib.sha256()
         for name in ("svo_traverse.cuh", "svo_kernels.cu", "svo_kernels.cuh"):
@@ -90,12 +94,12 @@ if __name__ == "__main__":
         entry = {
             "source": f"{sys.argv[1]} (ncu --set full --clock-control none, one launch)", "kernel": d["kernel"][:80],
             "kernel_source_hash": h.hexdigest()[:16], "commit": commit or None,
-            "dram_bytes_per_launch": (g("dram__bytes_read.sum") or 0) + (g("dram__bytes_write.sum") or 0),
-            "dram_bytes_read": g("dram__bytes_read.sum"), "dram_bytes_write": g("dram__bytes_write.sum"),
+            "dram_bytes_per_launch": (gb("dram__bytes_read.sum") or 0) + (gb("dram__bytes_write.sum") or 0),
+            "dram_bytes_read": gb("dram__bytes_read.sum"), "dram_bytes_write": gb("dram__bytes_write.sum"),
             "l1_hit_pct": g("l1tex__t_sector_hit_rate.pct"), "l2_hit_pct": g("lts__t_sector_hit_rate.pct"),
             "l1_throughput_pct": g("l1tex__throughput.avg.pct_of_peak_sustained_elapsed"),
             "l2_throughput_pct": g("lts__throughput.avg.pct_of_peak_sustained_elapsed"),
-            "l2_bytes": g("lts__t_bytes.sum"), "l1_bytes": g("l1tex__t_bytes.sum"),
+            "l2_bytes": gb("lts__t_bytes.sum"), "l1_bytes": gb("l1tex__t_bytes.sum"),
             "issue_active_pct": g("smsp__issue_active.avg.pct_of_peak_sustained_active"),
             "threads_per_instruction": g("smsp__thread_inst_executed_per_inst_executed.ratio"),
             "warp_instructions": g("smsp__inst_executed.sum"),
