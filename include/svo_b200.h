@@ -448,8 +448,9 @@ typedef struct svo_sequence_stats {
     uint64_t fine_rays;         /* renderTile's raymarch calls, all devices, all frames */
     uint64_t kernel_launches;   /* kernels enqueued, all devices */
     float device_ms;            /* SVO_OUTPUT_DEVICE: CUDA events on devices[0] around the whole sequence
-                                 * (first frame issued ... last frame gathered); SVO_OUTPUT_HOST: 0 */
-    float wall_ms;              /* host clock: call entered ... last frame complete (in HBM / in host memory) */
+                                 * (recorded when every worker is ready to enqueue ... last frame gathered); SVO_OUTPUT_HOST: 0 */
+    float wall_ms;              /* host clock: every device's worker ready to enqueue ... last frame complete (in HBM / in
+                                 * host memory); the workers' wake-up before that is not counted */
     int32_t lanes;              /* frames in flight */
     int32_t tile_run;           /* width of the devices' stripes in 8-pixel tile columns */
 } svo_sequence_stats;

