@@ -325,8 +325,20 @@ typedef struct svo_frame_desc {
      * renderHalfSize preview (Main.cpp:161, while the mouse drags): inside every 8x8 tile only pixels at
      * offsets 0, 3, 6 are traced and each other pixel repeats the traced pixel up-left of it. */
     int32_t pixel_stride;
-    int32_t reserved;
+    /* svo_pixel_format of HOST frames delivered by svo_multi_render_sequence / svo_multi_render_frame (every other entry
+     * point takes SVO_PIXELS_RGBA8 only). */
+    int32_t pixel_format;
 } svo_frame_desc;
+
+/* The reference's image is grey with full or no coverage: renderTile stores 0xFF000000 | g << 16 | g << 8 | g
+ * (Main.cpp:128-132) and skipped tiles keep the strip memset's 0x00000000 (Main.cpp:165). SVO_PIXELS_GREY8A8 ships exactly
+ * that information in two bytes per pixel -- byte 0 = g, byte 1 = alpha (0 or 255) -- packed on the GPU before the
+ * device -> host copy: half the bytes on links that are the limit of host-visible frame rates (one PCIe link for 720p
+ * frames of a small tree, the box's host links at 4 and 8 GPUs). svo_pixels_expand_grey8a turns it back into the
+ * reference's words, bit for bit. */
+typedef enum svo_pixel_format { SVO_PIXELS_RGBA8 = 0, SVO_PIXELS_GREY8A8 = 1 } svo_pixel_format;
+/* dst[i] = alpha << 24 | g << 16 | g << 8 | g for n pixels (host memory; dst may not overlap src). */
+SVO_API void svo_pixels_expand_grey8a(const uint16_t *src, uint64_t n, uint32_t *dst);
 
 typedef struct svo_frame_stats {
     uint64_t coarse_rays;       /* raymarch calls of the beam pass (Main.cpp:181) made by this rank (a subset of
@@ -460,7 +472,8 @@ typedef void (*svo_frame_callback)(void *user, int frame, const uint32_t *rgba);
 
 /* Renders cams[0 .. n_frames) back to back (the reference's renderLoop, Main.cpp:204-262, over a camera path).
  * desc->tile_rank / tile_world are ignored (the handle deals the tiles). SVO_OUTPUT_HOST: frame k lands in
- * host_frames[k % n_host_frames] (page-locked, width*height words each); min(6, n_host_frames) frames are in
+ * host_frames[k % n_host_frames] (page-locked; width*height words each, or width*height uint16 when desc->pixel_format is
+ * SVO_PIXELS_GREY8A8 -- the pointers are then really uint16_t *); min(6, n_host_frames) frames are in
  * flight; on_frame (optional) sees every frame. SVO_OUTPUT_DEVICE: host_frames is ignored; the last frames stay
  * in devices[0]'s HBM (svo_multi_device_frame). `stats` is optional. */
 SVO_API int svo_multi_render_sequence(svo_multi *m, const svo_camera *cams, int n_frames, const svo_frame_desc *desc,

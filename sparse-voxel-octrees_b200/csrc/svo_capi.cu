@@ -371,6 +371,8 @@ int checkDesc(const svo_frame_desc *desc) {
         return fail(SVO_ERR_INVALID_ARGUMENT, "bad tile interleave rank %d of %d", desc->tile_rank, desc->tile_world);
     if (desc->pixel_stride < 0 || desc->pixel_stride > 8)
         return fail(SVO_ERR_INVALID_ARGUMENT, "pixel_stride must be in [0, 8] (got %d)", desc->pixel_stride);
+    if (desc->pixel_format != SVO_PIXELS_RGBA8 && desc->pixel_format != SVO_PIXELS_GREY8A8)
+        return fail(SVO_ERR_INVALID_ARGUMENT, "unknown pixel format %d", desc->pixel_format);
     return SVO_OK;
 }
 
@@ -578,6 +580,13 @@ int svo_device_count(int *count) {
 }
 
 void svo_free(void *p) { free(p); }
+
+void svo_pixels_expand_grey8a(const uint16_t *src, uint64_t n, uint32_t *dst) {
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint32_t p = src[i], g = p & 0xFFu;
+        dst[i] = ((p & 0xFF00u) << 16) | (g << 16) | (g << 8) | g;
+    }
+}
 
 int svo_host_alloc(size_t bytes, void **out) {
     if (!out) return fail(SVO_ERR_INVALID_ARGUMENT, "null out");
@@ -1197,6 +1206,8 @@ int svo_render_frame_device(svo_tree *tree, const svo_camera *cam, const svo_fra
     if (!tree || !cam || !d_rgba) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_render_frame_device: null argument");
     int st = checkDesc(desc);
     if (st != SVO_OK) return st;
+    if (desc->pixel_format != SVO_PIXELS_RGBA8) return fail(SVO_ERR_UNSUPPORTED, "svo_render_frame_device writes SVO_PIXELS_RGBA8 only");
+    if (desc->pixel_format != SVO_PIXELS_RGBA8) return fail(SVO_ERR_UNSUPPORTED, "svo_render_frame_device writes SVO_PIXELS_RGBA8 only");
     SVO_DEVICE(tree->device);
     std::lock_guard<std::mutex> lock(tree->mutex);
     FramePlan *plan = nullptr;
@@ -1230,6 +1241,7 @@ int svo_render_frame_async(svo_tree *tree, const svo_camera *cam, const svo_fram
     if (!tree || !cam || !rgba || !ticket) return fail(SVO_ERR_INVALID_ARGUMENT, "svo_render_frame_async: null argument");
     int st = checkDesc(desc);
     if (st != SVO_OK) return st;
+    if (desc->pixel_format != SVO_PIXELS_RGBA8) return fail(SVO_ERR_UNSUPPORTED, "svo_render_frame[_async] delivers SVO_PIXELS_RGBA8 only (svo_multi_render_* take SVO_PIXELS_GREY8A8)");
     SVO_DEVICE(tree->device);
     std::lock_guard<std::mutex> lock(tree->mutex);
     FramePlan *plan = nullptr;

@@ -856,6 +856,32 @@ copyOwnedColumnsKernel(const uint32_t *__restrict__ src, uint32_t *__restrict__ 
     dst[at] = src[at];
 }
 
+// RGBA words -> (grey, alpha) byte pairs for the tile columns a rank owns (SVO_PIXELS_GREY8A8): the reference's pixel is
+// 0xFF000000 | g << 16 | g << 8 | g or 0 (Main.cpp:128-132, :165), so byte 0 and byte 3 of the word carry all of it.
+__global__ void __launch_bounds__(256)
+packGrey8a8Kernel(const uint32_t *__restrict__ src, uint16_t *__restrict__ dst, int width, int height, int ownedPixels,
+                  int run, int tileRank, int tileWorld) {
+    const uint32_t k = blockIdx.x*256u + threadIdx.x;
+    const int y = int(blockIdx.y);
+    if (k >= uint32_t(ownedPixels) || y >= height) return;
+    const uint32_t slot = k >> 3;
+    const uint32_t tx = (slot/uint32_t(run))*uint32_t(tileWorld*run) + uint32_t(tileRank*run) + slot%uint32_t(run);
+    const uint32_t x = tx*8u + (k & 7u);
+    if (x >= uint32_t(width)) return;
+    const size_t at = size_t(y)*size_t(width) + x;
+    const uint32_t p = src[at];
+    dst[at] = uint16_t((p & 0xFFu) | ((p >> 16) & 0xFF00u));
+}
+
+cudaError_t launchPackGrey8a8(const FramePlanDev &plan, int width, int height, const uint32_t *src, uint16_t *dst,
+                              int tileRank, int tileWorld, cudaStream_t stream) {
+    const int ownedPixels = ownedCols(plan, tileRank, tileWorld)*8;
+    if (ownedPixels <= 0) return cudaSuccess;
+    dim3 grid(unsigned((ownedPixels + 255)/256), unsigned(height));
+    packGrey8a8Kernel<<<grid, 256, 0, stream>>>(src, dst, width, height, ownedPixels, tileRunLength(tileWorld), tileRank, tileWorld);
+    return cudaGetLastError();
+}
+
 cudaError_t launchCopyOwnedColumns(const FramePlanDev &plan, int width, int height, const uint32_t *src, uint32_t *dst,
                                    int tileRank, int tileWorld, cudaStream_t stream) {
     const int ownedPixels = ownedCols(plan, tileRank, tileWorld)*8;

@@ -99,6 +99,9 @@ int finePassUsesPrefix(const TreeDev &tree, int flavour, int pixelStride);
 
 // The owned tile columns' pixels from `src` to `dst` (both width x height, pitch = width): the per-rank
 // device -> host leg of a multi-GPU frame when `dst` is mapped page-locked host memory.
+// The owned tile columns' pixels as (grey, alpha) byte pairs (SVO_PIXELS_GREY8A8), same pitch in pixels.
+cudaError_t launchPackGrey8a8(const FramePlanDev &plan, int width, int height, const uint32_t *src, uint16_t *dst,
+                              int tileRank, int tileWorld, cudaStream_t stream);
 cudaError_t launchCopyOwnedColumns(const FramePlanDev &plan, int width, int height, const uint32_t *src, uint32_t *dst,
                                    int tileRank, int tileWorld, cudaStream_t stream);
 

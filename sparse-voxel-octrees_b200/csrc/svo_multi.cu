@@ -53,6 +53,8 @@ struct Replica {
     cudaStream_t copy = nullptr;
     uint32_t *fb[kLanes] = {};          // local framebuffers (host output)
     size_t fbBytes = 0;
+    uint16_t *fb16[kLanes] = {};        // ... packed to (grey, alpha) pairs for SVO_PIXELS_GREY8A8 host frames
+    size_t fb16Bytes = 0;
     cudaEvent_t done[kLanes] = {};      // the device's share of the frame in lane l is rendered
     cudaEvent_t copied[kLanes] = {};    // ... and has left fb[l] for host memory
     bool copiedRecorded[kLanes] = {};
@@ -143,6 +145,16 @@ int runSequence(svo_multi *M, Replica &rep, const Job &job, uint64_t generation)
             }
             rep.fbBytes = frameBytes;
         }
+        if (desc.pixel_format == SVO_PIXELS_GREY8A8 && rep.fb16Bytes < frameBytes/2) {
+            SVO_CUDA(cudaDeviceSynchronize());
+            for (int l = 0; l < kLanes; ++l) {
+                if (rep.fb16[l]) cudaFree(rep.fb16[l]);
+                rep.fb16[l] = nullptr;
+            }
+            rep.fb16Bytes = 0;
+            for (int l = 0; l < kLanes; ++l) SVO_CUDA(cudaMalloc(&rep.fb16[l], frameBytes/2));
+            rep.fb16Bytes = frameBytes/2;
+        }
     }
     // ready; the caller records the sequence's start event once every device is, then opens the gate
     M->ready.fetch_add(1, std::memory_order_acq_rel);
@@ -185,9 +197,19 @@ int runSequence(svo_multi *M, Replica &rep, const Job &job, uint64_t generation)
         if (job.output == SVO_OUTPUT_HOST) {
             uint32_t *host = job.hostFrames[k % job.nHost];
             SVO_CUDA(cudaStreamWaitEvent(rep.copy, rep.done[l], 0));
+            const bool packed = desc.pixel_format == SVO_PIXELS_GREY8A8;
+            const size_t pixelBytes = packed ? sizeof(uint16_t) : sizeof(uint32_t);
+            const unsigned char *srcBytes = reinterpret_cast<const unsigned char *>(rep.fb[l]);
+            if (packed) {
+                // two bytes per pixel: this device's stripes packed to (grey, alpha) on the GPU, then shipped
+                SVO_CUDA(svo::launchPackGrey8a8(plan->dev, desc.width, desc.height, rep.fb[l], rep.fb16[l], rep.index, N, rep.copy));
+                ++rep.launches;
+                srcBytes = reinterpret_cast<const unsigned char *>(rep.fb16[l]);
+            }
+            unsigned char *hostBytes = reinterpret_cast<unsigned char *>(host);
             if (N == 1) {
-                SVO_CUDA(cudaMemcpyAsync(host, rep.fb[l], frameBytes, cudaMemcpyDeviceToHost, rep.copy));   // copy engine
-            } else if (hostCopyByKernel()) {
+                SVO_CUDA(cudaMemcpyAsync(hostBytes, srcBytes, frameBytes/sizeof(uint32_t)*pixelBytes, cudaMemcpyDeviceToHost, rep.copy));   // copy engine
+            } else if (hostCopyByKernel() && !packed) {
                 // this device's stripes only, stored by a kernel straight into the (mapped, page-locked) host frame
                 void *mapped = nullptr;
                 SVO_CUDA(cudaHostGetDevicePointer(&mapped, host, 0));
@@ -197,11 +219,11 @@ int runSequence(svo_multi *M, Replica &rep, const Job &job, uint64_t generation)
             } else {
                 // this device's stripes only, one strided copy per stripe on the copy engine (no SM involved)
                 const int run = svo::tileRunLength(N);
-                const size_t pitch = size_t(desc.width)*sizeof(uint32_t);
+                const size_t pitch = size_t(desc.width)*pixelBytes;
                 for (int tx0 = rep.index*run; tx0 < plan->dev.tileCols; tx0 += N*run) {
                     const int x0 = tx0*8, x1 = std::min((tx0 + run)*8, desc.width);
-                    SVO_CUDA(cudaMemcpy2DAsync(host + x0, pitch, rep.fb[l] + x0, pitch, size_t(x1 - x0)*sizeof(uint32_t),
-                                               size_t(desc.height), cudaMemcpyDeviceToHost, rep.copy));
+                    SVO_CUDA(cudaMemcpy2DAsync(hostBytes + size_t(x0)*pixelBytes, pitch, srcBytes + size_t(x0)*pixelBytes, pitch,
+                                               size_t(x1 - x0)*pixelBytes, size_t(desc.height), cudaMemcpyDeviceToHost, rep.copy));
                 }
             }
             SVO_CUDA(cudaEventRecord(rep.copied[l], rep.copy));
@@ -261,6 +283,7 @@ int destroyMulti(svo_multi *M) {
         for (int l = 0; l < kLanes; ++l) {
             if (r->lane[l]) cudaStreamDestroy(r->lane[l]);
             if (r->fb[l]) cudaFree(r->fb[l]);
+            if (r->fb16[l]) cudaFree(r->fb16[l]);
             if (r->done[l]) cudaEventDestroy(r->done[l]);
             if (r->copied[l]) cudaEventDestroy(r->copied[l]);
         }
@@ -411,6 +434,8 @@ int svo_multi_render_sequence(svo_multi *M, const svo_camera *cams, int n_frames
     } else if (!M->peer) {
         return fail(SVO_ERR_UNSUPPORTED, "SVO_OUTPUT_DEVICE needs peer access from every device to devices[0]; use SVO_OUTPUT_HOST");
     }
+    if (output == SVO_OUTPUT_DEVICE && desc.pixel_format != SVO_PIXELS_RGBA8)
+        return fail(SVO_ERR_UNSUPPORTED, "SVO_OUTPUT_DEVICE frames are SVO_PIXELS_RGBA8 (the packed format is for host frames)");
     std::lock_guard<std::mutex> call(M->callMutex);
     const auto wallStart = std::chrono::steady_clock::now();
     const size_t frameBytes = size_t(desc.width)*size_t(desc.height)*sizeof(uint32_t);
@@ -575,7 +600,7 @@ int svo_multi_render_frame(svo_multi *m, const svo_camera *cam, const svo_frame_
         cudaError_t e = cudaPointerGetAttributes(&attr, rgba);
         if (e != cudaSuccess || attr.type == cudaMemoryTypeUnregistered) {
             cudaGetLastError();
-            const size_t bytes = size_t(desc->width)*size_t(desc->height)*sizeof(uint32_t);
+            const size_t bytes = size_t(desc->width)*size_t(desc->height)*(desc->pixel_format == SVO_PIXELS_GREY8A8 ? sizeof(uint16_t) : sizeof(uint32_t));
             e = cudaHostRegister(rgba, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
             if (e != cudaSuccess) return failCuda(e, "cudaHostRegister(host frame)");
             registered = true;

@@ -89,7 +89,7 @@ class WordsReport(C.Structure):
 
 class FrameDesc(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("strips", C.c_int32), ("flavour", C.c_int32),
-                ("tile_rank", C.c_int32), ("tile_world", C.c_int32), ("pixel_stride", C.c_int32), ("reserved", C.c_int32)]
+                ("tile_rank", C.c_int32), ("tile_world", C.c_int32), ("pixel_stride", C.c_int32), ("pixel_format", C.c_int32)]
 
 
 class FrameStats(C.Structure):
@@ -114,6 +114,7 @@ class SequenceStats(C.Structure):
 
 FRAME_CALLBACK = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_void_p)
 OUTPUT_DEVICE, OUTPUT_HOST = 0, 1
+PIXELS_RGBA8, PIXELS_GREY8A8 = 0, 1     # svo_pixel_format of host frames (MultiOctree.render_frame / render_sequence)
 
 
 class FrameLayout(C.Structure):
@@ -225,6 +226,7 @@ def lib():
         "svo_multi_render_frame": (i32, [vp, P(Camera), P(FrameDesc), vp, P(FrameStats)]),
         "svo_multi_device_frame": (i32, [vp, i32, P(vp)]),
         "svo_multi_raymarch_batch": (i32, [vp, u64, vp, vp, f32, i32, vp, vp, vp, vp]),
+        "svo_pixels_expand_grey8a": (None, [vp, u64, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)
@@ -669,26 +671,28 @@ class MultiOctree:
         t._borrowed = True
         return t
 
-    def _desc(self, width, height, strips, flavour, pixel_stride=0):
-        return FrameDesc(int(width), int(height), int(strips), int(flavour), 0, 1, int(pixel_stride), 0)
+    def _desc(self, width, height, strips, flavour, pixel_stride=0, pixel_format=PIXELS_RGBA8):
+        return FrameDesc(int(width), int(height), int(strips), int(flavour), 0, 1, int(pixel_stride), int(pixel_format))
 
-    def render_frame(self, cam: Camera, width, height, strips=16, flavour=FLAVOUR_VALIDATION, rgba=None, pixel_stride=0):
-        """-> (rgba uint32[H, W], FrameStats): renderBatch over all strips, all devices, into host memory."""
+    def render_frame(self, cam: Camera, width, height, strips=16, flavour=FLAVOUR_VALIDATION, rgba=None, pixel_stride=0,
+                     pixel_format=PIXELS_RGBA8):
+        """-> (rgba uint32[H, W] -- or (grey, alpha) byte pairs as uint16[H, W] for PIXELS_GREY8A8 --, FrameStats):
+        renderBatch over all strips, all devices, into host memory."""
         if rgba is None:
-            rgba = np.zeros((height, width), np.uint32)
+            rgba = np.zeros((height, width), np.uint16 if pixel_format == PIXELS_GREY8A8 else np.uint32)
         st = FrameStats()
-        d = self._desc(width, height, strips, flavour, pixel_stride)
+        d = self._desc(width, height, strips, flavour, pixel_stride, pixel_format)
         _check(lib().svo_multi_render_frame(self._h, C.byref(cam), C.byref(d), _ptr(rgba), C.byref(st)))
         return rgba, st
 
     def render_sequence(self, cams, width, height, strips=16, flavour=FLAVOUR_FAST, output=OUTPUT_DEVICE, host_frames=None,
-                        on_frame=None):
+                        on_frame=None, pixel_format=PIXELS_RGBA8):
         """Renders the camera path back to back (up to four frames in flight). OUTPUT_HOST: frame k lands in
         host_frames[k % len(host_frames)] (page-locked numpy arrays, e.g. PinnedArray.array); on_frame(k, array)
         is called for every finished frame. -> SequenceStats."""
         n = len(cams)
         arr = (Camera * n)(*cams)
-        d = self._desc(width, height, strips, flavour)
+        d = self._desc(width, height, strips, flavour, 0, pixel_format)
         st = SequenceStats()
         frames, nh = None, 0
         if output == OUTPUT_HOST:
@@ -731,6 +735,14 @@ class MultiOctree:
             self.close()
         except Exception:
             pass
+
+
+def expand_grey8a(packed):
+    """(grey, alpha) byte pairs (uint16 array, PIXELS_GREY8A8) -> the reference's RGBA words, svo_pixels_expand_grey8a."""
+    packed = np.ascontiguousarray(packed, np.uint16)
+    out = np.empty(packed.shape, np.uint32)
+    lib().svo_pixels_expand_grey8a(_ptr(packed), packed.size, _ptr(out))
+    return out
 
 
 def frame_layout(width, height, strips) -> FrameLayout:

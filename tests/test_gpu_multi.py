@@ -55,6 +55,18 @@ def test_multi_frames_equal_single_device(pysvo, cams, single_frames):
         assert stats.device_ms > 0 and stats.fine_rays == sum(int((w != 0).sum()) for w in want)
         for back in range(4):
             assert np.array_equal(m.device_frame(W, H, back), want[len(cams) - 1 - back]), f"devices {devices}, back {back}"
+        # the same host sequence as (grey, alpha) byte pairs: half the bytes, expanded on the host to the same words
+        ring16 = [pysvo.PinnedArray((H, W), np.uint16) for _ in range(4)]
+        seen16 = {}
+        stats = m.render_sequence(cams, W, H, strips=S, flavour=pysvo.FLAVOUR_VALIDATION, output=pysvo.OUTPUT_HOST,
+                                  host_frames=[r.array for r in ring16], on_frame=lambda k, a: seen16.__setitem__(k, a.copy()),
+                                  pixel_format=pysvo.PIXELS_GREY8A8)
+        for k in range(len(cams)):
+            assert np.array_equal(pysvo.expand_grey8a(seen16[k]), want[k]), f"devices {devices}, packed host frame {k}"
+        one16, _ = m.render_frame(cams[2], W, H, strips=S, flavour=pysvo.FLAVOUR_VALIDATION, pixel_format=pysvo.PIXELS_GREY8A8)
+        assert one16.dtype == np.uint16 and np.array_equal(pysvo.expand_grey8a(one16), want[2])
+        with pytest.raises(pysvo.SvoError):     # frames that stay on the GPU are RGBA words
+            m.render_sequence(cams[:2], W, H, strips=S, output=pysvo.OUTPUT_DEVICE, pixel_format=pysvo.PIXELS_GREY8A8)
         # a second sequence on the same handle, other size (buffers are re-used / re-allocated)
         one, _ = m.render_frame(cams[3], 200, 120, strips=4, flavour=pysvo.FLAVOUR_VALIDATION)
         t = m.tree(0)

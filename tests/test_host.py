@@ -552,6 +552,18 @@ def test_words_validate(pysvo, dragon_words, monkeypatch):
         assert e.value.status == 6
 
 
+def test_pixels_expand_grey8a(pysvo):
+    """svo_pixels_expand_grey8a: (grey, alpha) byte pairs -> the reference's pixel words (Main.cpp:128-132, :165)."""
+    rng = np.random.default_rng(2)
+    g = rng.integers(0, 256, 10007, dtype=np.uint32)
+    a = rng.choice(np.array([0, 255], np.uint32), 10007)
+    g[a == 0] = 0
+    rgba = (a << 24) | (g << 16) | (g << 8) | g
+    packed = (g | (a << 8)).astype(np.uint16)
+    assert np.array_equal(pysvo.expand_grey8a(packed), rgba)
+    assert pysvo.expand_grey8a(np.zeros(0, np.uint16)).size == 0
+
+
 def test_plain_c_example_builds_against_the_abi(pysvo, tmp_path):
     """host/example_render.c: the boundary is usable from pedantic C99 (no C++ in the header), links against the
     library, and without a device fails with the library's message instead of doing anything else."""
