@@ -873,12 +873,46 @@ packGrey8a8Kernel(const uint32_t *__restrict__ src, uint16_t *__restrict__ dst, 
     dst[at] = uint16_t((p & 0xFFu) | ((p >> 16) & 0xFF00u));
 }
 
+// four pixels per thread: a warp stores 256 contiguous bytes -- one full-width write burst when `dst` is mapped host memory
+__global__ void __launch_bounds__(256)
+packGrey8a8Vec4Kernel(const uint32_t *__restrict__ src, uint16_t *__restrict__ dst, int width, int height, int ownedQuads,
+                      int run, int tileRank, int tileWorld) {
+    const uint32_t k = blockIdx.x*256u + threadIdx.x;      // quad k of this rank's columns laid side by side (two per tile column)
+    const int y = int(blockIdx.y);
+    if (k >= uint32_t(ownedQuads) || y >= height) return;
+    const uint32_t slot = k >> 1;
+    const uint32_t tx = (slot/uint32_t(run))*uint32_t(tileWorld*run) + uint32_t(tileRank*run) + slot%uint32_t(run);
+    const uint32_t x = tx*8u + (k & 1u)*4u;
+    if (x >= uint32_t(width)) return;
+    const size_t at = size_t(y)*size_t(width) + x;
+    if (x + 4u <= uint32_t(width)) {
+        const uint4 p = *reinterpret_cast<const uint4 *>(src + at);
+        auto pack = [](uint32_t a, uint32_t b) {
+            return ((a & 0xFFu) | ((a >> 16) & 0xFF00u)) | (((b & 0xFFu) | ((b >> 16) & 0xFF00u)) << 16);
+        };
+        *reinterpret_cast<uint2 *>(dst + at) = make_uint2(pack(p.x, p.y), pack(p.z, p.w));
+    } else {
+        for (uint32_t i = 0; x + i < uint32_t(width); ++i) {
+            const uint32_t p = src[at + i];
+            dst[at + i] = uint16_t((p & 0xFFu) | ((p >> 16) & 0xFF00u));
+        }
+    }
+}
+
 cudaError_t launchPackGrey8a8(const FramePlanDev &plan, int width, int height, const uint32_t *src, uint16_t *dst,
                               int tileRank, int tileWorld, cudaStream_t stream) {
-    const int ownedPixels = ownedCols(plan, tileRank, tileWorld)*8;
-    if (ownedPixels <= 0) return cudaSuccess;
-    dim3 grid(unsigned((ownedPixels + 255)/256), unsigned(height));
-    packGrey8a8Kernel<<<grid, 256, 0, stream>>>(src, dst, width, height, ownedPixels, tileRunLength(tileWorld), tileRank, tileWorld);
+    const int cols = ownedCols(plan, tileRank, tileWorld);
+    if (cols <= 0) return cudaSuccess;
+    const bool aligned = (width & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0;
+    if (aligned) {
+        const int quads = cols*2;
+        dim3 grid(unsigned((quads + 255)/256), unsigned(height));
+        packGrey8a8Vec4Kernel<<<grid, 256, 0, stream>>>(src, dst, width, height, quads, tileRunLength(tileWorld), tileRank, tileWorld);
+    } else {
+        const int ownedPixels = cols*8;
+        dim3 grid(unsigned((ownedPixels + 255)/256), unsigned(height));
+        packGrey8a8Kernel<<<grid, 256, 0, stream>>>(src, dst, width, height, ownedPixels, tileRunLength(tileWorld), tileRank, tileWorld);
+    }
     return cudaGetLastError();
 }
 

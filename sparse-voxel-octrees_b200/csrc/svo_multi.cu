@@ -200,14 +200,27 @@ int runSequence(svo_multi *M, Replica &rep, const Job &job, uint64_t generation)
             const bool packed = desc.pixel_format == SVO_PIXELS_GREY8A8;
             const size_t pixelBytes = packed ? sizeof(uint16_t) : sizeof(uint32_t);
             const unsigned char *srcBytes = reinterpret_cast<const unsigned char *>(rep.fb[l]);
-            if (packed) {
-                // two bytes per pixel: this device's stripes packed to (grey, alpha) on the GPU, then shipped
+            bool shipped = false;
+            if (packed && N > 1) {
+                // two bytes per pixel, several devices: every device packs its stripes to (grey, alpha) pairs and stores them
+                // straight into the mapped host frame, 256 contiguous bytes per warp. (Strided copies of such narrow rows are
+                // bound by the copy engine's per-row cost, not by bytes: at N = 8, 480-byte rows took 0.286 ms per 4K frame
+                // where the RGBA frame's 960-byte rows take 0.308.)
+                void *mapped = nullptr;
+                SVO_CUDA(cudaHostGetDevicePointer(&mapped, host, 0));
+                SVO_CUDA(svo::launchPackGrey8a8(plan->dev, desc.width, desc.height, rep.fb[l], static_cast<uint16_t *>(mapped), rep.index, N, rep.copy));
+                ++rep.launches;
+                shipped = true;
+            } else if (packed) {
+                // one device: packed on the GPU, then one contiguous copy on the copy engine
                 SVO_CUDA(svo::launchPackGrey8a8(plan->dev, desc.width, desc.height, rep.fb[l], rep.fb16[l], rep.index, N, rep.copy));
                 ++rep.launches;
                 srcBytes = reinterpret_cast<const unsigned char *>(rep.fb16[l]);
             }
             unsigned char *hostBytes = reinterpret_cast<unsigned char *>(host);
-            if (N == 1) {
+            if (shipped) {
+                // nothing left to copy
+            } else if (N == 1) {
                 SVO_CUDA(cudaMemcpyAsync(hostBytes, srcBytes, frameBytes/sizeof(uint32_t)*pixelBytes, cudaMemcpyDeviceToHost, rep.copy));   // copy engine
             } else if (hostCopyByKernel() && !packed) {
                 // this device's stripes only, stored by a kernel straight into the (mapped, page-locked) host frame
@@ -343,7 +356,11 @@ int createMulti(const uint32_t *words, uint64_t nWords, const float center[3], c
             SVO_CUDA(cudaEventCreateWithFlags(&r.done[l], cudaEventDisableTiming));
             SVO_CUDA(cudaEventCreateWithFlags(&r.copied[l], cudaEventDisableTiming));
         }
-        SVO_CUDA(cudaStreamCreateWithFlags(&r.copy, cudaStreamNonBlocking));
+        // high priority: the packing kernel of SVO_PIXELS_GREY8A8 frames must not queue behind the pending blocks of the
+        // next frames' fine passes (the copies themselves run on the copy engines)
+        int prioLow = 0, prioHigh = 0;
+        SVO_CUDA(cudaDeviceGetStreamPriorityRange(&prioLow, &prioHigh));
+        SVO_CUDA(cudaStreamCreateWithPriority(&r.copy, cudaStreamNonBlocking, prioHigh));
         if (r.device != dev0) {
             int can = 0;
             SVO_CUDA(cudaDeviceCanAccessPeer(&can, r.device, dev0));
