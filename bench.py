@@ -683,7 +683,14 @@ def run_own(args):
         achieved = alg_bytes / (fine_ms_sum * 1e-3) / 1e9
         traffic = profile_traffic(w["name"]) or {}
         src_hash = kernel_source_hash()
-        fresh = traffic.get("kernel_source_hash") == src_hash
+        # the capture is quoted only if it profiled THIS machine code: the hash of the fine-pass kernel's SASS in the library
+        # being run (cuobjdump), or -- where cuobjdump is missing -- the hash of the kernel sources
+        from tools.ncu_summary import kernel_sass_hash
+        sass_hash = kernel_sass_hash(pysvo.LIB_PATH)
+        if sass_hash and traffic.get("kernel_sass_hash"):
+            fresh = traffic.get("kernel_sass_hash") == sass_hash
+        else:
+            fresh = traffic.get("kernel_source_hash") == src_hash
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic.get("dram_bytes_per_launch") if fresh else None,
                     "kernel": "finePassKernel<FAST>", "peak_source": peak_src,
@@ -691,8 +698,9 @@ def run_own(args):
                     "bytes_per_fine_ray": {"node_words": node_bytes_sum / max(fine_rays_sum, 1), "pixel_store": 4.0},
                     "launch_ms": fine_ms_sum / len(roof_cams),
                     "kernel_share_of_step": float(np.mean(shares)),
-                    "kernel_source_hash": src_hash, "source_commit": git_head(),
+                    "kernel_source_hash": src_hash, "kernel_sass_hash": sass_hash, "source_commit": git_head(),
                     "ncu_capture": {"fresh": fresh, "capture_kernel_source_hash": traffic.get("kernel_source_hash"),
+                                    "capture_kernel_sass_hash": traffic.get("kernel_sass_hash"),
                                     "capture_commit": traffic.get("commit"), "source": traffic.get("source")},
                     "note": "instruction-issue bound pointer chasing with SIMT divergence, not HBM-bound: node "
                             "fetches hit L1/L2 (see profiles/ and DESIGN.md section 4)"}
@@ -707,7 +715,7 @@ def run_own(args):
                     "note": "fraction of the SMs' issue slots (148 SMs x 4 schedulers x elapsed cycles of the ncu capture) "
                             "that issued an instruction of this kernel: the limit this pass actually runs against"}
         else:
-            roofline["ncu_capture"]["note"] = ("profiles/traffic.json was captured from other kernel sources (or is absent): "
+            roofline["ncu_capture"]["note"] = ("profiles/traffic.json was captured from other kernel code (or is absent): "
                                                "traffic / ncu counters are withheld rather than reported stale")
         fb.free()
 

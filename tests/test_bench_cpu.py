@@ -38,3 +38,20 @@ def test_own_arm_refuses_without_a_gpu(pysvo):
     out = subprocess.run([sys.executable, "bench.py", "--steps", "1", "--warmup", "1"], capture_output=True, text=True,
                          cwd=str(ROOT), timeout=300)
     assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
+
+
+def test_committed_ncu_capture_matches_the_built_kernel(pysvo):
+    """profiles/traffic.json is quoted by bench.py (roofline.traffic and the ncu counters) only while the fine-pass kernel's
+    SASS in the library being run hashes to the value stamped into the entry when the capture was filed. This keeps the
+    committed entry and the built library in step: a change of the kernel's machine code fails here until the capture is
+    retaken (tools/gpu_session.sh ncu) or the entry removed."""
+    import shutil
+    from tools.ncu_summary import kernel_sass_hash
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    entry = json.loads((ROOT / "profiles" / "traffic.json").read_text())["c3_ico8192_4k"]
+    built = kernel_sass_hash(pysvo.LIB_PATH)
+    assert built is not None and len(built) == 16
+    assert entry["kernel_sass_hash"] == built
+    assert entry["dram_bytes_per_launch"] > 1e8 and entry["warp_instructions"] > 1e8     # bytes and counts, not scaled units
+    assert kernel_sass_hash(pysvo.LIB_PATH, pattern="noSuchKernel") is None

@@ -42,6 +42,25 @@ WANT = [
 WANT_SUBSTRINGS = ("nvlrx", "nvltx", "nvlink", "aperture_peer", "aperture_sysmem", "pcie")
 
 
+def kernel_sass_hash(binary, pattern="finePassKernelILb1EjE"):
+    """sha256 (16 hex digits) over the SASS of one kernel inside a cubin-carrying file (the library, an object file):
+    ties an ncu capture to the MACHINE CODE it profiled -- edits elsewhere in the source files do not change it, any change
+    of the kernel's code does. None when cuobjdump is unavailable or the kernel is not found."""
+    import hashlib
+    import re
+    try:
+        out = subprocess.run(["cuobjdump", "-sass", str(binary)], capture_output=True, text=True, timeout=300).stdout
+    except Exception:  # noqa: BLE001
+        return None
+    keep, lines = False, []
+    for ln in out.splitlines():
+        if "Function :" in ln:
+            keep = pattern in ln
+        elif keep and re.match(r"\s+/\*[0-9a-f]{4}\*/", ln):
+            lines.append(re.sub(r"/\* 0x[0-9a-f]* \*/", "", ln).rstrip())
+    return hashlib.sha256("\n".join(lines).encode()).hexdigest()[:16] if lines else None
+
+
 def summarise(path):
     raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
@@ -94,6 +113,7 @@ if __name__ == "__main__":
         entry = {
             "source": f"{sys.argv[1]} (ncu --set full --clock-control none, one launch)", "kernel": d["kernel"][:80],
             "kernel_source_hash": h.hexdigest()[:16], "commit": commit or None,
+            "kernel_sass_hash": kernel_sass_hash(root / "sparse-voxel-octrees_b200" / "libsvo_b200.so"),
             "dram_bytes_per_launch": (gb("dram__bytes_read.sum") or 0) + (gb("dram__bytes_write.sum") or 0),
             "dram_bytes_read": gb("dram__bytes_read.sum"), "dram_bytes_write": gb("dram__bytes_write.sum"),
             "l1_hit_pct": g("l1tex__t_sector_hit_rate.pct"), "l2_hit_pct": g("lts__t_sector_hit_rate.pct"),
