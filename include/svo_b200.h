@@ -376,7 +376,10 @@ SVO_API int svo_frame_tile_owner(int width, int height, int strips, int tile, in
  * environment variable SVO_TILE_RUN sets the initial value; run <= 0 restores the default). Process-wide, to be
  * called by every rank with the same value while no frame is in flight. The image does not depend on it. Wider
  * stripes make each rank's rows of pixels longer -- what svo_frame_copy_owned_tiles moves per PCIe write burst:
- * measured on B200, 128-byte runs (the default) reach 28 GB/s into mapped host memory, whole rows 50 GB/s. */
+ * measured on B200, 128-byte runs (the default) reach 28 GB/s into mapped host memory, whole rows 50 GB/s.
+ * Read once per call of the single-device entry points that take tile_rank / tile_world (one-process-per-GPU callers);
+ * the multi-GPU handle (svo_multi_*) neither reads nor changes it: every sequence carries its own stripe width
+ * (svo_sequence_stats.tile_run). */
 SVO_API int svo_frame_set_tile_run(int run);
 
 /* Host-buffer variant: rgba (width*height uint32, the reference's backBuffer

@@ -444,10 +444,11 @@ bool prefixRestartEnabled() {
 // Enqueues one frame. The beam pass goes to the tree's high-priority internal stream (unless the
 // caller wants the depth buffer in its own memory, which must be ordered on `stream`), the tile
 // classifier and the fine pass to `stream`. Returns the double-buffer slot used. Caller holds
-// tree->mutex and has made the device current.
+// tree->mutex and has made the device current. `share` is this call's part of the frame (desc's tile_rank /
+// tile_world plus the stripe width, which the descriptor does not carry).
 int enqueueFrame(svo_tree *tree, FramePlan *plan, const svo_camera *cam, const svo_frame_desc *desc,
-                 uint32_t *dRgba, float *userDepth, cudaStream_t stream, bool wantStats, uint32_t *launches,
-                 int *slotOut) {
+                 const svo::TileShare &share, uint32_t *dRgba, float *userDepth, cudaStream_t stream, bool wantStats,
+                 uint32_t *launches, int *slotOut) {
     svo_frame_constants c;
     svo::frameConstants(*cam, tree->center, desc->width, desc->height, desc->strips, c);
     svo::FrameConsts f = toDeviceConsts(c);
@@ -477,8 +478,7 @@ int enqueueFrame(svo_tree *tree, FramePlan *plan, const svo_camera *cam, const s
     // (also with a caller-owned depth buffer: only the depths are the caller's, the counters and the tile list are not)
     if (plan->fineRecorded[b]) SVO_CUDA(cudaStreamWaitEvent(cs, plan->fineDone[b], 0));
     if (wantStats) SVO_CUDA(cudaEventRecord(plan->timing[b][0], cs));
-    SVO_CUDA(svo::launchCoarsePass(tree->dev(), plan->dev, f, desc->flavour, depth, plan->dCounters[b], desc->tile_rank,
-                                   desc->tile_world, cs));
+    SVO_CUDA(svo::launchCoarsePass(tree->dev(), plan->dev, f, desc->flavour, depth, plan->dCounters[b], share, cs));
     ++n;
     if (wantStats) SVO_CUDA(cudaEventRecord(plan->timing[b][1], cs));
     if (!userDepth) {
@@ -491,13 +491,13 @@ int enqueueFrame(svo_tree *tree, FramePlan *plan, const svo_camera *cam, const s
         SVO_CUDA(cudaStreamWaitEvent(ps, plan->laneReady[b], 0));
     }
     if (wantStats && !split) SVO_CUDA(cudaEventRecord(plan->timing[b][2], stream));
-    SVO_CUDA(svo::launchClassifyTiles(plan->dev, f, depth, dRgba, desc->tile_rank, desc->tile_world, desc->pixel_stride,
+    SVO_CUDA(svo::launchClassifyTiles(plan->dev, f, depth, dRgba, share, desc->pixel_stride,
                                       plan->dTiles[b], plan->dCounters[b], plan->dFineTotal, ps));
     ++n;
     uint32_t *prefix = prefixRestartEnabled() && svo::finePassUsesPrefix(tree->dev(), desc->flavour, desc->pixel_stride) ? plan->dPrefix[b] : nullptr;
     if (prefix) {
         SVO_CUDA(svo::launchTilePrefix(tree->dev(), plan->dev, f, desc->flavour, plan->dTiles[b], plan->dCounters[b],
-                                       desc->tile_rank, desc->tile_world, desc->pixel_stride, prefix, ps));
+                                       share, desc->pixel_stride, prefix, ps));
         ++n;
     }
     if (split) {
@@ -506,7 +506,7 @@ int enqueueFrame(svo_tree *tree, FramePlan *plan, const svo_camera *cam, const s
         if (wantStats) SVO_CUDA(cudaEventRecord(plan->timing[b][2], stream));
     }
     SVO_CUDA(svo::launchFinePass(tree->dev(), plan->dev, f, desc->flavour, plan->dTiles[b], plan->dCounters[b], dRgba,
-                                 desc->tile_rank, desc->tile_world, desc->pixel_stride, prefix, stream));
+                                 share, desc->pixel_stride, prefix, stream));
     ++n;
     if (wantStats) {
         SVO_CUDA(cudaEventRecord(plan->timing[b][3], stream));
@@ -521,11 +521,10 @@ int enqueueFrame(svo_tree *tree, FramePlan *plan, const svo_camera *cam, const s
 }
 
 // Valid once the frame's stream work has completed (caller synchronised).
-void fillStats(const FramePlan *plan, int slot, const svo_frame_desc *desc, uint32_t launches, svo_frame_stats *stats) {
+void fillStats(const FramePlan *plan, int slot, const svo::TileShare &share, uint32_t launches, svo_frame_stats *stats) {
     const svo::FramePlanDev &p = plan->dev;
-    const int world = desc->tile_world, rank = desc->tile_rank;
+    const int world = share.world, rank = share.rank, run = share.run;
     // corner columns this rank traces: those on either side of its tile-column runs
-    const int run = svo::tileRunLength(world);
     int cols = 0;
     for (int cx = 0; cx < p.tilesX; ++cx) {
         bool right = cx < p.tileCols && (cx/run) % world == rank;        // tile column to the right of the corner
@@ -536,7 +535,7 @@ void fillStats(const FramePlan *plan, int slot, const svo_frame_desc *desc, uint
     stats->coarse_rays = uint64_t(cols)*uint64_t(cornerRows);
     stats->fine_rays = plan->hCounters[slot].fineRays;
     stats->tiles_rendered = plan->hCounters[slot].tilesRendered;
-    stats->tiles_total = uint64_t(svo::ownedTileColumns(p.tileCols, rank, world))*uint64_t(p.totalTileRows);
+    stats->tiles_total = uint64_t(svo::ownedTileColumns(p.tileCols, share))*uint64_t(p.totalTileRows);
     stats->kernel_launches = launches;
     stats->reserved = 0;
     stats->coarse_ms = stats->fine_ms = 0.0f;
@@ -549,12 +548,10 @@ void fillStats(const FramePlan *plan, int slot, const svo_frame_desc *desc, uint
 namespace svo_detail {   // what svo_multi.cu uses of the above
 int checkDesc(const svo_frame_desc *desc) { return ::checkDesc(desc); }
 int getPlan(svo_tree *tree, int width, int height, int strips, FramePlan **out) { return ::getPlan(tree, width, height, strips, out); }
-int enqueueFrame(svo_tree *tree, FramePlan *plan, const svo_camera *cam, const svo_frame_desc *desc, uint32_t *dRgba,
-                 float *userDepth, cudaStream_t stream, bool wantStats, uint32_t *launches, int *slotOut) {
-    return ::enqueueFrame(tree, plan, cam, desc, dRgba, userDepth, stream, wantStats, launches, slotOut);
-}
-void fillStats(const FramePlan *plan, int slot, const svo_frame_desc *desc, uint32_t launches, svo_frame_stats *stats) {
-    ::fillStats(plan, slot, desc, launches, stats);
+int enqueueFrame(svo_tree *tree, FramePlan *plan, const svo_camera *cam, const svo_frame_desc *desc,
+                 const svo::TileShare &share, uint32_t *dRgba, float *userDepth, cudaStream_t stream, bool wantStats,
+                 uint32_t *launches, int *slotOut) {
+    return ::enqueueFrame(tree, plan, cam, desc, share, dRgba, userDepth, stream, wantStats, launches, slotOut);
 }
 void planGeometry(int width, int height, int strips, svo::FramePlanDev &p) { ::planGeometry(width, height, strips, p); }
 int createTreeOnDevice(const uint32_t *words, uint64_t nWords, const float center[3], int device, bool validate, svo_tree **out) {
@@ -1171,12 +1168,12 @@ int svo_frame_tile_owner(int width, int height, int strips, int tile, int tile_w
         fail(SVO_ERR_INVALID_ARGUMENT, "tile %d out of range [0, %d)", tile, p.totalTiles);
         return -1;
     }
-    return ((tile % p.tileCols)/svo::tileRunLength(tile_world)) % tile_world;
+    return ((tile % p.tileCols)/svo::tileShare(0, tile_world).run) % tile_world;
 }
 
 int svo_frame_set_tile_run(int run) {
     if (run > 4096) return fail(SVO_ERR_INVALID_ARGUMENT, "tile run %d is out of range", run);
-    svo::setTileRunLength(run);
+    svo::setDefaultTileRun(run);
     return SVO_OK;
 }
 
@@ -1207,7 +1204,6 @@ int svo_render_frame_device(svo_tree *tree, const svo_camera *cam, const svo_fra
     int st = checkDesc(desc);
     if (st != SVO_OK) return st;
     if (desc->pixel_format != SVO_PIXELS_RGBA8) return fail(SVO_ERR_UNSUPPORTED, "svo_render_frame_device writes SVO_PIXELS_RGBA8 only");
-    if (desc->pixel_format != SVO_PIXELS_RGBA8) return fail(SVO_ERR_UNSUPPORTED, "svo_render_frame_device writes SVO_PIXELS_RGBA8 only");
     SVO_DEVICE(tree->device);
     std::lock_guard<std::mutex> lock(tree->mutex);
     FramePlan *plan = nullptr;
@@ -1216,10 +1212,11 @@ int svo_render_frame_device(svo_tree *tree, const svo_camera *cam, const svo_fra
     bool wantStats = stats && sync_stats;
     uint32_t launches = 0;
     int slot = 0;
-    if ((st = enqueueFrame(tree, plan, cam, desc, d_rgba, d_depth, s, wantStats, &launches, &slot)) != SVO_OK) return st;
+    const svo::TileShare share = svo::tileShare(desc->tile_rank, desc->tile_world);
+    if ((st = enqueueFrame(tree, plan, cam, desc, share, d_rgba, d_depth, s, wantStats, &launches, &slot)) != SVO_OK) return st;
     if (wantStats) {
         SVO_CUDA(cudaStreamSynchronize(s));
-        fillStats(plan, slot, desc, launches, stats);
+        fillStats(plan, slot, share, launches, stats);
     }
     return SVO_OK;
 }
@@ -1231,8 +1228,8 @@ int svo_frame_copy_owned_tiles(int device, const svo_frame_desc *desc, const uin
     SVO_DEVICE(device);
     svo::FramePlanDev p{};
     planGeometry(desc->width, desc->height, desc->strips, p);
-    SVO_CUDA(svo::launchCopyOwnedColumns(p, desc->width, desc->height, d_src, d_dst, desc->tile_rank, desc->tile_world,
-                                         static_cast<cudaStream_t>(stream)));
+    SVO_CUDA(svo::launchCopyOwnedColumns(p, desc->width, desc->height, d_src, d_dst,
+                                         svo::tileShare(desc->tile_rank, desc->tile_world), static_cast<cudaStream_t>(stream)));
     return SVO_OK;
 }
 
@@ -1261,7 +1258,8 @@ int svo_render_frame_async(svo_tree *tree, const svo_camera *cam, const svo_fram
     if (plan->copyRecorded[b]) SVO_CUDA(cudaStreamWaitEvent(s, plan->copyDone[b], 0));
     uint32_t launches = 0;
     int slot = 0;
-    if ((st = enqueueFrame(tree, plan, cam, desc, plan->dRgba[b], nullptr, s, want_stats != 0, &launches, &slot)) != SVO_OK) return st;
+    const svo::TileShare share = svo::tileShare(desc->tile_rank, desc->tile_world);
+    if ((st = enqueueFrame(tree, plan, cam, desc, share, plan->dRgba[b], nullptr, s, want_stats != 0, &launches, &slot)) != SVO_OK) return st;
     // copies run on their own stream so that the next frame's kernels are not queued behind them
     SVO_CUDA(cudaStreamWaitEvent(tree->copyStream, plan->fineDone[slot], 0));
     SVO_CUDA(cudaMemcpyAsync(rgba, plan->dRgba[b], frameBytes, cudaMemcpyDeviceToHost, tree->copyStream));
@@ -1275,7 +1273,7 @@ int svo_render_frame_async(svo_tree *tree, const svo_camera *cam, const svo_fram
     plan->pendingStats[b] = want_stats != 0;
     plan->pendingRing[b] = slot;
     plan->pendingLaunches[b] = launches;
-    plan->pendingDesc[b] = *desc;
+    plan->pendingShare[b] = share;
     *ticket = b;
     return SVO_OK;
 }
@@ -1294,7 +1292,7 @@ int svo_frame_wait(svo_tree *tree, const svo_frame_desc *desc, int ticket, svo_f
     if (stats) {
         if (!plan->pendingStats[ticket])
             return fail(SVO_ERR_INVALID_ARGUMENT, "svo_frame_wait: statistics were not requested for this frame");
-        fillStats(plan, plan->pendingRing[ticket], &plan->pendingDesc[ticket], plan->pendingLaunches[ticket], stats);
+        fillStats(plan, plan->pendingRing[ticket], plan->pendingShare[ticket], plan->pendingLaunches[ticket], stats);
     }
     return SVO_OK;
 }

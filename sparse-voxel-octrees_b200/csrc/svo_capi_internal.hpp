@@ -93,7 +93,7 @@ struct FramePlan {
     bool pendingStats[kHostLanes] = {};
     int pendingRing[kHostLanes] = {};
     uint32_t pendingLaunches[kHostLanes] = {};
-    svo_frame_desc pendingDesc[kHostLanes] = {};
+    svo::TileShare pendingShare[kHostLanes] = {};      // the frame's part of the image, as it was enqueued
     uint64_t hostFrameNumber = 0;
 
     void destroy() {
@@ -168,9 +168,8 @@ namespace svo_detail {
 int checkDesc(const svo_frame_desc *desc);
 int getPlan(svo_tree *tree, int width, int height, int strips, FramePlan **out);
 int enqueueFrame(svo_tree *tree, FramePlan *plan, const svo_camera *cam, const svo_frame_desc *desc,
-                 uint32_t *dRgba, float *userDepth, cudaStream_t stream, bool wantStats, uint32_t *launches,
-                 int *slotOut);
-void fillStats(const FramePlan *plan, int slot, const svo_frame_desc *desc, uint32_t launches, svo_frame_stats *stats);
+                 const svo::TileShare &share, uint32_t *dRgba, float *userDepth, cudaStream_t stream, bool wantStats,
+                 uint32_t *launches, int *slotOut);
 void planGeometry(int width, int height, int strips, svo::FramePlanDev &p);
 // Replica of a node array on `device`; validate == false skips the host-side walk (the caller has done it once).
 int createTreeOnDevice(const uint32_t *words, uint64_t nWords, const float center[3], int device, bool validate, svo_tree **out);

@@ -495,25 +495,29 @@ std::atomic<int> &tileRunSetting() {
 }
 } // namespace
 
-int tileRunLength(int tileWorld) { return tileWorld > 1 ? tileRunSetting().load(std::memory_order_relaxed) : 1; }
+int defaultTileRun() { return tileRunSetting().load(std::memory_order_relaxed); }
 
-void setTileRunLength(int run) { tileRunSetting().store(run > 0 ? run : 4, std::memory_order_relaxed); }
+void setDefaultTileRun(int run) { tileRunSetting().store(run > 0 ? run : 4, std::memory_order_relaxed); }
 
-int ownedTileColumns(int tileCols, int tileRank, int tileWorld) {
-    int run = tileRunLength(tileWorld), n = 0;
-    for (int start = tileRank*run; start < tileCols; start += tileWorld*run)
-        n += (start + run <= tileCols) ? run : tileCols - start;
+TileShare tileShare(int tileRank, int tileWorld, int run) {
+    TileShare share;
+    share.rank = tileRank;
+    share.world = tileWorld;
+    share.run = tileWorld > 1 ? (run > 0 ? run : defaultTileRun()) : 1;
+    return share;
+}
+
+int ownedTileColumns(int tileCols, const TileShare &share) {
+    int n = 0;
+    for (int start = share.rank*share.run; start < tileCols; start += share.world*share.run)
+        n += (start + share.run <= tileCols) ? share.run : tileCols - start;
     return n;
 }
 
 namespace {
 
-inline int ownedCols(const FramePlanDev &plan, int tileRank, int tileWorld) {
-    return ownedTileColumns(plan.tileCols, tileRank, tileWorld);
-}
-inline int ownedTiles(const FramePlanDev &plan, int tileRank, int tileWorld) {
-    return ownedCols(plan, tileRank, tileWorld)*plan.totalTileRows;
-}
+inline int ownedCols(const FramePlanDev &plan, const TileShare &share) { return ownedTileColumns(plan.tileCols, share); }
+inline int ownedTiles(const FramePlanDev &plan, const TileShare &share) { return ownedCols(plan, share)*plan.totalTileRows; }
 
 template <bool FAST, bool LOD, typename IdxT>
 cudaError_t launchBatchT(const TreeDev &tree, uint64_t n, const float *o, const float *d, float rayScale,
@@ -537,15 +541,14 @@ cudaError_t launchBatchRefillT(const TreeDev &tree, uint64_t n, const float *o, 
     auto kernel = raymarchBatchRefillKernel<FAST, LOD, IdxT>;
     cudaError_t e = ensureSmem(kernel, smem);
     if (e != cudaSuccess) return e;
-    // persistent grid: as many blocks as fit the device at once (one wave), never more than the rays need
-    static int residentBlocks = 0;
-    if (residentBlocks == 0) {
-        int device = 0, sms = 0, perSm = 0;
-        cudaGetDevice(&device);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, kBatchThreads, smem);
-        residentBlocks = sms*(perSm > 0 ? perSm : 1);
-    }
+    // persistent grid: as many blocks as fit the device at once (one wave), never more than the rays need. Asked for on
+    // every call (microseconds): the answer depends on the current device and, through the stack, on the tree's depth, and
+    // svo_multi_raymarch_batch launches from one thread per device.
+    int device = 0, sms = 0, perSm = 0;
+    if ((e = cudaGetDevice(&device)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, kBatchThreads, smem)) != cudaSuccess) return e;
+    const int residentBlocks = (sms > 0 ? sms : 1)*(perSm > 0 ? perSm : 1);
     uint64_t blocks = (n + kBatchThreads - 1)/kBatchThreads;
     if (blocks > uint64_t(residentBlocks)) blocks = uint64_t(residentBlocks);
     if ((e = cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), stream)) != cudaSuccess) return e;
@@ -560,13 +563,13 @@ cudaError_t launchBatchRefillT(const TreeDev &tree, uint64_t n, const float *o, 
 
 template <typename IdxT>
 cudaError_t launchCoarseT(const TreeDev &tree, const FramePlanDev &plan, const FrameConsts &consts, float *depth,
-                          FrameCounters *counters, int tileRank, int tileWorld, cudaStream_t stream) {
+                          FrameCounters *counters, const TileShare &share, cudaStream_t stream) {
+    const int tileRank = share.rank, tileWorld = share.world, run = share.run;
     size_t smem = SmemStack<IdxT, kCoarseThreads, true>::bytes(stackSlots(tree));
     auto kernel = coarsePassKernel<IdxT>;
     cudaError_t e = ensureSmem(kernel, smem);
     if (e != cudaSuccess) return e;
     // a rank needs the corner columns on both sides of each of its runs: run + 1 per run
-    int run = tileRunLength(tileWorld);
     int runsOwned = (plan.tileCols + tileWorld*run - 1)/(tileWorld*run);
     int colSlots = tileWorld == 1 ? plan.tilesX : runsOwned*(run + 1);
     int groupsPerStrip = ((colSlots + 7)/8)*((plan.tilesYFull + 3)/4);      // 8 x 4 corners per warp
@@ -769,33 +772,32 @@ cudaError_t launchShadeBatch(uint64_t n, const uint8_t *hit, const uint32_t *nor
 }
 
 cudaError_t launchCoarsePass(const TreeDev &tree, const FramePlanDev &plan, const FrameConsts &consts, int flavour,
-                             float *depth, FrameCounters *counters, int tileRank, int tileWorld,
-                             cudaStream_t stream) {
+                             float *depth, FrameCounters *counters, const TileShare &share, cudaStream_t stream) {
     // The beam pass is individually rounded in BOTH flavours: its depths feed
     // `minT - 0.03` (Main.cpp:197) and the tile-skip test (Main.cpp:191), so a
     // last-bit change here moves every ray origin of a tile or drops / adds a
     // whole tile. It is < 5 % of the rays; FAST only changes the fine pass.
     (void)flavour;
     bool wide = wideIndex(tree);
-    return wide ? launchCoarseT<uint64_t>(tree, plan, consts, depth, counters, tileRank, tileWorld, stream)
-                : launchCoarseT<uint32_t>(tree, plan, consts, depth, counters, tileRank, tileWorld, stream);
+    return wide ? launchCoarseT<uint64_t>(tree, plan, consts, depth, counters, share, stream)
+                : launchCoarseT<uint32_t>(tree, plan, consts, depth, counters, share, stream);
 }
 
 cudaError_t launchClassifyTiles(const FramePlanDev &plan, const FrameConsts &consts, const float *depth,
-                                uint32_t *rgba, int tileRank, int tileWorld, int pixelStride, TileRecord *tiles,
+                                uint32_t *rgba, const TileShare &share, int pixelStride, TileRecord *tiles,
                                 FrameCounters *counters, unsigned long long *fineRaysTotal, cudaStream_t stream) {
-    int owned = ownedTiles(plan, tileRank, tileWorld);
+    int owned = ownedTiles(plan, share);
     if (owned <= 0) return cudaSuccess;
     classifyTilesKernel<<<(owned + kClassifyThreads - 1)/kClassifyThreads, kClassifyThreads, 0, stream>>>(
-        plan, consts.beamBias, depth, rgba, tileRank, tileWorld, tileRunLength(tileWorld),
-        ownedCols(plan, tileRank, tileWorld), owned, pixelStride > 1 ? pixelStride : 1, tiles, counters, fineRaysTotal);
+        plan, consts.beamBias, depth, rgba, share.rank, share.world, share.run,
+        ownedCols(plan, share), owned, pixelStride > 1 ? pixelStride : 1, tiles, counters, fineRaysTotal);
     return cudaGetLastError();
 }
 
 cudaError_t launchFinePass(const TreeDev &tree, const FramePlanDev &plan, const FrameConsts &consts, int flavour,
                            const TileRecord *tiles, const FrameCounters *counters, uint32_t *rgba,
-                           int tileRank, int tileWorld, int pixelStride, uint32_t *prefix, cudaStream_t stream) {
-    int owned = ownedTiles(plan, tileRank, tileWorld);
+                           const TileShare &share, int pixelStride, uint32_t *prefix, cudaStream_t stream) {
+    int owned = ownedTiles(plan, share);
     if (owned <= 0) return cudaSuccess;
     bool wide = wideIndex(tree);
     if (flavour != 0)
@@ -808,9 +810,9 @@ cudaError_t launchFinePass(const TreeDev &tree, const FramePlanDev &plan, const 
 // K2c: the tile's shared traversal prefix, four corner rays per tile in lock step; a no-op (returns 0 launches) when
 // launchFinePass would not use the records.
 cudaError_t launchTilePrefix(const TreeDev &tree, const FramePlanDev &plan, const FrameConsts &consts, int flavour,
-                             const TileRecord *tiles, const FrameCounters *counters, int tileRank, int tileWorld,
+                             const TileRecord *tiles, const FrameCounters *counters, const TileShare &share,
                              int pixelStride, uint32_t *prefix, cudaStream_t stream) {
-    const int owned = ownedTiles(plan, tileRank, tileWorld);
+    const int owned = ownedTiles(plan, share);
     if (owned <= 0 || !prefix || !finePassUsesPrefix(tree, flavour, pixelStride)) return cudaSuccess;
     const size_t psmem = SmemStack<uint32_t, kPrefixThreads, false>::bytes(stackSlots(tree));
     cudaError_t e = ensureSmem(tilePrefixKernel, psmem);
@@ -900,29 +902,28 @@ packGrey8a8Vec4Kernel(const uint32_t *__restrict__ src, uint16_t *__restrict__ d
 }
 
 cudaError_t launchPackGrey8a8(const FramePlanDev &plan, int width, int height, const uint32_t *src, uint16_t *dst,
-                              int tileRank, int tileWorld, cudaStream_t stream) {
-    const int cols = ownedCols(plan, tileRank, tileWorld);
+                              const TileShare &share, cudaStream_t stream) {
+    const int cols = ownedCols(plan, share);
     if (cols <= 0) return cudaSuccess;
     const bool aligned = (width & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0;
     if (aligned) {
         const int quads = cols*2;
         dim3 grid(unsigned((quads + 255)/256), unsigned(height));
-        packGrey8a8Vec4Kernel<<<grid, 256, 0, stream>>>(src, dst, width, height, quads, tileRunLength(tileWorld), tileRank, tileWorld);
+        packGrey8a8Vec4Kernel<<<grid, 256, 0, stream>>>(src, dst, width, height, quads, share.run, share.rank, share.world);
     } else {
         const int ownedPixels = cols*8;
         dim3 grid(unsigned((ownedPixels + 255)/256), unsigned(height));
-        packGrey8a8Kernel<<<grid, 256, 0, stream>>>(src, dst, width, height, ownedPixels, tileRunLength(tileWorld), tileRank, tileWorld);
+        packGrey8a8Kernel<<<grid, 256, 0, stream>>>(src, dst, width, height, ownedPixels, share.run, share.rank, share.world);
     }
     return cudaGetLastError();
 }
 
 cudaError_t launchCopyOwnedColumns(const FramePlanDev &plan, int width, int height, const uint32_t *src, uint32_t *dst,
-                                   int tileRank, int tileWorld, cudaStream_t stream) {
-    const int ownedPixels = ownedCols(plan, tileRank, tileWorld)*8;
+                                   const TileShare &share, cudaStream_t stream) {
+    const int ownedPixels = ownedCols(plan, share)*8;
     if (ownedPixels <= 0) return cudaSuccess;
     dim3 grid(unsigned((ownedPixels + 255)/256), unsigned(height));
-    copyOwnedColumnsKernel<<<grid, 256, 0, stream>>>(src, dst, width, height, ownedPixels, tileRunLength(tileWorld),
-                                                     tileRank, tileWorld);
+    copyOwnedColumnsKernel<<<grid, 256, 0, stream>>>(src, dst, width, height, ownedPixels, share.run, share.rank, share.world);
     return cudaGetLastError();
 }
 

@@ -67,21 +67,27 @@ cudaError_t buildCoherenceOrder(uint64_t n, const float *d, void *workspace, con
 cudaError_t launchShadeBatch(uint64_t n, const uint8_t *hit, const uint32_t *normal, const float *d, const float light[3],
                              uint32_t *rgba, cudaStream_t stream);
 
-// Multi-GPU tile interleave: tile column tx belongs to rank (tx / run) % world.
-int tileRunLength(int tileWorld);
-void setTileRunLength(int run);      // process-wide; <= 0 restores the default of four
-int ownedTileColumns(int tileCols, int tileRank, int tileWorld);
+// Multi-GPU tile interleave: tile column tx belongs to rank (tx / run) % world -- vertical stripes `run` tile columns
+// wide, dealt round-robin. One value per call: nothing process-wide is read while a frame is being enqueued.
+struct TileShare {
+    int rank = 0, world = 1, run = 1;
+};
+// The stripe width of callers that do not name one (svo_frame_desc has no field for it): SVO_TILE_RUN or
+// svo_frame_set_tile_run, else four. run <= 0: that default; world == 1: stripes do not exist (run 1).
+int defaultTileRun();
+void setDefaultTileRun(int run);     // <= 0 restores four
+TileShare tileShare(int tileRank, int tileWorld, int run = 0);
+int ownedTileColumns(int tileCols, const TileShare &share);
 
 // Beam pass; also zeroes `counters` for the classifier that follows on the same stream.
-// With tileWorld >= 3 only the corners next to this rank's tile columns are traced.
+// With share.world >= 3 only the corners next to this rank's tile columns are traced.
 cudaError_t launchCoarsePass(const TreeDev &tree, const FramePlanDev &plan, const FrameConsts &consts, int flavour,
-                             float *depth, FrameCounters *counters, int tileRank, int tileWorld,
-                             cudaStream_t stream);
+                             float *depth, FrameCounters *counters, const TileShare &share, cudaStream_t stream);
 
 // Per owned tile: min of the four corner depths; skipped tiles are zero-filled (the strip memset,
 // Main.cpp:165), rendered tiles are appended to `tiles` (capacity = owned tiles) and counted.
 cudaError_t launchClassifyTiles(const FramePlanDev &plan, const FrameConsts &consts, const float *depth,
-                                uint32_t *rgba, int tileRank, int tileWorld, int pixelStride, TileRecord *tiles,
+                                uint32_t *rgba, const TileShare &share, int pixelStride, TileRecord *tiles,
                                 FrameCounters *counters, unsigned long long *fineRaysTotal, cudaStream_t stream);
 
 // Fine pass over the tile list (grid covers the worst case; blocks past the list length exit).
@@ -89,11 +95,11 @@ cudaError_t launchClassifyTiles(const FramePlanDev &plan, const FrameConsts &con
 // prefix != nullptr (room for prefixRecordWords(tree) words per owned tile, filled by launchTilePrefix): in the FAST
 // flavour the rays of a tile start at the traversal state its four corner rays share instead of at the root.
 cudaError_t launchTilePrefix(const TreeDev &tree, const FramePlanDev &plan, const FrameConsts &consts, int flavour,
-                             const TileRecord *tiles, const FrameCounters *counters, int tileRank, int tileWorld,
+                             const TileRecord *tiles, const FrameCounters *counters, const TileShare &share,
                              int pixelStride, uint32_t *prefix, cudaStream_t stream);
 cudaError_t launchFinePass(const TreeDev &tree, const FramePlanDev &plan, const FrameConsts &consts, int flavour,
                            const TileRecord *tiles, const FrameCounters *counters, uint32_t *rgba,
-                           int tileRank, int tileWorld, int pixelStride, uint32_t *prefix, cudaStream_t stream);
+                           const TileShare &share, int pixelStride, uint32_t *prefix, cudaStream_t stream);
 int prefixRecordWords(const TreeDev &tree);
 int finePassUsesPrefix(const TreeDev &tree, int flavour, int pixelStride);
 
@@ -101,8 +107,8 @@ int finePassUsesPrefix(const TreeDev &tree, int flavour, int pixelStride);
 // device -> host leg of a multi-GPU frame when `dst` is mapped page-locked host memory.
 // The owned tile columns' pixels as (grey, alpha) byte pairs (SVO_PIXELS_GREY8A8), same pitch in pixels.
 cudaError_t launchPackGrey8a8(const FramePlanDev &plan, int width, int height, const uint32_t *src, uint16_t *dst,
-                              int tileRank, int tileWorld, cudaStream_t stream);
+                              const TileShare &share, cudaStream_t stream);
 cudaError_t launchCopyOwnedColumns(const FramePlanDev &plan, int width, int height, const uint32_t *src, uint32_t *dst,
-                                   int tileRank, int tileWorld, cudaStream_t stream);
+                                   const TileShare &share, cudaStream_t stream);
 
 } // namespace svo

@@ -44,6 +44,7 @@ struct Job {
     uint32_t *const *hostFrames = nullptr;
     int nHost = 0;
     int lanes = kDefaultLanes;
+    int tileRun = 1;                    // stripe width of this sequence, in tile columns (per job: handles do not share it)
 };
 
 struct Replica {
@@ -123,6 +124,7 @@ int runSequence(svo_multi *M, Replica &rep, const Job &job, uint64_t generation)
     svo_frame_desc desc = job.desc;
     desc.tile_rank = rep.index;
     desc.tile_world = N;
+    const svo::TileShare share = svo::tileShare(rep.index, N, job.tileRun);
     const size_t frameBytes = size_t(desc.width)*size_t(desc.height)*sizeof(uint32_t);
     FramePlan *plan = nullptr;
     {
@@ -189,7 +191,7 @@ int runSequence(svo_multi *M, Replica &rep, const Job &job, uint64_t generation)
         uint32_t launches = 0;
         {
             std::lock_guard<std::mutex> lock(tree->mutex);
-            int st = svo_detail::enqueueFrame(tree, plan, &job.cams[k], &desc, target, nullptr, s, false, &launches, nullptr);
+            int st = svo_detail::enqueueFrame(tree, plan, &job.cams[k], &desc, share, target, nullptr, s, false, &launches, nullptr);
             if (st != SVO_OK) return st;
         }
         rep.launches += launches;
@@ -208,12 +210,12 @@ int runSequence(svo_multi *M, Replica &rep, const Job &job, uint64_t generation)
                 // where the RGBA frame's 960-byte rows take 0.308.)
                 void *mapped = nullptr;
                 SVO_CUDA(cudaHostGetDevicePointer(&mapped, host, 0));
-                SVO_CUDA(svo::launchPackGrey8a8(plan->dev, desc.width, desc.height, rep.fb[l], static_cast<uint16_t *>(mapped), rep.index, N, rep.copy));
+                SVO_CUDA(svo::launchPackGrey8a8(plan->dev, desc.width, desc.height, rep.fb[l], static_cast<uint16_t *>(mapped), share, rep.copy));
                 ++rep.launches;
                 shipped = true;
             } else if (packed) {
                 // one device: packed on the GPU, then one contiguous copy on the copy engine
-                SVO_CUDA(svo::launchPackGrey8a8(plan->dev, desc.width, desc.height, rep.fb[l], rep.fb16[l], rep.index, N, rep.copy));
+                SVO_CUDA(svo::launchPackGrey8a8(plan->dev, desc.width, desc.height, rep.fb[l], rep.fb16[l], share, rep.copy));
                 ++rep.launches;
                 srcBytes = reinterpret_cast<const unsigned char *>(rep.fb16[l]);
             }
@@ -227,11 +229,11 @@ int runSequence(svo_multi *M, Replica &rep, const Job &job, uint64_t generation)
                 void *mapped = nullptr;
                 SVO_CUDA(cudaHostGetDevicePointer(&mapped, host, 0));
                 SVO_CUDA(svo::launchCopyOwnedColumns(plan->dev, desc.width, desc.height, rep.fb[l], static_cast<uint32_t *>(mapped),
-                                                     rep.index, N, rep.copy));
+                                                     share, rep.copy));
                 ++rep.launches;
             } else {
                 // this device's stripes only, one strided copy per stripe on the copy engine (no SM involved)
-                const int run = svo::tileRunLength(N);
+                const int run = share.run;
                 const size_t pitch = size_t(desc.width)*pixelBytes;
                 for (int tx0 = rep.index*run; tx0 < plan->dev.tileCols; tx0 += N*run) {
                     const int x0 = tx0*8, x1 = std::min((tx0 + run)*8, desc.width);
@@ -466,7 +468,7 @@ int svo_multi_render_sequence(svo_multi *M, const svo_camera *cams, int n_frames
     job.nHost = n_host_frames;
     job.lanes = output == SVO_OUTPUT_HOST ? std::min(lanesInFlight(), n_host_frames) : lanesInFlight();
     const int run = N > 1 ? (output == SVO_OUTPUT_HOST ? hostStripeRun(desc.width, N) : 4) : 1;
-    if (N > 1) svo::setTileRunLength(run);
+    job.tileRun = run;
 
     if (output == SVO_OUTPUT_DEVICE) {
         SVO_DEVICE(dev0);
@@ -565,7 +567,6 @@ int svo_multi_render_sequence(svo_multi *M, const svo_camera *cams, int n_frames
         std::unique_lock<std::mutex> lock(M->m);
         M->cvDone.wait(lock, [&] { return M->finished == N; });
     }
-    if (N > 1) svo::setTileRunLength(0);
     for (auto &r : M->reps)
         if (r->status != SVO_OK) return fail(r->status, "device %d: %s", r->device, r->error.c_str());
     if (cudaErr != cudaSuccess) return failCuda(cudaErr, "frame barrier");

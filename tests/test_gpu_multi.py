@@ -75,6 +75,60 @@ def test_multi_frames_equal_single_device(pysvo, cams, single_frames):
         m.close()
 
 
+def test_two_handles_render_concurrently(pysvo, dragon_words, cams, single_frames):
+    """The stripe width belongs to the sequence, not to the process: a handle gathering frames in HBM (stripes of 4 tile
+    columns) and one shipping host frames (here 27 columns: svo_sequence_stats.tile_run) render at the same time from two
+    threads, and a caller-set default (svo_frame_set_tile_run) is neither read nor reset by them."""
+    import threading
+    W, H, S, want = single_frames
+    words, center = dragon_words
+    a = pysvo.MultiOctree(words=words, center=center, devices=(0, 0))
+    b = pysvo.MultiOctree(words=words, center=center, devices=(0, 0, 0))
+    ring = [pysvo.PinnedArray((H, W), np.uint32) for _ in range(3)]
+    errors, runs = [], {}
+    pysvo.frame_set_tile_run(7)
+    try:
+        def device_side():
+            try:
+                for _ in range(6):
+                    st = a.render_sequence(cams, W, H, strips=S, flavour=pysvo.FLAVOUR_VALIDATION, output=pysvo.OUTPUT_DEVICE)
+                    runs["device"] = st.tile_run
+                    for back in range(3):
+                        if not np.array_equal(a.device_frame(W, H, back), want[len(cams) - 1 - back]):
+                            errors.append(f"device frame {back} back differs")
+            except Exception as e:      # noqa: BLE001 -- reported by the main thread
+                errors.append(repr(e))
+
+        def host_side():
+            try:
+                for _ in range(6):
+                    seen = {}
+                    st = b.render_sequence(cams, W, H, strips=S, flavour=pysvo.FLAVOUR_VALIDATION, output=pysvo.OUTPUT_HOST,
+                                           host_frames=[r.array for r in ring],
+                                           on_frame=lambda k, arr: seen.__setitem__(k, arr.copy()))
+                    runs["host"] = st.tile_run
+                    for k in range(len(cams)):
+                        if not np.array_equal(seen[k], want[k]):
+                            errors.append(f"host frame {k} differs")
+            except Exception as e:      # noqa: BLE001
+                errors.append(repr(e))
+
+        threads = [threading.Thread(target=device_side), threading.Thread(target=host_side)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        assert not errors, errors[:5]
+        assert runs["device"] == 4 and runs["host"] == 27        # 81 tile columns over three devices
+        # the single-device interleave still follows the caller's setting
+        lay = pysvo.frame_layout(W, H, S)
+        assert [pysvo.tile_owner(W, H, S, t, 2) for t in (0, 6, 7, 13, 14)] == [0, 0, 1, 1, 0] and lay.tile_cols == 81
+    finally:
+        pysvo.frame_set_tile_run(0)
+        a.close()
+        b.close()
+
+
 def test_multi_batch_shards_rays(pysvo, port, dragon_words, cams):
     from oracle.pyoracle import pixel_rays
     words, center = dragon_words
