@@ -353,6 +353,9 @@ class Port:
         L.svo_oracle_free.argtypes = [C.c_void_p]
         L.svo_oracle_voxelize_ply.restype = C.POINTER(C.c_uint32)
         L.svo_oracle_voxelize_ply.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int * 3), C.POINTER(C.c_uint64)]
+        L.svo_oracle_block_list_aliases.restype = C.c_int64
+        L.svo_oracle_block_list_aliases.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64),
+                                                    C.POINTER(C.c_int * 3), C.POINTER(C.c_int * 3)]
         L.svo_oracle_ply_triangles.restype = C.POINTER(C.c_float)
         L.svo_oracle_ply_triangles.argtypes = [C.c_char_p, C.POINTER(C.c_uint64), _f32p, _f32p]
         L.svo_oracle_tree_to_volume.restype = None
@@ -452,6 +455,18 @@ class Port:
             return np.ctypeslib.as_array(ptr, shape=(d, h, w)).copy(), int(ntri.value)
         finally:
             self.lib.svo_oracle_free(ptr)
+
+    def block_list_aliases(self, path, resolution, block_edge, threads):
+        """PlyLoader's block lists for a cubic cache block of `block_edge` cells (0: one block) and a pool of `threads`:
+        -> (listings outside the sub-block grid -- flat indices that alias another block, PlyLoader.cpp:263 --,
+        rejected candidates outside it, (gridW, gridH, gridD), sub-blocks that exist per axis)."""
+        cand = C.c_uint64(0)
+        grid, real = (C.c_int * 3)(), (C.c_int * 3)()
+        n = self.lib.svo_oracle_block_list_aliases(str(path).encode(), int(resolution), int(block_edge), int(threads),
+                                                   C.byref(cand), C.byref(grid), C.byref(real))
+        if n < 0:
+            raise ValueError(f"svo_oracle_block_list_aliases: cannot read {path}")
+        return int(n), int(cand.value), tuple(grid), tuple(real)
 
     def ply_triangles(self, path):
         """-> (float32[n, 33], lower[3], upper[3]): PlyLoader's triangle list after its constructor."""

@@ -119,6 +119,10 @@ void svo_oracle_free(void *p);
  * result depends on). malloc'ed w*h*d volume (svo_oracle_free) or NULL. */
 uint32_t *svo_oracle_voxelize_ply(const char *plyPath, int sideLength, int threadCount, int dims[3], uint64_t *nTrianglesOut);
 /* PlyLoader's triangle list (33 floats each: pos[3][3], normal[3][3], color[3][3], lower[3], upper[3]). */
+/* (triangle, sub-block) listings that fall outside the reference's sub-block grid (aliased flat indices): see
+ * oracle/svo_oracle_ply.c. Block lists only; blockEdge 0 = one cache block. */
+int64_t svo_oracle_block_list_aliases(const char *plyPath, int sideLength, int blockEdge, int threadCount,
+                                      uint64_t *candidatesOut, int grid[3], int real[3]);
 float *svo_oracle_ply_triangles(const char *plyPath, uint64_t *nOut, float lower[3], float upper[3]);
 /* The filled voxels of a node array spanning side^3 voxels, written into vol (w*h*d, x fastest, pre-zeroed). */
 void svo_oracle_tree_to_volume(const uint32_t *octree, int side, uint32_t *vol, int w, int h, int d);

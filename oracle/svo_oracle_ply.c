@@ -307,6 +307,15 @@ static void pointToGrid(const Loader *L, const float *p, int *x, int *y, int *z)
 
 typedef void (*BlockFn)(Loader *, size_t idx, uint32_t tri, int pass);
 
+/* Sub-blocks a triangle was LISTED for whose (x, y, z) lies outside the sub-block grid: the flat index
+ * x + gridW*(y + gridH*z) then names a block of the next row / slice (the reference blends the triangle into that
+ * block as well) or, for z, lies past _blockOffsets. The GPU voxeliser does not mirror that aliasing
+ * (csrc/svo_voxelize.cu header); svo_oracle_block_list_aliases counts it so that tests can show it never happens:
+ * the loader rescales every mesh into [0, 1]^3, pointToGrid maps 1 to sideLength - 3 (:228-233 on top of :415), so
+ * (u + 1)/sub stays inside the grid of a volume of sideLength cells (:431-433); and a sub-block past the volume would
+ * start beyond 1, where triBoxOverlap rejects every triangle. */
+static uint64_t g_listedOutsideGrid = 0, g_candidatesOutsideGrid = 0;
+
 static void iterateOverlappingBlocks(Loader *L, uint32_t ti, BlockFn body, int pass) {   /* :235-277 */
     const Tri *t = &L->tris[ti];
     int lx, ly, lz, ux, uy, uz;
@@ -325,8 +334,14 @@ static void iterateOverlappingBlocks(Loader *L, uint32_t ti, BlockFn body, int p
             center[1] = (lgy + 0.5f)*hy;
             for (int y = lgy; y <= ugy; ++y, center[1] += hy) {
                 center[0] = (lgx + 0.5f)*hx;
-                for (int x = lgx; x <= ugx; ++x, center[0] += hx)
-                    if (triBoxOverlap(center, half, tv)) body(L, (size_t)(x + L->gridW*(y + L->gridH*z)), ti, pass);
+                for (int x = lgx; x <= ugx; ++x, center[0] += hx) {
+                    int outside = x >= L->gridW || y >= L->gridH || z >= L->gridD;
+                    if (outside && pass == 0) ++g_candidatesOutsideGrid;
+                    if (triBoxOverlap(center, half, tv)) {
+                        if (outside) { if (pass == 0) ++g_listedOutsideGrid; if (z >= L->gridD) continue; }
+                        body(L, (size_t)(x + L->gridW*(y + L->gridH*z)), ti, pass);
+                    }
+                }
             }
         }
     } else {
@@ -491,6 +506,44 @@ uint32_t *svo_oracle_voxelize_ply(const char *plyPath, int sideLength, int threa
     free(L.blockOffsets); free(L.blockLists); free(L.counts); free(tris);
     dims[0] = w; dims[1] = h; dims[2] = d;
     return data;
+}
+
+/* Block lists only (setupBlockProcessing, :407-440) for a cubic cache block of edge `blockEdge` (0: the power-of-two
+ * side, one block) and `threadCount` pool threads: -> number of (triangle, sub-block) listings outside the sub-block
+ * grid (see g_listedOutsideGrid); *candidatesOut: sub-blocks outside the grid that a triangle's index range reached
+ * and triBoxOverlap then rejected; grid[3]: gridW, gridH, gridD; real[3]: sub-blocks that exist per axis.
+ * < 0 when the file cannot be read. */
+int64_t svo_oracle_block_list_aliases(const char *plyPath, int sideLength, int blockEdge, int threadCount,
+                                      uint64_t *candidatesOut, int grid[3], int real[3]) {
+    Loader L;
+    memset(&L, 0, sizeof L);
+    size_t nTris = 0;
+    Tri *tris = loadPly(plyPath, &nTris, L.lower, L.upper);
+    if (!tris) return -1;
+    L.tris = tris; L.nTris = nTris;
+    float sizes[3];
+    for (int q = 0; q < 3; ++q) sizes[q] = (L.upper[q] - L.lower[q])*(float)(sideLength - 2);
+    int w = (int)sizes[0] + 2, h = (int)sizes[1] + 2, d = (int)sizes[2] + 2;
+    int side = 1;
+    while (side < w || side < h || side < d) side <<= 1;
+    if (blockEdge <= 0 || blockEdge > side) blockEdge = side;
+    g_listedOutsideGrid = g_candidatesOutsideGrid = 0;
+    /* setupBlockProcessing without the counts array (a block of 8192^3 bytes is not needed to list triangles) */
+    L.sideLength = sideLength - 2;
+    L.blockW = L.subW = L.blockH = L.subH = L.blockD = L.subD = blockEdge;
+    findBestBlockPartition(&L.subW, &L.subH, &L.subD, threadCount);
+    L.partW = L.blockW/L.subW; L.partH = L.blockH/L.subH; L.partD = L.blockD/L.subD;
+    L.numPartitions = L.partW*L.partH*L.partD;
+    L.volumeW = w; L.volumeH = h; L.volumeD = d;
+    L.gridW = L.partW*(L.volumeW + L.blockW - 1)/L.blockW;
+    L.gridH = L.partH*(L.volumeH + L.blockH - 1)/L.blockH;
+    L.gridD = L.partD*(L.volumeD + L.blockD - 1)/L.blockD;
+    buildBlockLists(&L);
+    free(L.blockOffsets); free(L.blockLists); free(tris);
+    if (candidatesOut) *candidatesOut = g_candidatesOutsideGrid;
+    if (grid) { grid[0] = L.gridW; grid[1] = L.gridH; grid[2] = L.gridD; }
+    if (real) { real[0] = (w + L.subW - 1)/L.subW; real[1] = (h + L.subH - 1)/L.subH; real[2] = (d + L.subD - 1)/L.subD; }
+    return (int64_t)g_listedOutsideGrid;
 }
 
 /* The triangle list PlyLoader holds after its constructor, 33 floats per triangle: pos[3][3], normal[3][3],

@@ -19,8 +19,11 @@
 // inside every cell; one thread per cell folds its run. The filled cells go straight into the octree
 // builder (svo_build.cu) as a sparse list. Nothing of the volume ever exists densely.
 //
-// Not mirrored: a triangle so large that its sub-block range wraps around the sub-block grid's flat
-// index (the reference then lists it twice for a sub-block and blends it twice).
+// Not mirrored: a triangle whose sub-block range reaches past the sub-block grid, so that the flat index
+// x + gridW*(y + gridH*z) names a block of the next row (the reference would blend it into that block as well).
+// It cannot happen for a mesh this loader or the reference's produced: positions are rescaled into [0, 1]^3 and
+// pointToGrid maps 1 to sideLength - 3; tests/test_oracle_pins.py::test_block_lists_never_alias_another_sub_block
+// counts such listings in the restatement of the reference's loop (zero for every mesh, block size and pool size).
 #include "svo_voxelize.cuh"
 
 #include <algorithm>

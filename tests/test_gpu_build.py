@@ -240,22 +240,8 @@ def _ico_ply(path, freq):
 
 
 def _lowpoly_ply(path):
-    """Nine triangles that are large at any resolution: a skewed, slightly rotated octahedron and one thin sliver across
-    the whole volume (binary little-endian, positions only: face normals come from the loader)."""
-    import struct
-    c, s_ = np.cos(0.3), np.sin(0.3)
-    rot = np.array([[c, -s_, 0.0], [s_, c, 0.0], [0.0, 0.0, 1.0]]) @ np.array([[1.0, 0.0, 0.0], [0.0, np.cos(0.2), -np.sin(0.2)], [0.0, np.sin(0.2), np.cos(0.2)]])
-    octa = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]], np.float64) * [1.0, 0.7, 0.85]
-    verts = np.vstack([octa @ rot.T, [[-0.9, -0.6, -0.8], [0.95, 0.62, 0.7], [0.9, 0.66, 0.74]]]).astype(np.float32)
-    faces = [(0, 2, 4), (2, 1, 4), (1, 3, 4), (3, 0, 4), (2, 0, 5), (1, 2, 5), (3, 1, 5), (0, 3, 5), (6, 7, 8)]
-    with open(path, "wb") as fp:
-        fp.write(("ply\nformat binary_little_endian 1.0\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z\n"
-                  "element face %d\nproperty list uchar int vertex_indices\nend_header\n" % (len(verts), len(faces))).encode())
-        for v in verts:
-            fp.write(struct.pack("<fff", *v))
-        for f in faces:
-            fp.write(struct.pack("<Biii", 3, *f))
-    return path
+    from ply_meshes import write_lowpoly
+    return write_lowpoly(path)
 
 
 def test_build_from_low_poly_ply_large_triangles(pysvo, ref, tmp_path):

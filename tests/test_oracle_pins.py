@@ -243,6 +243,31 @@ def test_voxeliser_port_equals_golden(port, tmp_path):
         assert np.array_equal(center, np.array(pin["center"], np.float32)), (name, res)
 
 
+def test_block_lists_never_alias_another_sub_block(port, tmp_path):
+    """The one reference behaviour the GPU voxeliser does not mirror (csrc/svo_voxelize.cu header): a triangle listed
+    for a sub-block whose x or y index lies outside the sub-block grid lands, through the flat index
+    x + gridW*(y + gridH*z) (PlyLoader.cpp:263), in a block of the next row as well. Counted in the restatement's
+    iterateOverlappingBlocks over the benchmark mesh, the container variants and nine triangles that span the whole
+    volume and touch its faces, for one and several cache blocks and pool sizes 1 .. 64: nothing is ever listed there,
+    and the index ranges never even reach past the grid -- the loader rescales every mesh into [0, 1]^3, pointToGrid
+    maps 1 to sideLength - 3 (the member _sideLength is already sideLength - 2, and pointToGrid subtracts 2 again,
+    PlyLoader.cpp:228-233, :415), and the grid covers the volume of sideLength cells."""
+    from ply_meshes import write_lowpoly, write_variants
+    meshes = [_ico_ply(tmp_path / "ico20.ply", 20), write_lowpoly(tmp_path / "lowpoly.ply")]
+    meshes += [p for name, p in write_variants(tmp_path) if name.startswith("le_")]
+    reached = 0
+    for ply in meshes:
+        for res, edges in ((48, (0, 16)), (64, (0, 32)), (200, (0, 64)), (256, (0, 128, 32)), (1000, (0, 256)),
+                           (2048, (0, 512)), (8192, (512,))):
+            for edge in edges:
+                for threads in (1, 2, 3, 16, 64):
+                    listed, candidates, grid, real = port.block_list_aliases(ply, res, edge, threads)
+                    assert listed == 0, (ply.name, res, edge, threads, grid, real)
+                    assert all(g >= r for g, r in zip(grid, real)), (grid, real)
+                    reached += candidates
+    assert reached == 0
+
+
 def test_voxeliser_port_equals_reference(port, ref, tmp_path):
     """PlyLoader + VoxelData(loader, res, mem) + VoxelOctree (reference src/Main.cpp:320-325): the volume the
     restatement voxelises must hold exactly the voxels of the tree the reference builds from the same PLY (same
