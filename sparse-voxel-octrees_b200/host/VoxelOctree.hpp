@@ -13,11 +13,13 @@
 //
 // When this header is included after the reference's math/Vec3.hpp and
 // IntTypes.hpp it uses their Vec3 / uint32; otherwise it supplies minimal
-// stand-ins. The builder constructor VoxelOctree(VoxelData*) becomes three
-// factories that build the same node array on the GPU from what VoxelData
-// wraps -- a raw .voxel file (VoxelData(path, mem), VoxelData.cpp:36-48), a
-// dense grid, or a list of filled voxels (what a voxeliser produces) -- and
-// adopt(words, count, center) still uploads an array built elsewhere unchanged.
+// stand-ins. The builder constructor VoxelOctree(VoxelData*) builds the same
+// node array on the GPU from the source the VoxelData stand-in names -- a raw
+// .voxel file (VoxelData(path, mem), VoxelData.cpp:36-48) or a mesh
+// (VoxelData(PlyLoader*, sideLength, mem), VoxelData.cpp:50-56); the factories
+// take the same sources directly, or a dense grid / a list of filled voxels
+// (what a voxeliser produces), and adopt(words, count, center) uploads an
+// array built elsewhere unchanged.
 //
 // Differences a caller can observe: failures throw std::runtime_error carrying
 // svo_last_error() instead of being ignored (the reference silently continues
